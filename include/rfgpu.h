@@ -1,0 +1,148 @@
+/* rfgpu.h -- C ABI of the B200-native one-vs-many fuzzy-string scoring engine (librfgpu.so).
+ *
+ * Drop-in boundary for the `BatchComparator` hot path of rapidfuzz-rs 0.5.0.  The reference has no FFI
+ * (pure safe Rust, src/lib.rs:78); every entry point below names the reference interface it replaces
+ * (paths relative to the reference's src/).  A Rust shim binding these symbols is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain pointers + sizes, no C++/torch types; every function returns rf_status (0 = ok), never aborts.
+ *  - `None` (score worse than score_cutoff: common.rs:43-45, :83-85) is UINT32_MAX in u32 outputs and NaN in
+ *    f64 outputs.
+ *  - handles are immutable after creation; concurrent calls on the same handles are safe
+ *    (BatchComparator is Clone + Send + Sync in the reference: levenshtein.rs:1635-1639).
+ *  - `*_device` variants take/return device pointers (e.g. torch tensor data_ptr()) and a cudaStream_t
+ *    passed as void*; they enqueue work and return without synchronising.
+ *  - there is NO CPU fallback: without a usable CUDA device every compute entry point returns RF_ERR_CUDA.
+ */
+#ifndef RFGPU_H
+#define RFGPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum rf_status {
+  RF_OK = 0,
+  RF_ERR_INVALID_ARG = 1,
+  RF_ERR_UNSUPPORTED = 2, /* e.g. generic (non-uniform, non-indel) weights; query longer than RF_MAX_QUERY_LEN */
+  RF_ERR_CUDA = 3,
+  RF_ERR_OOM = 4
+} rf_status;
+
+/* metric modules: distance/{levenshtein,indel,lcs_seq,osa,jaro,jaro_winkler}.rs and fuzz.rs (ratio) */
+typedef enum rf_metric {
+  RF_LEVENSHTEIN = 0,
+  RF_INDEL = 1,
+  RF_LCS_SEQ = 2,
+  RF_OSA = 3,
+  RF_JARO = 4,
+  RF_JARO_WINKLER = 5,
+  RF_RATIO = 6
+} rf_metric;
+
+/* which BatchComparator method: distance / similarity / normalized_distance / normalized_similarity */
+typedef enum rf_kind {
+  RF_DISTANCE = 0,
+  RF_SIMILARITY = 1,
+  RF_NORMALIZED_DISTANCE = 2,
+  RF_NORMALIZED_SIMILARITY = 3
+} rf_kind;
+
+/* POD image of the per-metric `Args` builders (levenshtein.rs:86-126, jaro_winkler.rs:25-62, ...).
+ * cutoff_u/hint_u are used by integer-valued results, cutoff_f/hint_f by float-valued ones.
+ * score_hint only steers the reference's band search (levenshtein.rs:1069-1088); accepted and ignored. */
+typedef struct rf_args {
+  uint8_t has_cutoff;
+  uint64_t cutoff_u;
+  double cutoff_f;
+  uint8_t has_hint;
+  uint64_t hint_u;
+  double hint_f;
+  uint64_t insertion_cost, deletion_cost, substitution_cost; /* WeightTable, levenshtein.rs:130-148 */
+  double prefix_weight;                                      /* jaro_winkler.rs:31-39, default 0.1 */
+  uint8_t reference_quirks; /* 1: RatioBatchComparator divides by max(len1,len2) like fuzz.rs:141 */
+} rf_args;
+
+#define RF_MAX_QUERY_LEN 16384u
+
+typedef struct rf_corpus rf_corpus; /* packed candidates resident in one GPU's HBM */
+typedef struct rf_batch rf_batch;   /* one cached query == one BatchComparator */
+
+void rf_args_default(rf_args* a); /* Args::default(): no cutoff, no hint, weights (1,1,1), prefix_weight 0.1 */
+const char* rf_status_string(rf_status s);
+const char* rf_last_error(void); /* thread-local detail of the last non-OK status */
+int rf_device_count(void);       /* 0 when no CUDA device is usable */
+
+/* ---- corpus: the candidates the reference receives one iterator at a time
+ * (BatchComparator::distance(s2), levenshtein.rs:1740-1777).  chars = concatenated u8 elements,
+ * offsets[n+1] = CSR starts (offsets[0] = 0).  Host buffers are copied; caller keeps ownership. */
+rf_status rf_corpus_create_u8(const uint8_t* chars, const uint64_t* offsets, uint64_t n, int device,
+                              rf_corpus** out);
+/* same, CSR starts given as u32 (total bytes < 2^32) -- halves the offset upload */
+rf_status rf_corpus_create_u8_off32(const uint8_t* chars, const uint32_t* offsets, uint64_t n, int device,
+                                    rf_corpus** out);
+/* buffers already on `device` (copied device-to-device on `stream`) */
+rf_status rf_corpus_create_device_u8(const uint8_t* d_chars, const uint64_t* d_offsets, uint64_t n,
+                                     uint64_t total_chars, int device, void* stream, rf_corpus** out);
+rf_status rf_corpus_destroy(rf_corpus* c);
+uint64_t rf_corpus_size(const rf_corpus* c);        /* number of candidates */
+uint64_t rf_corpus_total_chars(const rf_corpus* c); /* sum of candidate lengths */
+int rf_corpus_device(const rf_corpus* c);
+
+/* ---- batch comparator: `BatchComparator::new(query)` -- keeps s1 and builds the pattern-match bit table
+ * (levenshtein.rs:1645-1657, pattern_match_vector.rs:203-281). */
+rf_status rf_batch_create_u8(rf_metric metric, const uint8_t* query, uint32_t query_len, int device,
+                             rf_batch** out);
+rf_status rf_batch_destroy(rf_batch* b);
+
+/* ---- scoring: one call == the user's loop `for c in candidates { scorer.<kind>_with_args(c, &args) }`.
+ * Integer-valued: levenshtein/indel/lcs_seq/osa distance|similarity            -> u32 out[n]
+ * Float-valued:   every normalized_*; jaro/jaro_winkler distance|similarity; ratio similarity -> f64 out[n]
+ * (levenshtein.rs:1660-1817, lcs_seq.rs:796-949, indel.rs:371-520, osa.rs:463-616, jaro.rs:826-979,
+ *  jaro_winkler.rs:409-578, fuzz.rs:102-150).  args == NULL means Args::default(). */
+rf_status rf_batch_score_u32(const rf_batch* b, const rf_corpus* c, rf_kind kind, const rf_args* args,
+                             uint32_t* out_host);
+rf_status rf_batch_score_f64(const rf_batch* b, const rf_corpus* c, rf_kind kind, const rf_args* args,
+                             double* out_host);
+rf_status rf_batch_score_u32_device(const rf_batch* b, const rf_corpus* c, rf_kind kind, const rf_args* args,
+                                    uint32_t* out_device, void* stream);
+rf_status rf_batch_score_f64_device(const rf_batch* b, const rf_corpus* c, rf_kind kind, const rf_args* args,
+                                    double* out_device, void* stream);
+/* 1 if (metric, kind) yields f64, 0 if u32 */
+int rf_result_is_float(rf_metric metric, rf_kind kind);
+
+/* named wrappers, one per reference method */
+rf_status rf_batch_distance_u32(const rf_batch* b, const rf_corpus* c, const rf_args* args, uint32_t* out);
+rf_status rf_batch_similarity_u32(const rf_batch* b, const rf_corpus* c, const rf_args* args, uint32_t* out);
+rf_status rf_batch_distance_f64(const rf_batch* b, const rf_corpus* c, const rf_args* args, double* out);
+rf_status rf_batch_similarity_f64(const rf_batch* b, const rf_corpus* c, const rf_args* args, double* out);
+rf_status rf_batch_normalized_distance_f64(const rf_batch* b, const rf_corpus* c, const rf_args* args, double* out);
+rf_status rf_batch_normalized_similarity_f64(const rf_batch* b, const rf_corpus* c, const rf_args* args, double* out);
+
+/* ---- many-vs-many (new on this side; the reference has no cdist -- SURVEY fact 3): for each of nq queries
+ * the k best candidates by (distance ascending, index ascending); fewer than k hits are padded with
+ * (UINT32_MAX, UINT32_MAX).  Levenshtein distance, queries of length <= 64.  idx/dist are [nq][k]. */
+rf_status rf_cdist_topk_u8(const uint8_t* q_chars, const uint64_t* q_offsets, uint32_t nq, const rf_corpus* c,
+                           const rf_args* args, uint32_t k, uint32_t* idx_host, uint32_t* dist_host);
+rf_status rf_cdist_topk_u8_device(const uint8_t* q_chars, const uint64_t* q_offsets, uint32_t nq,
+                                  const rf_corpus* c, const rf_args* args, uint32_t k, uint32_t* idx_device,
+                                  uint32_t* dist_device, void* stream);
+
+/* ---- synthetic workload generator (SplitMix64, 62-symbol alphanumeric ASCII,
+ * lengths uniform in [min_len,max_len], 1/64 of the candidates = query with <= kmax random edits).
+ * Host-side utility used by bench.py and the tests; writes offsets[n+1] and, if chars != NULL, the bytes.
+ * Call once with chars == NULL to size the buffer (offsets[n] = total). */
+rf_status rf_synth_query_u8(uint64_t seed, uint32_t len, uint8_t* out);
+rf_status rf_synth_corpus_u8(uint64_t seed, const uint8_t* query, uint32_t query_len, uint64_t n,
+                             uint32_t min_len, uint32_t max_len, uint32_t kmax, uint64_t* offsets,
+                             uint8_t* chars, int nthreads);
+
+/* kernel launches issued by this library in this process so far (bench.py reports the delta) */
+uint64_t rf_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RFGPU_H */

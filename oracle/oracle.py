@@ -22,7 +22,7 @@ class OrcArgs(C.Structure):
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "rf_oracle.hpp", "rf_textbook.hpp")]
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "rf_oracle.hpp", "rf_textbook.hpp", "Makefile")]
     if (not force and os.path.exists(_LIB_PATH)
             and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in srcs)):
         return _LIB_PATH

@@ -1,0 +1,481 @@
+// rf_core.cuh -- per-candidate arithmetic of the scoring kernels, written __host__ __device__ so that the
+// very same code is unit-tested on the CPU (tests/test_core_host.py compiles it with g++) and runs inside
+// the sm_100a kernels (rf_kernels.cu).
+//
+// What is computed follows rapidfuzz-rs 0.5.0 (paths relative to the reference's src/); how it is computed
+// is GPU-first:
+//  * Levenshtein / OSA (levenshtein.rs:435-507, osa.rs:84-135): Hyyro/Myers bit-vectors, but the pattern is
+//    TOP-aligned in the machine word (bit BITS-len1 .. BITS-1) so no per-column score tracking is needed:
+//    D[m][n] = n + popc(VP) - popc(VN) from the final vertical delta vectors.  The unused low bits stay at
+//    VP=VN=0 and feed the +1 horizontal carry into the pattern's first row by themselves.
+//  * LCSseq / Indel / ratio (lcs_seq.rs:199-261): S = (S + (S&M)) | (S & ~(S&M)), lcs = popc(~S).
+//  * Jaro / Jaro-Winkler (jaro.rs:147-190, :339-368, :516-598; jaro_winkler.rs:103-141): flag pass +
+//    transposition pass on 64-bit flags, f64 epilogue in the reference's operation order.
+//  * score algebra (details/distance.rs:154-385, common.rs:43-45, :83-85) in finish_int / finish_float.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define RF_HD __host__ __device__ __forceinline__
+#else
+#define RF_HD inline
+#endif
+
+namespace rfk {
+
+enum Metric : int { M_LEVENSHTEIN = 0, M_INDEL = 1, M_LCS_SEQ = 2, M_OSA = 3, M_JARO = 4, M_JARO_WINKLER = 5, M_RATIO = 6 };
+enum Kind : int { K_DISTANCE = 0, K_SIMILARITY = 1, K_NORM_DISTANCE = 2, K_NORM_SIMILARITY = 3 };
+// which bit-parallel recurrence a metric needs
+enum Family : int { F_LEV = 0, F_LCS = 1, F_OSA = 2, F_JARO = 3 };
+// Levenshtein weight classes (levenshtein.rs:1301-1330)
+enum WeightClass : int { WC_UNIFORM = 0, WC_INDEL = 1, WC_ZERO = 2 };
+
+constexpr uint32_t NONE_U32 = 0xFFFFFFFFu;
+
+RF_HD int popc(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __popc(x);
+#else
+  return __builtin_popcount(x);
+#endif
+}
+RF_HD int popc(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+  return __popcll(x);
+#else
+  return __builtin_popcountll(x);
+#endif
+}
+RF_HD int ctz64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+  return __ffsll((long long)x) - 1;
+#else
+  return __builtin_ctzll(x);
+#endif
+}
+RF_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {  // (hi:lo) >> sh, sh in {0,8,16,24}
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_r(lo, hi, sh);
+#else
+  return sh ? ((lo >> sh) | (hi << (32 - sh))) : lo;
+#endif
+}
+
+// Sequential reader over candidate bytes that start at an arbitrary byte of a 4-byte-aligned buffer.
+// Reads whole aligned words (one word of over-read slack is required behind the data).
+struct ByteReader {
+  const uint32_t* p;
+  uint32_t sh;
+  uint32_t cur;
+  RF_HD ByteReader(const uint8_t* aligned_base, uint32_t start) {
+    p = reinterpret_cast<const uint32_t*>(aligned_base + (start & ~3u));
+    sh = (start & 3u) * 8u;
+    cur = *p++;
+  }
+  RF_HD uint32_t next4() {
+    uint32_t nxt = *p++;
+    uint32_t r = funnel_r(cur, nxt, sh);
+    cur = nxt;
+    return r;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Levenshtein, one machine word (query length 1..BITS).  `tab(ch)` returns the TOP-aligned match mask
+// PM[ch] << (BITS - len1).
+template <class W, class Tab>
+RF_HD uint32_t lev_w1(const Tab& tab, ByteReader rd, uint32_t len2, uint32_t len1) {
+  constexpr int BITS = (int)sizeof(W) * 8;
+  W VP = (W)(~(W)0) << (BITS - (int)len1);
+  W VN = 0;
+#define RF_LEV_STEP(CH)                               \
+  {                                                   \
+    const W X = tab(CH);                              \
+    const W D0 = ((((X & VP) + VP) ^ VP) | X) | VN;   \
+    W HP = VN | ~(D0 | VP);                           \
+    W HN = D0 & VP;                                   \
+    HP = (HP << 1) | (W)1;                            \
+    HN = HN << 1;                                     \
+    VP = HN | ~(D0 | HP);                             \
+    VN = HP & D0;                                     \
+  }
+  const uint32_t nfull = len2 >> 2;
+  for (uint32_t i = 0; i < nfull; ++i) {
+    const uint32_t w = rd.next4();
+    RF_LEV_STEP(w & 0xffu)
+    RF_LEV_STEP((w >> 8) & 0xffu)
+    RF_LEV_STEP((w >> 16) & 0xffu)
+    RF_LEV_STEP(w >> 24)
+  }
+  const uint32_t rem = len2 & 3u;
+  if (rem) {
+    const uint32_t w = rd.next4();
+    RF_LEV_STEP(w & 0xffu)
+    if (rem > 1) RF_LEV_STEP((w >> 8) & 0xffu)
+    if (rem > 2) RF_LEV_STEP((w >> 16) & 0xffu)
+  }
+#undef RF_LEV_STEP
+  return len2 + (uint32_t)popc(VP) - (uint32_t)popc(VN);
+}
+
+// OSA, one machine word, TOP-aligned like lev_w1 (osa.rs:84-135: D0 |= TR with
+// TR = (((~D0_prev) & PM_j) << 1) & PM_{j-1}).
+template <class W, class Tab>
+RF_HD uint32_t osa_w1(const Tab& tab, ByteReader rd, uint32_t len2, uint32_t len1) {
+  constexpr int BITS = (int)sizeof(W) * 8;
+  W VP = (W)(~(W)0) << (BITS - (int)len1);
+  W VN = 0, D0 = 0, PMold = 0;
+#define RF_OSA_STEP(CH)                               \
+  {                                                   \
+    const W X = tab(CH);                              \
+    const W TR = (((~D0) & X) << 1) & PMold;          \
+    D0 = (((((X & VP) + VP) ^ VP) | X) | VN) | TR;    \
+    W HP = VN | ~(D0 | VP);                           \
+    W HN = D0 & VP;                                   \
+    HP = (HP << 1) | (W)1;                            \
+    HN = HN << 1;                                     \
+    VP = HN | ~(D0 | HP);                             \
+    VN = HP & D0;                                     \
+    PMold = X;                                        \
+  }
+  const uint32_t nfull = len2 >> 2;
+  for (uint32_t i = 0; i < nfull; ++i) {
+    const uint32_t w = rd.next4();
+    RF_OSA_STEP(w & 0xffu)
+    RF_OSA_STEP((w >> 8) & 0xffu)
+    RF_OSA_STEP((w >> 16) & 0xffu)
+    RF_OSA_STEP(w >> 24)
+  }
+  const uint32_t rem = len2 & 3u;
+  if (rem) {
+    const uint32_t w = rd.next4();
+    RF_OSA_STEP(w & 0xffu)
+    if (rem > 1) RF_OSA_STEP((w >> 8) & 0xffu)
+    if (rem > 2) RF_OSA_STEP((w >> 16) & 0xffu)
+  }
+#undef RF_OSA_STEP
+  return len2 + (uint32_t)popc(VP) - (uint32_t)popc(VN);
+}
+
+// LCS length, one machine word; `tab(ch)` is the plain (bottom-aligned) PM[ch] (lcs_seq.rs:222-257).
+template <class W, class Tab>
+RF_HD uint32_t lcs_w1(const Tab& tab, ByteReader rd, uint32_t len2) {
+  W S = ~(W)0;
+#define RF_LCS_STEP(CH)              \
+  {                                  \
+    const W U = S & tab(CH);         \
+    S = (S + U) | (S & ~U);          \
+  }
+  const uint32_t nfull = len2 >> 2;
+  for (uint32_t i = 0; i < nfull; ++i) {
+    const uint32_t w = rd.next4();
+    RF_LCS_STEP(w & 0xffu)
+    RF_LCS_STEP((w >> 8) & 0xffu)
+    RF_LCS_STEP((w >> 16) & 0xffu)
+    RF_LCS_STEP(w >> 24)
+  }
+  const uint32_t rem = len2 & 3u;
+  if (rem) {
+    const uint32_t w = rd.next4();
+    RF_LCS_STEP(w & 0xffu)
+    if (rem > 1) RF_LCS_STEP((w >> 8) & 0xffu)
+    if (rem > 2) RF_LCS_STEP((w >> 16) & 0xffu)
+  }
+#undef RF_LCS_STEP
+  return (uint32_t)popc((W)~S);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Jaro building blocks (jaro.rs:106-145)
+RF_HD double jaro_calculate_similarity(uint32_t p_len, uint32_t t_len, uint32_t cc, uint32_t transpositions) {
+  transpositions /= 2;
+  double sim = 0.0;
+  sim += (double)cc / (double)p_len;
+  sim += (double)cc / (double)t_len;
+  sim += ((double)cc - (double)transpositions) / (double)cc;
+  return sim / 3.0;
+}
+RF_HD bool jaro_length_filter(uint32_t p_len, uint32_t t_len, double cutoff) {
+  if (t_len == 0 || p_len == 0) return false;
+  const double min_len = (double)(p_len < t_len ? p_len : t_len);
+  double sim = min_len / (double)p_len + min_len / (double)t_len + 1.0;
+  sim /= 3.0;
+  return sim >= cutoff;
+}
+RF_HD bool jaro_common_char_filter(uint32_t p_len, uint32_t t_len, uint32_t cc, double cutoff) {
+  if (cc == 0) return false;
+  double sim = 0.0;
+  sim += (double)cc / (double)p_len;
+  sim += (double)cc / (double)t_len;
+  sim += 1.0;
+  sim /= 3.0;
+  return sim >= cutoff;
+}
+
+// Jaro similarity with a cached query (jaro.rs:516-598).
+//   pmw(word, ch) -> bottom-aligned PM word; bytes(j) -> candidate byte j.
+//   Query length 1..MAXQ (MAXQ multiple of 64); the candidate may have any length: instead of the
+//   reference's t_flag bit-vector (which grows with the candidate) the matched text characters are kept
+//   in order (at most len1 of them), which yields the identical transposition count.
+template <int MAXQ, class PMW, class Bytes>
+RF_HD double jaro_similarity_generic(const PMW& pmw, const Bytes& bytes, uint32_t len1, uint32_t len2, double cutoff) {
+  const uint32_t len1_orig = len1, len2_orig = len2;
+  if (cutoff > 1.0) return 0.0;
+  if (len1_orig == 0 && len2_orig == 0) return 1.0;
+  if (!jaro_length_filter(len1_orig, len2_orig, cutoff)) return 0.0;
+  if (len1_orig == 1 && len2_orig == 1) return (pmw(0u, bytes(0u)) & 1u) ? 1.0 : 0.0;
+  uint32_t bound;
+  if (len2 > len1) {
+    bound = len2 / 2 - 1;
+    if (len2 > len1 + bound) len2 = len1 + bound;
+  } else {
+    bound = len1 / 2 - 1;
+    if (len1 > len2 + bound) len1 = len2 + bound;
+  }
+  if (len1 == 0 || len2 == 0) return jaro_calculate_similarity(len1_orig, len2_orig, 0, 0);  // NaN like the reference (0/0); unreachable: both >= 1 here
+  constexpr int PW = MAXQ / 64;
+  uint64_t P[PW];
+  uint8_t matched[MAXQ];
+#pragma unroll
+  for (int i = 0; i < PW; ++i) P[i] = 0;
+  const uint32_t words = (len1_orig + 63) / 64;
+  uint32_t cc = 0;
+  for (uint32_t j = 0; j < len2; ++j) {
+    // window of pattern positions [lo, hi] (jaro.rs:168-187 / :306-334), clipped to the truncated len1
+    const uint32_t lo = j > bound ? j - bound : 0;
+    uint32_t hi = j + bound;
+    if (hi >= len1) hi = len1 - 1;
+    if (lo > hi) continue;
+    const uint32_t ch = bytes(j);
+    const uint32_t w0 = lo / 64, w1 = hi / 64;
+    for (uint32_t w = w0; w <= w1 && w < words; ++w) {
+      uint64_t m = pmw(w, ch) & ~P[w];
+      if (w == w0) m &= ~0ULL << (lo % 64);
+      if (w == w1) m &= ~0ULL >> (63 - (hi % 64));
+      if (m) {
+        P[w] |= m & (0 - m);
+        matched[cc++] = (uint8_t)ch;
+        break;
+      }
+    }
+  }
+  if (!jaro_common_char_filter(len1_orig, len2_orig, cc, cutoff)) return 0.0;
+  // transpositions: k-th flagged pattern position vs k-th matched text character (jaro.rs:339-420)
+  uint32_t transpositions = 0, k = 0;
+  for (uint32_t w = 0; w < words; ++w) {
+    uint64_t p = P[w];
+    while (p) {
+      const uint64_t bit = p & (0 - p);
+      transpositions += (pmw(w, (uint32_t)matched[k]) & bit) == 0;
+      ++k;
+      p ^= bit;
+    }
+  }
+  return jaro_calculate_similarity(len1_orig, len2_orig, cc, transpositions);
+}
+
+// Fast path: query <= 64 and (truncated) candidate <= 64: flags in two registers (jaro.rs:147-190, :339-368).
+// tab(ch) -> bottom-aligned 64-bit PM; bytes(j) -> candidate byte j.  Falls back to the generic routine
+// when the truncated candidate is longer than 64 (the reference's block path, jaro.rs:584-595).
+template <class Tab, class Bytes>
+RF_HD double jaro_similarity_w1(const Tab& tab, const Bytes& bytes, uint32_t len1, uint32_t len2, double cutoff) {
+  const uint32_t len1_orig = len1, len2_orig = len2;
+  if (cutoff > 1.0) return 0.0;
+  if (len1_orig == 0 && len2_orig == 0) return 1.0;
+  if (!jaro_length_filter(len1_orig, len2_orig, cutoff)) return 0.0;
+  if (len1_orig == 1 && len2_orig == 1) return (tab(bytes(0u)) & 1u) ? 1.0 : 0.0;
+  uint32_t bound;
+  if (len2 > len1) {
+    bound = len2 / 2 - 1;
+    if (len2 > len1 + bound) len2 = len1 + bound;
+  } else {
+    bound = len1 / 2 - 1;
+    if (len1 > len2 + bound) len1 = len2 + bound;
+  }
+  if (len2 > 64) {
+    auto pmw = [&](uint32_t, uint32_t ch) -> uint64_t { return tab(ch); };
+    return jaro_similarity_generic<64>(pmw, bytes, len1_orig, len2_orig, cutoff);
+  }
+  uint64_t P = 0, T = 0;
+  uint64_t bound_mask = (bound + 1 < 64) ? ((1ULL << (bound + 1)) - 1) : ~0ULL;  // bit_mask_lsb_u64(bound+1)
+  uint32_t j = 0;
+  const uint32_t n0 = bound < len2 ? bound : len2;
+  for (; j < n0; ++j) {
+    const uint64_t m = tab(bytes(j)) & bound_mask & ~P;
+    P |= m & (0 - m);
+    T |= (uint64_t)(m != 0) << j;
+    bound_mask = (bound_mask << 1) | 1;
+  }
+  for (; j < len2; ++j) {
+    const uint64_t m = tab(bytes(j)) & bound_mask & ~P;
+    P |= m & (0 - m);
+    T |= (uint64_t)(m != 0) << j;
+    bound_mask <<= 1;
+  }
+  const uint32_t cc = (uint32_t)popc(P);
+  if (!jaro_common_char_filter(len1_orig, len2_orig, cc, cutoff)) return 0.0;
+  uint32_t transpositions = 0;
+  while (T) {
+    const uint64_t pbit = P & (0 - P);
+    const int idx = ctz64(T);
+    transpositions += (tab(bytes((uint32_t)idx)) & pbit) == 0;
+    T &= T - 1;
+    P ^= pbit;
+  }
+  return jaro_calculate_similarity(len1_orig, len2_orig, cc, transpositions);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Score algebra.  `Epi` is the per-launch image of rf_args + metric + kind.
+struct Epi {
+  int metric;
+  int kind;
+  int has_cutoff;
+  uint64_t cutoff_u;
+  double cutoff_f;
+  int wclass;          // Levenshtein only
+  uint64_t w_ins, w_del, w_sub;
+  double prefix_weight;
+  int quirks;
+};
+
+RF_HD Family family_of(int metric, int wclass) {
+  switch (metric) {
+    case M_LEVENSHTEIN: return wclass == WC_INDEL ? F_LCS : F_LEV;
+    case M_INDEL: case M_LCS_SEQ: case M_RATIO: return F_LCS;
+    case M_OSA: return F_OSA;
+    default: return F_JARO;
+  }
+}
+RF_HD bool result_is_float(int metric, int kind) {
+  if (metric == M_JARO || metric == M_JARO_WINKLER || metric == M_RATIO) return true;
+  return kind == K_NORM_DISTANCE || kind == K_NORM_SIMILARITY;
+}
+
+RF_HD uint64_t umin64(uint64_t a, uint64_t b) { return a < b ? a : b; }
+RF_HD uint64_t umax64(uint64_t a, uint64_t b) { return a > b ? a : b; }
+
+// maximum(len1,len2) per metric (levenshtein.rs:263-277, indel.rs:331, lcs_seq.rs:773, osa.rs:432)
+RF_HD uint64_t int_maximum(const Epi& e, uint64_t len1, uint64_t len2) {
+  switch (e.metric) {
+    case M_LEVENSHTEIN: {
+      const uint64_t max_dist = len1 * e.w_del + len2 * e.w_ins;
+      if (len1 >= len2) return umin64(max_dist, len2 * e.w_sub + (len1 - len2) * e.w_del);
+      return umin64(max_dist, len1 * e.w_sub + (len2 - len1) * e.w_ins);
+    }
+    case M_INDEL: return len1 + len2;
+    case M_RATIO: return e.quirks ? umax64(len1, len2) : len1 + len2;
+    default: return umax64(len1, len2);
+  }
+}
+
+// exact distance of the metric from the raw kernel result
+//   F_LEV/F_OSA raw = unit-cost distance, F_LCS raw = LCS length
+RF_HD uint64_t int_distance(const Epi& e, uint64_t raw, uint64_t len1, uint64_t len2) {
+  switch (e.metric) {
+    case M_LEVENSHTEIN:
+      if (e.wclass == WC_ZERO) return 0;                                     // levenshtein.rs:1303-1305
+      if (e.wclass == WC_INDEL) return (len1 + len2 - 2 * raw) * e.w_ins;    // :1321-1327
+      return raw * e.w_ins;                                                  // :1308-1316
+    case M_INDEL: return len1 + len2 - 2 * raw;                              // indel.rs:367
+    case M_RATIO: return e.quirks ? umax64(len1, len2) - raw : len1 + len2 - 2 * raw;
+    case M_LCS_SEQ: return umax64(len1, len2) - raw;                         // details/distance.rs:178
+    default: return raw;                                                     // OSA
+  }
+}
+
+// Integer-valued kinds.  Returns NONE_U32 for `None`.
+RF_HD uint32_t finish_int(const Epi& e, uint64_t raw, uint64_t len1, uint64_t len2) {
+  const uint64_t d = int_distance(e, raw, len1, len2);
+  if (e.kind == K_DISTANCE) {
+    if (e.has_cutoff && d > e.cutoff_u) return NONE_U32;                     // common.rs:43-45
+    return (uint32_t)d;
+  }
+  const uint64_t M = int_maximum(e, len1, len2);
+  const uint64_t s = M - d;
+  if (e.has_cutoff && s < e.cutoff_u) return NONE_U32;                       // common.rs:83-85
+  return (uint32_t)s;
+}
+
+RF_HD double clamp01(double x) { return x < 0.0 ? 0.0 : (x > 1.0 ? 1.0 : x); }
+RF_HD double qnan() {
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double(0x7ff8000000000000LL);
+#else
+  return NAN;
+#endif
+}
+
+// normalized_distance / normalized_similarity of the integer metrics (+ fuzz::ratio).  NaN for `None`.
+// Follows details/distance.rs:213-274 literally: the float cutoff is first turned into an integer
+// distance cutoff (internal early-out), the final `score()` filter is applied on the float result.
+RF_HD double finish_norm(const Epi& e, uint64_t raw, uint64_t len1, uint64_t len2) {
+  const uint64_t d = int_distance(e, raw, len1, len2);
+  const uint64_t M = int_maximum(e, len1, len2);
+  const bool sim_kind = (e.kind == K_NORM_SIMILARITY) || (e.metric == M_RATIO);
+  if (e.has_cutoff) {
+    const double c = sim_kind ? fmin(1.0 - e.cutoff_f + 0.00001, 1.0) : e.cutoff_f;   // details/common.rs:4-7
+    const uint64_t cd = (uint64_t)ceil((double)M * clamp01(c));                         // :231-236
+    if (d > cd) return qnan();
+  }
+  const double nd = (M == 0) ? 0.0 : (double)d / (double)M;                            // :247-251
+  if (!sim_kind) {
+    if (e.has_cutoff && !(nd <= e.cutoff_f)) return qnan();
+    return nd;
+  }
+  const double ns = 1.0 - nd;                                                           // :273
+  if (e.has_cutoff && !(ns >= e.cutoff_f)) return qnan();
+  return ns;
+}
+
+// Jaro / Jaro-Winkler: the four kinds through Metricf64 (details/distance.rs:277-385), maximum = 1.0.
+//   sim_fn(cutoff) computes the metric's `_similarity` for the given internal cutoff.
+template <class SimFn>
+RF_HD double finish_float(const Epi& e, const SimFn& sim_fn) {
+  const bool has = e.has_cutoff != 0;
+  const double c = e.cutoff_f;
+  switch (e.kind) {
+    case K_SIMILARITY: {
+      const double sim = sim_fn(has ? c : 0.0);
+      return (has && !(sim >= c)) ? qnan() : sim;
+    }
+    case K_DISTANCE: {
+      const double cs = has ? (1.0 >= c ? 1.0 - c : 0.0) : 0.0;                // :297
+      const double dist = 1.0 - sim_fn(cs);                                    // :300-301
+      return (has && !(dist <= c)) ? qnan() : dist;
+    }
+    case K_NORM_DISTANCE: {
+      const double cd = has ? 1.0 * c : 0.0;                                   // :353
+      const double cs = has ? (1.0 >= cd ? 1.0 - cd : 0.0) : 0.0;
+      const double dist = 1.0 - sim_fn(cs);
+      const double nd = dist / 1.0;                                            // :357-358
+      return (has && !(nd <= c)) ? qnan() : nd;
+    }
+    default: {
+      const double cn = has ? fmin(1.0 - c + 0.00001, 1.0) : 0.0;              // :379
+      const double cd = has ? 1.0 * cn : 0.0;
+      const double cs = has ? (1.0 >= cd ? 1.0 - cd : 0.0) : 0.0;
+      const double dist = 1.0 - sim_fn(cs);
+      const double nd = dist / 1.0;
+      const double ns = 1.0 - nd;                                              // :382-383
+      return (has && !(ns >= c)) ? qnan() : ns;
+    }
+  }
+}
+
+// Jaro-Winkler on top of a Jaro routine (jaro_winkler.rs:103-141). prefix = common prefix length (<= 4).
+template <class JaroFn>
+RF_HD double jaro_winkler_from(const JaroFn& jaro_fn, uint32_t prefix, double prefix_weight, double cutoff) {
+  double jaro_cutoff = cutoff;
+  if (jaro_cutoff > 0.7) {
+    const double prefix_sim = (double)prefix * prefix_weight;
+    if (prefix_sim >= 1.0) jaro_cutoff = 0.7;
+    else jaro_cutoff = fmax(0.7, (prefix_sim - jaro_cutoff) / (prefix_sim - 1.0));
+  }
+  double sim = jaro_fn(jaro_cutoff);
+  if (sim > 0.7) sim += (double)prefix * prefix_weight * (1.0 - sim);
+  return sim;
+}
+
+}  // namespace rfk

@@ -1,0 +1,107 @@
+// Host build of rapidfuzz-rs_b200/csrc/rf_core.cuh (the exact arithmetic the CUDA kernels run), exposed
+// to pytest so the bit tricks are checked against the oracle on the CPU box before any GPU time is spent.
+#include <cstring>
+#include <vector>
+#include "../rapidfuzz-rs_b200/csrc/rf_core.cuh"
+
+using namespace rfk;
+
+template <class W>
+static void build_tab(const uint8_t* q, uint32_t len1, bool top, W* tab) {
+  for (int i = 0; i < 256; ++i) tab[i] = 0;
+  for (uint32_t i = 0; i < len1; ++i) tab[q[i]] |= (W)1 << i;
+  if (top) {
+    const int sh = (int)sizeof(W) * 8 - (int)len1;
+    for (int i = 0; i < 256; ++i) tab[i] <<= sh;
+  }
+}
+
+// copies s into a 4B-aligned padded buffer at byte offset `mis` (0..3) to exercise the funnel reader
+struct Padded {
+  std::vector<uint32_t> buf;
+  uint32_t start;
+  Padded(const uint8_t* s, uint32_t len, uint32_t mis) : buf((len + mis) / 4 + 4, 0xA5A5A5A5u), start(mis) {
+    if (len) memcpy(reinterpret_cast<uint8_t*>(buf.data()) + mis, s, len);
+  }
+  const uint8_t* base() const { return reinterpret_cast<const uint8_t*>(buf.data()); }
+};
+
+extern "C" {
+
+uint32_t core_raw(int family, int bits, const uint8_t* q, uint32_t len1, const uint8_t* s, uint32_t len2, uint32_t mis) {
+  Padded p(s, len2, mis);
+  ByteReader rd(p.base(), p.start);
+  if (bits == 32) {
+    uint32_t tab[256];
+    build_tab(q, len1, family != F_LCS, tab);
+    auto t = [&](uint32_t ch) { return tab[ch]; };
+    if (family == F_LEV) return lev_w1<uint32_t>(t, rd, len2, len1);
+    if (family == F_OSA) return osa_w1<uint32_t>(t, rd, len2, len1);
+    return lcs_w1<uint32_t>(t, rd, len2);
+  }
+  uint64_t tab[256];
+  build_tab(q, len1, family != F_LCS, tab);
+  auto t = [&](uint32_t ch) { return tab[ch]; };
+  if (family == F_LEV) return lev_w1<uint64_t>(t, rd, len2, len1);
+  if (family == F_OSA) return osa_w1<uint64_t>(t, rd, len2, len1);
+  return lcs_w1<uint64_t>(t, rd, len2);
+}
+
+static Epi make_epi(int metric, int kind, int has_cutoff, uint64_t cu, double cf, uint64_t wi, uint64_t wd, uint64_t ws,
+                    double pw, int quirks) {
+  Epi e{};
+  e.metric = metric; e.kind = kind; e.has_cutoff = has_cutoff; e.cutoff_u = cu; e.cutoff_f = cf;
+  e.w_ins = wi; e.w_del = wd; e.w_sub = ws; e.prefix_weight = pw; e.quirks = quirks;
+  e.wclass = WC_UNIFORM;
+  if (metric == M_LEVENSHTEIN) {
+    if (wi == 0 && wd == 0) e.wclass = WC_ZERO;
+    else if (wi == wd && wi == ws) e.wclass = WC_UNIFORM;
+    else e.wclass = WC_INDEL;
+  }
+  return e;
+}
+
+// full per-candidate pipeline for query <= 64: raw kernel + score algebra; out_u (NONE_U32 = None) / out_f (NaN = None)
+int core_score(int metric, int kind, const uint8_t* q, uint32_t len1, const uint8_t* s, uint32_t len2, int has_cutoff,
+               uint64_t cu, double cf, uint64_t wi, uint64_t wd, uint64_t ws, double pw, int quirks, uint32_t mis,
+               uint32_t* out_u, double* out_f) {
+  Epi e = make_epi(metric, kind, has_cutoff, cu, cf, wi, wd, ws, pw, quirks);
+  Padded p(s, len2, mis);
+  const Family fam = family_of(metric, e.wclass);
+  if (fam == F_JARO) {
+    uint64_t tab[256];
+    build_tab(q, len1, false, tab);
+    auto t = [&](uint32_t ch) { return tab[ch]; };
+    const uint8_t* b = p.base() + p.start;
+    auto bytes = [&](uint32_t j) -> uint32_t { return b[j]; };
+    auto jaro = [&](double c) { return jaro_similarity_w1(t, bytes, len1, len2, c); };
+    uint32_t prefix = 0;
+    while (prefix < 4 && prefix < len1 && prefix < len2 && ((t(bytes(prefix)) >> prefix) & 1)) ++prefix;
+    auto sim = [&](double c) {
+      return metric == M_JARO ? jaro(c) : jaro_winkler_from(jaro, prefix, e.prefix_weight, c);
+    };
+    *out_f = finish_float(e, sim);
+    return 1;
+  }
+  uint32_t raw;
+  if (len1 == 0) raw = (fam == F_LCS) ? 0 : len2;
+  else {
+    const int bits = len1 <= 32 ? 32 : 64;
+    raw = core_raw(fam, bits, q, len1, s, len2, mis);
+  }
+  if (result_is_float(metric, kind)) { *out_f = finish_norm(e, raw, len1, len2); return 1; }
+  *out_u = finish_int(e, raw, len1, len2);
+  return 0;
+}
+
+// generic (multi-word) Jaro on the host, query <= 1024
+double core_jaro_generic(const uint8_t* q, uint32_t len1, const uint8_t* s, uint32_t len2, double cutoff) {
+  const uint32_t words = (len1 + 63) / 64;
+  std::vector<uint64_t> pm(256 * (words ? words : 1), 0);
+  for (uint32_t i = 0; i < len1; ++i) pm[q[i] * words + i / 64] |= 1ULL << (i % 64);
+  auto pmw = [&](uint32_t w, uint32_t ch) -> uint64_t { return pm[ch * words + w]; };
+  auto bytes = [&](uint32_t j) -> uint32_t { return s[j]; };
+  return jaro_similarity_generic<1024>(pmw, bytes, len1, len2, cutoff);
+}
+
+}  // extern "C"

@@ -1,0 +1,147 @@
+"""CPU check of the exact per-candidate arithmetic the CUDA kernels execute (csrc/rf_core.cuh compiled for
+the host by tests/core_host_shim.cpp) against the oracle: bit tricks (top-aligned Myers, popcount score,
+funnel-shift byte reader), Jaro flag/transposition passes and the score algebra incl. cutoffs."""
+import ctypes as C
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "_build", "core_host.so")
+
+
+@pytest.fixture(scope="module")
+def core():
+    os.makedirs(os.path.dirname(SO), exist_ok=True)
+    src = os.path.join(HERE, "core_host_shim.cpp")
+    hdr = os.path.join(HERE, "..", "rapidfuzz-rs_b200", "csrc", "rf_core.cuh")
+    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
+                               "-x", "c++", "-o", SO, src])
+    lib = C.CDLL(SO)
+    lib.core_raw.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32]
+    lib.core_raw.restype = C.c_uint32
+    lib.core_score.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int, C.c_uint64,
+                               C.c_double, C.c_uint64, C.c_uint64, C.c_uint64, C.c_double, C.c_int, C.c_uint32,
+                               C.POINTER(C.c_uint32), C.POINTER(C.c_double)]
+    lib.core_score.restype = C.c_int
+    lib.core_jaro_generic.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_double]
+    lib.core_jaro_generic.restype = C.c_double
+    return lib
+
+
+def _pairs(rng, n, qlens, clens, alphabet):
+    for _ in range(n):
+        l1, l2 = int(rng.choice(qlens)), int(rng.choice(clens))
+        a = (rng.integers(0, alphabet, l1) + 97).astype(np.uint8)
+        if rng.random() < 0.5 and l1 > 0:
+            b = list(a)
+            for _ in range(rng.integers(0, 8)):
+                op, pos = rng.integers(0, 3), rng.integers(0, len(b) + 1)
+                if op == 0 and b:
+                    b[min(pos, len(b) - 1)] = 97 + rng.integers(0, alphabet)
+                elif op == 1:
+                    b.insert(pos, 97 + rng.integers(0, alphabet))
+                elif b:
+                    del b[min(pos, len(b) - 1)]
+            b = np.array(b, dtype=np.uint8)
+        else:
+            b = (rng.integers(0, alphabet, l2) + 97).astype(np.uint8)
+        yield a, b
+
+
+QL = [1, 2, 3, 7, 8, 16, 31, 32, 33, 40, 63, 64]
+CL = [0, 1, 2, 3, 4, 5, 7, 8, 9, 31, 32, 33, 63, 64, 65, 100, 130, 200]
+
+
+def _score(core, metric, kind, a, b, mis=0, cutoff=None, weights=(1, 1, 1), pw=0.1, quirks=False):
+    is_f = orc.result_is_float(metric, kind)
+    ou, of = C.c_uint32(0), C.c_double(0.0)
+    cu = int(cutoff) if (cutoff is not None and not is_f) else 0
+    cf = float(cutoff) if (cutoff is not None and is_f) else 0.0
+    r = core.core_score(orc.METRICS[metric], orc.KINDS[kind], a.ctypes.data, len(a), b.ctypes.data, len(b),
+                        0 if cutoff is None else 1, cu, cf, weights[0], weights[1], weights[2], pw, 1 if quirks else 0,
+                        mis, C.byref(ou), C.byref(of))
+    if r == 1:
+        return None if math.isnan(of.value) else of.value
+    return None if ou.value == 0xFFFFFFFF else ou.value
+
+
+def test_raw_kernels_vs_textbook(core):
+    rng = np.random.default_rng(3)
+    for a, b in _pairs(rng, 3000, QL, CL, 4):
+        d, l, o = orc.tb("levenshtein", a, b), orc.tb("lcs", a, b), orc.tb("osa", a, b)
+        for bits in ((32, 64) if len(a) <= 32 else (64,)):
+            mis = int(rng.integers(0, 4))
+            assert core.core_raw(0, bits, a.ctypes.data, len(a), b.ctypes.data, len(b), mis) == d, (bytes(a), bytes(b), bits)
+            assert core.core_raw(1, bits, a.ctypes.data, len(a), b.ctypes.data, len(b), mis) == l
+            assert core.core_raw(2, bits, a.ctypes.data, len(a), b.ctypes.data, len(b), mis) == o, (bytes(a), bytes(b), bits)
+
+
+INT_METRICS = ["levenshtein", "indel", "lcs_seq", "osa"]
+
+
+def test_score_algebra_vs_oracle(core):
+    rng = np.random.default_rng(5)
+    for a, b in _pairs(rng, 1200, [0] + QL, CL, 4):
+        mis = int(rng.integers(0, 4))
+        for m in INT_METRICS:
+            for kind in ("distance", "similarity"):
+                for c in (None, 0, 1, 2, 3, 4, 5, 10, 31, 32, 64, 2**64 - 1):
+                    if m == "levenshtein" and kind == "similarity" and c is not None:
+                        continue  # reference wraps; we return None (tested separately)
+                    exp = orc.pair(m, kind, a, b, cutoff=c)
+                    got = _score(core, m, kind, a, b, mis, cutoff=c)
+                    assert got == exp, (m, kind, bytes(a), bytes(b), c, got, exp)
+            for kind in ("normalized_distance", "normalized_similarity"):
+                for c in (None, 0.0, 0.1, 0.25, 0.3, 0.5, 0.75, 0.9, 1.0, 1.5, -0.5):
+                    exp = orc.pair(m, kind, a, b, cutoff=c)
+                    got = _score(core, m, kind, a, b, mis, cutoff=c)
+                    assert got == exp, (m, kind, bytes(a), bytes(b), c, got, exp)
+        for c in (None, 0.0, 0.3, 0.5, 0.9, 1.0):
+            for quirks in (False, True):
+                exp = orc.pair("ratio", "similarity", a, b, cutoff=c, reference_quirks=quirks)
+                got = _score(core, "ratio", "similarity", a, b, mis, cutoff=c, quirks=quirks)
+                assert got == exp, ("ratio", bytes(a), bytes(b), c, quirks, got, exp)
+        for w in ((2, 2, 2), (1, 1, 2), (3, 3, 7), (0, 0, 5)):
+            for c in (None, 0, 3, 10, 100):
+                exp = orc.pair("levenshtein", "distance", a, b, cutoff=c, weights=w)
+                got = _score(core, "levenshtein", "distance", a, b, mis, cutoff=c, weights=w)
+                assert got == exp, ("wlev", bytes(a), bytes(b), c, w, got, exp)
+
+
+def test_lev_similarity_cutoff_quirk_q2(core):
+    # reference: maximum - usize::MAX wraps (release) / panics (debug); ours: None when dist > max - cutoff
+    a, b = np.frombuffer(b"kitten", np.uint8), np.frombuffer(b"sitting", np.uint8)
+    assert _score(core, "levenshtein", "similarity", a, b, cutoff=4) == 4
+    assert _score(core, "levenshtein", "similarity", a, b, cutoff=5) is None
+
+
+def test_jaro_family_vs_oracle_bit_exact(core):
+    rng = np.random.default_rng(9)
+    for a, b in _pairs(rng, 2500, [0] + QL, CL, 5):
+        for m in ("jaro", "jaro_winkler"):
+            for kind in ("distance", "similarity", "normalized_distance", "normalized_similarity"):
+                for c in (None, 0.0, 0.3, 0.6, 0.7, 0.75, 0.85, 0.95, 1.0, 1.1):
+                    exp = orc.pair(m, kind, a, b, cutoff=c)
+                    got = _score(core, m, kind, a, b, int(rng.integers(0, 4)), cutoff=c)
+                    assert got == exp, (m, kind, bytes(a), bytes(b), c, got, exp)
+        exp = orc.pair("jaro_winkler", "similarity", a, b, prefix_weight=0.25)
+        assert _score(core, "jaro_winkler", "similarity", a, b, pw=0.25) == exp
+
+
+def test_jaro_generic_multiword_vs_oracle(core):
+    rng = np.random.default_rng(21)
+    for a, b in _pairs(rng, 1500, [1, 5, 64, 65, 100, 128, 129, 200, 300, 700], CL + [300, 500, 900], 5):
+        for c in (0.0, 0.5, 0.8):
+            exp = orc.pair("jaro", "similarity", a, b, cutoff=c)
+            exp = 0.0 if exp is None else exp   # raw _similarity returns 0.0 below the cutoff
+            got = core.core_jaro_generic(a.ctypes.data, len(a), b.ctypes.data, len(b), c)
+            if got < c:
+                got = 0.0
+            assert got == exp, (bytes(a), bytes(b), c, got, exp)

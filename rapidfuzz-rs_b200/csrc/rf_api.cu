@@ -1,0 +1,440 @@
+// rf_api.cu -- the extern "C" boundary declared in include/rfgpu.h: corpus / batch-comparator handles and
+// the scoring entry points.  Plain CUDA runtime; no torch, no CPU fallback (every compute entry point needs a
+// CUDA device and reports RF_ERR_CUDA otherwise).
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/rfgpu.h"
+#include "rf_kernels.cuh"
+
+using namespace rfk;
+
+static thread_local std::string g_last_error;
+
+static rf_status fail(rf_status s, const std::string& msg) {
+  g_last_error = msg;
+  return s;
+}
+static rf_status cuda_fail(cudaError_t e, const char* what) {
+  rf_status s = (e == cudaErrorMemoryAllocation) ? RF_ERR_OOM : RF_ERR_CUDA;
+  return fail(s, std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
+}
+#define RF_CUDA(call)                                  \
+  do {                                                 \
+    cudaError_t e__ = (call);                          \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+static int sm_count_of(int device) {
+  static std::mutex mu;
+  static std::vector<int> cache;
+  std::lock_guard<std::mutex> lk(mu);
+  if ((int)cache.size() <= device) cache.resize(device + 1, 0);
+  if (cache[device] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || v <= 0) v = 148;
+    cache[device] = v;
+  }
+  return cache[device];
+}
+
+struct rf_corpus {
+  int device = 0;
+  uint64_t n = 0, total = 0;
+  uint8_t* d_chars = nullptr;
+  uint32_t* d_off32 = nullptr;
+  uint64_t* d_off64 = nullptr;
+};
+
+struct rf_batch {
+  int device = 0;
+  rf_metric metric = RF_LEVENSHTEIN;
+  std::vector<uint8_t> s1;
+  uint32_t len1 = 0, words = 0;
+  uint8_t* d_blob = nullptr;  // all tables in one allocation
+  QueryView view{};
+};
+
+extern "C" {
+
+void rf_args_default(rf_args* a) {
+  if (!a) return;
+  memset(a, 0, sizeof(*a));
+  a->insertion_cost = a->deletion_cost = a->substitution_cost = 1;
+  a->prefix_weight = 0.1;
+}
+
+const char* rf_status_string(rf_status s) {
+  switch (s) {
+    case RF_OK: return "ok";
+    case RF_ERR_INVALID_ARG: return "invalid argument";
+    case RF_ERR_UNSUPPORTED: return "unsupported";
+    case RF_ERR_CUDA: return "CUDA error";
+    case RF_ERR_OOM: return "out of device memory";
+  }
+  return "unknown";
+}
+const char* rf_last_error(void) { return g_last_error.c_str(); }
+
+int rf_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+uint64_t rf_kernel_launch_count(void) { return kernel_launch_count(); }
+
+int rf_result_is_float(rf_metric metric, rf_kind kind) { return result_is_float((int)metric, (int)kind) ? 1 : 0; }
+
+// ------------------------------------------------------------------------------------------------ corpus
+static rf_status corpus_alloc(rf_corpus* c, bool off64) {
+  // 64 bytes of zeroed slack behind the chars (TMA copies whole 16-byte lines, readers over-read one word);
+  // 16 entries of slack behind the offsets.
+  RF_CUDA(cudaMalloc(&c->d_chars, c->total + 64));
+  RF_CUDA(cudaMemset(c->d_chars + c->total, 0, 64));
+  if (off64) RF_CUDA(cudaMalloc(&c->d_off64, (c->n + 1 + 16) * sizeof(uint64_t)));
+  else RF_CUDA(cudaMalloc(&c->d_off32, (c->n + 1 + 16) * sizeof(uint32_t)));
+  return RF_OK;
+}
+
+__global__ void fill_tail_u32(uint32_t* p, uint64_t from, uint32_t v) { p[from + threadIdx.x] = v; }
+__global__ void fill_tail_u64(uint64_t* p, uint64_t from, uint64_t v) { p[from + threadIdx.x] = v; }
+__global__ void narrow_offsets(const uint64_t* __restrict__ in, uint32_t* __restrict__ out, uint64_t n1) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n1; i += (uint64_t)gridDim.x * blockDim.x)
+    out[i] = (uint32_t)in[i];
+}
+
+static rf_status corpus_finish(rf_corpus* c, cudaStream_t st) {
+  if (c->d_off32) fill_tail_u32<<<1, 16, 0, st>>>(c->d_off32, c->n + 1, (uint32_t)c->total);
+  else fill_tail_u64<<<1, 16, 0, st>>>(c->d_off64, c->n + 1, c->total);
+  RF_CUDA(cudaGetLastError());
+  return RF_OK;
+}
+
+static rf_status corpus_create_host(const uint8_t* chars, const void* offsets, bool in64, uint64_t n, int device,
+                                    rf_corpus** out) {
+  if (!out) return fail(RF_ERR_INVALID_ARG, "out is NULL");
+  *out = nullptr;
+  if (!offsets) return fail(RF_ERR_INVALID_ARG, "offsets is NULL");
+  if (n >= 0xFFFFFFFFull) return fail(RF_ERR_UNSUPPORTED, "more than 2^32-2 candidates in one corpus");
+  const uint64_t first = in64 ? ((const uint64_t*)offsets)[0] : ((const uint32_t*)offsets)[0];
+  const uint64_t total = in64 ? ((const uint64_t*)offsets)[n] : ((const uint32_t*)offsets)[n];
+  if (first != 0) return fail(RF_ERR_INVALID_ARG, "offsets[0] must be 0");
+  if (total && !chars) return fail(RF_ERR_INVALID_ARG, "chars is NULL");
+  if (rf_device_count() <= device || device < 0) return fail(RF_ERR_CUDA, "no such CUDA device");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(RF_ERR_CUDA, "cudaSetDevice failed");
+  rf_corpus* c = new (std::nothrow) rf_corpus();
+  if (!c) return fail(RF_ERR_OOM, "host allocation failed");
+  c->device = device;
+  c->n = n;
+  c->total = total;
+  const bool off64 = total >= 0xFFFFFFF0ull;
+  rf_status s = corpus_alloc(c, off64);
+  if (s != RF_OK) { rf_corpus_destroy(c); return s; }
+  cudaStream_t st;
+  if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { rf_corpus_destroy(c); return fail(RF_ERR_CUDA, "stream"); }
+  cudaError_t e = cudaSuccess;
+  if (total) e = cudaMemcpyAsync(c->d_chars, chars, total, cudaMemcpyHostToDevice, st);
+  uint64_t* tmp64 = nullptr;
+  if (e == cudaSuccess) {
+    if (off64 == in64) {
+      e = cudaMemcpyAsync(off64 ? (void*)c->d_off64 : (void*)c->d_off32, offsets, (n + 1) * (in64 ? 8 : 4),
+                          cudaMemcpyHostToDevice, st);
+    } else if (in64) {  // u64 on the host, u32 on the device: upload then narrow on the GPU
+      e = cudaMalloc(&tmp64, (n + 1) * 8);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(tmp64, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, st);
+      if (e == cudaSuccess) {
+        narrow_offsets<<<1024, 256, 0, st>>>(tmp64, c->d_off32, n + 1);
+        e = cudaGetLastError();
+      }
+    } else {
+      e = cudaErrorInvalidValue;  // u32 host offsets cannot describe >= 4 GiB
+    }
+  }
+  if (e == cudaSuccess) {
+    s = corpus_finish(c, st);
+    if (s == RF_OK) e = cudaStreamSynchronize(st);
+  }
+  if (tmp64) cudaFree(tmp64);
+  cudaStreamDestroy(st);
+  if (e != cudaSuccess) { rf_corpus_destroy(c); return cuda_fail(e, "corpus upload"); }
+  if (s != RF_OK) { rf_corpus_destroy(c); return s; }
+  *out = c;
+  return RF_OK;
+}
+
+rf_status rf_corpus_create_u8(const uint8_t* chars, const uint64_t* offsets, uint64_t n, int device, rf_corpus** out) {
+  return corpus_create_host(chars, offsets, true, n, device, out);
+}
+rf_status rf_corpus_create_u8_off32(const uint8_t* chars, const uint32_t* offsets, uint64_t n, int device, rf_corpus** out) {
+  return corpus_create_host(chars, offsets, false, n, device, out);
+}
+
+rf_status rf_corpus_create_device_u8(const uint8_t* d_chars, const uint64_t* d_offsets, uint64_t n, uint64_t total_chars,
+                                     int device, void* stream, rf_corpus** out) {
+  if (!out) return fail(RF_ERR_INVALID_ARG, "out is NULL");
+  *out = nullptr;
+  if (!d_offsets || (total_chars && !d_chars)) return fail(RF_ERR_INVALID_ARG, "NULL device buffer");
+  if (n >= 0xFFFFFFFFull) return fail(RF_ERR_UNSUPPORTED, "more than 2^32-2 candidates in one corpus");
+  if (rf_device_count() <= device || device < 0) return fail(RF_ERR_CUDA, "no such CUDA device");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(RF_ERR_CUDA, "cudaSetDevice failed");
+  rf_corpus* c = new (std::nothrow) rf_corpus();
+  if (!c) return fail(RF_ERR_OOM, "host allocation failed");
+  c->device = device;
+  c->n = n;
+  c->total = total_chars;
+  const bool off64 = total_chars >= 0xFFFFFFF0ull;
+  rf_status s = corpus_alloc(c, off64);
+  if (s != RF_OK) { rf_corpus_destroy(c); return s; }
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaSuccess;
+  if (total_chars) e = cudaMemcpyAsync(c->d_chars, d_chars, total_chars, cudaMemcpyDeviceToDevice, st);
+  if (e == cudaSuccess) {
+    if (off64) e = cudaMemcpyAsync(c->d_off64, d_offsets, (n + 1) * 8, cudaMemcpyDeviceToDevice, st);
+    else {
+      narrow_offsets<<<1024, 256, 0, st>>>(d_offsets, c->d_off32, n + 1);
+      e = cudaGetLastError();
+    }
+  }
+  if (e == cudaSuccess) {
+    s = corpus_finish(c, st);
+    if (s == RF_OK) e = cudaStreamSynchronize(st);
+  }
+  if (e != cudaSuccess) { rf_corpus_destroy(c); return cuda_fail(e, "corpus device copy"); }
+  if (s != RF_OK) { rf_corpus_destroy(c); return s; }
+  *out = c;
+  return RF_OK;
+}
+
+rf_status rf_corpus_destroy(rf_corpus* c) {
+  if (!c) return RF_OK;
+  DeviceGuard g(c->device);
+  if (c->d_chars) cudaFree(c->d_chars);
+  if (c->d_off32) cudaFree(c->d_off32);
+  if (c->d_off64) cudaFree(c->d_off64);
+  delete c;
+  return RF_OK;
+}
+uint64_t rf_corpus_size(const rf_corpus* c) { return c ? c->n : 0; }
+uint64_t rf_corpus_total_chars(const rf_corpus* c) { return c ? c->total : 0; }
+int rf_corpus_device(const rf_corpus* c) { return c ? c->device : -1; }
+
+// ------------------------------------------------------------------------------------------------ batch
+rf_status rf_batch_create_u8(rf_metric metric, const uint8_t* query, uint32_t query_len, int device, rf_batch** out) {
+  if (!out) return fail(RF_ERR_INVALID_ARG, "out is NULL");
+  *out = nullptr;
+  if ((int)metric < 0 || (int)metric > (int)RF_RATIO) return fail(RF_ERR_INVALID_ARG, "unknown metric");
+  if (query_len && !query) return fail(RF_ERR_INVALID_ARG, "query is NULL");
+  if (query_len > RF_MAX_QUERY_LEN) return fail(RF_ERR_UNSUPPORTED, "query longer than RF_MAX_QUERY_LEN");
+  if ((metric == RF_JARO || metric == RF_JARO_WINKLER) && query_len > 2048)
+    return fail(RF_ERR_UNSUPPORTED, "Jaro / Jaro-Winkler queries longer than 2048 elements");
+  if (rf_device_count() <= device || device < 0) return fail(RF_ERR_CUDA, "no such CUDA device");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(RF_ERR_CUDA, "cudaSetDevice failed");
+  rf_batch* b = new (std::nothrow) rf_batch();
+  if (!b) return fail(RF_ERR_OOM, "host allocation failed");
+  b->device = device;
+  b->metric = metric;
+  b->s1.assign(query, query + query_len);
+  b->len1 = query_len;
+  b->words = (query_len + 63) / 64;
+  // Pattern-match tables (pattern_match_vector.rs:213-224: bit i%64 of PM[ch][i/64] set iff q[i]==ch),
+  // in the layouts the kernels want.  One blob: [tab32_top | tab32_bot | tab64_top | tab64_bot | pm_words]
+  const uint32_t words = b->words ? b->words : 1;
+  const size_t sz32 = 256 * sizeof(uint32_t), sz64 = 256 * sizeof(uint64_t);
+  const size_t szw = (size_t)256 * words * sizeof(uint64_t);
+  std::vector<uint8_t> blob(2 * sz32 + 2 * sz64 + szw, 0);
+  uint32_t* t32t = (uint32_t*)blob.data();
+  uint32_t* t32b = t32t + 256;
+  uint64_t* t64t = (uint64_t*)(blob.data() + 2 * sz32);
+  uint64_t* t64b = t64t + 256;
+  uint64_t* pmw = t64b + 256;
+  for (uint32_t i = 0; i < query_len; ++i) pmw[(size_t)query[i] * words + i / 64] |= 1ull << (i % 64);
+  if (query_len >= 1 && query_len <= 64) {
+    for (int ch = 0; ch < 256; ++ch) {
+      const uint64_t m = pmw[(size_t)ch * words];
+      t64b[ch] = m;
+      t64t[ch] = m << (64 - query_len);
+      if (query_len <= 32) {
+        t32b[ch] = (uint32_t)m;
+        t32t[ch] = (uint32_t)m << (32 - query_len);
+      }
+    }
+  }
+  cudaError_t e = cudaMalloc(&b->d_blob, blob.size());
+  if (e == cudaSuccess) e = cudaMemcpy(b->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { rf_batch_destroy(b); return cuda_fail(e, "query table upload"); }
+  b->view.len1 = b->len1;
+  b->view.words = b->words;
+  b->view.tab32_top = (const uint32_t*)b->d_blob;
+  b->view.tab32_bot = b->view.tab32_top + 256;
+  b->view.tab64_top = (const uint64_t*)(b->d_blob + 2 * sz32);
+  b->view.tab64_bot = b->view.tab64_top + 256;
+  b->view.pm_words = b->view.tab64_bot + 256;
+  *out = b;
+  return RF_OK;
+}
+
+rf_status rf_batch_destroy(rf_batch* b) {
+  if (!b) return RF_OK;
+  DeviceGuard g(b->device);
+  if (b->d_blob) cudaFree(b->d_blob);
+  delete b;
+  return RF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ scoring
+static rf_status make_epi(const rf_batch* b, rf_kind kind, const rf_args* args, Epi* e) {
+  rf_args def;
+  rf_args_default(&def);
+  const rf_args* a = args ? args : &def;
+  memset(e, 0, sizeof(*e));
+  e->metric = (int)b->metric;
+  e->kind = (int)kind;
+  e->has_cutoff = a->has_cutoff ? 1 : 0;
+  e->cutoff_u = a->cutoff_u;
+  e->cutoff_f = a->cutoff_f;
+  e->w_ins = a->insertion_cost;
+  e->w_del = a->deletion_cost;
+  e->w_sub = a->substitution_cost;
+  e->prefix_weight = a->prefix_weight;
+  e->quirks = a->reference_quirks ? 1 : 0;
+  e->wclass = WC_UNIFORM;
+  if (b->metric == RF_LEVENSHTEIN) {  // weight classes of levenshtein.rs:1301-1330
+    if (a->insertion_cost == a->deletion_cost) {
+      if (a->insertion_cost == 0) e->wclass = WC_ZERO;
+      else if (a->insertion_cost == a->substitution_cost) e->wclass = WC_UNIFORM;
+      else if (a->substitution_cost >= a->insertion_cost + a->deletion_cost) e->wclass = WC_INDEL;
+      else return fail(RF_ERR_UNSUPPORTED, "generic Levenshtein weights (Wagner-Fischer route) are not on the GPU path");
+    } else {
+      return fail(RF_ERR_UNSUPPORTED, "generic Levenshtein weights (Wagner-Fischer route) are not on the GPU path");
+    }
+  } else {
+    e->w_ins = e->w_del = e->w_sub = 1;
+  }
+  if (b->metric == RF_RATIO) e->kind = K_NORM_SIMILARITY;  // fuzz.rs:127-149 has one method only
+  return RF_OK;
+}
+
+static rf_status score_device(const rf_batch* b, const rf_corpus* c, rf_kind kind, const rf_args* args, void* out_dev,
+                              bool want_f64, cudaStream_t st) {
+  if (!b || !c) return fail(RF_ERR_INVALID_ARG, "NULL handle");
+  if ((int)kind < 0 || (int)kind > 3) return fail(RF_ERR_INVALID_ARG, "unknown kind");
+  if (b->device != c->device) return fail(RF_ERR_INVALID_ARG, "batch and corpus live on different devices");
+  if ((rf_result_is_float(b->metric, kind) != 0) != want_f64)
+    return fail(RF_ERR_INVALID_ARG, want_f64 ? "this (metric, kind) yields u32 results; use the _u32 entry point"
+                                             : "this (metric, kind) yields f64 results; use the _f64 entry point");
+  if (c->n == 0) return RF_OK;
+  if (!out_dev) return fail(RF_ERR_INVALID_ARG, "out is NULL");
+  ScanLaunch L{};
+  rf_status s = make_epi(b, kind, args, &L.epi);
+  if (s != RF_OK) return s;
+  DeviceGuard g(c->device);
+  if (!g.ok) return fail(RF_ERR_CUDA, "cudaSetDevice failed");
+  L.corpus = CorpusView{c->d_chars, c->d_off32, c->d_off64, c->n, c->total};
+  L.query = b->view;
+  L.out = out_dev;
+  L.out_is_f64 = want_f64 ? 1 : 0;
+  L.stream = st;
+  L.sm_count = sm_count_of(c->device);
+  const Family fam = family_of(L.epi.metric, L.epi.wclass);
+  cudaError_t e;
+  if (b->len1 <= 64) e = launch_scan_w1(L);
+  else if (fam == F_JARO) e = launch_jaro_mw(L);
+  else e = launch_scan_mw(L);
+  if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+  return RF_OK;
+}
+
+static rf_status score_host(const rf_batch* b, const rf_corpus* c, rf_kind kind, const rf_args* args, void* out_host,
+                            bool want_f64) {
+  if (!b || !c) return fail(RF_ERR_INVALID_ARG, "NULL handle");
+  if (c->n == 0) return score_device(b, c, kind, args, nullptr, want_f64, nullptr);
+  if (!out_host) return fail(RF_ERR_INVALID_ARG, "out is NULL");
+  DeviceGuard g(c->device);
+  if (!g.ok) return fail(RF_ERR_CUDA, "cudaSetDevice failed");
+  const size_t bytes = (size_t)c->n * (want_f64 ? 8 : 4);
+  void* d_out = nullptr;
+  RF_CUDA(cudaMalloc(&d_out, bytes));
+  cudaStream_t st;
+  cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { cudaFree(d_out); return cuda_fail(e, "cudaStreamCreate"); }
+  rf_status s = score_device(b, c, kind, args, d_out, want_f64, st);
+  if (s == RF_OK) {
+    e = cudaMemcpyAsync(out_host, d_out, bytes, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) s = cuda_fail(e, "result download");
+  }
+  cudaStreamDestroy(st);
+  cudaFree(d_out);
+  return s;
+}
+
+rf_status rf_batch_score_u32(const rf_batch* b, const rf_corpus* c, rf_kind kind, const rf_args* args, uint32_t* out) {
+  return score_host(b, c, kind, args, out, false);
+}
+rf_status rf_batch_score_f64(const rf_batch* b, const rf_corpus* c, rf_kind kind, const rf_args* args, double* out) {
+  return score_host(b, c, kind, args, out, true);
+}
+rf_status rf_batch_score_u32_device(const rf_batch* b, const rf_corpus* c, rf_kind kind, const rf_args* args,
+                                    uint32_t* out, void* stream) {
+  return score_device(b, c, kind, args, out, false, (cudaStream_t)stream);
+}
+rf_status rf_batch_score_f64_device(const rf_batch* b, const rf_corpus* c, rf_kind kind, const rf_args* args,
+                                    double* out, void* stream) {
+  return score_device(b, c, kind, args, out, true, (cudaStream_t)stream);
+}
+rf_status rf_batch_distance_u32(const rf_batch* b, const rf_corpus* c, const rf_args* a, uint32_t* out) {
+  return score_host(b, c, RF_DISTANCE, a, out, false);
+}
+rf_status rf_batch_similarity_u32(const rf_batch* b, const rf_corpus* c, const rf_args* a, uint32_t* out) {
+  return score_host(b, c, RF_SIMILARITY, a, out, false);
+}
+rf_status rf_batch_distance_f64(const rf_batch* b, const rf_corpus* c, const rf_args* a, double* out) {
+  return score_host(b, c, RF_DISTANCE, a, out, true);
+}
+rf_status rf_batch_similarity_f64(const rf_batch* b, const rf_corpus* c, const rf_args* a, double* out) {
+  return score_host(b, c, RF_SIMILARITY, a, out, true);
+}
+rf_status rf_batch_normalized_distance_f64(const rf_batch* b, const rf_corpus* c, const rf_args* a, double* out) {
+  return score_host(b, c, RF_NORMALIZED_DISTANCE, a, out, true);
+}
+rf_status rf_batch_normalized_similarity_f64(const rf_batch* b, const rf_corpus* c, const rf_args* a, double* out) {
+  return score_host(b, c, RF_NORMALIZED_SIMILARITY, a, out, true);
+}
+
+// ------------------------------------------------------------------------------------------------ cdist
+rf_status rf_cdist_topk_u8_device(const uint8_t*, const uint64_t*, uint32_t, const rf_corpus*, const rf_args*, uint32_t,
+                                  uint32_t*, uint32_t*, void*) {
+  return fail(RF_ERR_UNSUPPORTED, "cdist top-k: not built yet");
+}
+rf_status rf_cdist_topk_u8(const uint8_t*, const uint64_t*, uint32_t, const rf_corpus*, const rf_args*, uint32_t,
+                           uint32_t*, uint32_t*) {
+  return fail(RF_ERR_UNSUPPORTED, "cdist top-k: not built yet");
+}
+
+}  // extern "C"

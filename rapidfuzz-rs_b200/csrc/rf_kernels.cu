@@ -1,0 +1,570 @@
+// rf_kernels.cu -- hand-written sm_100a kernels for the one-vs-many scoring path.
+//
+//  scan_w1_kernel  query <= 64 elements.  One thread per candidate.  A producer warp streams candidate
+//                  tiles (CSR offsets + packed bytes) HBM -> shared memory with TMA bulk copies
+//                  (cp.async.bulk + mbarrier, double buffered); the compute warps bucket the tile's
+//                  candidates by length (shared-memory counting sort) so that the 32 lanes of a warp run
+//                  the same number of Myers/Hyyro steps, look the query's match masks up in a
+//                  lane-replicated (bank-conflict-free) shared-memory table, and write results back
+//                  coalesced.  Integer/bitwise work only -- no tensor cores.
+//  scan_mw_kernel  query > 64 elements.  A sub-warp of G lanes per candidate, lane w owns 64-bit block(s)
+//                  w of the bit-vectors; columns are skewed (lane w handles text char j-w at step j) and
+//                  the horizontal carries (+ the text char itself) travel lane-to-lane in one
+//                  __shfl_up_sync per step.
+//  jaro_mw_kernel  Jaro / Jaro-Winkler with a multi-word query, thread per candidate.
+//  cdist_*         many queries x corpus tile, per-query top-k.
+#include <atomic>
+#include "rf_kernels.cuh"
+
+namespace rfk {
+
+static std::atomic<uint64_t> g_launches{0};
+uint64_t kernel_launch_count() { return g_launches.load(); }
+
+// ------------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// TMA bulk copy global -> shared, completion signalled on an mbarrier (16-byte aligned, size % 16 == 0)
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+template <int NT>
+__device__ __forceinline__ void bar_compute() {  // named barrier 1: the NT compute threads only
+  asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ w1
+struct W1Params {
+  const uint8_t* chars;
+  const uint32_t* off32;
+  const uint64_t* off64;
+  uint64_t n;
+  const void* tab;  // 256 x W compact match table (alignment per family, see QueryView)
+  uint32_t len1;
+  uint32_t T;  // candidates per tile, multiple of 4, <= TMAX
+  uint32_t num_tiles;
+  void* out;
+  int out_f64;
+  Epi epi;
+};
+
+template <class W, int NT, int TMAX, int BCAP>
+struct W1Smem {
+  alignas(16) W pm[256 * 32];            // pm[ch*32 + lane]: every lane owns a bank -> conflict-free gather
+  alignas(16) uint8_t chars[2][BCAP + 32];
+  alignas(16) uint8_t offs[2][(TMAX + 8) * 8];
+  alignas(16) uint64_t res[TMAX];        // staged results (u32 or f64 view)
+  uint32_t hist[256];
+  uint16_t order[TMAX];
+  alignas(8) uint64_t full[2];
+  alignas(8) uint64_t empty[2];
+};
+
+template <int FAM, class W>
+__device__ __forceinline__ void score_one(const W* __restrict__ pm_lane, const uint8_t* base, uint32_t start,
+                                          uint32_t len2, const W1Params& p, uint32_t& ru, double& rf) {
+  auto tab = [&](uint32_t ch) -> W { return pm_lane[ch * 32u]; };
+  if constexpr (FAM == F_JARO) {
+    const uint8_t* b = base + start;
+    auto bytes = [&](uint32_t j) -> uint32_t { return b[j]; };
+    const uint32_t len1 = p.len1;
+    auto jaro = [&](double c) { return jaro_similarity_w1(tab, bytes, len1, len2, c); };
+    if (p.epi.metric == M_JARO) {
+      rf = finish_float(p.epi, jaro);
+    } else {
+      uint32_t prefix = 0;  // common prefix, at most 4 (jaro_winkler.rs:118-123): q[i]==s[i] <=> bit i of PM[s[i]]
+      while (prefix < 4 && prefix < len1 && prefix < len2 && ((tab(bytes(prefix)) >> prefix) & 1u)) ++prefix;
+      const double pw = p.epi.prefix_weight;
+      auto jw = [&](double c) { return jaro_winkler_from(jaro, prefix, pw, c); };
+      rf = finish_float(p.epi, jw);
+    }
+  } else {
+    uint32_t raw;
+    if (p.len1 == 0) {
+      raw = (FAM == F_LCS) ? 0u : len2;
+    } else {
+      ByteReader rd(base, start);
+      if constexpr (FAM == F_LEV) raw = lev_w1<W>(tab, rd, len2, p.len1);
+      else if constexpr (FAM == F_OSA) raw = osa_w1<W>(tab, rd, len2, p.len1);
+      else raw = lcs_w1<W>(tab, rd, len2);
+    }
+    if (p.out_f64) rf = finish_norm(p.epi, raw, p.len1, len2);
+    else ru = finish_int(p.epi, raw, p.len1, len2);
+  }
+}
+
+template <int FAM, class W, int NT, int TMAX, int BCAP>
+__global__ void __launch_bounds__(NT + 32) scan_w1_kernel(const __grid_constant__ W1Params p) {
+  using Smem = W1Smem<W, NT, TMAX, BCAP>;
+  constexpr int CPT = TMAX / NT;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+  const uint32_t tid = threadIdx.x;
+  const bool off64 = p.off64 != nullptr;
+  const uint32_t osz = off64 ? 8u : 4u;
+
+  if (tid == 0) {
+    mbar_init(&S.full[0], 1);
+    mbar_init(&S.full[1], 1);
+    mbar_init(&S.empty[0], 1);
+    mbar_init(&S.empty[1], 1);
+    mbar_fence_init();
+  }
+  // replicate the 256-entry match table 32x: pm[ch*32 + lane]
+  {
+    const W* __restrict__ t = reinterpret_cast<const W*>(p.tab);
+    for (uint32_t i = tid; i < 256u * 32u; i += NT + 32) S.pm[i] = t[i >> 5];
+  }
+  __syncthreads();
+
+  if (tid >= NT) {
+    // ===================== producer warp: one lane streams tiles with TMA bulk copies =====================
+    if (tid != NT) return;
+    uint32_t it = 0;
+    for (uint32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t s = it & 1u;
+      if (it >= 2) mbar_wait(&S.empty[s], ((it >> 1) - 1u) & 1u);
+      const uint64_t t0 = (uint64_t)tile * p.T;
+      const uint32_t tn = (uint32_t)((p.n - t0 < (uint64_t)p.T) ? (p.n - t0) : (uint64_t)p.T);
+      const uint64_t o_lo = off64 ? p.off64[t0] : (uint64_t)p.off32[t0];
+      const uint64_t o_hi = off64 ? p.off64[t0 + tn] : (uint64_t)p.off32[t0 + tn];
+      const uint64_t a0 = o_lo & ~15ull;
+      const uint64_t bytes = ((o_hi + 15ull) & ~15ull) - a0;
+      const uint32_t off_bytes = ((tn + 1u) * osz + 15u) & ~15u;
+      const bool fits = bytes <= (uint64_t)BCAP;
+      const uint32_t tx = off_bytes + ((fits && bytes) ? (uint32_t)bytes : 0u);
+      fence_proxy_async();
+      mbar_expect_tx(&S.full[s], tx);
+      const void* osrc = off64 ? (const void*)(p.off64 + t0) : (const void*)(p.off32 + t0);
+      tma_bulk_g2s(S.offs[s], osrc, off_bytes, &S.full[s]);
+      if (fits && bytes) tma_bulk_g2s(S.chars[s], p.chars + a0, (uint32_t)bytes, &S.full[s]);
+    }
+    return;
+  }
+
+  // ===================== compute warps =====================
+  const uint32_t lane = tid & 31u;
+  const W* __restrict__ pm_lane = S.pm + lane;
+  uint32_t it = 0;
+  for (uint32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    const uint32_t s = it & 1u;
+    const uint64_t t0 = (uint64_t)tile * p.T;
+    const uint32_t tn = (uint32_t)((p.n - t0 < (uint64_t)p.T) ? (p.n - t0) : (uint64_t)p.T);
+    for (uint32_t i = tid; i < 256; i += NT) S.hist[i] = 0;
+    mbar_wait(&S.full[s], (it >> 1) & 1u);
+    const uint8_t* offs = S.offs[s];
+    auto off_at = [&](uint32_t i) -> uint64_t {
+      return off64 ? reinterpret_cast<const uint64_t*>(offs)[i] : (uint64_t) reinterpret_cast<const uint32_t*>(offs)[i];
+    };
+    const uint64_t a0 = off_at(0) & ~15ull;
+    const bool in_smem = (((off_at(tn) + 15ull) & ~15ull) - a0) <= (uint64_t)BCAP;
+    bar_compute<NT>();  // hist zeroed
+
+    // ---- bucket by length: counting sort of the tile's candidates (keys clamp at 255)
+    uint32_t key[CPT], pos[CPT];
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      const uint32_t i = c * NT + tid;
+      if (i < tn) {
+        const uint32_t len = (uint32_t)(off_at(i + 1) - off_at(i));
+        key[c] = len < 255u ? len : 255u;
+        pos[c] = atomicAdd(&S.hist[key[c]], 1u);
+      }
+    }
+    bar_compute<NT>();
+    if (tid < 32) {  // exclusive scan of the 256 bins by one warp
+      uint32_t v[8], sum = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { v[k] = S.hist[tid * 8 + k]; sum += v[k]; }
+      uint32_t incl = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (uint32_t)d) incl += t;
+      }
+      uint32_t run = incl - sum;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { S.hist[tid * 8 + k] = run; run += v[k]; }
+    }
+    bar_compute<NT>();
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      const uint32_t i = c * NT + tid;
+      if (i < tn) S.order[S.hist[key[c]] + pos[c]] = (uint16_t)i;
+    }
+    bar_compute<NT>();
+
+    // ---- score: rank r*NT+tid of the length-sorted order -> a warp's 32 candidates have ~equal length
+    uint32_t* res_u = reinterpret_cast<uint32_t*>(S.res);
+    double* res_f = reinterpret_cast<double*>(S.res);
+    for (uint32_t rank = tid; rank < tn; rank += NT) {
+      const uint32_t i = S.order[rank];
+      const uint64_t o0 = off_at(i);
+      const uint32_t len2 = (uint32_t)(off_at(i + 1) - o0);
+      uint32_t ru = 0;
+      double rf = 0.0;
+      if (in_smem) {
+        score_one<FAM, W>(pm_lane, S.chars[s], (uint32_t)(o0 - a0), len2, p, ru, rf);
+      } else {  // tile larger than the staging buffer (long candidates): read straight from global / L1
+        score_one<FAM, W>(pm_lane, p.chars + (o0 & ~3ull), (uint32_t)(o0 & 3ull), len2, p, ru, rf);
+      }
+      if (p.out_f64) res_f[i] = rf;
+      else res_u[i] = ru;
+    }
+    bar_compute<NT>();  // stage s fully consumed, results staged
+    if (tid == 0) mbar_arrive(&S.empty[s]);
+    if (p.out_f64) {
+      double* out = reinterpret_cast<double*>(p.out) + t0;
+      for (uint32_t i = tid; i < tn; i += NT) out[i] = res_f[i];
+    } else {
+      uint32_t* out = reinterpret_cast<uint32_t*>(p.out) + t0;
+      for (uint32_t i = tid; i < tn; i += NT) out[i] = res_u[i];
+    }
+  }
+}
+
+template <int FAM, class W, int NT, int TMAX, int BCAP>
+static cudaError_t launch_w1_inst(const ScanLaunch& L, const void* tab) {
+  using Smem = W1Smem<W, NT, TMAX, BCAP>;
+  auto kern = scan_w1_kernel<FAM, W, NT, TMAX, BCAP>;
+  const size_t smem = sizeof(Smem);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int ctas_per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, NT + 32, smem);
+  if (e != cudaSuccess) return e;
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+
+  W1Params p{};
+  p.chars = L.corpus.chars;
+  p.off32 = L.corpus.off32;
+  p.off64 = L.corpus.off64;
+  p.n = L.corpus.n;
+  p.tab = tab;
+  p.len1 = L.query.len1;
+  // candidates per tile: keep the average tile ~85% of the staging buffer
+  const double avg = L.corpus.n ? (double)L.corpus.total / (double)L.corpus.n : 0.0;
+  uint64_t T = TMAX;
+  if (avg > 0.0) {
+    const uint64_t fit = (uint64_t)((double)BCAP * 0.85 / avg);
+    if (fit < T) T = fit;
+  }
+  if (T >= NT) T = T / NT * NT;
+  else T = T / 32 * 32;
+  if (T < 32) T = 32;
+  p.T = (uint32_t)T;
+  p.num_tiles = (uint32_t)((L.corpus.n + T - 1) / T);
+  p.out = L.out;
+  p.out_f64 = L.out_is_f64;
+  p.epi = L.epi;
+  uint32_t grid = (uint32_t)L.sm_count * (uint32_t)ctas_per_sm;
+  if (grid > p.num_tiles) grid = p.num_tiles;
+  kern<<<grid, NT + 32, smem, L.stream>>>(p);
+  g_launches.fetch_add(1);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_scan_w1(const ScanLaunch& L) {
+  const Family fam = family_of(L.epi.metric, L.epi.wclass);
+  const bool w32 = L.query.len1 <= 32;
+  // 32-bit words: 32 KB table, 24 KB tiles -> 2 CTAs/SM;  64-bit words: 64 KB table, 48 KB tiles -> 1 CTA/SM
+  switch (fam) {
+    case F_LEV:
+      return w32 ? launch_w1_inst<F_LEV, uint32_t, 256, 512, 24576>(L, L.query.tab32_top)
+                 : launch_w1_inst<F_LEV, uint64_t, 512, 1024, 49152>(L, L.query.tab64_top);
+    case F_OSA:
+      return w32 ? launch_w1_inst<F_OSA, uint32_t, 256, 512, 24576>(L, L.query.tab32_top)
+                 : launch_w1_inst<F_OSA, uint64_t, 512, 1024, 49152>(L, L.query.tab64_top);
+    case F_LCS:
+      return w32 ? launch_w1_inst<F_LCS, uint32_t, 256, 512, 24576>(L, L.query.tab32_bot)
+                 : launch_w1_inst<F_LCS, uint64_t, 512, 1024, 49152>(L, L.query.tab64_bot);
+    default:
+      return launch_w1_inst<F_JARO, uint64_t, 512, 1024, 49152>(L, L.query.tab64_bot);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ mw
+struct MwParams {
+  const uint8_t* chars;
+  const uint32_t* off32;
+  const uint64_t* off64;
+  uint64_t n;
+  const uint64_t* pm;  // [256][words]
+  uint32_t len1;
+  uint32_t words;
+  uint32_t G;  // lanes per candidate (power of two, <= 32)
+  void* out;
+  int out_f64;
+  Epi epi;
+};
+
+template <int FAM, int WPL>
+__global__ void __launch_bounds__(256) scan_mw_kernel(const __grid_constant__ MwParams p) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t G = p.G;
+  const uint32_t gl = lane & (G - 1u);       // lane within the candidate's group
+  const uint32_t gpw = 32u / G;              // groups (candidates) per warp
+  const uint32_t sub = lane / G;
+  const uint64_t warp_global = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const uint64_t total_groups = (uint64_t)gridDim.x * (blockDim.x >> 5) * gpw;
+  const uint32_t words = p.words;
+  const uint32_t w0 = gl * WPL;                                // first 64-bit block owned by this lane
+  const uint32_t act = (words + WPL - 1) / WPL;                // lanes that own at least one block
+  const uint32_t last_owner = (words - 1) / WPL, last_k = (words - 1) % WPL;
+  const uint32_t last_bit = (p.len1 - 1u) & 63u;
+  const bool off64 = p.off64 != nullptr;
+  const uint64_t* __restrict__ pm = p.pm;
+
+  for (uint64_t cw = warp_global * gpw; cw < p.n; cw += total_groups) {  // warp-uniform trip count
+    const uint64_t c = cw + sub;
+    const bool valid = c < p.n;
+    uint64_t o0 = 0;
+    uint32_t len2 = 0;
+    if (valid) {
+      o0 = off64 ? p.off64[c] : (uint64_t)p.off32[c];
+      const uint64_t o1 = off64 ? p.off64[c + 1] : (uint64_t)p.off32[c + 1];
+      len2 = (uint32_t)(o1 - o0);
+    }
+    // |len1-len2| already exceeds the cutoff -> None without touching the bytes (levenshtein.rs:1045-1047)
+    bool skip = false;
+    if (FAM == F_LEV && p.epi.metric == M_LEVENSHTEIN && p.epi.kind == K_DISTANCE && p.epi.has_cutoff) {
+      const uint64_t diff = p.len1 > len2 ? p.len1 - len2 : len2 - p.len1;
+      skip = diff * p.epi.w_ins > p.epi.cutoff_u;
+    }
+    const uint8_t* __restrict__ txt = p.chars + o0;
+    const uint32_t my_steps = (valid && !skip && len2) ? len2 + act - 1u : 0u;
+    const uint32_t steps = __reduce_max_sync(0xffffffffu, my_steps);
+
+    uint64_t VP[WPL], VN[WPL], D0[WPL], PMo[WPL], Xc[WPL], Xn[WPL];
+#pragma unroll
+    for (int k = 0; k < WPL; ++k) {
+      VP[k] = (FAM == F_LCS) ? ~0ull : ~0ull;  // LCS: VP plays the role of S
+      VN[k] = 0; D0[k] = 0; PMo[k] = 0; Xc[k] = 0; Xn[k] = 0;
+    }
+    int32_t score = 0;
+    // lane 0 of a group feeds the text: ch_cur = text[t], two bytes prefetched ahead
+    uint32_t ch_cur = 0, c1 = 0, c2 = 0;
+    if (gl == 0 && my_steps) {
+      ch_cur = txt[0];
+      c1 = len2 > 1 ? txt[1] : 0;
+      c2 = len2 > 2 ? txt[2] : 0;
+#pragma unroll
+      for (int k = 0; k < WPL; ++k) Xc[k] = (w0 + k < words) ? __ldg(pm + (uint64_t)ch_cur * words + w0 + k) : 0ull;
+    }
+    uint32_t cout = 0;
+    for (uint32_t t = 0; t < steps; ++t) {
+      const uint32_t pk_in = __shfl_up_sync(0xffffffffu, ch_cur | (cout << 8), 1, G);
+      uint32_t ch_nxt, cin;
+      if (gl == 0) {
+        ch_nxt = c1;
+        c1 = c2;
+        c2 = (t + 3 < len2) ? (uint32_t)txt[t + 3] : 0u;
+        cin = (FAM == F_LCS) ? 0u : 1u;  // Levenshtein/OSA: +1 horizontal delta enters row 0; LCS: no carry
+      } else {
+        ch_nxt = pk_in & 0xffu;
+        cin = pk_in >> 8;
+      }
+      // this lane's match words for the NEXT step (text char flows one step ahead of the carries)
+#pragma unroll
+      for (int k = 0; k < WPL; ++k) Xn[k] = (w0 + k < words) ? __ldg(pm + (uint64_t)ch_nxt * words + w0 + k) : 0ull;
+
+      const int32_t j = (int32_t)t - (int32_t)gl;  // text column handled by this lane in this step
+      const bool active = (gl < act) && j >= 0 && j < (int32_t)len2 && my_steps;
+      if (active) {
+        if constexpr (FAM == F_LCS) {
+          uint64_t carry = cin & 1u;
+#pragma unroll
+          for (int k = 0; k < WPL; ++k) {
+            const uint64_t S = VP[k];
+            const uint64_t u = S & Xc[k];
+            const uint64_t x1 = S + u;
+            const uint64_t x2 = x1 + carry;
+            carry = (uint64_t)(x1 < S) | (uint64_t)(x2 < x1);
+            VP[k] = x2 | (S - u);
+          }
+          cout = (uint32_t)carry;
+        } else {
+          uint64_t hp_c = cin & 1u, hn_c = (cin >> 1) & 1u, tr_c = (cin >> 2) & 1u;
+#pragma unroll
+          for (int k = 0; k < WPL; ++k) {
+            const uint64_t X0 = Xc[k];
+            const uint64_t X = X0 | hn_c;
+            uint64_t d0 = ((((X & VP[k]) + VP[k]) ^ VP[k]) | X) | VN[k];
+            if constexpr (FAM == F_OSA) {
+              const uint64_t nd = (~D0[k]) & X0;
+              d0 |= ((nd << 1) | tr_c) & PMo[k];
+              tr_c = nd >> 63;
+              D0[k] = d0;
+              PMo[k] = X0;
+            }
+            uint64_t HP = VN[k] | ~(d0 | VP[k]);
+            uint64_t HN = d0 & VP[k];
+            if (gl == last_owner && k == (int)last_k)
+              score += (int32_t)((HP >> last_bit) & 1u) - (int32_t)((HN >> last_bit) & 1u);
+            const uint64_t hp_o = HP >> 63, hn_o = HN >> 63;
+            HP = (HP << 1) | hp_c;
+            HN = (HN << 1) | hn_c;
+            VP[k] = HN | ~(d0 | HP);
+            VN[k] = HP & d0;
+            hp_c = hp_o;
+            hn_c = hn_o;
+          }
+          cout = (uint32_t)hp_c | ((uint32_t)hn_c << 1) | ((uint32_t)tr_c << 2);
+        }
+      }
+      ch_cur = ch_nxt;
+#pragma unroll
+      for (int k = 0; k < WPL; ++k) Xc[k] = Xn[k];
+    }
+
+    // ---- result
+    uint32_t raw;
+    if constexpr (FAM == F_LCS) {
+      uint32_t cnt = 0;
+#pragma unroll
+      for (int k = 0; k < WPL; ++k)
+        if (w0 + k < words) cnt += (uint32_t)__popcll(~VP[k]);
+      for (uint32_t d = G >> 1; d >= 1; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d, G);
+      raw = cnt;
+    } else {
+      const int32_t sc = __shfl_sync(0xffffffffu, score, last_owner, G);
+      raw = (uint32_t)((int32_t)p.len1 + sc);
+      if (len2 == 0) raw = p.len1;
+    }
+    if (valid && gl == 0) {
+      if (skip) {
+        if (p.out_f64) reinterpret_cast<double*>(p.out)[c] = qnan();
+        else reinterpret_cast<uint32_t*>(p.out)[c] = NONE_U32;
+      } else if (p.out_f64) {
+        reinterpret_cast<double*>(p.out)[c] = finish_norm(p.epi, raw, p.len1, len2);
+      } else {
+        reinterpret_cast<uint32_t*>(p.out)[c] = finish_int(p.epi, raw, p.len1, len2);
+      }
+    }
+  }
+}
+
+template <int FAM>
+static cudaError_t launch_mw_fam(const ScanLaunch& L) {
+  MwParams p{};
+  p.chars = L.corpus.chars;
+  p.off32 = L.corpus.off32;
+  p.off64 = L.corpus.off64;
+  p.n = L.corpus.n;
+  p.pm = L.query.pm_words;
+  p.len1 = L.query.len1;
+  p.words = L.query.words;
+  p.out = L.out;
+  p.out_f64 = L.out_is_f64;
+  p.epi = L.epi;
+  // blocks per lane: 1 up to 32 blocks (2048 elements), then 2/4/8 (RF_MAX_QUERY_LEN = 16384)
+  int wpl = 1;
+  while ((uint32_t)wpl * 32u < p.words) wpl <<= 1;
+  if (wpl > 8) return cudaErrorInvalidValue;
+  const uint32_t act = (p.words + wpl - 1) / wpl;
+  uint32_t G = 1;
+  while (G < act) G <<= 1;
+  p.G = G;
+  const uint32_t gpw = 32u / G, warps_per_block = 8;
+  const uint64_t warps_needed = (p.n + gpw - 1) / gpw;
+  uint64_t blocks = (warps_needed + warps_per_block - 1) / warps_per_block;
+  const uint64_t max_blocks = (uint64_t)L.sm_count * 8;  // 8 x 256 threads = 2048 threads / SM
+  if (blocks > max_blocks) blocks = max_blocks;
+  if (blocks < 1) blocks = 1;
+  switch (wpl) {
+    case 1: scan_mw_kernel<FAM, 1><<<(uint32_t)blocks, 256, 0, L.stream>>>(p); break;
+    case 2: scan_mw_kernel<FAM, 2><<<(uint32_t)blocks, 256, 0, L.stream>>>(p); break;
+    case 4: scan_mw_kernel<FAM, 4><<<(uint32_t)blocks, 256, 0, L.stream>>>(p); break;
+    default: scan_mw_kernel<FAM, 8><<<(uint32_t)blocks, 256, 0, L.stream>>>(p); break;
+  }
+  g_launches.fetch_add(1);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_scan_mw(const ScanLaunch& L) {
+  switch (family_of(L.epi.metric, L.epi.wclass)) {
+    case F_LEV: return launch_mw_fam<F_LEV>(L);
+    case F_OSA: return launch_mw_fam<F_OSA>(L);
+    case F_LCS: return launch_mw_fam<F_LCS>(L);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ jaro mw
+template <int MAXQ>
+__global__ void __launch_bounds__(128) jaro_mw_kernel(const __grid_constant__ MwParams p) {
+  const bool off64 = p.off64 != nullptr;
+  const uint64_t* __restrict__ pm = p.pm;
+  const uint32_t words = p.words;
+  for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < p.n; c += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t o0 = off64 ? p.off64[c] : (uint64_t)p.off32[c];
+    const uint64_t o1 = off64 ? p.off64[c + 1] : (uint64_t)p.off32[c + 1];
+    const uint32_t len2 = (uint32_t)(o1 - o0);
+    const uint8_t* __restrict__ txt = p.chars + o0;
+    auto pmw = [&](uint32_t w, uint32_t ch) -> uint64_t { return __ldg(pm + (uint64_t)ch * words + w); };
+    auto bytes = [&](uint32_t j) -> uint32_t { return txt[j]; };
+    const uint32_t len1 = p.len1;
+    auto jaro = [&](double cut) { return jaro_similarity_generic<MAXQ>(pmw, bytes, len1, len2, cut); };
+    double r;
+    if (p.epi.metric == M_JARO) {
+      r = finish_float(p.epi, jaro);
+    } else {
+      uint32_t prefix = 0;
+      while (prefix < 4 && prefix < len1 && prefix < len2 && ((pmw(0u, bytes(prefix)) >> prefix) & 1u)) ++prefix;
+      const double pw = p.epi.prefix_weight;
+      auto jw = [&](double cut) { return jaro_winkler_from(jaro, prefix, pw, cut); };
+      r = finish_float(p.epi, jw);
+    }
+    reinterpret_cast<double*>(p.out)[c] = r;
+  }
+}
+
+cudaError_t launch_jaro_mw(const ScanLaunch& L) {
+  MwParams p{};
+  p.chars = L.corpus.chars;
+  p.off32 = L.corpus.off32;
+  p.off64 = L.corpus.off64;
+  p.n = L.corpus.n;
+  p.pm = L.query.pm_words;
+  p.len1 = L.query.len1;
+  p.words = L.query.words;
+  p.out = L.out;
+  p.out_f64 = 1;
+  p.epi = L.epi;
+  uint64_t blocks = (p.n + 127) / 128;
+  const uint64_t max_blocks = (uint64_t)L.sm_count * 8;
+  if (blocks > max_blocks) blocks = max_blocks;
+  if (p.len1 <= 256) jaro_mw_kernel<256><<<(uint32_t)blocks, 128, 0, L.stream>>>(p);
+  else if (p.len1 <= 2048) jaro_mw_kernel<2048><<<(uint32_t)blocks, 128, 0, L.stream>>>(p);
+  else return cudaErrorInvalidValue;
+  g_launches.fetch_add(1);
+  return cudaGetLastError();
+}
+
+}  // namespace rfk

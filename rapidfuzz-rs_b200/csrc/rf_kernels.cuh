@@ -1,0 +1,68 @@
+// rf_kernels.cuh -- launch-side view of the sm_100a scoring kernels (rf_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "rf_core.cuh"
+
+namespace rfk {
+
+// Packed corpus resident in HBM (CSR).  `chars` is 16-byte aligned and has >= 64 bytes of zeroed slack
+// behind the data; the offset array has >= 16 entries of slack (TMA bulk copies move 16-byte multiples).
+struct CorpusView {
+  const uint8_t* chars;
+  const uint32_t* off32;  // exactly one of off32/off64 is non-null
+  const uint64_t* off64;
+  uint64_t n;
+  uint64_t total;
+};
+
+// One cached query (BatchComparator::new): compact match tables in device memory.
+struct QueryView {
+  uint32_t len1;
+  uint32_t words;            // ceil(len1/64)
+  const uint32_t* tab32_top; // [256] PM << (32-len1)   (len1 <= 32)   Levenshtein / OSA
+  const uint32_t* tab32_bot; // [256] PM                (len1 <= 32)   LCS family
+  const uint64_t* tab64_top; // [256] PM << (64-len1)   (len1 <= 64)
+  const uint64_t* tab64_bot; // [256] PM                (len1 <= 64)   LCS family, Jaro
+  const uint64_t* pm_words;  // [256][words] row-major (pattern_match_vector.rs layout), any len1
+};
+
+struct ScanLaunch {
+  CorpusView corpus;
+  QueryView query;
+  Epi epi;
+  void* out;          // uint32_t[n] or double[n]
+  int out_is_f64;
+  cudaStream_t stream;
+  int sm_count;
+};
+
+// Single-word path (query <= 64): thread per candidate over TMA-staged, length-bucketed tiles.
+cudaError_t launch_scan_w1(const ScanLaunch& L);
+// Multi-word path (query > 64): sub-warp per candidate, carries propagated with warp shuffles.
+cudaError_t launch_scan_mw(const ScanLaunch& L);
+// Jaro / Jaro-Winkler with a multi-word query (65..2048).
+cudaError_t launch_jaro_mw(const ScanLaunch& L);
+
+// many-vs-many Levenshtein top-k (queries <= 64).
+struct CdistLaunch {
+  CorpusView corpus;
+  const uint64_t* q_tab64_top;  // [nq][256] top-aligned 64-bit tables
+  const uint32_t* q_len;        // [nq]
+  uint32_t nq;
+  uint32_t k;
+  int has_cutoff;
+  uint32_t cutoff;
+  uint32_t* out_idx;   // [nq][k]
+  uint32_t* out_dist;  // [nq][k]
+  unsigned long long* scratch;  // [nq][parts][k] packed (dist<<32|idx) partial results
+  uint32_t parts;
+  cudaStream_t stream;
+  int sm_count;
+};
+cudaError_t launch_cdist_topk(const CdistLaunch& L);
+uint32_t cdist_parts(int sm_count);
+
+uint64_t kernel_launch_count();
+
+}  // namespace rfk

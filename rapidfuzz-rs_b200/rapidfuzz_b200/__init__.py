@@ -1,0 +1,9 @@
+"""rapidfuzz_b200 -- host-side mirror of the rapidfuzz-rs `distance::*::BatchComparator` / `fuzz::*` API
+over the B200 CUDA engine (librfgpu.so, C ABI in include/rfgpu.h).  No CPU fallback."""
+from . import _ffi
+from ._scorer import Args
+from .corpus import Corpus, synth_corpus, synth_query
+from . import distance, fuzz
+
+RfError = _ffi.RfError
+__all__ = ["Args", "Corpus", "RfError", "distance", "fuzz", "synth_corpus", "synth_query"]

@@ -1,0 +1,94 @@
+"""ctypes view of the C ABI in include/rfgpu.h (librfgpu.so, built in-tree by rapidfuzz-rs_b200/build.py).
+
+There is no CPU fallback: if the shared library is missing it is built; if it cannot be loaded, or no CUDA
+device is usable, the compute entry points raise RfError."""
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+LIB_PATH = os.path.join(_ROOT, "lib", "librfgpu.so")
+
+RF_OK, RF_ERR_INVALID_ARG, RF_ERR_UNSUPPORTED, RF_ERR_CUDA, RF_ERR_OOM = range(5)
+METRICS = {"levenshtein": 0, "indel": 1, "lcs_seq": 2, "osa": 3, "jaro": 4, "jaro_winkler": 5, "ratio": 6}
+KINDS = {"distance": 0, "similarity": 1, "normalized_distance": 2, "normalized_similarity": 3}
+NONE_U32 = 0xFFFFFFFF
+RF_MAX_QUERY_LEN = 16384
+
+
+class RfArgs(C.Structure):
+    _fields_ = [("has_cutoff", C.c_uint8), ("cutoff_u", C.c_uint64), ("cutoff_f", C.c_double),
+                ("has_hint", C.c_uint8), ("hint_u", C.c_uint64), ("hint_f", C.c_double),
+                ("insertion_cost", C.c_uint64), ("deletion_cost", C.c_uint64), ("substitution_cost", C.c_uint64),
+                ("prefix_weight", C.c_double), ("reference_quirks", C.c_uint8)]
+
+
+class RfError(RuntimeError):
+    def __init__(self, status, detail):
+        super().__init__("rfgpu status %d: %s" % (status, detail))
+        self.status = status
+
+
+# every symbol include/rfgpu.h declares: name -> (restype, argtypes)
+_vp, _u64, _u32, _int = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
+_PA = C.POINTER(RfArgs)
+SYMBOLS = {
+    "rf_args_default": (None, [_PA]),
+    "rf_status_string": (C.c_char_p, [_int]),
+    "rf_last_error": (C.c_char_p, []),
+    "rf_device_count": (_int, []),
+    "rf_corpus_create_u8": (_int, [_vp, _vp, _u64, _int, C.POINTER(_vp)]),
+    "rf_corpus_create_u8_off32": (_int, [_vp, _vp, _u64, _int, C.POINTER(_vp)]),
+    "rf_corpus_create_device_u8": (_int, [_vp, _vp, _u64, _u64, _int, _vp, C.POINTER(_vp)]),
+    "rf_corpus_destroy": (_int, [_vp]),
+    "rf_corpus_size": (_u64, [_vp]),
+    "rf_corpus_total_chars": (_u64, [_vp]),
+    "rf_corpus_device": (_int, [_vp]),
+    "rf_batch_create_u8": (_int, [_int, _vp, _u32, _int, C.POINTER(_vp)]),
+    "rf_batch_destroy": (_int, [_vp]),
+    "rf_batch_score_u32": (_int, [_vp, _vp, _int, _PA, _vp]),
+    "rf_batch_score_f64": (_int, [_vp, _vp, _int, _PA, _vp]),
+    "rf_batch_score_u32_device": (_int, [_vp, _vp, _int, _PA, _vp, _vp]),
+    "rf_batch_score_f64_device": (_int, [_vp, _vp, _int, _PA, _vp, _vp]),
+    "rf_result_is_float": (_int, [_int, _int]),
+    "rf_batch_distance_u32": (_int, [_vp, _vp, _PA, _vp]),
+    "rf_batch_similarity_u32": (_int, [_vp, _vp, _PA, _vp]),
+    "rf_batch_distance_f64": (_int, [_vp, _vp, _PA, _vp]),
+    "rf_batch_similarity_f64": (_int, [_vp, _vp, _PA, _vp]),
+    "rf_batch_normalized_distance_f64": (_int, [_vp, _vp, _PA, _vp]),
+    "rf_batch_normalized_similarity_f64": (_int, [_vp, _vp, _PA, _vp]),
+    "rf_cdist_topk_u8": (_int, [_vp, _vp, _u32, _vp, _PA, _u32, _vp, _vp]),
+    "rf_cdist_topk_u8_device": (_int, [_vp, _vp, _u32, _vp, _PA, _u32, _vp, _vp, _vp]),
+    "rf_synth_query_u8": (_int, [_u64, _u32, _vp]),
+    "rf_synth_corpus_u8": (_int, [_u64, _vp, _u32, _u64, _u32, _u32, _u32, _vp, _vp, _int]),
+    "rf_kernel_launch_count": (_u64, []),
+}
+
+_lib = None
+
+
+def build():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_rf_build", os.path.join(_ROOT, "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.build()
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            f = getattr(l, name)
+            f.restype = res
+            f.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(status):
+    if status != RF_OK:
+        raise RfError(status, lib().rf_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,175 @@
+"""Shared machinery of the per-metric BatchComparator mirrors."""
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi
+from .corpus import Corpus
+
+
+class Args:
+    """Mirror of the reference's per-metric `Args` builder (levenshtein.rs:86-126, jaro_winkler.rs:25-62,
+    lcs_seq.rs / indel.rs / osa.rs / jaro.rs / fuzz.rs equivalents): Args().score_cutoff(x).score_hint(y)
+    [.weights(ins, del, sub)] [.prefix_weight(w)].  With a score_cutoff the result carries `None`
+    (masked) entries, exactly where the reference returns Option::None."""
+
+    def __init__(self):
+        self._cutoff = None
+        self._hint = None
+        self._weights = (1, 1, 1)
+        self._prefix_weight = 0.1
+        self._quirks = False
+
+    def _copy(self):
+        a = type(self)()
+        a.__dict__.update(self.__dict__)
+        return a
+
+    def score_cutoff(self, v):
+        a = self._copy()
+        a._cutoff = v
+        return a
+
+    def score_hint(self, v):
+        a = self._copy()
+        a._hint = v
+        return a
+
+    def weights(self, insertion_cost=1, deletion_cost=1, substitution_cost=1):
+        a = self._copy()
+        a._weights = (insertion_cost, deletion_cost, substitution_cost)
+        return a
+
+    def prefix_weight(self, w):
+        a = self._copy()
+        a._prefix_weight = w
+        return a
+
+    def reference_quirks(self, on=True):
+        a = self._copy()
+        a._quirks = on
+        return a
+
+    def _c(self, is_float):
+        r = _ffi.RfArgs()
+        _ffi.lib().rf_args_default(C.byref(r))
+        r.insertion_cost, r.deletion_cost, r.substitution_cost = self._weights
+        r.prefix_weight = self._prefix_weight
+        r.reference_quirks = 1 if self._quirks else 0
+        if self._cutoff is not None:
+            r.has_cutoff = 1
+            if is_float:
+                r.cutoff_f = float(self._cutoff)
+            else:
+                r.cutoff_u = min(int(self._cutoff), 2**64 - 1)
+        if self._hint is not None:
+            r.has_hint = 1
+            if is_float:
+                r.hint_f = float(self._hint)
+            else:
+                r.hint_u = min(int(self._hint), 2**64 - 1)
+        return r
+
+
+def _as_query(q):
+    if isinstance(q, str):
+        q = q.encode("latin-1")
+    if isinstance(q, (bytes, bytearray)):
+        return np.frombuffer(bytes(q), dtype=np.uint8)
+    return np.ascontiguousarray(q, dtype=np.uint8)
+
+
+class BatchComparatorBase:
+    """`BatchComparator::new(query)` of one metric module: caches the query and its pattern-match bit
+    table on the GPU; every scoring method takes a Corpus (one-vs-many in one launch) or a single
+    candidate (bytes/str, returns a scalar like the reference)."""
+    METRIC = None
+
+    def __init__(self, query, device=0):
+        q = _as_query(query)
+        h = C.c_void_p()
+        _ffi.check(_ffi.lib().rf_batch_create_u8(_ffi.METRICS[self.METRIC], q.ctypes.data, len(q), device, C.byref(h)))
+        self._h = h
+        self.device = device
+        self.query = q
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _ffi.lib().rf_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _score(self, kind, s2, args):
+        args = args if args is not None else Args()
+        single = not isinstance(s2, Corpus)
+        corpus = Corpus.from_strings([s2], self.device) if single else s2
+        is_f = bool(_ffi.lib().rf_result_is_float(_ffi.METRICS[self.METRIC], _ffi.KINDS[kind]))
+        ca = args._c(is_f)
+        n = len(corpus)
+        out = np.empty(n, dtype=np.float64 if is_f else np.uint32)
+        fn = _ffi.lib().rf_batch_score_f64 if is_f else _ffi.lib().rf_batch_score_u32
+        _ffi.check(fn(self._h, corpus._h, _ffi.KINDS[kind], C.byref(ca), out.ctypes.data))
+        has_cutoff = args._cutoff is not None
+        if single:
+            v = out[0]
+            if is_f:
+                return None if np.isnan(v) else float(v)
+            return None if (has_cutoff and v == _ffi.NONE_U32) else int(v)
+        if not has_cutoff:
+            return out
+        mask = np.isnan(out) if is_f else (out == _ffi.NONE_U32)
+        return np.ma.MaskedArray(out, mask=mask)
+
+    def score_into(self, kind, corpus, out_ptr, args=None, stream=0):
+        """Device-pointer variant (rf_batch_score_*_device): results stay on the GPU at `out_ptr`
+        (u32[n] or f64[n]); enqueued on `stream` (a cudaStream_t as int), no synchronisation."""
+        args = args if args is not None else Args()
+        is_f = bool(_ffi.lib().rf_result_is_float(_ffi.METRICS[self.METRIC], _ffi.KINDS[kind]))
+        ca = args._c(is_f)
+        fn = _ffi.lib().rf_batch_score_f64_device if is_f else _ffi.lib().rf_batch_score_u32_device
+        _ffi.check(fn(self._h, corpus._h, _ffi.KINDS[kind], C.byref(ca), out_ptr, stream))
+
+    # --- the reference's method set (e.g. levenshtein.rs:1660-1817)
+    def distance(self, s2):
+        return self._score("distance", s2, None)
+
+    def distance_with_args(self, s2, args):
+        return self._score("distance", s2, args)
+
+    def similarity(self, s2):
+        return self._score("similarity", s2, None)
+
+    def similarity_with_args(self, s2, args):
+        return self._score("similarity", s2, args)
+
+    def normalized_distance(self, s2):
+        return self._score("normalized_distance", s2, None)
+
+    def normalized_distance_with_args(self, s2, args):
+        return self._score("normalized_distance", s2, args)
+
+    def normalized_similarity(self, s2):
+        return self._score("normalized_similarity", s2, None)
+
+    def normalized_similarity_with_args(self, s2, args):
+        return self._score("normalized_similarity", s2, args)
+
+
+def make_module(metric):
+    cls = type("BatchComparator", (BatchComparatorBase,), {"METRIC": metric, "__doc__": BatchComparatorBase.__doc__})
+
+    def _free(kind):
+        def f(s1, s2, args=None, device=0):
+            b = cls(s1, device)
+            try:
+                return b._score(kind, s2, args)
+            finally:
+                b.close()
+        f.__name__ = kind
+        return f
+    return cls, {k: _free(k) for k in _ffi.KINDS}

@@ -1,0 +1,93 @@
+"""Packed candidate corpus resident in one GPU's HBM (CSR: chars u8[total] + offsets[n+1]).
+
+New on this side: the reference consumes one candidate iterator per call
+(levenshtein.rs:1750-1762); here the candidates are uploaded once and scored by whole-corpus kernels."""
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi
+
+
+class Corpus:
+    def __init__(self, chars, offsets, device=0):
+        """chars: uint8 array/bytes of all candidates back to back; offsets: n+1 CSR starts (u32 or u64)."""
+        chars = np.ascontiguousarray(np.frombuffer(chars, dtype=np.uint8) if isinstance(chars, (bytes, bytearray)) else chars,
+                                     dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets)
+        if offsets.dtype not in (np.uint32, np.uint64):
+            offsets = offsets.astype(np.uint64)
+        n = len(offsets) - 1
+        if n < 0:
+            raise ValueError("offsets needs n+1 entries")
+        h = C.c_void_p()
+        fn = _ffi.lib().rf_corpus_create_u8 if offsets.dtype == np.uint64 else _ffi.lib().rf_corpus_create_u8_off32
+        _ffi.check(fn(chars.ctypes.data, offsets.ctypes.data, n, device, C.byref(h)))
+        self._h = h
+        self.device = device
+
+    @classmethod
+    def from_strings(cls, strings, device=0):
+        bs = [s.encode("latin-1") if isinstance(s, str) else bytes(s) for s in strings]
+        offsets = np.zeros(len(bs) + 1, dtype=np.uint64)
+        if bs:
+            offsets[1:] = np.cumsum([len(b) for b in bs])
+        return cls(np.frombuffer(b"".join(bs), dtype=np.uint8), offsets, device)
+
+    @classmethod
+    def from_device(cls, chars_ptr, offsets_ptr, n, total_chars, device=0, stream=0):
+        """Adopt (copy) buffers already on `device`: raw device pointers, e.g. torch tensor .data_ptr();
+        offsets are u64."""
+        self = cls.__new__(cls)
+        h = C.c_void_p()
+        _ffi.check(_ffi.lib().rf_corpus_create_device_u8(chars_ptr, offsets_ptr, n, total_chars, device, stream, C.byref(h)))
+        self._h = h
+        self.device = device
+        return self
+
+    def __len__(self):
+        return int(_ffi.lib().rf_corpus_size(self._h))
+
+    @property
+    def total_chars(self):
+        return int(_ffi.lib().rf_corpus_total_chars(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _ffi.lib().rf_corpus_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def synth_query(seed, length):
+    out = np.empty(length, dtype=np.uint8)
+    _ffi.check(_ffi.lib().rf_synth_query_u8(seed, length, out.ctypes.data))
+    return out
+
+
+def synth_corpus(seed, query, n, min_len, max_len, kmax, nthreads=0, pinned=False):
+    """Deterministic synthetic candidates. Returns (chars u8, offsets u64)."""
+    query = np.ascontiguousarray(query, dtype=np.uint8)
+    l = _ffi.lib()
+    if pinned:
+        import torch
+        offsets_t = torch.empty(n + 1, dtype=torch.int64).pin_memory()
+        offsets = offsets_t.numpy().view(np.uint64)
+    else:
+        offsets = np.empty(n + 1, dtype=np.uint64)
+    _ffi.check(l.rf_synth_corpus_u8(seed, query.ctypes.data, len(query), n, min_len, max_len, kmax,
+                                    offsets.ctypes.data, None, nthreads))
+    total = int(offsets[n])
+    if pinned:
+        chars_t = torch.empty(max(total, 1), dtype=torch.uint8).pin_memory()
+        chars = chars_t.numpy()[:total]
+    else:
+        chars = np.empty(total, dtype=np.uint8)
+    _ffi.check(l.rf_synth_corpus_u8(seed, query.ctypes.data, len(query), n, min_len, max_len, kmax,
+                                    offsets.ctypes.data, chars.ctypes.data, nthreads))
+    return chars, offsets

@@ -74,4 +74,4 @@ def check(metric, kind, query, chars, offsets, corpus=None, **kw):
         if own:
             corpus.close()
     exp = orc.batch(metric, kind, query, chars, offsets, nthreads=0, **kw)
-    assert_same(got, exp, (metric, kind, bytes(np.asarray(query, dtype=np.uint8))[:40], kw))
+    assert_same(got, exp, (metric, kind, bytes(query)[:40], kw))

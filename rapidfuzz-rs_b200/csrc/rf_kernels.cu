@@ -14,6 +14,7 @@
 //  jaro_mw_kernel  Jaro / Jaro-Winkler with a multi-word query, thread per candidate.
 //  cdist_*         many queries x corpus tile, per-query top-k.
 #include <atomic>
+#include <cstdlib>
 #include "rf_kernels.cuh"
 
 namespace rfk {
@@ -46,6 +47,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// same, but lets the hardware suspend the thread between polls (producer lane: must not burn issue slots)
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity), "r"(1000000u)
+      : "memory");
+}
 // TMA bulk copy global -> shared, completion signalled on an mbarrier (16-byte aligned, size % 16 == 0)
 __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -71,6 +86,7 @@ struct W1Params {
   uint32_t num_tiles;
   void* out;
   int out_f64;
+  uint32_t two;  // the constant 2, opaque to ptxas: keeps x*2+1 an IMAD (FMA pipe) instead of an ALU-pipe LEA
   Epi epi;
 };
 
@@ -86,7 +102,49 @@ struct W1Smem {
   alignas(8) uint64_t empty[2];
 };
 
-template <int FAM, class W>
+// Levenshtein, 32-bit words, shared-memory tile: same recurrence as rfk::lev_w1<uint32_t> with the address
+// arithmetic spelled out so that it lands on the FMA pipe (the ALU pipe is the bound): per text char
+//   PRMT (byte extract) . IMAD (ch*128 + lane base) . LDS . 7 LOP3 . 3 IMAD (add, HP*2+1, HN*2)
+__device__ __forceinline__ uint32_t lev_w1_u32_smem(uint32_t pm_lane_saddr, const uint8_t* base, uint32_t start,
+                                                    uint32_t len2, uint32_t len1, uint32_t two) {
+  const uint32_t one = two >> 1;
+  uint32_t VP = 0xFFFFFFFFu << (32u - len1);
+  uint32_t VN = 0;
+  ByteReader rd(base, start);
+#define RF_LEV32_STEP(K)                                                             \
+  {                                                                                  \
+    const uint32_t ch = __byte_perm(w, 0u, 0x4440u + (K));                           \
+    uint32_t addr, X;                                                                \
+    asm("mad.lo.u32 %0, %1, 128, %2;" : "=r"(addr) : "r"(ch), "r"(pm_lane_saddr));   \
+    asm("ld.shared.u32 %0, [%1];" : "=r"(X) : "r"(addr));                            \
+    const uint32_t D0 = ((((X & VP) + VP) ^ VP) | X) | VN;                           \
+    uint32_t HP = VN | ~(D0 | VP);                                                   \
+    uint32_t HN = D0 & VP;                                                           \
+    HP = HP * two + one;                                                             \
+    HN = HN * two;                                                                   \
+    VP = HN | ~(D0 | HP);                                                            \
+    VN = HP & D0;                                                                    \
+  }
+  const uint32_t nfull = len2 >> 2;
+  for (uint32_t i = 0; i < nfull; ++i) {
+    const uint32_t w = rd.next4();
+    RF_LEV32_STEP(0)
+    RF_LEV32_STEP(1)
+    RF_LEV32_STEP(2)
+    RF_LEV32_STEP(3)
+  }
+  const uint32_t rem = len2 & 3u;
+  if (rem) {
+    const uint32_t w = rd.next4();
+    RF_LEV32_STEP(0)
+    if (rem > 1) RF_LEV32_STEP(1)
+    if (rem > 2) RF_LEV32_STEP(2)
+  }
+#undef RF_LEV32_STEP
+  return len2 + (uint32_t)__popc(VP) - (uint32_t)__popc(VN);
+}
+
+template <int FAM, class W, bool SMEM>
 __device__ __forceinline__ void score_one(const W* __restrict__ pm_lane, const uint8_t* base, uint32_t start,
                                           uint32_t len2, const W1Params& p, uint32_t& ru, double& rf) {
   auto tab = [&](uint32_t ch) -> W { return pm_lane[ch * 32u]; };
@@ -110,7 +168,8 @@ __device__ __forceinline__ void score_one(const W* __restrict__ pm_lane, const u
       raw = (FAM == F_LCS) ? 0u : len2;
     } else {
       ByteReader rd(base, start);
-      if constexpr (FAM == F_LEV) raw = lev_w1<W>(tab, rd, len2, p.len1);
+      if constexpr (FAM == F_LEV && sizeof(W) == 4 && SMEM) raw = lev_w1_u32_smem(smem_u32(pm_lane), base, start, len2, p.len1, p.two);
+      else if constexpr (FAM == F_LEV) raw = lev_w1<W>(tab, rd, len2, p.len1);
       else if constexpr (FAM == F_OSA) raw = osa_w1<W>(tab, rd, len2, p.len1);
       else raw = lcs_w1<W>(tab, rd, len2);
     }
@@ -149,7 +208,7 @@ __global__ void __launch_bounds__(NT + 32) scan_w1_kernel(const __grid_constant_
     uint32_t it = 0;
     for (uint32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const uint32_t s = it & 1u;
-      if (it >= 2) mbar_wait(&S.empty[s], ((it >> 1) - 1u) & 1u);
+      if (it >= 2) mbar_wait_sleep(&S.empty[s], ((it >> 1) - 1u) & 1u);
       const uint64_t t0 = (uint64_t)tile * p.T;
       const uint32_t tn = (uint32_t)((p.n - t0 < (uint64_t)p.T) ? (p.n - t0) : (uint64_t)p.T);
       const uint64_t o_lo = off64 ? p.off64[t0] : (uint64_t)p.off32[t0];
@@ -223,16 +282,20 @@ __global__ void __launch_bounds__(NT + 32) scan_w1_kernel(const __grid_constant_
     // ---- score: rank r*NT+tid of the length-sorted order -> a warp's 32 candidates have ~equal length
     uint32_t* res_u = reinterpret_cast<uint32_t*>(S.res);
     double* res_f = reinterpret_cast<double*>(S.res);
-    for (uint32_t rank = tid; rank < tn; rank += NT) {
+    // Rounds alternate direction (boustrophedon) so that every warp gets short AND long candidates:
+    // without it the warp holding the longest ranks of every round is the one the barrier waits for.
+    for (uint32_t r = 0; r * NT < tn; ++r) {
+      const uint32_t rank = r * NT + ((r & 1u) ? (NT - 1u - tid) : tid);
+      if (rank >= tn) continue;
       const uint32_t i = S.order[rank];
       const uint64_t o0 = off_at(i);
       const uint32_t len2 = (uint32_t)(off_at(i + 1) - o0);
       uint32_t ru = 0;
       double rf = 0.0;
       if (in_smem) {
-        score_one<FAM, W>(pm_lane, S.chars[s], (uint32_t)(o0 - a0), len2, p, ru, rf);
+        score_one<FAM, W, true>(pm_lane, S.chars[s], (uint32_t)(o0 - a0), len2, p, ru, rf);
       } else {  // tile larger than the staging buffer (long candidates): read straight from global / L1
-        score_one<FAM, W>(pm_lane, p.chars + (o0 & ~3ull), (uint32_t)(o0 & 3ull), len2, p, ru, rf);
+        score_one<FAM, W, false>(pm_lane, p.chars + (o0 & ~3ull), (uint32_t)(o0 & 3ull), len2, p, ru, rf);
       }
       if (p.out_f64) res_f[i] = rf;
       else res_u[i] = ru;
@@ -282,6 +345,7 @@ static cudaError_t launch_w1_inst(const ScanLaunch& L, const void* tab) {
   p.num_tiles = (uint32_t)((L.corpus.n + T - 1) / T);
   p.out = L.out;
   p.out_f64 = L.out_is_f64;
+  p.two = 2;
   p.epi = L.epi;
   uint32_t grid = (uint32_t)L.sm_count * (uint32_t)ctas_per_sm;
   if (grid > p.num_tiles) grid = p.num_tiles;
@@ -293,9 +357,12 @@ static cudaError_t launch_w1_inst(const ScanLaunch& L, const void* tab) {
 cudaError_t launch_scan_w1(const ScanLaunch& L) {
   const Family fam = family_of(L.epi.metric, L.epi.wclass);
   const bool w32 = L.query.len1 <= 32;
+  static const int tune = getenv("RF_W1_TUNE") ? atoi(getenv("RF_W1_TUNE")) : 0;  // tile-shape experiments
   // 32-bit words: 32 KB table, 24 KB tiles -> 2 CTAs/SM;  64-bit words: 64 KB table, 48 KB tiles -> 1 CTA/SM
   switch (fam) {
     case F_LEV:
+      if (w32 && tune == 1) return launch_w1_inst<F_LEV, uint32_t, 384, 768, 32768>(L, L.query.tab32_top);
+      if (w32 && tune == 2) return launch_w1_inst<F_LEV, uint32_t, 512, 1024, 45056>(L, L.query.tab32_top);
       return w32 ? launch_w1_inst<F_LEV, uint32_t, 256, 512, 24576>(L, L.query.tab32_top)
                  : launch_w1_inst<F_LEV, uint64_t, 512, 1024, 49152>(L, L.query.tab64_top);
     case F_OSA:

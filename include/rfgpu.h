@@ -139,6 +139,13 @@ rf_status rf_synth_corpus_u8(uint64_t seed, const uint8_t* query, uint32_t query
                              uint32_t min_len, uint32_t max_len, uint32_t kmax, uint64_t* offsets,
                              uint8_t* chars, int nthreads);
 
+/* tuning knobs (process-wide):
+ *   "build_interleaved_layout" (default 1): corpora created afterwards also keep the length-bucketed,
+ *        warp-interleaved copy that the fastest single-word kernel reads (about +1.2x corpus memory);
+ *   "single_word_path" (default 0): 0 = interleaved-layout kernel when the corpus has it,
+ *        1 = CSR kernel (TMA-staged tiles, bucketed by length in shared memory). */
+rf_status rf_set_option(const char* name, int value);
+
 /* kernel launches issued by this library in this process so far (bench.py reports the delta) */
 uint64_t rf_kernel_launch_count(void);
 

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <limits>
+#include <atomic>
 #include <mutex>
 #include <new>
 #include <string>
@@ -17,6 +18,9 @@
 using namespace rfk;
 
 static thread_local std::string g_last_error;
+// tuning knobs (rf_set_option)
+static std::atomic<int> g_build_lb{1};   // build the length-bucketed interleaved layout at corpus creation
+static std::atomic<int> g_w1_path{0};    // 0: interleaved-layout kernel when available, 1: CSR/TMA-tile kernel
 
 static rf_status fail(rf_status s, const std::string& msg) {
   g_last_error = msg;
@@ -63,6 +67,7 @@ struct rf_corpus {
   uint8_t* d_chars = nullptr;
   uint32_t* d_off32 = nullptr;
   uint64_t* d_off64 = nullptr;
+  LbAlloc lb;  // length-bucketed interleaved copy for the single-word kernels
 };
 
 struct rf_batch {
@@ -106,6 +111,13 @@ int rf_device_count(void) {
 
 uint64_t rf_kernel_launch_count(void) { return kernel_launch_count(); }
 
+rf_status rf_set_option(const char* name, int value) {
+  if (!name) return fail(RF_ERR_INVALID_ARG, "name is NULL");
+  if (!strcmp(name, "build_interleaved_layout")) { g_build_lb.store(value ? 1 : 0); return RF_OK; }
+  if (!strcmp(name, "single_word_path")) { g_w1_path.store(value ? 1 : 0); return RF_OK; }
+  return fail(RF_ERR_INVALID_ARG, std::string("unknown option: ") + name);
+}
+
 int rf_result_is_float(rf_metric metric, rf_kind kind) { return result_is_float((int)metric, (int)kind) ? 1 : 0; }
 
 // ------------------------------------------------------------------------------------------------ corpus
@@ -130,6 +142,10 @@ static rf_status corpus_finish(rf_corpus* c, cudaStream_t st) {
   if (c->d_off32) fill_tail_u32<<<1, 16, 0, st>>>(c->d_off32, c->n + 1, (uint32_t)c->total);
   else fill_tail_u64<<<1, 16, 0, st>>>(c->d_off64, c->n + 1, c->total);
   RF_CUDA(cudaGetLastError());
+  if (g_build_lb.load()) {
+    CorpusView v{c->d_chars, c->d_off32, c->d_off64, c->n, c->total};
+    RF_CUDA(lb_build(v, st, &c->lb));
+  }
   return RF_OK;
 }
 
@@ -236,6 +252,7 @@ rf_status rf_corpus_destroy(rf_corpus* c) {
   if (c->d_chars) cudaFree(c->d_chars);
   if (c->d_off32) cudaFree(c->d_off32);
   if (c->d_off64) cudaFree(c->d_off64);
+  lb_free(&c->lb);
   delete c;
   return RF_OK;
 }
@@ -356,6 +373,7 @@ static rf_status score_device(const rf_batch* b, const rf_corpus* c, rf_kind kin
   DeviceGuard g(c->device);
   if (!g.ok) return fail(RF_ERR_CUDA, "cudaSetDevice failed");
   L.corpus = CorpusView{c->d_chars, c->d_off32, c->d_off64, c->n, c->total};
+  L.lb = LbView{c->lb.perm, c->lb.lens, c->lb.goff, c->lb.gdata, c->lb.ngroups};
   L.query = b->view;
   L.out = out_dev;
   L.out_is_f64 = want_f64 ? 1 : 0;
@@ -363,7 +381,7 @@ static rf_status score_device(const rf_batch* b, const rf_corpus* c, rf_kind kin
   L.sm_count = sm_count_of(c->device);
   const Family fam = family_of(L.epi.metric, L.epi.wclass);
   cudaError_t e;
-  if (b->len1 <= 64) e = launch_scan_w1(L);
+  if (b->len1 <= 64) e = (c->lb.gdata && g_w1_path.load() == 0) ? launch_scan_lb(L) : launch_scan_w1(L);
   else if (fam == F_JARO) e = launch_jaro_mw(L);
   else e = launch_scan_mw(L);
   if (e != cudaSuccess) return cuda_fail(e, "kernel launch");

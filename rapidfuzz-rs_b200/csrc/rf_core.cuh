@@ -84,8 +84,8 @@ struct ByteReader {
 // ------------------------------------------------------------------------------------------------
 // Levenshtein, one machine word (query length 1..BITS).  `tab(ch)` returns the TOP-aligned match mask
 // PM[ch] << (BITS - len1).
-template <class W, class Tab>
-RF_HD uint32_t lev_w1(const Tab& tab, ByteReader rd, uint32_t len2, uint32_t len1) {
+template <class W, class Tab, class Rd>
+RF_HD uint32_t lev_w1(const Tab& tab, Rd rd, uint32_t len2, uint32_t len1) {
   constexpr int BITS = (int)sizeof(W) * 8;
   W VP = (W)(~(W)0) << (BITS - (int)len1);
   W VN = 0;
@@ -121,8 +121,8 @@ RF_HD uint32_t lev_w1(const Tab& tab, ByteReader rd, uint32_t len2, uint32_t len
 
 // OSA, one machine word, TOP-aligned like lev_w1 (osa.rs:84-135: D0 |= TR with
 // TR = (((~D0_prev) & PM_j) << 1) & PM_{j-1}).
-template <class W, class Tab>
-RF_HD uint32_t osa_w1(const Tab& tab, ByteReader rd, uint32_t len2, uint32_t len1) {
+template <class W, class Tab, class Rd>
+RF_HD uint32_t osa_w1(const Tab& tab, Rd rd, uint32_t len2, uint32_t len1) {
   constexpr int BITS = (int)sizeof(W) * 8;
   W VP = (W)(~(W)0) << (BITS - (int)len1);
   W VN = 0, D0 = 0, PMold = 0;
@@ -159,8 +159,8 @@ RF_HD uint32_t osa_w1(const Tab& tab, ByteReader rd, uint32_t len2, uint32_t len
 }
 
 // LCS length, one machine word; `tab(ch)` is the plain (bottom-aligned) PM[ch] (lcs_seq.rs:222-257).
-template <class W, class Tab>
-RF_HD uint32_t lcs_w1(const Tab& tab, ByteReader rd, uint32_t len2) {
+template <class W, class Tab, class Rd>
+RF_HD uint32_t lcs_w1(const Tab& tab, Rd rd, uint32_t len2) {
   W S = ~(W)0;
 #define RF_LCS_STEP(CH)              \
   {                                  \

@@ -102,15 +102,47 @@ struct W1Smem {
   alignas(8) uint64_t empty[2];
 };
 
-// Levenshtein, 32-bit words, shared-memory tile: same recurrence as rfk::lev_w1<uint32_t> with the address
-// arithmetic spelled out so that it lands on the FMA pipe (the ALU pipe is the bound): per text char
+// Where a candidate's bytes come from.
+//  TileSrc: packed bytes at an arbitrary offset of a 4-byte aligned buffer (TMA-staged tile in shared memory, or
+//           the CSR array in global memory).
+//  LaneSrc: one lane's column of a length-bucketed, warp-interleaved group (word k of lane l at col[k*32]):
+//           every 32-bit load of a warp is one fully coalesced 128-byte line, one word prefetched ahead.
+struct TileSrc {
+  const uint8_t* base;
+  uint32_t start;
+  __device__ __forceinline__ ByteReader reader() const { return ByteReader(base, start); }
+  __device__ __forceinline__ uint32_t byte(uint32_t j) const { return base[start + j]; }
+};
+struct LaneReader {
+  const uint32_t* p;
+  uint32_t nxt;
+  __device__ __forceinline__ explicit LaneReader(const uint32_t* col) : p(col + 32) { nxt = __ldg(col); }
+  __device__ __forceinline__ uint32_t next4() {
+    const uint32_t r = nxt;
+    nxt = __ldg(p);
+    p += 32;
+    return r;
+  }
+};
+struct LaneSrc {
+  const uint32_t* col;
+  __device__ __forceinline__ LaneReader reader() const { return LaneReader(col); }
+  __device__ __forceinline__ uint32_t byte(uint32_t j) const {
+    return reinterpret_cast<const uint8_t*>(col + (size_t)(j >> 2) * 32)[j & 3u];
+  }
+};
+
+// Levenshtein, 32-bit words, match table in shared memory: same recurrence as rfk::lev_w1<uint32_t> with the
+// address arithmetic spelled out so that it lands on the FMA pipe (the ALU pipe is the bound): per text char
 //   PRMT (byte extract) . IMAD (ch*128 + lane base) . LDS . 7 LOP3 . 3 IMAD (add, HP*2+1, HN*2)
-__device__ __forceinline__ uint32_t lev_w1_u32_smem(uint32_t pm_lane_saddr, const uint8_t* base, uint32_t start,
-                                                    uint32_t len2, uint32_t len1, uint32_t two) {
+// `two` is the constant 2 passed as a kernel parameter: opaque to ptxas, so x*2+1 stays an IMAD (FMA pipe)
+// instead of becoming an ALU-pipe LEA.
+template <class Rd>
+__device__ __forceinline__ uint32_t lev_w1_u32_fast(uint32_t pm_lane_saddr, Rd rd, uint32_t len2, uint32_t len1,
+                                                    uint32_t two) {
   const uint32_t one = two >> 1;
   uint32_t VP = 0xFFFFFFFFu << (32u - len1);
   uint32_t VN = 0;
-  ByteReader rd(base, start);
 #define RF_LEV32_STEP(K)                                                             \
   {                                                                                  \
     const uint32_t ch = __byte_perm(w, 0u, 0x4440u + (K));                           \
@@ -144,37 +176,35 @@ __device__ __forceinline__ uint32_t lev_w1_u32_smem(uint32_t pm_lane_saddr, cons
   return len2 + (uint32_t)__popc(VP) - (uint32_t)__popc(VN);
 }
 
-template <int FAM, class W, bool SMEM>
-__device__ __forceinline__ void score_one(const W* __restrict__ pm_lane, const uint8_t* base, uint32_t start,
-                                          uint32_t len2, const W1Params& p, uint32_t& ru, double& rf) {
+// One candidate: raw bit-parallel kernel + score algebra.  pm_lane = &pm[lane] of the lane-replicated table.
+template <int FAM, class W, class Src>
+__device__ __forceinline__ void score_one(const W* __restrict__ pm_lane, const Src& src, uint32_t len2, uint32_t len1,
+                                          const Epi& epi, int out_f64, uint32_t two, uint32_t& ru, double& rf) {
   auto tab = [&](uint32_t ch) -> W { return pm_lane[ch * 32u]; };
   if constexpr (FAM == F_JARO) {
-    const uint8_t* b = base + start;
-    auto bytes = [&](uint32_t j) -> uint32_t { return b[j]; };
-    const uint32_t len1 = p.len1;
+    auto bytes = [&](uint32_t j) -> uint32_t { return src.byte(j); };
     auto jaro = [&](double c) { return jaro_similarity_w1(tab, bytes, len1, len2, c); };
-    if (p.epi.metric == M_JARO) {
-      rf = finish_float(p.epi, jaro);
+    if (epi.metric == M_JARO) {
+      rf = finish_float(epi, jaro);
     } else {
       uint32_t prefix = 0;  // common prefix, at most 4 (jaro_winkler.rs:118-123): q[i]==s[i] <=> bit i of PM[s[i]]
       while (prefix < 4 && prefix < len1 && prefix < len2 && ((tab(bytes(prefix)) >> prefix) & 1u)) ++prefix;
-      const double pw = p.epi.prefix_weight;
+      const double pw = epi.prefix_weight;
       auto jw = [&](double c) { return jaro_winkler_from(jaro, prefix, pw, c); };
-      rf = finish_float(p.epi, jw);
+      rf = finish_float(epi, jw);
     }
   } else {
     uint32_t raw;
-    if (p.len1 == 0) {
+    if (len1 == 0) {
       raw = (FAM == F_LCS) ? 0u : len2;
     } else {
-      ByteReader rd(base, start);
-      if constexpr (FAM == F_LEV && sizeof(W) == 4 && SMEM) raw = lev_w1_u32_smem(smem_u32(pm_lane), base, start, len2, p.len1, p.two);
-      else if constexpr (FAM == F_LEV) raw = lev_w1<W>(tab, rd, len2, p.len1);
-      else if constexpr (FAM == F_OSA) raw = osa_w1<W>(tab, rd, len2, p.len1);
-      else raw = lcs_w1<W>(tab, rd, len2);
+      if constexpr (FAM == F_LEV && sizeof(W) == 4) raw = lev_w1_u32_fast(smem_u32(pm_lane), src.reader(), len2, len1, two);
+      else if constexpr (FAM == F_LEV) raw = lev_w1<W>(tab, src.reader(), len2, len1);
+      else if constexpr (FAM == F_OSA) raw = osa_w1<W>(tab, src.reader(), len2, len1);
+      else raw = lcs_w1<W>(tab, src.reader(), len2);
     }
-    if (p.out_f64) rf = finish_norm(p.epi, raw, p.len1, len2);
-    else ru = finish_int(p.epi, raw, p.len1, len2);
+    if (out_f64) rf = finish_norm(epi, raw, len1, len2);
+    else ru = finish_int(epi, raw, len1, len2);
   }
 }
 
@@ -293,9 +323,9 @@ __global__ void __launch_bounds__(NT + 32) scan_w1_kernel(const __grid_constant_
       uint32_t ru = 0;
       double rf = 0.0;
       if (in_smem) {
-        score_one<FAM, W, true>(pm_lane, S.chars[s], (uint32_t)(o0 - a0), len2, p, ru, rf);
+        score_one<FAM, W>(pm_lane, TileSrc{S.chars[s], (uint32_t)(o0 - a0)}, len2, p.len1, p.epi, p.out_f64, p.two, ru, rf);
       } else {  // tile larger than the staging buffer (long candidates): read straight from global / L1
-        score_one<FAM, W, false>(pm_lane, p.chars + (o0 & ~3ull), (uint32_t)(o0 & 3ull), len2, p, ru, rf);
+        score_one<FAM, W>(pm_lane, TileSrc{p.chars + (o0 & ~3ull), (uint32_t)(o0 & 3ull)}, len2, p.len1, p.epi, p.out_f64, p.two, ru, rf);
       }
       if (p.out_f64) res_f[i] = rf;
       else res_u[i] = ru;
@@ -373,6 +403,95 @@ cudaError_t launch_scan_w1(const ScanLaunch& L) {
                  : launch_w1_inst<F_LCS, uint64_t, 512, 1024, 49152>(L, L.query.tab64_bot);
     default:
       return launch_w1_inst<F_JARO, uint64_t, 512, 1024, 49152>(L, L.query.tab64_bot);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ lb
+// Single-word path over the length-bucketed, warp-interleaved layout (rf_layout.cu): one warp per group of
+// 32 equal-length candidates, one thread per candidate.  No tile staging, no sorting, no CTA barriers in the
+// steady state: candidate words arrive as coalesced 128-byte lines, the only shared-memory traffic is the
+// conflict-free match-table gather, and all 32 lanes run the same trip count.
+struct LbParams {
+  LbView lb;
+  const void* tab;
+  uint32_t len1;
+  void* out;
+  int out_f64;
+  uint32_t two;
+  Epi epi;
+};
+
+template <int FAM, class W, int NT>
+__global__ void __launch_bounds__(NT) scan_lb_kernel(const __grid_constant__ LbParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  W* pm = reinterpret_cast<W*>(smem_raw);
+  {
+    const W* __restrict__ t = reinterpret_cast<const W*>(p.tab);
+    for (uint32_t i = threadIdx.x; i < 256u * 32u; i += NT) pm[i] = t[i >> 5];
+  }
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31u;
+  const W* __restrict__ pm_lane = pm + lane;
+  const uint64_t warp_global = (uint64_t)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
+  const uint64_t total_warps = (uint64_t)gridDim.x * (NT / 32);
+  for (uint64_t g = warp_global; g < p.lb.ngroups; g += total_warps) {
+    const uint64_t i = g * 32 + lane;
+    const uint32_t len2 = __ldg(p.lb.lens + i);
+    const uint32_t idx = __ldg(p.lb.perm + i);
+    const uint64_t r0 = __ldg(p.lb.goff + g);
+    const LaneSrc src{p.lb.gdata + r0 * 32 + lane};
+    uint32_t ru = 0;
+    double rf = 0.0;
+    score_one<FAM, W>(pm_lane, src, len2, p.len1, p.epi, p.out_f64, p.two, ru, rf);
+    if (idx != 0xFFFFFFFFu) {
+      if (p.out_f64) reinterpret_cast<double*>(p.out)[idx] = rf;
+      else reinterpret_cast<uint32_t*>(p.out)[idx] = ru;
+    }
+  }
+}
+
+template <int FAM, class W, int NT>
+static cudaError_t launch_lb_inst(const ScanLaunch& L, const void* tab) {
+  auto kern = scan_lb_kernel<FAM, W, NT>;
+  const size_t smem = sizeof(W) * 256 * 32;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int ctas_per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, NT, smem);
+  if (e != cudaSuccess) return e;
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  LbParams p{};
+  p.lb = L.lb;
+  p.tab = tab;
+  p.len1 = L.query.len1;
+  p.out = L.out;
+  p.out_f64 = L.out_is_f64;
+  p.two = 2;
+  p.epi = L.epi;
+  uint64_t grid = (uint64_t)L.sm_count * ctas_per_sm;
+  const uint64_t need = (L.lb.ngroups + NT / 32 - 1) / (NT / 32);
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  kern<<<(uint32_t)grid, NT, smem, L.stream>>>(p);
+  g_launches.fetch_add(1);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_scan_lb(const ScanLaunch& L) {
+  const Family fam = family_of(L.epi.metric, L.epi.wclass);
+  const bool w32 = L.query.len1 <= 32;
+  switch (fam) {
+    case F_LEV:
+      return w32 ? launch_lb_inst<F_LEV, uint32_t, 512>(L, L.query.tab32_top)
+                 : launch_lb_inst<F_LEV, uint64_t, 512>(L, L.query.tab64_top);
+    case F_OSA:
+      return w32 ? launch_lb_inst<F_OSA, uint32_t, 512>(L, L.query.tab32_top)
+                 : launch_lb_inst<F_OSA, uint64_t, 512>(L, L.query.tab64_top);
+    case F_LCS:
+      return w32 ? launch_lb_inst<F_LCS, uint32_t, 512>(L, L.query.tab32_bot)
+                 : launch_lb_inst<F_LCS, uint64_t, 512>(L, L.query.tab64_bot);
+    default:
+      return launch_lb_inst<F_JARO, uint64_t, 512>(L, L.query.tab64_bot);
   }
 }
 

@@ -27,8 +27,33 @@ struct QueryView {
   const uint64_t* pm_words;  // [256][words] row-major (pattern_match_vector.rs layout), any len1
 };
 
+// Length-bucketed, warp-interleaved copy of the corpus (built once at corpus creation, rf_layout.cu):
+// candidates are sorted by length inside blocks of LB_BLOCK candidates and cut into groups of 32; group g
+// stores word k of its lane-l candidate at gdata[(goff[g] + k) * 32 + l]  (rows of 128 bytes).
+struct LbView {
+  const uint32_t* perm;   // [ngroups*32] original candidate index, 0xFFFFFFFF = padding lane
+  const uint32_t* lens;   // [ngroups*32] candidate length
+  const uint64_t* goff;   // [ngroups+1]  first row of each group
+  const uint32_t* gdata;  // [total_rows*32 (+ slack)]
+  uint64_t ngroups;
+};
+constexpr uint32_t LB_BLOCK = 65536;
+
+struct LbAlloc {  // owning pointers of an LbView
+  uint32_t* perm = nullptr;
+  uint32_t* lens = nullptr;
+  uint64_t* goff = nullptr;
+  uint32_t* gdata = nullptr;
+  uint64_t ngroups = 0;
+  uint64_t total_rows = 0;
+};
+// Builds the layout from the CSR corpus on `stream` (synchronises once to size the data array).
+cudaError_t lb_build(const CorpusView& c, cudaStream_t stream, LbAlloc* out);
+void lb_free(LbAlloc* a);
+
 struct ScanLaunch {
   CorpusView corpus;
+  LbView lb;
   QueryView query;
   Epi epi;
   void* out;          // uint32_t[n] or double[n]
@@ -37,8 +62,10 @@ struct ScanLaunch {
   int sm_count;
 };
 
-// Single-word path (query <= 64): thread per candidate over TMA-staged, length-bucketed tiles.
+// Single-word path (query <= 64), CSR input: thread per candidate over TMA-staged tiles bucketed by length in-kernel.
 cudaError_t launch_scan_w1(const ScanLaunch& L);
+// Single-word path (query <= 64), pre-bucketed interleaved layout: warp per group of 32 equal-length candidates.
+cudaError_t launch_scan_lb(const ScanLaunch& L);
 // Multi-word path (query > 64): sub-warp per candidate, carries propagated with warp shuffles.
 cudaError_t launch_scan_mw(const ScanLaunch& L);
 // Jaro / Jaro-Winkler with a multi-word query (65..2048).

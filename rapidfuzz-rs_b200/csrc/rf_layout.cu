@@ -1,0 +1,191 @@
+// rf_layout.cu -- builds the length-bucketed, warp-interleaved corpus layout (LbView) from the CSR corpus.
+//
+// Why: with one thread per candidate the 32 lanes of a warp must run the same number of Myers steps, and
+// every lane's next 4 characters should arrive in one coalesced transaction.  Sorting candidates by length
+// inside blocks of LB_BLOCK (so results still scatter into an L2-resident window of the output) and storing
+// each group of 32 equal-length candidates word-interleaved gives both, once, at corpus creation.
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+#include "rf_kernels.cuh"
+
+namespace rfk {
+
+constexpr int LB_KEYS = 2048;  // counting-sort keys: exact for lengths < 2047, longer ones share the last bin
+
+__device__ __forceinline__ uint64_t off_ld(const uint32_t* o32, const uint64_t* o64, uint64_t i) {
+  return o64 ? o64[i] : (uint64_t)o32[i];
+}
+
+// one CTA per block of LB_BLOCK candidates: counting sort by length -> perm / lens in sorted order
+__global__ void __launch_bounds__(1024) lb_sort_kernel(const uint32_t* __restrict__ o32, const uint64_t* __restrict__ o64,
+                                                       uint64_t n, uint64_t n_pad, uint32_t* __restrict__ perm,
+                                                       uint32_t* __restrict__ lens) {
+  __shared__ uint32_t hist[LB_KEYS];
+  __shared__ uint32_t wsum[32];
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint64_t b0 = (uint64_t)blockIdx.x * LB_BLOCK;
+  const uint64_t b1 = (b0 + LB_BLOCK < n) ? b0 + LB_BLOCK : n;
+  for (uint32_t i = tid; i < LB_KEYS; i += 1024) hist[i] = 0;
+  __syncthreads();
+  for (uint64_t i = b0 + tid; i < b1; i += 1024) {
+    const uint64_t len = off_ld(o32, o64, i + 1) - off_ld(o32, o64, i);
+    atomicAdd(&hist[len < LB_KEYS - 1 ? (uint32_t)len : LB_KEYS - 1], 1u);
+  }
+  __syncthreads();
+  {  // exclusive scan of the 2048 bins: 2 bins per thread
+    const uint32_t v0 = hist[2 * tid], v1 = hist[2 * tid + 1];
+    const uint32_t s = v0 + v1;
+    uint32_t incl = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= (uint32_t)d) incl += t;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = wsum[lane], wi = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+        if (lane >= (uint32_t)d) wi += t;
+      }
+      wsum[lane] = wi - w;
+    }
+    __syncthreads();
+    const uint32_t ex = wsum[warp] + incl - s;
+    hist[2 * tid] = ex;
+    hist[2 * tid + 1] = ex + v0;
+  }
+  __syncthreads();
+  for (uint64_t i = b0 + tid; i < b1; i += 1024) {
+    const uint64_t len = off_ld(o32, o64, i + 1) - off_ld(o32, o64, i);
+    const uint32_t pos = atomicAdd(&hist[len < LB_KEYS - 1 ? (uint32_t)len : LB_KEYS - 1], 1u);
+    perm[b0 + pos] = (uint32_t)i;
+    lens[b0 + pos] = (uint32_t)len;
+  }
+  // padding lanes of the very last group
+  const uint64_t e1 = (b0 + LB_BLOCK < n_pad) ? b0 + LB_BLOCK : n_pad;
+  for (uint64_t j = b1 + tid; j < e1; j += 1024) {
+    perm[j] = 0xFFFFFFFFu;
+    lens[j] = 0;
+  }
+}
+
+// rows (4-byte words per lane) of every group = ceil(max length in group / 4); grows[ngroups] = 0 (scan sentinel)
+__global__ void lb_rows_kernel(const uint32_t* __restrict__ lens, uint64_t ngroups, uint32_t* __restrict__ grows) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint64_t warp_global = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t total_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t g = warp_global; g <= ngroups; g += total_warps) {
+    uint32_t m = 0;
+    if (g < ngroups) m = __reduce_max_sync(0xffffffffu, lens[g * 32 + lane]);
+    if (lane == 0) grows[g] = (g < ngroups) ? (m + 3u) / 4u : 0u;
+  }
+}
+
+// transposes each group's candidates into the interleaved rows
+__global__ void lb_fill_kernel(const uint8_t* __restrict__ chars, const uint32_t* __restrict__ o32,
+                               const uint64_t* __restrict__ o64, const uint32_t* __restrict__ perm,
+                               const uint32_t* __restrict__ lens, const uint64_t* __restrict__ goff, uint64_t ngroups,
+                               uint32_t* __restrict__ gdata) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint64_t warp_global = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t total_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t g = warp_global; g < ngroups; g += total_warps) {
+    const uint32_t idx = perm[g * 32 + lane];
+    const uint32_t len = lens[g * 32 + lane];
+    const uint64_t r0 = goff[g];
+    const uint32_t rows = (uint32_t)(goff[g + 1] - r0);
+    uint32_t* dst = gdata + r0 * 32 + lane;
+    if (idx == 0xFFFFFFFFu || len == 0) {
+      for (uint32_t k = 0; k < rows; ++k) dst[(size_t)k * 32] = 0;
+      continue;
+    }
+    const uint64_t o = off_ld(o32, o64, idx);
+    ByteReader rd(chars + (o & ~3ull), (uint32_t)(o & 3ull));
+    for (uint32_t k = 0; k < rows; ++k) {
+      uint32_t w = 0;
+      if (4 * k < len) {
+        w = rd.next4();
+        const uint32_t left = len - 4 * k;
+        if (left < 4) w &= (1u << (8 * left)) - 1u;
+      }
+      dst[(size_t)k * 32] = w;
+    }
+  }
+}
+
+struct CastU64 {
+  __host__ __device__ uint64_t operator()(uint32_t v) const { return (uint64_t)v; }
+};
+
+void lb_free(LbAlloc* a) {
+  if (!a) return;
+  if (a->perm) cudaFree(a->perm);
+  if (a->lens) cudaFree(a->lens);
+  if (a->goff) cudaFree(a->goff);
+  if (a->gdata) cudaFree(a->gdata);
+  *a = LbAlloc{};
+}
+
+cudaError_t lb_build(const CorpusView& c, cudaStream_t st, LbAlloc* out) {
+  *out = LbAlloc{};
+  if (c.n == 0) return cudaSuccess;
+  const uint64_t n_pad = (c.n + 31) / 32 * 32;
+  const uint64_t ngroups = n_pad / 32;
+  const uint32_t nblocks = (uint32_t)((c.n + LB_BLOCK - 1) / LB_BLOCK);
+  LbAlloc a;
+  a.ngroups = ngroups;
+  uint32_t* grows = nullptr;
+  void* tmp = nullptr;
+  size_t tmp_bytes = 0;
+  cudaError_t e;
+#define LB_TRY(x)              \
+  do {                         \
+    e = (x);                   \
+    if (e != cudaSuccess) goto fail; \
+  } while (0)
+  LB_TRY(cudaMalloc(&a.perm, n_pad * sizeof(uint32_t)));
+  LB_TRY(cudaMalloc(&a.lens, n_pad * sizeof(uint32_t)));
+  LB_TRY(cudaMalloc(&a.goff, (ngroups + 1) * sizeof(uint64_t)));
+  LB_TRY(cudaMalloc(&grows, (ngroups + 1) * sizeof(uint32_t)));
+  lb_sort_kernel<<<nblocks, 1024, 0, st>>>(c.off32, c.off64, c.n, n_pad, a.perm, a.lens);
+  LB_TRY(cudaGetLastError());
+  {
+    uint64_t blocks = (ngroups + 1 + 7) / 8;
+    if (blocks > 65535 * 8) blocks = 65535 * 8;
+    lb_rows_kernel<<<(uint32_t)blocks, 256, 0, st>>>(a.lens, ngroups, grows);
+    LB_TRY(cudaGetLastError());
+  }
+  {
+    cub::TransformInputIterator<uint64_t, CastU64, const uint32_t*> in(grows, CastU64());
+    LB_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, a.goff, (int64_t)(ngroups + 1), st));
+    LB_TRY(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
+    LB_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, in, a.goff, (int64_t)(ngroups + 1), st));
+  }
+  LB_TRY(cudaMemcpyAsync(&a.total_rows, a.goff + ngroups, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  LB_TRY(cudaStreamSynchronize(st));
+  // 8 rows of slack: readers prefetch one row past the end of a group
+  LB_TRY(cudaMalloc(&a.gdata, (a.total_rows + 8) * 128));
+  LB_TRY(cudaMemsetAsync(a.gdata + a.total_rows * 32, 0, 8 * 128, st));
+  {
+    uint64_t blocks = (ngroups + 7) / 8;
+    if (blocks > 148 * 64) blocks = 148 * 64;
+    lb_fill_kernel<<<(uint32_t)blocks, 256, 0, st>>>(c.chars, c.off32, c.off64, a.perm, a.lens, a.goff, ngroups, a.gdata);
+    LB_TRY(cudaGetLastError());
+  }
+  LB_TRY(cudaStreamSynchronize(st));
+  cudaFree(grows);
+  cudaFree(tmp);
+  *out = a;
+  return cudaSuccess;
+fail:
+  if (grows) cudaFree(grows);
+  if (tmp) cudaFree(tmp);
+  lb_free(&a);
+  return e;
+#undef LB_TRY
+}
+
+}  // namespace rfk

@@ -62,6 +62,7 @@ SYMBOLS = {
     "rf_synth_query_u8": (_int, [_u64, _u32, _vp]),
     "rf_synth_corpus_u8": (_int, [_u64, _vp, _u32, _u64, _u32, _u32, _u32, _vp, _vp, _int]),
     "rf_kernel_launch_count": (_u64, []),
+    "rf_set_option": (_int, [C.c_char_p, _int]),
 }
 
 _lib = None

@@ -15,6 +15,17 @@ from rapidfuzz_b200 import _ffi
 from oracle import oracle as orc
 from gpu_util import make_corpus, check, gpu_batch, assert_same
 
+
+
+@pytest.fixture(autouse=True, params=["interleaved", "csr_tiles"])
+def single_word_path(request):
+    """Every test runs against both single-word kernels: the length-bucketed interleaved layout
+    (scan_lb_kernel) and the CSR / TMA-tile path (scan_w1_kernel)."""
+    _ffi.check(_ffi.lib().rf_set_option(b"single_word_path", 0 if request.param == "interleaved" else 1))
+    yield request.param
+    _ffi.check(_ffi.lib().rf_set_option(b"single_word_path", 0))
+
+
 INT_METRICS = ["levenshtein", "indel", "lcs_seq", "osa"]
 ALL_KINDS = ["distance", "similarity", "normalized_distance", "normalized_similarity"]
 EDGE_LENS = [0, 1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 31, 32, 33, 63, 64, 65, 66, 100, 127, 128, 129, 200, 255, 256, 257]

@@ -4,7 +4,7 @@ import json, os, subprocess, sys
 tunes = sys.argv[1].split(",") if len(sys.argv) > 1 else ["0"]
 extra = sys.argv[2:]
 for t in tunes:
-    env = dict(os.environ, RF_W1_TUNE=t)
+    env = dict(os.environ, RF_W1_TUNE=t, RF_W1_PATH=("1" if t != "lb" else "0"))
     out = subprocess.run([sys.executable, "bench.py", "--no-cpu-baseline", "--e2e-steps", "1"] + extra,
                          env=env, capture_output=True, text=True)
     try:

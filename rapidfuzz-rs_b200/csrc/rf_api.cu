@@ -61,6 +61,21 @@ static int sm_count_of(int device) {
   return cache[device];
 }
 
+// scratch counters for the chunk scheduler of scan_lb_kernel: a ring of slots per device so that concurrent
+// launches never share one
+static unsigned long long* counter_slot(int device) {
+  static std::mutex mu;
+  static std::vector<unsigned long long*> pools;
+  static std::vector<uint32_t> next;
+  constexpr uint32_t kSlots = 4096;
+  std::lock_guard<std::mutex> lk(mu);
+  if ((int)pools.size() <= device) { pools.resize(device + 1, nullptr); next.resize(device + 1, 0); }
+  if (!pools[device]) {
+    if (cudaMalloc(&pools[device], kSlots * sizeof(unsigned long long)) != cudaSuccess) return nullptr;
+  }
+  return pools[device] + (next[device]++ % kSlots);
+}
+
 struct rf_corpus {
   int device = 0;
   uint64_t n = 0, total = 0;
@@ -374,6 +389,8 @@ static rf_status score_device(const rf_batch* b, const rf_corpus* c, rf_kind kin
   if (!g.ok) return fail(RF_ERR_CUDA, "cudaSetDevice failed");
   L.corpus = CorpusView{c->d_chars, c->d_off32, c->d_off64, c->n, c->total};
   L.lb = LbView{c->lb.perm, c->lb.lens, c->lb.goff, c->lb.gdata, c->lb.ngroups};
+  L.lb_counter = counter_slot(c->device);
+  if (!L.lb_counter) return fail(RF_ERR_OOM, "scheduler scratch allocation failed");
   L.query = b->view;
   L.out = out_dev;
   L.out_is_f64 = want_f64 ? 1 : 0;

@@ -105,30 +105,47 @@ struct W1Smem {
 // Where a candidate's bytes come from.
 //  TileSrc: packed bytes at an arbitrary offset of a 4-byte aligned buffer (TMA-staged tile in shared memory, or
 //           the CSR array in global memory).
-//  LaneSrc: one lane's column of a length-bucketed, warp-interleaved group (word k of lane l at col[k*32]):
-//           every 32-bit load of a warp is one fully coalesced 128-byte line, one word prefetched ahead.
+//  LaneSrc: one lane's column of a length-bucketed, warp-interleaved group (8-byte row k of lane l at
+//           col[k*32]): every load of a warp is 256 contiguous bytes, one row (8 chars) prefetched ahead.
+struct TileReader : ByteReader {
+  static constexpr bool kRow8 = false;
+  __device__ __forceinline__ TileReader(const uint8_t* b, uint32_t s) : ByteReader(b, s) {}
+};
 struct TileSrc {
   const uint8_t* base;
   uint32_t start;
-  __device__ __forceinline__ ByteReader reader() const { return ByteReader(base, start); }
+  __device__ __forceinline__ TileReader reader() const { return TileReader(base, start); }
   __device__ __forceinline__ uint32_t byte(uint32_t j) const { return base[start + j]; }
 };
+__device__ __forceinline__ uint2 ld_stream8(const uint2* p) {  // streamed once: evict-first in L2, no L1 allocate
+  return __ldcs(p);  // ld.global.cs: streaming (evict-first) so the scattered result sectors stay in L2
+}
 struct LaneReader {
-  const uint32_t* p;
-  uint32_t nxt;
-  __device__ __forceinline__ explicit LaneReader(const uint32_t* col) : p(col + 32) { nxt = __ldg(col); }
-  __device__ __forceinline__ uint32_t next4() {
-    const uint32_t r = nxt;
-    nxt = __ldg(p);
+  static constexpr bool kRow8 = true;
+  const uint2* p;  // next row to fetch
+  uint2 nxt;       // row already in flight / in registers
+  uint2 cur;
+  uint32_t half;
+  __device__ __forceinline__ LaneReader(const uint2* second_row, uint2 first_row) : p(second_row), nxt(first_row), half(0) {}
+  __device__ __forceinline__ uint2 next8() {
+    const uint2 r = nxt;
+    nxt = ld_stream8(p);
     p += 32;
     return r;
   }
+  __device__ __forceinline__ uint32_t next4() {
+    if (half) { half = 0; return cur.y; }
+    cur = next8();
+    half = 1;
+    return cur.x;
+  }
 };
 struct LaneSrc {
-  const uint32_t* col;
-  __device__ __forceinline__ LaneReader reader() const { return LaneReader(col); }
+  const uint2* col;  // this lane's column: row k at col[k*32]
+  uint2 first;       // row 0, prefetched by the caller
+  __device__ __forceinline__ LaneReader reader() const { return LaneReader(col + 32, first); }
   __device__ __forceinline__ uint32_t byte(uint32_t j) const {
-    return reinterpret_cast<const uint8_t*>(col + (size_t)(j >> 2) * 32)[j & 3u];
+    return reinterpret_cast<const uint8_t*>(col + (size_t)(j >> 3) * 32)[j & 7u];
   }
 };
 
@@ -157,20 +174,44 @@ __device__ __forceinline__ uint32_t lev_w1_u32_fast(uint32_t pm_lane_saddr, Rd r
     VP = HN | ~(D0 | HP);                                                            \
     VN = HP & D0;                                                                    \
   }
-  const uint32_t nfull = len2 >> 2;
-  for (uint32_t i = 0; i < nfull; ++i) {
-    const uint32_t w = rd.next4();
-    RF_LEV32_STEP(0)
-    RF_LEV32_STEP(1)
-    RF_LEV32_STEP(2)
-    RF_LEV32_STEP(3)
-  }
-  const uint32_t rem = len2 & 3u;
-  if (rem) {
-    const uint32_t w = rd.next4();
-    RF_LEV32_STEP(0)
-    if (rem > 1) RF_LEV32_STEP(1)
-    if (rem > 2) RF_LEV32_STEP(2)
+  if constexpr (Rd::kRow8) {
+    const uint32_t nfull = len2 >> 3;
+    for (uint32_t i = 0; i < nfull; ++i) {
+      const uint2 ww = rd.next8();
+      { const uint32_t w = ww.x; RF_LEV32_STEP(0) RF_LEV32_STEP(1) RF_LEV32_STEP(2) RF_LEV32_STEP(3) }
+      { const uint32_t w = ww.y; RF_LEV32_STEP(0) RF_LEV32_STEP(1) RF_LEV32_STEP(2) RF_LEV32_STEP(3) }
+    }
+    const uint32_t rem = len2 & 7u;
+    if (rem) {
+      const uint2 ww = rd.next8();
+      { const uint32_t w = ww.x;
+        RF_LEV32_STEP(0)
+        if (rem > 1) RF_LEV32_STEP(1)
+        if (rem > 2) RF_LEV32_STEP(2)
+        if (rem > 3) RF_LEV32_STEP(3) }
+      if (rem > 4) {
+        const uint32_t w = ww.y;
+        RF_LEV32_STEP(0)
+        if (rem > 5) RF_LEV32_STEP(1)
+        if (rem > 6) RF_LEV32_STEP(2)
+      }
+    }
+  } else {
+    const uint32_t nfull = len2 >> 2;
+    for (uint32_t i = 0; i < nfull; ++i) {
+      const uint32_t w = rd.next4();
+      RF_LEV32_STEP(0)
+      RF_LEV32_STEP(1)
+      RF_LEV32_STEP(2)
+      RF_LEV32_STEP(3)
+    }
+    const uint32_t rem = len2 & 3u;
+    if (rem) {
+      const uint32_t w = rd.next4();
+      RF_LEV32_STEP(0)
+      if (rem > 1) RF_LEV32_STEP(1)
+      if (rem > 2) RF_LEV32_STEP(2)
+    }
   }
 #undef RF_LEV32_STEP
   return len2 + (uint32_t)__popc(VP) - (uint32_t)__popc(VN);
@@ -418,6 +459,8 @@ struct LbParams {
   void* out;
   int out_f64;
   uint32_t two;
+  uint32_t chunk;               // consecutive groups handed to a warp at a time
+  unsigned long long* counter;  // dynamic chunk scheduler (zeroed before the launch)
   Epi epi;
 };
 
@@ -432,21 +475,41 @@ __global__ void __launch_bounds__(NT) scan_lb_kernel(const __grid_constant__ LbP
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31u;
   const W* __restrict__ pm_lane = pm + lane;
-  const uint64_t warp_global = (uint64_t)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
   const uint64_t total_warps = (uint64_t)gridDim.x * (NT / 32);
-  for (uint64_t g = warp_global; g < p.lb.ngroups; g += total_warps) {
-    const uint64_t i = g * 32 + lane;
-    const uint32_t len2 = __ldg(p.lb.lens + i);
-    const uint32_t idx = __ldg(p.lb.perm + i);
-    const uint64_t r0 = __ldg(p.lb.goff + g);
-    const LaneSrc src{p.lb.gdata + r0 * 32 + lane};
-    uint32_t ru = 0;
-    double rf = 0.0;
-    score_one<FAM, W>(pm_lane, src, len2, p.len1, p.epi, p.out_f64, p.two, ru, rf);
-    if (idx != 0xFFFFFFFFu) {
-      if (p.out_f64) reinterpret_cast<double*>(p.out)[idx] = rf;
-      else reinterpret_cast<uint32_t*>(p.out)[idx] = ru;
+  const uint64_t ngroups = p.lb.ngroups;
+  const uint64_t nchunks = (ngroups + p.chunk - 1) / p.chunk;
+  const uint2* __restrict__ gdata = reinterpret_cast<const uint2*>(p.lb.gdata);
+  // first chunk statically, further chunks from the global counter (groups differ 8x in cost)
+  uint64_t chunk = (uint64_t)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
+  while (chunk < nchunks) {
+    unsigned long long next_chunk = 0;
+    if (lane == 0) next_chunk = total_warps + atomicAdd(p.counter, 1ull);  // latency hidden behind this chunk
+    const uint64_t g0 = chunk * p.chunk;
+    const uint64_t g1 = (g0 + p.chunk < ngroups) ? g0 + p.chunk : ngroups;
+    uint64_t r = __ldg(p.lb.goff + g0);
+    uint32_t len_n = __ldg(p.lb.lens + g0 * 32 + lane);
+    uint32_t idx_n = __ldg(p.lb.perm + g0 * 32 + lane);
+    uint2 first_n = ld_stream8(gdata + r * 32 + lane);
+    for (uint64_t g = g0; g < g1; ++g) {
+      const uint32_t len2 = len_n, idx = idx_n;
+      const LaneSrc src{gdata + r * 32 + lane, first_n};
+      // rows of this group = ceil(longest candidate / 8); the next group's rows follow immediately, so its
+      // length / index / first row are requested now and arrive while this group is being scored
+      r += (__reduce_max_sync(0xffffffffu, len2) + 7u) >> 3;
+      if (g + 1 < g1) {
+        len_n = __ldg(p.lb.lens + (g + 1) * 32 + lane);
+        idx_n = __ldg(p.lb.perm + (g + 1) * 32 + lane);
+        first_n = ld_stream8(gdata + r * 32 + lane);
+      }
+      uint32_t ru = 0;
+      double rf = 0.0;
+      score_one<FAM, W>(pm_lane, src, len2, p.len1, p.epi, p.out_f64, p.two, ru, rf);
+      if (idx != 0xFFFFFFFFu) {
+        if (p.out_f64) reinterpret_cast<double*>(p.out)[idx] = rf;
+        else reinterpret_cast<uint32_t*>(p.out)[idx] = ru;
+      }
     }
+    chunk = __shfl_sync(0xffffffffu, next_chunk, 0);
   }
 }
 
@@ -467,9 +530,14 @@ static cudaError_t launch_lb_inst(const ScanLaunch& L, const void* tab) {
   p.out = L.out;
   p.out_f64 = L.out_is_f64;
   p.two = 2;
+  p.chunk = 16;
+  p.counter = L.lb_counter;
   p.epi = L.epi;
+  e = cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), L.stream);
+  if (e != cudaSuccess) return e;
   uint64_t grid = (uint64_t)L.sm_count * ctas_per_sm;
-  const uint64_t need = (L.lb.ngroups + NT / 32 - 1) / (NT / 32);
+  const uint64_t nchunks = (L.lb.ngroups + p.chunk - 1) / p.chunk;
+  const uint64_t need = (nchunks + NT / 32 - 1) / (NT / 32);
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
   kern<<<(uint32_t)grid, NT, smem, L.stream>>>(p);

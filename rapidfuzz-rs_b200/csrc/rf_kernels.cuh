@@ -29,12 +29,12 @@ struct QueryView {
 
 // Length-bucketed, warp-interleaved copy of the corpus (built once at corpus creation, rf_layout.cu):
 // candidates are sorted by length inside blocks of LB_BLOCK candidates and cut into groups of 32; group g
-// stores word k of its lane-l candidate at gdata[(goff[g] + k) * 32 + l]  (rows of 128 bytes).
+// stores bytes [8k, 8k+8) of its lane-l candidate at ((uint2*)gdata)[(goff[g] + k) * 32 + l]  (rows of 256 bytes).
 struct LbView {
   const uint32_t* perm;   // [ngroups*32] original candidate index, 0xFFFFFFFF = padding lane
   const uint32_t* lens;   // [ngroups*32] candidate length
   const uint64_t* goff;   // [ngroups+1]  first row of each group
-  const uint32_t* gdata;  // [total_rows*32 (+ slack)]
+  const uint32_t* gdata;  // [total_rows*64 (+ slack)] viewed as uint2 rows
   uint64_t ngroups;
 };
 constexpr uint32_t LB_BLOCK = 65536;
@@ -54,6 +54,7 @@ void lb_free(LbAlloc* a);
 struct ScanLaunch {
   CorpusView corpus;
   LbView lb;
+  unsigned long long* lb_counter;  // 8 bytes of device scratch for the chunk scheduler (one per in-flight launch)
   QueryView query;
   Epi epi;
   void* out;          // uint32_t[n] or double[n]

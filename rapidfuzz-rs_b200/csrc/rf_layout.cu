@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(1024) lb_sort_kernel(const uint32_t* __restric
   }
 }
 
-// rows (4-byte words per lane) of every group = ceil(max length in group / 4); grows[ngroups] = 0 (scan sentinel)
+// rows (8 bytes per lane) of every group = ceil(max length in group / 8); grows[ngroups] = 0 (scan sentinel)
 __global__ void lb_rows_kernel(const uint32_t* __restrict__ lens, uint64_t ngroups, uint32_t* __restrict__ grows) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint64_t warp_global = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -80,7 +80,7 @@ __global__ void lb_rows_kernel(const uint32_t* __restrict__ lens, uint64_t ngrou
   for (uint64_t g = warp_global; g <= ngroups; g += total_warps) {
     uint32_t m = 0;
     if (g < ngroups) m = __reduce_max_sync(0xffffffffu, lens[g * 32 + lane]);
-    if (lane == 0) grows[g] = (g < ngroups) ? (m + 3u) / 4u : 0u;
+    if (lane == 0) grows[g] = (g < ngroups) ? (m + 7u) / 8u : 0u;
   }
 }
 
@@ -97,21 +97,25 @@ __global__ void lb_fill_kernel(const uint8_t* __restrict__ chars, const uint32_t
     const uint32_t len = lens[g * 32 + lane];
     const uint64_t r0 = goff[g];
     const uint32_t rows = (uint32_t)(goff[g + 1] - r0);
-    uint32_t* dst = gdata + r0 * 32 + lane;
+    uint2* dst = reinterpret_cast<uint2*>(gdata) + r0 * 32 + lane;
     if (idx == 0xFFFFFFFFu || len == 0) {
-      for (uint32_t k = 0; k < rows; ++k) dst[(size_t)k * 32] = 0;
+      for (uint32_t k = 0; k < rows; ++k) dst[(size_t)k * 32] = make_uint2(0u, 0u);
       continue;
     }
     const uint64_t o = off_ld(o32, o64, idx);
     ByteReader rd(chars + (o & ~3ull), (uint32_t)(o & 3ull));
+    auto word = [&](uint32_t w4) -> uint32_t {  // 4-byte word w4 of the candidate, zero beyond its end
+      if (4 * w4 >= len) return 0u;
+      uint32_t w = rd.next4();
+      const uint32_t left = len - 4 * w4;
+      if (left < 4) w &= (1u << (8 * left)) - 1u;
+      return w;
+    };
     for (uint32_t k = 0; k < rows; ++k) {
-      uint32_t w = 0;
-      if (4 * k < len) {
-        w = rd.next4();
-        const uint32_t left = len - 4 * k;
-        if (left < 4) w &= (1u << (8 * left)) - 1u;
-      }
-      dst[(size_t)k * 32] = w;
+      uint2 v;
+      v.x = word(2 * k);
+      v.y = word(2 * k + 1);
+      dst[(size_t)k * 32] = v;
     }
   }
 }
@@ -167,8 +171,8 @@ cudaError_t lb_build(const CorpusView& c, cudaStream_t st, LbAlloc* out) {
   LB_TRY(cudaMemcpyAsync(&a.total_rows, a.goff + ngroups, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
   LB_TRY(cudaStreamSynchronize(st));
   // 8 rows of slack: readers prefetch one row past the end of a group
-  LB_TRY(cudaMalloc(&a.gdata, (a.total_rows + 8) * 128));
-  LB_TRY(cudaMemsetAsync(a.gdata + a.total_rows * 32, 0, 8 * 128, st));
+  LB_TRY(cudaMalloc(&a.gdata, (a.total_rows + 8) * 256));
+  LB_TRY(cudaMemsetAsync(a.gdata + a.total_rows * 64, 0, 8 * 256, st));
   {
     uint64_t blocks = (ngroups + 7) / 8;
     if (blocks > 148 * 64) blocks = 148 * 64;

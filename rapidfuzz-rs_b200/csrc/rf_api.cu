@@ -369,6 +369,10 @@ static rf_status make_epi(const rf_batch* b, rf_kind kind, const rf_args* args, 
     e->w_ins = e->w_del = e->w_sub = 1;
   }
   if (b->metric == RF_RATIO) e->kind = K_NORM_SIMILARITY;  // fuzz.rs:127-149 has one method only
+  e->unit32 = ((b->metric == RF_LEVENSHTEIN && e->wclass == WC_UNIFORM && e->w_ins == 1) || b->metric == RF_INDEL ||
+               b->metric == RF_LCS_SEQ || b->metric == RF_OSA)
+                  ? 1
+                  : 0;
   return RF_OK;
 }
 

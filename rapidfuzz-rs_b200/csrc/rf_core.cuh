@@ -338,6 +338,7 @@ struct Epi {
   uint64_t w_ins, w_del, w_sub;
   double prefix_weight;
   int quirks;
+  int unit32;  // set by the launcher: integer metric with unit weights -> 32-bit epilogue
 };
 
 RF_HD Family family_of(int metric, int wclass) {
@@ -387,6 +388,22 @@ RF_HD uint64_t int_distance(const Epi& e, uint64_t raw, uint64_t len1, uint64_t 
 
 // Integer-valued kinds.  Returns NONE_U32 for `None`.
 RF_HD uint32_t finish_int(const Epi& e, uint64_t raw, uint64_t len1, uint64_t len2) {
+  if (e.unit32) {  // unit weights and 32-bit lengths (the common case): same algebra in 32-bit arithmetic
+    const uint32_t r = (uint32_t)raw, l1 = (uint32_t)len1, l2 = (uint32_t)len2;
+    const uint32_t mx = l1 > l2 ? l1 : l2;
+    uint32_t d, M;
+    switch (e.metric) {
+      case M_INDEL: d = l1 + l2 - 2u * r; M = l1 + l2; break;
+      case M_LCS_SEQ: d = mx - r; M = mx; break;
+      default: d = r; M = mx; break;  // Levenshtein (1,1,1), OSA
+    }
+    const uint32_t v = (e.kind == K_DISTANCE) ? d : M - d;
+    if (e.has_cutoff) {
+      const bool ok = (e.kind == K_DISTANCE) ? ((uint64_t)v <= e.cutoff_u) : ((uint64_t)v >= e.cutoff_u);
+      if (!ok) return NONE_U32;
+    }
+    return v;
+  }
   const uint64_t d = int_distance(e, raw, len1, len2);
   if (e.kind == K_DISTANCE) {
     if (e.has_cutoff && d > e.cutoff_u) return NONE_U32;                     // common.rs:43-45

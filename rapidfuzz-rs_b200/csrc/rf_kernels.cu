@@ -120,16 +120,23 @@ struct TileSrc {
 __device__ __forceinline__ uint2 ld_stream8(const uint2* p) {  // streamed once: evict-first in L2, no L1 allocate
   return __ldcs(p);  // ld.global.cs: streaming (evict-first) so the scattered result sectors stay in L2
 }
+// ptxas sinks the row loads towards their first use to save registers, which shortens the look-ahead; an
+// explicit L2 prefetch a few rows ahead (it needs no destination register, so nothing is gained by moving
+// it) takes the DRAM latency off the critical path, the late load then only pays an L2 hit.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 struct LaneReader {
   static constexpr bool kRow8 = true;
   const uint2* p;  // next row to fetch
-  uint2 nxt;       // row already in flight / in registers
+  uint2 q0, q1;    // two rows in flight / in registers (16 chars of look-ahead)
   uint2 cur;
   uint32_t half;
-  __device__ __forceinline__ LaneReader(const uint2* second_row, uint2 first_row) : p(second_row), nxt(first_row), half(0) {}
+  __device__ __forceinline__ LaneReader(const uint2* third_row, uint2 first_row, uint2 second_row)
+      : p(third_row), q0(first_row), q1(second_row), half(0) {}
   __device__ __forceinline__ uint2 next8() {
-    const uint2 r = nxt;
-    nxt = ld_stream8(p);
+    const uint2 r = q0;
+    q0 = q1;
+    prefetch_l2(p + 32 * 6);
+    q1 = ld_stream8(p);
     p += 32;
     return r;
   }
@@ -141,9 +148,9 @@ struct LaneReader {
   }
 };
 struct LaneSrc {
-  const uint2* col;  // this lane's column: row k at col[k*32]
-  uint2 first;       // row 0, prefetched by the caller
-  __device__ __forceinline__ LaneReader reader() const { return LaneReader(col + 32, first); }
+  const uint2* col;     // this lane's column: row k at col[k*32]
+  uint2 first, second;  // rows 0 and 1, prefetched by the caller
+  __device__ __forceinline__ LaneReader reader() const { return LaneReader(col + 64, first, second); }
   __device__ __forceinline__ uint32_t byte(uint32_t j) const {
     return reinterpret_cast<const uint8_t*>(col + (size_t)(j >> 3) * 32)[j & 7u];
   }
@@ -175,15 +182,36 @@ __device__ __forceinline__ uint32_t lev_w1_u32_fast(uint32_t pm_lane_saddr, Rd r
     VN = HP & D0;                                                                    \
   }
   if constexpr (Rd::kRow8) {
+    // Two rows (16 chars) always in flight: rows i+2 / i+3 are requested before rows i / i+1 are consumed, and
+    // the loop is unrolled by two rows so that the loads rotate through registers without early moves.
+#define RF_LEV32_ROW(R)                                                                      \
+  {                                                                                          \
+    { const uint32_t w = (R).x; RF_LEV32_STEP(0) RF_LEV32_STEP(1) RF_LEV32_STEP(2) RF_LEV32_STEP(3) } \
+    { const uint32_t w = (R).y; RF_LEV32_STEP(0) RF_LEV32_STEP(1) RF_LEV32_STEP(2) RF_LEV32_STEP(3) } \
+  }
+    uint2 A = rd.q0, B = rd.q1;
+    const uint2* p = rd.p;
     const uint32_t nfull = len2 >> 3;
-    for (uint32_t i = 0; i < nfull; ++i) {
-      const uint2 ww = rd.next8();
-      { const uint32_t w = ww.x; RF_LEV32_STEP(0) RF_LEV32_STEP(1) RF_LEV32_STEP(2) RF_LEV32_STEP(3) }
-      { const uint32_t w = ww.y; RF_LEV32_STEP(0) RF_LEV32_STEP(1) RF_LEV32_STEP(2) RF_LEV32_STEP(3) }
+    uint32_t i = 0;
+    for (; i + 2 <= nfull; i += 2) {
+      prefetch_l2(p + 32 * 6);
+      prefetch_l2(p + 32 * 7);
+      const uint2 C = ld_stream8(p);
+      const uint2 D = ld_stream8(p + 32);
+      p += 64;
+      RF_LEV32_ROW(A)
+      RF_LEV32_ROW(B)
+      A = C;
+      B = D;
     }
+    if (i < nfull) {
+      RF_LEV32_ROW(A)
+      A = B;
+    }
+#undef RF_LEV32_ROW
     const uint32_t rem = len2 & 7u;
     if (rem) {
-      const uint2 ww = rd.next8();
+      const uint2 ww = A;
       { const uint32_t w = ww.x;
         RF_LEV32_STEP(0)
         if (rem > 1) RF_LEV32_STEP(1)
@@ -490,9 +518,10 @@ __global__ void __launch_bounds__(NT) scan_lb_kernel(const __grid_constant__ LbP
     uint32_t len_n = __ldg(p.lb.lens + g0 * 32 + lane);
     uint32_t idx_n = __ldg(p.lb.perm + g0 * 32 + lane);
     uint2 first_n = ld_stream8(gdata + r * 32 + lane);
+    uint2 second_n = ld_stream8(gdata + (r + 1) * 32 + lane);
     for (uint64_t g = g0; g < g1; ++g) {
       const uint32_t len2 = len_n, idx = idx_n;
-      const LaneSrc src{gdata + r * 32 + lane, first_n};
+      const LaneSrc src{gdata + r * 32 + lane, first_n, second_n};
       // rows of this group = ceil(longest candidate / 8); the next group's rows follow immediately, so its
       // length / index / first row are requested now and arrive while this group is being scored
       r += (__reduce_max_sync(0xffffffffu, len2) + 7u) >> 3;
@@ -500,6 +529,7 @@ __global__ void __launch_bounds__(NT) scan_lb_kernel(const __grid_constant__ LbP
         len_n = __ldg(p.lb.lens + (g + 1) * 32 + lane);
         idx_n = __ldg(p.lb.perm + (g + 1) * 32 + lane);
         first_n = ld_stream8(gdata + r * 32 + lane);
+        second_n = ld_stream8(gdata + (r + 1) * 32 + lane);
       }
       uint32_t ru = 0;
       double rf = 0.0;
@@ -550,13 +580,13 @@ cudaError_t launch_scan_lb(const ScanLaunch& L) {
   const bool w32 = L.query.len1 <= 32;
   switch (fam) {
     case F_LEV:
-      return w32 ? launch_lb_inst<F_LEV, uint32_t, 512>(L, L.query.tab32_top)
+      return w32 ? launch_lb_inst<F_LEV, uint32_t, 256>(L, L.query.tab32_top)
                  : launch_lb_inst<F_LEV, uint64_t, 512>(L, L.query.tab64_top);
     case F_OSA:
-      return w32 ? launch_lb_inst<F_OSA, uint32_t, 512>(L, L.query.tab32_top)
+      return w32 ? launch_lb_inst<F_OSA, uint32_t, 256>(L, L.query.tab32_top)
                  : launch_lb_inst<F_OSA, uint64_t, 512>(L, L.query.tab64_top);
     case F_LCS:
-      return w32 ? launch_lb_inst<F_LCS, uint32_t, 512>(L, L.query.tab32_bot)
+      return w32 ? launch_lb_inst<F_LCS, uint32_t, 256>(L, L.query.tab32_bot)
                  : launch_lb_inst<F_LCS, uint64_t, 512>(L, L.query.tab64_bot);
     default:
       return launch_lb_inst<F_JARO, uint64_t, 512>(L, L.query.tab64_bot);

@@ -170,9 +170,9 @@ cudaError_t lb_build(const CorpusView& c, cudaStream_t st, LbAlloc* out) {
   }
   LB_TRY(cudaMemcpyAsync(&a.total_rows, a.goff + ngroups, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
   LB_TRY(cudaStreamSynchronize(st));
-  // 8 rows of slack: readers prefetch one row past the end of a group
-  LB_TRY(cudaMalloc(&a.gdata, (a.total_rows + 8) * 256));
-  LB_TRY(cudaMemsetAsync(a.gdata + a.total_rows * 64, 0, 8 * 256, st));
+  // 16 rows of slack: readers load up to 3 rows and prefetch up to 8 rows past the end of the last group
+  LB_TRY(cudaMalloc(&a.gdata, (a.total_rows + 16) * 256));
+  LB_TRY(cudaMemsetAsync(a.gdata + a.total_rows * 64, 0, 16 * 256, st));
   {
     uint64_t blocks = (ngroups + 7) / 8;
     if (blocks > 148 * 64) blocks = 148 * 64;

@@ -58,6 +58,8 @@ static Epi make_epi(int metric, int kind, int has_cutoff, uint64_t cu, double cf
     else if (wi == wd && wi == ws) e.wclass = WC_UNIFORM;
     else e.wclass = WC_INDEL;
   }
+  e.unit32 = ((metric == M_LEVENSHTEIN && e.wclass == WC_UNIFORM && wi == 1) || metric == M_INDEL || metric == M_LCS_SEQ ||
+              metric == M_OSA) ? 1 : 0;   // same rule as rf_api.cu make_epi()
   return e;
 }
 

@@ -123,7 +123,10 @@ rf_status rf_batch_normalized_similarity_f64(const rf_batch* b, const rf_corpus*
 
 /* ---- many-vs-many (new on this side; the reference has no cdist -- SURVEY fact 3): for each of nq queries
  * the k best candidates by (distance ascending, index ascending); fewer than k hits are padded with
- * (UINT32_MAX, UINT32_MAX).  Levenshtein distance, queries of length <= 64.  idx/dist are [nq][k]. */
+ * (UINT32_MAX, UINT32_MAX).  Levenshtein distance (unit weights), queries of length <= 64, k <= 64; with
+ * args->has_cutoff only candidates with distance <= cutoff_u qualify.  Queries are host buffers (CSR like the
+ * corpus); idx/dist are [nq][k]; the _device variant writes device buffers and returns after the work on
+ * `stream` has completed (the per-call scratch is freed on return). */
 rf_status rf_cdist_topk_u8(const uint8_t* q_chars, const uint64_t* q_offsets, uint32_t nq, const rf_corpus* c,
                            const rf_args* args, uint32_t k, uint32_t* idx_host, uint32_t* dist_host);
 rf_status rf_cdist_topk_u8_device(const uint8_t* q_chars, const uint64_t* q_offsets, uint32_t nq,

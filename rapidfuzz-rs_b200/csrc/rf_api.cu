@@ -467,13 +467,124 @@ rf_status rf_batch_normalized_similarity_f64(const rf_batch* b, const rf_corpus*
 }
 
 // ------------------------------------------------------------------------------------------------ cdist
-rf_status rf_cdist_topk_u8_device(const uint8_t*, const uint64_t*, uint32_t, const rf_corpus*, const rf_args*, uint32_t,
-                                  uint32_t*, uint32_t*, void*) {
-  return fail(RF_ERR_UNSUPPORTED, "cdist top-k: not built yet");
+static rf_status cdist_impl(const uint8_t* q_chars, const uint64_t* q_offsets, uint32_t nq, const rf_corpus* c,
+                            const rf_args* args, uint32_t k, uint32_t* idx_out, uint32_t* dist_out, bool out_on_device,
+                            cudaStream_t user_stream) {
+  if (!c) return fail(RF_ERR_INVALID_ARG, "NULL corpus");
+  if (nq == 0) return RF_OK;
+  if (!q_offsets || !idx_out || !dist_out) return fail(RF_ERR_INVALID_ARG, "NULL argument");
+  if (k == 0 || k > 64) return fail(RF_ERR_INVALID_ARG, "k must be in 1..64");
+  if (q_offsets[0] != 0) return fail(RF_ERR_INVALID_ARG, "q_offsets[0] must be 0");
+  if (q_offsets[nq] && !q_chars) return fail(RF_ERR_INVALID_ARG, "q_chars is NULL");
+  rf_args def;
+  rf_args_default(&def);
+  const rf_args* a = args ? args : &def;
+  if (a->insertion_cost != 1 || a->deletion_cost != 1 || a->substitution_cost != 1)
+    return fail(RF_ERR_UNSUPPORTED, "cdist top-k supports unit Levenshtein weights only");
+  uint32_t max_len = 0;
+  for (uint32_t q = 0; q < nq; ++q) {
+    const uint64_t l = q_offsets[q + 1] - q_offsets[q];
+    if (l > 64) return fail(RF_ERR_UNSUPPORTED, "cdist top-k supports queries of at most 64 elements");
+    if (l > max_len) max_len = (uint32_t)l;
+  }
+  DeviceGuard g(c->device);
+  if (!g.ok) return fail(RF_ERR_CUDA, "cudaSetDevice failed");
+  const size_t kk = (size_t)nq * k;
+  cudaStream_t st = user_stream;
+  bool own_stream = false;
+  if (!out_on_device) {
+    RF_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    own_stream = true;
+  }
+  uint32_t *d_idx = nullptr, *d_dist = nullptr, *d_qlen = nullptr;
+  void* d_tabs = nullptr;
+  unsigned long long* d_scratch = nullptr;
+  rf_status s = RF_OK;
+  cudaError_t e = cudaSuccess;
+  const bool wide = max_len > 32;
+  if (c->n == 0 || !c->lb.gdata) {
+    // empty corpus (or no interleaved layout): every row is padding
+    if (c->n != 0) s = fail(RF_ERR_UNSUPPORTED, "cdist top-k needs the interleaved layout (build_interleaved_layout=1)");
+    else {
+      if (out_on_device) {
+        e = cudaMemsetAsync(idx_out, 0xFF, kk * 4, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(dist_out, 0xFF, kk * 4, st);
+        if (e != cudaSuccess) s = cuda_fail(e, "memset");
+      } else {
+        memset(idx_out, 0xFF, kk * 4);
+        memset(dist_out, 0xFF, kk * 4);
+      }
+    }
+  } else {
+    // per-query top-aligned match tables (pattern_match_vector.rs:213-224), built on the host
+    const size_t wsz = wide ? 8 : 4;
+    std::vector<uint8_t> tabs((size_t)nq * 256 * wsz, 0);
+    std::vector<uint32_t> qlen(nq);
+    for (uint32_t q = 0; q < nq; ++q) {
+      const uint8_t* s1 = q_chars + q_offsets[q];
+      const uint32_t l = (uint32_t)(q_offsets[q + 1] - q_offsets[q]);
+      qlen[q] = l;
+      if (wide) {
+        uint64_t* t = (uint64_t*)tabs.data() + (size_t)q * 256;
+        for (uint32_t i = 0; i < l; ++i) t[s1[i]] |= 1ull << (i + 64 - l);
+      } else {
+        uint32_t* t = (uint32_t*)tabs.data() + (size_t)q * 256;
+        for (uint32_t i = 0; i < l; ++i) t[s1[i]] |= 1u << (i + 32 - l);
+      }
+    }
+    const uint32_t parts = cdist_parts(sm_count_of(c->device));
+    do {
+      if ((e = cudaMalloc(&d_tabs, tabs.size())) != cudaSuccess) break;
+      if ((e = cudaMalloc(&d_qlen, nq * 4)) != cudaSuccess) break;
+      if ((e = cudaMalloc(&d_scratch, (size_t)nq * parts * k * 8)) != cudaSuccess) break;
+      if (!out_on_device) {
+        if ((e = cudaMalloc(&d_idx, kk * 4)) != cudaSuccess) break;
+        if ((e = cudaMalloc(&d_dist, kk * 4)) != cudaSuccess) break;
+      }
+      if ((e = cudaMemcpyAsync(d_tabs, tabs.data(), tabs.size(), cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+      if ((e = cudaMemcpyAsync(d_qlen, qlen.data(), nq * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+      CdistLaunch L{};
+      L.lb = LbView{c->lb.perm, c->lb.lens, c->lb.goff, c->lb.gdata, c->lb.ngroups};
+      L.total_rows = c->lb.total_rows;
+      L.q_tabs = d_tabs;
+      L.wide = wide ? 1 : 0;
+      L.q_len = d_qlen;
+      L.nq = nq;
+      L.k = k;
+      L.has_cutoff = a->has_cutoff ? 1 : 0;
+      L.cutoff = (uint32_t)(a->cutoff_u > 0xFFFFFFFEull ? 0xFFFFFFFEull : a->cutoff_u);
+      L.out_idx = out_on_device ? idx_out : d_idx;
+      L.out_dist = out_on_device ? dist_out : d_dist;
+      L.scratch = d_scratch;
+      L.parts = parts;
+      L.stream = st;
+      if ((e = launch_cdist_topk(L)) != cudaSuccess) break;
+      if (!out_on_device) {
+        if ((e = cudaMemcpyAsync(idx_out, d_idx, kk * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(dist_out, d_dist, kk * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
+      }
+      // the pageable host tables and the scratch buffers must outlive the asynchronous work
+      e = cudaStreamSynchronize(st);
+    } while (0);
+    if (e != cudaSuccess) s = cuda_fail(e, "cdist top-k");
+  }
+  if (d_tabs) cudaFree(d_tabs);
+  if (d_qlen) cudaFree(d_qlen);
+  if (d_scratch) cudaFree(d_scratch);
+  if (d_idx) cudaFree(d_idx);
+  if (d_dist) cudaFree(d_dist);
+  if (own_stream) cudaStreamDestroy(st);
+  return s;
 }
-rf_status rf_cdist_topk_u8(const uint8_t*, const uint64_t*, uint32_t, const rf_corpus*, const rf_args*, uint32_t,
-                           uint32_t*, uint32_t*) {
-  return fail(RF_ERR_UNSUPPORTED, "cdist top-k: not built yet");
+
+rf_status rf_cdist_topk_u8_device(const uint8_t* q_chars, const uint64_t* q_offsets, uint32_t nq, const rf_corpus* c,
+                                  const rf_args* args, uint32_t k, uint32_t* idx_device, uint32_t* dist_device,
+                                  void* stream) {
+  return cdist_impl(q_chars, q_offsets, nq, c, args, k, idx_device, dist_device, true, (cudaStream_t)stream);
+}
+rf_status rf_cdist_topk_u8(const uint8_t* q_chars, const uint64_t* q_offsets, uint32_t nq, const rf_corpus* c,
+                           const rf_args* args, uint32_t k, uint32_t* idx_host, uint32_t* dist_host) {
+  return cdist_impl(q_chars, q_offsets, nq, c, args, k, idx_host, dist_host, false, nullptr);
 }
 
 }  // extern "C"

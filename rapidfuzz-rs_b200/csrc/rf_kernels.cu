@@ -117,26 +117,32 @@ struct TileSrc {
   __device__ __forceinline__ TileReader reader() const { return TileReader(base, start); }
   __device__ __forceinline__ uint32_t byte(uint32_t j) const { return base[start + j]; }
 };
-__device__ __forceinline__ uint2 ld_stream8(const uint2* p) {  // streamed once: evict-first in L2, no L1 allocate
-  return __ldcs(p);  // ld.global.cs: streaming (evict-first) so the scattered result sectors stay in L2
+// STREAM: the row is read once per launch (one-vs-many) -> ld.global.cs (evict-first) so the scattered result
+// sectors stay in L2; otherwise (many-vs-many re-reads the shard per query) -> plain read-only load, L2 resident.
+template <bool STREAM>
+__device__ __forceinline__ uint2 ld_row8(const uint2* p) {
+  if constexpr (STREAM) return __ldcs(p);
+  else return __ldg(p);
 }
 // ptxas sinks the row loads towards their first use to save registers, which shortens the look-ahead; an
 // explicit L2 prefetch a few rows ahead (it needs no destination register, so nothing is gained by moving
 // it) takes the DRAM latency off the critical path, the late load then only pays an L2 hit.
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-struct LaneReader {
+template <bool STREAM>
+struct LaneReaderT {
   static constexpr bool kRow8 = true;
+  static constexpr bool kStream = STREAM;
   const uint2* p;  // next row to fetch
   uint2 q0, q1;    // two rows in flight / in registers (16 chars of look-ahead)
   uint2 cur;
   uint32_t half;
-  __device__ __forceinline__ LaneReader(const uint2* third_row, uint2 first_row, uint2 second_row)
+  __device__ __forceinline__ LaneReaderT(const uint2* third_row, uint2 first_row, uint2 second_row)
       : p(third_row), q0(first_row), q1(second_row), half(0) {}
   __device__ __forceinline__ uint2 next8() {
     const uint2 r = q0;
     q0 = q1;
-    prefetch_l2(p + 32 * 6);
-    q1 = ld_stream8(p);
+    if constexpr (STREAM) prefetch_l2(p + 32 * 6);
+    q1 = ld_row8<STREAM>(p);
     p += 32;
     return r;
   }
@@ -147,10 +153,11 @@ struct LaneReader {
     return cur.x;
   }
 };
-struct LaneSrc {
+template <bool STREAM>
+struct LaneSrcT {
   const uint2* col;     // this lane's column: row k at col[k*32]
   uint2 first, second;  // rows 0 and 1, prefetched by the caller
-  __device__ __forceinline__ LaneReader reader() const { return LaneReader(col + 64, first, second); }
+  __device__ __forceinline__ LaneReaderT<STREAM> reader() const { return LaneReaderT<STREAM>(col + 64, first, second); }
   __device__ __forceinline__ uint32_t byte(uint32_t j) const {
     return reinterpret_cast<const uint8_t*>(col + (size_t)(j >> 3) * 32)[j & 7u];
   }
@@ -194,10 +201,12 @@ __device__ __forceinline__ uint32_t lev_w1_u32_fast(uint32_t pm_lane_saddr, Rd r
     const uint32_t nfull = len2 >> 3;
     uint32_t i = 0;
     for (; i + 2 <= nfull; i += 2) {
-      prefetch_l2(p + 32 * 6);
-      prefetch_l2(p + 32 * 7);
-      const uint2 C = ld_stream8(p);
-      const uint2 D = ld_stream8(p + 32);
+      if constexpr (Rd::kStream) {
+        prefetch_l2(p + 32 * 6);
+        prefetch_l2(p + 32 * 7);
+      }
+      const uint2 C = ld_row8<Rd::kStream>(p);
+      const uint2 D = ld_row8<Rd::kStream>(p + 32);
       p += 64;
       RF_LEV32_ROW(A)
       RF_LEV32_ROW(B)
@@ -517,19 +526,19 @@ __global__ void __launch_bounds__(NT) scan_lb_kernel(const __grid_constant__ LbP
     uint64_t r = __ldg(p.lb.goff + g0);
     uint32_t len_n = __ldg(p.lb.lens + g0 * 32 + lane);
     uint32_t idx_n = __ldg(p.lb.perm + g0 * 32 + lane);
-    uint2 first_n = ld_stream8(gdata + r * 32 + lane);
-    uint2 second_n = ld_stream8(gdata + (r + 1) * 32 + lane);
+    uint2 first_n = ld_row8<true>(gdata + r * 32 + lane);
+    uint2 second_n = ld_row8<true>(gdata + (r + 1) * 32 + lane);
     for (uint64_t g = g0; g < g1; ++g) {
       const uint32_t len2 = len_n, idx = idx_n;
-      const LaneSrc src{gdata + r * 32 + lane, first_n, second_n};
+      const LaneSrcT<true> src{gdata + r * 32 + lane, first_n, second_n};
       // rows of this group = ceil(longest candidate / 8); the next group's rows follow immediately, so its
       // length / index / first row are requested now and arrive while this group is being scored
       r += (__reduce_max_sync(0xffffffffu, len2) + 7u) >> 3;
       if (g + 1 < g1) {
         len_n = __ldg(p.lb.lens + (g + 1) * 32 + lane);
         idx_n = __ldg(p.lb.perm + (g + 1) * 32 + lane);
-        first_n = ld_stream8(gdata + r * 32 + lane);
-        second_n = ld_stream8(gdata + (r + 1) * 32 + lane);
+        first_n = ld_row8<true>(gdata + r * 32 + lane);
+        second_n = ld_row8<true>(gdata + (r + 1) * 32 + lane);
       }
       uint32_t ru = 0;
       double rf = 0.0;
@@ -592,6 +601,191 @@ cudaError_t launch_scan_lb(const ScanLaunch& L) {
       return launch_lb_inst<F_JARO, uint64_t, 512>(L, L.query.tab64_bot);
   }
 }
+
+// ------------------------------------------------------------------------------------------------ cdist
+// many-vs-many Levenshtein top-k.  Each CTA owns a fixed slice of the (L2-resident) corpus shard, balanced by
+// rows; queries are the OUTER loop: per query the CTA rebuilds the lane-replicated match table in shared
+// memory (1 KB read, ~2% of the slice's scan time), scans its slice with the same per-lane kernel as the
+// one-vs-many path, and extracts its k best (distance, index) keys; a second kernel merges the per-CTA
+// candidates of every query.  The shard is read from HBM once and then served from L2.
+constexpr int CD_NT = 256;
+constexpr int CD_KEYCAP = 4096;   // keys scored per extraction batch
+constexpr int CD_KMAX = 128;
+constexpr unsigned long long CD_NOKEY = 0xFFFFFFFFFFFFFFFFull;
+
+struct CdistParams {
+  LbView lb;
+  uint64_t total_rows;
+  const void* tabs;        // [nq][256] top-aligned tables of W
+  const uint32_t* q_len;   // [nq]
+  uint32_t nq, k;
+  int has_cutoff;
+  uint32_t cutoff;
+  unsigned long long* scratch;  // [nq][gridDim.x][k]
+  uint32_t two;
+};
+
+// CTA-wide extraction of the k smallest keys of keys[0..m) (destroys them), ascending, into best[0..k)
+__device__ __forceinline__ void cd_extract(unsigned long long* keys, uint32_t m, unsigned long long* best, uint32_t k,
+                                           unsigned long long* wmin) {
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  unsigned long long last = CD_NOKEY;
+  for (uint32_t r = 0; r < k; ++r) {
+    unsigned long long mn = CD_NOKEY;
+    for (uint32_t i = tid; i < m; i += CD_NT) {
+      unsigned long long v = keys[i];
+      if (v == last && last != CD_NOKEY) { v = CD_NOKEY; keys[i] = v; }  // retire the previous winner
+      mn = v < mn ? v : mn;
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+      const unsigned long long o = __shfl_xor_sync(0xffffffffu, mn, d);
+      mn = o < mn ? o : mn;
+    }
+    if (lane == 0) wmin[warp] = mn;
+    __syncthreads();
+    unsigned long long g = wmin[0];
+#pragma unroll
+    for (int w = 1; w < CD_NT / 32; ++w) g = wmin[w] < g ? wmin[w] : g;
+    if (tid == 0) best[r] = g;
+    last = g;
+    __syncthreads();
+    if (g == CD_NOKEY) {  // nothing left: pad the remainder
+      for (uint32_t j = r + 1 + tid; j < k; j += CD_NT) best[j] = CD_NOKEY;
+      break;
+    }
+  }
+  __syncthreads();
+}
+
+template <class W>
+__global__ void __launch_bounds__(CD_NT) cdist_scan_kernel(const __grid_constant__ CdistParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  W* pm = reinterpret_cast<W*>(smem_raw);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw + sizeof(W) * 8192);  // CD_KEYCAP + CD_KMAX
+  unsigned long long* best = keys + CD_KEYCAP + CD_KMAX;                                           // CD_KMAX
+  unsigned long long* wmin = best + CD_KMAX;                                                       // CD_NT/32
+  __shared__ uint64_t s_glo, s_ghi;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint64_t ngroups = p.lb.ngroups;
+  if (tid < 2) {  // slice [g_lo, g_hi): equal share of rows (= work), found by binary search in goff
+    const uint64_t b = blockIdx.x + tid;
+    uint64_t g = ngroups;
+    if (b < gridDim.x) {
+      const uint64_t target = (uint64_t)((unsigned __int128)p.total_rows * b / gridDim.x);
+      uint64_t lo = 0, hi = ngroups;
+      while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (p.lb.goff[mid] < target) lo = mid + 1; else hi = mid;
+      }
+      g = lo;
+      if (b == 0) g = 0;
+    }
+    if (tid == 0) s_glo = g; else s_ghi = g;
+  }
+  __syncthreads();
+  const uint64_t g_lo = s_glo, g_hi = s_ghi;
+  const W* __restrict__ pm_lane = pm + lane;
+  const uint2* __restrict__ gdata = reinterpret_cast<const uint2*>(p.lb.gdata);
+  constexpr uint32_t GPB = CD_KEYCAP / 32;  // groups per extraction batch
+  for (uint32_t q = 0; q < p.nq; ++q) {
+    __syncthreads();
+    {
+      const W* __restrict__ t = reinterpret_cast<const W*>(p.tabs) + (size_t)q * 256;
+      for (uint32_t i = tid; i < 8192u; i += CD_NT) pm[i] = t[i >> 5];
+      for (uint32_t i = tid; i < p.k; i += CD_NT) best[i] = CD_NOKEY;
+    }
+    __syncthreads();
+    const uint32_t len1 = p.q_len[q];
+    for (uint64_t gb = g_lo; gb < g_hi; gb += GPB) {
+      const uint64_t ge = (gb + GPB < g_hi) ? gb + GPB : g_hi;
+      for (uint64_t g = gb + warp; g < ge; g += CD_NT / 32) {
+        const uint32_t len2 = __ldg(p.lb.lens + g * 32 + lane);
+        const uint32_t idx = __ldg(p.lb.perm + g * 32 + lane);
+        const uint64_t r = __ldg(p.lb.goff + g);
+        const uint2* col = gdata + r * 32 + lane;
+        const LaneSrcT<false> src{col, __ldg(col), __ldg(col + 32)};
+        uint32_t d;
+        if (len1 == 0) d = len2;
+        else if constexpr (sizeof(W) == 4) d = lev_w1_u32_fast(smem_u32(pm_lane), src.reader(), len2, len1, p.two);
+        else {
+          auto tab = [&](uint32_t ch) -> W { return pm_lane[ch * 32u]; };
+          d = lev_w1<W>(tab, src.reader(), len2, len1);
+        }
+        const bool ok = idx != 0xFFFFFFFFu && !(p.has_cutoff && d > p.cutoff);
+        keys[(uint32_t)(g - gb) * 32 + lane] = ok ? (((unsigned long long)d << 32) | idx) : CD_NOKEY;
+      }
+      __syncthreads();
+      // merge with the running best of earlier batches, then keep the k smallest
+      const uint32_t m = (uint32_t)(ge - gb) * 32;
+      for (uint32_t i = tid; i < p.k; i += CD_NT) keys[m + i] = best[i];
+      __syncthreads();
+      cd_extract(keys, m + p.k, best, p.k, wmin);
+    }
+    unsigned long long* out = p.scratch + ((size_t)q * gridDim.x + blockIdx.x) * p.k;
+    for (uint32_t i = tid; i < p.k; i += CD_NT) out[i] = best[i];
+  }
+}
+
+// one CTA per query: k smallest of the parts*k per-CTA keys -> (idx, dist) rows
+__global__ void __launch_bounds__(CD_NT) cdist_merge_kernel(const unsigned long long* __restrict__ scratch, uint32_t parts,
+                                                            uint32_t k, uint32_t* __restrict__ out_idx,
+                                                            uint32_t* __restrict__ out_dist) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);  // parts*k
+  unsigned long long* best = keys + (size_t)parts * k;
+  unsigned long long* wmin = best + CD_KMAX;
+  const uint32_t q = blockIdx.x, m = parts * k;
+  const unsigned long long* src = scratch + (size_t)q * m;
+  for (uint32_t i = threadIdx.x; i < m; i += CD_NT) keys[i] = src[i];
+  __syncthreads();
+  cd_extract(keys, m, best, k, wmin);
+  for (uint32_t i = threadIdx.x; i < k; i += CD_NT) {
+    const unsigned long long v = best[i];
+    out_idx[(size_t)q * k + i] = (v == CD_NOKEY) ? 0xFFFFFFFFu : (uint32_t)v;
+    out_dist[(size_t)q * k + i] = (v == CD_NOKEY) ? 0xFFFFFFFFu : (uint32_t)(v >> 32);
+  }
+}
+
+uint32_t cdist_parts(int sm_count) { return (uint32_t)sm_count * 2u; }
+
+cudaError_t launch_cdist_topk(const CdistLaunch& L) {
+  if (L.k == 0 || L.k > CD_KMAX) return cudaErrorInvalidValue;
+  CdistParams p{};
+  p.lb = L.lb;
+  p.total_rows = L.total_rows;
+  p.tabs = L.q_tabs;
+  p.q_len = L.q_len;
+  p.nq = L.nq;
+  p.k = L.k;
+  p.has_cutoff = L.has_cutoff;
+  p.cutoff = L.cutoff;
+  p.scratch = L.scratch;
+  p.two = 2;
+  const uint32_t parts = L.parts;
+  const size_t wsz = L.wide ? 8 : 4;
+  const size_t smem = wsz * 8192 + sizeof(unsigned long long) * (CD_KEYCAP + CD_KMAX + CD_KMAX + CD_NT / 32);
+  cudaError_t e;
+  if (L.wide) {
+    e = cudaFuncSetAttribute(cdist_scan_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cdist_scan_kernel<uint64_t><<<parts, CD_NT, smem, L.stream>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(cdist_scan_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cdist_scan_kernel<uint32_t><<<parts, CD_NT, smem, L.stream>>>(p);
+  }
+  g_launches.fetch_add(1);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const size_t msmem = sizeof(unsigned long long) * ((size_t)parts * L.k + CD_KMAX + CD_NT / 32);
+  e = cudaFuncSetAttribute(cdist_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem);
+  if (e != cudaSuccess) return e;
+  cdist_merge_kernel<<<L.nq, CD_NT, msmem, L.stream>>>(L.scratch, parts, L.k, L.out_idx, L.out_dist);
+  g_launches.fetch_add(1);
+  return cudaGetLastError();
+}
+
 
 // ------------------------------------------------------------------------------------------------ mw
 struct MwParams {

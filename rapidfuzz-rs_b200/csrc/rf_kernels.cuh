@@ -72,21 +72,22 @@ cudaError_t launch_scan_mw(const ScanLaunch& L);
 // Jaro / Jaro-Winkler with a multi-word query (65..2048).
 cudaError_t launch_jaro_mw(const ScanLaunch& L);
 
-// many-vs-many Levenshtein top-k (queries <= 64).
+// many-vs-many Levenshtein top-k (queries <= 64) over the interleaved layout.
 struct CdistLaunch {
-  CorpusView corpus;
-  const uint64_t* q_tab64_top;  // [nq][256] top-aligned 64-bit tables
-  const uint32_t* q_len;        // [nq]
+  LbView lb;
+  uint64_t total_rows;
+  const void* q_tabs;       // [nq][256] top-aligned tables: uint32_t if !wide (all queries <= 32) else uint64_t
+  int wide;
+  const uint32_t* q_len;    // [nq]
   uint32_t nq;
-  uint32_t k;
+  uint32_t k;               // 1..64
   int has_cutoff;
   uint32_t cutoff;
-  uint32_t* out_idx;   // [nq][k]
-  uint32_t* out_dist;  // [nq][k]
-  unsigned long long* scratch;  // [nq][parts][k] packed (dist<<32|idx) partial results
-  uint32_t parts;
+  uint32_t* out_idx;        // [nq][k]
+  uint32_t* out_dist;       // [nq][k]
+  unsigned long long* scratch;  // [nq][parts][k] packed (dist<<32|idx) per-CTA candidates
+  uint32_t parts;           // CTAs of the scan kernel (cdist_parts)
   cudaStream_t stream;
-  int sm_count;
 };
 cudaError_t launch_cdist_topk(const CdistLaunch& L);
 uint32_t cdist_parts(int sm_count);

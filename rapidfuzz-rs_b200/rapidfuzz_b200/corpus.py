@@ -91,3 +91,30 @@ def synth_corpus(seed, query, n, min_len, max_len, kmax, nthreads=0, pinned=Fals
     _ffi.check(l.rf_synth_corpus_u8(seed, query.ctypes.data, len(query), n, min_len, max_len, kmax,
                                     offsets.ctypes.data, chars.ctypes.data, nthreads))
     return chars, offsets
+
+
+def cdist_topk(queries, corpus, k=10, score_cutoff=None):
+    """Many-vs-many Levenshtein: for every query the k best candidates of `corpus` by (distance, index).
+    New on this side (the reference has no cdist).  queries: list of bytes/str, or (chars u8, offsets u64).
+    Returns (idx [nq,k] uint32, dist [nq,k] uint32); rows with fewer than k hits are padded with 0xFFFFFFFF."""
+    import ctypes as C
+    if isinstance(queries, tuple):
+        q_chars = np.ascontiguousarray(queries[0], dtype=np.uint8)
+        q_off = np.ascontiguousarray(queries[1], dtype=np.uint64)
+    else:
+        bs = [q.encode("latin-1") if isinstance(q, str) else bytes(q) for q in queries]
+        q_off = np.zeros(len(bs) + 1, dtype=np.uint64)
+        if bs:
+            q_off[1:] = np.cumsum([len(b) for b in bs])
+        q_chars = np.frombuffer(b"".join(bs), dtype=np.uint8)
+    nq = len(q_off) - 1
+    a = _ffi.RfArgs()
+    _ffi.lib().rf_args_default(C.byref(a))
+    if score_cutoff is not None:
+        a.has_cutoff = 1
+        a.cutoff_u = int(score_cutoff)
+    idx = np.empty((nq, k), dtype=np.uint32)
+    dist = np.empty((nq, k), dtype=np.uint32)
+    _ffi.check(_ffi.lib().rf_cdist_topk_u8(q_chars.ctypes.data, q_off.ctypes.data, nq, corpus._h, C.byref(a), k,
+                                          idx.ctypes.data, dist.ctypes.data))
+    return idx, dist

@@ -240,3 +240,38 @@ def test_large_corpus_properties():
         assert gpu_batch("levenshtein", "distance", c, cq)[0] == d[i]
     cq.close()
     corpus.close()
+
+
+def _oracle_topk(queries, chars, offsets, k, cutoff=None):
+    n = len(offsets) - 1
+    idx = np.full((len(queries), k), 0xFFFFFFFF, dtype=np.uint32)
+    dist = np.full((len(queries), k), 0xFFFFFFFF, dtype=np.uint32)
+    for qi, q in enumerate(queries):
+        d = orc.batch("levenshtein", "distance", q, chars, offsets, nthreads=0).astype(np.int64)
+        keys = d * (1 << 32) + np.arange(n)
+        if cutoff is not None:
+            keys = keys[d <= cutoff]
+        keys = np.sort(keys)[:k]
+        idx[qi, :len(keys)] = (keys & 0xFFFFFFFF).astype(np.uint32)
+        dist[qi, :len(keys)] = (keys >> 32).astype(np.uint32)
+    return idx, dist
+
+
+@pytest.mark.parametrize("qlens,n,k", [([32], 50000, 10), ([0, 1, 7, 20, 32], 20000, 10), ([5, 33, 40, 64], 30000, 7),
+                                        ([32], 100, 10), ([16], 5, 10), ([32], 300000, 64)])
+def test_cdist_topk_vs_oracle_full_matrix(qlens, n, k):
+    """config 5 shape (small): per-query top-k by (distance, index) against the oracle's full matrix."""
+    rng = np.random.default_rng(n + k)
+    queries = []
+    for rep in range(12):
+        for ql in qlens:
+            queries.append(rf.synth_query(1000 + rep, ql))
+    base = queries[0] if len(queries[0]) else rf.synth_query(5, 32)
+    chars, offsets = rf.synth_corpus(5, base, n, 8, 64, 16)
+    corpus = rf.Corpus(chars, offsets)
+    for cutoff in (None, 20, 3):
+        idx, dist = rf.cdist_topk(queries, corpus, k=k, score_cutoff=cutoff)
+        eidx, edist = _oracle_topk(queries, chars, offsets, k, cutoff)
+        assert np.array_equal(dist, edist), (qlens, n, k, cutoff)
+        assert np.array_equal(idx, eidx), (qlens, n, k, cutoff)
+    corpus.close()

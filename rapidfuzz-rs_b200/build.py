@@ -34,6 +34,8 @@ def build(force=False, verbose=False):
            "-shared", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lgomp"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
+    if os.environ.get("RF_DEBUG_MW"):
+        cmd.insert(1, "-DRF_DEBUG_MW")
     subprocess.check_call(cmd)
     return LIB
 

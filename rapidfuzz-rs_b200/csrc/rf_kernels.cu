@@ -14,6 +14,7 @@
 //  jaro_mw_kernel  Jaro / Jaro-Winkler with a multi-word query, thread per candidate.
 //  cdist_*         many queries x corpus tile, per-query top-k.
 #include <atomic>
+#include <cstdio>
 #include <cstdlib>
 #include "rf_kernels.cuh"
 
@@ -807,10 +808,10 @@ __global__ void __launch_bounds__(256) scan_mw_kernel(const __grid_constant__ Mw
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t G = p.G;
   const uint32_t gl = lane & (G - 1u);       // lane within the candidate's group
-  const uint32_t gpw = 32u / G;              // groups (candidates) per warp
+  const uint32_t gpw = 32u / G;              // groups (candidates) per warp pass
   const uint32_t sub = lane / G;
   const uint64_t warp_global = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const uint64_t total_groups = (uint64_t)gridDim.x * (blockDim.x >> 5) * gpw;
+  const uint64_t total_warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
   const uint32_t words = p.words;
   const uint32_t w0 = gl * WPL;                                // first 64-bit block owned by this lane
   const uint32_t act = (words + WPL - 1) / WPL;                // lanes that own at least one block
@@ -818,131 +819,176 @@ __global__ void __launch_bounds__(256) scan_mw_kernel(const __grid_constant__ Mw
   const uint32_t last_bit = (p.len1 - 1u) & 63u;
   const bool off64 = p.off64 != nullptr;
   const uint64_t* __restrict__ pm = p.pm;
+  // Levenshtein distance with a cutoff: candidates are dropped on |len1-len2| (levenshtein.rs:1045-1047) and
+  // abandoned as soon as the bottom-row score can no longer come back under the cutoff (the reference's
+  // Ukkonen band does the same job, levenshtein.rs:897-985); both only ever turn a result into None.
+  const bool lev_cut = (FAM == F_LEV) && p.epi.metric == M_LEVENSHTEIN && p.epi.kind == K_DISTANCE && p.epi.has_cutoff &&
+                       p.epi.wclass == WC_UNIFORM;
+  const uint64_t cut64 = lev_cut ? p.epi.cutoff_u / p.epi.w_ins : 0;
+  const uint32_t cut = cut64 > 0x7FFFFFFFull ? 0x7FFFFFFFu : (uint32_t)cut64;
 
-  for (uint64_t cw = warp_global * gpw; cw < p.n; cw += total_groups) {  // warp-uniform trip count
-    const uint64_t c = cw + sub;
-    const bool valid = c < p.n;
-    uint64_t o0 = 0;
-    uint32_t len2 = 0;
-    if (valid) {
-      o0 = off64 ? p.off64[c] : (uint64_t)p.off32[c];
-      const uint64_t o1 = off64 ? p.off64[c + 1] : (uint64_t)p.off32[c + 1];
-      len2 = (uint32_t)(o1 - o0);
-    }
-    // |len1-len2| already exceeds the cutoff -> None without touching the bytes (levenshtein.rs:1045-1047)
-    bool skip = false;
-    if (FAM == F_LEV && p.epi.metric == M_LEVENSHTEIN && p.epi.kind == K_DISTANCE && p.epi.has_cutoff) {
-      const uint64_t diff = p.len1 > len2 ? p.len1 - len2 : len2 - p.len1;
-      skip = diff * p.epi.w_ins > p.epi.cutoff_u;
-    }
-    const uint8_t* __restrict__ txt = p.chars + o0;
-    const uint32_t my_steps = (valid && !skip && len2) ? len2 + act - 1u : 0u;
-    const uint32_t steps = __reduce_max_sync(0xffffffffu, my_steps);
-
-    uint64_t VP[WPL], VN[WPL], D0[WPL], PMo[WPL], Xc[WPL], Xn[WPL];
-#pragma unroll
-    for (int k = 0; k < WPL; ++k) {
-      VP[k] = (FAM == F_LCS) ? ~0ull : ~0ull;  // LCS: VP plays the role of S
-      VN[k] = 0; D0[k] = 0; PMo[k] = 0; Xc[k] = 0; Xn[k] = 0;
-    }
-    int32_t score = 0;
-    // lane 0 of a group feeds the text: ch_cur = text[t], two bytes prefetched ahead
-    uint32_t ch_cur = 0, c1 = 0, c2 = 0;
-    if (gl == 0 && my_steps) {
-      ch_cur = txt[0];
-      c1 = len2 > 1 ? txt[1] : 0;
-      c2 = len2 > 2 ? txt[2] : 0;
-#pragma unroll
-      for (int k = 0; k < WPL; ++k) Xc[k] = (w0 + k < words) ? __ldg(pm + (uint64_t)ch_cur * words + w0 + k) : 0ull;
-    }
-    uint32_t cout = 0;
-    for (uint32_t t = 0; t < steps; ++t) {
-      const uint32_t pk_in = __shfl_up_sync(0xffffffffu, ch_cur | (cout << 8), 1, G);
-      uint32_t ch_nxt, cin;
-      if (gl == 0) {
-        ch_nxt = c1;
-        c1 = c2;
-        c2 = (t + 3 < len2) ? (uint32_t)txt[t + 3] : 0u;
-        cin = (FAM == F_LCS) ? 0u : 1u;  // Levenshtein/OSA: +1 horizontal delta enters row 0; LCS: no carry
+  // A warp takes 32 consecutive candidates at a time: every lane classifies one of them, trivial ones are
+  // finished on the spot, the survivors are compacted with a ballot and scored gpw at a time.
+  for (uint64_t base = warp_global * 32; base < p.n; base += total_warps * 32) {
+    const uint64_t c_mine = base + lane;
+    uint64_t o0_mine = 0;
+    uint32_t len2_mine = 0;
+    bool need = false;
+    if (c_mine < p.n) {
+      o0_mine = off64 ? p.off64[c_mine] : (uint64_t)p.off32[c_mine];
+      const uint64_t o1 = off64 ? p.off64[c_mine + 1] : (uint64_t)p.off32[c_mine + 1];
+      len2_mine = (uint32_t)(o1 - o0_mine);
+      const uint32_t diff = p.len1 > len2_mine ? p.len1 - len2_mine : len2_mine - p.len1;
+      if (lev_cut && diff > cut) {
+        if (p.out_f64) reinterpret_cast<double*>(p.out)[c_mine] = qnan();
+        else reinterpret_cast<uint32_t*>(p.out)[c_mine] = NONE_U32;
+      } else if (len2_mine == 0) {
+        const uint32_t raw = (FAM == F_LCS) ? 0u : p.len1;
+        if (p.out_f64) reinterpret_cast<double*>(p.out)[c_mine] = finish_norm(p.epi, raw, p.len1, 0);
+        else reinterpret_cast<uint32_t*>(p.out)[c_mine] = finish_int(p.epi, raw, p.len1, 0);
       } else {
-        ch_nxt = pk_in & 0xffu;
-        cin = pk_in >> 8;
+        need = true;
       }
-      // this lane's match words for the NEXT step (text char flows one step ahead of the carries)
-#pragma unroll
-      for (int k = 0; k < WPL; ++k) Xn[k] = (w0 + k < words) ? __ldg(pm + (uint64_t)ch_nxt * words + w0 + k) : 0ull;
+    }
+    uint32_t todo = __ballot_sync(0xffffffffu, need);
+#ifdef RF_DEBUG_MW
+    if (lane == 0) printf("warp %llu base %llu todo %08x\n", (unsigned long long)warp_global, (unsigned long long)base, todo);
+#endif
+    while (todo) {
+      const uint32_t src = __fns(todo, 0, sub + 1);  // this sub-group's candidate = (sub+1)-th surviving lane
+      const bool have = src != 0xFFFFFFFFu;
+      const uint32_t srcl = have ? src : 0u;
+      const uint64_t c = __shfl_sync(0xffffffffu, c_mine, srcl);
+      const uint64_t o0 = __shfl_sync(0xffffffffu, o0_mine, srcl);
+      const uint32_t len2_src = __shfl_sync(0xffffffffu, len2_mine, srcl);
+      const uint32_t len2 = have ? len2_src : 0u;
+      for (uint32_t i = 0; i < gpw; ++i) todo &= todo - 1;  // retire the gpw candidates of this pass
 
-      const int32_t j = (int32_t)t - (int32_t)gl;  // text column handled by this lane in this step
-      const bool active = (gl < act) && j >= 0 && j < (int32_t)len2 && my_steps;
-      if (active) {
-        if constexpr (FAM == F_LCS) {
-          uint64_t carry = cin & 1u;
+      const uint8_t* __restrict__ txt = p.chars + o0;
+      const uint32_t my_steps = have ? len2 + act - 1u : 0u;
+      const uint32_t steps = __reduce_max_sync(0xffffffffu, my_steps);
+
+      uint64_t VP[WPL], VN[WPL], D0[WPL], PMo[WPL], Xc[WPL], Xn[WPL];
 #pragma unroll
-          for (int k = 0; k < WPL; ++k) {
-            const uint64_t S = VP[k];
-            const uint64_t u = S & Xc[k];
-            const uint64_t x1 = S + u;
-            const uint64_t x2 = x1 + carry;
-            carry = (uint64_t)(x1 < S) | (uint64_t)(x2 < x1);
-            VP[k] = x2 | (S - u);
-          }
-          cout = (uint32_t)carry;
+      for (int k = 0; k < WPL; ++k) {
+        VP[k] = ~0ull;  // LCS: VP plays the role of S
+        VN[k] = 0; D0[k] = 0; PMo[k] = 0; Xc[k] = 0; Xn[k] = 0;
+      }
+      int32_t score = 0;
+      bool dead = false;  // abandoned: result is None
+      // lane 0 of a group feeds the text: ch_cur = text[t], two bytes prefetched ahead
+      uint32_t ch_cur = 0, c1 = 0, c2 = 0;
+      if (gl == 0 && my_steps) {
+        ch_cur = txt[0];
+        c1 = len2 > 1 ? txt[1] : 0;
+        c2 = len2 > 2 ? txt[2] : 0;
+#pragma unroll
+        for (int k = 0; k < WPL; ++k) Xc[k] = (w0 + k < words) ? __ldg(pm + (uint64_t)ch_cur * words + w0 + k) : 0ull;
+      }
+      uint32_t cout = 0;
+      for (uint32_t t = 0; t < steps; ++t) {
+        const uint32_t pk_in = __shfl_up_sync(0xffffffffu, ch_cur | (cout << 8), 1, G);
+        uint32_t ch_nxt, cin;
+        if (gl == 0) {
+          ch_nxt = c1;
+          c1 = c2;
+          c2 = (t + 3 < len2) ? (uint32_t)txt[t + 3] : 0u;
+          cin = (FAM == F_LCS) ? 0u : 1u;  // Levenshtein/OSA: +1 horizontal delta enters row 0; LCS: no carry
         } else {
-          uint64_t hp_c = cin & 1u, hn_c = (cin >> 1) & 1u, tr_c = (cin >> 2) & 1u;
+          ch_nxt = pk_in & 0xffu;
+          cin = pk_in >> 8;
+        }
+        // this lane's match words for the NEXT step (text char flows one step ahead of the carries)
 #pragma unroll
-          for (int k = 0; k < WPL; ++k) {
-            const uint64_t X0 = Xc[k];
-            const uint64_t X = X0 | hn_c;
-            uint64_t d0 = ((((X & VP[k]) + VP[k]) ^ VP[k]) | X) | VN[k];
-            if constexpr (FAM == F_OSA) {
-              const uint64_t nd = (~D0[k]) & X0;
-              d0 |= ((nd << 1) | tr_c) & PMo[k];
-              tr_c = nd >> 63;
-              D0[k] = d0;
-              PMo[k] = X0;
+        for (int k = 0; k < WPL; ++k) Xn[k] = (w0 + k < words) ? __ldg(pm + (uint64_t)ch_nxt * words + w0 + k) : 0ull;
+
+        const int32_t j = (int32_t)t - (int32_t)gl;  // text column handled by this lane in this step
+        const bool active = (gl < act) && j >= 0 && j < (int32_t)len2 && my_steps && !dead;
+        if (active) {
+          if constexpr (FAM == F_LCS) {
+            uint64_t carry = cin & 1u;
+#pragma unroll
+            for (int k = 0; k < WPL; ++k) {
+              const uint64_t S = VP[k];
+              const uint64_t u = S & Xc[k];
+              const uint64_t x1 = S + u;
+              const uint64_t x2 = x1 + carry;
+              carry = (uint64_t)(x1 < S) | (uint64_t)(x2 < x1);
+              VP[k] = x2 | (S - u);
             }
-            uint64_t HP = VN[k] | ~(d0 | VP[k]);
-            uint64_t HN = d0 & VP[k];
-            if (gl == last_owner && k == (int)last_k)
-              score += (int32_t)((HP >> last_bit) & 1u) - (int32_t)((HN >> last_bit) & 1u);
-            const uint64_t hp_o = HP >> 63, hn_o = HN >> 63;
-            HP = (HP << 1) | hp_c;
-            HN = (HN << 1) | hn_c;
-            VP[k] = HN | ~(d0 | HP);
-            VN[k] = HP & d0;
-            hp_c = hp_o;
-            hn_c = hn_o;
+            cout = (uint32_t)carry;
+          } else {
+            uint64_t hp_c = cin & 1u, hn_c = (cin >> 1) & 1u, tr_c = (cin >> 2) & 1u;
+#pragma unroll
+            for (int k = 0; k < WPL; ++k) {
+              const uint64_t X0 = Xc[k];
+              const uint64_t X = X0 | hn_c;
+              uint64_t d0 = ((((X & VP[k]) + VP[k]) ^ VP[k]) | X) | VN[k];
+              if constexpr (FAM == F_OSA) {
+                const uint64_t nd = (~D0[k]) & X0;
+                d0 |= ((nd << 1) | tr_c) & PMo[k];
+                tr_c = nd >> 63;
+                D0[k] = d0;
+                PMo[k] = X0;
+              }
+              uint64_t HP = VN[k] | ~(d0 | VP[k]);
+              uint64_t HN = d0 & VP[k];
+              if (gl == last_owner && k == (int)last_k)
+                score += (int32_t)((HP >> last_bit) & 1u) - (int32_t)((HN >> last_bit) & 1u);
+              const uint64_t hp_o = HP >> 63, hn_o = HN >> 63;
+              HP = (HP << 1) | hp_c;
+              HN = (HN << 1) | hn_c;
+              VP[k] = HN | ~(d0 | HP);
+              VN[k] = HP & d0;
+              hp_c = hp_o;
+              hn_c = hn_o;
+            }
+            cout = (uint32_t)hp_c | ((uint32_t)hn_c << 1) | ((uint32_t)tr_c << 2);
           }
-          cout = (uint32_t)hp_c | ((uint32_t)hn_c << 1) | ((uint32_t)tr_c << 2);
+        }
+        ch_cur = ch_nxt;
+#pragma unroll
+        for (int k = 0; k < WPL; ++k) Xc[k] = Xn[k];
+
+        if (lev_cut && (t & 7u) == 7u) {
+          // bottom-row score after column jl: D[m][jl] = len1 + score; each remaining column lowers it by <= 1
+          const int32_t jl = (int32_t)t - (int32_t)last_owner;
+          bool hopeless = false;
+          if (gl == last_owner && jl >= 0 && jl < (int32_t)len2 && !dead && my_steps) {
+            const int64_t cur = (int64_t)p.len1 + score;
+            hopeless = cur > (int64_t)cut + (int64_t)(len2 - 1 - (uint32_t)jl);
+          }
+          const int hopeless_g = __shfl_sync(0xffffffffu, (int)hopeless, last_owner, G);  // every lane, no short-circuit
+          dead = dead || (hopeless_g != 0);
+#ifdef RF_DEBUG_MW
+          if (lane == 0) printf("  t %u steps %u my_steps %u dead %d score %d\n", t, steps, my_steps, (int)dead, score);
+#endif
+          if (__ballot_sync(0xffffffffu, my_steps && !dead && t + 1 < my_steps) == 0) break;  // whole warp done
         }
       }
-      ch_cur = ch_nxt;
-#pragma unroll
-      for (int k = 0; k < WPL; ++k) Xc[k] = Xn[k];
-    }
 
-    // ---- result
-    uint32_t raw;
-    if constexpr (FAM == F_LCS) {
-      uint32_t cnt = 0;
+      // ---- result
+      uint32_t raw;
+      if constexpr (FAM == F_LCS) {
+        uint32_t cnt = 0;
 #pragma unroll
-      for (int k = 0; k < WPL; ++k)
-        if (w0 + k < words) cnt += (uint32_t)__popcll(~VP[k]);
-      for (uint32_t d = G >> 1; d >= 1; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d, G);
-      raw = cnt;
-    } else {
-      const int32_t sc = __shfl_sync(0xffffffffu, score, last_owner, G);
-      raw = (uint32_t)((int32_t)p.len1 + sc);
-      if (len2 == 0) raw = p.len1;
-    }
-    if (valid && gl == 0) {
-      if (skip) {
-        if (p.out_f64) reinterpret_cast<double*>(p.out)[c] = qnan();
-        else reinterpret_cast<uint32_t*>(p.out)[c] = NONE_U32;
-      } else if (p.out_f64) {
-        reinterpret_cast<double*>(p.out)[c] = finish_norm(p.epi, raw, p.len1, len2);
+        for (int k = 0; k < WPL; ++k)
+          if (w0 + k < words) cnt += (uint32_t)__popcll(~VP[k]);
+        for (uint32_t d = G >> 1; d >= 1; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d, G);
+        raw = cnt;
       } else {
-        reinterpret_cast<uint32_t*>(p.out)[c] = finish_int(p.epi, raw, p.len1, len2);
+        const int32_t sc = __shfl_sync(0xffffffffu, score, last_owner, G);
+        raw = (uint32_t)((int32_t)p.len1 + sc);
+      }
+      if (have && gl == 0) {
+        if (dead) {
+          if (p.out_f64) reinterpret_cast<double*>(p.out)[c] = qnan();
+          else reinterpret_cast<uint32_t*>(p.out)[c] = NONE_U32;
+        } else if (p.out_f64) {
+          reinterpret_cast<double*>(p.out)[c] = finish_norm(p.epi, raw, p.len1, len2);
+        } else {
+          reinterpret_cast<uint32_t*>(p.out)[c] = finish_int(p.epi, raw, p.len1, len2);
+        }
       }
     }
   }
@@ -969,8 +1015,8 @@ static cudaError_t launch_mw_fam(const ScanLaunch& L) {
   uint32_t G = 1;
   while (G < act) G <<= 1;
   p.G = G;
-  const uint32_t gpw = 32u / G, warps_per_block = 8;
-  const uint64_t warps_needed = (p.n + gpw - 1) / gpw;
+  const uint32_t warps_per_block = 8;
+  const uint64_t warps_needed = (p.n + 31) / 32;
   uint64_t blocks = (warps_needed + warps_per_block - 1) / warps_per_block;
   const uint64_t max_blocks = (uint64_t)L.sm_count * 8;  // 8 x 256 threads = 2048 threads / SM
   if (blocks > max_blocks) blocks = max_blocks;

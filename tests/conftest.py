@@ -11,3 +11,10 @@ for p in (ROOT, os.path.join(ROOT, "rapidfuzz-rs_b200")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    # a hung kernel must not eat the GPU budget: every GPU test gets a hard per-test timeout (pytest-timeout)
+    for it in items:
+        if it.get_closest_marker("gpu") and not it.get_closest_marker("timeout"):
+            it.add_marker(pytest.mark.timeout(180))

@@ -1,0 +1,125 @@
+#!/usr/bin/env python3
+"""Secondary configurations of BASELINE.json (configs 3, 4, 5 and the 64-bit-word variant of config 2) on one
+GPU: device-resident inputs, CUDA-event timing, parity spot-check against the CPU oracle on a sample.
+Prints one JSON line per configuration (kept under profiles/ per round)."""
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "rapidfuzz-rs_b200"))
+import numpy as np
+import torch
+import rapidfuzz_b200 as rf
+from rapidfuzz_b200 import _ffi
+from oracle import oracle as orc
+
+L = _ffi.lib()
+PEAK = 6547.8
+try:
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+scale = float(os.environ.get("RF_CFG_SCALE", "1.0"))
+
+
+def timed(fn, steps, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def one_vs_many(name, metric, kind, seed, qlen, n, lo, hi, kmax, cutoff, out_f64, bytes_per_pair_fn, steps=20, tol=0.0):
+    q = rf.synth_query(seed, qlen)
+    chars, offsets = rf.synth_corpus(seed, q, n, lo, hi, kmax)
+    corpus = rf.Corpus(chars, offsets)
+    cls = type("B", (rf._scorer.BatchComparatorBase,), {"METRIC": metric})
+    b = cls(q)
+    args = rf.Args() if cutoff is None else rf.Args().score_cutoff(cutoff)
+    out = torch.empty(n, dtype=torch.float64 if out_f64 else torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    ms = timed(lambda: b.score_into(kind, corpus, out.data_ptr(), args, st), steps)
+    m = min(n, 200_000)
+    kw = {} if cutoff is None else {"cutoff": cutoff}
+    exp = orc.batch(metric, kind, q, chars[: int(offsets[m])], offsets[: m + 1], nthreads=0, **kw)
+    got = out[:m].cpu().numpy()
+    if out_f64:
+        ok = bool(np.all((np.isnan(got) & np.isnan(exp)) | (np.abs(got - exp) <= tol)))
+        exact = bool(np.all((np.isnan(got) & np.isnan(exp)) | (got == exp)))
+    else:
+        ok = exact = bool(np.array_equal(got.view(np.uint32), exp))
+    t0 = time.perf_counter()
+    orc.batch(metric, kind, q, chars[: int(offsets[min(n, 2_000_000)])], offsets[: min(n, 2_000_000) + 1], nthreads=0, **kw)
+    cpu = min(n, 2_000_000) / (time.perf_counter() - t0)
+    lens = np.diff(offsets.astype(np.int64))
+    alg = float(bytes_per_pair_fn(lens).sum())
+    pps = n / (ms * 1e-3)
+    print(json.dumps({"config": name, "metric": metric, "kind": kind, "n": n, "query_len": qlen, "cutoff": cutoff,
+                      "ms_per_step": ms, "pairs_per_s": pps, "algorithmic_GBps": alg / (ms * 1e-3) / 1e9,
+                      "hbm_frac_of_measured_peak": alg / (ms * 1e-3) / 1e9 / PEAK, "matches_oracle_sample": ok,
+                      "bit_exact": exact, "some_frac": float(np.mean(~np.isnan(got)) if out_f64 else np.mean(got.view(np.uint32) != 0xFFFFFFFF)),
+                      "cpu_oracle_pairs_per_s_all_threads": cpu, "cpu_threads": orc.max_threads()}), flush=True)
+    b.close()
+    corpus.close()
+
+
+def cdist(nq, n, k=10, steps=2):
+    q0 = rf.synth_query(5, 32)
+    qs = [rf.synth_query(5 + i, 32) for i in range(nq)]
+    q_chars = np.concatenate(qs)
+    q_off = (np.arange(nq + 1, dtype=np.uint64) * 32)
+    chars, offsets = rf.synth_corpus(5, q0, n, 8, 64, 16)
+    corpus = rf.Corpus(chars, offsets)
+    idx = torch.empty((nq, k), dtype=torch.int32, device="cuda")
+    dist = torch.empty((nq, k), dtype=torch.int32, device="cuda")
+    a = _ffi.RfArgs()
+    L.rf_args_default(C.byref(a))
+    st = torch.cuda.current_stream().cuda_stream
+
+    def run():
+        _ffi.check(L.rf_cdist_topk_u8_device(q_chars.ctypes.data, q_off.ctypes.data, nq, corpus._h, C.byref(a), k,
+                                             idx.data_ptr(), dist.data_ptr(), st))
+    ms = timed(run, steps, warmup=1)
+    # parity on a 100 x 100000 sub-problem against the oracle's full matrix
+    sub_q, sub_n = min(nq, 100), min(n, 100_000)
+    sc = rf.Corpus(chars[: int(offsets[sub_n])], offsets[: sub_n + 1])
+    gi, gd = rf.cdist_topk((q_chars[: sub_q * 32], q_off[: sub_q + 1]), sc, k=k)
+    ok = True
+    for qi in range(sub_q):
+        d = orc.batch("levenshtein", "distance", qs[qi], chars[: int(offsets[sub_n])], offsets[: sub_n + 1], nthreads=0).astype(np.int64)
+        keys = np.sort(d * (1 << 32) + np.arange(sub_n))[:k]
+        ok = ok and np.array_equal(gi[qi], (keys & 0xFFFFFFFF).astype(np.uint32)) and np.array_equal(gd[qi], (keys >> 32).astype(np.uint32))
+    sc.close()
+    pairs = nq * n
+    print(json.dumps({"config": "C5 cdist top-%d (one GPU's shard)" % k, "nq": nq, "n": n, "ms_per_step": ms,
+                      "pairs_per_s": pairs / (ms * 1e-3), "matches_oracle_submatrix_%dx%d" % (sub_q, sub_n): bool(ok)}), flush=True)
+    corpus.close()
+
+
+if __name__ == "__main__":
+    which = sys.argv[1].split(",") if len(sys.argv) > 1 else ["c2w", "c3", "c4", "c5"]
+    if "c2w" in which:  # config 2 with a 64-element query (64-bit words)
+        one_vs_many("C2 (query len 64, 64-bit words)", "levenshtein", "distance", 2, 64, int(1e8 * scale), 8, 64, 16, None, False,
+                    lambda l: l + 8)
+    if "c3" in which:
+        one_vs_many("C3 multi-block", "levenshtein", "distance", 3, 256, int(1e7 * scale), 64, 256, 48, 32, False,
+                    lambda l: np.where(np.abs(256 - l) <= 32, l + 8, 8))
+    if "c4" in which:
+        one_vs_many("C4 jaro_winkler", "jaro_winkler", "normalized_similarity", 4, 32, int(1e8 * scale), 8, 64, 16, None, True,
+                    lambda l: l + 12, tol=1e-6)
+    if "c5" in which:
+        cdist(int(1e4 * scale), int(1.25e6))
+    for extra in which:
+        if extra in ("indel", "lcs_seq", "osa", "jaro"):
+            kind = "similarity" if extra in ("lcs_seq", "jaro") else "distance"
+            one_vs_many("C2-shape " + extra, extra, kind, 2, 32, int(1e8 * scale), 8, 64, 16, None, extra == "jaro", lambda l: l + 8)

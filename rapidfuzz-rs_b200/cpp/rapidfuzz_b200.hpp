@@ -1,0 +1,228 @@
+// rapidfuzz_b200.hpp -- header-only C++17 host mirror of the rapidfuzz-rs API surface for the one-vs-many
+// path, over the C ABI of include/rfgpu.h (librfgpu.so).  The reference's host language is Rust, which this
+// image cannot compile; C++ is the compiled-language stand-in, and the Rust shim a maintainer would add is in
+// INTEGRATION.md / rapidfuzz-rs_b200/rust/src/lib.rs.
+//
+// Mirrors (reference paths relative to src/):
+//   distance::{levenshtein,indel,lcs_seq,osa,jaro,jaro_winkler}::{Args, BatchComparator, distance,
+//     similarity, normalized_distance, normalized_similarity}            (e.g. levenshtein.rs:86-126, :1636-1818)
+//   fuzz::{ratio, RatioBatchComparator}                                   (fuzz.rs:48-150)
+// Differences forced by the batch model: the candidate side is a Corpus (all candidates, uploaded once) and
+// every method returns one value per candidate; methods taking a single string are provided for parity with
+// the reference's tests.  With a score_cutoff the element type becomes std::optional<T> exactly where the
+// reference's return type becomes Option<T> (common.rs:18-86).
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <string_view>
+#include <vector>
+
+#include "rfgpu.h"
+
+namespace rapidfuzz_b200 {
+
+struct Error : std::runtime_error {
+  rf_status status;
+  Error(rf_status s, const std::string& m) : std::runtime_error(m), status(s) {}
+};
+inline void check(rf_status s) {
+  if (s != RF_OK) throw Error(s, std::string(rf_status_string(s)) + ": " + rf_last_error());
+}
+
+// Packed candidates resident in one GPU's HBM.
+class Corpus {
+ public:
+  Corpus(const uint8_t* chars, const uint64_t* offsets, uint64_t n, int device = 0) {
+    check(rf_corpus_create_u8(chars, offsets, n, device, &h_));
+  }
+  template <class Strings>
+  static Corpus from_strings(const Strings& strings, int device = 0) {
+    std::vector<uint8_t> chars;
+    std::vector<uint64_t> offsets{0};
+    for (const auto& s : strings) {
+      chars.insert(chars.end(), std::begin(s), std::end(s));
+      offsets.push_back(chars.size());
+    }
+    return Corpus(chars.data(), offsets.data(), offsets.size() - 1, device);
+  }
+  Corpus(Corpus&& o) noexcept : h_(o.h_) { o.h_ = nullptr; }
+  Corpus(const Corpus&) = delete;
+  Corpus& operator=(const Corpus&) = delete;
+  ~Corpus() { rf_corpus_destroy(h_); }
+  uint64_t size() const { return rf_corpus_size(h_); }
+  const rf_corpus* handle() const { return h_; }
+
+ private:
+  rf_corpus* h_ = nullptr;
+};
+
+struct NoScoreCutoff {};
+template <class T>
+struct WithScoreCutoff { T value; };
+
+// Args<ResultType, CutoffType> builder (levenshtein.rs:86-126 and the per-metric equivalents)
+template <class T, class Cutoff = NoScoreCutoff>
+struct Args {
+  Cutoff cutoff{};
+  std::optional<T> hint{};
+  uint64_t ins = 1, del = 1, sub = 1;
+  double prefix_weight_ = 0.1;
+  bool quirks = false;
+  Args score_hint(T h) const { Args a = *this; a.hint = h; return a; }
+  Args<T, WithScoreCutoff<T>> score_cutoff(T c) const {
+    Args<T, WithScoreCutoff<T>> a;
+    a.cutoff = {c}; a.hint = hint; a.ins = ins; a.del = del; a.sub = sub; a.prefix_weight_ = prefix_weight_; a.quirks = quirks;
+    return a;
+  }
+  Args weights(uint64_t insertion_cost, uint64_t deletion_cost, uint64_t substitution_cost) const {
+    Args a = *this; a.ins = insertion_cost; a.del = deletion_cost; a.sub = substitution_cost; return a;
+  }
+  Args prefix_weight(double w) const { Args a = *this; a.prefix_weight_ = w; return a; }
+  Args reference_quirks(bool on = true) const { Args a = *this; a.quirks = on; return a; }
+};
+
+namespace detail {
+template <class T, class C>
+rf_args to_c(const Args<T, C>& a) {
+  rf_args r;
+  rf_args_default(&r);
+  r.insertion_cost = a.ins; r.deletion_cost = a.del; r.substitution_cost = a.sub;
+  r.prefix_weight = a.prefix_weight_;
+  r.reference_quirks = a.quirks ? 1 : 0;
+  if constexpr (!std::is_same_v<C, NoScoreCutoff>) {
+    r.has_cutoff = 1;
+    if constexpr (std::is_floating_point_v<T>) r.cutoff_f = (double)a.cutoff.value; else r.cutoff_u = (uint64_t)a.cutoff.value;
+  }
+  if (a.hint) {
+    r.has_hint = 1;
+    if constexpr (std::is_floating_point_v<T>) r.hint_f = (double)*a.hint; else r.hint_u = (uint64_t)*a.hint;
+  }
+  return r;
+}
+template <class T> struct Raw;
+template <> struct Raw<uint32_t> {
+  static std::vector<uint32_t> run(const rf_batch* b, const Corpus& c, rf_kind k, const rf_args& a) {
+    std::vector<uint32_t> out(c.size());
+    check(rf_batch_score_u32(b, c.handle(), k, &a, out.data()));
+    return out;
+  }
+  static bool none(uint32_t v) { return v == UINT32_MAX; }
+};
+template <> struct Raw<double> {
+  static std::vector<double> run(const rf_batch* b, const Corpus& c, rf_kind k, const rf_args& a) {
+    std::vector<double> out(c.size());
+    check(rf_batch_score_f64(b, c.handle(), k, &a, out.data()));
+    return out;
+  }
+  static bool none(double v) { return std::isnan(v); }
+};
+}  // namespace detail
+
+// One metric module.  IntT = element type of distance/similarity (uint32_t for the edit-distance family,
+// double for Jaro / Jaro-Winkler).
+template <rf_metric M, class IntT>
+struct MetricModule {
+  using ArgsInt = Args<IntT>;
+  using ArgsF64 = Args<double>;
+
+  class BatchComparator {  // BatchComparator::new(query): caches s1 and its pattern-match table on the GPU
+   public:
+    explicit BatchComparator(std::string_view query, int device = 0) : device_(device) {
+      check(rf_batch_create_u8(M, reinterpret_cast<const uint8_t*>(query.data()), (uint32_t)query.size(), device, &h_));
+    }
+    BatchComparator(BatchComparator&& o) noexcept : h_(o.h_), device_(o.device_) { o.h_ = nullptr; }
+    BatchComparator(const BatchComparator&) = delete;
+    ~BatchComparator() { rf_batch_destroy(h_); }
+
+    // one value per candidate, no cutoff: bare values (common.rs:18-31)
+    std::vector<IntT> distance(const Corpus& c) const { return score<IntT>(c, RF_DISTANCE, ArgsInt{}); }
+    std::vector<IntT> similarity(const Corpus& c) const { return score<IntT>(c, RF_SIMILARITY, ArgsInt{}); }
+    std::vector<double> normalized_distance(const Corpus& c) const { return score<double>(c, RF_NORMALIZED_DISTANCE, ArgsF64{}); }
+    std::vector<double> normalized_similarity(const Corpus& c) const { return score<double>(c, RF_NORMALIZED_SIMILARITY, ArgsF64{}); }
+    // *_with_args: Option-valued when a score_cutoff is set (common.rs:33-46, :73-86)
+    template <class C> auto distance_with_args(const Corpus& c, const Args<IntT, C>& a) const { return wrap<IntT, C>(score<IntT>(c, RF_DISTANCE, a)); }
+    template <class C> auto similarity_with_args(const Corpus& c, const Args<IntT, C>& a) const { return wrap<IntT, C>(score<IntT>(c, RF_SIMILARITY, a)); }
+    template <class C> auto normalized_distance_with_args(const Corpus& c, const Args<double, C>& a) const { return wrap<double, C>(score<double>(c, RF_NORMALIZED_DISTANCE, a)); }
+    template <class C> auto normalized_similarity_with_args(const Corpus& c, const Args<double, C>& a) const { return wrap<double, C>(score<double>(c, RF_NORMALIZED_SIMILARITY, a)); }
+    // single-candidate forms, as in the reference's signatures
+    IntT distance(std::string_view s2) const { return distance(one(s2))[0]; }
+    IntT similarity(std::string_view s2) const { return similarity(one(s2))[0]; }
+    double normalized_distance(std::string_view s2) const { return normalized_distance(one(s2))[0]; }
+    double normalized_similarity(std::string_view s2) const { return normalized_similarity(one(s2))[0]; }
+    template <class C> auto distance_with_args(std::string_view s2, const Args<IntT, C>& a) const { return distance_with_args(one(s2), a)[0]; }
+    template <class C> auto similarity_with_args(std::string_view s2, const Args<IntT, C>& a) const { return similarity_with_args(one(s2), a)[0]; }
+    template <class C> auto normalized_similarity_with_args(std::string_view s2, const Args<double, C>& a) const { return normalized_similarity_with_args(one(s2), a)[0]; }
+    template <class C> auto normalized_distance_with_args(std::string_view s2, const Args<double, C>& a) const { return normalized_distance_with_args(one(s2), a)[0]; }
+
+   private:
+    Corpus one(std::string_view s) const { return Corpus::from_strings(std::vector<std::string_view>{s}, device_); }
+    template <class T, class A>
+    std::vector<T> score(const Corpus& c, rf_kind k, const A& a) const {
+      return detail::Raw<T>::run(h_, c, k, detail::to_c(a));
+    }
+    template <class T, class C>
+    static auto wrap(std::vector<T> raw) {
+      if constexpr (std::is_same_v<C, NoScoreCutoff>) return raw;
+      else {
+        std::vector<std::optional<T>> out(raw.size());
+        for (size_t i = 0; i < raw.size(); ++i)
+          if (!detail::Raw<T>::none(raw[i])) out[i] = raw[i];
+        return out;
+      }
+    }
+    rf_batch* h_ = nullptr;
+    int device_;
+  };
+
+  // pairwise free functions of the reference (e.g. levenshtein.rs:1380-1585)
+  static IntT distance(std::string_view s1, std::string_view s2) { return BatchComparator(s1).distance(s2); }
+  static IntT similarity(std::string_view s1, std::string_view s2) { return BatchComparator(s1).similarity(s2); }
+  static double normalized_distance(std::string_view s1, std::string_view s2) { return BatchComparator(s1).normalized_distance(s2); }
+  static double normalized_similarity(std::string_view s1, std::string_view s2) { return BatchComparator(s1).normalized_similarity(s2); }
+  template <class C> static auto distance_with_args(std::string_view s1, std::string_view s2, const Args<IntT, C>& a) { return BatchComparator(s1).distance_with_args(s2, a); }
+};
+
+namespace distance {
+using levenshtein = MetricModule<RF_LEVENSHTEIN, uint32_t>;
+using indel = MetricModule<RF_INDEL, uint32_t>;
+using lcs_seq = MetricModule<RF_LCS_SEQ, uint32_t>;
+using osa = MetricModule<RF_OSA, uint32_t>;
+using jaro = MetricModule<RF_JARO, double>;
+using jaro_winkler = MetricModule<RF_JARO_WINKLER, double>;
+}  // namespace distance
+
+namespace fuzz {  // fuzz.rs:48-150
+class RatioBatchComparator {
+ public:
+  explicit RatioBatchComparator(std::string_view query, int device = 0) : device_(device) {
+    check(rf_batch_create_u8(RF_RATIO, reinterpret_cast<const uint8_t*>(query.data()), (uint32_t)query.size(), device, &h_));
+  }
+  RatioBatchComparator(const RatioBatchComparator&) = delete;
+  ~RatioBatchComparator() { rf_batch_destroy(h_); }
+  std::vector<double> similarity(const Corpus& c) const { return detail::Raw<double>::run(h_, c, RF_SIMILARITY, detail::to_c(Args<double>{})); }
+  template <class C>
+  auto similarity_with_args(const Corpus& c, const Args<double, C>& a) const {
+    auto raw = detail::Raw<double>::run(h_, c, RF_SIMILARITY, detail::to_c(a));
+    if constexpr (std::is_same_v<C, NoScoreCutoff>) return raw;
+    else {
+      std::vector<std::optional<double>> out(raw.size());
+      for (size_t i = 0; i < raw.size(); ++i)
+        if (!std::isnan(raw[i])) out[i] = raw[i];
+      return out;
+    }
+  }
+  double similarity(std::string_view s2) const {
+    return similarity(Corpus::from_strings(std::vector<std::string_view>{s2}, device_))[0];
+  }
+
+ private:
+  rf_batch* h_ = nullptr;
+  int device_;
+};
+inline double ratio(std::string_view s1, std::string_view s2) { return RatioBatchComparator(s1).similarity(s2); }
+}  // namespace fuzz
+
+}  // namespace rapidfuzz_b200

@@ -1,0 +1,232 @@
+//! rapidfuzz-b200 -- Rust host shim over the C ABI of `include/rfgpu.h` (librfgpu.so).
+//!
+//! NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no cargo/rustc.  It is the
+//! binding a maintainer of rapidfuzz-rs would add to route the one-vs-many `BatchComparator` hot path
+//! to the B200 engine; it is kept mechanical on purpose.  Reference signatures it mirrors:
+//! `distance::levenshtein::{Args, BatchComparator}` (src/distance/levenshtein.rs:86-126, :1636-1818) and the
+//! same shape for indel / lcs_seq / osa / jaro / jaro_winkler and `fuzz::RatioBatchComparator`
+//! (src/fuzz.rs:98-150).  `None` (score worse than `score_cutoff`, src/common.rs:43-45, :83-85) crosses the
+//! boundary as `u32::MAX` / NaN.
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int, c_void};
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct rf_args {
+    pub has_cutoff: u8,
+    pub cutoff_u: u64,
+    pub cutoff_f: f64,
+    pub has_hint: u8,
+    pub hint_u: u64,
+    pub hint_f: f64,
+    pub insertion_cost: u64,
+    pub deletion_cost: u64,
+    pub substitution_cost: u64,
+    pub prefix_weight: f64,
+    pub reference_quirks: u8,
+}
+#[repr(C)] pub struct rf_corpus { _p: [u8; 0] }
+#[repr(C)] pub struct rf_batch { _p: [u8; 0] }
+
+pub const RF_LEVENSHTEIN: c_int = 0;
+pub const RF_INDEL: c_int = 1;
+pub const RF_LCS_SEQ: c_int = 2;
+pub const RF_OSA: c_int = 3;
+pub const RF_JARO: c_int = 4;
+pub const RF_JARO_WINKLER: c_int = 5;
+pub const RF_RATIO: c_int = 6;
+pub const RF_DISTANCE: c_int = 0;
+pub const RF_SIMILARITY: c_int = 1;
+pub const RF_NORMALIZED_DISTANCE: c_int = 2;
+pub const RF_NORMALIZED_SIMILARITY: c_int = 3;
+
+#[link(name = "rfgpu")]
+extern "C" {
+    pub fn rf_args_default(a: *mut rf_args);
+    pub fn rf_last_error() -> *const c_char;
+    pub fn rf_corpus_create_u8(chars: *const u8, offsets: *const u64, n: u64, device: c_int, out: *mut *mut rf_corpus) -> c_int;
+    pub fn rf_corpus_destroy(c: *mut rf_corpus) -> c_int;
+    pub fn rf_corpus_size(c: *const rf_corpus) -> u64;
+    pub fn rf_batch_create_u8(metric: c_int, query: *const u8, len: u32, device: c_int, out: *mut *mut rf_batch) -> c_int;
+    pub fn rf_batch_destroy(b: *mut rf_batch) -> c_int;
+    pub fn rf_batch_score_u32(b: *const rf_batch, c: *const rf_corpus, kind: c_int, args: *const rf_args, out: *mut u32) -> c_int;
+    pub fn rf_batch_score_f64(b: *const rf_batch, c: *const rf_corpus, kind: c_int, args: *const rf_args, out: *mut f64) -> c_int;
+    pub fn rf_cdist_topk_u8(q_chars: *const u8, q_offsets: *const u64, nq: u32, c: *const rf_corpus, args: *const rf_args,
+                            k: u32, idx: *mut u32, dist: *mut u32) -> c_int;
+    pub fn rf_set_option(name: *const c_char, value: c_int) -> c_int;
+    #[allow(dead_code)]
+    fn rf_kernel_launch_count() -> u64;
+    #[allow(dead_code)]
+    fn rf_device_count() -> c_int;
+    #[allow(dead_code)]
+    fn rf_status_string(s: c_int) -> *const c_char;
+    #[allow(dead_code)]
+    fn rf_result_is_float(metric: c_int, kind: c_int) -> c_int;
+    #[allow(dead_code)]
+    fn rf_corpus_total_chars(c: *const rf_corpus) -> u64;
+    #[allow(dead_code)]
+    fn rf_corpus_device(c: *const rf_corpus) -> c_int;
+    #[allow(dead_code)]
+    fn rf_batch_score_u32_device(b: *const rf_batch, c: *const rf_corpus, kind: c_int, args: *const rf_args, out: *mut u32, stream: *mut c_void) -> c_int;
+}
+
+fn check(status: c_int) {
+    if status != 0 {
+        let msg = unsafe { std::ffi::CStr::from_ptr(rf_last_error()) }.to_string_lossy().into_owned();
+        panic!("rfgpu status {status}: {msg}"); // the reference has no Result on this path either
+    }
+}
+
+/// Packed candidates resident in GPU memory (new: the reference takes one iterator per call).
+pub struct Corpus { h: *mut rf_corpus }
+unsafe impl Send for Corpus {}
+unsafe impl Sync for Corpus {}
+impl Corpus {
+    pub fn new<I, S>(candidates: I, device: i32) -> Self where I: IntoIterator<Item = S>, S: AsRef<[u8]> {
+        let mut chars = Vec::new();
+        let mut offsets = vec![0u64];
+        for s in candidates { chars.extend_from_slice(s.as_ref()); offsets.push(chars.len() as u64); }
+        let mut h = std::ptr::null_mut();
+        check(unsafe { rf_corpus_create_u8(chars.as_ptr(), offsets.as_ptr(), (offsets.len() - 1) as u64, device, &mut h) });
+        Corpus { h }
+    }
+    pub fn len(&self) -> usize { unsafe { rf_corpus_size(self.h) as usize } }
+}
+impl Drop for Corpus { fn drop(&mut self) { unsafe { rf_corpus_destroy(self.h); } } }
+
+/// `NoScoreCutoff` / `WithScoreCutoff<T>` exactly as in src/common.rs:4-86: the cutoff type picks the output type.
+#[derive(Default, Copy, Clone)] pub struct NoScoreCutoff;
+#[derive(Default, Copy, Clone)] pub struct WithScoreCutoff<T>(pub T);
+pub trait Cutoff<T: Copy> { type Output; fn cutoff(&self) -> Option<T>; fn wrap(raw: T, none: bool) -> Self::Output; }
+impl<T: Copy> Cutoff<T> for NoScoreCutoff { type Output = T; fn cutoff(&self) -> Option<T> { None } fn wrap(raw: T, _: bool) -> T { raw } }
+impl<T: Copy> Cutoff<T> for WithScoreCutoff<T> { type Output = Option<T>; fn cutoff(&self) -> Option<T> { Some(self.0) } fn wrap(raw: T, none: bool) -> Option<T> { (!none).then_some(raw) } }
+
+macro_rules! metric_module {
+    ($modname:ident, $metric:expr, $int_t:ty, $int_is_f64:expr) => {
+        pub mod $modname {
+            use super::*;
+            #[derive(Copy, Clone)]
+            pub struct Args<ResultType, CutoffType> {
+                pub(crate) score_cutoff: CutoffType,
+                pub(crate) score_hint: Option<ResultType>,
+                pub(crate) weights: (u64, u64, u64),
+                pub(crate) prefix_weight: f64,
+            }
+            impl<R> Default for Args<R, NoScoreCutoff> {
+                fn default() -> Self { Args { score_cutoff: NoScoreCutoff, score_hint: None, weights: (1, 1, 1), prefix_weight: 0.1 } }
+            }
+            impl<R: Copy, C> Args<R, C> {
+                pub fn score_hint(mut self, h: R) -> Self { self.score_hint = Some(h); self }
+                pub fn score_cutoff(self, c: R) -> Args<R, WithScoreCutoff<R>> {
+                    Args { score_cutoff: WithScoreCutoff(c), score_hint: self.score_hint, weights: self.weights, prefix_weight: self.prefix_weight }
+                }
+                pub fn weights(mut self, ins: u64, del: u64, sub: u64) -> Self { self.weights = (ins, del, sub); self }
+                pub fn prefix_weight(mut self, w: f64) -> Self { self.prefix_weight = w; self }
+            }
+            /// `BatchComparator::new(query)`: caches s1 and its pattern-match bit table on the GPU.
+            pub struct BatchComparator { h: *mut rf_batch }
+            unsafe impl Send for BatchComparator {}
+            unsafe impl Sync for BatchComparator {}
+            impl Drop for BatchComparator { fn drop(&mut self) { unsafe { rf_batch_destroy(self.h); } } }
+            impl BatchComparator {
+                pub fn new<Q: AsRef<[u8]>>(query: Q, device: i32) -> Self {
+                    let q = query.as_ref();
+                    let mut h = std::ptr::null_mut();
+                    check(unsafe { rf_batch_create_u8($metric, q.as_ptr(), q.len() as u32, device, &mut h) });
+                    BatchComparator { h }
+                }
+                fn c_args_f(cut: Option<f64>, w: (u64, u64, u64), pw: f64) -> rf_args {
+                    let mut a: rf_args = unsafe { std::mem::zeroed() };
+                    unsafe { rf_args_default(&mut a) };
+                    a.insertion_cost = w.0; a.deletion_cost = w.1; a.substitution_cost = w.2; a.prefix_weight = pw;
+                    if let Some(c) = cut { a.has_cutoff = 1; a.cutoff_f = c; }
+                    a
+                }
+                fn run_u32(&self, c: &Corpus, kind: c_int, a: &rf_args) -> Vec<u32> {
+                    let mut out = vec![0u32; c.len()];
+                    check(unsafe { rf_batch_score_u32(self.h, c.h, kind, a, out.as_mut_ptr()) });
+                    out
+                }
+                fn run_f64(&self, c: &Corpus, kind: c_int, a: &rf_args) -> Vec<f64> {
+                    let mut out = vec![0f64; c.len()];
+                    check(unsafe { rf_batch_score_f64(self.h, c.h, kind, a, out.as_mut_ptr()) });
+                    out
+                }
+                /// one score per candidate == the user's `for c in candidates { scorer.normalized_similarity_with_args(c, args) }`
+                pub fn normalized_similarity_with_args<C: Cutoff<f64>>(&self, c: &Corpus, args: &Args<f64, C>) -> Vec<C::Output> {
+                    let a = Self::c_args_f(args.score_cutoff.cutoff(), args.weights, args.prefix_weight);
+                    self.run_f64(c, RF_NORMALIZED_SIMILARITY, &a).into_iter().map(|v| C::wrap(v, v.is_nan())).collect()
+                }
+                pub fn normalized_distance_with_args<C: Cutoff<f64>>(&self, c: &Corpus, args: &Args<f64, C>) -> Vec<C::Output> {
+                    let a = Self::c_args_f(args.score_cutoff.cutoff(), args.weights, args.prefix_weight);
+                    self.run_f64(c, RF_NORMALIZED_DISTANCE, &a).into_iter().map(|v| C::wrap(v, v.is_nan())).collect()
+                }
+                pub fn normalized_similarity(&self, c: &Corpus) -> Vec<f64> { self.normalized_similarity_with_args(c, &Args::default()) }
+                pub fn normalized_distance(&self, c: &Corpus) -> Vec<f64> { self.normalized_distance_with_args(c, &Args::default()) }
+            }
+            metric_module!(@intmethods $int_t, $int_is_f64);
+        }
+    };
+    // distance / similarity: usize-valued for the edit-distance family ...
+    (@intmethods $int_t:ty, false) => {
+        impl BatchComparator {
+            pub fn distance_with_args<C: Cutoff<usize>>(&self, c: &Corpus, args: &Args<usize, C>) -> Vec<C::Output> {
+                let mut a = Self::c_args_f(None, args.weights, args.prefix_weight);
+                if let Some(k) = args.score_cutoff.cutoff() { a.has_cutoff = 1; a.cutoff_u = k as u64; }
+                self.run_u32(c, RF_DISTANCE, &a).into_iter().map(|v| C::wrap(v as usize, v == u32::MAX)).collect()
+            }
+            pub fn similarity_with_args<C: Cutoff<usize>>(&self, c: &Corpus, args: &Args<usize, C>) -> Vec<C::Output> {
+                let mut a = Self::c_args_f(None, args.weights, args.prefix_weight);
+                if let Some(k) = args.score_cutoff.cutoff() { a.has_cutoff = 1; a.cutoff_u = k as u64; }
+                self.run_u32(c, RF_SIMILARITY, &a).into_iter().map(|v| C::wrap(v as usize, v == u32::MAX)).collect()
+            }
+            pub fn distance(&self, c: &Corpus) -> Vec<usize> { self.distance_with_args(c, &Args::default()) }
+            pub fn similarity(&self, c: &Corpus) -> Vec<usize> { self.similarity_with_args(c, &Args::default()) }
+        }
+    };
+    // ... and f64-valued for Jaro / Jaro-Winkler
+    (@intmethods $int_t:ty, true) => {
+        impl BatchComparator {
+            pub fn distance_with_args<C: Cutoff<f64>>(&self, c: &Corpus, args: &Args<f64, C>) -> Vec<C::Output> {
+                let a = Self::c_args_f(args.score_cutoff.cutoff(), args.weights, args.prefix_weight);
+                self.run_f64(c, RF_DISTANCE, &a).into_iter().map(|v| C::wrap(v, v.is_nan())).collect()
+            }
+            pub fn similarity_with_args<C: Cutoff<f64>>(&self, c: &Corpus, args: &Args<f64, C>) -> Vec<C::Output> {
+                let a = Self::c_args_f(args.score_cutoff.cutoff(), args.weights, args.prefix_weight);
+                self.run_f64(c, RF_SIMILARITY, &a).into_iter().map(|v| C::wrap(v, v.is_nan())).collect()
+            }
+            pub fn distance(&self, c: &Corpus) -> Vec<f64> { self.distance_with_args(c, &Args::default()) }
+            pub fn similarity(&self, c: &Corpus) -> Vec<f64> { self.similarity_with_args(c, &Args::default()) }
+        }
+    };
+}
+
+pub mod distance {
+    use super::*;
+    metric_module!(levenshtein, RF_LEVENSHTEIN, usize, false);
+    metric_module!(indel, RF_INDEL, usize, false);
+    metric_module!(lcs_seq, RF_LCS_SEQ, usize, false);
+    metric_module!(osa, RF_OSA, usize, false);
+    metric_module!(jaro, RF_JARO, f64, true);
+    metric_module!(jaro_winkler, RF_JARO_WINKLER, f64, true);
+}
+
+/// `fuzz::RatioBatchComparator` (src/fuzz.rs:98-150); documented semantics (== `fuzz::ratio`), see DESIGN.md Q1.
+pub mod fuzz {
+    use super::*;
+    pub struct RatioBatchComparator { h: *mut rf_batch }
+    impl Drop for RatioBatchComparator { fn drop(&mut self) { unsafe { rf_batch_destroy(self.h); } } }
+    impl RatioBatchComparator {
+        pub fn new<Q: AsRef<[u8]>>(query: Q, device: i32) -> Self {
+            let q = query.as_ref();
+            let mut h = std::ptr::null_mut();
+            check(unsafe { rf_batch_create_u8(RF_RATIO, q.as_ptr(), q.len() as u32, device, &mut h) });
+            RatioBatchComparator { h }
+        }
+        pub fn similarity(&self, c: &Corpus) -> Vec<f64> {
+            let mut out = vec![0f64; c.len()];
+            check(unsafe { rf_batch_score_f64(self.h, c.h, RF_SIMILARITY, std::ptr::null(), out.as_mut_ptr()) });
+            out
+        }
+    }
+}

@@ -1,0 +1,46 @@
+// Known-answer tests of the C++ host mirror, written like the reference's own tests / doc-tests
+// (levenshtein.rs:1378, :1632-1633, :2024-2066; Readme.md:62-106; jaro.rs:1081-1092; fuzz.rs:94-96).
+#include <cmath>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "rapidfuzz_b200.hpp"
+
+using namespace rapidfuzz_b200;
+static int fails = 0;
+#define EXPECT(c) do { if (!(c)) { std::printf("FAIL %s:%d %s\n", __FILE__, __LINE__, #c); ++fails; } } while (0)
+
+int main() {
+  namespace lev = distance;
+  EXPECT(distance::levenshtein::distance("CA", "ABC") == 3);
+  distance::levenshtein::BatchComparator scorer("CA");
+  EXPECT(scorer.distance("ABC") == 3);
+  EXPECT(distance::levenshtein::distance("kitten", "sitting") == 3);
+  auto none = distance::levenshtein::distance_with_args("kitten", "sitting", Args<uint32_t>{}.score_cutoff(2));
+  EXPECT(!none.has_value());
+  auto some = distance::levenshtein::distance_with_args("kitten", "sitting", Args<uint32_t>{}.score_cutoff(3));
+  EXPECT(some.has_value() && *some == 3);
+
+  std::vector<std::string> cands = {"North Korea", "South Korea", "", "aabc", "cccd", "Korea"};
+  Corpus corpus = Corpus::from_strings(cands);
+  distance::levenshtein::BatchComparator sk("South Korea");
+  auto d = sk.distance(corpus);
+  EXPECT(d.size() == 6 && d[0] == 2 && d[1] == 0 && d[2] == 11 && d[5] == 6);
+  auto dc = sk.distance_with_args(corpus, Args<uint32_t>{}.score_cutoff(2));
+  EXPECT(dc[0].has_value() && *dc[0] == 2 && dc[1].has_value() && !dc[2].has_value() && !dc[5].has_value());
+  auto w = sk.distance_with_args(corpus, Args<uint32_t>{}.weights(1, 1, 2));   // levenshtein.rs:2036-2042
+  EXPECT(w[0] == 4);
+  EXPECT(distance::indel::distance("lewenstein", "levenshtein") == 3);         // indel.rs:119
+  EXPECT(distance::lcs_seq::BatchComparator("lewenstein").similarity("levenshtein") == 9);  // lcs_seq.rs:763-764
+  EXPECT(distance::osa::distance("CA", "AC") == 1);                            // osa.rs:678
+  EXPECT(std::fabs(distance::jaro::similarity("james", "robert") - 0.455556) < 1e-4);        // jaro.rs:1081-1086
+  EXPECT(std::fabs(distance::jaro_winkler::similarity("aaaaaaaa", "aabaaab") - 0.82381) < 1e-4);  // jaro_winkler.rs:694-798
+  EXPECT(std::fabs(fuzz::ratio("this is a test", "this is a test!") - 0.9655172) < 1e-6);   // fuzz.rs:94-96
+  auto ns = sk.normalized_similarity_with_args(corpus, Args<double>{}.score_cutoff(0.5));
+  EXPECT(ns[0].has_value() && std::fabs(*ns[0] - (1.0 - 2.0 / 11.0)) < 1e-12 && !ns[2].has_value());
+  bool threw = false;
+  try { sk.distance_with_args(corpus, Args<uint32_t>{}.weights(1, 2, 3)); } catch (const Error& e) { threw = e.status == RF_ERR_UNSUPPORTED; }
+  EXPECT(threw);
+  std::printf(fails ? "cpp api: %d failure(s)\n" : "cpp api: all ok\n", fails);
+  return fails ? 1 : 0;
+}

@@ -275,3 +275,18 @@ def test_cdist_topk_vs_oracle_full_matrix(qlens, n, k):
         assert np.array_equal(dist, edist), (qlens, n, k, cutoff)
         assert np.array_equal(idx, eidx), (qlens, n, k, cutoff)
     corpus.close()
+
+
+def test_cpp_host_mirror_known_answers(tmp_path):
+    """Compiles tests/cpp/test_cpp_api.cpp against the header-only C++ mirror and runs it on the GPU."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "test_cpp_api")
+    libdir = os.path.join(root, "rapidfuzz-rs_b200", "lib")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-I", os.path.join(root, "include"),
+                           "-I", os.path.join(root, "rapidfuzz-rs_b200", "cpp"),
+                           os.path.join(root, "tests", "cpp", "test_cpp_api.cpp"), "-o", exe,
+                           "-L", libdir, "-lrfgpu", "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "all ok" in out.stdout

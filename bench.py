@@ -52,7 +52,7 @@ def measured_peak():
 
 def ncu_traffic_per_launch():
     """dram__bytes_read.sum + dram__bytes_write.sum of the scan kernel from the committed ncu capture."""
-    p = os.path.join(ROOT, "profiles", "scan_w1_traffic.json")
+    p = os.path.join(ROOT, "profiles", "scan_lb_traffic.json")
     try:
         return float(json.load(open(p))["dram_bytes_per_launch"])
     except Exception:
@@ -320,8 +320,8 @@ def main():
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes, "kernel": "scan_w1_kernel<F_LEV,u32>",
-                         "note": "ALU-bound by design: ~11 int ops per candidate char; see DESIGN.md"},
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel": "scan_lb_kernel<F_LEV,u32>",
+                         "note": "ALU-pipe bound by design (8 ALU-pipe ops per candidate char, pipe ~83% busy); traffic = ncu DRAM bytes of one launch; see DESIGN.md section 5"},
         }
         if world == 1 and not args.no_cpu_baseline:
             from oracle import oracle as orc

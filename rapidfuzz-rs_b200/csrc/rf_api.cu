@@ -136,13 +136,13 @@ rf_status rf_set_option(const char* name, int value) {
 int rf_result_is_float(rf_metric metric, rf_kind kind) { return result_is_float((int)metric, (int)kind) ? 1 : 0; }
 
 // ------------------------------------------------------------------------------------------------ corpus
-static rf_status corpus_alloc(rf_corpus* c, bool off64) {
+static rf_status corpus_alloc(rf_corpus* c, bool off64, cudaStream_t st) {
   // 64 bytes of zeroed slack behind the chars (TMA copies whole 16-byte lines, readers over-read one word);
   // 16 entries of slack behind the offsets.
-  RF_CUDA(cudaMalloc(&c->d_chars, c->total + 64));
-  RF_CUDA(cudaMemset(c->d_chars + c->total, 0, 64));
-  if (off64) RF_CUDA(cudaMalloc(&c->d_off64, (c->n + 1 + 16) * sizeof(uint64_t)));
-  else RF_CUDA(cudaMalloc(&c->d_off32, (c->n + 1 + 16) * sizeof(uint32_t)));
+  RF_CUDA(dev_alloc(&c->d_chars, c->total + 64, st));
+  RF_CUDA(cudaMemsetAsync(c->d_chars + c->total, 0, 64, st));
+  if (off64) RF_CUDA(dev_alloc(&c->d_off64, (c->n + 1 + 16) * sizeof(uint64_t), st));
+  else RF_CUDA(dev_alloc(&c->d_off32, (c->n + 1 + 16) * sizeof(uint32_t), st));
   return RF_OK;
 }
 
@@ -183,10 +183,10 @@ static rf_status corpus_create_host(const uint8_t* chars, const void* offsets, b
   c->n = n;
   c->total = total;
   const bool off64 = total >= 0xFFFFFFF0ull;
-  rf_status s = corpus_alloc(c, off64);
-  if (s != RF_OK) { rf_corpus_destroy(c); return s; }
   cudaStream_t st;
   if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { rf_corpus_destroy(c); return fail(RF_ERR_CUDA, "stream"); }
+  rf_status s = corpus_alloc(c, off64, st);
+  if (s != RF_OK) { cudaStreamSynchronize(st); cudaStreamDestroy(st); rf_corpus_destroy(c); return s; }
   cudaError_t e = cudaSuccess;
   if (total) e = cudaMemcpyAsync(c->d_chars, chars, total, cudaMemcpyHostToDevice, st);
   uint64_t* tmp64 = nullptr;
@@ -195,7 +195,7 @@ static rf_status corpus_create_host(const uint8_t* chars, const void* offsets, b
       e = cudaMemcpyAsync(off64 ? (void*)c->d_off64 : (void*)c->d_off32, offsets, (n + 1) * (in64 ? 8 : 4),
                           cudaMemcpyHostToDevice, st);
     } else if (in64) {  // u64 on the host, u32 on the device: upload then narrow on the GPU
-      e = cudaMalloc(&tmp64, (n + 1) * 8);
+      e = dev_alloc(&tmp64, (n + 1) * 8, st);
       if (e == cudaSuccess) e = cudaMemcpyAsync(tmp64, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, st);
       if (e == cudaSuccess) {
         narrow_offsets<<<1024, 256, 0, st>>>(tmp64, c->d_off32, n + 1);
@@ -209,7 +209,8 @@ static rf_status corpus_create_host(const uint8_t* chars, const void* offsets, b
     s = corpus_finish(c, st);
     if (s == RF_OK) e = cudaStreamSynchronize(st);
   }
-  if (tmp64) cudaFree(tmp64);
+  dev_free(tmp64, st);
+  cudaStreamSynchronize(st);
   cudaStreamDestroy(st);
   if (e != cudaSuccess) { rf_corpus_destroy(c); return cuda_fail(e, "corpus upload"); }
   if (s != RF_OK) { rf_corpus_destroy(c); return s; }
@@ -239,9 +240,9 @@ rf_status rf_corpus_create_device_u8(const uint8_t* d_chars, const uint64_t* d_o
   c->n = n;
   c->total = total_chars;
   const bool off64 = total_chars >= 0xFFFFFFF0ull;
-  rf_status s = corpus_alloc(c, off64);
-  if (s != RF_OK) { rf_corpus_destroy(c); return s; }
   cudaStream_t st = (cudaStream_t)stream;
+  rf_status s = corpus_alloc(c, off64, st);
+  if (s != RF_OK) { cudaStreamSynchronize(st); rf_corpus_destroy(c); return s; }
   cudaError_t e = cudaSuccess;
   if (total_chars) e = cudaMemcpyAsync(c->d_chars, d_chars, total_chars, cudaMemcpyDeviceToDevice, st);
   if (e == cudaSuccess) {
@@ -264,10 +265,11 @@ rf_status rf_corpus_create_device_u8(const uint8_t* d_chars, const uint64_t* d_o
 rf_status rf_corpus_destroy(rf_corpus* c) {
   if (!c) return RF_OK;
   DeviceGuard g(c->device);
-  if (c->d_chars) cudaFree(c->d_chars);
-  if (c->d_off32) cudaFree(c->d_off32);
-  if (c->d_off64) cudaFree(c->d_off64);
-  lb_free(&c->lb);
+  cudaStream_t st = util_stream(c->device);
+  dev_free(c->d_chars, st);
+  dev_free(c->d_off32, st);
+  dev_free(c->d_off64, st);
+  lb_free(&c->lb, st);
   delete c;
   return RF_OK;
 }
@@ -418,18 +420,20 @@ static rf_status score_host(const rf_batch* b, const rf_corpus* c, rf_kind kind,
   if (!g.ok) return fail(RF_ERR_CUDA, "cudaSetDevice failed");
   const size_t bytes = (size_t)c->n * (want_f64 ? 8 : 4);
   void* d_out = nullptr;
-  RF_CUDA(cudaMalloc(&d_out, bytes));
   cudaStream_t st;
   cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
-  if (e != cudaSuccess) { cudaFree(d_out); return cuda_fail(e, "cudaStreamCreate"); }
+  if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
+  e = dev_alloc(&d_out, bytes, st);
+  if (e != cudaSuccess) { cudaStreamDestroy(st); return cuda_fail(e, "result buffer"); }
   rf_status s = score_device(b, c, kind, args, d_out, want_f64, st);
   if (s == RF_OK) {
     e = cudaMemcpyAsync(out_host, d_out, bytes, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) s = cuda_fail(e, "result download");
   }
+  dev_free(d_out, st);
+  cudaStreamSynchronize(st);
   cudaStreamDestroy(st);
-  cudaFree(d_out);
   return s;
 }
 

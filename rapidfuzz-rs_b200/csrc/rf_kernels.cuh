@@ -49,7 +49,7 @@ struct LbAlloc {  // owning pointers of an LbView
 };
 // Builds the layout from the CSR corpus on `stream` (synchronises once to size the data array).
 cudaError_t lb_build(const CorpusView& c, cudaStream_t stream, LbAlloc* out);
-void lb_free(LbAlloc* a);
+void lb_free(LbAlloc* a, cudaStream_t stream);
 
 struct ScanLaunch {
   CorpusView corpus;
@@ -93,5 +93,13 @@ cudaError_t launch_cdist_topk(const CdistLaunch& L);
 uint32_t cdist_parts(int sm_count);
 
 uint64_t kernel_launch_count();
+
+// Stream-ordered device allocations from the device's default memory pool (release threshold = never), so that
+// creating / destroying multi-GB corpora repeatedly does not pay cudaMalloc / cudaFree page-table work each time.
+cudaError_t dev_alloc(void** p, size_t bytes, cudaStream_t st);
+template <class T>
+inline cudaError_t dev_alloc(T** p, size_t bytes, cudaStream_t st) { return dev_alloc(reinterpret_cast<void**>(p), bytes, st); }
+void dev_free(void* p, cudaStream_t st);
+cudaStream_t util_stream(int device);  // internal non-blocking stream (frees issued from destroy functions)
 
 }  // namespace rfk

@@ -6,6 +6,8 @@
 // each group of 32 equal-length candidates word-interleaved gives both, once, at corpus creation.
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
+#include <mutex>
+#include <vector>
 #include "rf_kernels.cuh"
 
 namespace rfk {
@@ -124,12 +126,52 @@ struct CastU64 {
   __host__ __device__ uint64_t operator()(uint32_t v) const { return (uint64_t)v; }
 };
 
-void lb_free(LbAlloc* a) {
+// ---- pooled allocation helpers
+static std::mutex g_pool_mu;
+static std::vector<int> g_pool_ready;
+static std::vector<cudaStream_t> g_util_streams;
+
+static void ensure_pool(int dev) {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  if ((int)g_pool_ready.size() <= dev) g_pool_ready.resize(dev + 1, 0);
+  if (g_pool_ready[dev]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t never = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &never);
+  }
+  cudaGetLastError();
+  g_pool_ready[dev] = 1;
+}
+
+cudaError_t dev_alloc(void** p, size_t bytes, cudaStream_t st) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  ensure_pool(dev);
+  return cudaMallocAsync(p, bytes ? bytes : 16, st);
+}
+void dev_free(void* p, cudaStream_t st) {
+  if (p) cudaFreeAsync(p, st);
+}
+cudaStream_t util_stream(int device) {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  if ((int)g_util_streams.size() <= device) g_util_streams.resize(device + 1, nullptr);
+  if (!g_util_streams[device]) {
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(device);
+    cudaStreamCreateWithFlags(&g_util_streams[device], cudaStreamNonBlocking);
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  return g_util_streams[device];
+}
+
+void lb_free(LbAlloc* a, cudaStream_t st) {
   if (!a) return;
-  if (a->perm) cudaFree(a->perm);
-  if (a->lens) cudaFree(a->lens);
-  if (a->goff) cudaFree(a->goff);
-  if (a->gdata) cudaFree(a->gdata);
+  dev_free(a->perm, st);
+  dev_free(a->lens, st);
+  dev_free(a->goff, st);
+  dev_free(a->gdata, st);
   *a = LbAlloc{};
 }
 
@@ -150,10 +192,10 @@ cudaError_t lb_build(const CorpusView& c, cudaStream_t st, LbAlloc* out) {
     e = (x);                   \
     if (e != cudaSuccess) goto fail; \
   } while (0)
-  LB_TRY(cudaMalloc(&a.perm, n_pad * sizeof(uint32_t)));
-  LB_TRY(cudaMalloc(&a.lens, n_pad * sizeof(uint32_t)));
-  LB_TRY(cudaMalloc(&a.goff, (ngroups + 1) * sizeof(uint64_t)));
-  LB_TRY(cudaMalloc(&grows, (ngroups + 1) * sizeof(uint32_t)));
+  LB_TRY(dev_alloc(&a.perm, n_pad * sizeof(uint32_t), st));
+  LB_TRY(dev_alloc(&a.lens, n_pad * sizeof(uint32_t), st));
+  LB_TRY(dev_alloc(&a.goff, (ngroups + 1) * sizeof(uint64_t), st));
+  LB_TRY(dev_alloc(&grows, (ngroups + 1) * sizeof(uint32_t), st));
   lb_sort_kernel<<<nblocks, 1024, 0, st>>>(c.off32, c.off64, c.n, n_pad, a.perm, a.lens);
   LB_TRY(cudaGetLastError());
   {
@@ -165,13 +207,13 @@ cudaError_t lb_build(const CorpusView& c, cudaStream_t st, LbAlloc* out) {
   {
     cub::TransformInputIterator<uint64_t, CastU64, const uint32_t*> in(grows, CastU64());
     LB_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, a.goff, (int64_t)(ngroups + 1), st));
-    LB_TRY(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
+    LB_TRY(dev_alloc(&tmp, tmp_bytes, st));
     LB_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, in, a.goff, (int64_t)(ngroups + 1), st));
   }
   LB_TRY(cudaMemcpyAsync(&a.total_rows, a.goff + ngroups, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
   LB_TRY(cudaStreamSynchronize(st));
   // 16 rows of slack: readers load up to 3 rows and prefetch up to 8 rows past the end of the last group
-  LB_TRY(cudaMalloc(&a.gdata, (a.total_rows + 16) * 256));
+  LB_TRY(dev_alloc(&a.gdata, (a.total_rows + 16) * 256, st));
   LB_TRY(cudaMemsetAsync(a.gdata + a.total_rows * 64, 0, 16 * 256, st));
   {
     uint64_t blocks = (ngroups + 7) / 8;
@@ -180,14 +222,14 @@ cudaError_t lb_build(const CorpusView& c, cudaStream_t st, LbAlloc* out) {
     LB_TRY(cudaGetLastError());
   }
   LB_TRY(cudaStreamSynchronize(st));
-  cudaFree(grows);
-  cudaFree(tmp);
+  dev_free(grows, st);
+  dev_free(tmp, st);
   *out = a;
   return cudaSuccess;
 fail:
-  if (grows) cudaFree(grows);
-  if (tmp) cudaFree(tmp);
-  lb_free(&a);
+  dev_free(grows, st);
+  dev_free(tmp, st);
+  lb_free(&a, st);
   return e;
 #undef LB_TRY
 }

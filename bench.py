@@ -35,7 +35,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=int(os.environ.get("RF_BENCH_N", 100_000_000)),
+    ap.add_argument("--candidates", dest="n", type=int, default=int(os.environ.get("RF_BENCH_N", 100_000_000)),
                     help="candidates per GPU (default 10^8 = BASELINE config 2)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -54,7 +54,8 @@ def ncu_traffic_per_launch():
     """dram__bytes_read.sum + dram__bytes_write.sum of the scan kernel from the committed ncu capture."""
     p = os.path.join(ROOT, "profiles", "scan_lb_traffic.json")
     try:
-        return float(json.load(open(p))["dram_bytes_per_launch"])
+        d = json.load(open(p))
+        return float(d["dram_bytes_per_launch"]), float(d.get("candidates", 1e8))
     except Exception:
         return None
 
@@ -118,6 +119,14 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def host_threads():
+    """All host threads this process may use (torchrun exports OMP_NUM_THREADS=1; the CPU arm must not obey it)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def cpu_oracle_rate(n_sample, threads, reps=1):
     """Times the CPU oracle (port of the reference path) on the first n_sample candidates of the workload."""
     from oracle import oracle as orc
@@ -142,7 +151,7 @@ def run_reference(args):
         return
     from oracle import oracle as orc
     import rapidfuzz_b200 as rf
-    threads = orc.max_threads()
+    threads = host_threads()
     n_sample = min(args.n, 4_000_000 * max(1, min(threads, 16)))
     q = rf.synth_query(SEED, QUERY_LEN)
     chars, offsets = rf.synth_corpus(SEED, q, n_sample, MIN_LEN, MAX_LEN, KMAX)
@@ -196,8 +205,7 @@ def main():
     if os.environ.get("RF_W1_PATH"):  # dev knob: 1 = CSR/TMA-tile kernel instead of the interleaved-layout kernel
         _ffi.check(L.rf_set_option(b"single_word_path", int(os.environ["RF_W1_PATH"])))
     n = args.n
-    ncpu = os.cpu_count() or 8
-    gen_threads = max(1, ncpu // world)
+    gen_threads = max(1, host_threads() // world)
 
     # ---- synthetic shard of this rank, generated into pinned host memory
     q = rf.synth_query(SEED, QUERY_LEN)
@@ -301,6 +309,8 @@ def main():
         alg_bytes = total + 8 * n
         achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
         traffic = ncu_traffic_per_launch()
+        if traffic is not None:  # the capture was taken at `candidates` per launch; traffic is linear in n
+            traffic = traffic[0] * (n / traffic[1])
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -324,8 +334,7 @@ def main():
                          "note": "ALU-pipe bound by design (8 ALU-pipe ops per candidate char, pipe ~83% busy); traffic = ncu DRAM bytes of one launch; see DESIGN.md section 5"},
         }
         if world == 1 and not args.no_cpu_baseline:
-            from oracle import oracle as orc
-            threads = orc.max_threads()
+            threads = host_threads()
             n_sample = min(n, 2_000_000 * max(1, min(threads, 32)))
             rate, secs = cpu_oracle_rate(n_sample, threads)
             rate1, _ = cpu_oracle_rate(min(n, 2_000_000), 1)

@@ -121,6 +121,22 @@ rf_status rf_batch_similarity_f64(const rf_batch* b, const rf_corpus* c, const r
 rf_status rf_batch_normalized_distance_f64(const rf_batch* b, const rf_corpus* c, const rf_args* args, double* out);
 rf_status rf_batch_normalized_similarity_f64(const rf_batch* b, const rf_corpus* c, const rf_args* args, double* out);
 
+/* ---- streaming: the same loop when the candidates live in HOST memory and are not kept on the GPU
+ * (the literal shape of `for c in candidates { scorer.distance(c) }`, levenshtein.rs:1740-1777 / bench_levenshtein.rs:51-58).
+ * The CSR corpus is cut into chunks; H2D copy, scan and result D2H of successive chunks overlap on separate
+ * streams, so a call costs about (total bytes + 4..8 B offsets per candidate) / PCIe bandwidth.  Pinned
+ * (page-locked) chars/offsets/out buffers give full link speed; pageable buffers work, slower.  Results and
+ * errors are identical to rf_corpus_create_* + rf_batch_score_*.  Tunables: rf_set_option("stream_chunk_mb" |
+ * "stream_chunk_kcand"). */
+rf_status rf_batch_stream_u32(const rf_batch* b, const uint8_t* chars, const uint64_t* offsets, uint64_t n,
+                              rf_kind kind, const rf_args* args, uint32_t* out_host);
+rf_status rf_batch_stream_u32_off32(const rf_batch* b, const uint8_t* chars, const uint32_t* offsets, uint64_t n,
+                                    rf_kind kind, const rf_args* args, uint32_t* out_host);
+rf_status rf_batch_stream_f64(const rf_batch* b, const uint8_t* chars, const uint64_t* offsets, uint64_t n,
+                              rf_kind kind, const rf_args* args, double* out_host);
+rf_status rf_batch_stream_f64_off32(const rf_batch* b, const uint8_t* chars, const uint32_t* offsets, uint64_t n,
+                                    rf_kind kind, const rf_args* args, double* out_host);
+
 /* ---- many-vs-many (new on this side; the reference has no cdist -- SURVEY fact 3): for each of nq queries
  * the k best candidates by (distance ascending, index ascending); fewer than k hits are padded with
  * (UINT32_MAX, UINT32_MAX).  Levenshtein distance (unit weights), queries of length <= 64, k <= 64; with
@@ -146,7 +162,9 @@ rf_status rf_synth_corpus_u8(uint64_t seed, const uint8_t* query, uint32_t query
  *   "build_interleaved_layout" (default 1): corpora created afterwards also keep the length-bucketed,
  *        warp-interleaved copy that the fastest single-word kernel reads (about +1.2x corpus memory);
  *   "single_word_path" (default 0): 0 = interleaved-layout kernel when the corpus has it,
- *        1 = CSR kernel (TMA-staged tiles, bucketed by length in shared memory). */
+ *        1 = CSR kernel (TMA-staged tiles, bucketed by length in shared memory);
+ *   "stream_chunk_mb" (default 64), "stream_chunk_kcand" (default 2048): chunk size of rf_batch_stream_* in
+ *        MiB of candidate bytes / thousands (x1024) of candidates, whichever is hit first. */
 rf_status rf_set_option(const char* name, int value);
 
 /* kernel launches issued by this library in this process so far (bench.py reports the delta) */

@@ -36,6 +36,10 @@ def build(force=False, verbose=False):
         cmd.insert(1, "-Xptxas=-v")
     if os.environ.get("RF_DEBUG_MW"):
         cmd.insert(1, "-DRF_DEBUG_MW")
+    for d in os.environ.get("RF_DEFINES", "").split():   # dev A/B builds, e.g. RF_DEFINES=RF_LEV_NO_DP4A RF_LIB_OUT=...
+        cmd.insert(1, "-D" + d)
+    if os.environ.get("RF_LIB_OUT"):
+        cmd[cmd.index("-o") + 1] = os.environ["RF_LIB_OUT"]
     subprocess.check_call(cmd)
     return LIB
 

@@ -21,6 +21,8 @@ static thread_local std::string g_last_error;
 // tuning knobs (rf_set_option)
 static std::atomic<int> g_build_lb{1};   // build the length-bucketed interleaved layout at corpus creation
 static std::atomic<int> g_w1_path{0};    // 0: interleaved-layout kernel when available, 1: CSR/TMA-tile kernel
+static std::atomic<int> g_stream_mb{64};      // rf_batch_stream_*: chunk size in candidate bytes (MiB)
+static std::atomic<int> g_stream_kcand{2048}; // rf_batch_stream_*: chunk size in candidates (x1024)
 
 static rf_status fail(rf_status s, const std::string& msg) {
   g_last_error = msg;
@@ -130,6 +132,8 @@ rf_status rf_set_option(const char* name, int value) {
   if (!name) return fail(RF_ERR_INVALID_ARG, "name is NULL");
   if (!strcmp(name, "build_interleaved_layout")) { g_build_lb.store(value ? 1 : 0); return RF_OK; }
   if (!strcmp(name, "single_word_path")) { g_w1_path.store(value ? 1 : 0); return RF_OK; }
+  if (!strcmp(name, "stream_chunk_mb")) { if (value < 1) return fail(RF_ERR_INVALID_ARG, "stream_chunk_mb < 1"); g_stream_mb.store(value); return RF_OK; }
+  if (!strcmp(name, "stream_chunk_kcand")) { if (value < 1) return fail(RF_ERR_INVALID_ARG, "stream_chunk_kcand < 1"); g_stream_kcand.store(value); return RF_OK; }
   return fail(RF_ERR_INVALID_ARG, std::string("unknown option: ") + name);
 }
 
@@ -378,37 +382,48 @@ static rf_status make_epi(const rf_batch* b, rf_kind kind, const rf_args* args, 
   return RF_OK;
 }
 
-static rf_status score_device(const rf_batch* b, const rf_corpus* c, rf_kind kind, const rf_args* args, void* out_dev,
-                              bool want_f64, cudaStream_t st) {
-  if (!b || !c) return fail(RF_ERR_INVALID_ARG, "NULL handle");
+// Scores the candidates described by `cv` (+ optional interleaved copy `lb`), all resident on `device`.
+static rf_status score_view(const rf_batch* b, const CorpusView& cv, const LbAlloc* lb, int device, rf_kind kind,
+                            const rf_args* args, void* out_dev, bool want_f64, cudaStream_t st) {
+  if (!b) return fail(RF_ERR_INVALID_ARG, "NULL handle");
   if ((int)kind < 0 || (int)kind > 3) return fail(RF_ERR_INVALID_ARG, "unknown kind");
-  if (b->device != c->device) return fail(RF_ERR_INVALID_ARG, "batch and corpus live on different devices");
+  if (b->device != device) return fail(RF_ERR_INVALID_ARG, "batch and corpus live on different devices");
   if ((rf_result_is_float(b->metric, kind) != 0) != want_f64)
     return fail(RF_ERR_INVALID_ARG, want_f64 ? "this (metric, kind) yields u32 results; use the _u32 entry point"
                                              : "this (metric, kind) yields f64 results; use the _f64 entry point");
-  if (c->n == 0) return RF_OK;
+  if (cv.n == 0) return RF_OK;
   if (!out_dev) return fail(RF_ERR_INVALID_ARG, "out is NULL");
   ScanLaunch L{};
   rf_status s = make_epi(b, kind, args, &L.epi);
   if (s != RF_OK) return s;
-  DeviceGuard g(c->device);
+  DeviceGuard g(device);
   if (!g.ok) return fail(RF_ERR_CUDA, "cudaSetDevice failed");
-  L.corpus = CorpusView{c->d_chars, c->d_off32, c->d_off64, c->n, c->total};
-  L.lb = LbView{c->lb.perm, c->lb.lens, c->lb.goff, c->lb.gdata, c->lb.ngroups};
-  L.lb_counter = counter_slot(c->device);
-  if (!L.lb_counter) return fail(RF_ERR_OOM, "scheduler scratch allocation failed");
+  L.corpus = cv;
+  const bool use_lb = lb && lb->gdata && g_w1_path.load() == 0;
+  if (use_lb) {
+    L.lb = LbView{lb->perm, lb->lens, lb->goff, lb->gdata, lb->ngroups};
+    L.lb_counter = counter_slot(device);
+    if (!L.lb_counter) return fail(RF_ERR_OOM, "scheduler scratch allocation failed");
+  }
   L.query = b->view;
   L.out = out_dev;
   L.out_is_f64 = want_f64 ? 1 : 0;
   L.stream = st;
-  L.sm_count = sm_count_of(c->device);
+  L.sm_count = sm_count_of(device);
   const Family fam = family_of(L.epi.metric, L.epi.wclass);
   cudaError_t e;
-  if (b->len1 <= 64) e = (c->lb.gdata && g_w1_path.load() == 0) ? launch_scan_lb(L) : launch_scan_w1(L);
+  if (b->len1 <= 64) e = use_lb ? launch_scan_lb(L) : launch_scan_w1(L);
   else if (fam == F_JARO) e = launch_jaro_mw(L);
   else e = launch_scan_mw(L);
   if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
   return RF_OK;
+}
+
+static rf_status score_device(const rf_batch* b, const rf_corpus* c, rf_kind kind, const rf_args* args, void* out_dev,
+                              bool want_f64, cudaStream_t st) {
+  if (!b || !c) return fail(RF_ERR_INVALID_ARG, "NULL handle");
+  return score_view(b, CorpusView{c->d_chars, c->d_off32, c->d_off64, c->n, c->total}, &c->lb, c->device, kind, args,
+                    out_dev, want_f64, st);
 }
 
 static rf_status score_host(const rf_batch* b, const rf_corpus* c, rf_kind kind, const rf_args* args, void* out_host,
@@ -469,6 +484,152 @@ rf_status rf_batch_normalized_distance_f64(const rf_batch* b, const rf_corpus* c
 rf_status rf_batch_normalized_similarity_f64(const rf_batch* b, const rf_corpus* c, const rf_args* a, double* out) {
   return score_host(b, c, RF_NORMALIZED_SIMILARITY, a, out, true);
 }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ streaming
+// One-shot scoring of HOST-resident candidates: the literal shape of the reference's hot loop
+// (`for c in candidates { scorer.distance(c) }`, levenshtein.rs:1740-1777) when the candidates are not kept on
+// the GPU.  The CSR corpus is cut into chunks; every chunk goes H2D -> scan (CSR kernels, no layout build) ->
+// D2H on one of kSlots streams, so the PCIe copies of one chunk overlap the scan and the result download of
+// the others.  Steady state is bound by the H2D link (about len+4 bytes per candidate).
+namespace {
+constexpr int kSlots = 3;
+struct StreamSlot {
+  cudaStream_t st = nullptr;
+  uint8_t* d_chars = nullptr;
+  void* d_offs = nullptr;
+  void* d_out = nullptr;
+};
+struct StreamCtx {
+  std::mutex mu;  // one streaming call per device at a time
+  bool ready = false;
+  uint64_t cap_bytes = 0, cap_n = 0;
+  StreamSlot slot[kSlots];
+};
+
+StreamCtx* stream_ctx(int device) {
+  static std::mutex mu;
+  static std::vector<StreamCtx*> all;
+  std::lock_guard<std::mutex> lk(mu);
+  if ((int)all.size() <= device) all.resize(device + 1, nullptr);
+  if (!all[device]) all[device] = new StreamCtx();
+  return all[device];
+}
+
+void stream_ctx_release(StreamCtx* x) {
+  for (auto& s : x->slot) {
+    if (s.d_chars) cudaFree(s.d_chars);
+    if (s.d_offs) cudaFree(s.d_offs);
+    if (s.d_out) cudaFree(s.d_out);
+    if (s.st) cudaStreamDestroy(s.st);
+    s = StreamSlot{};
+  }
+  x->ready = false;
+}
+
+cudaError_t stream_ctx_prepare(StreamCtx* x, uint64_t cap_bytes, uint64_t cap_n) {
+  if (x->ready && x->cap_bytes == cap_bytes && x->cap_n == cap_n) return cudaSuccess;
+  stream_ctx_release(x);
+  cudaError_t e = cudaSuccess;
+  for (auto& s : x->slot) {
+    if ((e = cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking)) != cudaSuccess) break;
+    // chars: 16 bytes of alignment lead-in + 64 bytes of over-read slack; offsets: 16 entries of slack
+    if ((e = cudaMalloc(&s.d_chars, cap_bytes + 256)) != cudaSuccess) break;
+    if ((e = cudaMemset(s.d_chars, 0, cap_bytes + 256)) != cudaSuccess) break;
+    if ((e = cudaMalloc(&s.d_offs, (cap_n + 1 + 16) * 8)) != cudaSuccess) break;
+    if ((e = cudaMemset(s.d_offs, 0, (cap_n + 1 + 16) * 8)) != cudaSuccess) break;
+    if ((e = cudaMalloc(&s.d_out, cap_n * 8)) != cudaSuccess) break;
+  }
+  if (e != cudaSuccess) { stream_ctx_release(x); return e; }
+  x->cap_bytes = cap_bytes;
+  x->cap_n = cap_n;
+  x->ready = true;
+  return cudaSuccess;
+}
+
+template <class OffT>
+rf_status stream_impl(const rf_batch* b, const uint8_t* chars, const OffT* offsets, uint64_t n, rf_kind kind,
+                      const rf_args* args, void* out_host, bool want_f64) {
+  if (!b) return fail(RF_ERR_INVALID_ARG, "NULL handle");
+  if ((int)kind < 0 || (int)kind > 3) return fail(RF_ERR_INVALID_ARG, "unknown kind");
+  if ((rf_result_is_float(b->metric, kind) != 0) != want_f64)
+    return fail(RF_ERR_INVALID_ARG, want_f64 ? "this (metric, kind) yields u32 results; use the _u32 entry point"
+                                             : "this (metric, kind) yields f64 results; use the _f64 entry point");
+  if (n == 0) return RF_OK;
+  if (!offsets || !out_host) return fail(RF_ERR_INVALID_ARG, "NULL argument");
+  if (offsets[0] != 0) return fail(RF_ERR_INVALID_ARG, "offsets[0] must be 0");
+  if (offsets[n] && !chars) return fail(RF_ERR_INVALID_ARG, "chars is NULL");
+  if (rf_device_count() <= b->device) return fail(RF_ERR_CUDA, "no such CUDA device");
+  DeviceGuard g(b->device);
+  if (!g.ok) return fail(RF_ERR_CUDA, "cudaSetDevice failed");
+  StreamCtx* x = stream_ctx(b->device);
+  std::lock_guard<std::mutex> lk(x->mu);
+  const uint64_t cap_bytes = (uint64_t)(g_stream_mb.load() > 0 ? g_stream_mb.load() : 1) << 20;
+  const uint64_t cap_n = (uint64_t)(g_stream_kcand.load() > 0 ? g_stream_kcand.load() : 1) << 10;
+  cudaError_t e = stream_ctx_prepare(x, cap_bytes, cap_n);
+  if (e != cudaSuccess) return cuda_fail(e, "streaming buffers");
+  const size_t osz = sizeof(OffT), rsz = want_f64 ? 8 : 4;
+  rf_status s = RF_OK;
+  uint64_t i0 = 0;
+  int k = 0;
+  while (i0 < n && s == RF_OK) {
+    // largest i1 <= i0 + cap_n whose bytes (from the 16-byte aligned start) fit the slot
+    const uint64_t B0 = (uint64_t)offsets[i0] & ~15ull;
+    uint64_t hi = (n - i0 < cap_n) ? n : i0 + cap_n;
+    if ((uint64_t)offsets[hi] - B0 > cap_bytes) {
+      uint64_t lo = i0;  // invariant: offsets[lo] - B0 <= cap_bytes < offsets[hi] - B0
+      while (hi - lo > 1) {
+        const uint64_t mid = lo + (hi - lo) / 2;
+        if ((uint64_t)offsets[mid] - B0 <= cap_bytes) lo = mid; else hi = mid;
+      }
+      hi = lo;
+      if (hi == i0) { s = fail(RF_ERR_UNSUPPORTED, "a single candidate exceeds the streaming chunk size (raise stream_chunk_mb)"); break; }
+    }
+    const uint64_t i1 = hi, cn = i1 - i0;
+    const uint64_t B1 = (uint64_t)offsets[i1];
+    StreamSlot& sl = x->slot[k];
+    k = (k + 1) % kSlots;
+    if (B1 > B0) e = cudaMemcpyAsync(sl.d_chars, chars + B0, B1 - B0, cudaMemcpyHostToDevice, sl.st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(sl.d_offs, offsets + i0, (cn + 1) * osz, cudaMemcpyHostToDevice, sl.st);
+    if (e != cudaSuccess) { s = cuda_fail(e, "chunk upload"); break; }
+    // the kernels index chars with the caller's absolute offsets: hand them the slot shifted back by B0
+    CorpusView cv{sl.d_chars - B0, osz == 4 ? (const uint32_t*)sl.d_offs : nullptr,
+                  osz == 8 ? (const uint64_t*)sl.d_offs : nullptr, cn, B1 - (uint64_t)offsets[i0]};
+    s = score_view(b, cv, nullptr, b->device, kind, args, sl.d_out, want_f64, sl.st);
+    if (s != RF_OK) break;
+    e = cudaMemcpyAsync((uint8_t*)out_host + i0 * rsz, sl.d_out, cn * rsz, cudaMemcpyDeviceToHost, sl.st);
+    if (e != cudaSuccess) { s = cuda_fail(e, "chunk download"); break; }
+    i0 = i1;
+  }
+  for (auto& sl : x->slot) {
+    e = cudaStreamSynchronize(sl.st);
+    if (e != cudaSuccess && s == RF_OK) s = cuda_fail(e, "streaming scan");
+  }
+  return s;
+}
+}  // namespace
+
+extern "C" {
+rf_status rf_batch_stream_u32(const rf_batch* b, const uint8_t* chars, const uint64_t* offsets, uint64_t n, rf_kind kind,
+                              const rf_args* args, uint32_t* out_host) {
+  return stream_impl(b, chars, offsets, n, kind, args, out_host, false);
+}
+rf_status rf_batch_stream_u32_off32(const rf_batch* b, const uint8_t* chars, const uint32_t* offsets, uint64_t n,
+                                    rf_kind kind, const rf_args* args, uint32_t* out_host) {
+  return stream_impl(b, chars, offsets, n, kind, args, out_host, false);
+}
+rf_status rf_batch_stream_f64(const rf_batch* b, const uint8_t* chars, const uint64_t* offsets, uint64_t n, rf_kind kind,
+                              const rf_args* args, double* out_host) {
+  return stream_impl(b, chars, offsets, n, kind, args, out_host, true);
+}
+rf_status rf_batch_stream_f64_off32(const rf_batch* b, const uint8_t* chars, const uint32_t* offsets, uint64_t n,
+                                    rf_kind kind, const rf_args* args, double* out_host) {
+  return stream_impl(b, chars, offsets, n, kind, args, out_host, true);
+}
+}  // extern "C"
+
+extern "C" {
 
 // ------------------------------------------------------------------------------------------------ cdist
 static rf_status cdist_impl(const uint8_t* q_chars, const uint64_t* q_offsets, uint32_t nq, const rf_corpus* c,

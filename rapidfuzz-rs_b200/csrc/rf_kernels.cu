@@ -175,11 +175,22 @@ __device__ __forceinline__ uint32_t lev_w1_u32_fast(uint32_t pm_lane_saddr, Rd r
   const uint32_t one = two >> 1;
   uint32_t VP = 0xFFFFFFFFu << (32u - len1);
   uint32_t VN = 0;
+  // table address of text byte K of w = byte*128 + lane base.  IDP.4A (dot product of the 4 bytes of w with a
+  // selector word holding 128 in byte K, plus the base) does extract + scale + add in ONE FMA-pipe instruction;
+  // the PRMT + IMAD pair it replaces costs an ALU-pipe slot, and the ALU pipe is this kernel's bound.
+#ifdef RF_LEV_NO_DP4A
+#define RF_LEV32_ADDR(K)                                                             \
+    {                                                                                \
+      const uint32_t ch = __byte_perm(w, 0u, 0x4440u + (K));                         \
+      asm("mad.lo.u32 %0, %1, 128, %2;" : "=r"(addr) : "r"(ch), "r"(pm_lane_saddr)); \
+    }
+#else
+#define RF_LEV32_ADDR(K) addr = __dp4a(w, 0x80u << (8 * (K)), pm_lane_saddr);
+#endif
 #define RF_LEV32_STEP(K)                                                             \
   {                                                                                  \
-    const uint32_t ch = __byte_perm(w, 0u, 0x4440u + (K));                           \
     uint32_t addr, X;                                                                \
-    asm("mad.lo.u32 %0, %1, 128, %2;" : "=r"(addr) : "r"(ch), "r"(pm_lane_saddr));   \
+    RF_LEV32_ADDR(K)                                                                 \
     asm("ld.shared.u32 %0, [%1];" : "=r"(X) : "r"(addr));                            \
     const uint32_t D0 = ((((X & VP) + VP) ^ VP) | X) | VN;                           \
     uint32_t HP = VN | ~(D0 | VP);                                                   \
@@ -252,6 +263,7 @@ __device__ __forceinline__ uint32_t lev_w1_u32_fast(uint32_t pm_lane_saddr, Rd r
     }
   }
 #undef RF_LEV32_STEP
+#undef RF_LEV32_ADDR
   return len2 + (uint32_t)__popc(VP) - (uint32_t)__popc(VN);
 }
 

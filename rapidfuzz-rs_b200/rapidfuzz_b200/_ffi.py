@@ -7,7 +7,7 @@ import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-LIB_PATH = os.path.join(_ROOT, "lib", "librfgpu.so")
+LIB_PATH = os.environ.get("RF_LIB_PATH") or os.path.join(_ROOT, "lib", "librfgpu.so")  # RF_LIB_PATH: dev A/B builds
 
 RF_OK, RF_ERR_INVALID_ARG, RF_ERR_UNSUPPORTED, RF_ERR_CUDA, RF_ERR_OOM = range(5)
 METRICS = {"levenshtein": 0, "indel": 1, "lcs_seq": 2, "osa": 3, "jaro": 4, "jaro_winkler": 5, "ratio": 6}
@@ -57,6 +57,10 @@ SYMBOLS = {
     "rf_batch_similarity_f64": (_int, [_vp, _vp, _PA, _vp]),
     "rf_batch_normalized_distance_f64": (_int, [_vp, _vp, _PA, _vp]),
     "rf_batch_normalized_similarity_f64": (_int, [_vp, _vp, _PA, _vp]),
+    "rf_batch_stream_u32": (_int, [_vp, _vp, _vp, _u64, _int, _PA, _vp]),
+    "rf_batch_stream_u32_off32": (_int, [_vp, _vp, _vp, _u64, _int, _PA, _vp]),
+    "rf_batch_stream_f64": (_int, [_vp, _vp, _vp, _u64, _int, _PA, _vp]),
+    "rf_batch_stream_f64_off32": (_int, [_vp, _vp, _vp, _u64, _int, _PA, _vp]),
     "rf_cdist_topk_u8": (_int, [_vp, _vp, _u32, _vp, _PA, _u32, _vp, _vp]),
     "rf_cdist_topk_u8_device": (_int, [_vp, _vp, _u32, _vp, _PA, _u32, _vp, _vp, _vp]),
     "rf_synth_query_u8": (_int, [_u64, _u32, _vp]),

@@ -125,6 +125,26 @@ class BatchComparatorBase:
         mask = np.isnan(out) if is_f else (out == _ffi.NONE_U32)
         return np.ma.MaskedArray(out, mask=mask)
 
+    def stream(self, kind, chars, offsets, args=None, out=None):
+        """rf_batch_stream_*: scores HOST-resident candidates (CSR chars u8 + offsets u32/u64) without keeping a
+        corpus on the GPU; chunked H2D / scan / D2H pipeline.  Returns the raw sentinel-carrying array
+        (0xFFFFFFFF / NaN == None).  Pinned buffers (e.g. torch .pin_memory()) run at full PCIe speed."""
+        args = args if args is not None else Args()
+        chars = np.ascontiguousarray(chars, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets)
+        if offsets.dtype not in (np.uint32, np.uint64):
+            offsets = offsets.astype(np.uint64)
+        n = len(offsets) - 1
+        is_f = bool(_ffi.lib().rf_result_is_float(_ffi.METRICS[self.METRIC], _ffi.KINDS[kind]))
+        ca = args._c(is_f)
+        if out is None:
+            out = np.empty(n, dtype=np.float64 if is_f else np.uint32)
+        assert out.dtype == (np.float64 if is_f else np.uint32) and len(out) >= n and out.flags.c_contiguous
+        name = "rf_batch_stream_%s%s" % ("f64" if is_f else "u32", "_off32" if offsets.dtype == np.uint32 else "")
+        _ffi.check(getattr(_ffi.lib(), name)(self._h, chars.ctypes.data, offsets.ctypes.data, n, _ffi.KINDS[kind],
+                                             C.byref(ca), out.ctypes.data))
+        return out
+
     def score_into(self, kind, corpus, out_ptr, args=None, stream=0):
         """Device-pointer variant (rf_batch_score_*_device): results stay on the GPU at `out_ptr`
         (u32[n] or f64[n]); enqueued on `stream` (a cudaStream_t as int), no synchronisation."""

@@ -242,6 +242,67 @@ def test_large_corpus_properties():
     corpus.close()
 
 
+def _stream(metric, kind, q, chars, offsets, **kw):
+    from rapidfuzz_b200._scorer import Args, BatchComparatorBase
+    b = type("B", (BatchComparatorBase,), {"METRIC": metric})(q)
+    a = Args()
+    if kw.get("cutoff") is not None:
+        a = a.score_cutoff(kw["cutoff"])
+    try:
+        return b.stream(kind, chars, offsets, a)
+    finally:
+        b.close()
+
+
+@pytest.mark.parametrize("chunk_mb,chunk_kcand", [(64, 2048), (1, 2048), (64, 1), (1, 3)])
+def test_streaming_matches_oracle(chunk_mb, chunk_kcand):
+    """rf_batch_stream_*: host-resident CSR candidates, chunked H2D/scan/D2H pipeline; chunk boundaries at
+    arbitrary (unaligned) byte offsets; u32 and u64 offsets; every family; ragged + empty candidates."""
+    L = _ffi.lib()
+    _ffi.check(L.rf_set_option(b"stream_chunk_mb", chunk_mb))
+    _ffi.check(L.rf_set_option(b"stream_chunk_kcand", chunk_kcand))
+    try:
+        rng = np.random.default_rng(77)
+        q = (rng.integers(0, 5, 29) + 97).astype(np.uint8)
+        chars, offsets = make_corpus(rng, 20000, [0, 1, 3, 8, 20, 33, 64, 70, 300], alphabet=5, query=q)
+        for off in (offsets, offsets.astype(np.uint32)):
+            for m, kind, kw in (("levenshtein", "distance", {}), ("levenshtein", "distance", {"cutoff": 6}),
+                                ("indel", "normalized_similarity", {}), ("osa", "distance", {}),
+                                ("lcs_seq", "similarity", {}), ("jaro_winkler", "similarity", {}),
+                                ("jaro", "normalized_distance", {"cutoff": 0.4})):
+                got = _stream(m, kind, q, chars, off, **kw)
+                exp = orc.batch(m, kind, q, chars, offsets, nthreads=0, **kw)
+                assert_same(got, exp, ("stream", m, kind, kw, off.dtype))
+        # multi-word query + cutoff (config 3 shape) and multi-word Jaro through the same pipeline
+        q3 = rf.synth_query(3, 256)
+        c3, o3 = rf.synth_corpus(3, q3, 30000, 64, 256, 48)
+        assert_same(_stream("levenshtein", "distance", q3, c3, o3, cutoff=32),
+                    orc.batch("levenshtein", "distance", q3, c3, o3, nthreads=0, cutoff=32), "stream mw")
+        assert_same(_stream("jaro", "similarity", q3[:100], c3[: int(o3[2000])], o3[:2001]),
+                    orc.batch("jaro", "similarity", q3[:100], c3[: int(o3[2000])], o3[:2001], nthreads=0), "stream jaro mw")
+        # empty corpus / all-empty candidates
+        assert len(_stream("levenshtein", "distance", q, np.zeros(0, np.uint8), np.zeros(1, np.uint64))) == 0
+        z = np.zeros(6, np.uint64)
+        assert_same(_stream("levenshtein", "distance", q, np.zeros(0, np.uint8), z),
+                    orc.batch("levenshtein", "distance", q, np.zeros(0, np.uint8), z, nthreads=0), "stream empties")
+    finally:
+        _ffi.check(L.rf_set_option(b"stream_chunk_mb", 64))
+        _ffi.check(L.rf_set_option(b"stream_chunk_kcand", 2048))
+
+
+def test_streaming_large_equals_resident():
+    """5e6 config-2 candidates: the streaming entry point and the resident-corpus path agree bit for bit."""
+    q = rf.synth_query(2, 32)
+    chars, offsets = rf.synth_corpus(2, q, 5_000_000, 8, 64, 16)
+    corpus = rf.Corpus(chars, offsets)
+    d = gpu_batch("levenshtein", "distance", q, corpus)
+    corpus.close()
+    s = _stream("levenshtein", "distance", q, chars, offsets.astype(np.uint32))
+    assert np.array_equal(d, s)
+    exp = orc.batch("levenshtein", "distance", q, chars[: int(offsets[300000])], offsets[:300001], nthreads=0)
+    assert np.array_equal(s[:300000], exp)
+
+
 def _oracle_topk(queries, chars, offsets, k, cutoff=None):
     n = len(offsets) - 1
     idx = np.full((len(queries), k), 0xFFFFFFFF, dtype=np.uint32)

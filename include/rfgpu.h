@@ -163,6 +163,8 @@ rf_status rf_synth_corpus_u8(uint64_t seed, const uint8_t* query, uint32_t query
  *        warp-interleaved copy that the fastest single-word kernel reads (about +1.2x corpus memory);
  *   "single_word_path" (default 0): 0 = interleaved-layout kernel when the corpus has it,
  *        1 = CSR kernel (TMA-staged tiles, bucketed by length in shared memory);
+ *   "banded_levenshtein" (default 1): multi-word Levenshtein distance with score_cutoff <= 63 edits uses the
+ *        one-thread-per-candidate 64-bit Ukkonen-band kernel; 0 = always the multi-word block kernel;
  *   "stream_chunk_mb" (default 64), "stream_chunk_kcand" (default 2048): chunk size of rf_batch_stream_* in
  *        MiB of candidate bytes / thousands (x1024) of candidates, whichever is hit first. */
 rf_status rf_set_option(const char* name, int value);

@@ -21,6 +21,7 @@ static thread_local std::string g_last_error;
 // tuning knobs (rf_set_option)
 static std::atomic<int> g_build_lb{1};   // build the length-bucketed interleaved layout at corpus creation
 static std::atomic<int> g_w1_path{0};    // 0: interleaved-layout kernel when available, 1: CSR/TMA-tile kernel
+static std::atomic<int> g_band{1};       // multi-word Levenshtein with cutoff <= 63: banded kernel (0: block kernel)
 static std::atomic<int> g_stream_mb{64};      // rf_batch_stream_*: chunk size in candidate bytes (MiB)
 static std::atomic<int> g_stream_kcand{2048}; // rf_batch_stream_*: chunk size in candidates (x1024)
 
@@ -132,6 +133,7 @@ rf_status rf_set_option(const char* name, int value) {
   if (!name) return fail(RF_ERR_INVALID_ARG, "name is NULL");
   if (!strcmp(name, "build_interleaved_layout")) { g_build_lb.store(value ? 1 : 0); return RF_OK; }
   if (!strcmp(name, "single_word_path")) { g_w1_path.store(value ? 1 : 0); return RF_OK; }
+  if (!strcmp(name, "banded_levenshtein")) { g_band.store(value ? 1 : 0); return RF_OK; }
   if (!strcmp(name, "stream_chunk_mb")) { if (value < 1) return fail(RF_ERR_INVALID_ARG, "stream_chunk_mb < 1"); g_stream_mb.store(value); return RF_OK; }
   if (!strcmp(name, "stream_chunk_kcand")) { if (value < 1) return fail(RF_ERR_INVALID_ARG, "stream_chunk_kcand < 1"); g_stream_kcand.store(value); return RF_OK; }
   return fail(RF_ERR_INVALID_ARG, std::string("unknown option: ") + name);
@@ -305,13 +307,17 @@ rf_status rf_batch_create_u8(rf_metric metric, const uint8_t* query, uint32_t qu
   const uint32_t words = b->words ? b->words : 1;
   const size_t sz32 = 256 * sizeof(uint32_t), sz64 = 256 * sizeof(uint64_t);
   const size_t szw = (size_t)256 * words * sizeof(uint64_t);
-  std::vector<uint8_t> blob(2 * sz32 + 2 * sz64 + szw, 0);
+  const uint32_t bstride = (2 * (words + 2)) | 1u;  // u32 units, odd
+  const size_t szp = (size_t)256 * bstride * sizeof(uint32_t);
+  std::vector<uint8_t> blob(2 * sz32 + 2 * sz64 + szw + szp, 0);
   uint32_t* t32t = (uint32_t*)blob.data();
   uint32_t* t32b = t32t + 256;
   uint64_t* t64t = (uint64_t*)(blob.data() + 2 * sz32);
   uint64_t* t64b = t64t + 256;
   uint64_t* pmw = t64b + 256;
+  uint32_t* pmb = (uint32_t*)(pmw + (size_t)256 * words);
   for (uint32_t i = 0; i < query_len; ++i) pmw[(size_t)query[i] * words + i / 64] |= 1ull << (i % 64);
+  for (uint32_t i = 0; i < query_len; ++i) pmb[(size_t)query[i] * bstride + 2 + i / 32] |= 1u << (i % 32);
   if (query_len >= 1 && query_len <= 64) {
     for (int ch = 0; ch < 256; ++ch) {
       const uint64_t m = pmw[(size_t)ch * words];
@@ -333,6 +339,8 @@ rf_status rf_batch_create_u8(rf_metric metric, const uint8_t* query, uint32_t qu
   b->view.tab64_top = (const uint64_t*)(b->d_blob + 2 * sz32);
   b->view.tab64_bot = b->view.tab64_top + 256;
   b->view.pm_words = b->view.tab64_bot + 256;
+  b->view.pm_band = (const uint32_t*)(b->view.pm_words + (size_t)256 * words);
+  b->view.band_stride = bstride;
   *out = b;
   return RF_OK;
 }
@@ -414,6 +422,9 @@ static rf_status score_view(const rf_batch* b, const CorpusView& cv, const LbAll
   cudaError_t e;
   if (b->len1 <= 64) e = use_lb ? launch_scan_lb(L) : launch_scan_w1(L);
   else if (fam == F_JARO) e = launch_jaro_mw(L);
+  else if (g_band.load() && L.epi.metric == M_LEVENSHTEIN && L.epi.wclass == WC_UNIFORM && L.epi.kind == K_DISTANCE &&
+           L.epi.has_cutoff && L.epi.cutoff_u / L.epi.w_ins <= 63)
+    e = launch_scan_band(L, (uint32_t)(L.epi.cutoff_u / L.epi.w_ins));  // small cutoff: 64-bit Ukkonen band per thread
   else e = launch_scan_mw(L);
   if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
   return RF_OK;

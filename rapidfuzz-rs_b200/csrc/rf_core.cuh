@@ -81,6 +81,48 @@ struct ByteReader {
   }
 };
 
+// Same for 16 bytes per call from a 16-byte-aligned buffer (one 128-bit load per 16 characters; a thread
+// that walks its own candidate issues 4x fewer memory requests than with 4-byte words).  Needs 31 bytes of
+// over-read slack behind the data.
+struct Bytes16 { uint32_t w[4]; };
+struct ByteReader16 {
+  const uint32_t* p;  // next aligned 16-byte line, as words
+  uint32_t sh, wsel;
+  uint32_t cur[4];
+  RF_HD ByteReader16(const uint8_t* aligned16_base, uint32_t start) {
+    p = reinterpret_cast<const uint32_t*>(aligned16_base + (start & ~15u));
+    sh = (start & 3u) * 8u;
+    wsel = (start >> 2) & 3u;
+    load(cur);
+  }
+  RF_HD void load(uint32_t* d) {
+#if defined(__CUDA_ARCH__)
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+#else
+    d[0] = p[0]; d[1] = p[1]; d[2] = p[2]; d[3] = p[3];
+#endif
+    p += 4;
+  }
+  RF_HD Bytes16 next16() {
+    uint32_t nxt[4];
+    load(nxt);
+    const uint32_t W[8] = {cur[0], cur[1], cur[2], cur[3], nxt[0], nxt[1], nxt[2], nxt[3]};
+    uint32_t A[6], B[5];
+    const bool s2 = (wsel & 2u) != 0, s1 = (wsel & 1u) != 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) A[i] = s2 ? W[i + 2] : W[i];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) B[i] = s1 ? A[i + 1] : A[i];
+    Bytes16 r;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r.w[i] = funnel_r(B[i], B[i + 1], sh);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
+    return r;
+  }
+};
+
 // ------------------------------------------------------------------------------------------------
 // Levenshtein, one machine word (query length 1..BITS).  `tab(ch)` returns the TOP-aligned match mask
 // PM[ch] << (BITS - len1).
@@ -184,6 +226,63 @@ RF_HD uint32_t lcs_w1(const Tab& tab, Rd rd, uint32_t len2) {
   }
 #undef RF_LCS_STEP
   return (uint32_t)popc((W)~S);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Banded Levenshtein for a distance cutoff k <= 63 and ANY query length (the job of the reference's
+// hyrroe2003_small_band, levenshtein.rs:509-617, and of the Ukkonen band in hyrroe2003_block, :897-985).
+// GPU-first formulation: a cell on diagonal h = j - i can lie on a path of cost <= k only if
+// |h| + |d - h| <= k (d = len2 - len1), i.e. on one of at most k + 1 <= 64 diagonals, so ONE 64-bit window that
+// slides down one pattern row per text column holds the whole band whatever the query length -- one thread per
+// candidate, no cross-lane carries.  Window bit b at (1-based) column j is pattern row j - h_hi + b.
+//   * rows above the matrix (<= 0) are a flat region (vertical delta 0, no match), which yields D[0][j] = j;
+//   * the row entering at the bottom takes the diagonal-move bound (VP = HN | ~HP of its upper neighbour);
+//   * the row leaving at the top becomes the boundary with horizontal delta +1.
+//   Out-of-band inputs are therefore never under-estimated, in-band cells of any path of cost <= k are exact,
+//   and values along a diagonal never decrease: once the cell on the end diagonal d exceeds k the result is
+//   None.  `bn` is the value of the window's first row, the score of the end diagonal follows by popcounts.
+struct LevBand64 {
+  uint64_t VP, VN, mask;
+  int32_t bn;  // D'[first window row][j] after column j
+  int32_t s;   // 0-based pattern index of window bit 0 at the next column (may be negative)
+  // requires |len2 - len1| <= k <= 63
+  RF_HD void init(uint32_t len1, uint32_t len2, uint32_t k) {
+    const int32_t d = (int32_t)len2 - (int32_t)len1;
+    const int32_t ad = d < 0 ? -d : d;
+    const int32_t e = ((int32_t)k - ad) / 2;
+    const int32_t h_hi = (d > 0 ? d : 0) + e;  // highest diagonal of the band, <= k
+    VP = ~0ull << h_hi;                        // rows >= 1 of column 0: vertical delta +1
+    VN = 0;
+    mask = (1ull << (h_hi - d)) - 1ull;        // window bits above the end diagonal's row (h_hi - d <= k)
+    bn = 0;
+    s = -h_hi;
+  }
+  // X = window of the match vector of text char j: bit b set iff query[s + b] == char (0 outside 0..len1-1)
+  RF_HD void step(uint64_t X) {
+    const uint64_t D0 = (((X & VP) + VP) ^ VP) | X | VN;
+    const uint64_t HP = VN | ~(D0 | VP);
+    const uint64_t HN = D0 & VP;
+    bn += 1 - (int32_t)((uint32_t)D0 & 1u);
+    const uint64_t D0s = D0 >> 1;  // the window moves down one row: shift D0 instead of HP/HN
+    VP = HN | ~(D0s | HP);
+    VN = D0s & HP;
+    ++s;
+  }
+  // value of the cell on the end diagonal in the column processed last (== the distance after column len2)
+  RF_HD int32_t score() const { return bn + popc(VP & mask) - popc(VN & mask); }
+};
+
+// 64-bit window starting at (possibly negative) bit position s of a match-vector row.  The row is stored as
+// 32-bit words with 64 zero bits in front and behind (row32[2 + w] = bits 32w.. of the match vector), so
+// position s + 64 >= 1 selects three consecutive words a,b,c at index (s+64)>>5 and two funnel shifts.
+RF_HD uint64_t band_window32(uint32_t a, uint32_t b, uint32_t c, uint32_t o) {
+  return (uint64_t)funnel_r(a, b, o) | ((uint64_t)funnel_r(b, c, o) << 32);
+}
+// k <= 32 only.  Only the band's own bits (at most k+1 <= 33 from bit 0) have to be right: rows above them in the window lie
+// outside the band, hold over-estimates anyway, and never influence lower bits (carries only travel up).  Two
+// words give window bits 0..(63 - o) >= 32, the rest reads as no-match.
+RF_HD uint64_t band_window32_low33(uint32_t a, uint32_t b, uint32_t o) {
+  return (uint64_t)funnel_r(a, b, o) | ((uint64_t)(b >> o) << 32);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -1052,6 +1052,229 @@ cudaError_t launch_scan_mw(const ScanLaunch& L) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------ band
+// Levenshtein distance with score_cutoff k <= 63 for multi-word queries (BASELINE config 3).  The Ukkonen band
+// of a cutoff-k problem has at most k+1 diagonals, so one 64-bit sliding window per candidate (LevBand64,
+// rf_core.cuh) replaces the ceil(len1/64)-word column of the block algorithm: one THREAD per candidate, no
+// shuffles.  Three dense passes, each a grid-stride loop of full warps:
+//   classify  length filter |len1-len2| > k -> None (levenshtein.rs:1045-1047); survivors appended to list A
+//   run<A>    first `cols_a` columns of every list-A candidate, early exit once the end diagonal exceeds k
+//             (random candidates die here); finished ones are written, the still-alive go to list B
+//   run<B>    list B (the true near-matches) start to end, 32 per warp
+// The query's match vectors (one zero word of padding on both sides of each row) sit in shared memory.
+struct BandParams {
+  const uint8_t* chars;
+  const uint32_t* off32;
+  const uint64_t* off64;
+  uint64_t i0, i1;        // candidate range of this batch
+  const uint32_t* pmb;    // [256][stride] match vectors as 32-bit words, 2 zero words in front, >= 2 behind
+  uint32_t stride;        // odd: the 32 lanes' rows spread over all shared-memory banks
+  uint32_t len1;
+  uint32_t cut;           // cutoff in unit-cost edits, <= 63
+  uint32_t maxcols;       // columns to run in this pass
+  const uint32_t* list_in;
+  const uint32_t* cnt_in;
+  uint32_t* list_out;
+  uint32_t* cnt_out;
+  uint32_t* out;
+  Epi epi;
+};
+
+__device__ __forceinline__ uint64_t band_off(const BandParams& p, uint64_t i) {
+  return p.off64 ? p.off64[i] : (uint64_t)p.off32[i];
+}
+
+// warp-aggregated append of the lanes with `flag` set
+__device__ __forceinline__ void band_append(bool flag, uint32_t value, uint32_t* list, uint32_t* cnt, uint32_t lane) {
+  const uint32_t m = __ballot_sync(0xffffffffu, flag);
+  if (m == 0) return;
+  uint32_t base = 0;
+  if (lane == 0) base = atomicAdd(cnt, (uint32_t)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (flag) list[base + __popc(m & ((1u << lane) - 1u))] = value;
+}
+
+// 256 threads x 8 candidates per CTA iteration; ONE global atomic per 2048 candidates (same-address atomics
+// serialise in L2: one per warp of 32 made this pass atomic-bound)
+constexpr int BAND_CL_ITEMS = 8;
+__global__ void __launch_bounds__(256) band_classify_kernel(const __grid_constant__ BandParams p) {
+  __shared__ uint32_t wcnt[8];
+  __shared__ uint32_t cta_base;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint64_t nb = p.i1 - p.i0;
+  constexpr uint64_t PER_CTA = 256ull * BAND_CL_ITEMS;
+  for (uint64_t t0 = (uint64_t)blockIdx.x * PER_CTA; t0 < nb; t0 += (uint64_t)gridDim.x * PER_CTA) {
+    uint32_t needm = 0, mine = 0;  // per lane: bit k = item k needs scoring
+#pragma unroll
+    for (int k = 0; k < BAND_CL_ITEMS; ++k) {
+      const uint64_t i = t0 + (uint64_t)k * 256 + threadIdx.x;
+      if (i < nb) {
+        const uint64_t c = p.i0 + i;
+        const uint64_t o0 = band_off(p, c);
+        const uint32_t len2 = (uint32_t)(band_off(p, c + 1) - o0);
+        const uint32_t diff = p.len1 > len2 ? p.len1 - len2 : len2 - p.len1;
+        if (diff > p.cut) p.out[c] = NONE_U32;
+        else if (len2 == 0) p.out[c] = finish_int(p.epi, p.len1, p.len1, 0);
+        else { needm |= 1u << k; ++mine; }
+      }
+    }
+    // exclusive prefix of `mine` over the CTA
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= (uint32_t)d) incl += t;
+    }
+    if (lane == 31) wcnt[warp] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t tot = 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) { const uint32_t v = wcnt[w]; wcnt[w] = tot; tot += v; }
+      cta_base = tot ? atomicAdd(p.cnt_out, tot) : 0u;
+    }
+    __syncthreads();
+    uint32_t pos = cta_base + wcnt[warp] + incl - mine;
+#pragma unroll
+    for (int k = 0; k < BAND_CL_ITEMS; ++k)
+      if (needm & (1u << k)) p.list_out[pos++] = (uint32_t)(t0 + (uint64_t)k * 256 + threadIdx.x);
+    __syncthreads();
+  }
+}
+
+// NARROW: cutoff <= 32, the band's <= 33 bits come from two table words instead of three.
+template <bool FINAL, bool PM_SMEM, bool NARROW>
+__global__ void __launch_bounds__(256) band_run_kernel(const __grid_constant__ BandParams p) {
+  extern __shared__ __align__(16) uint32_t band_pm_s[];
+  if constexpr (PM_SMEM) {
+    for (uint32_t i = threadIdx.x; i < 256u * p.stride; i += blockDim.x) band_pm_s[i] = p.pmb[i];
+    __syncthreads();
+  }
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t cnt = *p.cnt_in;
+  const uint32_t rounded = (cnt + 31u) / 32u * 32u;
+  const uint32_t cut = p.cut;
+  const uint32_t stride = p.stride;
+  for (uint32_t li = blockIdx.x * blockDim.x + threadIdx.x; li < rounded; li += gridDim.x * blockDim.x) {
+    const bool have = li < cnt;
+    const uint32_t rel = have ? p.list_in[li] : 0u;  // idle lanes shadow the batch's first candidate with 0 columns
+    const uint64_t c = p.i0 + rel;
+    const uint64_t o0 = band_off(p, c);
+    const uint32_t len2 = have ? (uint32_t)(band_off(p, c + 1) - o0) : 0u;
+    LevBand64 b;
+    b.init(p.len1, have ? len2 : p.len1, cut);
+    const uint32_t cols = have ? (len2 < p.maxcols ? len2 : p.maxcols) : 0u;
+    // each lane walks its own candidate: one 16-byte load per 16 columns
+    ByteReader16 rd(p.chars + (o0 & ~15ull), (uint32_t)(o0 & 15ull));
+    bool dead = false;
+    auto column = [&](uint32_t ch) {
+      const uint32_t sp = (uint32_t)(b.s + 64);
+      const uint32_t idx = ch * stride + (sp >> 5);
+      uint32_t w0, w1, w2 = 0;
+      if constexpr (PM_SMEM) {
+        w0 = band_pm_s[idx]; w1 = band_pm_s[idx + 1];
+        if constexpr (!NARROW) w2 = band_pm_s[idx + 2];
+      } else {
+        w0 = __ldg(p.pmb + idx); w1 = __ldg(p.pmb + idx + 1);
+        if constexpr (!NARROW) w2 = __ldg(p.pmb + idx + 2);
+      }
+      if constexpr (NARROW) b.step(band_window32_low33(w0, w1, sp & 31u));
+      else b.step(band_window32(w0, w1, w2, sp & 31u));
+    };
+    auto eight = [&](uint32_t wa, uint32_t wb, uint32_t j0) {  // columns j0 .. j0+7 (clipped to cols), then the death test
+      if (dead || j0 >= cols) return;
+      if (cols - j0 >= 8) {  // full block: no per-column predicates
+        column(wa & 0xffu); column((wa >> 8) & 0xffu); column((wa >> 16) & 0xffu); column(wa >> 24);
+        column(wb & 0xffu); column((wb >> 8) & 0xffu); column((wb >> 16) & 0xffu); column(wb >> 24);
+      } else {
+        const uint32_t nb = cols - j0;
+#pragma unroll
+        for (int t = 0; t < 7; ++t)
+          if ((uint32_t)t < nb) column(((t < 4 ? wa : wb) >> (8 * (t & 3))) & 0xffu);
+      }
+      dead = b.score() > (int32_t)cut;
+    };
+    const uint32_t steps = __reduce_max_sync(0xffffffffu, cols);
+    for (uint32_t j0 = 0; j0 < steps; j0 += 16) {
+      if (!dead && j0 < cols) {
+        const Bytes16 t = rd.next16();
+        eight(t.w[0], t.w[1], j0);
+        eight(t.w[2], t.w[3], j0 + 8);
+      }
+      if (__ballot_sync(0xffffffffu, !dead && j0 + 16 < cols) == 0) break;
+    }
+    bool more = false;
+    if (have) {
+      if (dead) p.out[c] = NONE_U32;
+      else if (FINAL || len2 <= p.maxcols) p.out[c] = finish_int(p.epi, (uint64_t)b.score(), p.len1, len2);
+      else more = true;
+    }
+    if constexpr (!FINAL) band_append(more, rel, p.list_out, p.cnt_out, lane);
+  }
+}
+
+cudaError_t launch_scan_band(const ScanLaunch& L, uint32_t cut) {
+  constexpr uint64_t kBatch = 1ull << 24;  // candidates per batch: bounds the two index lists to 64 MiB each
+  const uint64_t n = L.corpus.n;
+  const uint64_t cap = n < kBatch ? n : kBatch;
+  uint32_t* scratch = nullptr;  // [listA cap][listB cap][cntA][cntB] per batch parity
+  cudaError_t e = dev_alloc(&scratch, (2 * cap + 16) * sizeof(uint32_t), L.stream);
+  if (e != cudaSuccess) return e;
+  uint32_t* listA = scratch;
+  uint32_t* listB = scratch + cap;
+  uint32_t* cnts = scratch + 2 * cap;
+  BandParams p{};
+  p.chars = L.corpus.chars;
+  p.off32 = L.corpus.off32;
+  p.off64 = L.corpus.off64;
+  p.pmb = L.query.pm_band;
+  p.stride = L.query.band_stride;
+  p.len1 = L.query.len1;
+  p.cut = cut;
+  p.out = reinterpret_cast<uint32_t*>(L.out);
+  p.epi = L.epi;
+  const size_t pm_bytes = (size_t)256 * p.stride * sizeof(uint32_t);
+  const bool pm_smem = pm_bytes <= 96 * 1024;  // queries up to ~5900 elements; longer ones read the table through L1
+  const size_t smem = pm_smem ? pm_bytes : 0;
+  const bool narrow = cut <= 32;
+  void (*run_a)(BandParams);
+  void (*run_b)(BandParams);
+  if (pm_smem) {
+    run_a = narrow ? band_run_kernel<false, true, true> : band_run_kernel<false, true, false>;
+    run_b = narrow ? band_run_kernel<true, true, true> : band_run_kernel<true, true, false>;
+  } else {
+    run_a = narrow ? band_run_kernel<false, false, true> : band_run_kernel<false, false, false>;
+    run_b = narrow ? band_run_kernel<true, false, true> : band_run_kernel<true, false, false>;
+  }
+  if (smem > 48 * 1024) {
+    e = cudaFuncSetAttribute(run_a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(run_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { dev_free(scratch, L.stream); return e; }
+  }
+  // columns of the first pass: random candidates leave the band after about k columns
+  const uint32_t cols_a = (cut + cut / 4 + 8 + 15) / 16 * 16;
+  const uint32_t grid_max = (uint32_t)L.sm_count * 8;
+  for (uint64_t i0 = 0; i0 < n && e == cudaSuccess; i0 += kBatch) {
+    p.i0 = i0;
+    p.i1 = (i0 + kBatch < n) ? i0 + kBatch : n;
+    e = cudaMemsetAsync(cnts, 0, 16 * sizeof(uint32_t), L.stream);
+    if (e != cudaSuccess) break;
+    const uint64_t nb = p.i1 - p.i0;
+    const uint64_t cl_ctas = (nb + 256 * BAND_CL_ITEMS - 1) / (256 * BAND_CL_ITEMS);
+    const uint32_t grid = (uint32_t)((nb + 255) / 256 < grid_max ? (nb + 255) / 256 : grid_max);
+    p.list_out = listA; p.cnt_out = cnts;
+    band_classify_kernel<<<(uint32_t)(cl_ctas < grid_max ? cl_ctas : grid_max), 256, 0, L.stream>>>(p);
+    p.list_in = listA; p.cnt_in = cnts; p.list_out = listB; p.cnt_out = cnts + 1; p.maxcols = cols_a;
+    run_a<<<grid, 256, smem, L.stream>>>(p);
+    p.list_in = listB; p.cnt_in = cnts + 1; p.list_out = nullptr; p.cnt_out = nullptr; p.maxcols = 0xFFFFFFFFu;
+    run_b<<<grid, 256, smem, L.stream>>>(p);
+    g_launches.fetch_add(3);
+    e = cudaGetLastError();
+  }
+  dev_free(scratch, L.stream);
+  return e;
+}
+
 // ------------------------------------------------------------------------------------------------ jaro mw
 template <int MAXQ>
 __global__ void __launch_bounds__(128) jaro_mw_kernel(const __grid_constant__ MwParams p) {

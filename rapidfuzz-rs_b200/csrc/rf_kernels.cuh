@@ -25,6 +25,8 @@ struct QueryView {
   const uint64_t* tab64_top; // [256] PM << (64-len1)   (len1 <= 64)
   const uint64_t* tab64_bot; // [256] PM                (len1 <= 64)   LCS family, Jaro
   const uint64_t* pm_words;  // [256][words] row-major (pattern_match_vector.rs layout), any len1
+  const uint32_t* pm_band;   // [256][band_stride] 32-bit words: 2 zero words, the match vector, >= 2 zero words (banded kernel)
+  uint32_t band_stride;      // (2*(words+2)) | 1
 };
 
 // Length-bucketed, warp-interleaved copy of the corpus (built once at corpus creation, rf_layout.cu):
@@ -69,6 +71,8 @@ cudaError_t launch_scan_w1(const ScanLaunch& L);
 cudaError_t launch_scan_lb(const ScanLaunch& L);
 // Multi-word path (query > 64): sub-warp per candidate, carries propagated with warp shuffles.
 cudaError_t launch_scan_mw(const ScanLaunch& L);
+// Levenshtein distance with a cutoff of at most 63 unit edits, any query length: one 64-bit sliding band per candidate.
+cudaError_t launch_scan_band(const ScanLaunch& L, uint32_t cut);
 // Jaro / Jaro-Winkler with a multi-word query (65..2048).
 cudaError_t launch_jaro_mw(const ScanLaunch& L);
 

@@ -96,6 +96,37 @@ int core_score(int metric, int kind, const uint8_t* q, uint32_t len1, const uint
   return 0;
 }
 
+// banded Levenshtein (LevBand64): distance if <= k else 0xFFFFFFFF; check_every = early-exit stride (0: only at the end)
+uint32_t core_lev_band(const uint8_t* q, uint32_t len1, const uint8_t* s2, uint32_t len2, uint32_t k, uint32_t check_every) {
+  const uint32_t diff = len1 > len2 ? len1 - len2 : len2 - len1;
+  if (diff > k) return 0xFFFFFFFFu;
+  if (len2 == 0) return len1;
+  if (len1 == 0) return len2;
+  const uint32_t words = (len1 + 63) / 64, stride = (2 * (words + 2)) | 1u;  // u32 units, odd (as rf_api.cu builds it)
+  std::vector<uint32_t> pm((size_t)256 * stride, 0);
+  for (uint32_t i = 0; i < len1; ++i) pm[(size_t)q[i] * stride + 2 + i / 32] |= 1u << (i % 32);
+  LevBand64 b;
+  b.init(len1, len2, k);
+  // candidate at a random-ish misalignment inside a 16-byte aligned buffer, read with ByteReader16 like the kernel
+  const uint32_t mis = (len1 * 7u + len2 * 3u + k) & 15u;
+  std::vector<uint32_t> buf((len2 + mis) / 4 + 16, 0xA5A5A5A5u);
+  memcpy(reinterpret_cast<uint8_t*>(buf.data()) + mis, s2, len2);
+  ByteReader16 rd(reinterpret_cast<const uint8_t*>(buf.data()), mis);
+  Bytes16 blk{};
+  for (uint32_t j = 0; j < len2; ++j) {
+    if ((j & 15u) == 0) blk = rd.next16();
+    const uint32_t ch = (blk.w[(j >> 2) & 3u] >> (8 * (j & 3u))) & 0xffu;
+    if (ch != s2[j]) return 0xDEADBEEFu;
+    const uint32_t sp = (uint32_t)(b.s + 64);
+    const uint32_t* row = pm.data() + (size_t)ch * stride + (sp >> 5);
+    // two-word window: valid when the band has at most 33 diagonals (k <= 32); odd k keep the three-word form under test
+    b.step((k > 32 || (k & 1u)) ? band_window32(row[0], row[1], row[2], sp & 31u) : band_window32_low33(row[0], row[1], sp & 31u));
+    if (check_every && (j % check_every) == check_every - 1 && b.score() > (int32_t)k) return 0xFFFFFFFFu;
+  }
+  const int32_t d = b.score();
+  return d <= (int32_t)k ? (uint32_t)d : 0xFFFFFFFFu;
+}
+
 // generic (multi-word) Jaro on the host, query <= 1024
 double core_jaro_generic(const uint8_t* q, uint32_t len1, const uint8_t* s, uint32_t len2, double cutoff) {
   const uint32_t words = (len1 + 63) / 64;

@@ -30,6 +30,8 @@ def core():
                                C.c_double, C.c_uint64, C.c_uint64, C.c_uint64, C.c_double, C.c_int, C.c_uint32,
                                C.POINTER(C.c_uint32), C.POINTER(C.c_double)]
     lib.core_score.restype = C.c_int
+    lib.core_lev_band.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
+    lib.core_lev_band.restype = C.c_uint32
     lib.core_jaro_generic.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_double]
     lib.core_jaro_generic.restype = C.c_double
     return lib
@@ -145,3 +147,20 @@ def test_jaro_generic_multiword_vs_oracle(core):
             if got < c:
                 got = 0.0
             assert got == exp, (bytes(a), bytes(b), c, got, exp)
+
+
+def test_banded_levenshtein_vs_oracle(core):
+    """LevBand64 (sliding 64-bit Ukkonen band, any query length, cutoff <= 63) == exact distance or None."""
+    rng = np.random.default_rng(33)
+    n = 0
+    for a, b in _pairs(rng, 2500, [1, 2, 5, 31, 32, 33, 63, 64, 65, 100, 128, 129, 200, 256, 300], CL + [250, 256, 260, 300], 3):
+        if len(b) == 0:
+            continue
+        exact = orc.tb("levenshtein", a, b)
+        for k in (0, 1, 2, 3, 5, 8, 16, 31, 32, 33, 48, 62, 63):
+            exp = exact if exact <= k else 0xFFFFFFFF
+            for ce in (0, 1, 8):
+                got = core.core_lev_band(a.ctypes.data, len(a), b.ctypes.data, len(b), k, ce)
+                assert got == exp, (bytes(a), bytes(b), k, ce, got, exp)
+                n += 1
+    assert n > 50000

@@ -100,9 +100,17 @@ def test_multi_word_integer_metrics(qlen):
     for m in INT_METRICS:
         check(m, "distance", q, chars, offsets, corpus)
         check(m, "normalized_similarity", q, chars, offsets, corpus)
-    for c in (0, 3, 4, 31, 32, 33, 64, 100):
-        check("levenshtein", "distance", q, chars, offsets, corpus, cutoff=c)
+    for c in (0, 3, 4, 31, 32, 33, 63, 64, 100):
+        check("levenshtein", "distance", q, chars, offsets, corpus, cutoff=c)   # <= 63: banded kernel, else block kernel
         check("indel", "distance", q, chars, offsets, corpus, cutoff=c)
+    _ffi.check(_ffi.lib().rf_set_option(b"banded_levenshtein", 0))             # same cutoffs through the block kernel
+    try:
+        for c in (0, 4, 32, 63):
+            check("levenshtein", "distance", q, chars, offsets, corpus, cutoff=c)
+    finally:
+        _ffi.check(_ffi.lib().rf_set_option(b"banded_levenshtein", 1))
+    for w, c in (((2, 2, 2), 64), ((3, 3, 3), 100), ((2, 2, 2), 127), ((5, 5, 5), 3)):
+        check("levenshtein", "distance", q, chars, offsets, corpus, weights=w, cutoff=c)
     check("lcs_seq", "similarity", q, chars, offsets, corpus, cutoff=qlen // 2)
     check("levenshtein", "distance", q, chars, offsets, corpus, weights=(1, 1, 2))
     check("ratio", "similarity", q, chars, offsets, corpus, cutoff=0.5)
@@ -121,6 +129,22 @@ def test_multi_word_jaro(qlen):
             check(m, kind, q, chars, offsets, corpus)
         check(m, "similarity", q, chars, offsets, corpus, cutoff=0.8)
     corpus.close()
+
+
+def test_config3_shape_banded_vs_oracle():
+    """BASELINE config 3 shape (query len 256, candidates 64-256, cutoff 32) at 3e5 candidates, plus other
+    cutoffs / query lengths: the three-pass banded path (classify, first columns, near-matches) vs the oracle."""
+    for seed, qlen, lo, hi, kmax, n, cut in ((3, 256, 64, 256, 48, 300_000, 32), (13, 1000, 900, 1100, 80, 20_000, 63),
+                                            (23, 65, 1, 130, 10, 50_000, 7), (33, 300, 280, 320, 5, 40_000, 0),
+                                            (43, 3000, 2990, 3010, 20, 3_000, 20)):
+        q = rf.synth_query(seed, qlen)
+        chars, offsets = rf.synth_corpus(seed, q, n, lo, hi, kmax)
+        corpus = rf.Corpus(chars, offsets)
+        got = gpu_batch("levenshtein", "distance", q, corpus, cutoff=cut)
+        exp = orc.batch("levenshtein", "distance", q, chars, offsets, nthreads=0, cutoff=cut)
+        assert_same(got, exp, ("banded", seed, qlen, cut))
+        assert (exp != 0xFFFFFFFF).sum() > 0
+        corpus.close()
 
 
 def test_query_64_vs_long_candidates_and_tile_overflow():

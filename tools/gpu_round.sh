@@ -1,13 +1,5 @@
 #!/bin/bash
-# Dev helper run under gpurun: microbench, GPU parity tests, bench A/B.  Output -> gpurun_out/
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.max.sm,pcie.link.gen.max,pcie.link.width.max --format=csv > gpurun_out/gpu.txt 2>&1
-nproc >> gpurun_out/gpu.txt
-./tools/ubench/pipes > gpurun_out/pipes.txt 2>&1
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
-tail -3 gpurun_out/pytest_gpu.log
-timeout 600 python bench.py > gpurun_out/bench_dp4a.json 2> gpurun_out/bench_dp4a.err
-RF_LIB_PATH=$PWD/rapidfuzz-rs_b200/lib/librfgpu_nodp4a.so timeout 300 python bench.py --steps 100 --no-cpu-baseline --e2e-steps 2 > gpurun_out/bench_nodp4a.json 2> gpurun_out/bench_nodp4a.err
-cat gpurun_out/pipes.txt
-cut -c1-1500 gpurun_out/bench_dp4a.json
-cut -c1-400 gpurun_out/bench_nodp4a.json
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:band_run -s 2 -c 2 -f -o gpurun_out/prof_band python tools/bench_configs.py c3 > gpurun_out/ncu_band.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:scan_lb -s 3 -c 1 -f -o gpurun_out/prof_lb python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_lb.log 2>&1
+ls -la gpurun_out/*.ncu-rep

@@ -202,7 +202,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     L = _ffi.lib()
-    if os.environ.get("RF_W1_PATH"):  # dev knob: 1 = CSR/TMA-tile kernel instead of the interleaved-layout kernel
+    if os.environ.get("RF_W1_PATH"):  # dev knob: 1 = CSR/TMA-tile kernel, 2 = interleaved layout through per-warp TMA rings
         _ffi.check(L.rf_set_option(b"single_word_path", int(os.environ["RF_W1_PATH"])))
     n = args.n
     gen_threads = max(1, host_threads() // world)

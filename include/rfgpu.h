@@ -161,8 +161,12 @@ rf_status rf_synth_corpus_u8(uint64_t seed, const uint8_t* query, uint32_t query
 /* tuning knobs (process-wide):
  *   "build_interleaved_layout" (default 1): corpora created afterwards also keep the length-bucketed,
  *        warp-interleaved copy that the fastest single-word kernel reads (about +1.2x corpus memory);
- *   "single_word_path" (default 0): 0 = interleaved-layout kernel when the corpus has it,
- *        1 = CSR kernel (TMA-staged tiles, bucketed by length in shared memory);
+ *   "single_word_path" (default 0): which kernel scores queries of at most 64 elements:
+ *        0 = interleaved layout, per-lane streaming loads with a two-row register pipeline (fastest measured);
+ *        1 = CSR kernel (TMA-staged tiles, bucketed by length in shared memory) -- also what corpora without the
+ *            interleaved copy and the streaming entry points use;
+ *        2 = interleaved layout, rows streamed into per-warp shared-memory rings by TMA bulk copies (Jaro /
+ *            Jaro-Winkler, which need random access to the candidate, stay on 0);
  *   "banded_levenshtein" (default 1): multi-word Levenshtein distance with score_cutoff <= 63 edits uses the
  *        one-thread-per-candidate 64-bit Ukkonen-band kernel; 0 = always the multi-word block kernel;
  *   "stream_chunk_mb" (default 64), "stream_chunk_kcand" (default 2048): chunk size of rf_batch_stream_* in

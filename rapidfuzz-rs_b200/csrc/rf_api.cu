@@ -132,7 +132,7 @@ uint64_t rf_kernel_launch_count(void) { return kernel_launch_count(); }
 rf_status rf_set_option(const char* name, int value) {
   if (!name) return fail(RF_ERR_INVALID_ARG, "name is NULL");
   if (!strcmp(name, "build_interleaved_layout")) { g_build_lb.store(value ? 1 : 0); return RF_OK; }
-  if (!strcmp(name, "single_word_path")) { g_w1_path.store(value ? 1 : 0); return RF_OK; }
+  if (!strcmp(name, "single_word_path")) { g_w1_path.store(value); return RF_OK; }
   if (!strcmp(name, "banded_levenshtein")) { g_band.store(value ? 1 : 0); return RF_OK; }
   if (!strcmp(name, "stream_chunk_mb")) { if (value < 1) return fail(RF_ERR_INVALID_ARG, "stream_chunk_mb < 1"); g_stream_mb.store(value); return RF_OK; }
   if (!strcmp(name, "stream_chunk_kcand")) { if (value < 1) return fail(RF_ERR_INVALID_ARG, "stream_chunk_kcand < 1"); g_stream_kcand.store(value); return RF_OK; }
@@ -407,7 +407,7 @@ static rf_status score_view(const rf_batch* b, const CorpusView& cv, const LbAll
   DeviceGuard g(device);
   if (!g.ok) return fail(RF_ERR_CUDA, "cudaSetDevice failed");
   L.corpus = cv;
-  const bool use_lb = lb && lb->gdata && g_w1_path.load() == 0;
+  const bool use_lb = lb && lb->gdata && g_w1_path.load() != 1;
   if (use_lb) {
     L.lb = LbView{lb->perm, lb->lens, lb->goff, lb->gdata, lb->ngroups};
     L.lb_counter = counter_slot(device);
@@ -420,7 +420,10 @@ static rf_status score_view(const rf_batch* b, const CorpusView& cv, const LbAll
   L.sm_count = sm_count_of(device);
   const Family fam = family_of(L.epi.metric, L.epi.wclass);
   cudaError_t e;
-  if (b->len1 <= 64) e = use_lb ? launch_scan_lb(L) : launch_scan_w1(L);
+  if (b->len1 <= 64) {
+    const int path = g_w1_path.load();
+    e = !use_lb ? launch_scan_w1(L) : path == 2 ? launch_scan_lbr(L) : launch_scan_lb(L);
+  }
   else if (fam == F_JARO) e = launch_jaro_mw(L);
   else if (g_band.load() && L.epi.metric == M_LEVENSHTEIN && L.epi.wclass == WC_UNIFORM && L.epi.kind == K_DISTANCE &&
            L.epi.has_cutoff && L.epi.cutoff_u / L.epi.w_ins <= 63)

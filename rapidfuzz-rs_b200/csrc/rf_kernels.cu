@@ -14,6 +14,7 @@
 //  jaro_mw_kernel  Jaro / Jaro-Winkler with a multi-word query, thread per candidate.
 //  cdist_*         many queries x corpus tile, per-query top-k.
 #include <atomic>
+#include <type_traits>
 #include <cstdio>
 #include <cstdlib>
 #include "rf_kernels.cuh"
@@ -68,6 +69,32 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
                    smem_u32(dst_smem)),
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+// the same issued by ONE elected lane of a converged warp: arms the mbarrier with the byte count and starts the copy
+// (operands are warp-uniform; elect.sync lets ptxas feed the uniform datapath without a per-value loop)
+__device__ __forceinline__ void tma_bulk_g2s_elect(uint32_t dst_saddr, const void* src_gmem, uint32_t bytes, uint32_t bar_saddr) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "elect.sync _|P1, 0xffffffff;\n"
+      "@P1 mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %2;\n"
+      "@P1 cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+      "}\n" ::"r"(dst_saddr),
+      "l"(src_gmem), "r"(bytes), "r"(bar_saddr)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait_saddr(uint32_t bar_saddr, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar_saddr),
+      "r"(parity)
+      : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 template <int NT>
@@ -129,6 +156,9 @@ __device__ __forceinline__ uint2 ld_row8(const uint2* p) {
 // explicit L2 prefetch a few rows ahead (it needs no destination register, so nothing is gained by moving
 // it) takes the DRAM latency off the critical path, the late load then only pays an L2 hit.
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// L2 prefetch of the streamed rows: per-lane prefetch.global.L2 of the two rows kPfDist ahead.  Measured on B200
+// (config 2): no prefetch 2.15 ms, distance 3 / 6 / 12 / 24 rows all 2.04 ms, one bulk L2 prefetch per warp 2.14 ms.
+constexpr int kPfDist = 6;
 template <bool STREAM>
 struct LaneReaderT {
   static constexpr bool kRow8 = true;
@@ -214,8 +244,8 @@ __device__ __forceinline__ uint32_t lev_w1_u32_fast(uint32_t pm_lane_saddr, Rd r
     uint32_t i = 0;
     for (; i + 2 <= nfull; i += 2) {
       if constexpr (Rd::kStream) {
-        prefetch_l2(p + 32 * 6);
-        prefetch_l2(p + 32 * 7);
+        prefetch_l2(p + 32 * kPfDist);
+        prefetch_l2(p + 32 * (kPfDist + 1));
       }
       const uint2 C = ld_row8<Rd::kStream>(p);
       const uint2 D = ld_row8<Rd::kStream>(p + 32);
@@ -514,7 +544,10 @@ struct LbParams {
   Epi epi;
 };
 
-template <int FAM, class W, int NT>
+// RAWDIST: the launch asks for the plain unit-cost distance of Levenshtein / OSA as u32 without a cutoff
+// (BatchComparator::distance, the headline call): the epilogue is the raw kernel result, so the per-group
+// score algebra (a dozen uniform loads and branches on Epi) is compiled out.
+template <int FAM, class W, int NT, bool RAWDIST>
 __global__ void __launch_bounds__(NT) scan_lb_kernel(const __grid_constant__ LbParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   W* pm = reinterpret_cast<W*>(smem_raw);
@@ -553,23 +586,38 @@ __global__ void __launch_bounds__(NT) scan_lb_kernel(const __grid_constant__ LbP
         first_n = ld_row8<true>(gdata + r * 32 + lane);
         second_n = ld_row8<true>(gdata + (r + 1) * 32 + lane);
       }
-      uint32_t ru = 0;
-      double rf = 0.0;
-      score_one<FAM, W>(pm_lane, src, len2, p.len1, p.epi, p.out_f64, p.two, ru, rf);
-      if (idx != 0xFFFFFFFFu) {
-        if (p.out_f64) reinterpret_cast<double*>(p.out)[idx] = rf;
-        else reinterpret_cast<uint32_t*>(p.out)[idx] = ru;
+      if constexpr (RAWDIST) {  // len1 >= 1 (checked by the launcher)
+        uint32_t raw;
+        if constexpr (FAM == F_LEV && sizeof(W) == 4) raw = lev_w1_u32_fast(smem_u32(pm_lane), src.reader(), len2, p.len1, p.two);
+        else {
+          auto tab = [&](uint32_t ch) -> W { return pm_lane[ch * 32u]; };
+          if constexpr (FAM == F_LEV) raw = lev_w1<W>(tab, src.reader(), len2, p.len1);
+          else raw = osa_w1<W>(tab, src.reader(), len2, p.len1);
+        }
+        if (idx != 0xFFFFFFFFu) reinterpret_cast<uint32_t*>(p.out)[idx] = raw;
+      } else {
+        uint32_t ru = 0;
+        double rf = 0.0;
+        score_one<FAM, W>(pm_lane, src, len2, p.len1, p.epi, p.out_f64, p.two, ru, rf);
+        if (idx != 0xFFFFFFFFu) {
+          if (p.out_f64) reinterpret_cast<double*>(p.out)[idx] = rf;
+          else reinterpret_cast<uint32_t*>(p.out)[idx] = ru;
+        }
       }
     }
     chunk = __shfl_sync(0xffffffffu, next_chunk, 0);
   }
 }
 
-template <int FAM, class W, int NT>
+template <int FAM, class W, int NT, bool RAWDIST = false>
 static cudaError_t launch_lb_inst(const ScanLaunch& L, const void* tab) {
-  auto kern = scan_lb_kernel<FAM, W, NT>;
+  auto kern = scan_lb_kernel<FAM, W, NT, RAWDIST>;
   const size_t smem = sizeof(W) * 256 * 32;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  // the rows are streamed (evict-first) and never re-read: give the whole unified array to shared memory so
+  // that one more CTA (and its table copy) fits per SM
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
   int ctas_per_sm = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, NT, smem);
@@ -600,11 +648,19 @@ static cudaError_t launch_lb_inst(const ScanLaunch& L, const void* tab) {
 cudaError_t launch_scan_lb(const ScanLaunch& L) {
   const Family fam = family_of(L.epi.metric, L.epi.wclass);
   const bool w32 = L.query.len1 <= 32;
+  const bool rawdist = (fam == F_LEV || fam == F_OSA) && L.epi.unit32 && L.epi.kind == K_DISTANCE && !L.epi.has_cutoff &&
+                       !L.out_is_f64 && L.query.len1 >= 1;
   switch (fam) {
     case F_LEV:
+      if (rawdist)
+        return w32 ? launch_lb_inst<F_LEV, uint32_t, 256, true>(L, L.query.tab32_top)
+                   : launch_lb_inst<F_LEV, uint64_t, 512, true>(L, L.query.tab64_top);
       return w32 ? launch_lb_inst<F_LEV, uint32_t, 256>(L, L.query.tab32_top)
                  : launch_lb_inst<F_LEV, uint64_t, 512>(L, L.query.tab64_top);
     case F_OSA:
+      if (rawdist)
+        return w32 ? launch_lb_inst<F_OSA, uint32_t, 256, true>(L, L.query.tab32_top)
+                   : launch_lb_inst<F_OSA, uint64_t, 512, true>(L, L.query.tab64_top);
       return w32 ? launch_lb_inst<F_OSA, uint32_t, 256>(L, L.query.tab32_top)
                  : launch_lb_inst<F_OSA, uint64_t, 512>(L, L.query.tab64_top);
     case F_LCS:
@@ -612,6 +668,275 @@ cudaError_t launch_scan_lb(const ScanLaunch& L) {
                  : launch_lb_inst<F_LCS, uint64_t, 512>(L, L.query.tab64_bot);
     default:
       return launch_lb_inst<F_JARO, uint64_t, 512>(L, L.query.tab64_bot);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ lb ring (TMA)
+// Same work as scan_lb_kernel (warp per group of 32 equal-length candidates of the interleaved layout), but the
+// rows reach the warp through a private shared-memory ring filled by TMA bulk copies instead of per-lane
+// global loads: the groups of a chunk are one contiguous row range, so lane 0 streams it in 1 KB blocks
+// (4 rows x 32 lanes x 8 bytes, cp.async.bulk + mbarrier, SASS UBLKCP), two blocks in flight per warp.  The
+// look-ahead (>= 32 characters per lane) costs no registers and no per-row address arithmetic, the consumer
+// reads a row with one conflict-free LDS.64.  Sequential readers only (Levenshtein, OSA, LCS family);
+// Jaro needs random access to the candidate and stays on scan_lb_kernel.
+// per-candidate state machines: step<K>() consumes byte K of a packed word of 4 text characters
+template <class W>
+struct LevSt {
+  W VP, VN;
+  __device__ __forceinline__ void init(uint32_t len1) { VP = (W)(~(W)0) << ((int)sizeof(W) * 8 - (int)len1); VN = 0; }
+  template <int K>
+  __device__ __forceinline__ void step(uint32_t w, const W* pm_lane, uint32_t, uint32_t) {
+    const W X = pm_lane[((w >> (8 * K)) & 0xffu) * 32u];
+    const W D0 = ((((X & VP) + VP) ^ VP) | X) | VN;
+    W HP = VN | ~(D0 | VP);
+    W HN = D0 & VP;
+    HP = (HP << 1) | (W)1;
+    HN = HN << 1;
+    VP = HN | ~(D0 | HP);
+    VN = HP & D0;
+  }
+  __device__ __forceinline__ uint32_t raw(uint32_t len2) const { return len2 + (uint32_t)popc(VP) - (uint32_t)popc(VN); }
+};
+// 32-bit Levenshtein with the address / shift arithmetic steered onto the FMA pipe (see lev_w1_u32_fast)
+struct LevSt32Fast {
+  uint32_t VP, VN;
+  __device__ __forceinline__ void init(uint32_t len1) { VP = 0xFFFFFFFFu << (32u - len1); VN = 0; }
+  template <int K>
+  __device__ __forceinline__ void step(uint32_t w, const uint32_t*, uint32_t pm_lane_saddr, uint32_t two) {
+    uint32_t X;
+    const uint32_t addr = __dp4a(w, 0x80u << (8 * K), pm_lane_saddr);
+    asm("ld.shared.u32 %0, [%1];" : "=r"(X) : "r"(addr));
+    const uint32_t D0 = ((((X & VP) + VP) ^ VP) | X) | VN;
+    uint32_t HP = VN | ~(D0 | VP);
+    uint32_t HN = D0 & VP;
+    HP = HP * two + (two >> 1);
+    HN = HN * two;
+    VP = HN | ~(D0 | HP);
+    VN = HP & D0;
+  }
+  __device__ __forceinline__ uint32_t raw(uint32_t len2) const { return len2 + (uint32_t)__popc(VP) - (uint32_t)__popc(VN); }
+};
+template <class W>
+struct OsaSt {
+  W VP, VN, D0, PMold;
+  __device__ __forceinline__ void init(uint32_t len1) { VP = (W)(~(W)0) << ((int)sizeof(W) * 8 - (int)len1); VN = 0; D0 = 0; PMold = 0; }
+  template <int K>
+  __device__ __forceinline__ void step(uint32_t w, const W* pm_lane, uint32_t, uint32_t) {
+    const W X = pm_lane[((w >> (8 * K)) & 0xffu) * 32u];
+    const W TR = (((~D0) & X) << 1) & PMold;
+    D0 = (((((X & VP) + VP) ^ VP) | X) | VN) | TR;
+    W HP = VN | ~(D0 | VP);
+    W HN = D0 & VP;
+    HP = (HP << 1) | (W)1;
+    HN = HN << 1;
+    VP = HN | ~(D0 | HP);
+    VN = HP & D0;
+    PMold = X;
+  }
+  __device__ __forceinline__ uint32_t raw(uint32_t len2) const { return len2 + (uint32_t)popc(VP) - (uint32_t)popc(VN); }
+};
+template <class W>
+struct LcsSt {
+  W S;
+  __device__ __forceinline__ void init(uint32_t) { S = ~(W)0; }
+  template <int K>
+  __device__ __forceinline__ void step(uint32_t w, const W* pm_lane, uint32_t, uint32_t) {
+    const W U = S & pm_lane[((w >> (8 * K)) & 0xffu) * 32u];
+    S = (S + U) | (S & ~U);
+  }
+  __device__ __forceinline__ uint32_t raw(uint32_t) const { return (uint32_t)popc((W)~S); }
+};
+
+// BLK = rows per ring block (one TMA copy of BLK*256 bytes); the ring holds two blocks.
+template <int FAM, class W, int NT, bool RAWDIST, int BLK>
+__global__ void __launch_bounds__(NT) scan_lbr_kernel(const __grid_constant__ LbParams p) {
+  constexpr int NW = NT / 32;
+  constexpr uint32_t RING = 2 * BLK, BLK_BYTES = BLK * 256;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  W* pm = reinterpret_cast<W*>(smem_raw);
+  unsigned char* rings = smem_raw + sizeof(W) * 8192;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rings + NW * RING * 256);
+  {
+    const W* __restrict__ t = reinterpret_cast<const W*>(p.tab);
+    for (uint32_t i = threadIdx.x; i < 256u * 32u; i += NT) pm[i] = t[i >> 5];
+  }
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    mbar_init(bars + warp * 2, 1);
+    mbar_init(bars + warp * 2 + 1, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const uint32_t ring_s = smem_u32(rings + warp * (RING * 256));
+  const uint32_t bar_s = smem_u32(bars + warp * 2);
+  const uint32_t ring_lane = ring_s + lane * 8u;
+  const W* __restrict__ pm_lane = pm + lane;
+  const uint32_t pm_lane_saddr = smem_u32(pm_lane);
+  const uint64_t total_warps = (uint64_t)gridDim.x * NW;
+  const uint64_t ngroups = p.lb.ngroups;
+  const uint64_t nchunks = (ngroups + p.chunk - 1) / p.chunk;
+  const unsigned char* __restrict__ gdata = reinterpret_cast<const unsigned char*>(p.lb.gdata);
+  uint32_t Q = 0;  // ring blocks consumed so far by this warp: block q uses slot q&1 with mbarrier parity (q>>1)&1
+  uint64_t chunk = (uint64_t)blockIdx.x * NW + warp;
+  while (chunk < nchunks) {
+    unsigned long long next_chunk = 0;
+    if (lane == 0) next_chunk = total_warps + atomicAdd(p.counter, 1ull);  // latency hidden behind this chunk
+    const uint64_t g0 = chunk * p.chunk;
+    const uint64_t g1 = (g0 + p.chunk < ngroups) ? g0 + p.chunk : ngroups;
+    // warp-uniform by construction; the shuffles say so to the compiler's uniformity analysis
+    const uint64_t ra = __shfl_sync(0xffffffffu, __ldg(p.lb.goff + g0), 0);
+    const uint64_t rb = __shfl_sync(0xffffffffu, __ldg(p.lb.goff + g1), 0);
+    const uint32_t nblk = (uint32_t)((rb - ra + BLK - 1) / BLK);
+    const unsigned char* gsrc = gdata + ra * 256;
+    auto fill = [&](uint32_t b) {  // block b of this chunk -> its ring slot (whole warp calls, one lane issues)
+      const uint32_t slot = (Q + b) & 1u;
+      tma_bulk_g2s_elect(ring_s + slot * BLK_BYTES, gsrc + (size_t)b * BLK_BYTES, BLK_BYTES, bar_s + slot * 8u);
+    };
+    if (nblk > 0) fill(0);
+    if (nblk > 1) fill(1);
+    uint32_t len_n = __ldg(p.lb.lens + g0 * 32 + lane);
+    uint32_t idx_n = __ldg(p.lb.perm + g0 * 32 + lane);
+    uint32_t k = 0;  // row cursor inside the chunk
+    // row kk of the chunk as (x,y) = 8 text bytes of this lane.  Entering a new block (kk % BLK == 0): every lane is
+    // done with the previous block (its LDS were issued long before the copy is even requested), so that slot is
+    // refilled with the block after this one; then wait for ours.
+    auto row = [&](uint32_t kk) -> uint2 {
+      if ((kk & (BLK - 1)) == 0) {
+        const uint32_t b = kk / BLK;
+        __syncwarp();
+        if (b >= 1 && b + 1 < nblk) fill(b + 1);
+        mbar_wait_saddr(bar_s + ((Q + b) & 1u) * 8u, ((Q + b) >> 1) & 1u);
+      }
+      const uint32_t a = ring_lane + (((kk + BLK * (Q & 1u)) & (RING - 1)) << 8);
+      uint2 v;
+      asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+      return v;
+    };
+    for (uint64_t g = g0; g < g1; ++g) {
+      const uint32_t len2 = len_n, idx = idx_n;
+      const uint32_t lmax = __reduce_max_sync(0xffffffffu, len2);
+      const uint32_t lmin = __reduce_min_sync(0xffffffffu, len2);
+      if (g + 1 < g1) {
+        len_n = __ldg(p.lb.lens + (g + 1) * 32 + lane);
+        idx_n = __ldg(p.lb.perm + (g + 1) * 32 + lane);
+      }
+      using St = typename std::conditional<FAM == F_LEV && sizeof(W) == 4, LevSt32Fast,
+                 typename std::conditional<FAM == F_LEV, LevSt<W>,
+                 typename std::conditional<FAM == F_OSA, OsaSt<W>, LcsSt<W>>::type>::type>::type;
+      St st;
+      st.init(p.len1);
+      const uint32_t nrows = (lmax + 7u) >> 3, nfull = lmin >> 3;
+#define RF_ST(K, WORD) st.template step<K>(WORD, pm_lane, pm_lane_saddr, p.two);
+#define RF_ROW8(V) RF_ST(0, (V).x) RF_ST(1, (V).x) RF_ST(2, (V).x) RF_ST(3, (V).x) RF_ST(0, (V).y) RF_ST(1, (V).y) RF_ST(2, (V).y) RF_ST(3, (V).y)
+      uint32_t i = 0;
+      for (; i < nfull; ++i) {  // rows every lane needs in full: no predicates
+        const uint2 v = row(k + i);
+        RF_ROW8(v)
+      }
+      if (lmin == lmax) {  // (nearly every group) all 32 candidates have the same length: warp-uniform remainder
+        const uint32_t rem = lmax & 7u;
+        if (rem) {
+          const uint2 v = row(k + i);
+          RF_ST(0, v.x)
+          if (rem > 1) RF_ST(1, v.x)
+          if (rem > 2) RF_ST(2, v.x)
+          if (rem > 3) RF_ST(3, v.x)
+          if (rem > 4) RF_ST(0, v.y)
+          if (rem > 5) RF_ST(1, v.y)
+          if (rem > 6) RF_ST(2, v.y)
+        }
+      } else {
+        for (; i < nrows; ++i) {  // ragged group (a length boundary of the sorted block, or padding lanes)
+          const uint2 v = row(k + i);
+          const uint32_t j0 = i * 8u;
+#define RF_TSTEP(T, WORD, K) if (j0 + (T) < len2) RF_ST(K, WORD)
+          RF_TSTEP(0, v.x, 0) RF_TSTEP(1, v.x, 1) RF_TSTEP(2, v.x, 2) RF_TSTEP(3, v.x, 3)
+          RF_TSTEP(4, v.y, 0) RF_TSTEP(5, v.y, 1) RF_TSTEP(6, v.y, 2) RF_TSTEP(7, v.y, 3)
+#undef RF_TSTEP
+        }
+      }
+#undef RF_ROW8
+#undef RF_ST
+      k += nrows;
+      const uint32_t raw = (p.len1 == 0) ? ((FAM == F_LCS) ? 0u : len2) : st.raw(len2);
+      if (idx != 0xFFFFFFFFu) {
+        if constexpr (RAWDIST) {
+          reinterpret_cast<uint32_t*>(p.out)[idx] = raw;
+        } else {
+          if (p.out_f64) reinterpret_cast<double*>(p.out)[idx] = finish_norm(p.epi, raw, p.len1, len2);
+          else reinterpret_cast<uint32_t*>(p.out)[idx] = finish_int(p.epi, raw, p.len1, len2);
+        }
+      }
+    }
+    Q += nblk;
+    chunk = __shfl_sync(0xffffffffu, next_chunk, 0);
+  }
+}
+
+template <int FAM, class W, int NT, bool RAWDIST, int BLK>
+static cudaError_t launch_lbr_cfg(const ScanLaunch& L, const void* tab) {
+  auto kern = scan_lbr_kernel<FAM, W, NT, RAWDIST, BLK>;
+  const size_t smem = sizeof(W) * 256 * 32 + (size_t)(NT / 32) * (2 * BLK * 256 + 16);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
+  int ctas_per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, NT, smem);
+  if (e != cudaSuccess) return e;
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  LbParams p{};
+  p.lb = L.lb;
+  p.tab = tab;
+  p.len1 = L.query.len1;
+  p.out = L.out;
+  p.out_f64 = L.out_is_f64;
+  p.two = 2;
+  p.chunk = 16;
+  p.counter = L.lb_counter;
+  p.epi = L.epi;
+  e = cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), L.stream);
+  if (e != cudaSuccess) return e;
+  uint64_t grid = (uint64_t)L.sm_count * ctas_per_sm;
+  const uint64_t nchunks = (L.lb.ngroups + p.chunk - 1) / p.chunk;
+  const uint64_t need = (nchunks + NT / 32 - 1) / (NT / 32);
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  kern<<<(uint32_t)grid, NT, smem, L.stream>>>(p);
+  g_launches.fetch_add(1);
+  return cudaGetLastError();
+}
+
+template <int FAM, class W, int NT, bool RAWDIST = false>
+static cudaError_t launch_lbr_inst(const ScanLaunch& L, const void* tab) {
+  static const int blk = getenv("RF_RING_BLK") ? atoi(getenv("RF_RING_BLK")) : 4;  // tuning knob: rows per TMA block
+  if (blk == 8) return launch_lbr_cfg<FAM, W, NT, RAWDIST, 8>(L, tab);
+  return launch_lbr_cfg<FAM, W, NT, RAWDIST, 4>(L, tab);
+}
+
+cudaError_t launch_scan_lbr(const ScanLaunch& L) {
+  const Family fam = family_of(L.epi.metric, L.epi.wclass);
+  const bool w32 = L.query.len1 <= 32;
+  const bool rawdist = (fam == F_LEV || fam == F_OSA) && L.epi.unit32 && L.epi.kind == K_DISTANCE && !L.epi.has_cutoff &&
+                       !L.out_is_f64 && L.query.len1 >= 1;
+  switch (fam) {
+    case F_LEV:
+      if (rawdist)
+        return w32 ? launch_lbr_inst<F_LEV, uint32_t, 512, true>(L, L.query.tab32_top)
+                   : launch_lbr_inst<F_LEV, uint64_t, 512, true>(L, L.query.tab64_top);
+      return w32 ? launch_lbr_inst<F_LEV, uint32_t, 512>(L, L.query.tab32_top)
+                 : launch_lbr_inst<F_LEV, uint64_t, 512>(L, L.query.tab64_top);
+    case F_OSA:
+      if (rawdist)
+        return w32 ? launch_lbr_inst<F_OSA, uint32_t, 512, true>(L, L.query.tab32_top)
+                   : launch_lbr_inst<F_OSA, uint64_t, 512, true>(L, L.query.tab64_top);
+      return w32 ? launch_lbr_inst<F_OSA, uint32_t, 512>(L, L.query.tab32_top)
+                 : launch_lbr_inst<F_OSA, uint64_t, 512>(L, L.query.tab64_top);
+    case F_LCS:
+      return w32 ? launch_lbr_inst<F_LCS, uint32_t, 512>(L, L.query.tab32_bot)
+                 : launch_lbr_inst<F_LCS, uint64_t, 512>(L, L.query.tab64_bot);
+    default:
+      return launch_scan_lb(L);  // Jaro: random access to the candidate
   }
 }
 

@@ -69,6 +69,8 @@ struct ScanLaunch {
 cudaError_t launch_scan_w1(const ScanLaunch& L);
 // Single-word path (query <= 64), pre-bucketed interleaved layout: warp per group of 32 equal-length candidates.
 cudaError_t launch_scan_lb(const ScanLaunch& L);
+// Same layout, rows streamed by per-warp TMA bulk copies into a shared-memory ring (sequential metrics; Jaro falls back).
+cudaError_t launch_scan_lbr(const ScanLaunch& L);
 // Multi-word path (query > 64): sub-warp per candidate, carries propagated with warp shuffles.
 cudaError_t launch_scan_mw(const ScanLaunch& L);
 // Levenshtein distance with a cutoff of at most 63 unit edits, any query length: one 64-bit sliding band per candidate.

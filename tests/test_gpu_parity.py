@@ -17,11 +17,15 @@ from gpu_util import make_corpus, check, gpu_batch, assert_same
 
 
 
-@pytest.fixture(autouse=True, params=["interleaved", "csr_tiles"])
+PATHS = {"interleaved_ldg": 0, "csr_tiles": 1, "interleaved_tma_ring": 2}
+
+
+@pytest.fixture(autouse=True, params=list(PATHS))
 def single_word_path(request):
-    """Every test runs against both single-word kernels: the length-bucketed interleaved layout
-    (scan_lb_kernel) and the CSR / TMA-tile path (scan_w1_kernel)."""
-    _ffi.check(_ffi.lib().rf_set_option(b"single_word_path", 0 if request.param == "interleaved" else 1))
+    """Every test runs against all three single-word kernels: the length-bucketed interleaved layout read with
+    per-lane streaming loads (scan_lb_kernel, default) or through per-warp TMA rings (scan_lbr_kernel), and the
+    CSR / TMA-tile path (scan_w1_kernel)."""
+    _ffi.check(_ffi.lib().rf_set_option(b"single_word_path", PATHS[request.param]))
     yield request.param
     _ffi.check(_ffi.lib().rf_set_option(b"single_word_path", 0))
 

@@ -1,5 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:band_run -s 2 -c 2 -f -o gpurun_out/prof_band python tools/bench_configs.py c3 > gpurun_out/ncu_band.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:scan_lb -s 3 -c 1 -f -o gpurun_out/prof_lb python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_lb.log 2>&1
-ls -la gpurun_out/*.ncu-rep
+for path in 0 2 0 2; do
+  RF_W1_PATH=$path timeout 300 python bench.py --steps 200 --no-cpu-baseline --e2e-steps 1 > gpurun_out/b$path.json 2> gpurun_out/b.err
+  echo "path $path: $(python -c "import json;d=json.load(open('gpurun_out/b$path.json'));print(d['ms_per_step'], d['config']['results_match_oracle_sample'])")"; tail -2 gpurun_out/b.err
+done

@@ -167,6 +167,8 @@ rf_status rf_synth_corpus_u8(uint64_t seed, const uint8_t* query, uint32_t query
  *            interleaved copy and the streaming entry points use;
  *        2 = interleaved layout, rows streamed into per-warp shared-memory rings by TMA bulk copies (Jaro /
  *            Jaro-Winkler, which need random access to the candidate, stay on 0);
+ *   "jaro32" (default 1): Jaro / Jaro-Winkler queries of at most 32 elements use the row-wise 32-bit kernel
+ *        (interleaved layout only); 0 = the generic per-lane routine;
  *   "banded_levenshtein" (default 1): multi-word Levenshtein distance with score_cutoff <= 63 edits uses the
  *        one-thread-per-candidate 64-bit Ukkonen-band kernel; 0 = always the multi-word block kernel;
  *   "stream_chunk_mb" (default 64), "stream_chunk_kcand" (default 2048): chunk size of rf_batch_stream_* in

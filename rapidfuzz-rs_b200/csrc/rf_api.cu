@@ -133,6 +133,7 @@ rf_status rf_set_option(const char* name, int value) {
   if (!name) return fail(RF_ERR_INVALID_ARG, "name is NULL");
   if (!strcmp(name, "build_interleaved_layout")) { g_build_lb.store(value ? 1 : 0); return RF_OK; }
   if (!strcmp(name, "single_word_path")) { g_w1_path.store(value); return RF_OK; }
+  if (!strcmp(name, "jaro32")) { set_jaro32(value ? 1 : 0); return RF_OK; }
   if (!strcmp(name, "banded_levenshtein")) { g_band.store(value ? 1 : 0); return RF_OK; }
   if (!strcmp(name, "stream_chunk_mb")) { if (value < 1) return fail(RF_ERR_INVALID_ARG, "stream_chunk_mb < 1"); g_stream_mb.store(value); return RF_OK; }
   if (!strcmp(name, "stream_chunk_kcand")) { if (value < 1) return fail(RF_ERR_INVALID_ARG, "stream_chunk_kcand < 1"); g_stream_kcand.store(value); return RF_OK; }
@@ -309,7 +310,9 @@ rf_status rf_batch_create_u8(rf_metric metric, const uint8_t* query, uint32_t qu
   const size_t szw = (size_t)256 * words * sizeof(uint64_t);
   const uint32_t bstride = (2 * (words + 2)) | 1u;  // u32 units, odd
   const size_t szp = (size_t)256 * bstride * sizeof(uint32_t);
-  std::vector<uint8_t> blob(2 * sz32 + 2 * sz64 + szw + szp, 0);
+  const size_t szp8 = (szp + 7) & ~(size_t)7;
+  const size_t szq = (size_t)kQuotDim * kQuotDim * sizeof(double);  // exact a/b for a,b <= 64 (Jaro epilogue)
+  std::vector<uint8_t> blob(2 * sz32 + 2 * sz64 + szw + szp8 + szq, 0);
   uint32_t* t32t = (uint32_t*)blob.data();
   uint32_t* t32b = t32t + 256;
   uint64_t* t64t = (uint64_t*)(blob.data() + 2 * sz32);
@@ -329,6 +332,11 @@ rf_status rf_batch_create_u8(rf_metric metric, const uint8_t* query, uint32_t qu
       }
     }
   }
+  {
+    double* quot = (double*)(blob.data() + 2 * sz32 + 2 * sz64 + szw + szp8);
+    for (int a = 0; a < kQuotDim; ++a)
+      for (int d = 1; d < kQuotDim; ++d) quot[a * kQuotDim + d] = (double)a / (double)d;
+  }
   cudaError_t e = cudaMalloc(&b->d_blob, blob.size());
   if (e == cudaSuccess) e = cudaMemcpy(b->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) { rf_batch_destroy(b); return cuda_fail(e, "query table upload"); }
@@ -341,6 +349,7 @@ rf_status rf_batch_create_u8(rf_metric metric, const uint8_t* query, uint32_t qu
   b->view.pm_words = b->view.tab64_bot + 256;
   b->view.pm_band = (const uint32_t*)(b->view.pm_words + (size_t)256 * words);
   b->view.band_stride = bstride;
+  b->view.quot = (const double*)(b->d_blob + 2 * sz32 + 2 * sz64 + szw + szp8);
   *out = b;
   return RF_OK;
 }

@@ -287,6 +287,26 @@ RF_HD uint64_t band_window32_low33(uint32_t a, uint32_t b, uint32_t o) {
 
 // ------------------------------------------------------------------------------------------------
 // Jaro building blocks (jaro.rs:106-145)
+// x / 3.0, correctly rounded, without the general division routine (Markstein: y = RN(1/3), q = RN(x*y),
+// r = x - 3q exactly (fma), result RN(q + r*y) is the correctly rounded quotient for normal operands).
+RF_HD double div3_exact(double x) {
+  const double y = 0.33333333333333331482961625624739;  // RN(1/3)
+  const double q = x * y;
+  const double r = fma(-3.0, q, x);
+  return fma(r, y, q);
+}
+// Jaro formula (jaro.rs:106-119) with the three quotients of small integers read from a table of exactly
+// rounded a/b (a, b <= 64) built on the host: bit-identical to the divisions, ~10x fewer instructions.
+constexpr int kQuotDim = 65;
+RF_HD double jaro_calculate_similarity_tab(const double* __restrict__ quot, uint32_t p_len, uint32_t t_len, uint32_t cc,
+                                           uint32_t transpositions) {
+  transpositions /= 2;
+  double sim = 0.0;
+  sim += quot[cc * kQuotDim + p_len];
+  sim += quot[cc * kQuotDim + t_len];
+  sim += quot[(cc - transpositions) * kQuotDim + cc];
+  return div3_exact(sim);
+}
 RF_HD double jaro_calculate_similarity(uint32_t p_len, uint32_t t_len, uint32_t cc, uint32_t transpositions) {
   transpositions /= 2;
   double sim = 0.0;
@@ -297,6 +317,7 @@ RF_HD double jaro_calculate_similarity(uint32_t p_len, uint32_t t_len, uint32_t 
 }
 RF_HD bool jaro_length_filter(uint32_t p_len, uint32_t t_len, double cutoff) {
   if (t_len == 0 || p_len == 0) return false;
+  if (cutoff <= 0.0) return true;  // the bound below is positive: same answer without the three divisions
   const double min_len = (double)(p_len < t_len ? p_len : t_len);
   double sim = min_len / (double)p_len + min_len / (double)t_len + 1.0;
   sim /= 3.0;
@@ -304,6 +325,7 @@ RF_HD bool jaro_length_filter(uint32_t p_len, uint32_t t_len, double cutoff) {
 }
 RF_HD bool jaro_common_char_filter(uint32_t p_len, uint32_t t_len, uint32_t cc, double cutoff) {
   if (cc == 0) return false;
+  if (cutoff <= 0.0) return true;  // as above
   double sim = 0.0;
   sim += (double)cc / (double)p_len;
   sim += (double)cc / (double)t_len;
@@ -423,6 +445,85 @@ RF_HD double jaro_similarity_w1(const Tab& tab, const Bytes& bytes, uint32_t len
     P ^= pbit;
   }
   return jaro_calculate_similarity(len1_orig, len2_orig, cc, transpositions);
+}
+
+// Jaro flag + transposition passes for query <= 32 and (truncated) candidate <= 64, written for a warp whose
+// lanes walk 8-byte rows in lock step (jaro.rs:147-190, :339-368): P (pattern flags) and the search window are
+// 32-bit, the text flags are collected 8 bits per row.  `tab(ch)` is the bottom-aligned 32-bit PM, `row(r)`
+// returns text bytes 8r..8r+7 (anything beyond len2), `nrows` >= ceil(len2/8) may be larger than this lane needs
+// (warp-uniform loop bound): characters at j >= len2 are masked out.  No early exits, no data-dependent loops:
+// per character ~8 instructions in pass 1 and ~9 in pass 2, identical control flow in all 32 lanes.
+//   len1, len2 are the TRUNCATED lengths and bound the window radius (jaro.rs:553-565); requires len2 <= 64.
+struct Jaro32Result { uint32_t cc, transpositions; };
+template <class Tab, class Row>
+RF_HD Jaro32Result jaro32_rows(const Tab& tab, const Row& row, uint32_t len2, uint32_t bound, uint32_t nrows) {
+  if (nrows > 8) nrows = 8;  // len2 <= 64
+  uint32_t P = 0;
+  uint64_t T = 0;
+  // window for text position j: pattern bits [j - bound, j + bound]; hi grows by one bit per character,
+  // lo drops one bit per character once j > bound
+  uint32_t hi = (bound + 1 < 32) ? ((1u << (bound + 1)) - 1u) : 0xFFFFFFFFu;
+  uint32_t lo = 0xFFFFFFFFu;
+  for (uint32_t r = 0; r < nrows; ++r) {
+    const uint2 v = row(r);
+    uint32_t t8 = 0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const uint32_t j = r * 8u + (uint32_t)t;
+      const uint32_t ch = ((t < 4 ? v.x : v.y) >> (8 * (t & 3))) & 0xffu;
+      uint32_t m = tab(ch) & hi & lo & ~P;
+      if (j >= len2) m = 0;
+      P |= m & (0u - m);
+      t8 |= (uint32_t)(m != 0) << t;
+      hi = (hi << 1) | 1u;
+      if (j >= bound) lo <<= 1;
+    }
+    T |= (uint64_t)t8 << (8 * r);
+  }
+  Jaro32Result res;
+  res.cc = (uint32_t)popc(P);
+  uint32_t tr = 0;
+  for (uint32_t r = 0; r < nrows; ++r) {
+    const uint2 v = row(r);
+    const uint32_t t8 = (uint32_t)(T >> (8 * r)) & 0xffu;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const uint32_t ch = ((t < 4 ? v.x : v.y) >> (8 * (t & 3))) & 0xffu;
+      const uint32_t pbit = P & (0u - P);
+      const bool hit = (t8 >> t) & 1u;
+      if (hit) {
+        tr += (tab(ch) & pbit) == 0;
+        P ^= pbit;
+      }
+    }
+  }
+  res.transpositions = tr;
+  return res;
+}
+
+// Jaro similarity from the pass results, with the reference's filters in the reference's order
+// (jaro.rs:516-598); len1/len2 are the ORIGINAL lengths, first_match = query[0] == text[0] (1 x 1 case).
+//   quot: optional table of exact quotients (see jaro_calculate_similarity_tab), used when both lengths fit.
+RF_HD double jaro32_finish(uint32_t len1, uint32_t len2, const Jaro32Result& r, bool first_match, double cutoff,
+                           const double* __restrict__ quot = nullptr) {
+  if (cutoff > 1.0) return 0.0;
+  if (len1 == 0 && len2 == 0) return 1.0;
+  if (!jaro_length_filter(len1, len2, cutoff)) return 0.0;
+  if (len1 == 1 && len2 == 1) return first_match ? 1.0 : 0.0;
+  if (!jaro_common_char_filter(len1, len2, r.cc, cutoff)) return 0.0;
+  if (quot && len1 < (uint32_t)kQuotDim && len2 < (uint32_t)kQuotDim)
+    return jaro_calculate_similarity_tab(quot, len1, len2, r.cc, r.transpositions);
+  return jaro_calculate_similarity(len1, len2, r.cc, r.transpositions);
+}
+// truncated lengths and window radius (jaro.rs:553-565)
+RF_HD void jaro_bounds(uint32_t& len1, uint32_t& len2, uint32_t& bound) {
+  if (len2 > len1) {
+    bound = len2 / 2 - 1;
+    if (len2 > len1 + bound) len2 = len1 + bound;
+  } else {
+    bound = len1 / 2 - 1;  // wraps for len1 < 2: only reached for 1 x 1 / empty inputs, whose result ignores the passes
+    if (len1 > len2 + bound) len1 = len2 + bound;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

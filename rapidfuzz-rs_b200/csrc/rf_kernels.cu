@@ -22,6 +22,7 @@
 namespace rfk {
 
 static std::atomic<uint64_t> g_launches{0};
+static int g_jaro32 = 1;  // Jaro with query <= 32: row-wise 32-bit kernel (0: generic per-lane routine)
 uint64_t kernel_launch_count() { return g_launches.load(); }
 
 // ------------------------------------------------------------------------------------------------ PTX
@@ -535,6 +536,7 @@ cudaError_t launch_scan_w1(const ScanLaunch& L) {
 struct LbParams {
   LbView lb;
   const void* tab;
+  const double* quot;           // QueryView::quot (Jaro kernels)
   uint32_t len1;
   void* out;
   int out_f64;
@@ -645,6 +647,226 @@ static cudaError_t launch_lb_inst(const ScanLaunch& L, const void* tab) {
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------ jaro32
+// Jaro / Jaro-Winkler with a query of at most 32 elements over the interleaved layout (BASELINE config 4).
+// Thread per candidate, warp per group like scan_lb_kernel, but both passes (flagging and transposition
+// counting, rf_core.cuh jaro32_rows) walk the group's 8-byte rows with warp-uniform control flow: 32-bit
+// pattern flags and window masks, no per-character byte loads, no data-dependent loops.  Groups whose
+// (truncated) candidates exceed 64 characters take the generic per-lane routine.
+// Device form of rf_core.cuh jaro32_rows (same results; the host form is the CPU-tested specification): table
+// addresses by IDP.4A, window masks advanced on the FMA pipe, per-lane predicates only in the rows that need them.
+//   LO: 0 = no character of the row is past the window radius (lo stays), 1 = all are (lo shifts every step),
+//       2 = mixed (per-character test);  LENP: the row may extend past this lane's candidate.
+struct Jaro32Dev {
+  uint32_t P, hi, lo, M;
+  uint64_t T;
+  template <int K>
+  __device__ __forceinline__ uint32_t look(uint32_t w, uint32_t pm_lane_saddr) const {
+    uint32_t X;
+    const uint32_t addr = __dp4a(w, 0x80u << (8 * K), pm_lane_saddr);
+    asm("ld.shared.u32 %0, [%1];" : "=r"(X) : "r"(addr));
+    return X;
+  }
+  template <int LO, bool LENP, int K>
+  __device__ __forceinline__ void flag_step(uint32_t w, uint32_t j, uint32_t len2, uint32_t bound, uint32_t pm_lane_saddr,
+                                            uint32_t two, uint32_t& t8) {
+    const uint32_t X = look<K>(w, pm_lane_saddr);
+    uint32_t m = X & (hi & lo) & ~P;
+    if (LENP) m = (j < len2) ? m : 0u;
+    P |= m & (0u - m);
+    t8 = t8 * two + min(m, 1u);           // row-local text flags, first character in the top bit
+    hi = hi * two + (two >> 1);
+    if (LO == 1) lo = lo * two;
+    if (LO == 2) lo = (j >= bound) ? lo << 1 : lo;
+  }
+  template <int LO, bool LENP>
+  __device__ __forceinline__ void flag_row(uint2 v, uint32_t r, uint32_t len2, uint32_t bound, uint32_t pm_lane_saddr,
+                                           uint32_t two) {
+    uint32_t t8 = 0;
+    const uint32_t j0 = r * 8u;
+    flag_step<LO, LENP, 0>(v.x, j0 + 0, len2, bound, pm_lane_saddr, two, t8);
+    flag_step<LO, LENP, 1>(v.x, j0 + 1, len2, bound, pm_lane_saddr, two, t8);
+    flag_step<LO, LENP, 2>(v.x, j0 + 2, len2, bound, pm_lane_saddr, two, t8);
+    flag_step<LO, LENP, 3>(v.x, j0 + 3, len2, bound, pm_lane_saddr, two, t8);
+    flag_step<LO, LENP, 0>(v.y, j0 + 4, len2, bound, pm_lane_saddr, two, t8);
+    flag_step<LO, LENP, 1>(v.y, j0 + 5, len2, bound, pm_lane_saddr, two, t8);
+    flag_step<LO, LENP, 2>(v.y, j0 + 6, len2, bound, pm_lane_saddr, two, t8);
+    flag_step<LO, LENP, 3>(v.y, j0 + 7, len2, bound, pm_lane_saddr, two, t8);
+    T = (T << 8) | t8;  // rows pile up from the bottom byte; align_T() moves row 0 to the top byte
+  }
+  __device__ __forceinline__ void align_T(uint32_t nrows) { T = nrows ? T << (8u * (8u - nrows)) : 0ull; }
+  template <int K, int TB>
+  __device__ __forceinline__ void trans_step(uint32_t w, uint32_t t8, uint32_t pm_lane_saddr) {
+    const uint32_t X = look<K>(w, pm_lane_saddr);
+    const uint32_t pbit = P & (0u - P);
+    if (t8 & (0x80u >> TB)) {  // this text character was flagged: it pairs with the lowest remaining pattern flag
+      M |= pbit & ~X;          // pattern flags whose partner differs (one bit per transposed pair member)
+      P ^= pbit;
+    }
+  }
+  __device__ __forceinline__ void trans_row(uint2 v, uint32_t pm_lane_saddr) {
+    const uint32_t t8 = (uint32_t)(T >> 56);
+    T <<= 8;
+    trans_step<0, 0>(v.x, t8, pm_lane_saddr);
+    trans_step<1, 1>(v.x, t8, pm_lane_saddr);
+    trans_step<2, 2>(v.x, t8, pm_lane_saddr);
+    trans_step<3, 3>(v.x, t8, pm_lane_saddr);
+    trans_step<0, 4>(v.y, t8, pm_lane_saddr);
+    trans_step<1, 5>(v.y, t8, pm_lane_saddr);
+    trans_step<2, 6>(v.y, t8, pm_lane_saddr);
+    trans_step<3, 7>(v.y, t8, pm_lane_saddr);
+  }
+};
+
+template <int NT>
+__global__ void __launch_bounds__(NT) scan_jaro32_kernel(const __grid_constant__ LbParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* pm = reinterpret_cast<uint32_t*>(smem_raw);
+  {
+    const uint32_t* __restrict__ t = reinterpret_cast<const uint32_t*>(p.tab);
+    for (uint32_t i = threadIdx.x; i < 256u * 32u; i += NT) pm[i] = t[i >> 5];
+  }
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t* __restrict__ pm_lane = pm + lane;
+  const uint64_t total_warps = (uint64_t)gridDim.x * (NT / 32);
+  const uint64_t ngroups = p.lb.ngroups;
+  const uint64_t nchunks = (ngroups + p.chunk - 1) / p.chunk;
+  const uint2* __restrict__ gdata = reinterpret_cast<const uint2*>(p.lb.gdata);
+  auto tab = [&](uint32_t ch) -> uint32_t { return pm_lane[ch * 32u]; };
+  uint64_t chunk = (uint64_t)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
+  while (chunk < nchunks) {
+    unsigned long long next_chunk = 0;
+    if (lane == 0) next_chunk = total_warps + atomicAdd(p.counter, 1ull);
+    const uint64_t g0 = chunk * p.chunk;
+    const uint64_t g1 = (g0 + p.chunk < ngroups) ? g0 + p.chunk : ngroups;
+    uint64_t r = __ldg(p.lb.goff + g0);
+    uint32_t len_n = __ldg(p.lb.lens + g0 * 32 + lane);
+    uint32_t idx_n = __ldg(p.lb.perm + g0 * 32 + lane);
+    uint2 first_n = __ldg(gdata + r * 32 + lane);
+    for (uint64_t g = g0; g < g1; ++g) {
+      const uint32_t len2 = len_n, idx = idx_n;
+      const uint2 first = first_n;
+      const uint2* col = gdata + r * 32 + lane;
+      r += (__reduce_max_sync(0xffffffffu, len2) + 7u) >> 3;
+      if (g + 1 < g1) {  // next group: metadata + first row into registers, its other rows into L2
+        len_n = __ldg(p.lb.lens + (g + 1) * 32 + lane);
+        idx_n = __ldg(p.lb.perm + (g + 1) * 32 + lane);
+        const uint2* ncol = gdata + r * 32 + lane;
+        first_n = __ldg(ncol);
+#pragma unroll
+        for (int k = 1; k < 8; ++k) prefetch_l2(ncol + k * 32);
+      }
+      uint32_t l1e = p.len1, l2e = len2, bound = 0;
+      jaro_bounds(l1e, l2e, bound);
+      const uint32_t l2max = __reduce_max_sync(0xffffffffu, l2e);
+      double res;
+      if (l2max <= 64) {
+        const uint32_t pm_lane_saddr = smem_u32(pm_lane);
+        const uint32_t nrows = (l2max + 7u) >> 3;
+        const uint32_t l2min = __reduce_min_sync(0xffffffffu, l2e);
+        const uint32_t bmin = __reduce_min_sync(0xffffffffu, bound), bmax = __reduce_max_sync(0xffffffffu, bound);
+        Jaro32Dev J;
+        J.P = 0; J.M = 0; J.T = 0; J.lo = 0xFFFFFFFFu;
+        J.hi = (bound + 1 < 32) ? ((1u << (bound + 1)) - 1u) : 0xFFFFFFFFu;
+        uint2 v = first;
+        for (uint32_t rr = 0; rr < nrows; ++rr) {  // pass 1: flags (row modes are warp-uniform)
+          const uint2 cur = v;
+          if (rr + 1 < nrows) v = __ldg(col + (rr + 1) * 32u);
+          const uint32_t j0 = rr * 8u;
+          const bool full = j0 + 8u <= l2min;
+          const int lo_mode = (j0 + 8u <= bmin) ? 0 : (j0 >= bmax) ? 1 : 2;
+          if (full) {
+            if (lo_mode == 0) J.flag_row<0, false>(cur, rr, l2e, bound, pm_lane_saddr, p.two);
+            else if (lo_mode == 1) J.flag_row<1, false>(cur, rr, l2e, bound, pm_lane_saddr, p.two);
+            else J.flag_row<2, false>(cur, rr, l2e, bound, pm_lane_saddr, p.two);
+          } else {
+            if (lo_mode == 1) J.flag_row<1, true>(cur, rr, l2e, bound, pm_lane_saddr, p.two);
+            else J.flag_row<2, true>(cur, rr, l2e, bound, pm_lane_saddr, p.two);
+          }
+        }
+        J.align_T(nrows);
+        Jaro32Result jr;
+        jr.cc = (uint32_t)__popc(J.P);
+        v = first;
+        for (uint32_t rr = 0; rr < nrows; ++rr) {  // pass 2: transpositions (rows now come from L1/L2)
+          const uint2 cur = v;
+          if (rr + 1 < nrows) v = __ldg(col + (rr + 1) * 32u);
+          J.trans_row(cur, pm_lane_saddr);
+        }
+        jr.transpositions = (uint32_t)__popc(J.M);
+        const uint32_t w0 = len2 ? first.x : 0u;
+        const bool fm = len2 && (tab(w0 & 0xffu) & 1u);
+        const uint32_t len1 = p.len1;
+        const double* quot = p.quot;
+        auto jaro = [&](double c) { return jaro32_finish(len1, len2, jr, fm, c, quot); };
+        if (p.epi.metric == M_JARO) {
+          res = finish_float(p.epi, jaro);
+        } else {
+          uint32_t prefix = 0;  // common prefix, at most 4 (jaro_winkler.rs:118-123)
+          const uint32_t lim = len1 < len2 ? (len1 < 4 ? len1 : 4) : (len2 < 4 ? len2 : 4);
+          while (prefix < lim && ((tab((w0 >> (8 * prefix)) & 0xffu) >> prefix) & 1u)) ++prefix;
+          const double pw = p.epi.prefix_weight;
+          auto jw = [&](double c) { return jaro_winkler_from(jaro, prefix, pw, c); };
+          res = finish_float(p.epi, jw);
+        }
+      } else {
+        const LaneSrcT<false> src{col, __ldg(col), __ldg(col + 32)};
+        uint32_t ru = 0;
+        auto tab64 = [&](uint32_t ch) -> uint64_t { return (uint64_t)pm_lane[ch * 32u]; };
+        auto bytes = [&](uint32_t j) -> uint32_t { return src.byte(j); };
+        const uint32_t len1 = p.len1;
+        auto jaro = [&](double c) { return jaro_similarity_w1(tab64, bytes, len1, len2, c); };
+        (void)ru;
+        if (p.epi.metric == M_JARO) {
+          res = finish_float(p.epi, jaro);
+        } else {
+          uint32_t prefix = 0;
+          while (prefix < 4 && prefix < len1 && prefix < len2 && ((tab64(bytes(prefix)) >> prefix) & 1u)) ++prefix;
+          const double pw = p.epi.prefix_weight;
+          auto jw = [&](double c) { return jaro_winkler_from(jaro, prefix, pw, c); };
+          res = finish_float(p.epi, jw);
+        }
+      }
+      if (idx != 0xFFFFFFFFu) reinterpret_cast<double*>(p.out)[idx] = res;
+    }
+    chunk = __shfl_sync(0xffffffffu, next_chunk, 0);
+  }
+}
+
+static cudaError_t launch_jaro32(const ScanLaunch& L) {
+  constexpr int NT = 256;
+  auto kern = scan_jaro32_kernel<NT>;
+  const size_t smem = sizeof(uint32_t) * 256 * 32;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int ctas_per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, NT, smem);
+  if (e != cudaSuccess) return e;
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  LbParams p{};
+  p.lb = L.lb;
+  p.tab = L.query.tab32_bot;
+  p.quot = L.query.quot;
+  p.len1 = L.query.len1;
+  p.out = L.out;
+  p.out_f64 = 1;
+  p.two = 2;
+  p.chunk = 16;
+  p.counter = L.lb_counter;
+  p.epi = L.epi;
+  e = cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), L.stream);
+  if (e != cudaSuccess) return e;
+  uint64_t grid = (uint64_t)L.sm_count * ctas_per_sm;
+  const uint64_t nchunks = (L.lb.ngroups + p.chunk - 1) / p.chunk;
+  const uint64_t need = (nchunks + NT / 32 - 1) / (NT / 32);
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  kern<<<(uint32_t)grid, NT, smem, L.stream>>>(p);
+  g_launches.fetch_add(1);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_scan_lb(const ScanLaunch& L) {
   const Family fam = family_of(L.epi.metric, L.epi.wclass);
   const bool w32 = L.query.len1 <= 32;
@@ -667,9 +889,11 @@ cudaError_t launch_scan_lb(const ScanLaunch& L) {
       return w32 ? launch_lb_inst<F_LCS, uint32_t, 256>(L, L.query.tab32_bot)
                  : launch_lb_inst<F_LCS, uint64_t, 512>(L, L.query.tab64_bot);
     default:
+      if (L.query.len1 >= 1 && L.query.len1 <= 32 && g_jaro32) return launch_jaro32(L);
       return launch_lb_inst<F_JARO, uint64_t, 512>(L, L.query.tab64_bot);
   }
 }
+void set_jaro32(int on) { g_jaro32 = on; }
 
 // ------------------------------------------------------------------------------------------------ lb ring (TMA)
 // Same work as scan_lb_kernel (warp per group of 32 equal-length candidates of the interleaved layout), but the

@@ -27,6 +27,7 @@ struct QueryView {
   const uint64_t* pm_words;  // [256][words] row-major (pattern_match_vector.rs layout), any len1
   const uint32_t* pm_band;   // [256][band_stride] 32-bit words: 2 zero words, the match vector, >= 2 zero words (banded kernel)
   uint32_t band_stride;      // (2*(words+2)) | 1
+  const double* quot;        // [65][65] exactly rounded a/b (b >= 1): the Jaro formula's quotients without divisions
 };
 
 // Length-bucketed, warp-interleaved copy of the corpus (built once at corpus creation, rf_layout.cu):
@@ -99,6 +100,7 @@ cudaError_t launch_cdist_topk(const CdistLaunch& L);
 uint32_t cdist_parts(int sm_count);
 
 uint64_t kernel_launch_count();
+void set_jaro32(int on);  // tuning/testing: 0 = Jaro queries <= 32 use the generic per-lane routine
 
 // Stream-ordered device allocations from the device's default memory pool (release threshold = never), so that
 // creating / destroying multi-GB corpora repeatedly does not pay cudaMalloc / cudaFree page-table work each time.

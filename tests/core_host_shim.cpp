@@ -2,6 +2,9 @@
 // to pytest so the bit tricks are checked against the oracle on the CPU box before any GPU time is spent.
 #include <cstring>
 #include <vector>
+#if !defined(__CUDACC__)
+struct uint2 { unsigned int x, y; };   // CUDA's vector type, for the host build of the row-wise routines
+#endif
 #include "../rapidfuzz-rs_b200/csrc/rf_core.cuh"
 
 using namespace rfk;
@@ -126,6 +129,35 @@ uint32_t core_lev_band(const uint8_t* q, uint32_t len1, const uint8_t* s2, uint3
   const int32_t d = b.score();
   return d <= (int32_t)k ? (uint32_t)d : 0xFFFFFFFFu;
 }
+
+// Jaro via the row-wise 32-bit passes (jaro32_rows); returns NaN when the pair is outside that path's domain
+double core_jaro32(const uint8_t* q, uint32_t len1, const uint8_t* s2, uint32_t len2, double cutoff, uint32_t extra_rows) {
+  if (len1 == 0 || len1 > 32) return NAN;
+  uint32_t tab32[256];
+  build_tab(q, len1, false, tab32);
+  uint32_t l1 = len1, l2 = len2, bound = 0;
+  jaro_bounds(l1, l2, bound);
+  if (l2 > 64) return NAN;
+  std::vector<uint8_t> buf((size_t)len2 + 8 * (extra_rows + 2), 0x5A);  // junk behind the candidate
+  if (len2) memcpy(buf.data(), s2, len2);
+  auto tab = [&](uint32_t ch) { return tab32[ch]; };
+  auto row = [&](uint32_t r) { uint2 v; memcpy(&v, buf.data() + 8 * r, 8); return v; };
+  const uint32_t nrows = (l2 + 7) / 8 + extra_rows;
+  const Jaro32Result res = jaro32_rows(tab, row, l2, bound, nrows);
+  const bool fm = len2 > 0 && (tab32[s2[0]] & 1u);
+  static std::vector<double> quot;
+  if (quot.empty()) {
+    quot.resize(kQuotDim * kQuotDim);
+    for (int a = 0; a < kQuotDim; ++a)
+      for (int b = 0; b < kQuotDim; ++b) quot[a * kQuotDim + b] = b ? (double)a / (double)b : 0.0;
+  }
+  const double with_tab = jaro32_finish(len1, len2, res, fm, cutoff, quot.data());
+  const double plain = jaro32_finish(len1, len2, res, fm, cutoff);
+  if (memcmp(&with_tab, &plain, sizeof(double)) != 0) return -12345.0;  // the table path must be bit-identical
+  return with_tab;
+}
+
+double core_div3(double x) { return div3_exact(x); }
 
 // generic (multi-word) Jaro on the host, query <= 1024
 double core_jaro_generic(const uint8_t* q, uint32_t len1, const uint8_t* s, uint32_t len2, double cutoff) {

@@ -32,6 +32,8 @@ def core():
     lib.core_score.restype = C.c_int
     lib.core_lev_band.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
     lib.core_lev_band.restype = C.c_uint32
+    lib.core_jaro32.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_double, C.c_uint32]
+    lib.core_jaro32.restype = C.c_double
     lib.core_jaro_generic.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_double]
     lib.core_jaro_generic.restype = C.c_double
     return lib
@@ -164,3 +166,36 @@ def test_banded_levenshtein_vs_oracle(core):
                 assert got == exp, (bytes(a), bytes(b), k, ce, got, exp)
                 n += 1
     assert n > 50000
+
+
+def test_jaro32_rows_vs_oracle_bit_exact(core):
+    """Row-wise 32-bit Jaro passes (query <= 32, truncated candidate <= 64) == the oracle's raw similarity."""
+    rng = np.random.default_rng(41)
+    n = 0
+    for a, b in _pairs(rng, 4000, [1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 24, 31, 32], CL, 5):
+        for c in (0.0, 0.5, 0.7, 0.8, 0.95, 1.0, 1.1):
+            exp = orc.pair("jaro", "similarity", a, b, cutoff=c)
+            exp = 0.0 if exp is None else exp
+            for extra in (0, 2):
+                got = core.core_jaro32(a.ctypes.data, len(a), b.ctypes.data, len(b), c, extra)
+                if math.isnan(got):
+                    continue  # outside the fast path's domain (long candidate)
+                if got < c:
+                    got = 0.0
+                assert got == exp, (bytes(a), bytes(b), c, extra, got, exp)
+                n += 1
+    assert n > 20000
+
+
+def test_div3_exact_is_correctly_rounded():
+    """div3_exact(x) == x / 3.0 bit for bit on the values the Jaro formula can produce and on random doubles."""
+    import ctypes
+    lib = ctypes.CDLL(SO)
+    lib.core_div3.argtypes = [ctypes.c_double]
+    lib.core_div3.restype = ctypes.c_double
+    rng = np.random.default_rng(1)
+    xs = [a / b + c / d + e / f for a in range(0, 33, 3) for b in range(1, 65, 7) for c in range(0, 33, 5)
+          for d in range(1, 65, 9) for e in range(0, 33, 4) for f in range(1, 33, 5)]
+    xs += list(rng.random(20000) * 3.0) + list(rng.random(2000) * 1e-3) + [0.0, 3.0, 1.0, 2.0, 1e-300, 2.9999999999999996]
+    for x in xs:
+        assert lib.core_div3(x) == x / 3.0, x

@@ -162,6 +162,12 @@ def test_query_64_vs_long_candidates_and_tile_overflow():
         check(m, "distance", q, chars, offsets, corpus)
     check("jaro_winkler", "normalized_similarity", q, chars, offsets, corpus)
     check("jaro", "similarity", q, chars, offsets, corpus, cutoff=0.4)
+    # query <= 32 (row-wise 32-bit Jaro kernel): groups of long candidates take its generic fallback
+    for ql in (20, 32):
+        q2 = q[:ql]
+        for m in ("jaro", "jaro_winkler"):
+            check(m, "similarity", q2, chars, offsets, corpus)
+            check(m, "normalized_distance", q2, chars, offsets, corpus, cutoff=0.5)
     corpus.close()
 
 

@@ -1,6 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for path in 0 2 0 2; do
-  RF_W1_PATH=$path timeout 300 python bench.py --steps 200 --no-cpu-baseline --e2e-steps 1 > gpurun_out/b$path.json 2> gpurun_out/b.err
-  echo "path $path: $(python -c "import json;d=json.load(open('gpurun_out/b$path.json'));print(d['ms_per_step'], d['config']['results_match_oracle_sample'])")"; tail -2 gpurun_out/b.err
-done
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:scan_jaro32 -s 2 -c 1 -f -o gpurun_out/prof_j32 python tools/bench_configs.py c4 > gpurun_out/ncu_j32.log 2>&1

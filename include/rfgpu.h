@@ -121,6 +121,24 @@ rf_status rf_batch_similarity_f64(const rf_batch* b, const rf_corpus* c, const r
 rf_status rf_batch_normalized_distance_f64(const rf_batch* b, const rf_corpus* c, const rf_args* args, double* out);
 rf_status rf_batch_normalized_similarity_f64(const rf_batch* b, const rf_corpus* c, const rf_args* args, double* out);
 
+/* ---- scoring + post-processing on the device (new on this side; what Python rapidfuzz calls process.extract --
+ * the Rust crate leaves the sort / cutoff collection to the caller's loop).  Only the selected (index, score) pairs
+ * cross PCIe instead of n scores.
+ *   extract: the k (<= 1024) best candidates by (score best-first, index ascending); "best" = smallest for the
+ *            distance kinds, largest for the similarity kinds; None scores (args->score_cutoff) never qualify;
+ *            *n_out = entries written (< k when fewer candidates qualify).
+ *   filter:  every candidate whose score is not None (i.e. passed args->score_cutoff), in index order;
+ *            *n_hits = their total number, of which the first min(n_hits, capacity) are written.
+ * Host output buffers; u32 / f64 as for rf_batch_score_*. */
+rf_status rf_batch_extract_u32(const rf_batch* b, const rf_corpus* c, rf_kind kind, const rf_args* args, uint32_t k,
+                               uint32_t* idx_out, uint32_t* score_out, uint32_t* n_out);
+rf_status rf_batch_extract_f64(const rf_batch* b, const rf_corpus* c, rf_kind kind, const rf_args* args, uint32_t k,
+                               uint32_t* idx_out, double* score_out, uint32_t* n_out);
+rf_status rf_batch_filter_u32(const rf_batch* b, const rf_corpus* c, rf_kind kind, const rf_args* args, uint64_t capacity,
+                              uint32_t* idx_out, uint32_t* score_out, uint64_t* n_hits);
+rf_status rf_batch_filter_f64(const rf_batch* b, const rf_corpus* c, rf_kind kind, const rf_args* args, uint64_t capacity,
+                              uint32_t* idx_out, double* score_out, uint64_t* n_hits);
+
 /* ---- streaming: the same loop when the candidates live in HOST memory and are not kept on the GPU
  * (the literal shape of `for c in candidates { scorer.distance(c) }`, levenshtein.rs:1740-1777 / bench_levenshtein.rs:51-58).
  * The CSR corpus is cut into chunks; H2D copy, scan and result D2H of successive chunks overlap on separate

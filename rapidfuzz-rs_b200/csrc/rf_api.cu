@@ -510,6 +510,94 @@ rf_status rf_batch_normalized_similarity_f64(const rf_batch* b, const rf_corpus*
 
 }  // extern "C"
 
+// ------------------------------------------------------------------------------------------------ extract / filter
+// Scoring + on-device post-processing: only k (or the number of hits) index/score pairs cross PCIe.
+namespace {
+rf_status select_host(const rf_batch* b, const rf_corpus* c, rf_kind kind, const rf_args* args, bool want_f64, bool filter,
+                      uint32_t k, uint64_t cap, uint32_t* idx_out, void* score_out, uint32_t* n32_out, uint64_t* n64_out) {
+  if (!b || !c) return fail(RF_ERR_INVALID_ARG, "NULL handle");
+  if ((int)kind < 0 || (int)kind > 3) return fail(RF_ERR_INVALID_ARG, "unknown kind");
+  if ((rf_result_is_float(b->metric, kind) != 0) != want_f64)
+    return fail(RF_ERR_INVALID_ARG, want_f64 ? "this (metric, kind) yields u32 results; use the _u32 entry point"
+                                             : "this (metric, kind) yields f64 results; use the _f64 entry point");
+  if (!filter && (k == 0 || k > 1024)) return fail(RF_ERR_INVALID_ARG, "k must be in 1..1024");
+  if (filter ? !n64_out : !n32_out) return fail(RF_ERR_INVALID_ARG, "count output is NULL");
+  const uint64_t slots = filter ? cap : (uint64_t)k;
+  if (slots && (!idx_out || !score_out)) return fail(RF_ERR_INVALID_ARG, "output buffer is NULL");
+  if (filter) *n64_out = 0; else *n32_out = 0;
+  if (c->n == 0) return RF_OK;
+  DeviceGuard g(c->device);
+  if (!g.ok) return fail(RF_ERR_CUDA, "cudaSetDevice failed");
+  const size_t esz = want_f64 ? 8 : 4;
+  cudaStream_t st;
+  cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
+  void* d_scores = nullptr;
+  uint8_t* d_out = nullptr;  // [idx slots*4][score slots*esz][count 8]
+  rf_status s = RF_OK;
+  do {
+    if ((e = dev_alloc(&d_scores, (size_t)c->n * esz, st)) != cudaSuccess) break;
+    const size_t off_score = (slots * 4 + 7) & ~(size_t)7, off_n = off_score + slots * esz;
+    if ((e = dev_alloc(&d_out, off_n + 16, st)) != cudaSuccess) break;
+    if ((e = cudaMemsetAsync(d_out + off_n, 0, 16, st)) != cudaSuccess) break;
+    s = score_device(b, c, kind, args, d_scores, want_f64, st);
+    if (s != RF_OK) break;
+    rfk::SelectLaunch L{};
+    L.scores = d_scores;
+    L.n = c->n;
+    L.f64 = want_f64 ? 1 : 0;
+    const rf_kind ek = (b->metric == RF_RATIO) ? RF_NORMALIZED_SIMILARITY : kind;
+    L.desc = (ek == RF_SIMILARITY || ek == RF_NORMALIZED_SIMILARITY) ? 1 : 0;
+    L.filter = filter ? 1 : 0;
+    L.k = k;
+    L.cap = cap;
+    L.out_idx = (uint32_t*)d_out;
+    L.out_score = d_out + off_score;
+    L.out_n32 = (uint32_t*)(d_out + off_n);
+    L.out_n64 = (unsigned long long*)(d_out + off_n);
+    L.stream = st;
+    L.sm_count = sm_count_of(c->device);
+    if ((e = rfk::launch_select(L)) != cudaSuccess) break;
+    uint64_t cnt = 0;
+    if ((e = cudaMemcpyAsync(&cnt, d_out + off_n, 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) break;
+    uint64_t m;
+    if (filter) { *n64_out = cnt; m = cnt < cap ? cnt : cap; }
+    else { *n32_out = (uint32_t)cnt; m = (uint32_t)cnt; }
+    if (m) {
+      if ((e = cudaMemcpyAsync(idx_out, d_out, m * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
+      if ((e = cudaMemcpyAsync(score_out, d_out + off_score, m * esz, cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
+      if ((e = cudaStreamSynchronize(st)) != cudaSuccess) break;
+    }
+  } while (0);
+  if (e != cudaSuccess && s == RF_OK) s = cuda_fail(e, "extract/filter");
+  dev_free(d_scores, st);
+  dev_free(d_out, st);
+  cudaStreamSynchronize(st);
+  cudaStreamDestroy(st);
+  return s;
+}
+}  // namespace
+
+extern "C" {
+rf_status rf_batch_extract_u32(const rf_batch* b, const rf_corpus* c, rf_kind kind, const rf_args* args, uint32_t k,
+                               uint32_t* idx_out, uint32_t* score_out, uint32_t* n_out) {
+  return select_host(b, c, kind, args, false, false, k, 0, idx_out, score_out, n_out, nullptr);
+}
+rf_status rf_batch_extract_f64(const rf_batch* b, const rf_corpus* c, rf_kind kind, const rf_args* args, uint32_t k,
+                               uint32_t* idx_out, double* score_out, uint32_t* n_out) {
+  return select_host(b, c, kind, args, true, false, k, 0, idx_out, score_out, n_out, nullptr);
+}
+rf_status rf_batch_filter_u32(const rf_batch* b, const rf_corpus* c, rf_kind kind, const rf_args* args, uint64_t capacity,
+                              uint32_t* idx_out, uint32_t* score_out, uint64_t* n_hits) {
+  return select_host(b, c, kind, args, false, true, 0, capacity, idx_out, score_out, nullptr, n_hits);
+}
+rf_status rf_batch_filter_f64(const rf_batch* b, const rf_corpus* c, rf_kind kind, const rf_args* args, uint64_t capacity,
+                              uint32_t* idx_out, double* score_out, uint64_t* n_hits) {
+  return select_host(b, c, kind, args, true, true, 0, capacity, idx_out, score_out, nullptr, n_hits);
+}
+}  // extern "C"
+
 // ------------------------------------------------------------------------------------------------ streaming
 // One-shot scoring of HOST-resident candidates: the literal shape of the reference's hot loop
 // (`for c in candidates { scorer.distance(c) }`, levenshtein.rs:1740-1777) when the candidates are not kept on

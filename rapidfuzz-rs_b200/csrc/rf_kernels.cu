@@ -24,6 +24,7 @@ namespace rfk {
 static std::atomic<uint64_t> g_launches{0};
 static int g_jaro32 = 1;  // Jaro with query <= 32: row-wise 32-bit kernel (0: generic per-lane routine)
 uint64_t kernel_launch_count() { return g_launches.load(); }
+void count_launches(uint64_t n) { g_launches.fetch_add(n); }
 
 // ------------------------------------------------------------------------------------------------ PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

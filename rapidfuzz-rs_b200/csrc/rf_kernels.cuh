@@ -99,6 +99,26 @@ struct CdistLaunch {
 cudaError_t launch_cdist_topk(const CdistLaunch& L);
 uint32_t cdist_parts(int sm_count);
 
+// Result post-processing over a device-resident score vector (rf_select.cu): the k best by (score best-first,
+// index ascending), or every score that is not None in index order.
+struct SelectLaunch {
+  const void* scores;   // u32[n] (0xFFFFFFFF = None) or f64[n] (NaN = None)
+  uint64_t n;
+  int f64;              // element type of scores
+  int desc;             // 1: larger score is better (similarity kinds)
+  int filter;           // 0: top-k, 1: all non-None
+  uint32_t k;           // top-k: 1..1024
+  uint64_t cap;         // filter: capacity of the outputs
+  uint32_t* out_idx;    // device, [k] or [cap]
+  void* out_score;      // device, same element type as scores
+  uint32_t* out_n32;    // device, top-k: number of entries written (< k when fewer candidates qualify)
+  unsigned long long* out_n64;  // device, filter: total number of hits (may exceed cap)
+  cudaStream_t stream;
+  int sm_count;
+};
+cudaError_t launch_select(const SelectLaunch& L);
+void count_launches(uint64_t n);
+
 uint64_t kernel_launch_count();
 void set_jaro32(int on);  // tuning/testing: 0 = Jaro queries <= 32 use the generic per-lane routine
 

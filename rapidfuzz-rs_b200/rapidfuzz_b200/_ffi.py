@@ -57,6 +57,10 @@ SYMBOLS = {
     "rf_batch_similarity_f64": (_int, [_vp, _vp, _PA, _vp]),
     "rf_batch_normalized_distance_f64": (_int, [_vp, _vp, _PA, _vp]),
     "rf_batch_normalized_similarity_f64": (_int, [_vp, _vp, _PA, _vp]),
+    "rf_batch_extract_u32": (_int, [_vp, _vp, _int, _PA, _u32, _vp, _vp, _vp]),
+    "rf_batch_extract_f64": (_int, [_vp, _vp, _int, _PA, _u32, _vp, _vp, _vp]),
+    "rf_batch_filter_u32": (_int, [_vp, _vp, _int, _PA, _u64, _vp, _vp, _vp]),
+    "rf_batch_filter_f64": (_int, [_vp, _vp, _int, _PA, _u64, _vp, _vp, _vp]),
     "rf_batch_stream_u32": (_int, [_vp, _vp, _vp, _u64, _int, _PA, _vp]),
     "rf_batch_stream_u32_off32": (_int, [_vp, _vp, _vp, _u64, _int, _PA, _vp]),
     "rf_batch_stream_f64": (_int, [_vp, _vp, _vp, _u64, _int, _PA, _vp]),

@@ -125,6 +125,33 @@ class BatchComparatorBase:
         mask = np.isnan(out) if is_f else (out == _ffi.NONE_U32)
         return np.ma.MaskedArray(out, mask=mask)
 
+    def extract(self, kind, corpus, k=5, args=None):
+        """rf_batch_extract_*: the k best candidates of `corpus` by (score best-first, index ascending), selected on
+        the GPU (Python rapidfuzz's process.extract).  Returns (idx uint32[m], score[m]) with m <= k."""
+        args = args if args is not None else Args()
+        is_f = bool(_ffi.lib().rf_result_is_float(_ffi.METRICS[self.METRIC], _ffi.KINDS[kind]))
+        ca = args._c(is_f)
+        idx = np.empty(k, dtype=np.uint32)
+        score = np.empty(k, dtype=np.float64 if is_f else np.uint32)
+        m = C.c_uint32(0)
+        fn = _ffi.lib().rf_batch_extract_f64 if is_f else _ffi.lib().rf_batch_extract_u32
+        _ffi.check(fn(self._h, corpus._h, _ffi.KINDS[kind], C.byref(ca), k, idx.ctypes.data, score.ctypes.data, C.byref(m)))
+        return idx[: m.value], score[: m.value]
+
+    def filter(self, kind, corpus, args, capacity=None):
+        """rf_batch_filter_*: every candidate whose score passed args.score_cutoff, in index order, compacted on the
+        GPU.  Returns (idx uint32[m], score[m], total_hits); m = min(total_hits, capacity)."""
+        is_f = bool(_ffi.lib().rf_result_is_float(_ffi.METRICS[self.METRIC], _ffi.KINDS[kind]))
+        ca = args._c(is_f)
+        cap = len(corpus) if capacity is None else int(capacity)
+        idx = np.empty(cap, dtype=np.uint32)
+        score = np.empty(cap, dtype=np.float64 if is_f else np.uint32)
+        tot = C.c_uint64(0)
+        fn = _ffi.lib().rf_batch_filter_f64 if is_f else _ffi.lib().rf_batch_filter_u32
+        _ffi.check(fn(self._h, corpus._h, _ffi.KINDS[kind], C.byref(ca), cap, idx.ctypes.data, score.ctypes.data, C.byref(tot)))
+        m = min(tot.value, cap)
+        return idx[:m], score[:m], tot.value
+
     def stream(self, kind, chars, offsets, args=None, out=None):
         """rf_batch_stream_*: scores HOST-resident candidates (CSR chars u8 + offsets u32/u64) without keeping a
         corpus on the GPU; chunked H2D / scan / D2H pipeline.  Returns the raw sentinel-carrying array

@@ -337,6 +337,49 @@ def test_streaming_large_equals_resident():
     assert np.array_equal(s[:300000], exp)
 
 
+def _bc(metric, q):
+    from rapidfuzz_b200._scorer import BatchComparatorBase
+    return type("B", (BatchComparatorBase,), {"METRIC": metric})(q)
+
+
+@pytest.mark.parametrize("n", [1, 37, 5000, 300_000])
+def test_extract_and_filter_vs_oracle(n):
+    """On-device post-processing: k best by (score best-first, index ascending) and cutoff compaction in index
+    order, against the oracle's full score vector sorted / filtered with numpy."""
+    q = rf.synth_query(9, 32)
+    chars, offsets = rf.synth_corpus(9, q, n, 8, 64, 16)
+    corpus = rf.Corpus(chars, offsets)
+    idxs = np.arange(n)
+    for metric, kind, cut in (("levenshtein", "distance", None), ("levenshtein", "distance", 12),
+                              ("levenshtein", "normalized_similarity", None), ("indel", "similarity", None),
+                              ("lcs_seq", "similarity", 10), ("osa", "distance", None),
+                              ("jaro_winkler", "similarity", None), ("jaro", "normalized_distance", 0.45),
+                              ("ratio", "similarity", 0.4)):
+        kw = {} if cut is None else {"cutoff": cut}
+        exp = orc.batch(metric, kind, q, chars, offsets, nthreads=0, **kw)
+        is_f = exp.dtype == np.float64
+        valid = ~np.isnan(exp) if is_f else (exp != 0xFFFFFFFF)
+        desc = kind in ("similarity", "normalized_similarity") or metric == "ratio"
+        order = np.lexsort((idxs, -exp.astype(np.float64) if desc else exp.astype(np.float64)))
+        order = order[valid[order]]
+        b = _bc(metric, q)
+        a = rf.Args() if cut is None else rf.Args().score_cutoff(cut)
+        for k in (1, 5, 64, 1000):
+            gi, gs = b.extract(kind, corpus, k=k, args=a)
+            e = order[:k]
+            assert np.array_equal(gi, e.astype(np.uint32)), (metric, kind, cut, k, n)
+            assert np.array_equal(gs, exp[e]), (metric, kind, cut, k, n)
+        if cut is not None:
+            hits = np.nonzero(valid)[0]
+            for cap in (None, 3, 0):
+                gi, gs, tot = b.filter(kind, corpus, a, capacity=cap)
+                m = len(hits) if cap is None else min(cap, len(hits))
+                assert tot == len(hits), (metric, kind, cut, cap, tot, len(hits))
+                assert np.array_equal(gi, hits[:m].astype(np.uint32)) and np.array_equal(gs, exp[hits[:m]])
+        b.close()
+    corpus.close()
+
+
 def _oracle_topk(queries, chars, offsets, k, cutoff=None):
     n = len(offsets) - 1
     idx = np.full((len(queries), k), 0xFFFFFFFF, dtype=np.uint32)

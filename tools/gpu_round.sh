@@ -1,3 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:scan_jaro32 -s 2 -c 1 -f -o gpurun_out/prof_j32 python tools/bench_configs.py c4 > gpurun_out/ncu_j32.log 2>&1
+timeout 1200 python -m pytest tests -m gpu -x -q -k "extract" > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+tail -15 gpurun_out/pytest_gpu.log

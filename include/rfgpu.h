@@ -167,6 +167,26 @@ rf_status rf_cdist_topk_u8_device(const uint8_t* q_chars, const uint64_t* q_offs
                                   const rf_corpus* c, const rf_args* args, uint32_t k, uint32_t* idx_device,
                                   uint32_t* dist_device, void* stream);
 
+/* ---- packing and corpus files (host-side; the step before the scoring path).  The reference takes one iterator
+ * per candidate (levenshtein.rs:1750-1762); callers holding a Vec<String> pack it once:
+ *   rf_pack_u8: n strings given as (pointer, length) -> CSR offsets[n+1] (+ chars[offsets[n]] when chars_out != NULL;
+ *               call first with chars_out == NULL to size the buffer).  Parallel copy (nthreads <= 0: all cores).
+ *   corpus file: header + offsets (u32 when total < 2^32-16, else u64) + chars, 64-byte aligned sections, mapped
+ *               back with mmap -- the accessors' pointers can be passed to rf_corpus_create_u8[_off32] /
+ *               rf_batch_stream_* directly; rf_corpus_create_from_file does open + upload + close. */
+typedef struct rf_corpus_file rf_corpus_file;
+rf_status rf_pack_u8(const uint8_t* const* strings, const uint64_t* lengths, uint64_t n, uint64_t* offsets_out,
+                     uint8_t* chars_out, int nthreads);
+rf_status rf_corpus_file_write(const char* path, const uint8_t* chars, const uint64_t* offsets, uint64_t n);
+rf_status rf_corpus_file_open(const char* path, rf_corpus_file** out);
+rf_status rf_corpus_file_close(rf_corpus_file* f);
+uint64_t rf_corpus_file_size(const rf_corpus_file* f);
+uint64_t rf_corpus_file_total_chars(const rf_corpus_file* f);
+uint32_t rf_corpus_file_offset_width(const rf_corpus_file* f); /* 4 or 8: element type of rf_corpus_file_offsets */
+const void* rf_corpus_file_offsets(const rf_corpus_file* f);
+const uint8_t* rf_corpus_file_chars(const rf_corpus_file* f);
+rf_status rf_corpus_create_from_file(const char* path, int device, rf_corpus** out);
+
 /* ---- synthetic workload generator (SplitMix64, 62-symbol alphanumeric ASCII,
  * lengths uniform in [min_len,max_len], 1/64 of the candidates = query with <= kmax random edits).
  * Host-side utility used by bench.py and the tests; writes offsets[n+1] and, if chars != NULL, the bytes.

@@ -117,6 +117,7 @@ const char* rf_status_string(rf_status s) {
   return "unknown";
 }
 const char* rf_last_error(void) { return g_last_error.c_str(); }
+void rf__set_last_error(const char* msg) { g_last_error = msg ? msg : ""; }  // internal (rf_io.cpp)
 
 int rf_device_count(void) {
   int n = 0;

@@ -67,6 +67,16 @@ SYMBOLS = {
     "rf_batch_stream_f64_off32": (_int, [_vp, _vp, _vp, _u64, _int, _PA, _vp]),
     "rf_cdist_topk_u8": (_int, [_vp, _vp, _u32, _vp, _PA, _u32, _vp, _vp]),
     "rf_cdist_topk_u8_device": (_int, [_vp, _vp, _u32, _vp, _PA, _u32, _vp, _vp, _vp]),
+    "rf_pack_u8": (_int, [_vp, _vp, _u64, _vp, _vp, _int]),
+    "rf_corpus_file_write": (_int, [C.c_char_p, _vp, _vp, _u64]),
+    "rf_corpus_file_open": (_int, [C.c_char_p, C.POINTER(_vp)]),
+    "rf_corpus_file_close": (_int, [_vp]),
+    "rf_corpus_file_size": (_u64, [_vp]),
+    "rf_corpus_file_total_chars": (_u64, [_vp]),
+    "rf_corpus_file_offset_width": (_u32, [_vp]),
+    "rf_corpus_file_offsets": (_vp, [_vp]),
+    "rf_corpus_file_chars": (_vp, [_vp]),
+    "rf_corpus_create_from_file": (_int, [C.c_char_p, _int, C.POINTER(_vp)]),
     "rf_synth_query_u8": (_int, [_u64, _u32, _vp]),
     "rf_synth_corpus_u8": (_int, [_u64, _vp, _u32, _u64, _u32, _u32, _u32, _vp, _vp, _int]),
     "rf_kernel_launch_count": (_u64, []),

@@ -3,6 +3,7 @@
 New on this side: the reference consumes one candidate iterator per call
 (levenshtein.rs:1750-1762); here the candidates are uploaded once and scored by whole-corpus kernels."""
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -45,6 +46,16 @@ class Corpus:
         self.device = device
         return self
 
+    @classmethod
+    def from_file(cls, path, device=0):
+        """rf_corpus_create_from_file: map a corpus file (write_corpus_file) and upload it."""
+        self = cls.__new__(cls)
+        h = C.c_void_p()
+        _ffi.check(_ffi.lib().rf_corpus_create_from_file(os.fsencode(path), device, C.byref(h)))
+        self._h = h
+        self.device = device
+        return self
+
     def __len__(self):
         return int(_ffi.lib().rf_corpus_size(self._h))
 
@@ -62,6 +73,60 @@ class Corpus:
             self.close()
         except Exception:
             pass
+
+
+def pack_strings(strings, nthreads=0):
+    """rf_pack_u8: list of bytes/str -> (chars u8, offsets u64), copied in parallel by the C library."""
+    bs = [s.encode("latin-1") if isinstance(s, str) else bytes(s) for s in strings]
+    n = len(bs)
+    ptrs = (C.c_char_p * max(n, 1))(*bs) if n else (C.c_char_p * 1)()
+    lens = np.array([len(b) for b in bs], dtype=np.uint64)
+    offsets = np.empty(n + 1, dtype=np.uint64)
+    l = _ffi.lib()
+    _ffi.check(l.rf_pack_u8(C.cast(ptrs, C.c_void_p), lens.ctypes.data, n, offsets.ctypes.data, None, nthreads))
+    chars = np.empty(int(offsets[n]), dtype=np.uint8)
+    _ffi.check(l.rf_pack_u8(C.cast(ptrs, C.c_void_p), lens.ctypes.data, n, offsets.ctypes.data, chars.ctypes.data, nthreads))
+    return chars, offsets
+
+
+def write_corpus_file(path, chars, offsets):
+    """rf_corpus_file_write: CSR corpus -> a file that maps back without parsing (see include/rfgpu.h)."""
+    chars = np.ascontiguousarray(chars, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    _ffi.check(_ffi.lib().rf_corpus_file_write(os.fsencode(path), chars.ctypes.data, offsets.ctypes.data, len(offsets) - 1))
+
+
+class CorpusFile:
+    """rf_corpus_file_open: read-only mmap of a corpus file; .chars / .offsets are numpy views into the mapping
+    (valid until close()), usable with Corpus(...) and BatchComparator.stream(...)."""
+
+    def __init__(self, path):
+        h = C.c_void_p()
+        _ffi.check(_ffi.lib().rf_corpus_file_open(os.fsencode(path), C.byref(h)))
+        self._h = h
+        l = _ffi.lib()
+        self.n = int(l.rf_corpus_file_size(h))
+        self.total = int(l.rf_corpus_file_total_chars(h))
+        w = int(l.rf_corpus_file_offset_width(h))
+        odt = np.uint32 if w == 4 else np.uint64
+        self.offsets = np.ctypeslib.as_array(C.cast(l.rf_corpus_file_offsets(h), C.POINTER(C.c_uint32 if w == 4 else C.c_uint64)),
+                                             shape=(self.n + 1,)).view(odt)
+        if self.total:
+            self.chars = np.ctypeslib.as_array(C.cast(l.rf_corpus_file_chars(h), C.POINTER(C.c_uint8)), shape=(self.total,))
+        else:
+            self.chars = np.zeros(0, dtype=np.uint8)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.offsets = self.chars = None
+            _ffi.lib().rf_corpus_file_close(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
 
 
 def synth_query(seed, length):

@@ -337,6 +337,26 @@ def test_streaming_large_equals_resident():
     assert np.array_equal(s[:300000], exp)
 
 
+def test_corpus_file_to_gpu(tmp_path):
+    """Corpus file -> resident corpus (rf_corpus_create_from_file) and -> streaming scan straight from the mapping."""
+    q = rf.synth_query(4, 32)
+    chars, offsets = rf.synth_corpus(4, q, 50_000, 0, 64, 16)
+    path = str(tmp_path / "c.rfc")
+    rf.write_corpus_file(path, chars, offsets)
+    exp = orc.batch("levenshtein", "distance", q, chars, offsets, nthreads=0)
+    corpus = rf.Corpus.from_file(path)
+    assert len(corpus) == 50_000 and corpus.total_chars == len(chars)
+    assert np.array_equal(gpu_batch("levenshtein", "distance", q, corpus), exp)
+    corpus.close()
+    with rf.CorpusFile(path) as f:
+        assert np.array_equal(_stream("levenshtein", "distance", q, f.chars, f.offsets), exp)
+    strings = [bytes(chars[int(offsets[i]):int(offsets[i + 1])]) for i in range(2000)]
+    pc, po = rf.pack_strings(strings)
+    c2 = rf.Corpus(pc, po)
+    assert np.array_equal(gpu_batch("levenshtein", "distance", q, c2), exp[:2000])
+    c2.close()
+
+
 def _bc(metric, q):
     from rapidfuzz_b200._scorer import BatchComparatorBase
     return type("B", (BatchComparatorBase,), {"METRIC": metric})(q)

@@ -48,6 +48,12 @@ class Corpus {
     }
     return Corpus(chars.data(), offsets.data(), offsets.size() - 1, device);
   }
+  // corpus file written by rf_corpus_file_write (mmap + upload)
+  static Corpus from_file(const std::string& path, int device = 0) {
+    Corpus c;
+    check(rf_corpus_create_from_file(path.c_str(), device, &c.h_));
+    return c;
+  }
   Corpus(Corpus&& o) noexcept : h_(o.h_) { o.h_ = nullptr; }
   Corpus(const Corpus&) = delete;
   Corpus& operator=(const Corpus&) = delete;
@@ -56,7 +62,15 @@ class Corpus {
   const rf_corpus* handle() const { return h_; }
 
  private:
+  Corpus() = default;
   rf_corpus* h_ = nullptr;
+};
+
+// (candidate index, score) of the post-processing entry points
+template <class T>
+struct Hit {
+  uint32_t index;
+  T score;
 };
 
 struct NoScoreCutoff {};
@@ -104,6 +118,9 @@ rf_args to_c(const Args<T, C>& a) {
 }
 template <class T> struct Raw;
 template <> struct Raw<uint32_t> {
+  static rf_status extract(const rf_batch* b, const rf_corpus* c, rf_kind k, const rf_args* a, uint32_t kk, uint32_t* i, uint32_t* s, uint32_t* n) { return rf_batch_extract_u32(b, c, k, a, kk, i, s, n); }
+  static rf_status filter(const rf_batch* b, const rf_corpus* c, rf_kind k, const rf_args* a, uint64_t cap, uint32_t* i, uint32_t* s, uint64_t* n) { return rf_batch_filter_u32(b, c, k, a, cap, i, s, n); }
+  static rf_status stream(const rf_batch* b, const uint8_t* ch, const uint64_t* off, uint64_t n, rf_kind k, const rf_args* a, uint32_t* out) { return rf_batch_stream_u32(b, ch, off, n, k, a, out); }
   static std::vector<uint32_t> run(const rf_batch* b, const Corpus& c, rf_kind k, const rf_args& a) {
     std::vector<uint32_t> out(c.size());
     check(rf_batch_score_u32(b, c.handle(), k, &a, out.data()));
@@ -112,6 +129,9 @@ template <> struct Raw<uint32_t> {
   static bool none(uint32_t v) { return v == UINT32_MAX; }
 };
 template <> struct Raw<double> {
+  static rf_status extract(const rf_batch* b, const rf_corpus* c, rf_kind k, const rf_args* a, uint32_t kk, uint32_t* i, double* s, uint32_t* n) { return rf_batch_extract_f64(b, c, k, a, kk, i, s, n); }
+  static rf_status filter(const rf_batch* b, const rf_corpus* c, rf_kind k, const rf_args* a, uint64_t cap, uint32_t* i, double* s, uint64_t* n) { return rf_batch_filter_f64(b, c, k, a, cap, i, s, n); }
+  static rf_status stream(const rf_batch* b, const uint8_t* ch, const uint64_t* off, uint64_t n, rf_kind k, const rf_args* a, double* out) { return rf_batch_stream_f64(b, ch, off, n, k, a, out); }
   static std::vector<double> run(const rf_batch* b, const Corpus& c, rf_kind k, const rf_args& a) {
     std::vector<double> out(c.size());
     check(rf_batch_score_f64(b, c.handle(), k, &a, out.data()));
@@ -147,6 +167,39 @@ struct MetricModule {
     template <class C> auto similarity_with_args(const Corpus& c, const Args<IntT, C>& a) const { return wrap<IntT, C>(score<IntT>(c, RF_SIMILARITY, a)); }
     template <class C> auto normalized_distance_with_args(const Corpus& c, const Args<double, C>& a) const { return wrap<double, C>(score<double>(c, RF_NORMALIZED_DISTANCE, a)); }
     template <class C> auto normalized_similarity_with_args(const Corpus& c, const Args<double, C>& a) const { return wrap<double, C>(score<double>(c, RF_NORMALIZED_SIMILARITY, a)); }
+    // new on this side: the k best candidates by (score best-first, index), selected on the GPU; every candidate
+    // within the score_cutoff in index order; one-shot scoring of host-resident candidates (chunked PCIe pipeline).
+    // T = IntT for RF_DISTANCE / RF_SIMILARITY of the edit-distance metrics, double otherwise.
+    template <class T, class C>
+    std::vector<Hit<T>> extract(const Corpus& c, rf_kind kind, uint32_t k, const Args<T, C>& a) const {
+      std::vector<uint32_t> idx(k);
+      std::vector<T> sc(k);
+      uint32_t m = 0;
+      const rf_args ca = detail::to_c(a);
+      check(detail::Raw<T>::extract(h_, c.handle(), kind, &ca, k, idx.data(), sc.data(), &m));
+      std::vector<Hit<T>> out(m);
+      for (uint32_t i = 0; i < m; ++i) out[i] = {idx[i], sc[i]};
+      return out;
+    }
+    template <class T>
+    std::vector<Hit<T>> filter(const Corpus& c, rf_kind kind, const Args<T, WithScoreCutoff<T>>& a) const {
+      const rf_args ca = detail::to_c(a);
+      uint64_t total = 0;
+      check(detail::Raw<T>::filter(h_, c.handle(), kind, &ca, 0, nullptr, nullptr, &total));  // count, then fetch
+      std::vector<uint32_t> idx(total);
+      std::vector<T> sc(total);
+      if (total) check(detail::Raw<T>::filter(h_, c.handle(), kind, &ca, total, idx.data(), sc.data(), &total));
+      std::vector<Hit<T>> out(idx.size());
+      for (size_t i = 0; i < out.size(); ++i) out[i] = {idx[i], sc[i]};
+      return out;
+    }
+    template <class T, class C>
+    std::vector<T> stream(const uint8_t* chars, const uint64_t* offsets, uint64_t n, rf_kind kind, const Args<T, C>& a) const {
+      std::vector<T> out(n);
+      const rf_args ca = detail::to_c(a);
+      check(detail::Raw<T>::stream(h_, chars, offsets, n, kind, &ca, out.data()));
+      return out;
+    }
     // single-candidate forms, as in the reference's signatures
     IntT distance(std::string_view s2) const { return distance(one(s2))[0]; }
     IntT similarity(std::string_view s2) const { return similarity(one(s2))[0]; }

@@ -54,6 +54,18 @@ extern "C" {
     pub fn rf_cdist_topk_u8(q_chars: *const u8, q_offsets: *const u64, nq: u32, c: *const rf_corpus, args: *const rf_args,
                             k: u32, idx: *mut u32, dist: *mut u32) -> c_int;
     pub fn rf_set_option(name: *const c_char, value: c_int) -> c_int;
+    // one-shot scoring of host-resident candidates (chunked H2D / scan / D2H pipeline)
+    pub fn rf_batch_stream_u32(b: *const rf_batch, chars: *const u8, offsets: *const u64, n: u64, kind: c_int, args: *const rf_args, out: *mut u32) -> c_int;
+    pub fn rf_batch_stream_f64(b: *const rf_batch, chars: *const u8, offsets: *const u64, n: u64, kind: c_int, args: *const rf_args, out: *mut f64) -> c_int;
+    // post-processing on the GPU: k best by (score, index) / every candidate within the cutoff in index order
+    pub fn rf_batch_extract_u32(b: *const rf_batch, c: *const rf_corpus, kind: c_int, args: *const rf_args, k: u32, idx: *mut u32, score: *mut u32, n_out: *mut u32) -> c_int;
+    pub fn rf_batch_extract_f64(b: *const rf_batch, c: *const rf_corpus, kind: c_int, args: *const rf_args, k: u32, idx: *mut u32, score: *mut f64, n_out: *mut u32) -> c_int;
+    pub fn rf_batch_filter_u32(b: *const rf_batch, c: *const rf_corpus, kind: c_int, args: *const rf_args, capacity: u64, idx: *mut u32, score: *mut u32, n_hits: *mut u64) -> c_int;
+    pub fn rf_batch_filter_f64(b: *const rf_batch, c: *const rf_corpus, kind: c_int, args: *const rf_args, capacity: u64, idx: *mut u32, score: *mut f64, n_hits: *mut u64) -> c_int;
+    // packing + corpus files
+    pub fn rf_pack_u8(strings: *const *const u8, lengths: *const u64, n: u64, offsets_out: *mut u64, chars_out: *mut u8, nthreads: c_int) -> c_int;
+    pub fn rf_corpus_file_write(path: *const c_char, chars: *const u8, offsets: *const u64, n: u64) -> c_int;
+    pub fn rf_corpus_create_from_file(path: *const c_char, device: c_int, out: *mut *mut rf_corpus) -> c_int;
     #[allow(dead_code)]
     fn rf_kernel_launch_count() -> u64;
     #[allow(dead_code)]
@@ -88,6 +100,13 @@ impl Corpus {
         for s in candidates { chars.extend_from_slice(s.as_ref()); offsets.push(chars.len() as u64); }
         let mut h = std::ptr::null_mut();
         check(unsafe { rf_corpus_create_u8(chars.as_ptr(), offsets.as_ptr(), (offsets.len() - 1) as u64, device, &mut h) });
+        Corpus { h }
+    }
+    /// Corpus file written by `rf_corpus_file_write` (mmap + upload).
+    pub fn from_file(path: &std::path::Path, device: i32) -> Self {
+        let p = std::ffi::CString::new(path.to_string_lossy().as_bytes()).expect("path contains NUL");
+        let mut h = std::ptr::null_mut();
+        check(unsafe { rf_corpus_create_from_file(p.as_ptr(), device, &mut h) });
         Corpus { h }
     }
     pub fn len(&self) -> usize { unsafe { rf_corpus_size(self.h) as usize } }

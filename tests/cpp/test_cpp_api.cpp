@@ -38,6 +38,21 @@ int main() {
   EXPECT(std::fabs(fuzz::ratio("this is a test", "this is a test!") - 0.9655172) < 1e-6);   // fuzz.rs:94-96
   auto ns = sk.normalized_similarity_with_args(corpus, Args<double>{}.score_cutoff(0.5));
   EXPECT(ns[0].has_value() && std::fabs(*ns[0] - (1.0 - 2.0 / 11.0)) < 1e-12 && !ns[2].has_value());
+  // post-processing on the GPU + streaming from host memory
+  auto top = sk.extract<uint32_t>(corpus, RF_DISTANCE, 3, Args<uint32_t>{});
+  EXPECT(top.size() == 3 && top[0].index == 1 && top[0].score == 0 && top[1].index == 0 && top[1].score == 2 &&
+         top[2].index == 5 && top[2].score == 6);
+  auto within = sk.filter<uint32_t>(corpus, RF_DISTANCE, Args<uint32_t>{}.score_cutoff(6));
+  EXPECT(within.size() == 3 && within[0].index == 0 && within[1].index == 1 && within[2].index == 5 && within[2].score == 6);
+  auto best_sim = sk.extract<double>(corpus, RF_NORMALIZED_SIMILARITY, 1, Args<double>{});
+  EXPECT(best_sim.size() == 1 && best_sim[0].index == 1 && best_sim[0].score == 1.0);
+  {
+    std::vector<uint8_t> chars;
+    std::vector<uint64_t> offsets{0};
+    for (const auto& s : cands) { chars.insert(chars.end(), s.begin(), s.end()); offsets.push_back(chars.size()); }
+    auto ds = sk.stream<uint32_t>(chars.data(), offsets.data(), cands.size(), RF_DISTANCE, Args<uint32_t>{});
+    EXPECT(ds == d);
+  }
   bool threw = false;
   try { sk.distance_with_args(corpus, Args<uint32_t>{}.weights(1, 2, 3)); } catch (const Error& e) { threw = e.status == RF_ERR_UNSUPPORTED; }
   EXPECT(threw);

@@ -106,6 +106,37 @@ def cdist(nq, n, k=10, steps=2):
     corpus.close()
 
 
+def extract_filter(n):
+    """config-2 shape: scan + on-device top-10 / cutoff compaction, host wall clock (includes the k-entry D2H)."""
+    q = rf.synth_query(2, 32)
+    chars, offsets = rf.synth_corpus(2, q, n, 8, 64, 16)
+    corpus = rf.Corpus(chars, offsets)
+    b = type("B", (rf._scorer.BatchComparatorBase,), {"METRIC": "levenshtein"})(q)
+    exp = orc.batch("levenshtein", "distance", q, chars, offsets, nthreads=0)
+    order = np.lexsort((np.arange(n), exp))[:10]
+
+    def wall(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            r = fn()
+        return (time.perf_counter() - t0) / reps * 1e3, r
+    ms_x, (gi, gs) = wall(lambda: b.extract("distance", corpus, k=10))
+    ok_x = bool(np.array_equal(gi, order.astype(np.uint32)) and np.array_equal(gs, exp[order]))
+    a = rf.Args().score_cutoff(8)
+    ms_f, (fi, fs, tot) = wall(lambda: b.filter("distance", corpus, a, capacity=1 << 22))
+    hits = np.nonzero(exp <= 8)[0]
+    ok_f = bool(tot == len(hits) and np.array_equal(fi, hits[: 1 << 22].astype(np.uint32)))
+    out = np.empty(n, dtype=np.uint32)
+    ms_full, _ = wall(lambda: _ffi.check(L.rf_batch_score_u32(b._h, corpus._h, 0, None, out.ctypes.data)))
+    print(json.dumps({"config": "C2-shape post-processing", "n": n, "extract_top10_ms": ms_x, "extract_matches_oracle": ok_x,
+                      "filter_cutoff8_ms": ms_f, "filter_hits": int(tot), "filter_matches_oracle": ok_f,
+                      "full_scores_to_pageable_host_ms": ms_full}), flush=True)
+    b.close()
+    corpus.close()
+
+
 if __name__ == "__main__":
     which = sys.argv[1].split(",") if len(sys.argv) > 1 else ["c2w", "c3", "c4", "c5"]
     if "c2w" in which:  # config 2 with a 64-element query (64-bit words)
@@ -119,6 +150,8 @@ if __name__ == "__main__":
                     lambda l: l + 12, tol=1e-6)
     if "c5" in which:
         cdist(int(1e4 * scale), int(1.25e6))
+    if "post" in which:
+        extract_filter(int(1e8 * scale))
     for extra in which:
         if extra in ("indel", "lcs_seq", "osa", "jaro"):
             kind = "similarity" if extra in ("lcs_seq", "jaro") else "distance"

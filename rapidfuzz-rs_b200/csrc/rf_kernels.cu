@@ -1171,8 +1171,7 @@ cudaError_t launch_scan_lbr(const ScanLaunch& L) {
 // memory (1 KB read, ~2% of the slice's scan time), scans its slice with the same per-lane kernel as the
 // one-vs-many path, and extracts its k best (distance, index) keys; a second kernel merges the per-CTA
 // candidates of every query.  The shard is read from HBM once and then served from L2.
-constexpr int CD_NT = 256;
-constexpr int CD_KEYCAP = 4096;   // keys scored per extraction batch
+constexpr int CD_NT = 512;  // 2 CTAs / SM (cdist_parts) x 16 warps: 8 warps per scheduler
 constexpr int CD_KMAX = 128;
 constexpr unsigned long long CD_NOKEY = 0xFFFFFFFFFFFFFFFFull;
 
@@ -1221,13 +1220,60 @@ __device__ __forceinline__ void cd_extract(unsigned long long* keys, uint32_t m,
   __syncthreads();
 }
 
-template <class W>
+// A warp's running k-best list, ascending, held in registers: slot i = 32*r + lane lives in v[r] of that lane
+// (KR = ceil(k/32) registers of 64 bits per lane).  Inserting a key is warp-cooperative: count the slots below it
+// with ballots, shift the rest up by one slot with shuffles.  No shared memory, no CTA barrier while a CTA scans
+// its slice; with random data a warp inserts O(k log(n/k)) of the n keys it sees.
+template <int KR>
+struct WarpTopK {
+  unsigned long long v[KR];
+  unsigned long long kth;  // value of slot k-1 (warp-uniform): only keys below it can enter
+  __device__ __forceinline__ void reset() {
+#pragma unroll
+    for (int r = 0; r < KR; ++r) v[r] = CD_NOKEY;
+    kth = CD_NOKEY;
+  }
+  __device__ __forceinline__ void insert(unsigned long long key, uint32_t k, uint32_t lane) {  // key < kth, keys are unique
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int r = 0; r < KR; ++r) cnt += __popc(__ballot_sync(0xffffffffu, v[r] < key));
+#pragma unroll
+    for (int r = KR - 1; r >= 0; --r) {
+      const uint32_t i = (uint32_t)r * 32u + lane;
+      unsigned long long below = __shfl_up_sync(0xffffffffu, v[r], 1);
+      if (r > 0) {
+        const unsigned long long prev_top = __shfl_sync(0xffffffffu, v[r - 1], 31);
+        if (lane == 0) below = prev_top;
+      }
+      unsigned long long nv = (i < cnt) ? v[r] : (i == cnt ? key : below);
+      if (i >= k) nv = CD_NOKEY;
+      v[r] = nv;
+    }
+    unsigned long long t = v[0];
+#pragma unroll
+    for (int r = 1; r < KR; ++r) t = ((k - 1) / 32 == (uint32_t)r) ? v[r] : t;  // no dynamic register indexing
+    kth = __shfl_sync(0xffffffffu, t, (k - 1) & 31);
+  }
+  // the 32 keys of one scored group (one per lane)
+  __device__ __forceinline__ void offer(unsigned long long key, uint32_t k, uint32_t lane) {
+    uint32_t m = __ballot_sync(0xffffffffu, key < kth);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const unsigned long long kk = __shfl_sync(0xffffffffu, key, src);
+      if (kk < kth) insert(kk, k, lane);  // kth may have dropped since the ballot
+    }
+  }
+};
+
+template <class W, int KR>
 __global__ void __launch_bounds__(CD_NT) cdist_scan_kernel(const __grid_constant__ CdistParams p) {
+  constexpr int NW = CD_NT / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   W* pm = reinterpret_cast<W*>(smem_raw);
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw + sizeof(W) * 8192);  // CD_KEYCAP + CD_KMAX
-  unsigned long long* best = keys + CD_KEYCAP + CD_KMAX;                                           // CD_KMAX
-  unsigned long long* wmin = best + CD_KMAX;                                                       // CD_NT/32
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw + sizeof(W) * 8192);  // NW * k
+  unsigned long long* best = keys + NW * CD_KMAX;                                                  // CD_KMAX
+  unsigned long long* wmin = best + CD_KMAX;                                                       // NW
   __shared__ uint64_t s_glo, s_ghi;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint64_t ngroups = p.lb.ngroups;
@@ -1250,43 +1296,62 @@ __global__ void __launch_bounds__(CD_NT) cdist_scan_kernel(const __grid_constant
   const uint64_t g_lo = s_glo, g_hi = s_ghi;
   const W* __restrict__ pm_lane = pm + lane;
   const uint2* __restrict__ gdata = reinterpret_cast<const uint2*>(p.lb.gdata);
-  constexpr uint32_t GPB = CD_KEYCAP / 32;  // groups per extraction batch
+  const uint32_t k = p.k;
   for (uint32_t q = 0; q < p.nq; ++q) {
     __syncthreads();
     {
       const W* __restrict__ t = reinterpret_cast<const W*>(p.tabs) + (size_t)q * 256;
       for (uint32_t i = tid; i < 8192u; i += CD_NT) pm[i] = t[i >> 5];
-      for (uint32_t i = tid; i < p.k; i += CD_NT) best[i] = CD_NOKEY;
     }
     __syncthreads();
     const uint32_t len1 = p.q_len[q];
-    for (uint64_t gb = g_lo; gb < g_hi; gb += GPB) {
-      const uint64_t ge = (gb + GPB < g_hi) ? gb + GPB : g_hi;
-      for (uint64_t g = gb + warp; g < ge; g += CD_NT / 32) {
-        const uint32_t len2 = __ldg(p.lb.lens + g * 32 + lane);
-        const uint32_t idx = __ldg(p.lb.perm + g * 32 + lane);
-        const uint64_t r = __ldg(p.lb.goff + g);
-        const uint2* col = gdata + r * 32 + lane;
-        const LaneSrcT<false> src{col, __ldg(col), __ldg(col + 32)};
-        uint32_t d;
-        if (len1 == 0) d = len2;
-        else if constexpr (sizeof(W) == 4) d = lev_w1_u32_fast(smem_u32(pm_lane), src.reader(), len2, len1, p.two);
-        else {
-          auto tab = [&](uint32_t ch) -> W { return pm_lane[ch * 32u]; };
-          d = lev_w1<W>(tab, src.reader(), len2, len1);
-        }
-        const bool ok = idx != 0xFFFFFFFFu && !(p.has_cutoff && d > p.cutoff);
-        keys[(uint32_t)(g - gb) * 32 + lane] = ok ? (((unsigned long long)d << 32) | idx) : CD_NOKEY;
-      }
-      __syncthreads();
-      // merge with the running best of earlier batches, then keep the k smallest
-      const uint32_t m = (uint32_t)(ge - gb) * 32;
-      for (uint32_t i = tid; i < p.k; i += CD_NT) keys[m + i] = best[i];
-      __syncthreads();
-      cd_extract(keys, m + p.k, best, p.k, wmin);
+    WarpTopK<KR> top;
+    top.reset();
+    // the warps take the slice's groups round-robin (neighbouring groups have similar lengths); software pipeline:
+    // the next group's length / index / first two rows are requested (L2 hits: the shard is resident) before
+    // the current group is scored
+    uint64_t g = g_lo + warp;
+    uint32_t len_n = 0, idx_n = 0;
+    const uint2* col_n = gdata;
+    uint2 first_n = make_uint2(0u, 0u), second_n = make_uint2(0u, 0u);
+    if (g < g_hi) {
+      len_n = __ldg(p.lb.lens + g * 32 + lane);
+      idx_n = __ldg(p.lb.perm + g * 32 + lane);
+      col_n = gdata + __ldg(p.lb.goff + g) * 32 + lane;
+      first_n = __ldg(col_n);
+      second_n = __ldg(col_n + 32);
     }
-    unsigned long long* out = p.scratch + ((size_t)q * gridDim.x + blockIdx.x) * p.k;
-    for (uint32_t i = tid; i < p.k; i += CD_NT) out[i] = best[i];
+    for (; g < g_hi; g += NW) {
+      const uint32_t len2 = len_n, idx = idx_n;
+      const LaneSrcT<false> src{col_n, first_n, second_n};
+      const uint64_t gn = g + NW;
+      if (gn < g_hi) {
+        len_n = __ldg(p.lb.lens + gn * 32 + lane);
+        idx_n = __ldg(p.lb.perm + gn * 32 + lane);
+        col_n = gdata + __ldg(p.lb.goff + gn) * 32 + lane;
+        first_n = __ldg(col_n);
+        second_n = __ldg(col_n + 32);
+      }
+      uint32_t d;
+      if (len1 == 0) d = len2;
+      else if constexpr (sizeof(W) == 4) d = lev_w1_u32_fast(smem_u32(pm_lane), src.reader(), len2, len1, p.two);
+      else {
+        auto tab = [&](uint32_t ch) -> W { return pm_lane[ch * 32u]; };
+        d = lev_w1<W>(tab, src.reader(), len2, len1);
+      }
+      const bool ok = idx != 0xFFFFFFFFu && !(p.has_cutoff && d > p.cutoff);
+      top.offer(ok ? (((unsigned long long)d << 32) | idx) : CD_NOKEY, k, lane);
+    }
+    // the NW warp lists -> the CTA's k best of this query
+#pragma unroll
+    for (int r = 0; r < KR; ++r) {
+      const uint32_t i = (uint32_t)r * 32u + lane;
+      if (i < k) keys[warp * k + i] = top.v[r];
+    }
+    __syncthreads();
+    cd_extract(keys, NW * k, best, k, wmin);
+    unsigned long long* out = p.scratch + ((size_t)q * gridDim.x + blockIdx.x) * k;
+    for (uint32_t i = tid; i < k; i += CD_NT) out[i] = best[i];
   }
 }
 
@@ -1327,17 +1392,18 @@ cudaError_t launch_cdist_topk(const CdistLaunch& L) {
   p.two = 2;
   const uint32_t parts = L.parts;
   const size_t wsz = L.wide ? 8 : 4;
-  const size_t smem = wsz * 8192 + sizeof(unsigned long long) * (CD_KEYCAP + CD_KMAX + CD_KMAX + CD_NT / 32);
+  const size_t smem = wsz * 8192 + sizeof(unsigned long long) * ((CD_NT / 32) * CD_KMAX + CD_KMAX + CD_NT / 32);
   cudaError_t e;
-  if (L.wide) {
-    e = cudaFuncSetAttribute(cdist_scan_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    cdist_scan_kernel<uint64_t><<<parts, CD_NT, smem, L.stream>>>(p);
-  } else {
-    e = cudaFuncSetAttribute(cdist_scan_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    cdist_scan_kernel<uint32_t><<<parts, CD_NT, smem, L.stream>>>(p);
-  }
+  auto launch = [&](auto kern) -> cudaError_t {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    kern<<<parts, CD_NT, smem, L.stream>>>(p);
+    return cudaGetLastError();
+  };
+  const int kr = L.k <= 32 ? 1 : (L.k <= 64 ? 2 : 4);
+  if (L.wide) e = kr == 1 ? launch(cdist_scan_kernel<uint64_t, 1>) : kr == 2 ? launch(cdist_scan_kernel<uint64_t, 2>) : launch(cdist_scan_kernel<uint64_t, 4>);
+  else e = kr == 1 ? launch(cdist_scan_kernel<uint32_t, 1>) : kr == 2 ? launch(cdist_scan_kernel<uint32_t, 2>) : launch(cdist_scan_kernel<uint32_t, 4>);
+  if (e != cudaSuccess) return e;
   g_launches.fetch_add(1);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;

@@ -86,6 +86,9 @@ rf_status rf_corpus_create_u8_off32(const uint8_t* chars, const uint32_t* offset
 /* buffers already on `device` (copied device-to-device on `stream`) */
 rf_status rf_corpus_create_device_u8(const uint8_t* d_chars, const uint64_t* d_offsets, uint64_t n,
                                      uint64_t total_chars, int device, void* stream, rf_corpus** out);
+/* u32 elements (Rust `char`, u32: the reference accepts any HashableChar, details/common.rs:29-37).  Such a
+ * corpus is scored by comparators made with rf_batch_create_u32; results are exact (see there). */
+rf_status rf_corpus_create_u32(const uint32_t* elems, const uint64_t* offsets, uint64_t n, int device, rf_corpus** out);
 rf_status rf_corpus_destroy(rf_corpus* c);
 uint64_t rf_corpus_size(const rf_corpus* c);        /* number of candidates */
 uint64_t rf_corpus_total_chars(const rf_corpus* c); /* sum of candidate lengths */
@@ -95,6 +98,12 @@ int rf_corpus_device(const rf_corpus* c);
  * (levenshtein.rs:1645-1657, pattern_match_vector.rs:203-281). */
 rf_status rf_batch_create_u8(rf_metric metric, const uint8_t* query, uint32_t query_len, int device,
                              rf_batch** out);
+/* u32-element query.  Its distinct symbols (at most 255, else RF_ERR_UNSUPPORTED) are renamed to bytes and every
+ * scoring call renames the candidates on the device first (symbols absent from the query -> a byte that matches
+ * nothing).  All metrics of this library depend only on which query/candidate positions hold equal symbols, so
+ * the scores are identical to the reference's hashmap-based lookup (pattern_match_vector.rs:20-65, :226-280).
+ * Works against u8 and u32 corpora; costs one extra pass over the candidates per call. */
+rf_status rf_batch_create_u32(rf_metric metric, const uint32_t* query, uint32_t query_len, int device, rf_batch** out);
 rf_status rf_batch_destroy(rf_batch* b);
 
 /* ---- scoring: one call == the user's loop `for c in candidates { scorer.<kind>_with_args(c, &args) }`.

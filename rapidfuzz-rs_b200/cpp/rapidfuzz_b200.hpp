@@ -48,6 +48,12 @@ class Corpus {
     }
     return Corpus(chars.data(), offsets.data(), offsets.size() - 1, device);
   }
+  // u32 elements (code points); scored by comparators built from std::u32string_view queries
+  static Corpus from_u32(const uint32_t* elems, const uint64_t* offsets, uint64_t n, int device = 0) {
+    Corpus c;
+    check(rf_corpus_create_u32(elems, offsets, n, device, &c.h_));
+    return c;
+  }
   // corpus file written by rf_corpus_file_write (mmap + upload)
   static Corpus from_file(const std::string& path, int device = 0) {
     Corpus c;
@@ -152,6 +158,9 @@ struct MetricModule {
    public:
     explicit BatchComparator(std::string_view query, int device = 0) : device_(device) {
       check(rf_batch_create_u8(M, reinterpret_cast<const uint8_t*>(query.data()), (uint32_t)query.size(), device, &h_));
+    }
+    explicit BatchComparator(std::u32string_view query, int device = 0) : device_(device) {  // char / u32 elements
+      check(rf_batch_create_u32(M, reinterpret_cast<const uint32_t*>(query.data()), (uint32_t)query.size(), device, &h_));
     }
     BatchComparator(BatchComparator&& o) noexcept : h_(o.h_), device_(o.device_) { o.h_ = nullptr; }
     BatchComparator(const BatchComparator&) = delete;

@@ -82,7 +82,8 @@ static unsigned long long* counter_slot(int device) {
 struct rf_corpus {
   int device = 0;
   uint64_t n = 0, total = 0;
-  uint8_t* d_chars = nullptr;
+  uint8_t* d_chars = nullptr;     // u8 elements ...
+  uint32_t* d_elems32 = nullptr;  // ... or u32 elements (rf_corpus_create_u32); exactly one of the two is set
   uint32_t* d_off32 = nullptr;
   uint64_t* d_off64 = nullptr;
   LbAlloc lb;  // length-bucketed interleaved copy for the single-word kernels
@@ -95,6 +96,12 @@ struct rf_batch {
   uint32_t len1 = 0, words = 0;
   uint8_t* d_blob = nullptr;  // all tables in one allocation
   QueryView view{};
+  // rf_batch_create_u32: the query's distinct symbols are renamed to the bytes 1..D (D <= 255); candidates are
+  // renamed on the device per scoring call (symbols the query does not contain become 0, which matches nothing).
+  // Every metric here depends only on which (query, candidate) positions are equal, so the result is exact.
+  bool wide = false;
+  uint32_t* d_alpha_keys = nullptr;  // [kAlphaSlots] open-addressing table: symbol ...
+  uint8_t* d_alpha_codes = nullptr;  // ... -> byte code, 0 = empty slot
 };
 
 extern "C" {
@@ -270,11 +277,58 @@ rf_status rf_corpus_create_device_u8(const uint8_t* d_chars, const uint64_t* d_o
   return RF_OK;
 }
 
+rf_status rf_corpus_create_u32(const uint32_t* elems, const uint64_t* offsets, uint64_t n, int device, rf_corpus** out) {
+  if (!out) return fail(RF_ERR_INVALID_ARG, "out is NULL");
+  *out = nullptr;
+  if (!offsets) return fail(RF_ERR_INVALID_ARG, "offsets is NULL");
+  if (n >= 0xFFFFFFFFull) return fail(RF_ERR_UNSUPPORTED, "more than 2^32-2 candidates in one corpus");
+  if (offsets[0] != 0) return fail(RF_ERR_INVALID_ARG, "offsets[0] must be 0");
+  const uint64_t total = offsets[n];
+  if (total && !elems) return fail(RF_ERR_INVALID_ARG, "elems is NULL");
+  if (rf_device_count() <= device || device < 0) return fail(RF_ERR_CUDA, "no such CUDA device");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(RF_ERR_CUDA, "cudaSetDevice failed");
+  rf_corpus* c = new (std::nothrow) rf_corpus();
+  if (!c) return fail(RF_ERR_OOM, "host allocation failed");
+  c->device = device;
+  c->n = n;
+  c->total = total;
+  const bool off64 = total >= 0xFFFFFFF0ull;
+  cudaStream_t st = util_stream(device);
+  cudaError_t e = dev_alloc(&c->d_elems32, (total + 16) * sizeof(uint32_t), st);
+  if (e == cudaSuccess) e = off64 ? dev_alloc(&c->d_off64, (n + 1 + 16) * sizeof(uint64_t), st)
+                                  : dev_alloc(&c->d_off32, (n + 1 + 16) * sizeof(uint32_t), st);
+  uint64_t* tmp64 = nullptr;
+  if (e == cudaSuccess && total) e = cudaMemcpyAsync(c->d_elems32, elems, total * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) {
+    if (off64) e = cudaMemcpyAsync(c->d_off64, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, st);
+    else {
+      e = dev_alloc(&tmp64, (n + 1) * 8, st);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(tmp64, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, st);
+      if (e == cudaSuccess) {
+        narrow_offsets<<<1024, 256, 0, st>>>(tmp64, c->d_off32, n + 1);
+        e = cudaGetLastError();
+      }
+    }
+  }
+  if (e == cudaSuccess) {
+    if (c->d_off32) fill_tail_u32<<<1, 16, 0, st>>>(c->d_off32, n + 1, (uint32_t)total);
+    else fill_tail_u64<<<1, 16, 0, st>>>(c->d_off64, n + 1, total);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  dev_free(tmp64, st);
+  if (e != cudaSuccess) { rf_corpus_destroy(c); return cuda_fail(e, "u32 corpus upload"); }
+  *out = c;
+  return RF_OK;
+}
+
 rf_status rf_corpus_destroy(rf_corpus* c) {
   if (!c) return RF_OK;
   DeviceGuard g(c->device);
   cudaStream_t st = util_stream(c->device);
   dev_free(c->d_chars, st);
+  dev_free(c->d_elems32, st);
   dev_free(c->d_off32, st);
   dev_free(c->d_off64, st);
   lb_free(&c->lb, st);
@@ -286,7 +340,12 @@ uint64_t rf_corpus_total_chars(const rf_corpus* c) { return c ? c->total : 0; }
 int rf_corpus_device(const rf_corpus* c) { return c ? c->device : -1; }
 
 // ------------------------------------------------------------------------------------------------ batch
-rf_status rf_batch_create_u8(rf_metric metric, const uint8_t* query, uint32_t query_len, int device, rf_batch** out) {
+}  // extern "C"
+
+static constexpr uint32_t kAlphaSlots = 1024;
+static inline uint32_t alpha_hash(uint32_t x) { return (x * 2654435761u) >> 22; }  // 10 bits
+
+static rf_status batch_create_bytes(rf_metric metric, const uint8_t* query, uint32_t query_len, int device, rf_batch** out) {
   if (!out) return fail(RF_ERR_INVALID_ARG, "out is NULL");
   *out = nullptr;
   if ((int)metric < 0 || (int)metric > (int)RF_RATIO) return fail(RF_ERR_INVALID_ARG, "unknown metric");
@@ -355,10 +414,50 @@ rf_status rf_batch_create_u8(rf_metric metric, const uint8_t* query, uint32_t qu
   return RF_OK;
 }
 
+extern "C" {
+
+rf_status rf_batch_create_u8(rf_metric metric, const uint8_t* query, uint32_t query_len, int device, rf_batch** out) {
+  return batch_create_bytes(metric, query, query_len, device, out);
+}
+
+rf_status rf_batch_create_u32(rf_metric metric, const uint32_t* query, uint32_t query_len, int device, rf_batch** out) {
+  if (!out) return fail(RF_ERR_INVALID_ARG, "out is NULL");
+  *out = nullptr;
+  if (query_len && !query) return fail(RF_ERR_INVALID_ARG, "query is NULL");
+  if (query_len > RF_MAX_QUERY_LEN) return fail(RF_ERR_UNSUPPORTED, "query longer than RF_MAX_QUERY_LEN");
+  std::vector<uint32_t> keys(kAlphaSlots, 0);
+  std::vector<uint8_t> codes(kAlphaSlots, 0), renamed(query_len);
+  uint32_t distinct = 0;
+  for (uint32_t i = 0; i < query_len; ++i) {
+    uint32_t slot = alpha_hash(query[i]);
+    while (codes[slot] && keys[slot] != query[i]) slot = (slot + 1) & (kAlphaSlots - 1);
+    if (!codes[slot]) {
+      if (distinct == 255) return fail(RF_ERR_UNSUPPORTED, "u32 query with more than 255 distinct symbols");
+      keys[slot] = query[i];
+      codes[slot] = (uint8_t)++distinct;
+    }
+    renamed[i] = codes[slot];
+  }
+  rf_batch* b = nullptr;
+  rf_status s = batch_create_bytes(metric, renamed.data(), query_len, device, &b);
+  if (s != RF_OK) return s;
+  DeviceGuard g(device);
+  b->wide = true;
+  cudaError_t e = cudaMalloc(&b->d_alpha_keys, kAlphaSlots * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&b->d_alpha_codes, kAlphaSlots);
+  if (e == cudaSuccess) e = cudaMemcpy(b->d_alpha_keys, keys.data(), kAlphaSlots * sizeof(uint32_t), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(b->d_alpha_codes, codes.data(), kAlphaSlots, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { rf_batch_destroy(b); return cuda_fail(e, "alphabet upload"); }
+  *out = b;
+  return RF_OK;
+}
+
 rf_status rf_batch_destroy(rf_batch* b) {
   if (!b) return RF_OK;
   DeviceGuard g(b->device);
   if (b->d_blob) cudaFree(b->d_blob);
+  if (b->d_alpha_keys) cudaFree(b->d_alpha_keys);
+  if (b->d_alpha_codes) cudaFree(b->d_alpha_codes);
   delete b;
   return RF_OK;
 }
@@ -443,9 +542,66 @@ static rf_status score_view(const rf_batch* b, const CorpusView& cv, const LbAll
   return RF_OK;
 }
 
+}  // extern "C"
+
+// candidates' symbols -> the query's byte alphabet (see rf_batch::wide); 4 elements per thread, table in shared memory
+template <class In>
+__global__ void __launch_bounds__(256) remap_kernel(const In* __restrict__ in, uint64_t total, const uint32_t* __restrict__ keys,
+                                                    const uint8_t* __restrict__ codes, uint32_t* __restrict__ out4) {
+  __shared__ uint32_t skeys[1024];
+  __shared__ uint8_t scodes[1024];
+  for (uint32_t i = threadIdx.x; i < 1024; i += 256) { skeys[i] = keys[i]; scodes[i] = codes[i]; }
+  __syncthreads();
+  const uint64_t nquads = (total + 3) / 4;
+  for (uint64_t qd = (uint64_t)blockIdx.x * 256 + threadIdx.x; qd < nquads; qd += (uint64_t)gridDim.x * 256) {
+    uint32_t packed = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint64_t i = qd * 4 + j;
+      uint32_t code = 0;
+      if (i < total) {
+        const uint32_t x = (uint32_t)in[i];
+        uint32_t slot = (x * 2654435761u) >> 22;
+        while (scodes[slot] && skeys[slot] != x) slot = (slot + 1) & 1023u;
+        code = scodes[slot];
+      }
+      packed |= code << (8 * j);
+    }
+    out4[qd] = packed;
+  }
+}
+
+extern "C" {
+
 static rf_status score_device(const rf_batch* b, const rf_corpus* c, rf_kind kind, const rf_args* args, void* out_dev,
                               bool want_f64, cudaStream_t st) {
   if (!b || !c) return fail(RF_ERR_INVALID_ARG, "NULL handle");
+  if (c->d_elems32 && !b->wide)
+    return fail(RF_ERR_INVALID_ARG, "a u32 corpus needs a comparator created with rf_batch_create_u32");
+  if (b->wide) {
+    if (b->device != c->device) return fail(RF_ERR_INVALID_ARG, "batch and corpus live on different devices");
+    if (c->n == 0) return RF_OK;
+    DeviceGuard g(c->device);
+    if (!g.ok) return fail(RF_ERR_CUDA, "cudaSetDevice failed");
+    uint8_t* d_bytes = nullptr;
+    const uint64_t padded = (c->total + 3) / 4 * 4;
+    cudaError_t e = dev_alloc(&d_bytes, padded + 64, st);
+    if (e != cudaSuccess) return cuda_fail(e, "renamed candidates");
+    e = cudaMemsetAsync(d_bytes + padded, 0, 64, st);
+    if (e == cudaSuccess && c->total) {
+      const uint64_t blocks = ((c->total + 3) / 4 + 255) / 256;
+      const uint32_t grid = (uint32_t)(blocks < 148 * 16 ? blocks : 148 * 16);
+      if (c->d_elems32) remap_kernel<uint32_t><<<grid, 256, 0, st>>>(c->d_elems32, c->total, b->d_alpha_keys, b->d_alpha_codes, (uint32_t*)d_bytes);
+      else remap_kernel<uint8_t><<<grid, 256, 0, st>>>(c->d_chars, c->total, b->d_alpha_keys, b->d_alpha_codes, (uint32_t*)d_bytes);
+      e = cudaGetLastError();
+      rfk::count_launches(1);
+    }
+    rf_status s = (e == cudaSuccess) ? score_view(b, CorpusView{d_bytes, c->d_off32, c->d_off64, c->n, c->total}, nullptr, c->device,
+                                                  kind, args, out_dev, want_f64, st)
+                                     : cuda_fail(e, "alphabet renaming");
+    dev_free(d_bytes, st);
+    return s;
+  }
   return score_view(b, CorpusView{c->d_chars, c->d_off32, c->d_off64, c->n, c->total}, &c->lb, c->device, kind, args,
                     out_dev, want_f64, st);
 }

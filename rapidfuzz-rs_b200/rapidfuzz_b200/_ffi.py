@@ -40,11 +40,13 @@ SYMBOLS = {
     "rf_corpus_create_u8": (_int, [_vp, _vp, _u64, _int, C.POINTER(_vp)]),
     "rf_corpus_create_u8_off32": (_int, [_vp, _vp, _u64, _int, C.POINTER(_vp)]),
     "rf_corpus_create_device_u8": (_int, [_vp, _vp, _u64, _u64, _int, _vp, C.POINTER(_vp)]),
+    "rf_corpus_create_u32": (_int, [_vp, _vp, _u64, _int, C.POINTER(_vp)]),
     "rf_corpus_destroy": (_int, [_vp]),
     "rf_corpus_size": (_u64, [_vp]),
     "rf_corpus_total_chars": (_u64, [_vp]),
     "rf_corpus_device": (_int, [_vp]),
     "rf_batch_create_u8": (_int, [_int, _vp, _u32, _int, C.POINTER(_vp)]),
+    "rf_batch_create_u32": (_int, [_int, _vp, _u32, _int, C.POINTER(_vp)]),
     "rf_batch_destroy": (_int, [_vp]),
     "rf_batch_score_u32": (_int, [_vp, _vp, _int, _PA, _vp]),
     "rf_batch_score_f64": (_int, [_vp, _vp, _int, _PA, _vp]),

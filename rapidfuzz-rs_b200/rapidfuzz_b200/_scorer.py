@@ -73,10 +73,15 @@ class Args:
 
 def _as_query(q):
     if isinstance(q, str):
+        if any(ord(ch) > 255 for ch in q):   # code points, like Rust's .chars(): u32-element comparator
+            return np.fromiter((ord(ch) for ch in q), dtype=np.uint32, count=len(q))
         q = q.encode("latin-1")
     if isinstance(q, (bytes, bytearray)):
         return np.frombuffer(bytes(q), dtype=np.uint8)
-    return np.ascontiguousarray(q, dtype=np.uint8)
+    q = np.ascontiguousarray(q)
+    if q.dtype == np.uint32:
+        return q
+    return q.astype(np.uint8)
 
 
 class BatchComparatorBase:
@@ -88,7 +93,8 @@ class BatchComparatorBase:
     def __init__(self, query, device=0):
         q = _as_query(query)
         h = C.c_void_p()
-        _ffi.check(_ffi.lib().rf_batch_create_u8(_ffi.METRICS[self.METRIC], q.ctypes.data, len(q), device, C.byref(h)))
+        create = _ffi.lib().rf_batch_create_u32 if q.dtype == np.uint32 else _ffi.lib().rf_batch_create_u8
+        _ffi.check(create(_ffi.METRICS[self.METRIC], q.ctypes.data, len(q), device, C.byref(h)))
         self._h = h
         self.device = device
         self.query = q
@@ -107,7 +113,20 @@ class BatchComparatorBase:
     def _score(self, kind, s2, args):
         args = args if args is not None else Args()
         single = not isinstance(s2, Corpus)
-        corpus = Corpus.from_strings([s2], self.device) if single else s2
+        if single:
+            wide = (isinstance(s2, str) and any(ord(ch) > 255 for ch in s2)) or (isinstance(s2, np.ndarray) and s2.dtype == np.uint32)
+            if wide and self.query.dtype != np.uint32:   # a byte query still has to meet the candidate's symbols
+                other = type(self)(self.query.astype(np.uint32), self.device)
+                try:
+                    return other._score(kind, s2, args)
+                finally:
+                    other.close()
+            if isinstance(s2, np.ndarray) and s2.dtype == np.uint32:
+                corpus = Corpus.from_u32(s2, np.array([0, len(s2)], dtype=np.uint64), self.device)
+            else:
+                corpus = Corpus.from_unicode([s2], self.device) if wide else Corpus.from_strings([s2], self.device)
+        else:
+            corpus = s2
         is_f = bool(_ffi.lib().rf_result_is_float(_ffi.METRICS[self.METRIC], _ffi.KINDS[kind]))
         ca = args._c(is_f)
         n = len(corpus)

@@ -28,6 +28,29 @@ class Corpus:
         self.device = device
 
     @classmethod
+    def from_u32(cls, elems, offsets, device=0):
+        """rf_corpus_create_u32: candidates with u32 elements (e.g. Unicode code points); needs comparators created
+        from u32 / non-latin-1 queries."""
+        elems = np.ascontiguousarray(elems, dtype=np.uint32)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        self = cls.__new__(cls)
+        h = C.c_void_p()
+        _ffi.check(_ffi.lib().rf_corpus_create_u32(elems.ctypes.data, offsets.ctypes.data, len(offsets) - 1, device, C.byref(h)))
+        self._h = h
+        self.device = device
+        return self
+
+    @classmethod
+    def from_unicode(cls, strings, device=0):
+        """Python str candidates as sequences of code points (what Rust's `.chars()` yields)."""
+        cps = [np.fromiter((ord(ch) for ch in s), dtype=np.uint32, count=len(s)) for s in strings]
+        offsets = np.zeros(len(cps) + 1, dtype=np.uint64)
+        if cps:
+            offsets[1:] = np.cumsum([len(c) for c in cps])
+        elems = np.concatenate(cps + [np.zeros(0, np.uint32)]).astype(np.uint32)
+        return cls.from_u32(elems, offsets, device)
+
+    @classmethod
     def from_strings(cls, strings, device=0):
         bs = [s.encode("latin-1") if isinstance(s, str) else bytes(s) for s in strings]
         offsets = np.zeros(len(bs) + 1, dtype=np.uint64)

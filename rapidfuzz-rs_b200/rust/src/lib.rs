@@ -45,6 +45,9 @@ extern "C" {
     pub fn rf_args_default(a: *mut rf_args);
     pub fn rf_last_error() -> *const c_char;
     pub fn rf_corpus_create_u8(chars: *const u8, offsets: *const u64, n: u64, device: c_int, out: *mut *mut rf_corpus) -> c_int;
+    // `char` / u32 elements: per-query alphabet renaming on the device, exact (see include/rfgpu.h)
+    pub fn rf_corpus_create_u32(elems: *const u32, offsets: *const u64, n: u64, device: c_int, out: *mut *mut rf_corpus) -> c_int;
+    pub fn rf_batch_create_u32(metric: c_int, query: *const u32, len: u32, device: c_int, out: *mut *mut rf_batch) -> c_int;
     pub fn rf_corpus_destroy(c: *mut rf_corpus) -> c_int;
     pub fn rf_corpus_size(c: *const rf_corpus) -> u64;
     pub fn rf_batch_create_u8(metric: c_int, query: *const u8, len: u32, device: c_int, out: *mut *mut rf_batch) -> c_int;
@@ -100,6 +103,15 @@ impl Corpus {
         for s in candidates { chars.extend_from_slice(s.as_ref()); offsets.push(chars.len() as u64); }
         let mut h = std::ptr::null_mut();
         check(unsafe { rf_corpus_create_u8(chars.as_ptr(), offsets.as_ptr(), (offsets.len() - 1) as u64, device, &mut h) });
+        Corpus { h }
+    }
+    /// Candidates as `char` sequences (`str::chars()`), the reference's default element type for `&str` inputs.
+    pub fn from_chars<I, S>(candidates: I, device: i32) -> Self where I: IntoIterator<Item = S>, S: AsRef<str> {
+        let mut elems: Vec<u32> = Vec::new();
+        let mut offsets = vec![0u64];
+        for s in candidates { elems.extend(s.as_ref().chars().map(|c| c as u32)); offsets.push(elems.len() as u64); }
+        let mut h = std::ptr::null_mut();
+        check(unsafe { rf_corpus_create_u32(elems.as_ptr(), offsets.as_ptr(), (offsets.len() - 1) as u64, device, &mut h) });
         Corpus { h }
     }
     /// Corpus file written by `rf_corpus_file_write` (mmap + upload).

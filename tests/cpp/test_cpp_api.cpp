@@ -53,6 +53,12 @@ int main() {
     auto ds = sk.stream<uint32_t>(chars.data(), offsets.data(), cands.size(), RF_DISTANCE, Args<uint32_t>{});
     EXPECT(ds == d);
   }
+  {  // u32 elements: the reference's unicode test (levenshtein.rs:2164-2169)
+    const std::u32string a = U"\u0418\u0432\u0430\u043d\u043a\u043e", b = U"\u041f\u0435\u0442\u0440\u0443\u043d\u043a\u043e";
+    const uint64_t off[2] = {0, b.size()};
+    Corpus cu = Corpus::from_u32(reinterpret_cast<const uint32_t*>(b.data()), off, 1);
+    EXPECT(distance::levenshtein::BatchComparator(std::u32string_view(a)).distance(cu)[0] == 5);
+  }
   bool threw = false;
   try { sk.distance_with_args(corpus, Args<uint32_t>{}.weights(1, 2, 3)); } catch (const Error& e) { threw = e.status == RF_ERR_UNSUPPORTED; }
   EXPECT(threw);

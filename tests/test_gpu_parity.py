@@ -196,8 +196,15 @@ def test_reference_golden_vectors_on_gpu():
     """Every u8 known-answer vector of the reference (tests/golden/golden.json) through the GPU path."""
     n_run = 0
     for rec in G["cases"]:
-        if "s1" not in rec or "s2" not in rec:
-            continue  # non-ASCII (u32 element) cases: GPU path is u8 this round
+        if "s1" not in rec or "s2" not in rec:   # non-ASCII cases: u32 elements (code points)
+            a = rec["args"]
+            for cp1, cp2 in ((rec["s1_cp"], rec["s2_cp"]), (rec["s2_cp"], rec["s1_cp"])):
+                corpus = rf.Corpus.from_u32(np.array(cp2, np.uint32), np.array([0, len(cp2)], np.uint64))
+                got = gpu_batch(rec["metric"], rec["kind"], np.array(cp1, np.uint32), corpus, cutoff=a.get("cutoff"))[0]
+                corpus.close()
+                assert rec["expected"] is not None and abs(float(got) - rec["expected"]) <= rec["tol"], (rec, got)
+                n_run += 1
+            continue
         a = rec["args"]
         w = tuple(a["weights"]) if "weights" in a else None
         if w == (1, 2, 3):
@@ -231,6 +238,77 @@ def test_reference_golden_vectors_on_gpu():
                     else:
                         assert np.isnan(got[j]) or abs(got[j] - c) < 1e-9, (metric, n1, names[j], c, got[j])
         corpus.close()
+
+
+@pytest.mark.parametrize("qlen", [0, 1, 7, 32, 33, 64, 65, 200, 256])
+def test_u32_elements_vs_oracle(qlen):
+    """u32 elements (Rust char / u32): per-query alphabet renaming on the device, exact against the oracle's
+    hashmap-based u32 path; u32 query against a u8 corpus; unicode strings through the host mirror."""
+    rng = np.random.default_rng(500 + qlen)
+    alphabet = np.array([97, 98, 99, 255, 256, 1048, 0x4E2D, 0x1F600, 0xFFFFFFFF, 0], dtype=np.uint32)
+    q = alphabet[rng.integers(0, 6, qlen)]
+    lens = [0, 1, 5, 31, 32, 33, 64, 65, 100, max(qlen, 1), qlen + 3]
+    cands = []
+    for _ in range(1500):
+        if qlen and rng.random() < 0.4:
+            c = list(q)
+            for _ in range(int(rng.integers(0, 8))):
+                pos = int(rng.integers(0, len(c) + 1))
+                op = rng.integers(0, 3)
+                if op == 0 and c:
+                    c[min(pos, len(c) - 1)] = alphabet[rng.integers(0, len(alphabet))]
+                elif op == 1:
+                    c.insert(pos, alphabet[rng.integers(0, len(alphabet))])
+                elif c:
+                    del c[min(pos, len(c) - 1)]
+            cands.append(np.array(c, dtype=np.uint32))
+        else:
+            cands.append(alphabet[rng.integers(0, len(alphabet), int(rng.choice(lens)))])
+    elems = np.concatenate(cands + [np.zeros(0, np.uint32)]).astype(np.uint32)
+    offsets = np.zeros(len(cands) + 1, dtype=np.uint64)
+    offsets[1:] = np.cumsum([len(c) for c in cands])
+    corpus = rf.Corpus.from_u32(elems, offsets)
+    combos = [(m, k, None) for m in INT_METRICS + ["jaro", "jaro_winkler"] for k in ("distance", "normalized_similarity")]
+    combos += [("levenshtein", "distance", 3), ("levenshtein", "distance", 40), ("indel", "similarity", 10),
+               ("jaro_winkler", "similarity", 0.8), ("ratio", "similarity", 0.5)]
+    for m, kind, cut in combos:
+        if m in ("jaro", "jaro_winkler") and qlen > 2048:
+            continue
+        kw = {} if cut is None else {"cutoff": cut}
+        got = gpu_batch(m, kind, q, corpus, **kw)
+        exp = orc.batch(m, kind, q, elems, offsets, nthreads=0, **kw)
+        assert_same(got, exp, ("u32", m, kind, cut, qlen))
+    # top-k on a u32 corpus goes through the same renaming
+    if qlen:
+        b = _bc("levenshtein", q)
+        gi, gs = b.extract("distance", corpus, k=5)
+        exp = orc.batch("levenshtein", "distance", q, elems, offsets, nthreads=0)
+        order = np.lexsort((np.arange(len(exp)), exp))[:5]
+        assert np.array_equal(gi, order.astype(np.uint32)) and np.array_equal(gs, exp[order])
+        b.close()
+    corpus.close()
+    # a u32 query against a byte corpus == the byte query when all its symbols are bytes
+    qb = (q % 3 + 97).astype(np.uint32)
+    chars, off8 = make_corpus(rng, 500, [0, 5, 40, 70], alphabet=3, query=qb.astype(np.uint8))
+    c8 = rf.Corpus(chars, off8)
+    assert_same(gpu_batch("levenshtein", "distance", qb, c8), gpu_batch("levenshtein", "distance", qb.astype(np.uint8), c8), "u32 q / u8 corpus")
+    c8.close()
+
+
+def test_u32_host_mirror_and_limits():
+    assert rf.distance.levenshtein.distance("Иванко", "Петрунко") == 5            # levenshtein.rs:2164-2169
+    assert rf.distance.indel.distance("Иванко", "Петрунко") == 8                  # indel.rs:851-857
+    assert rf.distance.levenshtein.BatchComparator("kitten").distance("sittinĝ") == 3   # byte query, wide candidate
+    c = rf.Corpus.from_unicode(["Петрунко", "Иванко", "", "abc"])
+    assert rf.distance.levenshtein.BatchComparator("Иванко").distance(c).tolist() == [5, 0, 6, 6]
+    with pytest.raises(rf.RfError) as ei:    # more distinct symbols than the byte renaming can hold
+        rf.distance.levenshtein.BatchComparator(np.arange(1000, 1300, dtype=np.uint32))
+    assert ei.value.status == _ffi.RF_ERR_UNSUPPORTED
+    with pytest.raises(rf.RfError):          # u32 corpus with a byte comparator handle
+        b = rf.distance.levenshtein.BatchComparator(b"abc")
+        out = np.zeros(4, np.uint32)
+        _ffi.check(_ffi.lib().rf_batch_score_u32(b._h, c._h, 0, None, out.ctypes.data))
+    c.close()
 
 
 def test_unsupported_is_loud():

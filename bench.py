@@ -349,8 +349,8 @@ def main():
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes, "kernel": "scan_lb_kernel<F_LEV,u32>",
-                         "note": "ALU-pipe bound by design (8 ALU-pipe ops per candidate char, pipe ~83% busy); traffic = ncu DRAM bytes of one launch; see DESIGN.md section 5"},
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel": "scan_lb_kernel<F_LEV,u32,256,RAWDIST>",
+                         "note": "ALU-pipe bound by design (7 LOP3 per candidate char on a 16-lane/clk pipe, pipe ~79% busy, issue ~77%); traffic = ncu DRAM bytes of one launch; see DESIGN.md section 5"},
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = host_threads()

@@ -150,6 +150,12 @@ if __name__ == "__main__":
                     lambda l: l + 12, tol=1e-6)
     if "c5" in which:
         cdist(int(1e4 * scale), int(1.25e6))
+    if "norm" in which:   # the f64-valued kinds of the edit-distance family (8-byte results, division in the epilogue)
+        one_vs_many("C2-shape levenshtein normalized_similarity", "levenshtein", "normalized_similarity", 2, 32, int(1e8 * scale),
+                    8, 64, 16, None, True, lambda l: l + 12)
+        one_vs_many("C2-shape fuzz::ratio", "ratio", "similarity", 2, 32, int(1e8 * scale), 8, 64, 16, None, True, lambda l: l + 12)
+        one_vs_many("C2-shape levenshtein distance cutoff 8", "levenshtein", "distance", 2, 32, int(1e8 * scale), 8, 64, 16, 8,
+                    False, lambda l: l + 8)
     if "post" in which:
         extract_filter(int(1e8 * scale))
     for extra in which:

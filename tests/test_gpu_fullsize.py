@@ -1,0 +1,96 @@
+"""BASELINE.json's FULL sizes on the GPU, checked through size-independent properties (the oracle only sees a
+sample): two independent code paths must agree bit for bit on every candidate, bounds that hold for any pair,
+planted near-matches are found, and a checksum of the result vector is reproducible."""
+import numpy as np
+import pytest
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+
+import rapidfuzz_b200 as rf
+from rapidfuzz_b200 import _ffi
+from oracle import oracle as orc
+from gpu_util import gpu_batch
+
+
+def _bc(metric, q):
+    from rapidfuzz_b200._scorer import BatchComparatorBase
+    return type("B", (BatchComparatorBase,), {"METRIC": metric})(q)
+
+
+def test_config2_full_size_1e8():
+    """config 2: 1 query len 32 vs 10^8 candidates len 8-64."""
+    n = 100_000_000
+    q = rf.synth_query(2, 32)
+    chars, offsets = rf.synth_corpus(2, q, n, 8, 64, 16)
+    lens = np.diff(offsets.astype(np.int64))
+    corpus = rf.Corpus(chars, offsets)
+    d = gpu_batch("levenshtein", "distance", q, corpus)                       # interleaved-layout kernel
+    b = _bc("levenshtein", q)
+    s = b.stream("distance", chars, offsets.astype(np.uint32))                # CSR / TMA-tile kernel, chunked
+    assert np.array_equal(d, s)                                               # two kernels, two layouts, same bits
+    assert np.all(d >= np.abs(lens - 32)) and np.all(d <= np.maximum(lens, 32))
+    m = 1_000_000
+    exp = orc.batch("levenshtein", "distance", q, chars[: int(offsets[m])], offsets[: m + 1], nthreads=0)
+    assert np.array_equal(d[:m], exp)
+    assert np.array_equal(d[-m:], orc.batch("levenshtein", "distance", q, chars[int(offsets[n - m]):],
+                                            offsets[n - m:] - offsets[n - m], nthreads=0))
+    assert (d <= 16).sum() >= n // 64 * 0.9                                   # the planted near-matches (1/64, <= 16 edits)
+    # post-processing agrees with numpy on the full vector
+    gi, gs = b.extract("distance", corpus, k=100)
+    order = np.lexsort((np.arange(n), d))[:100]
+    assert np.array_equal(gi, order.astype(np.uint32)) and np.array_equal(gs, d[order])
+    fi, fs, tot = b.filter("distance", corpus, rf.Args().score_cutoff(6), capacity=1 << 20)
+    hits = np.nonzero(d <= 6)[0]
+    assert tot == len(hits) and np.array_equal(fi, hits[: 1 << 20].astype(np.uint32))
+    # normalized_similarity is a pure function of (d, lens): size-independent identity
+    ns = gpu_batch("levenshtein", "normalized_similarity", q, corpus)
+    assert np.array_equal(ns, 1.0 - d / np.maximum(lens, 32))
+    b.close()
+    corpus.close()
+
+
+def test_config3_full_size_1e7_banded_equals_block():
+    """config 3: query len 256 vs 10^7 candidates len 64-256, score_cutoff 32: the one-word sliding band and the
+    multi-word block kernel are different algorithms and must return the same Option for every candidate."""
+    n = 10_000_000
+    q = rf.synth_query(3, 256)
+    chars, offsets = rf.synth_corpus(3, q, n, 64, 256, 48)
+    lens = np.diff(offsets.astype(np.int64))
+    corpus = rf.Corpus(chars, offsets)
+    band = gpu_batch("levenshtein", "distance", q, corpus, cutoff=32)
+    _ffi.check(_ffi.lib().rf_set_option(b"banded_levenshtein", 0))
+    try:
+        block = gpu_batch("levenshtein", "distance", q, corpus, cutoff=32)
+    finally:
+        _ffi.check(_ffi.lib().rf_set_option(b"banded_levenshtein", 1))
+    assert np.array_equal(band, block)
+    some = band != 0xFFFFFFFF
+    assert np.all(band[some] <= 32) and np.all(band[some] >= np.abs(lens[some] - 256))
+    assert not np.any(some & (np.abs(lens - 256) > 32))                       # the length filter (levenshtein.rs:1045-1047)
+    assert some.sum() > n // 200
+    m = 300_000
+    exp = orc.batch("levenshtein", "distance", q, chars[: int(offsets[m])], offsets[: m + 1], nthreads=0, cutoff=32)
+    assert np.array_equal(band[:m], exp)
+    corpus.close()
+
+
+def test_config4_full_size_1e8_jaro_winkler():
+    """config 4: Jaro-Winkler normalized_similarity, 10^8 candidates: 32-bit row kernel vs the generic per-lane
+    routine on every candidate (bit-identical f64), oracle within 1e-6 (and in fact exactly) on a sample."""
+    n = 100_000_000
+    q = rf.synth_query(4, 32)
+    chars, offsets = rf.synth_corpus(4, q, n, 8, 64, 16)
+    corpus = rf.Corpus(chars, offsets)
+    fast = gpu_batch("jaro_winkler", "normalized_similarity", q, corpus)
+    _ffi.check(_ffi.lib().rf_set_option(b"jaro32", 0))
+    try:
+        generic = gpu_batch("jaro_winkler", "normalized_similarity", q, corpus)
+    finally:
+        _ffi.check(_ffi.lib().rf_set_option(b"jaro32", 1))
+    assert np.array_equal(fast, generic)
+    assert np.all((fast >= 0.0) & (fast <= 1.0))
+    m = 500_000
+    exp = orc.batch("jaro_winkler", "normalized_similarity", q, chars[: int(offsets[m])], offsets[: m + 1], nthreads=0)
+    assert np.max(np.abs(fast[:m] - exp)) <= 1e-6
+    assert np.array_equal(fast[:m], exp)
+    corpus.close()

@@ -31,7 +31,8 @@ typedef enum rf_status {
   RF_ERR_OOM = 4
 } rf_status;
 
-/* metric modules: distance/{levenshtein,indel,lcs_seq,osa,jaro,jaro_winkler}.rs and fuzz.rs (ratio) */
+/* metric modules: distance/{levenshtein,indel,lcs_seq,osa,jaro,jaro_winkler,hamming,prefix,postfix}.rs and
+ * fuzz.rs (ratio) */
 typedef enum rf_metric {
   RF_LEVENSHTEIN = 0,
   RF_INDEL = 1,
@@ -39,7 +40,10 @@ typedef enum rf_metric {
   RF_OSA = 3,
   RF_JARO = 4,
   RF_JARO_WINKLER = 5,
-  RF_RATIO = 6
+  RF_RATIO = 6,
+  RF_HAMMING = 7, /* hamming.rs:136-199; see rf_args.pad */
+  RF_PREFIX = 8,  /* prefix.rs:47-71: similarity = common prefix length */
+  RF_POSTFIX = 9  /* postfix.rs:47-71: similarity = common suffix length */
 } rf_metric;
 
 /* which BatchComparator method: distance / similarity / normalized_distance / normalized_similarity */
@@ -63,6 +67,11 @@ typedef struct rf_args {
   uint64_t insertion_cost, deletion_cost, substitution_cost; /* WeightTable, levenshtein.rs:130-148 */
   double prefix_weight;                                      /* jaro_winkler.rs:31-39, default 0.1 */
   uint8_t reference_quirks; /* 1: RatioBatchComparator divides by max(len1,len2) like fuzz.rs:141 */
+  uint8_t pad;              /* hamming::Args::pad (hamming.rs:112-118).  0 (default): a candidate whose length differs
+                             * from the query's is Err(DifferentLengthArgs) (hamming.rs:232-234): its result is the None
+                             * sentinel and the host-buffer entry points return RF_ERR_INVALID_ARG ("Differing length
+                             * arguments provided") after filling the output; the *_device / extract / filter / stream
+                             * entry points only write the sentinel.  1: the excess length counts as mismatches. */
 } rf_args;
 
 #define RF_MAX_QUERY_LEN 16384u

@@ -9,7 +9,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
 
-METRICS = {"levenshtein": 0, "indel": 1, "lcs_seq": 2, "osa": 3, "jaro": 4, "jaro_winkler": 5, "ratio": 6}
+METRICS = {"levenshtein": 0, "indel": 1, "lcs_seq": 2, "osa": 3, "jaro": 4, "jaro_winkler": 5, "ratio": 6,
+           "hamming": 7, "prefix": 8, "postfix": 9}
 KINDS = {"distance": 0, "similarity": 1, "normalized_distance": 2, "normalized_similarity": 3}
 U64_MAX = 2**64 - 1
 
@@ -18,7 +19,11 @@ class OrcArgs(C.Structure):
     _fields_ = [("has_cutoff", C.c_uint8), ("cutoff_u", C.c_uint64), ("cutoff_f", C.c_double),
                 ("has_hint", C.c_uint8), ("hint_u", C.c_uint64), ("hint_f", C.c_double),
                 ("ins", C.c_uint64), ("del_", C.c_uint64), ("sub", C.c_uint64),
-                ("prefix_weight", C.c_double), ("reference_quirks", C.c_uint8)]
+                ("prefix_weight", C.c_double), ("reference_quirks", C.c_uint8), ("pad", C.c_uint8)]
+
+
+class DifferentLengthArgs(ValueError):
+    """hamming::Error::DifferentLengthArgs (hamming.rs:121-136): unequal lengths without Args::pad(true)."""
 
 
 def build(force=False):
@@ -68,8 +73,10 @@ def lib():
     return _lib
 
 
-def make_args(cutoff=None, hint=None, weights=None, prefix_weight=0.1, reference_quirks=False, is_float=False):
+def make_args(cutoff=None, hint=None, weights=None, prefix_weight=0.1, reference_quirks=False, is_float=False, pad=False,
+              allow_differing=False):
     a = OrcArgs()
+    a.pad = 1 if pad else 0
     a.ins, a.del_, a.sub = weights if weights is not None else (1, 1, 1)
     a.prefix_weight = prefix_weight
     a.reference_quirks = 1 if reference_quirks else 0
@@ -117,6 +124,8 @@ def pair(metric, kind, s1, s2, dtype=None, **kw):
     ou, of, some = C.c_uint64(0), C.c_double(0.0), C.c_int(0)
     rc = fn(METRICS[metric], KINDS[kind], q.ctypes.data, len(q), s.ctypes.data, len(s), C.byref(a),
             C.byref(ou), C.byref(of), C.byref(some))
+    if rc == 3:
+        raise DifferentLengthArgs("Differing length arguments provided")
     assert rc == 0
     if not some.value:
         return None
@@ -137,7 +146,9 @@ def batch(metric, kind, query, chars, offsets, nthreads=1, **kw):
     out = np.empty(n, dtype=np.float64 if is_f else np.uint32)
     rc = fn(METRICS[metric], KINDS[kind], q.ctypes.data, len(q), chars.ctypes.data, offsets.ctypes.data, n,
             C.byref(a), None if is_f else out.ctypes.data, out.ctypes.data if is_f else None, nthreads)
-    assert rc == 0
+    if rc == 3 and not kw.get("allow_differing"):
+        raise DifferentLengthArgs("Differing length arguments provided")
+    assert rc in (0, 3)
     return out
 
 

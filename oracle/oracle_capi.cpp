@@ -23,6 +23,7 @@ struct orc_args {
   uint64_t ins, del, sub;
   double prefix_weight;
   uint8_t reference_quirks;
+  uint8_t pad;
 };
 
 static rfo::Args to_args(const orc_args* a) {
@@ -37,6 +38,7 @@ static rfo::Args to_args(const orc_args* a) {
   r.weights = {a->ins, a->del, a->sub};
   r.prefix_weight = a->prefix_weight;
   r.reference_quirks = a->reference_quirks != 0;
+  r.pad = a->pad != 0;
   return r;
 }
 
@@ -57,13 +59,19 @@ static int batch_impl(int metric, int kind, const CQ* q, uint64_t qlen, const CS
   if (is_f && !out_f64) return 1;
   if (!is_f && !out_u32) return 1;
   (void)nthreads;
+  int differing = 0;  // hamming without pad: Err(DifferentLengthArgs) (hamming.rs:232-234) for that candidate
 #ifdef _OPENMP
   if (nthreads <= 0) nthreads = omp_get_max_threads();
-#pragma omp parallel for schedule(static) num_threads(nthreads)
+#pragma omp parallel for schedule(static) num_threads(nthreads) reduction(|:differing)
 #endif
   for (int64_t i = 0; i < (int64_t)n; ++i) {
     const CS* s = chars + offsets[i];
     uint64_t len = offsets[i + 1] - offsets[i];
+    if (metric == rfo::HAMMING && !a.pad && len != qlen) {
+      differing |= 1;
+      if (is_f) out_f64[i] = std::numeric_limits<double>::quiet_NaN(); else out_u32[i] = UINT32_MAX;
+      continue;
+    }
     if (is_f) {
       rfo::OptF r = b.float_score((rfo::Kind)kind, s, len, a);
       out_f64[i] = r.some ? r.v : std::numeric_limits<double>::quiet_NaN();
@@ -72,7 +80,7 @@ static int batch_impl(int metric, int kind, const CQ* q, uint64_t qlen, const CS
       out_u32[i] = r.some ? (uint32_t)r.v : UINT32_MAX;
     }
   }
-  return 0;
+  return differing ? 3 : 0;
 }
 
 extern "C" {
@@ -90,6 +98,7 @@ int orc_batch_u32(int metric, int kind, const uint32_t* q, uint64_t qlen, const 
 int orc_pair_u8(int metric, int kind, const uint8_t* q, uint64_t qlen, const uint8_t* s, uint64_t slen,
                 const orc_args* a_, uint64_t* out_u, double* out_f, int* some) {
   rfo::Args a = to_args(a_);
+  if (metric == rfo::HAMMING && !a.pad && qlen != slen) { *some = 0; return 3; }  // Err(DifferentLengthArgs)
   rfo::Batch<uint8_t> b((rfo::Metric)metric, q, (size_t)qlen);
   if (orc_result_is_float(metric, kind)) {
     rfo::OptF r = b.float_score((rfo::Kind)kind, s, slen, a);
@@ -103,6 +112,7 @@ int orc_pair_u8(int metric, int kind, const uint8_t* q, uint64_t qlen, const uin
 int orc_pair_u32(int metric, int kind, const uint32_t* q, uint64_t qlen, const uint32_t* s, uint64_t slen,
                  const orc_args* a_, uint64_t* out_u, double* out_f, int* some) {
   rfo::Args a = to_args(a_);
+  if (metric == rfo::HAMMING && !a.pad && qlen != slen) { *some = 0; return 3; }  // Err(DifferentLengthArgs)
   rfo::Batch<uint32_t> b((rfo::Metric)metric, q, (size_t)qlen);
   if (orc_result_is_float(metric, kind)) {
     rfo::OptF r = b.float_score((rfo::Kind)kind, s, slen, a);

@@ -805,7 +805,8 @@ double jw_similarity_with_pm(const BlockPM& pm, const C1* s1, usize len1, const 
 }
 
 // ---------------------------------------------------------------- score algebra (details/distance.rs)
-enum Metric : int { LEVENSHTEIN = 0, INDEL = 1, LCS_SEQ = 2, OSA = 3, JARO = 4, JARO_WINKLER = 5, RATIO = 6 };
+enum Metric : int { LEVENSHTEIN = 0, INDEL = 1, LCS_SEQ = 2, OSA = 3, JARO = 4, JARO_WINKLER = 5, RATIO = 6,
+                    HAMMING = 7, PREFIX = 8, POSTFIX = 9 };
 enum Kind : int { DISTANCE = 0, SIMILARITY = 1, NORM_DISTANCE = 2, NORM_SIMILARITY = 3 };
 
 struct Args {
@@ -818,7 +819,32 @@ struct Args {
   Weights weights;
   double prefix_weight = 0.1;
   bool reference_quirks = false;   // Q1: literal RatioBatchComparator normalisation (fuzz.rs:141)
+  bool pad = false;                // hamming.rs:112-118: unequal lengths count as mismatches instead of being an error
 };
+
+// ---------------------------------------------------------------- distance/hamming.rs, prefix.rs, postfix.rs
+template <class C1, class C2>
+usize hamming_distance_impl(const C1* s1, usize len1, const C2* s2, usize len2) {  // hamming.rs:136-161
+  usize dist = 0, i = 0;
+  for (;; ++i) {
+    const bool a = i < len1, b = i < len2;
+    if (a && b) { if (!(s1[i] == s2[i])) ++dist; }
+    else if (!a && !b) return dist;
+    else ++dist;
+  }
+}
+template <class C1, class C2>
+usize find_common_prefix(const C1* s1, usize len1, const C2* s2, usize len2) {      // details/common.rs:39-49
+  usize n = 0;
+  while (n < len1 && n < len2 && s1[n] == s2[n]) ++n;
+  return n;
+}
+template <class C1, class C2>
+usize find_common_suffix(const C1* s1, usize len1, const C2* s2, usize len2) {      // details/common.rs:51-62
+  usize n = 0;
+  while (n < len1 && n < len2 && s1[len1 - 1 - n] == s2[len2 - 1 - n]) ++n;
+  return n;
+}
 
 struct OptU { bool some; usize v; };
 struct OptF { bool some; double v; };
@@ -853,6 +879,7 @@ struct Batch {
         return maximum - 2 * lcs;
       }
       case OSA: return osa_batch_distance(pm, len1, s2, len2);        // osa.rs:435-460
+      case HAMMING: return hamming_distance_impl(p, len1, s2, len2);  // hamming.rs:168-186 (cutoff and hint unused)
       default: {                                                       // default _distance :157-179
         usize maximum = std::max(len1, len2);
         bool hc = has_c; usize cs = hc ? (maximum >= c ? maximum - c : 0) : 0;
@@ -866,6 +893,8 @@ struct Batch {
   usize u_similarity(const C2* s2, usize len2, bool has_c, usize c, bool has_h, usize h, const Args& a) const {
     const C1* p = s1.data(); usize len1 = s1.size();
     if (metric == LCS_SEQ) return lcs_similarity_with_pm(pm, p, len1, s2, len2, has_c ? c : 0);  // lcs_seq.rs:777-793
+    if (metric == PREFIX) return find_common_prefix(p, len1, s2, len2);    // prefix.rs:47-71
+    if (metric == POSTFIX) return find_common_suffix(p, len1, s2, len2);   // postfix.rs:47-71
     usize maximum = this->maximum(len1, len2, a);                      // default _similarity :181-211
     if (has_c) {
       if (c > maximum) return maximum;

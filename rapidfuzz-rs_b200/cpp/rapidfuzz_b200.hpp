@@ -91,10 +91,12 @@ struct Args {
   uint64_t ins = 1, del = 1, sub = 1;
   double prefix_weight_ = 0.1;
   bool quirks = false;
+  bool pad_ = false;  // hamming::Args::pad (hamming.rs:112-118)
   Args score_hint(T h) const { Args a = *this; a.hint = h; return a; }
   Args<T, WithScoreCutoff<T>> score_cutoff(T c) const {
     Args<T, WithScoreCutoff<T>> a;
     a.cutoff = {c}; a.hint = hint; a.ins = ins; a.del = del; a.sub = sub; a.prefix_weight_ = prefix_weight_; a.quirks = quirks;
+    a.pad_ = pad_;
     return a;
   }
   Args weights(uint64_t insertion_cost, uint64_t deletion_cost, uint64_t substitution_cost) const {
@@ -102,6 +104,7 @@ struct Args {
   }
   Args prefix_weight(double w) const { Args a = *this; a.prefix_weight_ = w; return a; }
   Args reference_quirks(bool on = true) const { Args a = *this; a.quirks = on; return a; }
+  Args pad(bool on = true) const { Args a = *this; a.pad_ = on; return a; }
 };
 
 namespace detail {
@@ -112,6 +115,7 @@ rf_args to_c(const Args<T, C>& a) {
   r.insertion_cost = a.ins; r.deletion_cost = a.del; r.substitution_cost = a.sub;
   r.prefix_weight = a.prefix_weight_;
   r.reference_quirks = a.quirks ? 1 : 0;
+  r.pad = a.pad_ ? 1 : 0;
   if constexpr (!std::is_same_v<C, NoScoreCutoff>) {
     r.has_cutoff = 1;
     if constexpr (std::is_floating_point_v<T>) r.cutoff_f = (double)a.cutoff.value; else r.cutoff_u = (uint64_t)a.cutoff.value;
@@ -254,6 +258,9 @@ using lcs_seq = MetricModule<RF_LCS_SEQ, uint32_t>;
 using osa = MetricModule<RF_OSA, uint32_t>;
 using jaro = MetricModule<RF_JARO, double>;
 using jaro_winkler = MetricModule<RF_JARO_WINKLER, double>;
+using hamming = MetricModule<RF_HAMMING, uint32_t>;  // unequal lengths without Args::pad(): Error (status RF_ERR_INVALID_ARG)
+using prefix = MetricModule<RF_PREFIX, uint32_t>;
+using postfix = MetricModule<RF_POSTFIX, uint32_t>;
 }  // namespace distance
 
 namespace fuzz {  // fuzz.rs:48-150

@@ -348,7 +348,7 @@ static inline uint32_t alpha_hash(uint32_t x) { return (x * 2654435761u) >> 22; 
 static rf_status batch_create_bytes(rf_metric metric, const uint8_t* query, uint32_t query_len, int device, rf_batch** out) {
   if (!out) return fail(RF_ERR_INVALID_ARG, "out is NULL");
   *out = nullptr;
-  if ((int)metric < 0 || (int)metric > (int)RF_RATIO) return fail(RF_ERR_INVALID_ARG, "unknown metric");
+  if ((int)metric < 0 || (int)metric > (int)RF_POSTFIX) return fail(RF_ERR_INVALID_ARG, "unknown metric");
   if (query_len && !query) return fail(RF_ERR_INVALID_ARG, "query is NULL");
   if (query_len > RF_MAX_QUERY_LEN) return fail(RF_ERR_UNSUPPORTED, "query longer than RF_MAX_QUERY_LEN");
   if ((metric == RF_JARO || metric == RF_JARO_WINKLER) && query_len > 2048)
@@ -372,7 +372,9 @@ static rf_status batch_create_bytes(rf_metric metric, const uint8_t* query, uint
   const size_t szp = (size_t)256 * bstride * sizeof(uint32_t);
   const size_t szp8 = (szp + 7) & ~(size_t)7;
   const size_t szq = (size_t)kQuotDim * kQuotDim * sizeof(double);  // exact a/b for a,b <= 64 (Jaro epilogue)
-  std::vector<uint8_t> blob(2 * sz32 + 2 * sz64 + szw + szp8 + szq, 0);
+  const size_t szb = ((size_t)query_len + 15) / 16 * 16 + 16;      // the query bytes themselves (hamming / prefix / postfix)
+  std::vector<uint8_t> blob(2 * sz32 + 2 * sz64 + szw + szp8 + szq + szb, 0);
+  if (query_len) memcpy(blob.data() + 2 * sz32 + 2 * sz64 + szw + szp8 + szq, query, query_len);
   uint32_t* t32t = (uint32_t*)blob.data();
   uint32_t* t32b = t32t + 256;
   uint64_t* t64t = (uint64_t*)(blob.data() + 2 * sz32);
@@ -410,6 +412,7 @@ static rf_status batch_create_bytes(rf_metric metric, const uint8_t* query, uint
   b->view.pm_band = (const uint32_t*)(b->view.pm_words + (size_t)256 * words);
   b->view.band_stride = bstride;
   b->view.quot = (const double*)(b->d_blob + 2 * sz32 + 2 * sz64 + szw + szp8);
+  b->view.qbytes = b->d_blob + 2 * sz32 + 2 * sz64 + szw + szp8 + szq;
   *out = b;
   return RF_OK;
 }
@@ -478,6 +481,7 @@ static rf_status make_epi(const rf_batch* b, rf_kind kind, const rf_args* args, 
   e->w_sub = a->substitution_cost;
   e->prefix_weight = a->prefix_weight;
   e->quirks = a->reference_quirks ? 1 : 0;
+  e->pad = a->pad ? 1 : 0;
   e->wclass = WC_UNIFORM;
   if (b->metric == RF_LEVENSHTEIN) {  // weight classes of levenshtein.rs:1301-1330
     if (a->insertion_cost == a->deletion_cost) {
@@ -493,7 +497,8 @@ static rf_status make_epi(const rf_batch* b, rf_kind kind, const rf_args* args, 
   }
   if (b->metric == RF_RATIO) e->kind = K_NORM_SIMILARITY;  // fuzz.rs:127-149 has one method only
   e->unit32 = ((b->metric == RF_LEVENSHTEIN && e->wclass == WC_UNIFORM && e->w_ins == 1) || b->metric == RF_INDEL ||
-               b->metric == RF_LCS_SEQ || b->metric == RF_OSA)
+               b->metric == RF_LCS_SEQ || b->metric == RF_OSA || b->metric == RF_HAMMING || b->metric == RF_PREFIX ||
+               b->metric == RF_POSTFIX)
                   ? 1
                   : 0;
   return RF_OK;
@@ -501,7 +506,7 @@ static rf_status make_epi(const rf_batch* b, rf_kind kind, const rf_args* args, 
 
 // Scores the candidates described by `cv` (+ optional interleaved copy `lb`), all resident on `device`.
 static rf_status score_view(const rf_batch* b, const CorpusView& cv, const LbAlloc* lb, int device, rf_kind kind,
-                            const rf_args* args, void* out_dev, bool want_f64, cudaStream_t st) {
+                            const rf_args* args, void* out_dev, bool want_f64, cudaStream_t st, uint32_t* d_err = nullptr) {
   if (!b) return fail(RF_ERR_INVALID_ARG, "NULL handle");
   if ((int)kind < 0 || (int)kind > 3) return fail(RF_ERR_INVALID_ARG, "unknown kind");
   if (b->device != device) return fail(RF_ERR_INVALID_ARG, "batch and corpus live on different devices");
@@ -516,7 +521,8 @@ static rf_status score_view(const rf_batch* b, const CorpusView& cv, const LbAll
   DeviceGuard g(device);
   if (!g.ok) return fail(RF_ERR_CUDA, "cudaSetDevice failed");
   L.corpus = cv;
-  const bool use_lb = lb && lb->gdata && g_w1_path.load() != 1;
+  const bool use_lb = lb && lb->gdata && g_w1_path.load() != 1 &&
+                      family_of((int)b->metric, WC_UNIFORM) != F_SIMPLE;
   if (use_lb) {
     L.lb = LbView{lb->perm, lb->lens, lb->goff, lb->gdata, lb->ngroups};
     L.lb_counter = counter_slot(device);
@@ -529,7 +535,8 @@ static rf_status score_view(const rf_batch* b, const CorpusView& cv, const LbAll
   L.sm_count = sm_count_of(device);
   const Family fam = family_of(L.epi.metric, L.epi.wclass);
   cudaError_t e;
-  if (b->len1 <= 64) {
+  if (fam == F_SIMPLE) e = launch_simple(L, d_err);
+  else if (b->len1 <= 64) {
     const int path = g_w1_path.load();
     e = !use_lb ? launch_scan_w1(L) : path == 2 ? launch_scan_lbr(L) : launch_scan_lb(L);
   }
@@ -574,7 +581,7 @@ __global__ void __launch_bounds__(256) remap_kernel(const In* __restrict__ in, u
 extern "C" {
 
 static rf_status score_device(const rf_batch* b, const rf_corpus* c, rf_kind kind, const rf_args* args, void* out_dev,
-                              bool want_f64, cudaStream_t st) {
+                              bool want_f64, cudaStream_t st, uint32_t* d_err = nullptr) {
   if (!b || !c) return fail(RF_ERR_INVALID_ARG, "NULL handle");
   if (c->d_elems32 && !b->wide)
     return fail(RF_ERR_INVALID_ARG, "a u32 corpus needs a comparator created with rf_batch_create_u32");
@@ -597,13 +604,13 @@ static rf_status score_device(const rf_batch* b, const rf_corpus* c, rf_kind kin
       rfk::count_launches(1);
     }
     rf_status s = (e == cudaSuccess) ? score_view(b, CorpusView{d_bytes, c->d_off32, c->d_off64, c->n, c->total}, nullptr, c->device,
-                                                  kind, args, out_dev, want_f64, st)
+                                                  kind, args, out_dev, want_f64, st, d_err)
                                      : cuda_fail(e, "alphabet renaming");
     dev_free(d_bytes, st);
     return s;
   }
   return score_view(b, CorpusView{c->d_chars, c->d_off32, c->d_off64, c->n, c->total}, &c->lb, c->device, kind, args,
-                    out_dev, want_f64, st);
+                    out_dev, want_f64, st, d_err);
 }
 
 static rf_status score_host(const rf_batch* b, const rf_corpus* c, rf_kind kind, const rf_args* args, void* out_host,
@@ -614,17 +621,21 @@ static rf_status score_host(const rf_batch* b, const rf_corpus* c, rf_kind kind,
   DeviceGuard g(c->device);
   if (!g.ok) return fail(RF_ERR_CUDA, "cudaSetDevice failed");
   const size_t bytes = (size_t)c->n * (want_f64 ? 8 : 4);
-  void* d_out = nullptr;
+  uint8_t* d_out = nullptr;  // results, then 4 bytes of error flag (hamming without pad)
   cudaStream_t st;
   cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
   if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
-  e = dev_alloc(&d_out, bytes, st);
-  if (e != cudaSuccess) { cudaStreamDestroy(st); return cuda_fail(e, "result buffer"); }
-  rf_status s = score_device(b, c, kind, args, d_out, want_f64, st);
+  e = dev_alloc(&d_out, bytes + 16, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_out + bytes, 0, 16, st);
+  if (e != cudaSuccess) { dev_free(d_out, st); cudaStreamSynchronize(st); cudaStreamDestroy(st); return cuda_fail(e, "result buffer"); }
+  rf_status s = score_device(b, c, kind, args, d_out, want_f64, st, (uint32_t*)(d_out + bytes));
   if (s == RF_OK) {
+    uint32_t differing = 0;
     e = cudaMemcpyAsync(out_host, d_out, bytes, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&differing, d_out + bytes, 4, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) s = cuda_fail(e, "result download");
+    else if (differing) s = fail(RF_ERR_INVALID_ARG, "Differing length arguments provided");  // hamming::Error (hamming.rs:121-136)
   }
   dev_free(d_out, st);
   cudaStreamSynchronize(st);

@@ -24,10 +24,11 @@
 
 namespace rfk {
 
-enum Metric : int { M_LEVENSHTEIN = 0, M_INDEL = 1, M_LCS_SEQ = 2, M_OSA = 3, M_JARO = 4, M_JARO_WINKLER = 5, M_RATIO = 6 };
+enum Metric : int { M_LEVENSHTEIN = 0, M_INDEL = 1, M_LCS_SEQ = 2, M_OSA = 3, M_JARO = 4, M_JARO_WINKLER = 5, M_RATIO = 6,
+                    M_HAMMING = 7, M_PREFIX = 8, M_POSTFIX = 9 };
 enum Kind : int { K_DISTANCE = 0, K_SIMILARITY = 1, K_NORM_DISTANCE = 2, K_NORM_SIMILARITY = 3 };
 // which bit-parallel recurrence a metric needs
-enum Family : int { F_LEV = 0, F_LCS = 1, F_OSA = 2, F_JARO = 3 };
+enum Family : int { F_LEV = 0, F_LCS = 1, F_OSA = 2, F_JARO = 3, F_SIMPLE = 4 };  // F_SIMPLE: hamming / prefix / postfix
 // Levenshtein weight classes (levenshtein.rs:1301-1330)
 enum WeightClass : int { WC_UNIFORM = 0, WC_INDEL = 1, WC_ZERO = 2 };
 
@@ -286,6 +287,49 @@ RF_HD uint64_t band_window32_low33(uint32_t a, uint32_t b, uint32_t o) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Hamming / Prefix / Postfix (hamming.rs:136-161, details/common.rs:39-62): no bit-parallelism needed, the
+// candidate is compared with the query 4 bytes at a time.  q4(i) / t4(i) return bytes 4i..4i+3 of the query /
+// candidate packed little-endian (garbage beyond the end is masked here); qb(j) / tb(j) single bytes.
+RF_HD uint32_t differing_bytes(uint32_t a, uint32_t b) {  // number of byte lanes in which a and b differ
+  uint32_t x = a ^ b;
+  x |= x >> 4; x |= x >> 2; x |= x >> 1;                 // bit 0 of every byte = byte is non-zero
+  return (uint32_t)popc(x & 0x01010101u);
+}
+template <class Q4, class T4>
+RF_HD uint32_t hamming_raw(const Q4& q4, const T4& t4, uint32_t len1, uint32_t len2) {
+  const uint32_t mn = len1 < len2 ? len1 : len2, mx = len1 < len2 ? len2 : len1;
+  uint32_t dist = mx - mn;  // with pad: the excess counts as mismatches (hamming.rs:156-158)
+  uint32_t i = 0;
+  for (; i + 4 <= mn; i += 4) dist += differing_bytes(q4(i >> 2), t4(i >> 2));
+  if (i < mn) {
+    const uint32_t mask = (1u << (8 * (mn - i))) - 1u;
+    dist += differing_bytes(q4(i >> 2) & mask, t4(i >> 2) & mask);
+  }
+  return dist;
+}
+template <class Q4, class T4>
+RF_HD uint32_t prefix_raw(const Q4& q4, const T4& t4, uint32_t len1, uint32_t len2) {
+  const uint32_t mn = len1 < len2 ? len1 : len2;
+  for (uint32_t i = 0; i < mn; i += 4) {
+    const uint32_t x = q4(i >> 2) ^ t4(i >> 2);
+    if (x) {
+      uint32_t k = 0;
+      while (!((x >> (8 * k)) & 0xffu)) ++k;  // first differing byte of the word
+      const uint32_t n = i + k;
+      return n < mn ? n : mn;
+    }
+  }
+  return mn;
+}
+template <class QB, class TB>
+RF_HD uint32_t postfix_raw(const QB& qb, const TB& tb, uint32_t len1, uint32_t len2) {
+  const uint32_t mn = len1 < len2 ? len1 : len2;
+  uint32_t n = 0;
+  while (n < mn && qb(len1 - 1 - n) == tb(len2 - 1 - n)) ++n;
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Jaro building blocks (jaro.rs:106-145)
 // x / 3.0, correctly rounded, without the general division routine (Markstein: y = RN(1/3), q = RN(x*y),
 // r = x - 3q exactly (fma), result RN(q + r*y) is the correctly rounded quotient for normal operands).
@@ -539,6 +583,7 @@ struct Epi {
   double prefix_weight;
   int quirks;
   int unit32;  // set by the launcher: integer metric with unit weights -> 32-bit epilogue
+  int pad;     // hamming::Args::pad
 };
 
 RF_HD Family family_of(int metric, int wclass) {
@@ -546,6 +591,7 @@ RF_HD Family family_of(int metric, int wclass) {
     case M_LEVENSHTEIN: return wclass == WC_INDEL ? F_LCS : F_LEV;
     case M_INDEL: case M_LCS_SEQ: case M_RATIO: return F_LCS;
     case M_OSA: return F_OSA;
+    case M_HAMMING: case M_PREFIX: case M_POSTFIX: return F_SIMPLE;
     default: return F_JARO;
   }
 }
@@ -581,8 +627,8 @@ RF_HD uint64_t int_distance(const Epi& e, uint64_t raw, uint64_t len1, uint64_t 
       return raw * e.w_ins;                                                  // :1308-1316
     case M_INDEL: return len1 + len2 - 2 * raw;                              // indel.rs:367
     case M_RATIO: return e.quirks ? umax64(len1, len2) - raw : len1 + len2 - 2 * raw;
-    case M_LCS_SEQ: return umax64(len1, len2) - raw;                         // details/distance.rs:178
-    default: return raw;                                                     // OSA
+    case M_LCS_SEQ: case M_PREFIX: case M_POSTFIX: return umax64(len1, len2) - raw;  // details/distance.rs:178 (raw = similarity)
+    default: return raw;                                                     // OSA, Hamming
   }
 }
 
@@ -594,8 +640,8 @@ RF_HD uint32_t finish_int(const Epi& e, uint64_t raw, uint64_t len1, uint64_t le
     uint32_t d, M;
     switch (e.metric) {
       case M_INDEL: d = l1 + l2 - 2u * r; M = l1 + l2; break;
-      case M_LCS_SEQ: d = mx - r; M = mx; break;
-      default: d = r; M = mx; break;  // Levenshtein (1,1,1), OSA
+      case M_LCS_SEQ: case M_PREFIX: case M_POSTFIX: d = mx - r; M = mx; break;
+      default: d = r; M = mx; break;  // Levenshtein (1,1,1), OSA, Hamming
     }
     const uint32_t v = (e.kind == K_DISTANCE) ? d : M - d;
     if (e.has_cutoff) {

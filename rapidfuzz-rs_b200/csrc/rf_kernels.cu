@@ -1910,6 +1910,85 @@ cudaError_t launch_scan_band(const ScanLaunch& L, uint32_t cut) {
   return e;
 }
 
+// ------------------------------------------------------------------------------------------------ simple
+// Hamming / Prefix / Postfix over the CSR corpus: thread per candidate, query bytes in shared memory, the candidate
+// walked with 16-byte loads.  HBM-bound (every candidate byte is read once, nothing else scales).
+struct SimpleParams {
+  const uint8_t* chars;
+  const uint32_t* off32;
+  const uint64_t* off64;
+  uint64_t n;
+  const uint8_t* qbytes;  // query, padded with zeros to a multiple of 16 (+16)
+  uint32_t len1;
+  void* out;
+  int out_f64;
+  uint32_t* err_flag;     // set to 1 when Hamming without pad meets a candidate of another length (may be NULL)
+  Epi epi;
+};
+
+__global__ void __launch_bounds__(256) simple_kernel(const __grid_constant__ SimpleParams p) {
+  extern __shared__ __align__(16) uint32_t simple_q[];
+  const uint32_t qwords = (p.len1 + 3) / 4 + 4;
+  for (uint32_t i = threadIdx.x; i < qwords; i += blockDim.x) simple_q[i] = reinterpret_cast<const uint32_t*>(p.qbytes)[i];
+  __syncthreads();
+  const uint8_t* qb8 = reinterpret_cast<const uint8_t*>(simple_q);
+  const bool off64 = p.off64 != nullptr;
+  for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < p.n; c += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t o0 = off64 ? p.off64[c] : (uint64_t)p.off32[c];
+    const uint64_t o1 = off64 ? p.off64[c + 1] : (uint64_t)p.off32[c + 1];
+    const uint32_t len2 = (uint32_t)(o1 - o0);
+    bool none = false;
+    uint32_t raw = 0;
+    if (p.epi.metric == M_POSTFIX) {
+      const uint8_t* t = p.chars + o0;
+      raw = postfix_raw([&](uint32_t j) -> uint32_t { return qb8[j]; }, [&](uint32_t j) -> uint32_t { return t[j]; }, p.len1, len2);
+    } else {
+      ByteReader16 rd(p.chars + (o0 & ~15ull), (uint32_t)(o0 & 15ull));
+      Bytes16 blk{};
+      uint32_t have = 0xFFFFFFFFu;  // index (in 16-byte blocks) of the block held in blk
+      auto t4 = [&](uint32_t w) -> uint32_t {  // words are requested in increasing order
+        if ((w >> 2) != have) { blk = rd.next16(); have = w >> 2; }
+        return blk.w[w & 3u];
+      };
+      auto q4 = [&](uint32_t w) -> uint32_t { return simple_q[w]; };
+      if (p.epi.metric == M_HAMMING) {
+        if (!p.epi.pad && len2 != p.len1) {
+          none = true;
+          if (p.err_flag) atomicOr(p.err_flag, 1u);
+        } else {
+          raw = hamming_raw(q4, t4, p.len1, len2);
+        }
+      } else {
+        raw = prefix_raw(q4, t4, p.len1, len2);
+      }
+    }
+    if (p.out_f64) reinterpret_cast<double*>(p.out)[c] = none ? qnan() : finish_norm(p.epi, raw, p.len1, len2);
+    else reinterpret_cast<uint32_t*>(p.out)[c] = none ? NONE_U32 : finish_int(p.epi, raw, p.len1, len2);
+  }
+}
+
+cudaError_t launch_simple(const ScanLaunch& L, uint32_t* err_flag) {
+  SimpleParams p{};
+  p.chars = L.corpus.chars;
+  p.off32 = L.corpus.off32;
+  p.off64 = L.corpus.off64;
+  p.n = L.corpus.n;
+  p.qbytes = L.query.qbytes;
+  p.len1 = L.query.len1;
+  p.out = L.out;
+  p.out_f64 = L.out_is_f64;
+  p.err_flag = err_flag;
+  p.epi = L.epi;
+  const size_t smem = ((size_t)(p.len1 + 3) / 4 + 4) * 4;
+  uint64_t blocks = (p.n + 255) / 256;
+  const uint64_t max_blocks = (uint64_t)L.sm_count * 8;
+  if (blocks > max_blocks) blocks = max_blocks;
+  if (blocks < 1) blocks = 1;
+  simple_kernel<<<(uint32_t)blocks, 256, smem, L.stream>>>(p);
+  g_launches.fetch_add(1);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------ jaro mw
 template <int MAXQ>
 __global__ void __launch_bounds__(128) jaro_mw_kernel(const __grid_constant__ MwParams p) {

@@ -27,6 +27,7 @@ struct QueryView {
   const uint64_t* pm_words;  // [256][words] row-major (pattern_match_vector.rs layout), any len1
   const uint32_t* pm_band;   // [256][band_stride] 32-bit words: 2 zero words, the match vector, >= 2 zero words (banded kernel)
   uint32_t band_stride;      // (2*(words+2)) | 1
+  const uint8_t* qbytes;     // the query itself, zero-padded to a multiple of 16 plus 16 (hamming / prefix / postfix)
   const double* quot;        // [65][65] exactly rounded a/b (b >= 1): the Jaro formula's quotients without divisions
 };
 
@@ -76,6 +77,8 @@ cudaError_t launch_scan_lbr(const ScanLaunch& L);
 cudaError_t launch_scan_mw(const ScanLaunch& L);
 // Levenshtein distance with a cutoff of at most 63 unit edits, any query length: one 64-bit sliding band per candidate.
 cudaError_t launch_scan_band(const ScanLaunch& L, uint32_t cut);
+// Hamming / Prefix / Postfix (any query length): thread per candidate over the CSR corpus.
+cudaError_t launch_simple(const ScanLaunch& L, uint32_t* err_flag);
 // Jaro / Jaro-Winkler with a multi-word query (65..2048).
 cudaError_t launch_jaro_mw(const ScanLaunch& L);
 

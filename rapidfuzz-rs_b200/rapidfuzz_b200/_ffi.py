@@ -10,7 +10,8 @@ _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.environ.get("RF_LIB_PATH") or os.path.join(_ROOT, "lib", "librfgpu.so")  # RF_LIB_PATH: dev A/B builds
 
 RF_OK, RF_ERR_INVALID_ARG, RF_ERR_UNSUPPORTED, RF_ERR_CUDA, RF_ERR_OOM = range(5)
-METRICS = {"levenshtein": 0, "indel": 1, "lcs_seq": 2, "osa": 3, "jaro": 4, "jaro_winkler": 5, "ratio": 6}
+METRICS = {"levenshtein": 0, "indel": 1, "lcs_seq": 2, "osa": 3, "jaro": 4, "jaro_winkler": 5, "ratio": 6,
+           "hamming": 7, "prefix": 8, "postfix": 9}
 KINDS = {"distance": 0, "similarity": 1, "normalized_distance": 2, "normalized_similarity": 3}
 NONE_U32 = 0xFFFFFFFF
 RF_MAX_QUERY_LEN = 16384
@@ -20,7 +21,7 @@ class RfArgs(C.Structure):
     _fields_ = [("has_cutoff", C.c_uint8), ("cutoff_u", C.c_uint64), ("cutoff_f", C.c_double),
                 ("has_hint", C.c_uint8), ("hint_u", C.c_uint64), ("hint_f", C.c_double),
                 ("insertion_cost", C.c_uint64), ("deletion_cost", C.c_uint64), ("substitution_cost", C.c_uint64),
-                ("prefix_weight", C.c_double), ("reference_quirks", C.c_uint8)]
+                ("prefix_weight", C.c_double), ("reference_quirks", C.c_uint8), ("pad", C.c_uint8)]
 
 
 class RfError(RuntimeError):

@@ -19,6 +19,7 @@ class Args:
         self._weights = (1, 1, 1)
         self._prefix_weight = 0.1
         self._quirks = False
+        self._pad = False
 
     def _copy(self):
         a = type(self)()
@@ -45,6 +46,12 @@ class Args:
         a._prefix_weight = w
         return a
 
+    def pad(self, pad=True):
+        """hamming::Args::pad (hamming.rs:112-118)."""
+        a = self._copy()
+        a._pad = bool(pad)
+        return a
+
     def reference_quirks(self, on=True):
         a = self._copy()
         a._quirks = on
@@ -56,6 +63,7 @@ class Args:
         r.insertion_cost, r.deletion_cost, r.substitution_cost = self._weights
         r.prefix_weight = self._prefix_weight
         r.reference_quirks = 1 if self._quirks else 0
+        r.pad = 1 if self._pad else 0
         if self._cutoff is not None:
             r.has_cutoff = 1
             if is_float:

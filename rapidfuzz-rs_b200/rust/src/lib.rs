@@ -24,6 +24,7 @@ pub struct rf_args {
     pub substitution_cost: u64,
     pub prefix_weight: f64,
     pub reference_quirks: u8,
+    pub pad: u8, // hamming::Args::pad
 }
 #[repr(C)] pub struct rf_corpus { _p: [u8; 0] }
 #[repr(C)] pub struct rf_batch { _p: [u8; 0] }
@@ -35,6 +36,9 @@ pub const RF_OSA: c_int = 3;
 pub const RF_JARO: c_int = 4;
 pub const RF_JARO_WINKLER: c_int = 5;
 pub const RF_RATIO: c_int = 6;
+pub const RF_HAMMING: c_int = 7;
+pub const RF_PREFIX: c_int = 8;
+pub const RF_POSTFIX: c_int = 9;
 pub const RF_DISTANCE: c_int = 0;
 pub const RF_SIMILARITY: c_int = 1;
 pub const RF_NORMALIZED_DISTANCE: c_int = 2;
@@ -240,6 +244,11 @@ pub mod distance {
     metric_module!(osa, RF_OSA, usize, false);
     metric_module!(jaro, RF_JARO, f64, true);
     metric_module!(jaro_winkler, RF_JARO_WINKLER, f64, true);
+    metric_module!(prefix, RF_PREFIX, usize, false);
+    metric_module!(postfix, RF_POSTFIX, usize, false);
+    // hamming: same shape with `Args::pad` -> `rf_args.pad`; without it a candidate of another length makes the call
+    // return status 1 ("Differing length arguments provided"), which maps to Err(hamming::Error::DifferentLengthArgs).
+    metric_module!(hamming, RF_HAMMING, usize, false);
 }
 
 /// `fuzz::RatioBatchComparator` (src/fuzz.rs:98-150); documented semantics (== `fuzz::ratio`), see DESIGN.md Q1.

@@ -159,6 +159,18 @@ double core_jaro32(const uint8_t* q, uint32_t len1, const uint8_t* s2, uint32_t 
 
 double core_div3(double x) { return div3_exact(x); }
 
+// hamming (pad semantics) / prefix / postfix raw values through the word-wise routines the kernel uses
+uint32_t core_simple(int which, const uint8_t* q, uint32_t len1, const uint8_t* s2, uint32_t len2) {
+  std::vector<uint32_t> qw(len1 / 4 + 8, 0xA5A5A5A5u), tw(len2 / 4 + 8, 0x5A5A5A5Au);   // junk behind the data
+  if (len1) memcpy(qw.data(), q, len1);
+  if (len2) memcpy(tw.data(), s2, len2);
+  auto q4 = [&](uint32_t w) { return qw[w]; };
+  auto t4 = [&](uint32_t w) { return tw[w]; };
+  if (which == 0) return hamming_raw(q4, t4, len1, len2);
+  if (which == 1) return prefix_raw(q4, t4, len1, len2);
+  return postfix_raw([&](uint32_t j) -> uint32_t { return q[j]; }, [&](uint32_t j) -> uint32_t { return s2[j]; }, len1, len2);
+}
+
 // generic (multi-word) Jaro on the host, query <= 1024
 double core_jaro_generic(const uint8_t* q, uint32_t len1, const uint8_t* s, uint32_t len2, double cutoff) {
   const uint32_t words = (len1 + 63) / 64;

@@ -59,7 +59,14 @@ int main() {
     Corpus cu = Corpus::from_u32(reinterpret_cast<const uint32_t*>(b.data()), off, 1);
     EXPECT(distance::levenshtein::BatchComparator(std::u32string_view(a)).distance(cu)[0] == 5);
   }
+  EXPECT(distance::hamming::distance("hamming", "humming") == 1);                     // hamming.rs:198
+  EXPECT(distance::hamming::distance_with_args("ham", "hamming", Args<uint32_t>{}.pad(true)) == 4);  // :622-625
+  EXPECT(distance::prefix::similarity("prefix", "preference") == 4);                  // prefix.rs:122
+  EXPECT(distance::postfix::similarity("postfix", "prefix") == 3);                    // postfix.rs:122
   bool threw = false;
+  try { distance::hamming::distance("ham", "hamming"); } catch (const Error& e) { threw = e.status == RF_ERR_INVALID_ARG; }
+  EXPECT(threw);                                                                        // hamming.rs:617-620
+  threw = false;
   try { sk.distance_with_args(corpus, Args<uint32_t>{}.weights(1, 2, 3)); } catch (const Error& e) { threw = e.status == RF_ERR_UNSUPPORTED; }
   EXPECT(threw);
   std::printf(fails ? "cpp api: %d failure(s)\n" : "cpp api: all ok\n", fails);

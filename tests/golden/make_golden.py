@@ -57,6 +57,25 @@ for c, e in ((4, 4), (3, None), (2, None), (1, None), (0, None)):
 add("levenshtein", "distance", a, b, 6, L + ":2058", weights=W112)
 for c, e in ((6, 6), (5, None), (4, None), (3, None), (2, None), (1, None), (0, None)):
     add("levenshtein", "distance", a, b, e, L + ":2059-2065", weights=W112, cutoff=c)
+# ---- hamming.rs:549-641 (pad / error semantics: args pad=True, expected "error" = Err(DifferentLengthArgs))
+H = "distance/hamming.rs"
+add("hamming", "distance", "", "", 0, H + ":551")
+add("hamming", "distance", "hamming", "hamming", 0, H + ":556")
+add("hamming", "distance", "hamming", "hammers", 3, H + ":566")
+add("hamming", "distance", "hammers", "hamming", 3, H + ":568-575", pad=True)
+add("hamming", "distance", "hammers", "hamming", 3, H + ":576-583", pad=True, cutoff=3)
+add("hamming", "distance", "hammers", "hamming", None, H + ":584-591", pad=True, cutoff=2)
+add("hamming", "distance", "hammers", "hamming", 3, H + ":592-599", cutoff=3)
+add("hamming", "distance", "hammers", "hamming", None, H + ":600-607", cutoff=2)
+add("hamming", "distance", "hamming", "h\u9999mm\u00fcng", 2, H + ":612")
+add("hamming", "distance", "ham", "hamming", "error", H + ":617-620")
+add("hamming", "distance", "ham", "hamming", 4, H + ":622-625", pad=True)
+add("hamming", "distance", "ham", "hamming", None, H + ":627-634", pad=True, cutoff=3)
+add("hamming", "distance", "Friedrich Nietzs", "Jean-Paul Sartre", 14, H + ":639")
+add("hamming", "distance", "hamming", "humming", 1, H + ":198")
+# ---- prefix.rs / postfix.rs doc-tests
+add("prefix", "similarity", "prefix", "preference", 4, "distance/prefix.rs:122,256")
+add("postfix", "similarity", "postfix", "prefix", 3, "distance/postfix.rs:122,256")
 # test_banded (:2070-2130)
 banded = [
     ("kkkkbbbbfkkkkkkibfkkkafakkfekgkkkkkkkkkkbdbbddddddddddafkkkekkkhkk",

@@ -199,3 +199,21 @@ def test_div3_exact_is_correctly_rounded():
     xs += list(rng.random(20000) * 3.0) + list(rng.random(2000) * 1e-3) + [0.0, 3.0, 1.0, 2.0, 1e-300, 2.9999999999999996]
     for x in xs:
         assert lib.core_div3(x) == x / 3.0, x
+
+
+def test_simple_metrics_vs_oracle(core):
+    """Word-wise Hamming (pad semantics) / Prefix / Postfix == the oracle's restatement of hamming.rs / common.rs."""
+    core.core_simple.argtypes = [C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+    core.core_simple.restype = C.c_uint32
+    rng = np.random.default_rng(77)
+    for a, b in _pairs(rng, 3000, [0, 1, 2, 3, 4, 5, 7, 8, 9, 16, 31, 33, 64, 100], CL, 3):
+        if rng.random() < 0.3 and len(a) and len(b):      # long shared prefix / suffix
+            k = int(rng.integers(0, min(len(a), len(b)) + 1))
+            b = b.copy()
+            if rng.random() < 0.5:
+                b[:k] = a[:k]
+            elif k:
+                b[-k:] = a[-k:]
+        assert core.core_simple(0, a.ctypes.data, len(a), b.ctypes.data, len(b)) == orc.pair("hamming", "distance", a, b, pad=True)
+        assert core.core_simple(1, a.ctypes.data, len(a), b.ctypes.data, len(b)) == orc.pair("prefix", "similarity", a, b)
+        assert core.core_simple(2, a.ctypes.data, len(a), b.ctypes.data, len(b)) == orc.pair("postfix", "similarity", a, b)

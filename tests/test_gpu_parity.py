@@ -196,23 +196,31 @@ def test_reference_golden_vectors_on_gpu():
     """Every u8 known-answer vector of the reference (tests/golden/golden.json) through the GPU path."""
     n_run = 0
     for rec in G["cases"]:
-        if "s1" not in rec or "s2" not in rec:   # non-ASCII cases: u32 elements (code points)
-            a = rec["args"]
-            for cp1, cp2 in ((rec["s1_cp"], rec["s2_cp"]), (rec["s2_cp"], rec["s1_cp"])):
-                corpus = rf.Corpus.from_u32(np.array(cp2, np.uint32), np.array([0, len(cp2)], np.uint64))
-                got = gpu_batch(rec["metric"], rec["kind"], np.array(cp1, np.uint32), corpus, cutoff=a.get("cutoff"))[0]
-                corpus.close()
-                assert rec["expected"] is not None and abs(float(got) - rec["expected"]) <= rec["tol"], (rec, got)
-                n_run += 1
-            continue
         a = rec["args"]
         w = tuple(a["weights"]) if "weights" in a else None
         if w == (1, 2, 3):
             continue
-        for s1, s2 in ((rec["s1"], rec["s2"]), (rec["s2"], rec["s1"])):
-            corpus = rf.Corpus.from_strings([s2])
-            got = gpu_batch(rec["metric"], rec["kind"], s1.encode(), corpus, cutoff=a.get("cutoff"), weights=w)[0]
-            corpus.close()
+        wide = "s1" not in rec or "s2" not in rec   # non-ASCII cases: u32 elements (code points)
+        e1 = np.array(rec["s1_cp"], np.uint32) if "s1_cp" in rec else np.frombuffer(rec["s1"].encode(), np.uint8)
+        e2 = np.array(rec["s2_cp"], np.uint32) if "s2_cp" in rec else np.frombuffer(rec["s2"].encode(), np.uint8)
+        for q, c in ((e1, e2), (e2, e1)):
+            if wide:
+                corpus = rf.Corpus.from_u32(c.astype(np.uint32), np.array([0, len(c)], np.uint64))
+                q = q.astype(np.uint32)
+            else:
+                corpus = rf.Corpus(c, np.array([0, len(c)], np.uint64))
+            try:
+                if rec["expected"] == "error":       # hamming::Error::DifferentLengthArgs
+                    with pytest.raises(rf.RfError):
+                        _gpu_pad(rec["metric"], rec["kind"], q, corpus, cutoff=a.get("cutoff"), pad=a.get("pad", False))
+                    n_run += 1
+                    continue
+                if rec["metric"] in ("hamming", "prefix", "postfix"):
+                    got = _gpu_pad(rec["metric"], rec["kind"], q, corpus, cutoff=a.get("cutoff"), pad=a.get("pad", False))[0]
+                else:
+                    got = gpu_batch(rec["metric"], rec["kind"], q, corpus, cutoff=a.get("cutoff"), weights=w)[0]
+            finally:
+                corpus.close()
             exp = rec["expected"]
             is_none = (np.isnan(got) if got.dtype == np.float64 else got == _ffi.NONE_U32)
             if exp is None:
@@ -309,6 +317,64 @@ def test_u32_host_mirror_and_limits():
         out = np.zeros(4, np.uint32)
         _ffi.check(_ffi.lib().rf_batch_score_u32(b._h, c._h, 0, None, out.ctypes.data))
     c.close()
+
+
+@pytest.mark.parametrize("qlen", [0, 1, 3, 4, 17, 32, 64, 65, 300])
+def test_hamming_prefix_postfix_vs_oracle(qlen):
+    """distance::{hamming, prefix, postfix}: every kind and cutoff ladder against the oracle; Hamming's pad / error."""
+    rng = np.random.default_rng(700 + qlen)
+    q = (rng.integers(0, 3, qlen) + 97).astype(np.uint8)
+    chars, offsets = make_corpus(rng, 3000, [0, 1, 2, 3, 4, 5, 15, 16, 17, 33, 64, 100, max(qlen, 1), qlen + 1], alphabet=3,
+                                 query=q, near_frac=0.5)
+    corpus = rf.Corpus(chars, offsets)
+    for m, extra in (("prefix", {}), ("postfix", {}), ("hamming", {"pad": True})):
+        for kind in ALL_KINDS:
+            check2 = lambda **kw: assert_same(_gpu_pad(m, kind, q, corpus, **kw, **extra),
+                                              orc.batch(m, kind, q, chars, offsets, nthreads=0, **kw, **extra), (m, kind, kw, qlen))
+            check2()
+            for c in ((0, 1, 2, 5, 40, 2**64 - 1) if kind in ("distance", "similarity") else (0.0, 0.2, 0.5, 0.9, 1.0)):
+                check2(cutoff=c)
+    # Hamming without pad: candidates of another length are Err(DifferentLengthArgs)
+    exp = orc.batch("hamming", "distance", q, chars, offsets, nthreads=0, allow_differing=True)
+    lens = np.diff(offsets.astype(np.int64))
+    if np.any(lens != qlen):
+        with pytest.raises(rf.RfError) as ei:
+            _gpu_pad("hamming", "distance", q, corpus)
+        assert ei.value.status == _ffi.RF_ERR_INVALID_ARG and "Differing length" in str(ei.value)
+    same = np.nonzero(lens == qlen)[0]
+    if len(same):
+        sub_off = np.zeros(len(same) + 1, np.uint64)
+        sub_off[1:] = np.cumsum(lens[same])
+        sub_chars = np.concatenate([chars[int(offsets[i]):int(offsets[i + 1])] for i in same] + [np.zeros(0, np.uint8)]).astype(np.uint8)
+        sc = rf.Corpus(sub_chars, sub_off)
+        assert_same(_gpu_pad("hamming", "distance", q, sc), exp[same], "hamming equal lengths")
+        sc.close()
+    corpus.close()
+
+
+def _gpu_pad(metric, kind, q, corpus, cutoff=None, pad=False):
+    b = _bc(metric, q)
+    a = rf.Args().pad(pad)
+    if cutoff is not None:
+        a = a.score_cutoff(cutoff)
+    try:
+        r = b._score(kind, corpus, a)
+    finally:
+        b.close()
+    if isinstance(r, np.ma.MaskedArray):
+        return r.filled(np.nan if r.dtype == np.float64 else _ffi.NONE_U32)
+    return r
+
+
+def test_hamming_prefix_postfix_known_answers():
+    assert rf.distance.hamming.distance("hamming", "humming") == 1                                   # hamming.rs:198
+    assert rf.distance.hamming.distance("ham", "hamming", rf.Args().pad(True)) == 4                  # :622-625
+    assert rf.distance.hamming.distance("hammers", "hamming", rf.Args().pad(True).score_cutoff(2)) is None   # :584-591
+    with pytest.raises(rf.RfError):
+        rf.distance.hamming.distance("ham", "hamming")                                               # :617-620
+    assert rf.distance.hamming.distance("hamming", "h\u9999mm\u00fcng") == 2                         # :612 (u32 elements)
+    assert rf.distance.prefix.similarity("prefix", "preference") == 4                                # prefix.rs:122
+    assert rf.distance.postfix.BatchComparator("postfix").similarity("prefix") == 3                  # postfix.rs:256
 
 
 def test_unsupported_is_loud():

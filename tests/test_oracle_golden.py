@@ -28,6 +28,8 @@ def _kw(rec):
         kw["cutoff"] = a["cutoff"]
     if "weights" in a:
         kw["weights"] = tuple(a["weights"])
+    if "pad" in a:
+        kw["pad"] = a["pad"]
     return kw
 
 
@@ -48,8 +50,14 @@ def test_golden_case(idx):
     s1, s2 = _strs(rec)
     kw = _kw(rec)
     for a, b in ((s1, s2), (s2, s1)):   # BatchComparator::new(s1)(s2) and ::new(s2)(s1)
+        if rec["expected"] == "error":       # hamming::Error::DifferentLengthArgs
+            with pytest.raises(orc.DifferentLengthArgs):
+                orc.pair(rec["metric"], rec["kind"], a, b, **kw)
+            continue
         got = orc.pair(rec["metric"], rec["kind"], a, b, **kw)
         _check(got, rec["expected"], rec["tol"], (rec, a, b, got))
+    if rec["expected"] == "error":
+        return
     if all(ord(c) < 128 for c in s1 + s2):  # .chars() vs .bytes() (levenshtein.rs:1877-1890)
         got32 = orc.pair(rec["metric"], rec["kind"], s1, s2, dtype=np.uint32, **kw)
         _check(got32, rec["expected"], rec["tol"], (rec, "u32", got32))

@@ -137,6 +137,53 @@ def extract_filter(n):
     corpus.close()
 
 
+def widen(n):
+    """The steps either side of the path: u32 elements, packing, corpus files."""
+    import tempfile
+    q = rf.synth_query(2, 32)
+    chars, offsets = rf.synth_corpus(2, q, n, 8, 64, 16)
+    # --- u32 elements: same strings as code points (+0x400 so that nothing is a byte), alphabet renaming per call
+    elems = chars.astype(np.uint32) + 0x400
+    q32 = q.astype(np.uint32) + 0x400
+    c32 = rf.Corpus.from_u32(elems, offsets)
+    b32 = type("B", (rf._scorer.BatchComparatorBase,), {"METRIC": "levenshtein"})(q32)
+    out = torch.empty(n, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    ms32 = timed(lambda: b32.score_into("distance", c32, out.data_ptr(), None, st), 10)
+    m = min(n, 200_000)
+    exp = orc.batch("levenshtein", "distance", q, chars[: int(offsets[m])], offsets[: m + 1], nthreads=0)
+    ok32 = bool(np.array_equal(out[:m].cpu().numpy().view(np.uint32), exp))
+    b32.close(); c32.close(); del elems
+    # --- packing: n Python-side (pointer, length) strings -> CSR (rf_pack_u8), all host threads
+    ns = min(n, 20_000_000)
+    lens = np.diff(offsets[: ns + 1]).astype(np.uint64)
+    base = chars.ctypes.data
+    ptrs = (base + offsets[:ns]).astype(np.uint64)
+    off2 = np.empty(ns + 1, dtype=np.uint64)
+    dst = np.empty(int(offsets[ns]), dtype=np.uint8)
+    t0 = time.perf_counter()
+    _ffi.check(L.rf_pack_u8(ptrs.ctypes.data, lens.ctypes.data, ns, off2.ctypes.data, dst.ctypes.data, 0))
+    t_pack = time.perf_counter() - t0
+    okp = bool(np.array_equal(dst, chars[: int(offsets[ns])]) and np.array_equal(off2, offsets[: ns + 1]))
+    # --- corpus file: write, map + upload (page cache warm), score from the mapping through the streaming pipeline
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "c.rfc")
+        t0 = time.perf_counter(); rf.write_corpus_file(path, chars, offsets); t_w = time.perf_counter() - t0
+        size = os.path.getsize(path)
+        t0 = time.perf_counter(); cf = rf.Corpus.from_file(path); t_load = time.perf_counter() - t0
+        cf.close()
+        b8 = type("B", (rf._scorer.BatchComparatorBase,), {"METRIC": "levenshtein"})(q)
+        with rf.CorpusFile(path) as f:
+            t0 = time.perf_counter(); r = b8.stream("distance", f.chars, f.offsets); t_stream = time.perf_counter() - t0
+            okf = bool(np.array_equal(r[:m], exp))
+        b8.close()
+    print(json.dumps({"config": "widen: u32 elements / packing / corpus file", "n": n,
+                      "u32_levenshtein_ms_per_step": ms32, "u32_pairs_per_s": n / (ms32 * 1e-3), "u32_matches_oracle_sample": ok32,
+                      "pack_strings": ns, "pack_s": t_pack, "pack_GBps": float(offsets[ns]) / t_pack / 1e9, "pack_ok": okp,
+                      "file_bytes": size, "file_write_s": t_w, "file_map_upload_build_s": t_load,
+                      "file_stream_score_s_pageable_mmap": t_stream, "file_stream_matches_oracle_sample": okf}), flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1].split(",") if len(sys.argv) > 1 else ["c2w", "c3", "c4", "c5"]
     if "c2w" in which:  # config 2 with a 64-element query (64-bit words)
@@ -156,6 +203,27 @@ if __name__ == "__main__":
         one_vs_many("C2-shape fuzz::ratio", "ratio", "similarity", 2, 32, int(1e8 * scale), 8, 64, 16, None, True, lambda l: l + 12)
         one_vs_many("C2-shape levenshtein distance cutoff 8", "levenshtein", "distance", 2, 32, int(1e8 * scale), 8, 64, 16, 8,
                     False, lambda l: l + 8)
+    if "simple" in which:   # HBM-bound metrics: bytes = len + 4 + 4 per pair
+        for m, kind in (("hamming", "distance"), ("prefix", "similarity"), ("postfix", "similarity")):
+            q = rf.synth_query(2, 32)
+            n = int(1e8 * scale)
+            chars, offsets = rf.synth_corpus(2, q, n, 8, 64, 16)
+            corpus = rf.Corpus(chars, offsets)
+            b = type("B", (rf._scorer.BatchComparatorBase,), {"METRIC": m})(q)
+            out = torch.empty(n, dtype=torch.int32, device="cuda")
+            st = torch.cuda.current_stream().cuda_stream
+            a = rf.Args().pad(True)
+            ms = timed(lambda: b.score_into(kind, corpus, out.data_ptr(), a, st), 20)
+            mm = min(n, 200_000)
+            exp = orc.batch(m, kind, q, chars[: int(offsets[mm])], offsets[: mm + 1], nthreads=0, pad=True)
+            ok = bool(np.array_equal(out[:mm].cpu().numpy().view(np.uint32), exp))
+            alg = float(offsets[n]) + 8.0 * n
+            print(json.dumps({"config": "C2-shape " + m, "n": n, "ms_per_step": ms, "pairs_per_s": n / (ms * 1e-3),
+                              "algorithmic_GBps": alg / (ms * 1e-3) / 1e9, "hbm_frac_of_measured_peak": alg / (ms * 1e-3) / 1e9 / PEAK,
+                              "matches_oracle_sample": ok}), flush=True)
+            b.close(); corpus.close()
+    if "widen" in which:
+        widen(int(1e8 * scale))
     if "post" in which:
         extract_filter(int(1e8 * scale))
     for extra in which:

@@ -26,7 +26,8 @@ extern "C" {
 typedef enum rf_status {
   RF_OK = 0,
   RF_ERR_INVALID_ARG = 1,
-  RF_ERR_UNSUPPORTED = 2, /* e.g. generic (non-uniform, non-indel) weights; query longer than RF_MAX_QUERY_LEN */
+  RF_ERR_UNSUPPORTED = 2, /* e.g. query longer than RF_MAX_QUERY_LEN; generic (non-uniform, non-indel) Levenshtein weights
+                             with a query longer than 2048; u32 query with more than 255 distinct symbols */
   RF_ERR_CUDA = 3,
   RF_ERR_OOM = 4
 } rf_status;

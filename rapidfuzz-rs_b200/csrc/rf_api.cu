@@ -488,9 +488,9 @@ static rf_status make_epi(const rf_batch* b, rf_kind kind, const rf_args* args, 
       if (a->insertion_cost == 0) e->wclass = WC_ZERO;
       else if (a->insertion_cost == a->substitution_cost) e->wclass = WC_UNIFORM;
       else if (a->substitution_cost >= a->insertion_cost + a->deletion_cost) e->wclass = WC_INDEL;
-      else return fail(RF_ERR_UNSUPPORTED, "generic Levenshtein weights (Wagner-Fischer route) are not on the GPU path");
+      else e->wclass = WC_GENERIC;  // generalized_distance (levenshtein.rs:1330): Wagner-Fischer
     } else {
-      return fail(RF_ERR_UNSUPPORTED, "generic Levenshtein weights (Wagner-Fischer route) are not on the GPU path");
+      e->wclass = WC_GENERIC;
     }
   } else {
     e->w_ins = e->w_del = e->w_sub = 1;
@@ -521,8 +521,8 @@ static rf_status score_view(const rf_batch* b, const CorpusView& cv, const LbAll
   DeviceGuard g(device);
   if (!g.ok) return fail(RF_ERR_CUDA, "cudaSetDevice failed");
   L.corpus = cv;
-  const bool use_lb = lb && lb->gdata && g_w1_path.load() != 1 &&
-                      family_of((int)b->metric, WC_UNIFORM) != F_SIMPLE;
+  const Family fam0 = family_of(L.epi.metric, L.epi.wclass);
+  const bool use_lb = lb && lb->gdata && g_w1_path.load() != 1 && fam0 != F_SIMPLE && fam0 != F_WF;
   if (use_lb) {
     L.lb = LbView{lb->perm, lb->lens, lb->goff, lb->gdata, lb->ngroups};
     L.lb_counter = counter_slot(device);
@@ -536,6 +536,10 @@ static rf_status score_view(const rf_batch* b, const CorpusView& cv, const LbAll
   const Family fam = family_of(L.epi.metric, L.epi.wclass);
   cudaError_t e;
   if (fam == F_SIMPLE) e = launch_simple(L, d_err);
+  else if (fam == F_WF) {
+    if (b->len1 > 2048) return fail(RF_ERR_UNSUPPORTED, "generic Levenshtein weights: queries longer than 2048 elements");
+    e = launch_wf(L);
+  }
   else if (b->len1 <= 64) {
     const int path = g_w1_path.load();
     e = !use_lb ? launch_scan_w1(L) : path == 2 ? launch_scan_lbr(L) : launch_scan_lb(L);

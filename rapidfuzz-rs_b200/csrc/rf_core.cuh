@@ -28,9 +28,9 @@ enum Metric : int { M_LEVENSHTEIN = 0, M_INDEL = 1, M_LCS_SEQ = 2, M_OSA = 3, M_
                     M_HAMMING = 7, M_PREFIX = 8, M_POSTFIX = 9 };
 enum Kind : int { K_DISTANCE = 0, K_SIMILARITY = 1, K_NORM_DISTANCE = 2, K_NORM_SIMILARITY = 3 };
 // which bit-parallel recurrence a metric needs
-enum Family : int { F_LEV = 0, F_LCS = 1, F_OSA = 2, F_JARO = 3, F_SIMPLE = 4 };  // F_SIMPLE: hamming / prefix / postfix
+enum Family : int { F_LEV = 0, F_LCS = 1, F_OSA = 2, F_JARO = 3, F_SIMPLE = 4, F_WF = 5 };  // F_SIMPLE: hamming / prefix / postfix; F_WF: generic weights
 // Levenshtein weight classes (levenshtein.rs:1301-1330)
-enum WeightClass : int { WC_UNIFORM = 0, WC_INDEL = 1, WC_ZERO = 2 };
+enum WeightClass : int { WC_UNIFORM = 0, WC_INDEL = 1, WC_ZERO = 2, WC_GENERIC = 3 };
 
 constexpr uint32_t NONE_U32 = 0xFFFFFFFFu;
 
@@ -284,6 +284,34 @@ RF_HD uint64_t band_window32(uint32_t a, uint32_t b, uint32_t c, uint32_t o) {
 // words give window bits 0..(63 - o) >= 32, the rest reads as no-match.
 RF_HD uint64_t band_window32_low33(uint32_t a, uint32_t b, uint32_t o) {
   return (uint64_t)funnel_r(a, b, o) | ((uint64_t)(b >> o) << 32);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generic weighted Levenshtein (levenshtein.rs:212-259, the Wagner-Fischer route of :1330): one cost row of
+// len1+1 entries, `cache(i)` is a reference to entry i (strided global scratch on the device).  A match takes the
+// diagonal without looking at the other two moves, exactly as the reference does.
+template <class QB, class TB, class Cache>
+RF_HD uint64_t weighted_wagner_fischer(const QB& qb, const TB& tb, uint32_t len1, uint32_t len2, uint64_t w_ins, uint64_t w_del,
+                                       uint64_t w_sub, const Cache& cache) {
+  for (uint32_t i = 0; i <= len1; ++i) cache(i) = (uint64_t)i * w_del;
+  for (uint32_t j = 0; j < len2; ++j) {
+    const uint32_t ch2 = tb(j);
+    uint64_t temp = cache(0);
+    cache(0) += w_ins;
+    for (uint32_t i = 0; i < len1; ++i) {
+      uint64_t x = temp;
+      const uint64_t old_next = cache(i + 1);
+      if (qb(i) != ch2) {
+        const uint64_t a = cache(i) + w_del, b = temp + w_sub;
+        x = a < b ? a : b;
+        const uint64_t c = old_next + w_ins;
+        x = x < c ? x : c;
+      }
+      cache(i + 1) = x;
+      temp = old_next;
+    }
+  }
+  return cache(len1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -588,7 +616,7 @@ struct Epi {
 
 RF_HD Family family_of(int metric, int wclass) {
   switch (metric) {
-    case M_LEVENSHTEIN: return wclass == WC_INDEL ? F_LCS : F_LEV;
+    case M_LEVENSHTEIN: return wclass == WC_INDEL ? F_LCS : (wclass == WC_GENERIC ? F_WF : F_LEV);
     case M_INDEL: case M_LCS_SEQ: case M_RATIO: return F_LCS;
     case M_OSA: return F_OSA;
     case M_HAMMING: case M_PREFIX: case M_POSTFIX: return F_SIMPLE;
@@ -623,6 +651,7 @@ RF_HD uint64_t int_distance(const Epi& e, uint64_t raw, uint64_t len1, uint64_t 
   switch (e.metric) {
     case M_LEVENSHTEIN:
       if (e.wclass == WC_ZERO) return 0;                                     // levenshtein.rs:1303-1305
+      if (e.wclass == WC_GENERIC) return raw;                                // :1330 (raw = weighted Wagner-Fischer result)
       if (e.wclass == WC_INDEL) return (len1 + len2 - 2 * raw) * e.w_ins;    // :1321-1327
       return raw * e.w_ins;                                                  // :1308-1316
     case M_INDEL: return len1 + len2 - 2 * raw;                              // indel.rs:367

@@ -1989,6 +1989,71 @@ cudaError_t launch_simple(const ScanLaunch& L, uint32_t* err_flag) {
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------ wf
+// Generic Levenshtein weights (neither uniform nor insertion/deletion-only): Wagner-Fischer, thread per candidate,
+// the cost row in thread-strided global scratch (entry i of thread t at scratch[i*T + t]: coalesced across a warp).
+struct WfParams {
+  const uint8_t* chars;
+  const uint32_t* off32;
+  const uint64_t* off64;
+  uint64_t n;
+  const uint8_t* qbytes;
+  uint32_t len1;
+  uint64_t* scratch;  // [(len1+1)][T]
+  uint32_t T;         // threads in the grid
+  void* out;
+  int out_f64;
+  Epi epi;
+};
+
+__global__ void __launch_bounds__(128) wf_kernel(const __grid_constant__ WfParams p) {
+  extern __shared__ __align__(16) uint8_t wf_q[];
+  for (uint32_t i = threadIdx.x; i < p.len1; i += blockDim.x) wf_q[i] = p.qbytes[i];
+  __syncthreads();
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t* row = p.scratch + t;
+  const uint32_t T = p.T;
+  const bool off64 = p.off64 != nullptr;
+  for (uint64_t c = t; c < p.n; c += T) {
+    const uint64_t o0 = off64 ? p.off64[c] : (uint64_t)p.off32[c];
+    const uint64_t o1 = off64 ? p.off64[c + 1] : (uint64_t)p.off32[c + 1];
+    const uint32_t len2 = (uint32_t)(o1 - o0);
+    const uint8_t* txt = p.chars + o0;
+    const uint64_t raw = weighted_wagner_fischer([&](uint32_t i) -> uint32_t { return wf_q[i]; },
+                                                 [&](uint32_t j) -> uint32_t { return txt[j]; }, p.len1, len2, p.epi.w_ins,
+                                                 p.epi.w_del, p.epi.w_sub,
+                                                 [&](uint32_t i) -> uint64_t& { return row[(size_t)i * T]; });
+    if (p.out_f64) reinterpret_cast<double*>(p.out)[c] = finish_norm(p.epi, raw, p.len1, len2);
+    else reinterpret_cast<uint32_t*>(p.out)[c] = finish_int(p.epi, raw, p.len1, len2);
+  }
+}
+
+cudaError_t launch_wf(const ScanLaunch& L) {
+  if (L.query.len1 > 2048) return cudaErrorNotSupported;
+  WfParams p{};
+  p.chars = L.corpus.chars;
+  p.off32 = L.corpus.off32;
+  p.off64 = L.corpus.off64;
+  p.n = L.corpus.n;
+  p.qbytes = L.query.qbytes;
+  p.len1 = L.query.len1;
+  p.out = L.out;
+  p.out_f64 = L.out_is_f64;
+  p.epi = L.epi;
+  uint64_t blocks = (p.n + 127) / 128;
+  const uint64_t max_blocks = (uint64_t)L.sm_count * 4;
+  if (blocks > max_blocks) blocks = max_blocks;
+  if (blocks < 1) blocks = 1;
+  p.T = (uint32_t)blocks * 128u;
+  cudaError_t e = dev_alloc(&p.scratch, (size_t)(p.len1 + 1) * p.T * sizeof(uint64_t), L.stream);
+  if (e != cudaSuccess) return e;
+  wf_kernel<<<(uint32_t)blocks, 128, p.len1 + 16, L.stream>>>(p);
+  g_launches.fetch_add(1);
+  e = cudaGetLastError();
+  dev_free(p.scratch, L.stream);
+  return e;
+}
+
 // ------------------------------------------------------------------------------------------------ jaro mw
 template <int MAXQ>
 __global__ void __launch_bounds__(128) jaro_mw_kernel(const __grid_constant__ MwParams p) {

@@ -79,6 +79,8 @@ cudaError_t launch_scan_mw(const ScanLaunch& L);
 cudaError_t launch_scan_band(const ScanLaunch& L, uint32_t cut);
 // Hamming / Prefix / Postfix (any query length): thread per candidate over the CSR corpus.
 cudaError_t launch_simple(const ScanLaunch& L, uint32_t* err_flag);
+// Levenshtein with generic weights: Wagner-Fischer, query <= 2048 (cudaErrorNotSupported beyond).
+cudaError_t launch_wf(const ScanLaunch& L);
 // Jaro / Jaro-Winkler with a multi-word query (65..2048).
 cudaError_t launch_jaro_mw(const ScanLaunch& L);
 

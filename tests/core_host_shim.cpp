@@ -159,6 +159,14 @@ double core_jaro32(const uint8_t* q, uint32_t len1, const uint8_t* s2, uint32_t 
 
 double core_div3(double x) { return div3_exact(x); }
 
+// generic weighted Levenshtein through the routine the Wagner-Fischer kernel runs (strided row like on the device)
+uint64_t core_wf(const uint8_t* q, uint32_t len1, const uint8_t* s2, uint32_t len2, uint64_t wi, uint64_t wd, uint64_t ws) {
+  const size_t stride = 3;
+  std::vector<uint64_t> row((size_t)(len1 + 1) * stride, 0xDEADBEEFull);
+  return weighted_wagner_fischer([&](uint32_t i) -> uint32_t { return q[i]; }, [&](uint32_t j) -> uint32_t { return s2[j]; }, len1,
+                                 len2, wi, wd, ws, [&](uint32_t i) -> uint64_t& { return row[(size_t)i * stride]; });
+}
+
 // hamming (pad semantics) / prefix / postfix raw values through the word-wise routines the kernel uses
 uint32_t core_simple(int which, const uint8_t* q, uint32_t len1, const uint8_t* s2, uint32_t len2) {
   std::vector<uint32_t> qw(len1 / 4 + 8, 0xA5A5A5A5u), tw(len2 / 4 + 8, 0x5A5A5A5Au);   // junk behind the data

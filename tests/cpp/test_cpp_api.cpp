@@ -67,8 +67,10 @@ int main() {
   try { distance::hamming::distance("ham", "hamming"); } catch (const Error& e) { threw = e.status == RF_ERR_INVALID_ARG; }
   EXPECT(threw);                                                                        // hamming.rs:617-620
   threw = false;
-  try { sk.distance_with_args(corpus, Args<uint32_t>{}.weights(1, 2, 3)); } catch (const Error& e) { threw = e.status == RF_ERR_UNSUPPORTED; }
+  try { distance::levenshtein::BatchComparator too_long(std::string(RF_MAX_QUERY_LEN + 1, 'a')); } catch (const Error& e) { threw = e.status == RF_ERR_UNSUPPORTED; }
   EXPECT(threw);
+  auto wg = sk.distance_with_args(corpus, Args<uint32_t>{}.weights(1, 2, 3));   // generic weights: Wagner-Fischer route
+  EXPECT(wg[1] == 0 && wg[0] == 6 && wg[2] == 22);
   std::printf(fails ? "cpp api: %d failure(s)\n" : "cpp api: all ok\n", fails);
   return fails ? 1 : 0;
 }

@@ -217,3 +217,14 @@ def test_simple_metrics_vs_oracle(core):
         assert core.core_simple(0, a.ctypes.data, len(a), b.ctypes.data, len(b)) == orc.pair("hamming", "distance", a, b, pad=True)
         assert core.core_simple(1, a.ctypes.data, len(a), b.ctypes.data, len(b)) == orc.pair("prefix", "similarity", a, b)
         assert core.core_simple(2, a.ctypes.data, len(a), b.ctypes.data, len(b)) == orc.pair("postfix", "similarity", a, b)
+
+
+def test_weighted_wagner_fischer_vs_oracle_and_textbook(core):
+    core.core_wf.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64]
+    core.core_wf.restype = C.c_uint64
+    rng = np.random.default_rng(88)
+    for a, b in _pairs(rng, 1500, [0] + QL, CL, 3):
+        for w in ((1, 2, 3), (2, 1, 1), (3, 5, 4), (0, 1, 1), (7, 7, 9), (1, 1, 1)):
+            got = core.core_wf(a.ctypes.data, len(a), b.ctypes.data, len(b), *w)
+            assert got == orc.tb("levenshtein", a, b, *w), (bytes(a), bytes(b), w)
+            assert got == orc.pair("levenshtein", "distance", a, b, weights=w), (bytes(a), bytes(b), w)

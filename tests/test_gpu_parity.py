@@ -80,9 +80,12 @@ def test_single_word_cutoffs(qlen):
     check("jaro_winkler", "similarity", q, chars, offsets, corpus, prefix_weight=0.25)
     for c in (0.0, 0.5, 0.9):
         check("ratio", "similarity", q, chars, offsets, corpus, cutoff=c)
-    for w in ((2, 2, 2), (1, 1, 2), (3, 3, 7), (0, 0, 5)):
-        for c in (None, 3, 10, 100):
+    for w in ((2, 2, 2), (1, 1, 2), (3, 3, 7), (0, 0, 5), (1, 2, 3), (2, 1, 1), (3, 5, 4), (0, 1, 1), (7, 7, 9)):
+        for c in (None, 3, 10, 100):   # uniform, indel-class, zero and generic (Wagner-Fischer) weight classes
             check("levenshtein", "distance", q, chars, offsets, corpus, weights=w, cutoff=c)
+        check("levenshtein", "similarity", q, chars, offsets, corpus, weights=w)
+        check("levenshtein", "normalized_similarity", q, chars, offsets, corpus, weights=w)
+        check("levenshtein", "normalized_distance", q, chars, offsets, corpus, weights=w, cutoff=0.4)
     corpus.close()
 
 
@@ -117,6 +120,8 @@ def test_multi_word_integer_metrics(qlen):
         check("levenshtein", "distance", q, chars, offsets, corpus, weights=w, cutoff=c)
     check("lcs_seq", "similarity", q, chars, offsets, corpus, cutoff=qlen // 2)
     check("levenshtein", "distance", q, chars, offsets, corpus, weights=(1, 1, 2))
+    if qlen <= 2048:
+        check("levenshtein", "distance", q, chars, offsets, corpus, weights=(1, 2, 3), cutoff=qlen)
     check("ratio", "similarity", q, chars, offsets, corpus, cutoff=0.5)
     corpus.close()
 
@@ -198,8 +203,6 @@ def test_reference_golden_vectors_on_gpu():
     for rec in G["cases"]:
         a = rec["args"]
         w = tuple(a["weights"]) if "weights" in a else None
-        if w == (1, 2, 3):
-            continue
         wide = "s1" not in rec or "s2" not in rec   # non-ASCII cases: u32 elements (code points)
         e1 = np.array(rec["s1_cp"], np.uint32) if "s1_cp" in rec else np.frombuffer(rec["s1"].encode(), np.uint8)
         e2 = np.array(rec["s2_cp"], np.uint32) if "s2_cp" in rec else np.frombuffer(rec["s2"].encode(), np.uint8)
@@ -379,8 +382,9 @@ def test_hamming_prefix_postfix_known_answers():
 
 def test_unsupported_is_loud():
     c = rf.Corpus.from_strings([b"abc"])
-    with pytest.raises(rf.RfError) as ei:
-        rf.distance.levenshtein.BatchComparator(b"abcd").distance_with_args(c, rf.Args().weights(1, 2, 3))
+    assert rf.distance.levenshtein.BatchComparator(b"abcd").distance_with_args(c, rf.Args().weights(1, 2, 3)).tolist() == [2]
+    with pytest.raises(rf.RfError) as ei:   # generic weights (Wagner-Fischer) are limited to queries of 2048 elements
+        rf.distance.levenshtein.BatchComparator(np.full(2049, 97, np.uint8)).distance_with_args(c, rf.Args().weights(1, 2, 3))
     assert ei.value.status == _ffi.RF_ERR_UNSUPPORTED
     with pytest.raises(rf.RfError):
         rf.distance.levenshtein.BatchComparator(np.zeros(_ffi.RF_MAX_QUERY_LEN + 1, np.uint8))

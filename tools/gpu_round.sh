@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python tools/bench_configs.py simple > gpurun_out/cfg_simple.jsonl 2> gpurun_out/cfg_simple.err
-cat gpurun_out/cfg_simple.jsonl; tail -3 gpurun_out/cfg_simple.err
+timeout 1800 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "cutoffs or golden or unsupported or multi_word_integer or cpp" > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+tail -12 gpurun_out/pytest_gpu.log

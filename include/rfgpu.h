@@ -32,7 +32,7 @@ typedef enum rf_status {
   RF_ERR_OOM = 4
 } rf_status;
 
-/* metric modules: distance/{levenshtein,indel,lcs_seq,osa,jaro,jaro_winkler,hamming,prefix,postfix}.rs and
+/* metric modules: distance/{levenshtein,indel,lcs_seq,osa,jaro,jaro_winkler,hamming,prefix,postfix,damerau_levenshtein}.rs and
  * fuzz.rs (ratio) */
 typedef enum rf_metric {
   RF_LEVENSHTEIN = 0,
@@ -44,7 +44,8 @@ typedef enum rf_metric {
   RF_RATIO = 6,
   RF_HAMMING = 7, /* hamming.rs:136-199; see rf_args.pad */
   RF_PREFIX = 8,  /* prefix.rs:47-71: similarity = common prefix length */
-  RF_POSTFIX = 9  /* postfix.rs:47-71: similarity = common suffix length */
+  RF_POSTFIX = 9, /* postfix.rs:47-71: similarity = common suffix length */
+  RF_DAMERAU_LEVENSHTEIN = 10 /* damerau_levenshtein.rs:111-214 (unrestricted; query <= 2048 elements) */
 } rf_metric;
 
 /* which BatchComparator method: distance / similarity / normalized_distance / normalized_similarity */

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
 
 METRICS = {"levenshtein": 0, "indel": 1, "lcs_seq": 2, "osa": 3, "jaro": 4, "jaro_winkler": 5, "ratio": 6,
-           "hamming": 7, "prefix": 8, "postfix": 9}
+           "hamming": 7, "prefix": 8, "postfix": 9, "damerau_levenshtein": 10}
 KINDS = {"distance": 0, "similarity": 1, "normalized_distance": 2, "normalized_similarity": 3}
 U64_MAX = 2**64 - 1
 
@@ -59,7 +59,7 @@ def lib():
             f.restype = C.c_uint64
         _lib.orc_tb_levenshtein_u8.argtypes = [vp, C.c_uint64, vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]
         _lib.orc_tb_levenshtein_u8.restype = C.c_uint64
-        for name in ("orc_tb_lcs_u8", "orc_tb_osa_u8"):
+        for name in ("orc_tb_lcs_u8", "orc_tb_osa_u8", "orc_tb_damerau_levenshtein_u8"):
             f = getattr(_lib, name)
             f.argtypes = [vp, C.c_uint64, vp, C.c_uint64]
             f.restype = C.c_uint64
@@ -153,7 +153,7 @@ def batch(metric, kind, query, chars, offsets, nthreads=1, **kw):
 
 
 def tb(name, a, b, *extra):
-    """Textbook DP cross-checks: name in levenshtein|lcs|osa|jaro|jaro_winkler (u8 only)."""
+    """Textbook DP cross-checks: name in levenshtein|lcs|osa|damerau_levenshtein|jaro|jaro_winkler (u8 only)."""
     a, b = _as_arr(a, np.uint8), _as_arr(b, np.uint8)
     l = lib()
     if name == "levenshtein":

@@ -142,6 +142,9 @@ uint64_t orc_tb_levenshtein_u8(const uint8_t* a, uint64_t n, const uint8_t* b, u
 }
 uint64_t orc_tb_lcs_u8(const uint8_t* a, uint64_t n, const uint8_t* b, uint64_t m) { return rftb::lcs(a, n, b, m); }
 uint64_t orc_tb_osa_u8(const uint8_t* a, uint64_t n, const uint8_t* b, uint64_t m) { return rftb::osa(a, n, b, m); }
+uint64_t orc_tb_damerau_levenshtein_u8(const uint8_t* a, uint64_t n, const uint8_t* b, uint64_t m) {
+  return rftb::damerau_levenshtein(a, n, b, m);
+}
 double orc_tb_jaro_u8(const uint8_t* a, uint64_t n, const uint8_t* b, uint64_t m) { return rftb::jaro(a, n, b, m); }
 double orc_tb_jaro_winkler_u8(const uint8_t* a, uint64_t n, const uint8_t* b, uint64_t m, double w) {
   return rftb::jaro_winkler(a, n, b, m, w);

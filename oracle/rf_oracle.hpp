@@ -14,6 +14,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
+#include <map>
 #include <vector>
 
 namespace rfo {
@@ -806,7 +807,7 @@ double jw_similarity_with_pm(const BlockPM& pm, const C1* s1, usize len1, const 
 
 // ---------------------------------------------------------------- score algebra (details/distance.rs)
 enum Metric : int { LEVENSHTEIN = 0, INDEL = 1, LCS_SEQ = 2, OSA = 3, JARO = 4, JARO_WINKLER = 5, RATIO = 6,
-                    HAMMING = 7, PREFIX = 8, POSTFIX = 9 };
+                    HAMMING = 7, PREFIX = 8, POSTFIX = 9, DAMERAU_LEVENSHTEIN = 10 };
 enum Kind : int { DISTANCE = 0, SIMILARITY = 1, NORM_DISTANCE = 2, NORM_SIMILARITY = 3 };
 
 struct Args {
@@ -821,6 +822,57 @@ struct Args {
   bool reference_quirks = false;   // Q1: literal RatioBatchComparator normalisation (fuzz.rs:141)
   bool pad = false;                // hamming.rs:112-118: unequal lengths count as mismatches instead of being an error
 };
+
+// ---------------------------------------------------------------- distance/damerau_levenshtein.rs
+// distance_zhao (:111-168): Zhao & Sahni's linear-space Damerau-Levenshtein.  The reference's HybridGrowingHashmap
+// (last row in which a character of s1 was seen, default -1) is a std::map here.
+template <class C1, class C2>
+usize dl_distance_zhao(const C1* s1, usize len1, const C2* s2, usize len2) {
+  using isz = long long;
+  const isz max_val = (isz)std::max(len1, len2) + 1;
+  std::map<uint64_t, isz> last_row_id;
+  auto get_row = [&](uint64_t ch) -> isz { auto it = last_row_id.find(ch); return it == last_row_id.end() ? -1 : it->second; };
+  const usize size = len2 + 2;
+  std::vector<isz> fr(size, max_val), r1(size, max_val), r(size);
+  r[0] = max_val;
+  for (usize j = 1; j < size; ++j) r[j] = (isz)j - 1;
+  for (usize i = 1; i <= len1; ++i) {
+    const uint64_t ch1 = (uint64_t)s1[i - 1];
+    std::swap(r, r1);
+    isz last_col_id = -1;
+    isz last_i2l1 = r[1];
+    r[1] = (isz)i;
+    isz t = max_val;
+    for (usize j = 1; j <= len2; ++j) {
+      const uint64_t ch2 = (uint64_t)s2[j - 1];
+      const isz diag = r1[j] + (ch1 != ch2 ? 1 : 0);
+      const isz left = r[j] + 1;
+      const isz up = r1[j + 1] + 1;
+      isz temp = std::min(diag, std::min(left, up));
+      if (ch1 == ch2) {
+        last_col_id = (isz)j;
+        fr[j + 1] = r1[j - 1];
+        t = last_i2l1;
+      } else {
+        const isz k = get_row(ch2);
+        const isz l = last_col_id;
+        if ((isz)j - l == 1) temp = std::min(temp, fr[j + 1] + ((isz)i - k));
+        else if ((isz)i - k == 1) temp = std::min(temp, t + ((isz)j - l));
+      }
+      last_i2l1 = r[j + 1];
+      r[j + 1] = temp;
+    }
+    last_row_id[ch1] = (isz)i;
+  }
+  return (usize)r[len2 + 1];
+}
+template <class C1, class C2>
+usize dl_distance_impl(const C1* s1, usize len1, const C2* s2, usize len2, usize score_cutoff) {  // :170-189
+  const usize diff = len1 > len2 ? len1 - len2 : len2 - len1;
+  if (score_cutoff < diff) return USIZE_MAX;
+  auto a = remove_common_affix(s1, len1, s2, len2);
+  return dl_distance_zhao(a.s1, a.len1, a.s2, a.len2);
+}
 
 // ---------------------------------------------------------------- distance/hamming.rs, prefix.rs, postfix.rs
 template <class C1, class C2>
@@ -880,6 +932,7 @@ struct Batch {
       }
       case OSA: return osa_batch_distance(pm, len1, s2, len2);        // osa.rs:435-460
       case HAMMING: return hamming_distance_impl(p, len1, s2, len2);  // hamming.rs:168-186 (cutoff and hint unused)
+      case DAMERAU_LEVENSHTEIN: return dl_distance_impl(p, len1, s2, len2, has_c ? c : USIZE_MAX);  // damerau_levenshtein.rs:198-214
       default: {                                                       // default _distance :157-179
         usize maximum = std::max(len1, len2);
         bool hc = has_c; usize cs = hc ? (maximum >= c ? maximum - c : 0) : 0;

@@ -5,6 +5,7 @@
 #pragma once
 #include <algorithm>
 #include <cstdint>
+#include <map>
 #include <vector>
 
 namespace rftb {
@@ -92,6 +93,33 @@ double jaro_winkler(const C1* a, uint64_t n, const C2* b, uint64_t m, double w =
   while (p < 4 && p < n && p < m && (uint64_t)a[p] == (uint64_t)b[p]) ++p;
   if (sim > 0.7) sim += (double)p * w * (1.0 - sim);
   return sim;
+}
+
+// Unrestricted Damerau-Levenshtein, Lowrance & Wagner's full-matrix algorithm (adjacent transpositions with
+// arbitrary edits in between): independent of the Zhao/Sahni linear-space version the reference uses.
+template <class C1, class C2>
+uint64_t damerau_levenshtein(const C1* a, uint64_t n, const C2* b, uint64_t m) {
+  const uint64_t INF = n + m;
+  std::vector<std::vector<uint64_t>> H(n + 2, std::vector<uint64_t>(m + 2, 0));
+  std::map<uint64_t, uint64_t> da;
+  H[0][0] = INF;
+  for (uint64_t i = 0; i <= n; ++i) { H[i + 1][0] = INF; H[i + 1][1] = i; }
+  for (uint64_t j = 0; j <= m; ++j) { H[0][j + 1] = INF; H[1][j + 1] = j; }
+  for (uint64_t i = 1; i <= n; ++i) {
+    uint64_t db = 0;
+    for (uint64_t j = 1; j <= m; ++j) {
+      const uint64_t i1 = da.count((uint64_t)b[j - 1]) ? da[(uint64_t)b[j - 1]] : 0, j1 = db;
+      uint64_t cost = 1;
+      if ((uint64_t)a[i - 1] == (uint64_t)b[j - 1]) { cost = 0; db = j; }
+      uint64_t v = H[i][j] + cost;
+      v = std::min(v, H[i + 1][j] + 1);
+      v = std::min(v, H[i][j + 1] + 1);
+      v = std::min(v, H[i1][j1] + (i - i1 - 1) + 1 + (j - j1 - 1));
+      H[i + 1][j + 1] = v;
+    }
+    da[(uint64_t)a[i - 1]] = i;
+  }
+  return H[n + 1][m + 1];
 }
 
 }  // namespace rftb

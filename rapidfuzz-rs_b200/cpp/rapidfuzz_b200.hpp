@@ -261,6 +261,7 @@ using jaro_winkler = MetricModule<RF_JARO_WINKLER, double>;
 using hamming = MetricModule<RF_HAMMING, uint32_t>;  // unequal lengths without Args::pad(): Error (status RF_ERR_INVALID_ARG)
 using prefix = MetricModule<RF_PREFIX, uint32_t>;
 using postfix = MetricModule<RF_POSTFIX, uint32_t>;
+using damerau_levenshtein = MetricModule<RF_DAMERAU_LEVENSHTEIN, uint32_t>;
 }  // namespace distance
 
 namespace fuzz {  // fuzz.rs:48-150

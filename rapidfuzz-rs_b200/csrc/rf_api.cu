@@ -348,7 +348,7 @@ static inline uint32_t alpha_hash(uint32_t x) { return (x * 2654435761u) >> 22; 
 static rf_status batch_create_bytes(rf_metric metric, const uint8_t* query, uint32_t query_len, int device, rf_batch** out) {
   if (!out) return fail(RF_ERR_INVALID_ARG, "out is NULL");
   *out = nullptr;
-  if ((int)metric < 0 || (int)metric > (int)RF_POSTFIX) return fail(RF_ERR_INVALID_ARG, "unknown metric");
+  if ((int)metric < 0 || (int)metric > (int)RF_DAMERAU_LEVENSHTEIN) return fail(RF_ERR_INVALID_ARG, "unknown metric");
   if (query_len && !query) return fail(RF_ERR_INVALID_ARG, "query is NULL");
   if (query_len > RF_MAX_QUERY_LEN) return fail(RF_ERR_UNSUPPORTED, "query longer than RF_MAX_QUERY_LEN");
   if ((metric == RF_JARO || metric == RF_JARO_WINKLER) && query_len > 2048)
@@ -498,7 +498,7 @@ static rf_status make_epi(const rf_batch* b, rf_kind kind, const rf_args* args, 
   if (b->metric == RF_RATIO) e->kind = K_NORM_SIMILARITY;  // fuzz.rs:127-149 has one method only
   e->unit32 = ((b->metric == RF_LEVENSHTEIN && e->wclass == WC_UNIFORM && e->w_ins == 1) || b->metric == RF_INDEL ||
                b->metric == RF_LCS_SEQ || b->metric == RF_OSA || b->metric == RF_HAMMING || b->metric == RF_PREFIX ||
-               b->metric == RF_POSTFIX)
+               b->metric == RF_POSTFIX || b->metric == RF_DAMERAU_LEVENSHTEIN)
                   ? 1
                   : 0;
   return RF_OK;
@@ -522,7 +522,7 @@ static rf_status score_view(const rf_batch* b, const CorpusView& cv, const LbAll
   if (!g.ok) return fail(RF_ERR_CUDA, "cudaSetDevice failed");
   L.corpus = cv;
   const Family fam0 = family_of(L.epi.metric, L.epi.wclass);
-  const bool use_lb = lb && lb->gdata && g_w1_path.load() != 1 && fam0 != F_SIMPLE && fam0 != F_WF;
+  const bool use_lb = lb && lb->gdata && g_w1_path.load() != 1 && fam0 != F_SIMPLE && fam0 != F_WF && fam0 != F_DL;
   if (use_lb) {
     L.lb = LbView{lb->perm, lb->lens, lb->goff, lb->gdata, lb->ngroups};
     L.lb_counter = counter_slot(device);
@@ -539,6 +539,9 @@ static rf_status score_view(const rf_batch* b, const CorpusView& cv, const LbAll
   else if (fam == F_WF) {
     if (b->len1 > 2048) return fail(RF_ERR_UNSUPPORTED, "generic Levenshtein weights: queries longer than 2048 elements");
     e = launch_wf(L);
+  } else if (fam == F_DL) {
+    if (b->len1 > 2048) return fail(RF_ERR_UNSUPPORTED, "Damerau-Levenshtein: queries longer than 2048 elements");
+    e = launch_dl(L);
   }
   else if (b->len1 <= 64) {
     const int path = g_w1_path.load();

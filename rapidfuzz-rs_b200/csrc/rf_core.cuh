@@ -25,10 +25,11 @@
 namespace rfk {
 
 enum Metric : int { M_LEVENSHTEIN = 0, M_INDEL = 1, M_LCS_SEQ = 2, M_OSA = 3, M_JARO = 4, M_JARO_WINKLER = 5, M_RATIO = 6,
-                    M_HAMMING = 7, M_PREFIX = 8, M_POSTFIX = 9 };
+                    M_HAMMING = 7, M_PREFIX = 8, M_POSTFIX = 9, M_DAMERAU_LEVENSHTEIN = 10 };
 enum Kind : int { K_DISTANCE = 0, K_SIMILARITY = 1, K_NORM_DISTANCE = 2, K_NORM_SIMILARITY = 3 };
 // which bit-parallel recurrence a metric needs
-enum Family : int { F_LEV = 0, F_LCS = 1, F_OSA = 2, F_JARO = 3, F_SIMPLE = 4, F_WF = 5 };  // F_SIMPLE: hamming / prefix / postfix; F_WF: generic weights
+enum Family : int { F_LEV = 0, F_LCS = 1, F_OSA = 2, F_JARO = 3, F_SIMPLE = 4, F_WF = 5, F_DL = 6 };
+// F_SIMPLE: hamming / prefix / postfix; F_WF: generic Levenshtein weights; F_DL: Damerau-Levenshtein
 // Levenshtein weight classes (levenshtein.rs:1301-1330)
 enum WeightClass : int { WC_UNIFORM = 0, WC_INDEL = 1, WC_ZERO = 2, WC_GENERIC = 3 };
 
@@ -312,6 +313,62 @@ RF_HD uint64_t weighted_wagner_fischer(const QB& qb, const TB& tb, uint32_t len1
     }
   }
   return cache(len1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Damerau-Levenshtein (unrestricted), Zhao & Sahni's linear-space algorithm as in damerau_levenshtein.rs:111-168.
+// The distance is symmetric, so the device runs it with the CANDIDATE as the outer sequence and the QUERY as the
+// inner one: the three rows then have len_inner+2 = len1+2 entries whatever the candidate's length.
+//   row(k, j)   reference to entry j of row k in {0,1,2}
+//   last_row(c) reference to "last outer row in which symbol c was seen", all -1 on entry and restored on exit
+template <class Outer, class Inner, class Row, class LastRow>
+RF_HD uint32_t damerau_zhao(const Outer& outer, uint32_t len_o, const Inner& inner, uint32_t len_i, const Row& row,
+                            const LastRow& last_row) {
+  const int32_t max_val = (int32_t)(len_o > len_i ? len_o : len_i) + 1;
+  const uint32_t size = len_i + 2;
+  uint32_t FR = 0, R1 = 1, R = 2;
+  for (uint32_t j = 0; j < size; ++j) {
+    row(FR, j) = max_val;
+    row(R1, j) = max_val;
+    row(R, j) = j == 0 ? max_val : (int32_t)j - 1;
+  }
+  for (uint32_t i = 1; i <= len_o; ++i) {
+    const uint32_t ch1 = outer(i - 1);
+    const uint32_t sw = R; R = R1; R1 = sw;
+    int32_t last_col_id = -1;
+    int32_t last_i2l1 = row(R, 1);
+    row(R, 1) = (int32_t)i;
+    int32_t t = max_val;
+    for (uint32_t j = 1; j <= len_i; ++j) {
+      const uint32_t ch2 = inner(j - 1);
+      const int32_t diag = row(R1, j) + (ch1 != ch2 ? 1 : 0);
+      const int32_t left = row(R, j) + 1;
+      const int32_t up = row(R1, j + 1) + 1;
+      int32_t temp = diag < left ? diag : left;
+      temp = temp < up ? temp : up;
+      if (ch1 == ch2) {
+        last_col_id = (int32_t)j;        // last occurrence of the outer symbol in the inner sequence
+        row(FR, j + 1) = row(R1, j - 1);  // H[i-2][j-2]
+        t = last_i2l1;                    // H[i-2][l-1]
+      } else {
+        const int32_t k = last_row(ch2);
+        const int32_t l = last_col_id;
+        if ((int32_t)j - l == 1) {
+          const int32_t tr = row(FR, j + 1) + ((int32_t)i - k);
+          temp = temp < tr ? temp : tr;
+        } else if ((int32_t)i - k == 1) {
+          const int32_t tr = t + ((int32_t)j - l);
+          temp = temp < tr ? temp : tr;
+        }
+      }
+      last_i2l1 = row(R, j + 1);
+      row(R, j + 1) = temp;
+    }
+    last_row(ch1) = (int32_t)i;
+  }
+  const uint32_t result = (uint32_t)row(R, len_i + 1);
+  for (uint32_t i = 0; i < len_o; ++i) last_row(outer(i)) = -1;
+  return result;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -620,6 +677,7 @@ RF_HD Family family_of(int metric, int wclass) {
     case M_INDEL: case M_LCS_SEQ: case M_RATIO: return F_LCS;
     case M_OSA: return F_OSA;
     case M_HAMMING: case M_PREFIX: case M_POSTFIX: return F_SIMPLE;
+    case M_DAMERAU_LEVENSHTEIN: return F_DL;
     default: return F_JARO;
   }
 }

@@ -2054,6 +2054,79 @@ cudaError_t launch_wf(const ScanLaunch& L) {
   return e;
 }
 
+// ------------------------------------------------------------------------------------------------ dl
+// Damerau-Levenshtein: thread per candidate, the three DP rows (len1+2 entries each) and the 256-entry last-row
+// table in thread-strided global scratch (entry e of thread t at scratch[e*T + t]).
+struct DlParams {
+  const uint8_t* chars;
+  const uint32_t* off32;
+  const uint64_t* off64;
+  uint64_t n;
+  const uint8_t* qbytes;
+  uint32_t len1;
+  int32_t* scratch;  // [(3*(len1+2) + 256)][T]; the last 256 rows (last-row table) start out as -1
+  uint32_t T;
+  void* out;
+  int out_f64;
+  Epi epi;
+};
+
+__global__ void dl_init_kernel(int32_t* last_row, uint64_t count) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x) last_row[i] = -1;
+}
+
+__global__ void __launch_bounds__(128) dl_kernel(const __grid_constant__ DlParams p) {
+  extern __shared__ __align__(16) uint8_t dl_q[];
+  for (uint32_t i = threadIdx.x; i < p.len1; i += blockDim.x) dl_q[i] = p.qbytes[i];
+  __syncthreads();
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t T = p.T;
+  const uint32_t rowlen = p.len1 + 2;
+  int32_t* rows = p.scratch + t;
+  int32_t* last = p.scratch + (size_t)3 * rowlen * T + t;
+  const bool off64 = p.off64 != nullptr;
+  for (uint64_t c = t; c < p.n; c += T) {
+    const uint64_t o0 = off64 ? p.off64[c] : (uint64_t)p.off32[c];
+    const uint64_t o1 = off64 ? p.off64[c + 1] : (uint64_t)p.off32[c + 1];
+    const uint32_t len2 = (uint32_t)(o1 - o0);
+    const uint8_t* txt = p.chars + o0;
+    const uint32_t raw = damerau_zhao([&](uint32_t i) -> uint32_t { return txt[i]; }, len2,
+                                      [&](uint32_t j) -> uint32_t { return dl_q[j]; }, p.len1,
+                                      [&](uint32_t k, uint32_t j) -> int32_t& { return rows[((size_t)k * rowlen + j) * T]; },
+                                      [&](uint32_t ch) -> int32_t& { return last[(size_t)ch * T]; });
+    if (p.out_f64) reinterpret_cast<double*>(p.out)[c] = finish_norm(p.epi, raw, p.len1, len2);
+    else reinterpret_cast<uint32_t*>(p.out)[c] = finish_int(p.epi, raw, p.len1, len2);
+  }
+}
+
+cudaError_t launch_dl(const ScanLaunch& L) {
+  if (L.query.len1 > 2048) return cudaErrorNotSupported;
+  DlParams p{};
+  p.chars = L.corpus.chars;
+  p.off32 = L.corpus.off32;
+  p.off64 = L.corpus.off64;
+  p.n = L.corpus.n;
+  p.qbytes = L.query.qbytes;
+  p.len1 = L.query.len1;
+  p.out = L.out;
+  p.out_f64 = L.out_is_f64;
+  p.epi = L.epi;
+  uint64_t blocks = (p.n + 127) / 128;
+  const uint64_t max_blocks = (uint64_t)L.sm_count * 4;
+  if (blocks > max_blocks) blocks = max_blocks;
+  if (blocks < 1) blocks = 1;
+  p.T = (uint32_t)blocks * 128u;
+  const size_t entries = (size_t)3 * (p.len1 + 2) + 256;
+  cudaError_t e = dev_alloc(&p.scratch, entries * p.T * sizeof(int32_t), L.stream);
+  if (e != cudaSuccess) return e;
+  dl_init_kernel<<<(uint32_t)blocks, 256, 0, L.stream>>>(p.scratch + (size_t)3 * (p.len1 + 2) * p.T, (uint64_t)256 * p.T);
+  dl_kernel<<<(uint32_t)blocks, 128, p.len1 + 16, L.stream>>>(p);
+  g_launches.fetch_add(2);
+  e = cudaGetLastError();
+  dev_free(p.scratch, L.stream);
+  return e;
+}
+
 // ------------------------------------------------------------------------------------------------ jaro mw
 template <int MAXQ>
 __global__ void __launch_bounds__(128) jaro_mw_kernel(const __grid_constant__ MwParams p) {

@@ -81,6 +81,8 @@ cudaError_t launch_scan_band(const ScanLaunch& L, uint32_t cut);
 cudaError_t launch_simple(const ScanLaunch& L, uint32_t* err_flag);
 // Levenshtein with generic weights: Wagner-Fischer, query <= 2048 (cudaErrorNotSupported beyond).
 cudaError_t launch_wf(const ScanLaunch& L);
+// Damerau-Levenshtein (Zhao-Sahni), query <= 2048 (cudaErrorNotSupported beyond).
+cudaError_t launch_dl(const ScanLaunch& L);
 // Jaro / Jaro-Winkler with a multi-word query (65..2048).
 cudaError_t launch_jaro_mw(const ScanLaunch& L);
 

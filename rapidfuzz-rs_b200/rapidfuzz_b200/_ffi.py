@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("RF_LIB_PATH") or os.path.join(_ROOT, "lib", "librfgpu
 
 RF_OK, RF_ERR_INVALID_ARG, RF_ERR_UNSUPPORTED, RF_ERR_CUDA, RF_ERR_OOM = range(5)
 METRICS = {"levenshtein": 0, "indel": 1, "lcs_seq": 2, "osa": 3, "jaro": 4, "jaro_winkler": 5, "ratio": 6,
-           "hamming": 7, "prefix": 8, "postfix": 9}
+           "hamming": 7, "prefix": 8, "postfix": 9, "damerau_levenshtein": 10}
 KINDS = {"distance": 0, "similarity": 1, "normalized_distance": 2, "normalized_similarity": 3}
 NONE_U32 = 0xFFFFFFFF
 RF_MAX_QUERY_LEN = 16384

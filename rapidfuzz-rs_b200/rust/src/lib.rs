@@ -39,6 +39,7 @@ pub const RF_RATIO: c_int = 6;
 pub const RF_HAMMING: c_int = 7;
 pub const RF_PREFIX: c_int = 8;
 pub const RF_POSTFIX: c_int = 9;
+pub const RF_DAMERAU_LEVENSHTEIN: c_int = 10;
 pub const RF_DISTANCE: c_int = 0;
 pub const RF_SIMILARITY: c_int = 1;
 pub const RF_NORMALIZED_DISTANCE: c_int = 2;
@@ -246,6 +247,7 @@ pub mod distance {
     metric_module!(jaro_winkler, RF_JARO_WINKLER, f64, true);
     metric_module!(prefix, RF_PREFIX, usize, false);
     metric_module!(postfix, RF_POSTFIX, usize, false);
+    metric_module!(damerau_levenshtein, RF_DAMERAU_LEVENSHTEIN, usize, false);
     // hamming: same shape with `Args::pad` -> `rf_args.pad`; without it a candidate of another length makes the call
     // return status 1 ("Differing length arguments provided"), which maps to Err(hamming::Error::DifferentLengthArgs).
     metric_module!(hamming, RF_HAMMING, usize, false);

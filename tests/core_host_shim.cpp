@@ -159,6 +159,17 @@ double core_jaro32(const uint8_t* q, uint32_t len1, const uint8_t* s2, uint32_t 
 
 double core_div3(double x) { return div3_exact(x); }
 
+// Damerau-Levenshtein through the routine the kernel runs: candidate outer, query inner, strided scratch
+uint32_t core_dl(const uint8_t* q, uint32_t len1, const uint8_t* s2, uint32_t len2) {
+  const size_t T = 3, rowlen = len1 + 2;
+  std::vector<int32_t> rows(3 * rowlen * T, 12345), last(256 * T, -1);
+  const uint32_t r = damerau_zhao([&](uint32_t i) -> uint32_t { return s2[i]; }, len2, [&](uint32_t j) -> uint32_t { return q[j]; }, len1,
+                                  [&](uint32_t k, uint32_t j) -> int32_t& { return rows[(k * rowlen + j) * T]; },
+                                  [&](uint32_t ch) -> int32_t& { return last[ch * T]; });
+  for (size_t i = 0; i < 256; ++i) if (last[i * T] != -1) return 0xBADBADu;  // the table must be restored
+  return r;
+}
+
 // generic weighted Levenshtein through the routine the Wagner-Fischer kernel runs (strided row like on the device)
 uint64_t core_wf(const uint8_t* q, uint32_t len1, const uint8_t* s2, uint32_t len2, uint64_t wi, uint64_t wd, uint64_t ws) {
   const size_t stride = 3;

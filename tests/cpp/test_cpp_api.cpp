@@ -61,6 +61,7 @@ int main() {
   }
   EXPECT(distance::hamming::distance("hamming", "humming") == 1);                     // hamming.rs:198
   EXPECT(distance::hamming::distance_with_args("ham", "hamming", Args<uint32_t>{}.pad(true)) == 4);  // :622-625
+  EXPECT(distance::damerau_levenshtein::distance("CA", "ABC") == 2);                  // damerau_levenshtein.rs:226
   EXPECT(distance::prefix::similarity("prefix", "preference") == 4);                  // prefix.rs:122
   EXPECT(distance::postfix::similarity("postfix", "prefix") == 3);                    // postfix.rs:122
   bool threw = false;

@@ -73,6 +73,18 @@ add("hamming", "distance", "ham", "hamming", 4, H + ":622-625", pad=True)
 add("hamming", "distance", "ham", "hamming", None, H + ":627-634", pad=True, cutoff=3)
 add("hamming", "distance", "Friedrich Nietzs", "Jean-Paul Sartre", 14, H + ":639")
 add("hamming", "distance", "hamming", "humming", 1, H + ":198")
+# ---- damerau_levenshtein.rs:639-716
+D = "distance/damerau_levenshtein.rs"
+add("damerau_levenshtein", "distance", "", "", 0, D + ":641")
+add("damerau_levenshtein", "distance", "aaaa", "", 4, D + ":642")
+for s2, d, ns in (("aaaa", 0, 1.0), ("aaa", 1, 0.75), ("aaab", 1, 0.75), ("bbbb", 4, 0.0)):
+    add("damerau_levenshtein", "distance", "aaaa", s2, d, D + ":648-655")
+    add("damerau_levenshtein", "normalized_similarity", "aaaa", s2, ns, D + ":658-690", tol=1e-4, cutoff=0.0)
+add("damerau_levenshtein", "distance", "abaa", "baaa", 1, D + ":651-654")
+add("damerau_levenshtein", "normalized_similarity", "abaa", "baaa", 0.75, D + ":673-681", tol=1e-4, cutoff=0.0)
+add("damerau_levenshtein", "distance", "CA", "ABC", 2, D + ":656,34,226,402")
+add("damerau_levenshtein", "distance", "\u0418\u0432\u0430\u043d\u043a\u043e", "\u041f\u0435\u0442\u0440\u0443\u043d\u043a\u043e", 5, D + ":695-698")
+add("damerau_levenshtein", "distance", "\u0418\u0432a\u043d\u043aoIvan", "\u041f\u0435\u0442\u0440\u0443\u043d\u043a\u043e", 10, D + ":700-703")
 # ---- prefix.rs / postfix.rs doc-tests
 add("prefix", "similarity", "prefix", "preference", 4, "distance/prefix.rs:122,256")
 add("postfix", "similarity", "postfix", "prefix", 3, "distance/postfix.rs:122,256")

@@ -228,3 +228,12 @@ def test_weighted_wagner_fischer_vs_oracle_and_textbook(core):
             got = core.core_wf(a.ctypes.data, len(a), b.ctypes.data, len(b), *w)
             assert got == orc.tb("levenshtein", a, b, *w), (bytes(a), bytes(b), w)
             assert got == orc.pair("levenshtein", "distance", a, b, weights=w), (bytes(a), bytes(b), w)
+
+
+def test_damerau_zhao_vs_oracle(core):
+    core.core_dl.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+    core.core_dl.restype = C.c_uint32
+    rng = np.random.default_rng(99)
+    for a, b in _pairs(rng, 3000, [0] + QL, CL, 3):
+        got = core.core_dl(a.ctypes.data, len(a), b.ctypes.data, len(b))
+        assert got == orc.pair("damerau_levenshtein", "distance", a, b), (bytes(a), bytes(b), got)

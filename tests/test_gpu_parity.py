@@ -355,6 +355,24 @@ def test_hamming_prefix_postfix_vs_oracle(qlen):
     corpus.close()
 
 
+@pytest.mark.parametrize("qlen", [0, 1, 2, 5, 32, 64, 65, 200])
+def test_damerau_levenshtein_vs_oracle(qlen):
+    rng = np.random.default_rng(900 + qlen)
+    q = (rng.integers(0, 3, qlen) + 97).astype(np.uint8)
+    chars, offsets = make_corpus(rng, 1500, [0, 1, 2, 3, 8, 20, 33, 64, 70, max(qlen, 1), qlen + 2], alphabet=3, query=q, near_frac=0.5)
+    corpus = rf.Corpus(chars, offsets)
+    for kind in ALL_KINDS:
+        check("damerau_levenshtein", kind, q, chars, offsets, corpus)
+    for c in (0, 1, 2, 3, 10, 64, 2**64 - 1):
+        check("damerau_levenshtein", "distance", q, chars, offsets, corpus, cutoff=c)
+    for c in (0.0, 0.3, 0.7, 1.0):
+        check("damerau_levenshtein", "normalized_similarity", q, chars, offsets, corpus, cutoff=c)
+        check("damerau_levenshtein", "normalized_distance", q, chars, offsets, corpus, cutoff=c)
+    corpus.close()
+    assert rf.distance.damerau_levenshtein.distance("CA", "ABC") == 2                      # damerau_levenshtein.rs:226
+    assert rf.distance.damerau_levenshtein.distance("Иванко", "Петрунко") == 5            # :695-698 (u32 elements)
+
+
 def _gpu_pad(metric, kind, q, corpus, cutoff=None, pad=False):
     b = _bc(metric, q)
     a = rf.Args().pad(pad)

@@ -189,3 +189,17 @@ def test_ratio_quirk_q1():
     a, b = "this is a test", "this is a test!"
     assert abs(orc.pair("ratio", "similarity", a, b) - 28 / 29) < 1e-12
     assert abs(orc.pair("ratio", "similarity", a, b, reference_quirks=True) - 14 / 15) < 1e-12
+
+
+def test_damerau_levenshtein_zhao_vs_textbook():
+    """The restated Zhao/Sahni linear-space algorithm == Lowrance-Wagner full-matrix Damerau-Levenshtein; OSA >= DL."""
+    rng = np.random.default_rng(123)
+    for _ in range(4000):
+        a = (rng.integers(0, 3, int(rng.integers(0, 14))) + 97).astype(np.uint8)
+        b = (rng.integers(0, 3, int(rng.integers(0, 14))) + 97).astype(np.uint8)
+        d = orc.pair("damerau_levenshtein", "distance", a, b)
+        assert d == orc.tb("damerau_levenshtein", a, b), (bytes(a), bytes(b))
+        assert d == orc.pair("damerau_levenshtein", "distance", b, a)
+        assert orc.tb("levenshtein", a, b) >= orc.tb("osa", a, b) >= d
+        for c in (0, 1, 2, 5):
+            assert orc.pair("damerau_levenshtein", "distance", a, b, cutoff=c) == (d if d <= c else None)

@@ -222,6 +222,28 @@ if __name__ == "__main__":
                               "algorithmic_GBps": alg / (ms * 1e-3) / 1e9, "hbm_frac_of_measured_peak": alg / (ms * 1e-3) / 1e9 / PEAK,
                               "matches_oracle_sample": ok}), flush=True)
             b.close(); corpus.close()
+    if "dp" in which:   # the O(len1*len2) DP metrics: generic Levenshtein weights (Wagner-Fischer) and Damerau-Levenshtein
+        for m, w in (("levenshtein", (1, 2, 3)), ("damerau_levenshtein", None)):
+            q = rf.synth_query(2, 32)
+            n = int(1e7 * scale)
+            chars, offsets = rf.synth_corpus(2, q, n, 8, 64, 16)
+            corpus = rf.Corpus(chars, offsets)
+            b = type("B", (rf._scorer.BatchComparatorBase,), {"METRIC": m})(q)
+            out = torch.empty(n, dtype=torch.int32, device="cuda")
+            st = torch.cuda.current_stream().cuda_stream
+            a = rf.Args() if w is None else rf.Args().weights(*w)
+            ms = timed(lambda: b.score_into("distance", corpus, out.data_ptr(), a, st), 5, warmup=1)
+            mm = min(n, 100_000)
+            kw = {} if w is None else {"weights": w}
+            exp = orc.batch(m, "distance", q, chars[: int(offsets[mm])], offsets[: mm + 1], nthreads=0, **kw)
+            ok = bool(np.array_equal(out[:mm].cpu().numpy().view(np.uint32), exp))
+            t0 = time.perf_counter()
+            orc.batch(m, "distance", q, chars[: int(offsets[min(n, 1_000_000)])], offsets[: min(n, 1_000_000) + 1], nthreads=0, **kw)
+            cpu = min(n, 1_000_000) / (time.perf_counter() - t0)
+            print(json.dumps({"config": "C2-shape %s%s" % (m, "" if w is None else " weights %s" % (w,)), "n": n, "ms_per_step": ms,
+                              "pairs_per_s": n / (ms * 1e-3), "matches_oracle_sample": ok,
+                              "cpu_oracle_pairs_per_s_all_threads": cpu, "cpu_threads": orc.max_threads()}), flush=True)
+            b.close(); corpus.close()
     if "widen" in which:
         widen(int(1e8 * scale))
     if "post" in which:

@@ -376,9 +376,10 @@ RF_HD uint32_t damerau_zhao(const Outer& outer, uint32_t len_o, const Inner& inn
 // candidate is compared with the query 4 bytes at a time.  q4(i) / t4(i) return bytes 4i..4i+3 of the query /
 // candidate packed little-endian (garbage beyond the end is masked here); qb(j) / tb(j) single bytes.
 RF_HD uint32_t differing_bytes(uint32_t a, uint32_t b) {  // number of byte lanes in which a and b differ
-  uint32_t x = a ^ b;
-  x |= x >> 4; x |= x >> 2; x |= x >> 1;                 // bit 0 of every byte = byte is non-zero
-  return (uint32_t)popc(x & 0x01010101u);
+  const uint32_t x = a ^ b;
+  // bit 7 of every byte = that byte of x is non-zero (low 7 bits carry into bit 7, or bit 7 itself is set)
+  const uint32_t y = (((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
+  return (uint32_t)popc(y);
 }
 template <class Q4, class T4>
 RF_HD uint32_t hamming_raw(const Q4& q4, const T4& t4, uint32_t len1, uint32_t len2) {

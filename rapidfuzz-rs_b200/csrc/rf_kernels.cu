@@ -201,12 +201,15 @@ struct LaneSrcT {
 //   PRMT (byte extract) . IMAD (ch*128 + lane base) . LDS . 7 LOP3 . 3 IMAD (add, HP*2+1, HN*2)
 // `two` is the constant 2 passed as a kernel parameter: opaque to ptxas, so x*2+1 stays an IMAD (FMA pipe)
 // instead of becoming an ALU-pipe LEA.
-template <class Rd>
-__device__ __forceinline__ uint32_t lev_w1_u32_fast(uint32_t pm_lane_saddr, Rd rd, uint32_t len2, uint32_t len1,
-                                                    uint32_t two) {
+// OSA = true adds the transposition term of osa.rs:84-135 (TR = (((~D0_prev) & X) << 1) & X_prev, D0 |= TR):
+// two more LOP3 and one more IMAD per character.
+template <bool OSA, class Rd>
+__device__ __forceinline__ uint32_t myers_w1_u32_fast(uint32_t pm_lane_saddr, Rd rd, uint32_t len2, uint32_t len1,
+                                                      uint32_t two) {
   const uint32_t one = two >> 1;
   uint32_t VP = 0xFFFFFFFFu << (32u - len1);
   uint32_t VN = 0;
+  uint32_t D0p = 0, Xp = 0;  // OSA only: previous column's D0 and match mask
   // table address of text byte K of w = byte*128 + lane base.  IDP.4A (dot product of the 4 bytes of w with a
   // selector word holding 128 in byte K, plus the base) does extract + scale + add in ONE FMA-pipe instruction;
   // the PRMT + IMAD pair it replaces costs an ALU-pipe slot, and the ALU pipe is this kernel's bound.
@@ -224,7 +227,12 @@ __device__ __forceinline__ uint32_t lev_w1_u32_fast(uint32_t pm_lane_saddr, Rd r
     uint32_t addr, X;                                                                \
     RF_LEV32_ADDR(K)                                                                 \
     asm("ld.shared.u32 %0, [%1];" : "=r"(X) : "r"(addr));                            \
-    const uint32_t D0 = ((((X & VP) + VP) ^ VP) | X) | VN;                           \
+    uint32_t D0 = ((((X & VP) + VP) ^ VP) | X) | VN;                                 \
+    if constexpr (OSA) {                                                             \
+      D0 |= (((~D0p) & X) * two) & Xp;                                               \
+      D0p = D0;                                                                      \
+      Xp = X;                                                                        \
+    }                                                                                \
     uint32_t HP = VN | ~(D0 | VP);                                                   \
     uint32_t HN = D0 & VP;                                                           \
     HP = HP * two + one;                                                             \
@@ -298,6 +306,10 @@ __device__ __forceinline__ uint32_t lev_w1_u32_fast(uint32_t pm_lane_saddr, Rd r
 #undef RF_LEV32_ADDR
   return len2 + (uint32_t)__popc(VP) - (uint32_t)__popc(VN);
 }
+template <class Rd>
+__device__ __forceinline__ uint32_t lev_w1_u32_fast(uint32_t pm_lane_saddr, Rd rd, uint32_t len2, uint32_t len1, uint32_t two) {
+  return myers_w1_u32_fast<false>(pm_lane_saddr, rd, len2, len1, two);
+}
 
 // One candidate: raw bit-parallel kernel + score algebra.  pm_lane = &pm[lane] of the lane-replicated table.
 template <int FAM, class W, class Src>
@@ -323,6 +335,7 @@ __device__ __forceinline__ void score_one(const W* __restrict__ pm_lane, const S
     } else {
       if constexpr (FAM == F_LEV && sizeof(W) == 4) raw = lev_w1_u32_fast(smem_u32(pm_lane), src.reader(), len2, len1, two);
       else if constexpr (FAM == F_LEV) raw = lev_w1<W>(tab, src.reader(), len2, len1);
+      else if constexpr (FAM == F_OSA && sizeof(W) == 4) raw = myers_w1_u32_fast<true>(smem_u32(pm_lane), src.reader(), len2, len1, two);
       else if constexpr (FAM == F_OSA) raw = osa_w1<W>(tab, src.reader(), len2, len1);
       else raw = lcs_w1<W>(tab, src.reader(), len2);
     }
@@ -592,6 +605,7 @@ __global__ void __launch_bounds__(NT) scan_lb_kernel(const __grid_constant__ LbP
       if constexpr (RAWDIST) {  // len1 >= 1 (checked by the launcher)
         uint32_t raw;
         if constexpr (FAM == F_LEV && sizeof(W) == 4) raw = lev_w1_u32_fast(smem_u32(pm_lane), src.reader(), len2, p.len1, p.two);
+        else if constexpr (FAM == F_OSA && sizeof(W) == 4) raw = myers_w1_u32_fast<true>(smem_u32(pm_lane), src.reader(), len2, p.len1, p.two);
         else {
           auto tab = [&](uint32_t ch) -> W { return pm_lane[ch * 32u]; };
           if constexpr (FAM == F_LEV) raw = lev_w1<W>(tab, src.reader(), len2, p.len1);

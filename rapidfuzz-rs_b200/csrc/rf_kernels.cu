@@ -872,7 +872,7 @@ static cudaError_t launch_jaro32(const ScanLaunch& L) {
   p.out = L.out;
   p.out_f64 = 1;
   p.two = 2;
-  p.chunk = 16;
+  p.chunk = 16;  // groups per scheduler grab; 4...128 measured identical (1.99 ms): neither the atomic nor the tail matter
   p.counter = L.lb_counter;
   p.epi = L.epi;
   e = cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), L.stream);

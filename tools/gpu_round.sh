@@ -1,10 +1,6 @@
 #!/bin/bash
-# Dev helper run under gpurun.  Output -> gpurun_out/
 mkdir -p gpurun_out
-timeout 900 python tools/bench_configs.py osa,simple > gpurun_out/cfg_osa_simple.jsonl 2> gpurun_out/cfg_osa_simple.err
-python - <<'PY'
-import json
-for l in open('gpurun_out/cfg_osa_simple.jsonl'):
-    d=json.loads(l); print(d['config'], round(d['ms_per_step'],3), 'ms', '%.3g'%d['pairs_per_s'], d.get('matches_oracle_sample'))
-PY
-tail -2 gpurun_out/cfg_osa_simple.err
+for ch in 16 4 8 32 64 128; do
+  RF_LB_CHUNK=$ch timeout 300 python bench.py --steps 200 --no-cpu-baseline --e2e-steps 1 > gpurun_out/b.json 2> gpurun_out/b.err
+  echo "chunk $ch: $(python -c "import json;d=json.load(open('gpurun_out/b.json'));print(d['ms_per_step'])")"
+done

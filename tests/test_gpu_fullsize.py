@@ -94,3 +94,35 @@ def test_config4_full_size_1e8_jaro_winkler():
     assert np.max(np.abs(fast[:m] - exp)) <= 1e-6
     assert np.array_equal(fast[:m], exp)
     corpus.close()
+
+
+def test_corpus_beyond_4gib_uses_64bit_offsets():
+    """1.25e8 candidates = 4.5 GB of characters: the device keeps u64 CSR offsets (total >= 2^32 - 16).  Resident
+    path (interleaved layout built from u64 offsets), CSR path and the streaming pipeline (chunk bases beyond
+    2^32) must agree with each other everywhere and with the oracle at both ends of the corpus."""
+    n = 125_000_000
+    q = rf.synth_query(6, 32)
+    chars, offsets = rf.synth_corpus(6, q, n, 8, 64, 16)
+    assert int(offsets[n]) >= 2**32
+    corpus = rf.Corpus(chars, offsets)
+    d = gpu_batch("levenshtein", "distance", q, corpus)
+    _ffi.check(_ffi.lib().rf_set_option(b"single_word_path", 1))     # CSR / TMA-tile kernel on the resident corpus
+    try:
+        d_csr = gpu_batch("levenshtein", "distance", q, corpus)
+    finally:
+        _ffi.check(_ffi.lib().rf_set_option(b"single_word_path", 0))
+    assert np.array_equal(d, d_csr)
+    b = _bc("levenshtein", q)
+    s = b.stream("distance", chars, offsets)                         # u64 host offsets, chunked
+    b.close()
+    assert np.array_equal(d, s)
+    m = 300_000
+    assert np.array_equal(d[:m], orc.batch("levenshtein", "distance", q, chars[: int(offsets[m])], offsets[: m + 1], nthreads=0))
+    tail = orc.batch("levenshtein", "distance", q, chars[int(offsets[n - m]):], offsets[n - m:] - offsets[n - m], nthreads=0)
+    assert np.array_equal(d[-m:], tail)
+    # multi-word banded path reads the same u64 offsets
+    q3 = rf.synth_query(7, 100)
+    bd = gpu_batch("levenshtein", "distance", q3, corpus, cutoff=40)
+    exp = orc.batch("levenshtein", "distance", q3, chars[int(offsets[n - m]):], offsets[n - m:] - offsets[n - m], nthreads=0, cutoff=40)
+    assert np.array_equal(bd[-m:], exp)
+    corpus.close()

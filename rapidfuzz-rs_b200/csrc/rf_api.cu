@@ -24,6 +24,8 @@ static std::atomic<int> g_w1_path{0};    // 0: interleaved-layout kernel when av
 static std::atomic<int> g_band{1};       // multi-word Levenshtein with cutoff <= 63: banded kernel (0: block kernel)
 static std::atomic<int> g_stream_mb{64};      // rf_batch_stream_*: chunk size in candidate bytes (MiB)
 static std::atomic<int> g_stream_kcand{2048}; // rf_batch_stream_*: chunk size in candidates (x1024)
+static std::atomic<int> g_cdist_slices{0};    // rf_cdist_topk_*: corpus slices (0: automatic)
+static std::atomic<int> g_cdist_skip{1};      // rf_cdist_topk_*: skip groups by length against the running k-th bound
 
 static rf_status fail(rf_status s, const std::string& msg) {
   g_last_error = msg;
@@ -145,6 +147,8 @@ rf_status rf_set_option(const char* name, int value) {
   if (!strcmp(name, "banded_levenshtein")) { g_band.store(value ? 1 : 0); return RF_OK; }
   if (!strcmp(name, "stream_chunk_mb")) { if (value < 1) return fail(RF_ERR_INVALID_ARG, "stream_chunk_mb < 1"); g_stream_mb.store(value); return RF_OK; }
   if (!strcmp(name, "stream_chunk_kcand")) { if (value < 1) return fail(RF_ERR_INVALID_ARG, "stream_chunk_kcand < 1"); g_stream_kcand.store(value); return RF_OK; }
+  if (!strcmp(name, "cdist_slices")) { if (value < 0 || value > 256) return fail(RF_ERR_INVALID_ARG, "cdist_slices not in 0..256"); g_cdist_slices.store(value); return RF_OK; }
+  if (!strcmp(name, "cdist_skip")) { g_cdist_skip.store(value ? 1 : 0); return RF_OK; }
   return fail(RF_ERR_INVALID_ARG, std::string("unknown option: ") + name);
 }
 
@@ -983,11 +987,14 @@ static rf_status cdist_impl(const uint8_t* q_chars, const uint64_t* q_offsets, u
         for (uint32_t i = 0; i < l; ++i) t[s1[i]] |= 1u << (i + 32 - l);
       }
     }
-    const uint32_t parts = cdist_parts(sm_count_of(c->device));
+    const int sms = sm_count_of(c->device);
+    const uint64_t layout_bytes = c->lb.total_rows * 256ull + c->lb.ngroups * 32ull * 8ull;
+    uint32_t nslices = cdist_slices(sms, nq, layout_bytes, c->lb.ngroups);
+    if (g_cdist_slices.load() > 0) nslices = (uint32_t)g_cdist_slices.load();
     do {
       if ((e = cudaMalloc(&d_tabs, tabs.size())) != cudaSuccess) break;
       if ((e = cudaMalloc(&d_qlen, nq * 4)) != cudaSuccess) break;
-      if ((e = cudaMalloc(&d_scratch, (size_t)nq * parts * k * 8)) != cudaSuccess) break;
+      if ((e = cudaMalloc(&d_scratch, ((size_t)nq * nslices * k + 1) * 8)) != cudaSuccess) break;
       if (!out_on_device) {
         if ((e = cudaMalloc(&d_idx, kk * 4)) != cudaSuccess) break;
         if ((e = cudaMalloc(&d_dist, kk * 4)) != cudaSuccess) break;
@@ -1006,8 +1013,11 @@ static rf_status cdist_impl(const uint8_t* q_chars, const uint64_t* q_offsets, u
       L.cutoff = (uint32_t)(a->cutoff_u > 0xFFFFFFFEull ? 0xFFFFFFFEull : a->cutoff_u);
       L.out_idx = out_on_device ? idx_out : d_idx;
       L.out_dist = out_on_device ? dist_out : d_dist;
-      L.scratch = d_scratch;
-      L.parts = parts;
+      L.scratch = d_scratch + 1;
+      L.counter = d_scratch;
+      L.nslices = nslices;
+      L.grid = cdist_grid(sms);
+      L.skip = g_cdist_skip.load();
       L.stream = st;
       if ((e = launch_cdist_topk(L)) != cudaSuccess) break;
       if (!out_on_device) {

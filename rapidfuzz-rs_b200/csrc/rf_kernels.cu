@@ -1209,13 +1209,16 @@ cudaError_t launch_scan_lbr(const ScanLaunch& L) {
 }
 
 // ------------------------------------------------------------------------------------------------ cdist
-// many-vs-many Levenshtein top-k.  Each CTA owns a fixed slice of the (L2-resident) corpus shard, balanced by
-// rows; queries are the OUTER loop: per query the CTA rebuilds the lane-replicated match table in shared
-// memory (1 KB read, ~2% of the slice's scan time), scans its slice with the same per-lane kernel as the
-// one-vs-many path, and extracts its k best (distance, index) keys; a second kernel merges the per-CTA
-// candidates of every query.  The shard is read from HBM once and then served from L2.
-constexpr int CD_NT = 512;  // 2 CTAs / SM (cdist_parts) x 16 warps: 8 warps per scheduler
+// many-vs-many Levenshtein top-k.  Work unit = (corpus slice, query), handed to the persistent CTAs by a global
+// counter in slice-major order: at any time all CTAs scan the same (L2-resident) slice for different queries.  A
+// slice is the WHOLE shard whenever it fits in L2 and there are enough queries to fill the grid (config 5: one
+// slice, 10^4 units), so a CTA sees ~10^6 candidates per query: the k-best lists warm up once per unit, the
+// per-unit costs (1 KB match table rebuilt in shared memory, merge of the 16 warp lists) vanish, and the k-th
+// bound becomes tight early enough to skip whole groups by length (|len2 - len1| > bound  =>  d > bound).
+// Slices of different units of one query are merged by a second kernel (not launched for a single slice).
+constexpr int CD_NT = 512;  // 2 CTAs / SM (cdist_grid) x 16 warps: 8 warps per scheduler
 constexpr int CD_KMAX = 128;
+constexpr int CD_SMAX = 256;  // slices
 constexpr unsigned long long CD_NOKEY = 0xFFFFFFFFFFFFFFFFull;
 
 struct CdistParams {
@@ -1226,8 +1229,13 @@ struct CdistParams {
   uint32_t nq, k;
   int has_cutoff;
   uint32_t cutoff;
-  unsigned long long* scratch;  // [nq][gridDim.x][k]
+  uint32_t nslices;
+  unsigned long long* counter;  // next unit, zeroed before the launch
+  unsigned long long* scratch;  // [nq][nslices][k]   (nslices > 1)
+  uint32_t* out_idx;            // [nq][k]            (nslices == 1: written directly)
+  uint32_t* out_dist;
   uint32_t two;
+  int skip;                     // group skipping by length on (run-time switch for measurements)
 };
 
 // CTA-wide extraction of the k smallest keys of keys[0..m) (destroys them), ascending, into best[0..k)
@@ -1297,16 +1305,11 @@ struct WarpTopK {
     for (int r = 1; r < KR; ++r) t = ((k - 1) / 32 == (uint32_t)r) ? v[r] : t;  // no dynamic register indexing
     kth = __shfl_sync(0xffffffffu, t, (k - 1) & 31);
   }
-  // the 32 keys of one scored group (one per lane).  `shared_kth` (optional, shared memory) is the smallest k-th
-  // value any warp of the CTA has reached: a key at or above it is beaten by k keys of that warp, so it cannot be
-  // in the CTA's k best either.  Stale reads are safe (the bound only ever tightens).
-  __device__ __forceinline__ void offer(unsigned long long key, uint32_t k, uint32_t lane,
-                                        unsigned long long* shared_kth = nullptr) {
-    unsigned long long bound = kth;
-    if (shared_kth) {
-      const unsigned long long s = *reinterpret_cast<volatile unsigned long long*>(shared_kth);
-      bound = s < bound ? s : bound;
-    }
+  // the 32 keys of one scored group (one per lane).  `bound` = min(kth, CTA-wide bound): the smallest k-th value any
+  // warp of the CTA has reached; a key at or above it is beaten by k keys of that warp, so it cannot be in the
+  // CTA's k best either.  Stale bounds are safe (the bound only ever tightens).
+  __device__ __forceinline__ void offer(unsigned long long key, unsigned long long bound, uint32_t k, uint32_t lane,
+                                        unsigned long long* shared_kth) {
     uint32_t m = __ballot_sync(0xffffffffu, key < bound);
     if (m == 0) return;
     const unsigned long long before = kth;
@@ -1316,7 +1319,7 @@ struct WarpTopK {
       const unsigned long long kk = __shfl_sync(0xffffffffu, key, src);
       if (kk < kth) insert(kk, k, lane);  // kth may have dropped since the ballot
     }
-    if (shared_kth && kth < before && lane == 0) atomicMin(shared_kth, kth);
+    if (kth < before && lane == 0) atomicMin(shared_kth, kth);
   }
 };
 
@@ -1328,43 +1331,52 @@ __global__ void __launch_bounds__(CD_NT) cdist_scan_kernel(const __grid_constant
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw + sizeof(W) * 8192);  // NW * k
   unsigned long long* best = keys + NW * CD_KMAX;                                                  // CD_KMAX
   unsigned long long* wmin = best + CD_KMAX;                                                       // NW
-  __shared__ uint64_t s_glo, s_ghi;
-  __shared__ unsigned long long s_kth;  // CTA-wide bound on the k-th best key of the current query
+  __shared__ uint64_t s_bounds[CD_SMAX + 1];
+  __shared__ unsigned long long s_unit;
+  __shared__ unsigned long long s_kth;  // CTA-wide bound on the k-th best key of the current unit
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint64_t ngroups = p.lb.ngroups;
-  if (tid < 2) {  // slice [g_lo, g_hi): equal share of rows (= work), found by binary search in goff
-    const uint64_t b = blockIdx.x + tid;
+  const uint32_t nslices = p.nslices;
+  for (uint32_t b = tid; b <= nslices; b += CD_NT) {  // slice b = groups [bounds[b], bounds[b+1]): equal shares of rows
     uint64_t g = ngroups;
-    if (b < gridDim.x) {
-      const uint64_t target = (uint64_t)((unsigned __int128)p.total_rows * b / gridDim.x);
+    if (b == 0) g = 0;
+    else if (b < nslices) {
+      const uint64_t target = (uint64_t)((unsigned __int128)p.total_rows * b / nslices);
       uint64_t lo = 0, hi = ngroups;
       while (lo < hi) {
         const uint64_t mid = (lo + hi) >> 1;
         if (p.lb.goff[mid] < target) lo = mid + 1; else hi = mid;
       }
       g = lo;
-      if (b == 0) g = 0;
     }
-    if (tid == 0) s_glo = g; else s_ghi = g;
+    s_bounds[b] = g;
   }
-  __syncthreads();
-  const uint64_t g_lo = s_glo, g_hi = s_ghi;
   const W* __restrict__ pm_lane = pm + lane;
   const uint2* __restrict__ gdata = reinterpret_cast<const uint2*>(p.lb.gdata);
   const uint32_t k = p.k;
-  for (uint32_t q = 0; q < p.nq; ++q) {
+  const unsigned long long units = (unsigned long long)nslices * p.nq;
+  for (;;) {
+    __syncthreads();  // the previous unit's shared-memory traffic is complete
+    if (tid == 0) {
+      s_unit = atomicAdd(p.counter, 1ull);
+      s_kth = CD_NOKEY;
+    }
     __syncthreads();
+    const unsigned long long unit = s_unit;
+    if (unit >= units) break;
+    const uint32_t sl = (uint32_t)(unit / p.nq), q = (uint32_t)(unit - (unsigned long long)sl * p.nq);
+    const uint64_t g_lo = s_bounds[sl], g_hi = s_bounds[sl + 1];
     {
       const W* __restrict__ t = reinterpret_cast<const W*>(p.tabs) + (size_t)q * 256;
       for (uint32_t i = tid; i < 8192u; i += CD_NT) pm[i] = t[i >> 5];
-      if (tid == 0) s_kth = CD_NOKEY;
     }
     __syncthreads();
     const uint32_t len1 = p.q_len[q];
+    const uint32_t static_bound = p.has_cutoff ? p.cutoff : 0xFFFFFFFFu;
     WarpTopK<KR> top;
     top.reset();
     // the warps take the slice's groups round-robin (neighbouring groups have similar lengths); software pipeline:
-    // the next group's length / index / first two rows are requested (L2 hits: the shard is resident) before
+    // the next group's length / index / first two rows are requested (L2 hits: the slice is resident) before
     // the current group is scored
     uint64_t g = g_lo + warp;
     uint32_t len_n = 0, idx_n = 0;
@@ -1388,6 +1400,18 @@ __global__ void __launch_bounds__(CD_NT) cdist_scan_kernel(const __grid_constant
         first_n = __ldg(col_n);
         second_n = __ldg(col_n + 32);
       }
+      unsigned long long bound = top.kth;
+      {
+        const unsigned long long s = *reinterpret_cast<volatile unsigned long long*>(&s_kth);
+        bound = s < bound ? s : bound;
+      }
+      // d >= |len2 - len1|: a group whose every candidate is further than the current k-th distance (or the
+      // cutoff) by length alone cannot contribute.  Equal distance can still win on the index, hence '>'.
+      uint32_t bd = (uint32_t)(bound >> 32);
+      bd = bd < static_bound ? bd : static_bound;
+      const uint32_t ldiff = len2 > len1 ? len2 - len1 : len1 - len2;
+      const bool live = idx != 0xFFFFFFFFu && ldiff <= bd;
+      if (p.skip && !__any_sync(0xffffffffu, live)) continue;
       uint32_t d;
       if (len1 == 0) d = len2;
       else if constexpr (sizeof(W) == 4) d = lev_w1_u32_fast(smem_u32(pm_lane), src.reader(), len2, len1, p.two);
@@ -1395,11 +1419,10 @@ __global__ void __launch_bounds__(CD_NT) cdist_scan_kernel(const __grid_constant
         auto tab = [&](uint32_t ch) -> W { return pm_lane[ch * 32u]; };
         d = lev_w1<W>(tab, src.reader(), len2, len1);
       }
-      const bool ok = idx != 0xFFFFFFFFu && !(p.has_cutoff && d > p.cutoff);
-      top.offer(ok ? (((unsigned long long)d << 32) | idx) : CD_NOKEY, k, lane, &s_kth);
+      const bool ok = idx != 0xFFFFFFFFu && d <= static_bound;
+      top.offer(ok ? (((unsigned long long)d << 32) | idx) : CD_NOKEY, bound, k, lane, &s_kth);
     }
-    // the NW warp lists -> the CTA's k best of this query (CTA-wide extraction; folding them into warp 0's list
-    // serially was measured 1.6x slower for the whole kernel)
+    // the NW warp lists -> the CTA's k best of this unit
 #pragma unroll
     for (int r = 0; r < KR; ++r) {
       const uint32_t i = (uint32_t)r * 32u + lane;
@@ -1407,12 +1430,20 @@ __global__ void __launch_bounds__(CD_NT) cdist_scan_kernel(const __grid_constant
     }
     __syncthreads();
     cd_extract(keys, NW * k, best, k, wmin);
-    unsigned long long* out = p.scratch + ((size_t)q * gridDim.x + blockIdx.x) * k;
-    for (uint32_t i = tid; i < k; i += CD_NT) out[i] = best[i];
+    if (nslices == 1) {
+      for (uint32_t i = tid; i < k; i += CD_NT) {
+        const unsigned long long v = best[i];
+        p.out_idx[(size_t)q * k + i] = (v == CD_NOKEY) ? 0xFFFFFFFFu : (uint32_t)v;
+        p.out_dist[(size_t)q * k + i] = (v == CD_NOKEY) ? 0xFFFFFFFFu : (uint32_t)(v >> 32);
+      }
+    } else {
+      unsigned long long* out = p.scratch + ((size_t)q * nslices + sl) * k;
+      for (uint32_t i = tid; i < k; i += CD_NT) out[i] = best[i];
+    }
   }
 }
 
-// one CTA per query: k smallest of the parts*k per-CTA keys -> (idx, dist) rows
+// one CTA per query: k smallest of the parts*k per-slice keys -> (idx, dist) rows
 __global__ void __launch_bounds__(CD_NT) cdist_merge_kernel(const unsigned long long* __restrict__ scratch, uint32_t parts,
                                                             uint32_t k, uint32_t* __restrict__ out_idx,
                                                             uint32_t* __restrict__ out_dist) {
@@ -1432,10 +1463,24 @@ __global__ void __launch_bounds__(CD_NT) cdist_merge_kernel(const unsigned long 
   }
 }
 
-uint32_t cdist_parts(int sm_count) { return (uint32_t)sm_count * 2u; }
+uint32_t cdist_grid(int sm_count) { return (uint32_t)sm_count * 2u; }
+
+// slices: enough units to keep the grid busy when there are few queries, and a slice small enough to stay in L2
+// (the 126 MB L2 holds ~48 MB comfortably next to the tables and the other die's copy) while every query visits it
+uint32_t cdist_slices(int sm_count, uint32_t nq, uint64_t layout_bytes, uint64_t ngroups) {
+  const uint64_t grid = cdist_grid(sm_count);
+  uint64_t s_par = (3 * grid + nq - 1) / nq;
+  uint64_t s_l2 = (layout_bytes + (48ull << 20) - 1) / (48ull << 20);
+  uint64_t s = s_par > s_l2 ? s_par : s_l2;
+  const uint64_t cap = ngroups / 64 + 1;  // at least 64 groups (4 per warp) in a slice
+  if (s > cap) s = cap;
+  if (s > (uint64_t)CD_SMAX) s = CD_SMAX;
+  if (s < 1) s = 1;
+  return (uint32_t)s;
+}
 
 cudaError_t launch_cdist_topk(const CdistLaunch& L) {
-  if (L.k == 0 || L.k > CD_KMAX) return cudaErrorInvalidValue;
+  if (L.k == 0 || L.k > CD_KMAX || L.nslices == 0 || L.nslices > (uint32_t)CD_SMAX) return cudaErrorInvalidValue;
   CdistParams p{};
   p.lb = L.lb;
   p.total_rows = L.total_rows;
@@ -1445,16 +1490,23 @@ cudaError_t launch_cdist_topk(const CdistLaunch& L) {
   p.k = L.k;
   p.has_cutoff = L.has_cutoff;
   p.cutoff = L.cutoff;
+  p.nslices = L.nslices;
+  p.counter = L.counter;
   p.scratch = L.scratch;
+  p.out_idx = L.out_idx;
+  p.out_dist = L.out_dist;
   p.two = 2;
-  const uint32_t parts = L.parts;
+  p.skip = L.skip;
   const size_t wsz = L.wide ? 8 : 4;
   const size_t smem = wsz * 8192 + sizeof(unsigned long long) * ((CD_NT / 32) * CD_KMAX + CD_KMAX + CD_NT / 32);
-  cudaError_t e;
+  cudaError_t e = cudaMemsetAsync(L.counter, 0, sizeof(unsigned long long), L.stream);
+  if (e != cudaSuccess) return e;
+  const unsigned long long units = (unsigned long long)L.nslices * L.nq;
+  const uint32_t grid = (uint32_t)(units < L.grid ? units : L.grid);
   auto launch = [&](auto kern) -> cudaError_t {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
-    kern<<<parts, CD_NT, smem, L.stream>>>(p);
+    kern<<<grid, CD_NT, smem, L.stream>>>(p);
     return cudaGetLastError();
   };
   const int kr = L.k <= 32 ? 1 : (L.k <= 64 ? 2 : 4);
@@ -1462,12 +1514,11 @@ cudaError_t launch_cdist_topk(const CdistLaunch& L) {
   else e = kr == 1 ? launch(cdist_scan_kernel<uint32_t, 1>) : kr == 2 ? launch(cdist_scan_kernel<uint32_t, 2>) : launch(cdist_scan_kernel<uint32_t, 4>);
   if (e != cudaSuccess) return e;
   g_launches.fetch_add(1);
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  const size_t msmem = sizeof(unsigned long long) * ((size_t)parts * L.k + CD_KMAX + CD_NT / 32);
+  if (L.nslices == 1) return cudaSuccess;
+  const size_t msmem = sizeof(unsigned long long) * ((size_t)L.nslices * L.k + CD_KMAX + CD_NT / 32);
   e = cudaFuncSetAttribute(cdist_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem);
   if (e != cudaSuccess) return e;
-  cdist_merge_kernel<<<L.nq, CD_NT, msmem, L.stream>>>(L.scratch, parts, L.k, L.out_idx, L.out_dist);
+  cdist_merge_kernel<<<L.nq, CD_NT, msmem, L.stream>>>(L.scratch, L.nslices, L.k, L.out_idx, L.out_dist);
   g_launches.fetch_add(1);
   return cudaGetLastError();
 }

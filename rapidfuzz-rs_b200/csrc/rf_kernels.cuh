@@ -99,12 +99,16 @@ struct CdistLaunch {
   uint32_t cutoff;
   uint32_t* out_idx;        // [nq][k]
   uint32_t* out_dist;       // [nq][k]
-  unsigned long long* scratch;  // [nq][parts][k] packed (dist<<32|idx) per-CTA candidates
-  uint32_t parts;           // CTAs of the scan kernel (cdist_parts)
+  unsigned long long* scratch;  // [nq][nslices][k] packed (dist<<32|idx) per-slice candidates (unused for 1 slice)
+  unsigned long long* counter;  // device, one word: the unit dispenser
+  uint32_t nslices;         // corpus slices (cdist_slices); work units = nslices * nq
+  uint32_t grid;            // persistent CTAs (cdist_grid)
+  int skip;                 // 1: skip groups that cannot reach the current k-th distance by length alone
   cudaStream_t stream;
 };
 cudaError_t launch_cdist_topk(const CdistLaunch& L);
-uint32_t cdist_parts(int sm_count);
+uint32_t cdist_grid(int sm_count);
+uint32_t cdist_slices(int sm_count, uint32_t nq, uint64_t layout_bytes, uint64_t ngroups);
 
 // Result post-processing over a device-resident score vector (rf_select.cu): the k best by (score best-first,
 // index ascending), or every score that is not None in index order.

@@ -601,6 +601,29 @@ def test_cdist_topk_vs_oracle_full_matrix(qlens, n, k):
     corpus.close()
 
 
+@pytest.mark.parametrize("slices,skip", [(1, 1), (1, 0), (3, 1), (17, 1), (256, 1), (0, 0)])
+def test_cdist_work_decomposition_is_invisible(slices, skip):
+    """The (slice, query) work units, the merge of several slices and the skipping of groups by length against the
+    running k-th bound must not change a single entry: 330 queries of mixed length (more units than CTAs when there is
+    one slice), ties on the distance decided by the index, with and without a cutoff."""
+    queries = [rf.synth_query(2000 + i, (8, 20, 32, 32, 32, 47, 64, 3)[i % 8]) for i in range(330)]
+    chars, offsets = rf.synth_corpus(11, queries[2], 40000, 1, 64, 16)
+    corpus = rf.Corpus(chars, offsets)
+    L = _ffi.lib()
+    _ffi.check(L.rf_set_option(b"cdist_slices", slices))
+    _ffi.check(L.rf_set_option(b"cdist_skip", skip))
+    try:
+        for k, cutoff in ((10, None), (1, None), (33, 12), (5, 0)):
+            idx, dist = rf.cdist_topk(queries, corpus, k=k, score_cutoff=cutoff)
+            eidx, edist = _oracle_topk(queries, chars, offsets, k, cutoff)
+            assert np.array_equal(dist, edist), (slices, skip, k, cutoff)
+            assert np.array_equal(idx, eidx), (slices, skip, k, cutoff)
+    finally:
+        _ffi.check(L.rf_set_option(b"cdist_slices", 0))
+        _ffi.check(L.rf_set_option(b"cdist_skip", 1))
+    corpus.close()
+
+
 def test_cpp_host_mirror_known_answers(tmp_path):
     """Compiles tests/cpp/test_cpp_api.cpp against the header-only C++ mirror and runs it on the GPU."""
     import subprocess

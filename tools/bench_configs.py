@@ -186,6 +186,9 @@ def widen(n):
 
 if __name__ == "__main__":
     which = sys.argv[1].split(",") if len(sys.argv) > 1 else ["c2w", "c3", "c4", "c5"]
+    for kv in os.environ.get("RF_OPTS", "").split(","):   # A/B runs of the library's tuning knobs: RF_OPTS=cdist_skip=0,...
+        if kv:
+            _ffi.check(L.rf_set_option(kv.split("=")[0].encode(), int(kv.split("=")[1])))
     if "c2w" in which:  # config 2 with a 64-element query (64-bit words)
         one_vs_many("C2 (query len 64, 64-bit words)", "levenshtein", "distance", 2, 64, int(1e8 * scale), 8, 64, 16, None, False,
                     lambda l: l + 8)

@@ -187,6 +187,16 @@ rf_status rf_cdist_topk_u8_device(const uint8_t* q_chars, const uint64_t* q_offs
                                   const rf_corpus* c, const rf_args* args, uint32_t k, uint32_t* idx_device,
                                   uint32_t* dist_device, void* stream);
 
+/* Sharded corpora (one contiguous candidate range per GPU): global top-k from the per-shard
+ * lists after ONE all-gather.  Part p's rows are idx_parts / dist_parts + p * part_stride, each [nq][k] as written
+ * by rf_cdist_topk_u8_device on shard p (shard-local indices, UINT32_MAX padding); index_base_device[p] is the
+ * global index of shard p's first candidate (ascending in p).  Output rows: the k best by (distance, global
+ * index), padded with (UINT64_MAX, UINT32_MAX).  All pointers are device memory of `device`; asynchronous on
+ * `stream`.  parts * k <= 25600. */
+rf_status rf_topk_merge_device(const uint32_t* idx_parts, const uint32_t* dist_parts, uint64_t part_stride,
+                               const uint64_t* index_base_device, uint32_t parts, uint32_t nq, uint32_t k,
+                               uint64_t* idx_out_device, uint32_t* dist_out_device, int device, void* stream);
+
 /* ---- packing and corpus files (host-side; the step before the scoring path).  The reference takes one iterator
  * per candidate (levenshtein.rs:1750-1762); callers holding a Vec<String> pack it once:
  *   rf_pack_u8: n strings given as (pointer, length) -> CSR offsets[n+1] (+ chars[offsets[n]] when chars_out != NULL;

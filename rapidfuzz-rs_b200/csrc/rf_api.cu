@@ -1048,4 +1048,21 @@ rf_status rf_cdist_topk_u8(const uint8_t* q_chars, const uint64_t* q_offsets, ui
   return cdist_impl(q_chars, q_offsets, nq, c, args, k, idx_host, dist_host, false, nullptr);
 }
 
+rf_status rf_topk_merge_device(const uint32_t* idx_parts, const uint32_t* dist_parts, uint64_t part_stride,
+                               const uint64_t* index_base_device, uint32_t parts, uint32_t nq, uint32_t k,
+                               uint64_t* idx_out_device, uint32_t* dist_out_device, int device, void* stream) {
+  if (nq == 0) return RF_OK;
+  if (!idx_parts || !dist_parts || !index_base_device || !idx_out_device || !dist_out_device)
+    return fail(RF_ERR_INVALID_ARG, "NULL argument");
+  if (parts == 0 || k == 0) return fail(RF_ERR_INVALID_ARG, "parts and k must be positive");
+  if ((uint64_t)parts * k > 25600) return fail(RF_ERR_UNSUPPORTED, "parts * k must not exceed 25600");
+  if (part_stride < (uint64_t)nq * k) return fail(RF_ERR_INVALID_ARG, "part_stride < nq * k");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(RF_ERR_CUDA, "cudaSetDevice failed");
+  cudaError_t e = launch_topk_merge(idx_parts, dist_parts, part_stride, (const unsigned long long*)index_base_device, parts,
+                                    nq, k, (unsigned long long*)idx_out_device, dist_out_device, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "top-k merge");
+  return RF_OK;
+}
+
 }  // extern "C"

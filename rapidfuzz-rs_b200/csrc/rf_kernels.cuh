@@ -110,6 +110,11 @@ cudaError_t launch_cdist_topk(const CdistLaunch& L);
 uint32_t cdist_grid(int sm_count);
 uint32_t cdist_slices(int sm_count, uint32_t nq, uint64_t layout_bytes, uint64_t ngroups);
 
+// Global top-k of a sharded corpus from the gathered per-shard lists (rf_select.cu topk_merge_kernel).
+cudaError_t launch_topk_merge(const uint32_t* idx_parts, const uint32_t* dist_parts, uint64_t part_stride,
+                              const unsigned long long* base, uint32_t parts, uint32_t nq, uint32_t k,
+                              unsigned long long* out_idx, uint32_t* out_dist, cudaStream_t stream);
+
 // Result post-processing over a device-resident score vector (rf_select.cu): the k best by (score best-first,
 // index ascending), or every score that is not None in index order.
 struct SelectLaunch {

@@ -372,6 +372,68 @@ static cudaError_t select_impl(const SelectLaunch& L) {
   return e;
 }
 
+// ------------------------------------------------------------------------------------------------ shard merge
+// Per-shard top-k lists of a sharded corpus (one part per GPU, gathered with ONE all-gather) -> global top-k.
+// Part p holds [nq][k] (shard-local index, distance) rows, 0xFFFFFFFF padded; the global index of an entry is
+// base[p] + idx.  Shards are contiguous candidate ranges in part order, so (distance, part, local index) orders
+// exactly like (distance, global index): no wide keys are needed.  CTA per query, rank sort in shared memory
+// (parts*k is a few hundred entries): every entry counts the entries that precede it; rank < k writes slot rank.
+constexpr int MG_NT = 256;
+__global__ void __launch_bounds__(MG_NT) topk_merge_kernel(const uint32_t* __restrict__ idx_parts,
+                                                           const uint32_t* __restrict__ dist_parts, uint64_t part_stride,
+                                                           const unsigned long long* __restrict__ base, uint32_t parts,
+                                                           uint32_t k, unsigned long long* __restrict__ out_idx,
+                                                           uint32_t* __restrict__ out_dist) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned long long* key = reinterpret_cast<unsigned long long*>(smem_raw);  // [parts*k]  dist<<32 | idx, NOKEY = padding
+  const uint32_t q = blockIdx.x, m = parts * k;
+  for (uint32_t e = threadIdx.x; e < m; e += MG_NT) {
+    const uint32_t pt = e / k, i = e - pt * k;
+    const size_t src = (size_t)pt * part_stride + (size_t)q * k + i;
+    const uint32_t ix = idx_parts[src], d = dist_parts[src];
+    key[e] = (ix == 0xFFFFFFFFu) ? ~0ull : (((unsigned long long)d << 32) | ix);
+  }
+  for (uint32_t i = threadIdx.x; i < k; i += MG_NT) {
+    out_idx[(size_t)q * k + i] = ~0ull;
+    out_dist[(size_t)q * k + i] = 0xFFFFFFFFu;
+  }
+  __syncthreads();
+  for (uint32_t e = threadIdx.x; e < m; e += MG_NT) {
+    const unsigned long long me = key[e];
+    if (me == ~0ull) continue;
+    const uint32_t md = (uint32_t)(me >> 32);
+    const uint32_t pe = e / k;
+    uint32_t rank = 0;
+    // entry o precedes e: smaller distance, or equal distance and earlier (part, index)
+    for (uint32_t po = 0, o = 0; po < parts; ++po) {
+      for (uint32_t i = 0; i < k; ++i, ++o) {
+        const unsigned long long ot = key[o];
+        const uint32_t od = (uint32_t)(ot >> 32);
+        rank += (ot != ~0ull) && (od < md || (od == md && (po < pe || (po == pe && ot < me))));
+      }
+    }
+    if (rank < k) {
+      out_idx[(size_t)q * k + rank] = base[pe] + (uint32_t)me;
+      out_dist[(size_t)q * k + rank] = md;
+    }
+  }
+}
+
+cudaError_t launch_topk_merge(const uint32_t* idx_parts, const uint32_t* dist_parts, uint64_t part_stride,
+                              const unsigned long long* base, uint32_t parts, uint32_t nq, uint32_t k,
+                              unsigned long long* out_idx, uint32_t* out_dist, cudaStream_t stream) {
+  if (parts == 0 || k == 0 || nq == 0) return cudaErrorInvalidValue;
+  const size_t smem = sizeof(unsigned long long) * (size_t)parts * k;
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  topk_merge_kernel<<<nq, MG_NT, smem, stream>>>(idx_parts, dist_parts, part_stride, base, parts, k, out_idx, out_dist);
+  count_launches(1);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_select(const SelectLaunch& L) {
   if (L.n == 0 || (!L.filter && (L.k == 0 || L.k > 1024))) return cudaErrorInvalidValue;
   if (L.f64) return L.desc ? select_impl<true, true>(L) : select_impl<true, false>(L);

@@ -70,6 +70,7 @@ SYMBOLS = {
     "rf_batch_stream_f64_off32": (_int, [_vp, _vp, _vp, _u64, _int, _PA, _vp]),
     "rf_cdist_topk_u8": (_int, [_vp, _vp, _u32, _vp, _PA, _u32, _vp, _vp]),
     "rf_cdist_topk_u8_device": (_int, [_vp, _vp, _u32, _vp, _PA, _u32, _vp, _vp, _vp]),
+    "rf_topk_merge_device": (_int, [_vp, _vp, _u64, _vp, _u32, _u32, _u32, _vp, _vp, _int, _vp]),
     "rf_pack_u8": (_int, [_vp, _vp, _u64, _vp, _vp, _int]),
     "rf_corpus_file_write": (_int, [C.c_char_p, _vp, _vp, _u64]),
     "rf_corpus_file_open": (_int, [C.c_char_p, C.POINTER(_vp)]),

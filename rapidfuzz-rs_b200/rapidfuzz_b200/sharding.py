@@ -73,8 +73,65 @@ def merge_topk(idx_parts, dist_parts, shard_starts, k):
     return out_idx, out_dist
 
 
+def cdist_topk_device(q_chars, q_offsets, corpus, k=10, score_cutoff=None, device=None):
+    """rf_cdist_topk_u8_device on this rank's shard: (idx, dist) int32 CUDA tensors [nq,k] (shard-local indices,
+    -1 = none), left on the device for the gather.  q_chars u8 / q_offsets u64: host CSR of the queries."""
+    import ctypes as C
+    import torch
+    from . import _ffi
+    q_chars = np.ascontiguousarray(q_chars, dtype=np.uint8)
+    q_offsets = np.ascontiguousarray(q_offsets, dtype=np.uint64)
+    nq = len(q_offsets) - 1
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    idx = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    dist = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    a = _ffi.RfArgs()
+    _ffi.lib().rf_args_default(C.byref(a))
+    if score_cutoff is not None:
+        a.has_cutoff = 1
+        a.cutoff_u = int(score_cutoff)
+    _ffi.check(_ffi.lib().rf_cdist_topk_u8_device(q_chars.ctypes.data, q_offsets.ctypes.data, nq, corpus._h, C.byref(a), k,
+                                                 idx.data_ptr(), dist.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+    return idx, dist
+
+
+def merge_topk_device(parts_idx_dist, starts, k, stream=None):
+    """Device-side merge (rf_topk_merge_device): parts_idx_dist int32 CUDA tensor [parts, 2, nq, k] (what one
+    all_gather_into_tensor of the stacked per-shard (idx, dist) lists produces), starts int64 CUDA tensor [parts].
+    Returns (idx int64 [nq,k] global indices, -1 = none; dist int32 [nq,k], -1 = none) on the device."""
+    import torch
+    from . import _ffi
+    parts, two, nq, kk = parts_idx_dist.shape
+    assert two == 2 and kk == k and parts_idx_dist.is_contiguous() and parts_idx_dist.dtype == torch.int32
+    dev = parts_idx_dist.device
+    out_idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    out_dist = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    st = stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream
+    base = parts_idx_dist.data_ptr()
+    _ffi.check(_ffi.lib().rf_topk_merge_device(base, base + 4 * nq * k, 2 * nq * k, starts.data_ptr(), parts, nq, k,
+                                               out_idx.data_ptr(), out_dist.data_ptr(), dev.index or 0, st))
+    return out_idx, out_dist
+
+
+def all_gather_topk_device(idx_local, dist_local, shard_start, k, group=None):
+    """GPU path of all_gather_topk: ONE all-gather (NCCL over NVLink) of the stacked per-shard lists + one of the
+    shard starts, merged on the device; nothing touches the host.  idx_local / dist_local: int32 CUDA [nq,k]."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    dev = idx_local.device
+    packed = torch.stack([idx_local, dist_local], dim=0).contiguous()
+    parts = torch.empty((world,) + tuple(packed.shape), dtype=packed.dtype, device=dev)
+    start = torch.tensor([shard_start], dtype=torch.int64, device=dev)
+    starts = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(parts, packed, group=group)
+    dist.all_gather_into_tensor(starts, start, group=group)
+    return merge_topk_device(parts, starts, k)
+
+
 def all_gather_topk(idx_local, dist_local, shard_start, k, group=None):
-    """All-gather of the per-shard [nq,k] (index, distance) lists followed by a local merge."""
+    """All-gather of the per-shard [nq,k] (index, distance) lists followed by a local merge (host tensors / gloo:
+    the plumbing test; on GPUs use all_gather_topk_device)."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)

@@ -624,6 +624,37 @@ def test_cdist_work_decomposition_is_invisible(slices, skip):
     corpus.close()
 
 
+@pytest.mark.parametrize("world,k", [(3, 10), (8, 4), (2, 64)])
+def test_sharded_cdist_device_merge(world, k):
+    """SURVEY 8e on one GPU: the corpus is cut into `world` byte-balanced shards, every shard is scored on its own
+    (what each rank does), the per-shard lists are stacked the way one all_gather_into_tensor lays them out and merged
+    on the device (rf_topk_merge_device).  Must equal the oracle's global top-k, ties by GLOBAL index."""
+    import torch
+    from rapidfuzz_b200 import sharding
+    queries = [rf.synth_query(3000 + i, (32, 12, 50)[i % 3]) for i in range(40)]
+    q_off = np.zeros(len(queries) + 1, dtype=np.uint64)
+    q_off[1:] = np.cumsum([len(q) for q in queries])
+    q_chars = np.concatenate(queries)
+    chars, offsets = rf.synth_corpus(12, queries[0], 30000, 1, 64, 16)
+    for cutoff in (None, 14):
+        parts, starts = [], []
+        for r in range(world):
+            c, o, lo = sharding.local_shard(chars, offsets, world, r)
+            corpus = rf.Corpus(c, o)
+            i, d = sharding.cdist_topk_device(q_chars, q_off, corpus, k=k, score_cutoff=cutoff)
+            parts.append(torch.stack([i, d], dim=0))
+            starts.append(lo)
+            corpus.close()
+        gi, gd = sharding.merge_topk_device(torch.stack(parts, dim=0).contiguous(),
+                                            torch.tensor(starts, dtype=torch.int64, device="cuda"), k)
+        torch.cuda.synchronize()
+        eidx, edist = _oracle_topk(queries, chars, offsets, k, cutoff)
+        assert np.array_equal(gd.cpu().numpy().view(np.uint32), edist), (world, k, cutoff)
+        got = gi.cpu().numpy()
+        exp = np.where(eidx == 0xFFFFFFFF, -1, eidx.astype(np.int64))
+        assert np.array_equal(got, exp), (world, k, cutoff)
+
+
 def test_cpp_host_mirror_known_answers(tmp_path):
     """Compiles tests/cpp/test_cpp_api.cpp against the header-only C++ mirror and runs it on the GPU."""
     import subprocess

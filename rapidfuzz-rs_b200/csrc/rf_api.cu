@@ -349,6 +349,14 @@ int rf_corpus_device(const rf_corpus* c) { return c ? c->device : -1; }
 static constexpr uint32_t kAlphaSlots = 1024;
 static inline uint32_t alpha_hash(uint32_t x) { return (x * 2654435761u) >> 22; }  // 10 bits
 
+// host -> device copy that has LANDED when it returns (stream-ordered on the device's utility stream + a stream sync)
+static cudaError_t upload_sync(void* dst, const void* src, size_t bytes, int device) {
+  cudaStream_t st = util_stream(device);
+  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  return e;
+}
+
 static rf_status batch_create_bytes(rf_metric metric, const uint8_t* query, uint32_t query_len, int device, rf_batch** out) {
   if (!out) return fail(RF_ERR_INVALID_ARG, "out is NULL");
   *out = nullptr;
@@ -404,7 +412,9 @@ static rf_status batch_create_bytes(rf_metric metric, const uint8_t* query, uint
       for (int d = 1; d < kQuotDim; ++d) quot[a * kQuotDim + d] = (double)a / (double)d;
   }
   cudaError_t e = cudaMalloc(&b->d_blob, blob.size());
-  if (e == cudaSuccess) e = cudaMemcpy(b->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice);
+  // NOT cudaMemcpy: from pageable memory it may return once the data is staged, before the DMA has landed, and the
+  // scoring kernels run on non-blocking streams that do not order against the legacy stream.
+  if (e == cudaSuccess) e = upload_sync(b->d_blob, blob.data(), blob.size(), device);
   if (e != cudaSuccess) { rf_batch_destroy(b); return cuda_fail(e, "query table upload"); }
   b->view.len1 = b->len1;
   b->view.words = b->words;
@@ -452,8 +462,8 @@ rf_status rf_batch_create_u32(rf_metric metric, const uint32_t* query, uint32_t 
   b->wide = true;
   cudaError_t e = cudaMalloc(&b->d_alpha_keys, kAlphaSlots * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMalloc(&b->d_alpha_codes, kAlphaSlots);
-  if (e == cudaSuccess) e = cudaMemcpy(b->d_alpha_keys, keys.data(), kAlphaSlots * sizeof(uint32_t), cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(b->d_alpha_codes, codes.data(), kAlphaSlots, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = upload_sync(b->d_alpha_keys, keys.data(), kAlphaSlots * sizeof(uint32_t), device);
+  if (e == cudaSuccess) e = upload_sync(b->d_alpha_codes, codes.data(), kAlphaSlots, device);
   if (e != cudaSuccess) { rf_batch_destroy(b); return cuda_fail(e, "alphabet upload"); }
   *out = b;
   return RF_OK;

@@ -331,8 +331,92 @@ __device__ __forceinline__ uint32_t lev_w1_u32_fast(uint32_t pm_lane_saddr, Rd r
   return myers_w1_u32_fast<false>(pm_lane_saddr, rd, len2, len1, two);
 }
 
+// Levenshtein, query of 33..64 elements: the 64-bit recurrence of lev_w1<uint64_t> written on 32-bit halves so that,
+// as in the 32-bit routine, only the 14 LOP3 of a step remain on the ALU pipe.  ptxas expands a 64-bit add into
+// IADD3 + IADD3.X and a 64-bit shift into SHF + SHL, all ALU-pipe; here
+//   sum  = IMAD.WIDE.U32 (X&VP).lo * 1 + VP  ;  sum.hi += (X&VP).hi        (IMAD)
+//   HP<<1|1, HN<<1 = IMAD.WIDE.U32 lo * 2 + {1|0}  (the product's high word is the bit that crosses) ; hi*2 + carry (IMAD)
+// The match table is SPLIT: low words at pm_lo[ch*32 + lane], high words 32 KB further (one IDP.4A address, two LDS).
+constexpr uint32_t kSplitHi = 256u * 32u * 4u;  // byte distance between the low-word and the high-word table
+template <class Rd>
+__device__ __forceinline__ uint32_t lev_w1_u64_fast(uint32_t pm_lane_saddr, Rd rd, uint32_t len2, uint32_t len1, uint32_t two) {
+  static_assert(Rd::kRow8, "interleaved rows only");
+  const uint32_t one = two >> 1;
+  const uint64_t vp0 = ~0ull << (64u - len1);
+  uint32_t VPl = (uint32_t)vp0, VPh = (uint32_t)(vp0 >> 32), VNl = 0, VNh = 0;
+#define RF_LEV64_STEP(K)                                                                              \
+  {                                                                                                   \
+    uint32_t Xl, Xh, sl, sh, c;                                                                       \
+    const uint32_t addr = __dp4a(w, 0x80u << (8 * (K)), pm_lane_saddr);                               \
+    asm("ld.shared.u32 %0, [%1];" : "=r"(Xl) : "r"(addr));                                            \
+    asm("ld.shared.u32 %0, [%1+32768];" : "=r"(Xh) : "r"(addr));                                      \
+    /* 64-bit (X & VP) + VP: IADD3 (carry out) + IMAD.X (VPh * 1 + (Xh & VPh) + carry) */             \
+    asm("{\n\tadd.cc.u32 %0, %2, %3;\n\tmadc.lo.u32 %1, %4, %5, %6;\n\t}"                            \
+        : "=r"(sl), "=r"(sh) : "r"(Xl & VPl), "r"(VPl), "r"(VPh), "r"(one), "r"(Xh & VPh));           \
+    const uint32_t D0l = ((sl ^ VPl) | Xl) | VNl;                                                     \
+    const uint32_t D0h = ((sh ^ VPh) | Xh) | VNh;                                                     \
+    uint32_t HPl = VNl | ~(D0l | VPl), HPh = VNh | ~(D0h | VPh);                                      \
+    uint32_t HNl = D0l & VPl, HNh = D0h & VPh;                                                        \
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(c) : "r"(HPl), "r"(two));                                     \
+    HPl = HPl * two + one;                                                                            \
+    HPh = HPh * two + c;                                                                              \
+    asm("{\n\t.reg .b64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}"                  \
+        : "=r"(HNl), "=r"(c) : "r"(HNl), "r"(two));                                                   \
+    HNh = HNh * two + c;                                                                              \
+    VPl = HNl | ~(D0l | HPl);                                                                         \
+    VPh = HNh | ~(D0h | HPh);                                                                         \
+    VNl = HPl & D0l;                                                                                  \
+    VNh = HPh & D0h;                                                                                  \
+  }
+#define RF_LEV64_ROW(R)                                                                      \
+  {                                                                                          \
+    { const uint32_t w = (R).x; RF_LEV64_STEP(0) RF_LEV64_STEP(1) RF_LEV64_STEP(2) RF_LEV64_STEP(3) } \
+    { const uint32_t w = (R).y; RF_LEV64_STEP(0) RF_LEV64_STEP(1) RF_LEV64_STEP(2) RF_LEV64_STEP(3) } \
+  }
+  uint2 A = rd.q0, B = rd.q1;
+  const uint2* p = rd.p;
+  const uint32_t nfull = len2 >> 3;
+  uint32_t i = 0;
+  for (; i + 2 <= nfull; i += 2) {  // two rows per iteration, the next two requested first
+    if constexpr (Rd::kStream) {
+      prefetch_l2(p + 32 * kPfDist);
+      prefetch_l2(p + 32 * (kPfDist + 1));
+    }
+    const uint2 C = ld_row8<Rd::kStream>(p);
+    const uint2 D = ld_row8<Rd::kStream>(p + 32);
+    p += 64;
+    RF_LEV64_ROW(A)
+    RF_LEV64_ROW(B)
+    A = C;
+    B = D;
+  }
+  if (i < nfull) {
+    RF_LEV64_ROW(A)
+    A = B;
+  }
+  const uint32_t rem = len2 & 7u;
+  if (rem) {
+    const uint2 ww = A;
+    { const uint32_t w = ww.x;
+      RF_LEV64_STEP(0)
+      if (rem > 1) RF_LEV64_STEP(1)
+      if (rem > 2) RF_LEV64_STEP(2)
+      if (rem > 3) RF_LEV64_STEP(3) }
+    if (rem > 4) {
+      const uint32_t w = ww.y;
+      RF_LEV64_STEP(0)
+      if (rem > 5) RF_LEV64_STEP(1)
+      if (rem > 6) RF_LEV64_STEP(2)
+    }
+  }
+#undef RF_LEV64_ROW
+#undef RF_LEV64_STEP
+  return len2 + (uint32_t)__popc(VPl) + (uint32_t)__popc(VPh) - (uint32_t)__popc(VNl) - (uint32_t)__popc(VNh);
+}
+
 // One candidate: raw bit-parallel kernel + score algebra.  pm_lane = &pm[lane] of the lane-replicated table.
-template <int FAM, class W, class Src>
+// SPLIT64 (F_LEV, 64-bit words, interleaved rows only): pm_lane points into the split low/high table of lev_w1_u64_fast.
+template <int FAM, class W, class Src, bool SPLIT64 = false>
 __device__ __forceinline__ void score_one(const W* __restrict__ pm_lane, const Src& src, uint32_t len2, uint32_t len1,
                                           const Epi& epi, int out_f64, uint32_t two, uint32_t& ru, double& rf) {
   auto tab = [&](uint32_t ch) -> W { return pm_lane[ch * 32u]; };
@@ -354,6 +438,7 @@ __device__ __forceinline__ void score_one(const W* __restrict__ pm_lane, const S
       raw = (FAM == F_LCS) ? 0u : len2;
     } else {
       if constexpr (FAM == F_LEV && sizeof(W) == 4) raw = lev_w1_u32_fast(smem_u32(pm_lane), src.reader(), len2, len1, two);
+      else if constexpr (FAM == F_LEV && SPLIT64) raw = lev_w1_u64_fast(smem_u32(pm_lane), src.reader(), len2, len1, two);
       else if constexpr (FAM == F_LEV) raw = lev_w1<W>(tab, src.reader(), len2, len1);
       else if constexpr (FAM == F_OSA && sizeof(W) == 4) raw = myers_w1_u32_fast<true>(smem_u32(pm_lane), src.reader(), len2, len1, two);
       else if constexpr (FAM == F_OSA) raw = osa_w1<W>(tab, src.reader(), len2, len1);
@@ -586,14 +671,24 @@ struct LbParams {
 template <int FAM, class W, int NT, bool RAWDIST>
 __global__ void __launch_bounds__(NT) scan_lb_kernel(const __grid_constant__ LbParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr bool SPLIT64 = (FAM == F_LEV && sizeof(W) == 8);  // low / high words in two 32 KB tables (lev_w1_u64_fast)
   W* pm = reinterpret_cast<W*>(smem_raw);
   {
     const W* __restrict__ t = reinterpret_cast<const W*>(p.tab);
-    for (uint32_t i = threadIdx.x; i < 256u * 32u; i += NT) pm[i] = t[i >> 5];
+    if constexpr (SPLIT64) {
+      uint32_t* pm32 = reinterpret_cast<uint32_t*>(smem_raw);
+      for (uint32_t i = threadIdx.x; i < 256u * 32u; i += NT) {
+        const uint64_t v = t[i >> 5];
+        pm32[i] = (uint32_t)v;
+        pm32[i + 256u * 32u] = (uint32_t)(v >> 32);
+      }
+    } else {
+      for (uint32_t i = threadIdx.x; i < 256u * 32u; i += NT) pm[i] = t[i >> 5];
+    }
   }
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31u;
-  const W* __restrict__ pm_lane = pm + lane;
+  const W* __restrict__ pm_lane = SPLIT64 ? reinterpret_cast<const W*>(reinterpret_cast<const uint32_t*>(smem_raw) + lane) : pm + lane;
   const uint64_t total_warps = (uint64_t)gridDim.x * (NT / 32);
   const uint64_t ngroups = p.lb.ngroups;
   const uint64_t nchunks = (ngroups + p.chunk - 1) / p.chunk;
@@ -630,6 +725,7 @@ __global__ void __launch_bounds__(NT) scan_lb_kernel(const __grid_constant__ LbP
         uint32_t raw;
         if constexpr (FAM == F_LEV && sizeof(W) == 4) raw = lev_w1_u32_fast(smem_u32(pm_lane), src.reader(), len2, p.len1, p.two);
         else if constexpr (FAM == F_OSA && sizeof(W) == 4) raw = myers_w1_u32_fast<true>(smem_u32(pm_lane), src.reader(), len2, p.len1, p.two);
+        else if constexpr (SPLIT64) raw = lev_w1_u64_fast(smem_u32(pm_lane), src.reader(), len2, p.len1, p.two);
         else {
           auto tab = [&](uint32_t ch) -> W { return pm_lane[ch * 32u]; };
           if constexpr (FAM == F_LEV) raw = lev_w1<W>(tab, src.reader(), len2, p.len1);
@@ -639,7 +735,7 @@ __global__ void __launch_bounds__(NT) scan_lb_kernel(const __grid_constant__ LbP
       } else {
         uint32_t ru = 0;
         double rf = 0.0;
-        score_one<FAM, W>(pm_lane, src, len2, p.len1, p.epi, p.out_f64, p.two, ru, rf);
+        score_one<FAM, W, LaneSrcT<true>, SPLIT64>(pm_lane, src, len2, p.len1, p.epi, p.out_f64, p.two, ru, rf);
         if (idx != 0xFFFFFFFFu) {
           if (p.out_f64) reinterpret_cast<double*>(p.out)[idx] = rf;
           else reinterpret_cast<uint32_t*>(p.out)[idx] = ru;
@@ -1368,7 +1464,16 @@ __global__ void __launch_bounds__(CD_NT) cdist_scan_kernel(const __grid_constant
     const uint64_t g_lo = s_bounds[sl], g_hi = s_bounds[sl + 1];
     {
       const W* __restrict__ t = reinterpret_cast<const W*>(p.tabs) + (size_t)q * 256;
-      for (uint32_t i = tid; i < 8192u; i += CD_NT) pm[i] = t[i >> 5];
+      if constexpr (sizeof(W) == 8) {  // split low / high word tables (lev_w1_u64_fast)
+        uint32_t* pm32 = reinterpret_cast<uint32_t*>(smem_raw);
+        for (uint32_t i = tid; i < 8192u; i += CD_NT) {
+          const uint64_t v = t[i >> 5];
+          pm32[i] = (uint32_t)v;
+          pm32[i + 8192u] = (uint32_t)(v >> 32);
+        }
+      } else {
+        for (uint32_t i = tid; i < 8192u; i += CD_NT) pm[i] = t[i >> 5];
+      }
     }
     __syncthreads();
     const uint32_t len1 = p.q_len[q];
@@ -1415,10 +1520,7 @@ __global__ void __launch_bounds__(CD_NT) cdist_scan_kernel(const __grid_constant
       uint32_t d;
       if (len1 == 0) d = len2;
       else if constexpr (sizeof(W) == 4) d = lev_w1_u32_fast(smem_u32(pm_lane), src.reader(), len2, len1, p.two);
-      else {
-        auto tab = [&](uint32_t ch) -> W { return pm_lane[ch * 32u]; };
-        d = lev_w1<W>(tab, src.reader(), len2, len1);
-      }
+      else d = lev_w1_u64_fast(smem_u32(reinterpret_cast<const uint32_t*>(smem_raw) + lane), src.reader(), len2, len1, p.two);
       const bool ok = idx != 0xFFFFFFFFu && d <= static_bound;
       top.offer(ok ? (((unsigned long long)d << 32) | idx) : CD_NOKEY, bound, k, lane, &s_kth);
     }

@@ -23,6 +23,15 @@ import rapidfuzz_b200 as rf
 from rapidfuzz_b200 import sharding
 
 
+def sm_clock(index):
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        return pynvml.nvmlDeviceGetClockInfo(pynvml.nvmlDeviceGetHandleByIndex(index), pynvml.NVML_CLOCK_SM)
+    except Exception:
+        return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -73,8 +82,13 @@ def main():
         t_scan.append(ms_scan)
         t_all.append(ms_all)
     ms = torch.tensor([sum(t_all) / len(t_all), sum(t_scan) / len(t_scan)], dtype=torch.float64, device=dev)
+    mine = torch.tensor([float(ms[1]), float(sm_clock(local))], dtype=torch.float64, device=dev)
+    per_rank = [torch.zeros_like(mine) for _ in range(world)]
     if world > 1:
+        dist.all_gather(per_rank, mine)
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    else:
+        per_rank = [mine]
     ms_all, ms_scan = float(ms[0]), float(ms[1])
     if rank == 0:
         from oracle import oracle as orc   # checker only: global top-k of the first queries over the WHOLE corpus
@@ -88,6 +102,8 @@ def main():
                           "config": {"workload": "config5: %d queries len 32 x %d candidates len 8-64, top-%d, corpus sharded by "
                                                  "candidate (byte-balanced), one NCCL all-gather of the per-shard lists + device merge" % (nq, n, k),
                                      "scan_ms_max_over_ranks": ms_scan, "gather_merge_ms": ms_all - ms_scan,
+                                     "scan_ms_per_rank": [round(float(t[0]), 2) for t in per_rank],
+                                     "sm_mhz_after_last_step_per_rank": [int(t[1]) for t in per_rank],
                                      "global_topk_matches_oracle_first_%d_queries" % min(a.check_queries, nq): bool(ok)}}), flush=True)
     corpus.close()
     if world > 1:

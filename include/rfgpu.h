@@ -100,6 +100,7 @@ rf_status rf_corpus_create_device_u8(const uint8_t* d_chars, const uint64_t* d_o
 /* u32 elements (Rust `char`, u32: the reference accepts any HashableChar, details/common.rs:29-37).  Such a
  * corpus is scored by comparators made with rf_batch_create_u32; results are exact (see there). */
 rf_status rf_corpus_create_u32(const uint32_t* elems, const uint64_t* offsets, uint64_t n, int device, rf_corpus** out);
+/* Waits for the device to drain first (asynchronous *_device calls may still be reading the corpus). */
 rf_status rf_corpus_destroy(rf_corpus* c);
 uint64_t rf_corpus_size(const rf_corpus* c);        /* number of candidates */
 uint64_t rf_corpus_total_chars(const rf_corpus* c); /* sum of candidate lengths */

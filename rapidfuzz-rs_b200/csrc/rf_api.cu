@@ -330,6 +330,9 @@ rf_status rf_corpus_create_u32(const uint32_t* elems, const uint64_t* offsets, u
 rf_status rf_corpus_destroy(rf_corpus* c) {
   if (!c) return RF_OK;
   DeviceGuard g(c->device);
+  // the *_device entry points are asynchronous on the caller's stream: a scan may still be reading this corpus, and
+  // the stream-ordered frees below are ordered on an internal stream only -> drain the device first (destroy is rare)
+  cudaDeviceSynchronize();
   cudaStream_t st = util_stream(c->device);
   dev_free(c->d_chars, st);
   dev_free(c->d_elems32, st);

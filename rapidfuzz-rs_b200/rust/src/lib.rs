@@ -61,6 +61,13 @@ extern "C" {
     pub fn rf_batch_score_f64(b: *const rf_batch, c: *const rf_corpus, kind: c_int, args: *const rf_args, out: *mut f64) -> c_int;
     pub fn rf_cdist_topk_u8(q_chars: *const u8, q_offsets: *const u64, nq: u32, c: *const rf_corpus, args: *const rf_args,
                             k: u32, idx: *mut u32, dist: *mut u32) -> c_int;
+    // sharded corpora (one process per GPU): per-shard lists stay on the device, are exchanged with one all-gather
+    // (NCCL) and merged by (distance, global index)
+    pub fn rf_cdist_topk_u8_device(q_chars: *const u8, q_offsets: *const u64, nq: u32, c: *const rf_corpus, args: *const rf_args,
+                                   k: u32, idx_device: *mut u32, dist_device: *mut u32, stream: *mut c_void) -> c_int;
+    pub fn rf_topk_merge_device(idx_parts: *const u32, dist_parts: *const u32, part_stride: u64, index_base_device: *const u64,
+                                parts: u32, nq: u32, k: u32, idx_out_device: *mut u64, dist_out_device: *mut u32,
+                                device: c_int, stream: *mut c_void) -> c_int;
     pub fn rf_set_option(name: *const c_char, value: c_int) -> c_int;
     // one-shot scoring of host-resident candidates (chunked H2D / scan / D2H pipeline)
     pub fn rf_batch_stream_u32(b: *const rf_batch, chars: *const u8, offsets: *const u64, n: u64, kind: c_int, args: *const rf_args, out: *mut u32) -> c_int;

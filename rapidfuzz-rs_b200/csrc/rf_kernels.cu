@@ -331,6 +331,119 @@ __device__ __forceinline__ uint32_t lev_w1_u32_fast(uint32_t pm_lane_saddr, Rd r
   return myers_w1_u32_fast<false>(pm_lane_saddr, rd, len2, len1, two);
 }
 
+// Row walker for the interleaved layout: the software pipeline of myers_w1_u32_fast (two rows in flight, four rows
+// per iteration, L2 prefetch for streamed rows) around an arbitrary per-character step.  `st.template step<K>(w)`
+// consumes byte K of the 32-bit word w.
+template <class Rd, class St>
+__device__ __forceinline__ void walk_rows8(Rd rd, uint32_t len2, St& st) {
+  static_assert(Rd::kRow8, "interleaved rows only");
+#define RF_WALK_ROW(R)                                                                                   \
+  {                                                                                                      \
+    { const uint32_t w = (R).x; st.template step<0>(w); st.template step<1>(w); st.template step<2>(w); st.template step<3>(w); } \
+    { const uint32_t w = (R).y; st.template step<0>(w); st.template step<1>(w); st.template step<2>(w); st.template step<3>(w); } \
+  }
+  uint2 A = rd.q0, B = rd.q1;
+  const uint2* p = rd.p;
+  const uint32_t nfull = len2 >> 3;
+  uint32_t i = 0;
+  for (; i + 4 <= nfull; i += 4) {
+    if constexpr (Rd::kStream) {
+      prefetch_l2(p + 32 * kPfDist);
+      prefetch_l2(p + 32 * (kPfDist + 1));
+      prefetch_l2(p + 32 * (kPfDist + 2));
+      prefetch_l2(p + 32 * (kPfDist + 3));
+    }
+    const uint2 C = ld_row8<Rd::kStream>(p);
+    const uint2 D = ld_row8<Rd::kStream>(p + 32);
+    RF_WALK_ROW(A)
+    RF_WALK_ROW(B)
+    A = ld_row8<Rd::kStream>(p + 64);
+    B = ld_row8<Rd::kStream>(p + 96);
+    p += 128;
+    RF_WALK_ROW(C)
+    RF_WALK_ROW(D)
+  }
+  if (i + 2 <= nfull) {
+    if constexpr (Rd::kStream) {
+      prefetch_l2(p + 32 * kPfDist);
+      prefetch_l2(p + 32 * (kPfDist + 1));
+    }
+    const uint2 C = ld_row8<Rd::kStream>(p);
+    const uint2 D = ld_row8<Rd::kStream>(p + 32);
+    p += 64;
+    RF_WALK_ROW(A)
+    RF_WALK_ROW(B)
+    A = C;
+    B = D;
+    i += 2;
+  }
+  if (i < nfull) {
+    RF_WALK_ROW(A)
+    A = B;
+  }
+#undef RF_WALK_ROW
+  const uint32_t rem = len2 & 7u;
+  if (rem) {
+    const uint2 ww = A;
+    { const uint32_t w = ww.x;
+      st.template step<0>(w);
+      if (rem > 1) st.template step<1>(w);
+      if (rem > 2) st.template step<2>(w);
+      if (rem > 3) st.template step<3>(w); }
+    if (rem > 4) {
+      const uint32_t w = ww.y;
+      st.template step<0>(w);
+      if (rem > 5) st.template step<1>(w);
+      if (rem > 6) st.template step<2>(w);
+    }
+  }
+}
+
+// LCS length (Hyyro, lcs_seq.rs:222-257), 32-bit words, bottom-aligned table in shared memory.  Per text char:
+// IDP.4A (address) . LDS . LOP3 (U = S & X) . IMAD (S + U; `one` is opaque so it stays on the FMA pipe) . LOP3
+// ((S + U) | (S & ~U)): two ALU-pipe ops against Levenshtein's seven -- this kernel is bound by HBM, not by a pipe.
+struct Lcs32Step {
+  uint32_t S, base, one;
+  template <int K>
+  __device__ __forceinline__ void step(uint32_t w) {
+    uint32_t X;
+    const uint32_t addr = __dp4a(w, 0x80u << (8 * K), base);
+    asm("ld.shared.u32 %0, [%1];" : "=r"(X) : "r"(addr));
+    const uint32_t U = S & X;
+    S = (U * one + S) | (S & ~U);
+  }
+};
+template <class Rd>
+__device__ __forceinline__ uint32_t lcs_w1_u32_fast(uint32_t pm_lane_saddr, Rd rd, uint32_t len2, uint32_t two) {
+  Lcs32Step st{0xFFFFFFFFu, pm_lane_saddr, two >> 1};
+  walk_rows8(rd, len2, st);
+  return (uint32_t)__popc(~st.S);
+}
+
+// The same for queries of 33..64 elements on 32-bit halves: split low / high word tables (see lev_w1_u64_fast), the
+// 64-bit S + U as IADD3 (carry out) + IMAD.X.
+struct Lcs64Step {
+  uint32_t Sl, Sh, base, one;
+  template <int K>
+  __device__ __forceinline__ void step(uint32_t w) {
+    uint32_t Xl, Xh, al, ah;
+    const uint32_t addr = __dp4a(w, 0x80u << (8 * K), base);
+    asm("ld.shared.u32 %0, [%1];" : "=r"(Xl) : "r"(addr));
+    asm("ld.shared.u32 %0, [%1+32768];" : "=r"(Xh) : "r"(addr));
+    const uint32_t Ul = Sl & Xl, Uh = Sh & Xh;
+    asm("{\n\tadd.cc.u32 %0, %2, %3;\n\tmadc.lo.u32 %1, %4, %5, %6;\n\t}"
+        : "=r"(al), "=r"(ah) : "r"(Ul), "r"(Sl), "r"(Sh), "r"(one), "r"(Uh));
+    Sl = al | (Sl & ~Ul);
+    Sh = ah | (Sh & ~Uh);
+  }
+};
+template <class Rd>
+__device__ __forceinline__ uint32_t lcs_w1_u64_fast(uint32_t pm_lane_saddr, Rd rd, uint32_t len2, uint32_t two) {
+  Lcs64Step st{0xFFFFFFFFu, 0xFFFFFFFFu, pm_lane_saddr, two >> 1};
+  walk_rows8(rd, len2, st);
+  return (uint32_t)__popc(~st.Sl) + (uint32_t)__popc(~st.Sh);
+}
+
 // Levenshtein, query of 33..64 elements: the 64-bit recurrence of lev_w1<uint64_t> written on 32-bit halves so that,
 // as in the 32-bit routine, only the 14 LOP3 of a step remain on the ALU pipe.  ptxas expands a 64-bit add into
 // IADD3 + IADD3.X and a 64-bit shift into SHF + SHL, all ALU-pipe; here
@@ -442,6 +555,8 @@ __device__ __forceinline__ void score_one(const W* __restrict__ pm_lane, const S
       else if constexpr (FAM == F_LEV) raw = lev_w1<W>(tab, src.reader(), len2, len1);
       else if constexpr (FAM == F_OSA && sizeof(W) == 4) raw = myers_w1_u32_fast<true>(smem_u32(pm_lane), src.reader(), len2, len1, two);
       else if constexpr (FAM == F_OSA) raw = osa_w1<W>(tab, src.reader(), len2, len1);
+      else if constexpr (FAM == F_LCS && sizeof(W) == 4 && decltype(src.reader())::kRow8) raw = lcs_w1_u32_fast(smem_u32(pm_lane), src.reader(), len2, two);
+      else if constexpr (FAM == F_LCS && SPLIT64) raw = lcs_w1_u64_fast(smem_u32(pm_lane), src.reader(), len2, two);
       else raw = lcs_w1<W>(tab, src.reader(), len2);
     }
     if (out_f64) rf = finish_norm(epi, raw, len1, len2);
@@ -671,7 +786,7 @@ struct LbParams {
 template <int FAM, class W, int NT, bool RAWDIST>
 __global__ void __launch_bounds__(NT) scan_lb_kernel(const __grid_constant__ LbParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr bool SPLIT64 = (FAM == F_LEV && sizeof(W) == 8);  // low / high words in two 32 KB tables (lev_w1_u64_fast)
+  constexpr bool SPLIT64 = ((FAM == F_LEV || FAM == F_LCS) && sizeof(W) == 8);  // low / high words in two 32 KB tables (lev_w1_u64_fast, lcs_w1_u64_fast)
   W* pm = reinterpret_cast<W*>(smem_raw);
   {
     const W* __restrict__ t = reinterpret_cast<const W*>(p.tab);
@@ -725,7 +840,7 @@ __global__ void __launch_bounds__(NT) scan_lb_kernel(const __grid_constant__ LbP
         uint32_t raw;
         if constexpr (FAM == F_LEV && sizeof(W) == 4) raw = lev_w1_u32_fast(smem_u32(pm_lane), src.reader(), len2, p.len1, p.two);
         else if constexpr (FAM == F_OSA && sizeof(W) == 4) raw = myers_w1_u32_fast<true>(smem_u32(pm_lane), src.reader(), len2, p.len1, p.two);
-        else if constexpr (SPLIT64) raw = lev_w1_u64_fast(smem_u32(pm_lane), src.reader(), len2, p.len1, p.two);
+        else if constexpr (FAM == F_LEV && SPLIT64) raw = lev_w1_u64_fast(smem_u32(pm_lane), src.reader(), len2, p.len1, p.two);
         else {
           auto tab = [&](uint32_t ch) -> W { return pm_lane[ch * 32u]; };
           if constexpr (FAM == F_LEV) raw = lev_w1<W>(tab, src.reader(), len2, p.len1);

@@ -206,6 +206,11 @@ if __name__ == "__main__":
         one_vs_many("C2-shape fuzz::ratio", "ratio", "similarity", 2, 32, int(1e8 * scale), 8, 64, 16, None, True, lambda l: l + 12)
         one_vs_many("C2-shape levenshtein distance cutoff 8", "levenshtein", "distance", 2, 32, int(1e8 * scale), 8, 64, 16, 8,
                     False, lambda l: l + 8)
+    if "fam" in which:   # the other bit-parallel metrics of the family on the config-2 shape (u32 results)
+        for m, kind in (("indel", "distance"), ("lcs_seq", "similarity"), ("osa", "distance")):
+            one_vs_many("C2-shape " + m + " " + kind, m, kind, 2, 32, int(1e8 * scale), 8, 64, 16, None, False, lambda l: l + 8)
+        one_vs_many("C2-shape indel distance (query len 64)", "indel", "distance", 2, 64, int(1e8 * scale), 8, 64, 16, None, False,
+                    lambda l: l + 8)
     if "simple" in which:   # HBM-bound metrics: bytes = len + 4 + 4 per pair
         for m, kind in (("hamming", "distance"), ("prefix", "similarity"), ("postfix", "similarity")):
             q = rf.synth_query(2, 32)

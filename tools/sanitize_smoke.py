@@ -31,6 +31,25 @@ b.stream("distance", chars, offsets.astype(np.uint32))
 b.close()
 rf.cdist_topk([q, rf.synth_query(3, 20), rf.synth_query(4, 64)], corpus, k=10)
 rf.cdist_topk([q], corpus, k=40, score_cutoff=30)
+for sl in (3, 17, 0):   # several corpus slices -> cdist_merge_kernel; 0 = automatic
+    _ffi.check(L.rf_set_option(b"cdist_slices", sl))
+    rf.cdist_topk([rf.synth_query(10 + i, (8, 32, 47, 64)[i % 4]) for i in range(40)], corpus, k=10)
+try:   # sharded merge (rf_topk_merge_device), three shards on one GPU
+    import torch
+    from rapidfuzz_b200 import sharding
+    qs = [rf.synth_query(20 + i, 32) for i in range(8)]
+    qo = np.arange(9, dtype=np.uint64) * 32
+    parts, starts = [], []
+    for r in range(3):
+        c_, o_, lo = sharding.local_shard(chars, offsets, 3, r)
+        cp = rf.Corpus(c_, o_)
+        i_, d_ = sharding.cdist_topk_device(np.concatenate(qs), qo, cp, k=10)
+        parts.append(torch.stack([i_, d_], 0)); starts.append(lo)
+        torch.cuda.synchronize(); cp.close()
+    sharding.merge_topk_device(torch.stack(parts, 0).contiguous(), torch.tensor(starts, dtype=torch.int64, device="cuda"), 10)
+    torch.cuda.synchronize()
+except ImportError:
+    pass
 q3 = rf.synth_query(3, 256)
 c3, o3 = rf.synth_corpus(3, q3, 2000, 64, 256, 48)
 corpus3 = rf.Corpus(c3, o3)

@@ -98,7 +98,9 @@ rf_status rf_corpus_create_u8_off32(const uint8_t* chars, const uint32_t* offset
 rf_status rf_corpus_create_device_u8(const uint8_t* d_chars, const uint64_t* d_offsets, uint64_t n,
                                      uint64_t total_chars, int device, void* stream, rf_corpus** out);
 /* u32 elements (Rust `char`, u32: the reference accepts any HashableChar, details/common.rs:29-37).  Such a
- * corpus is scored by comparators made with rf_batch_create_u32; results are exact (see there). */
+ * corpus is scored by comparators made with rf_batch_create_u32; results are exact (see there).  A corpus whose
+ * elements take at most 255 distinct values is renamed to bytes once, here, and then costs and scores like a u8
+ * corpus (rf_set_option("compact_u32_corpus", 0) turns that off). */
 rf_status rf_corpus_create_u32(const uint32_t* elems, const uint64_t* offsets, uint64_t n, int device, rf_corpus** out);
 /* Waits for the device to drain first (asynchronous *_device calls may still be reading the corpus). */
 rf_status rf_corpus_destroy(rf_corpus* c);

@@ -12,6 +12,8 @@
 #include <string>
 #include <vector>
 
+#include <algorithm>
+#include <unordered_map>
 #include "../../include/rfgpu.h"
 #include "rf_kernels.cuh"
 
@@ -24,6 +26,7 @@ static std::atomic<int> g_w1_path{0};    // 0: interleaved-layout kernel when av
 static std::atomic<int> g_band{1};       // multi-word Levenshtein with cutoff <= 63: banded kernel (0: block kernel)
 static std::atomic<int> g_stream_mb{64};      // rf_batch_stream_*: chunk size in candidate bytes (MiB)
 static std::atomic<int> g_stream_kcand{2048}; // rf_batch_stream_*: chunk size in candidates (x1024)
+static std::atomic<int> g_compact32{1};       // rf_corpus_create_u32: keep corpora with <= 255 distinct symbols as renamed bytes
 static std::atomic<int> g_cdist_slices{0};    // rf_cdist_topk_*: corpus slices (0: automatic)
 static std::atomic<int> g_cdist_skip{1};      // rf_cdist_topk_*: skip groups by length against the running k-th bound
 
@@ -89,6 +92,13 @@ struct rf_corpus {
   uint32_t* d_off32 = nullptr;
   uint64_t* d_off64 = nullptr;
   LbAlloc lb;  // length-bucketed interleaved copy for the single-word kernels
+  // rf_corpus_create_u32 with at most 255 distinct symbols in the whole corpus: the symbols are renamed to the bytes
+  // 1..D ONCE at creation and the corpus is kept (and scored) as a u8 corpus; d_elems32 is released.  The dictionary
+  // stays on the host: a u32 comparator renames its query through it (absent symbols -> 0, which matches nothing).
+  bool compact32 = false;
+  uint64_t dict_serial = 0;
+  std::vector<uint32_t> dict_keys;   // [kAlphaSlots] open addressing (alpha_hash)
+  std::vector<uint8_t> dict_codes;   // [kAlphaSlots] 0 = empty slot
 };
 
 struct rf_batch {
@@ -102,6 +112,9 @@ struct rf_batch {
   // renamed on the device per scoring call (symbols the query does not contain become 0, which matches nothing).
   // Every metric here depends only on which (query, candidate) positions are equal, so the result is exact.
   bool wide = false;
+  std::vector<uint32_t> s1w;         // the u32 query as given
+  mutable std::mutex sub_mu;         // byte comparators of this query against compact u32 corpora, by dictionary
+  mutable std::unordered_map<uint64_t, rf_batch*> subs;
   uint32_t* d_alpha_keys = nullptr;  // [kAlphaSlots] open-addressing table: symbol ...
   uint8_t* d_alpha_codes = nullptr;  // ... -> byte code, 0 = empty slot
 };
@@ -148,6 +161,7 @@ rf_status rf_set_option(const char* name, int value) {
   if (!strcmp(name, "stream_chunk_mb")) { if (value < 1) return fail(RF_ERR_INVALID_ARG, "stream_chunk_mb < 1"); g_stream_mb.store(value); return RF_OK; }
   if (!strcmp(name, "stream_chunk_kcand")) { if (value < 1) return fail(RF_ERR_INVALID_ARG, "stream_chunk_kcand < 1"); g_stream_kcand.store(value); return RF_OK; }
   if (!strcmp(name, "cdist_slices")) { if (value < 0 || value > 256) return fail(RF_ERR_INVALID_ARG, "cdist_slices not in 0..256"); g_cdist_slices.store(value); return RF_OK; }
+  if (!strcmp(name, "compact_u32_corpus")) { g_compact32.store(value ? 1 : 0); return RF_OK; }
   if (!strcmp(name, "cdist_skip")) { g_cdist_skip.store(value ? 1 : 0); return RF_OK; }
   return fail(RF_ERR_INVALID_ARG, std::string("unknown option: ") + name);
 }
@@ -281,6 +295,8 @@ rf_status rf_corpus_create_device_u8(const uint8_t* d_chars, const uint64_t* d_o
   return RF_OK;
 }
 
+static rf_status compact_u32_corpus(rf_corpus* c, cudaStream_t st);
+
 rf_status rf_corpus_create_u32(const uint32_t* elems, const uint64_t* offsets, uint64_t n, int device, rf_corpus** out) {
   if (!out) return fail(RF_ERR_INVALID_ARG, "out is NULL");
   *out = nullptr;
@@ -323,6 +339,10 @@ rf_status rf_corpus_create_u32(const uint32_t* elems, const uint64_t* offsets, u
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   dev_free(tmp64, st);
   if (e != cudaSuccess) { rf_corpus_destroy(c); return cuda_fail(e, "u32 corpus upload"); }
+  if (g_compact32.load() && total) {
+    rf_status s = compact_u32_corpus(c, st);
+    if (s != RF_OK) { rf_corpus_destroy(c); return s; }
+  }
   *out = c;
   return RF_OK;
 }
@@ -463,6 +483,7 @@ rf_status rf_batch_create_u32(rf_metric metric, const uint32_t* query, uint32_t 
   if (s != RF_OK) return s;
   DeviceGuard g(device);
   b->wide = true;
+  b->s1w.assign(query, query + query_len);
   cudaError_t e = cudaMalloc(&b->d_alpha_keys, kAlphaSlots * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMalloc(&b->d_alpha_codes, kAlphaSlots);
   if (e == cudaSuccess) e = upload_sync(b->d_alpha_keys, keys.data(), kAlphaSlots * sizeof(uint32_t), device);
@@ -478,6 +499,7 @@ rf_status rf_batch_destroy(rf_batch* b) {
   if (b->d_blob) cudaFree(b->d_blob);
   if (b->d_alpha_keys) cudaFree(b->d_alpha_keys);
   if (b->d_alpha_codes) cudaFree(b->d_alpha_codes);
+  for (auto& kv : b->subs) rf_batch_destroy(kv.second);
   delete b;
   return RF_OK;
 }
@@ -602,13 +624,152 @@ __global__ void __launch_bounds__(256) remap_kernel(const In* __restrict__ in, u
   }
 }
 
+// distinct symbols of a u32 corpus: per-CTA hash set in shared memory, merged into a global one; more than 255 -> overflow
+__global__ void __launch_bounds__(256) distinct_kernel(const uint32_t* __restrict__ in, uint64_t total,
+                                                       unsigned long long* __restrict__ gset, uint32_t* __restrict__ gcount) {
+  __shared__ unsigned long long sset[1024];
+  __shared__ uint32_t scount, sover;
+  for (uint32_t i = threadIdx.x; i < 1024; i += 256) sset[i] = 0ull;
+  if (threadIdx.x == 0) { scount = 0; sover = 0; }
+  __syncthreads();
+  for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (uint64_t)gridDim.x * 256) {
+    if (*reinterpret_cast<volatile uint32_t*>(&sover)) break;
+    const uint32_t x = in[i];
+    const unsigned long long key = (1ull << 32) | x;
+    uint32_t slot = (x * 2654435761u) >> 22;
+    for (;;) {
+      const unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&sset[slot]);
+      if (cur == key) break;
+      if (cur == 0ull) {
+        const unsigned long long old = atomicCAS(&sset[slot], 0ull, key);
+        if (old == 0ull) { if (atomicAdd(&scount, 1u) >= 255u) sover = 1; break; }
+        if (old == key) break;
+      }
+      slot = (slot + 1) & 1023u;
+    }
+  }
+  __syncthreads();
+  if (sover) { if (threadIdx.x == 0) gcount[1] = 1; return; }
+  for (uint32_t s0 = threadIdx.x; s0 < 1024; s0 += 256) {
+    const unsigned long long key = sset[s0];
+    if (!key) continue;
+    uint32_t slot = ((uint32_t)key * 2654435761u) >> 22;
+    for (;;) {
+      const unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&gset[slot]);
+      if (cur == key) break;
+      if (cur == 0ull) {
+        const unsigned long long old = atomicCAS(&gset[slot], 0ull, key);
+        if (old == 0ull) { if (atomicAdd(&gcount[0], 1u) >= 255u) gcount[1] = 1; break; }
+        if (old == key) break;
+      }
+      if (*reinterpret_cast<volatile uint32_t*>(&gcount[1])) break;  // overflowing anyway: the set may fill up
+      slot = (slot + 1) & 1023u;
+    }
+  }
+}
+
+static std::atomic<uint64_t> g_dict_serial{1};
+
+// rf_corpus_create_u32, second half: if the whole corpus uses at most 255 distinct symbols, rename them to bytes once
+// (codes 1..D in ascending symbol order), keep the corpus as u8 CSR + interleaved layout and drop the u32 copy.
+static rf_status compact_u32_corpus(rf_corpus* c, cudaStream_t st) {
+  unsigned long long* d_set = nullptr;
+  uint32_t* d_cnt = nullptr;
+  uint32_t* d_keys = nullptr;
+  uint8_t* d_codes = nullptr;
+  rf_status s = RF_OK;
+  cudaError_t e;
+  do {
+    if ((e = dev_alloc(&d_set, 1024 * 8 + 16, st)) != cudaSuccess) break;
+    d_cnt = reinterpret_cast<uint32_t*>(d_set + 1024);
+    if ((e = cudaMemsetAsync(d_set, 0, 1024 * 8 + 16, st)) != cudaSuccess) break;
+    const uint64_t blocks = (c->total + 256 * 64 - 1) / (256 * 64);
+    const uint32_t grid = (uint32_t)(blocks < (uint64_t)sm_count_of(c->device) * 8 ? (blocks ? blocks : 1) : (uint64_t)sm_count_of(c->device) * 8);
+    distinct_kernel<<<grid, 256, 0, st>>>(c->d_elems32, c->total, d_set, d_cnt);
+    rfk::count_launches(1);
+    if ((e = cudaGetLastError()) != cudaSuccess) break;
+    std::vector<unsigned long long> hset(1024 + 2);
+    if ((e = cudaMemcpyAsync(hset.data(), d_set, 1024 * 8 + 16, cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) break;
+    const uint32_t* cnt = reinterpret_cast<const uint32_t*>(hset.data() + 1024);
+    if (cnt[1] || cnt[0] > 255) break;  // too many symbols: stays a u32 corpus (renamed per query)
+    std::vector<uint32_t> syms;
+    for (int i = 0; i < 1024; ++i)
+      if (hset[i]) syms.push_back((uint32_t)hset[i]);
+    std::sort(syms.begin(), syms.end());
+    c->dict_keys.assign(kAlphaSlots, 0);
+    c->dict_codes.assign(kAlphaSlots, 0);
+    for (size_t k = 0; k < syms.size(); ++k) {
+      uint32_t slot = alpha_hash(syms[k]);
+      while (c->dict_codes[slot]) slot = (slot + 1) & (kAlphaSlots - 1);
+      c->dict_keys[slot] = syms[k];
+      c->dict_codes[slot] = (uint8_t)(k + 1);
+    }
+    if ((e = dev_alloc(&d_keys, kAlphaSlots * 4, st)) != cudaSuccess) break;
+    if ((e = dev_alloc(&d_codes, kAlphaSlots, st)) != cudaSuccess) break;
+    if ((e = cudaMemcpyAsync(d_keys, c->dict_keys.data(), kAlphaSlots * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+    if ((e = cudaMemcpyAsync(d_codes, c->dict_codes.data(), kAlphaSlots, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+    const uint64_t padded = (c->total + 3) / 4 * 4;
+    if ((e = dev_alloc(&c->d_chars, padded + 64, st)) != cudaSuccess) break;
+    if ((e = cudaMemsetAsync(c->d_chars + (padded - 4), 0, 64 + 4, st)) != cudaSuccess) break;
+    {
+      const uint64_t rb = ((c->total + 3) / 4 + 255) / 256;
+      const uint32_t rgrid = (uint32_t)(rb < 148 * 16 ? rb : 148 * 16);
+      remap_kernel<uint32_t><<<rgrid, 256, 0, st>>>(c->d_elems32, c->total, d_keys, d_codes, (uint32_t*)c->d_chars);
+      rfk::count_launches(1);
+      if ((e = cudaGetLastError()) != cudaSuccess) break;
+    }
+    dev_free(c->d_elems32, st);
+    c->d_elems32 = nullptr;
+    c->compact32 = true;
+    c->dict_serial = g_dict_serial.fetch_add(1);
+    s = corpus_finish(c, st);  // interleaved layout for the single-word kernels (the offsets' tail is already filled)
+    if (s == RF_OK) e = cudaStreamSynchronize(st);
+  } while (0);
+  dev_free(d_set, st);
+  dev_free(d_keys, st);
+  dev_free(d_codes, st);
+  cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return cuda_fail(e, "u32 corpus alphabet");
+  return s;
+}
+
+// the byte comparator of a u32 query against one compact corpus (cached per dictionary)
+static const rf_batch* compact_sub(const rf_batch* b, const rf_corpus* c) {
+  std::lock_guard<std::mutex> lk(b->sub_mu);
+  auto it = b->subs.find(c->dict_serial);
+  if (it != b->subs.end()) return it->second;
+  std::vector<uint8_t> renamed(b->s1w.size());
+  for (size_t i = 0; i < b->s1w.size(); ++i) {
+    const uint32_t x = b->s1w[i];
+    uint32_t slot = alpha_hash(x);
+    while (c->dict_codes[slot] && c->dict_keys[slot] != x) slot = (slot + 1) & (kAlphaSlots - 1);
+    renamed[i] = c->dict_codes[slot];  // 0 when the corpus never contains x
+  }
+  rf_batch* sub = nullptr;
+  if (batch_create_bytes(b->metric, renamed.data(), (uint32_t)renamed.size(), b->device, &sub) != RF_OK) return nullptr;
+  if (b->subs.size() >= 64) {  // bound the cache: comparators are cheap to rebuild
+    for (auto& kv : b->subs) rf_batch_destroy(kv.second);
+    b->subs.clear();
+  }
+  b->subs.emplace(c->dict_serial, sub);
+  return sub;
+}
+
 extern "C" {
 
 static rf_status score_device(const rf_batch* b, const rf_corpus* c, rf_kind kind, const rf_args* args, void* out_dev,
                               bool want_f64, cudaStream_t st, uint32_t* d_err = nullptr) {
   if (!b || !c) return fail(RF_ERR_INVALID_ARG, "NULL handle");
-  if (c->d_elems32 && !b->wide)
+  if ((c->d_elems32 || c->compact32) && !b->wide)
     return fail(RF_ERR_INVALID_ARG, "a u32 corpus needs a comparator created with rf_batch_create_u32");
+  if (c->compact32) {  // the corpus already is bytes in ITS alphabet: score with the query renamed through its dictionary
+    if (b->device != c->device) return fail(RF_ERR_INVALID_ARG, "batch and corpus live on different devices");
+    const rf_batch* sub = compact_sub(b, c);
+    if (!sub) return RF_ERR_CUDA;  // message set by the failing call
+    return score_view(sub, CorpusView{c->d_chars, c->d_off32, c->d_off64, c->n, c->total}, &c->lb, c->device, kind, args,
+                      out_dev, want_f64, st, d_err);
+  }
   if (b->wide) {
     if (b->device != c->device) return fail(RF_ERR_INVALID_ARG, "batch and corpus live on different devices");
     if (c->n == 0) return RF_OK;

@@ -306,6 +306,62 @@ def test_u32_elements_vs_oracle(qlen):
     c8.close()
 
 
+@pytest.mark.parametrize("distinct", [10, 255, 256, 400])
+def test_u32_corpus_alphabet_compaction(distinct):
+    """rf_corpus_create_u32 keeps a corpus of at most 255 distinct symbols as bytes renamed ONCE (codes by ascending
+    symbol); a u32 query is renamed through the corpus dictionary, symbols the corpus never contains match nothing.
+    256+ distinct symbols fall back to the per-query renaming.  Both must equal the oracle, and each other."""
+    rng = np.random.default_rng(900 + distinct)
+    alphabet = np.unique(np.concatenate([np.array([0, 97, 255, 256, 0x4E2D, 0xFFFFFFFF], np.uint32),
+                                         rng.integers(0, 2**32, 2 * distinct, dtype=np.uint64).astype(np.uint32)]))[:distinct]
+    rng.shuffle(alphabet)
+    assert len(alphabet) == distinct
+    lens = rng.integers(0, 70, 4000)
+    elems = alphabet[rng.integers(0, distinct, int(lens.sum()))]
+    elems[:distinct] = alphabet                                   # every symbol occurs
+    offsets = np.zeros(len(lens) + 1, dtype=np.uint64)
+    offsets[1:] = np.cumsum(lens)
+    L = _ffi.lib()
+    absent = np.uint32(0x0BADF00D)
+    assert absent not in alphabet
+    queries = [alphabet[rng.integers(0, min(distinct, 40), 32)], alphabet[rng.integers(0, distinct, 50)],
+               np.concatenate([alphabet[:5], [absent, absent, np.uint32(0x0BADF00E)], alphabet[2:9]]).astype(np.uint32)]
+    # a candidate equal to each query (absent symbols cannot occur in the corpus, so only for the first two)
+    results = {}
+    for opt in (1, 0):
+        _ffi.check(L.rf_set_option(b"compact_u32_corpus", opt))
+        try:
+            corpus = rf.Corpus.from_u32(elems, offsets)
+            other = rf.Corpus.from_u32(elems[::-1].copy(), offsets)   # a second dictionary for the same comparator
+        finally:
+            _ffi.check(L.rf_set_option(b"compact_u32_corpus", 1))
+        for qi, q in enumerate(queries):
+            for m, kind, cut in (("levenshtein", "distance", None), ("indel", "normalized_similarity", None), ("osa", "distance", 30),
+                                 ("jaro_winkler", "similarity", None), ("hamming", "distance", None), ("damerau_levenshtein", "distance", None)):
+                b = _bc(m, q)
+                a = rf.Args().pad(True) if m == "hamming" else rf.Args()
+                if cut is not None:
+                    a = a.score_cutoff(cut)
+                fill = lambda r: r.filled(np.nan if r.dtype == np.float64 else _ffi.NONE_U32) if isinstance(r, np.ma.MaskedArray) else r
+                got = fill(b._score(kind, corpus, a))
+                got2 = fill(b._score(kind, other, a))      # same comparator, second dictionary
+                got = fill(b._score(kind, corpus, a)) if qi == 0 else got
+                b.close()
+                kw = {} if cut is None else {"cutoff": cut}
+                if m == "hamming":
+                    kw["pad"] = True
+                exp = orc.batch(m, kind, q, elems, offsets, nthreads=0, **kw)
+                exp2 = orc.batch(m, kind, q, elems[::-1].copy(), offsets, nthreads=0, **kw)
+                assert_same(got, exp, ("compact", opt, distinct, qi, m, kind))
+                assert_same(got2, exp2, ("compact other", opt, distinct, qi, m, kind))
+                results[(opt, qi, m)] = got
+        corpus.close()
+        other.close()
+    for (opt, qi, m), v in results.items():
+        if opt == 1:
+            assert_same(v, results[(0, qi, m)], ("compact == per-query", qi, m))
+
+
 def test_u32_host_mirror_and_limits():
     assert rf.distance.levenshtein.distance("Иванко", "Петрунко") == 5            # levenshtein.rs:2164-2169
     assert rf.distance.indel.distance("Иванко", "Петрунко") == 8                  # indel.rs:851-857

@@ -295,4 +295,35 @@ class RatioBatchComparator {
 inline double ratio(std::string_view s1, std::string_view s2) { return RatioBatchComparator(s1).similarity(s2); }
 }  // namespace fuzz
 
+namespace process {  // new on this side (the reference has no many-vs-many): rf_cdist_topk_u8
+struct TopK {
+  uint32_t nq = 0, k = 0;
+  std::vector<uint32_t> index, distance;  // [nq][k], UINT32_MAX = fewer than k hits
+  std::optional<Hit<uint32_t>> at(uint32_t q, uint32_t i) const {
+    const size_t j = (size_t)q * k + i;
+    if (index[j] == UINT32_MAX) return std::nullopt;
+    return Hit<uint32_t>{index[j], distance[j]};
+  }
+};
+// for every query the k best candidates of `c` by (Levenshtein distance, index); queries of at most 64 bytes
+template <class Strings, class C = NoScoreCutoff>
+TopK cdist_topk(const Strings& queries, const Corpus& c, uint32_t k, const Args<uint32_t, C>& a = Args<uint32_t>{}) {
+  std::vector<uint8_t> chars;
+  std::vector<uint64_t> offsets{0};
+  for (const auto& q : queries) {
+    const std::string_view v(q);
+    chars.insert(chars.end(), v.begin(), v.end());
+    offsets.push_back(chars.size());
+  }
+  TopK r;
+  r.nq = (uint32_t)(offsets.size() - 1);
+  r.k = k;
+  r.index.resize((size_t)r.nq * k);
+  r.distance.resize((size_t)r.nq * k);
+  const rf_args ca = detail::to_c(a);
+  check(rf_cdist_topk_u8(chars.data(), offsets.data(), r.nq, c.handle(), &ca, k, r.index.data(), r.distance.data()));
+  return r;
+}
+}  // namespace process
+
 }  // namespace rapidfuzz_b200

@@ -72,6 +72,13 @@ int main() {
   EXPECT(threw);
   auto wg = sk.distance_with_args(corpus, Args<uint32_t>{}.weights(1, 2, 3));   // generic weights: Wagner-Fischer route
   EXPECT(wg[1] == 0 && wg[0] == 6 && wg[2] == 22);
+  {  // many-vs-many top-k: ties on the distance go to the smaller index
+    auto tk = process::cdist_topk(std::vector<std::string>{"South Korea", "aabd", ""}, corpus, 2);
+    EXPECT(tk.nq == 3 && tk.at(0, 0)->index == 1 && tk.at(0, 0)->score == 0 && tk.at(0, 1)->index == 0 && tk.at(0, 1)->score == 2);
+    EXPECT(tk.at(1, 0)->index == 3 && tk.at(1, 0)->score == 1 && tk.at(2, 0)->index == 2 && tk.at(2, 0)->score == 0);
+    auto tc = process::cdist_topk(std::vector<std::string>{"aabd"}, corpus, 3, Args<uint32_t>{}.score_cutoff(1));
+    EXPECT(tc.at(0, 0).has_value() && !tc.at(0, 1).has_value());
+  }
   std::printf(fails ? "cpp api: %d failure(s)\n" : "cpp api: all ok\n", fails);
   return fails ? 1 : 0;
 }

@@ -565,7 +565,8 @@ static rf_status score_view(const rf_batch* b, const CorpusView& cv, const LbAll
   if (use_lb) {
     L.lb = LbView{lb->perm, lb->lens, lb->goff, lb->gdata, lb->ngroups};
     L.lb_counter = counter_slot(device);
-    if (!L.lb_counter) return fail(RF_ERR_OOM, "scheduler scratch allocation failed");
+    L.lb_flag = counter_slot(device);
+    if (!L.lb_counter || !L.lb_flag) return fail(RF_ERR_OOM, "scheduler scratch allocation failed");
   }
   L.query = b->view;
   L.out = out_dev;

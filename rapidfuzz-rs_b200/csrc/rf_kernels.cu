@@ -777,6 +777,7 @@ struct LbParams {
   uint32_t two;
   uint32_t chunk;               // consecutive groups handed to a warp at a time
   unsigned long long* counter;  // dynamic chunk scheduler (zeroed before the launch)
+  unsigned long long* flag;     // scan_jaro32_kernel: set when a group was left to jaro32_long_kernel (zeroed before the launch)
   Epi epi;
 };
 
@@ -921,10 +922,14 @@ struct Jaro32Dev {
   __device__ __forceinline__ void flag_step(uint32_t w, uint32_t j, uint32_t len2, uint32_t bound, uint32_t pm_lane_saddr,
                                             uint32_t two, uint32_t& t8) {
     const uint32_t X = look<K>(w, pm_lane_saddr);
-    uint32_t m = X & (hi & lo) & ~P;
+    uint32_t m;
+    if (LO == 0) asm("lop3.b32 %0, %1, %2, %3, 0x40;" : "=r"(m) : "r"(X), "r"(hi), "r"(P));  // X & hi & ~P in ONE LOP3
+    else m = X & (hi & lo) & ~P;
     if (LENP) m = (j < len2) ? m : 0u;
     P |= m & (0u - m);
-    t8 = t8 * two + min(m, 1u);           // row-local text flags, first character in the top bit
+    // row-local text flags, first character in the top bit: t8 = t8 * 2 + (m != 0).  The flag is the carry of
+    // m + 0xFFFFFFFF (IADD3) consumed by an IMAD.X -- one ALU-pipe op instead of a predicate-setting LOP3 + SEL.
+    asm("{\n\t.reg .u32 d;\n\tadd.cc.u32 d, %1, 0xFFFFFFFF;\n\tmadc.lo.u32 %0, %0, %2, 0;\n\t}" : "+r"(t8) : "r"(m), "r"(two));
     hi = hi * two + (two >> 1);
     if (LO == 1) lo = lo * two;
     if (LO == 2) lo = (j >= bound) ? lo << 1 : lo;
@@ -945,26 +950,28 @@ struct Jaro32Dev {
     T = (T << 8) | t8;  // rows pile up from the bottom byte; align_T() moves row 0 to the top byte
   }
   __device__ __forceinline__ void align_T(uint32_t nrows) { T = nrows ? T << (8u * (8u - nrows)) : 0ull; }
-  template <int K, int TB>
-  __device__ __forceinline__ void trans_step(uint32_t w, uint32_t t8, uint32_t pm_lane_saddr) {
+  // `tt` holds the INVERTED text flags of the row, current character in bit 31.  A flagged character pairs with the
+  // lowest remaining pattern flag: x = P - flagged (add.cc shifts the flag out into the carry, the IMAD.X computes
+  // P + 0xFFFFFFFF + !flagged), P & ~x is that pattern flag (or 0), P &= x retires it.
+  template <int K>
+  __device__ __forceinline__ void trans_step(uint32_t w, uint32_t& tt, uint32_t pm_lane_saddr, uint32_t one) {
     const uint32_t X = look<K>(w, pm_lane_saddr);
-    const uint32_t pbit = P & (0u - P);
-    if (t8 & (0x80u >> TB)) {  // this text character was flagged: it pairs with the lowest remaining pattern flag
-      M |= pbit & ~X;          // pattern flags whose partner differs (one bit per transposed pair member)
-      P ^= pbit;
-    }
+    uint32_t x;
+    asm("{\n\tadd.cc.u32 %1, %1, %1;\n\tmadc.lo.u32 %0, %2, %3, 0xFFFFFFFF;\n\t}" : "=r"(x), "+r"(tt) : "r"(P), "r"(one));
+    M |= P & ~x & ~X;  // pattern flags whose partner differs (one bit per transposed pair member)
+    P &= x;
   }
-  __device__ __forceinline__ void trans_row(uint2 v, uint32_t pm_lane_saddr) {
-    const uint32_t t8 = (uint32_t)(T >> 56);
+  __device__ __forceinline__ void trans_row(uint2 v, uint32_t pm_lane_saddr, uint32_t one) {
+    uint32_t tt = ~(uint32_t)(T >> 32) & 0xFF000000u;
     T <<= 8;
-    trans_step<0, 0>(v.x, t8, pm_lane_saddr);
-    trans_step<1, 1>(v.x, t8, pm_lane_saddr);
-    trans_step<2, 2>(v.x, t8, pm_lane_saddr);
-    trans_step<3, 3>(v.x, t8, pm_lane_saddr);
-    trans_step<0, 4>(v.y, t8, pm_lane_saddr);
-    trans_step<1, 5>(v.y, t8, pm_lane_saddr);
-    trans_step<2, 6>(v.y, t8, pm_lane_saddr);
-    trans_step<3, 7>(v.y, t8, pm_lane_saddr);
+    trans_step<0>(v.x, tt, pm_lane_saddr, one);
+    trans_step<1>(v.x, tt, pm_lane_saddr, one);
+    trans_step<2>(v.x, tt, pm_lane_saddr, one);
+    trans_step<3>(v.x, tt, pm_lane_saddr, one);
+    trans_step<0>(v.y, tt, pm_lane_saddr, one);
+    trans_step<1>(v.y, tt, pm_lane_saddr, one);
+    trans_step<2>(v.y, tt, pm_lane_saddr, one);
+    trans_step<3>(v.y, tt, pm_lane_saddr, one);
   }
 };
 
@@ -1062,7 +1069,7 @@ __global__ void __launch_bounds__(NT) scan_jaro32_kernel(const __grid_constant__
         for (rr = 0; rr < nrows; ++rr) {  // pass 2: transpositions (rows now come from L1/L2)
           const uint2 cur = v;
           if (rr + 1 < nrows) v = __ldg(col + (rr + 1) * 32u);
-          J.trans_row(cur, pm_lane_saddr);
+          J.trans_row(cur, pm_lane_saddr, p.two >> 1);
         }
         jr.transpositions = (uint32_t)__popc(J.M);
         const uint32_t w0 = len2 ? first.x : 0u;
@@ -1081,11 +1088,41 @@ __global__ void __launch_bounds__(NT) scan_jaro32_kernel(const __grid_constant__
           res = finish_float(p.epi, jw);
         }
       } else {
-        res = jaro32_long_fallback(pm_lane, col, p.len1, len2, p.epi);
+        // (truncated) candidates longer than 64 characters: left to jaro32_long_kernel, which runs right after this
+        // kernel and exits at once when no group raised the flag.  A call to the generic routine from here costs the
+        // hot path 16 more registers and spills around the call site (measured: 64 registers + 112 B of stack).
+        if (lane == 0) *p.flag = 1ull;
+        continue;
       }
       if (idx != 0xFFFFFFFFu) reinterpret_cast<double*>(p.out)[idx] = res;
     }
     chunk = __shfl_sync(0xffffffffu, next_chunk, 0);
+  }
+}
+
+// The groups scan_jaro32_kernel skipped: the generic per-lane routine (any candidate length).
+__global__ void __launch_bounds__(256) jaro32_long_kernel(const __grid_constant__ LbParams p) {
+  if (*reinterpret_cast<const volatile unsigned long long*>(p.flag) == 0ull) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* pm = reinterpret_cast<uint32_t*>(smem_raw);
+  {
+    const uint32_t* __restrict__ t = reinterpret_cast<const uint32_t*>(p.tab);
+    for (uint32_t i = threadIdx.x; i < 256u * 32u; i += 256) pm[i] = t[i >> 5];
+  }
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t* __restrict__ pm_lane = pm + lane;
+  const uint2* __restrict__ gdata = reinterpret_cast<const uint2*>(p.lb.gdata);
+  const uint64_t nwarps = (uint64_t)gridDim.x * 8, w0 = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  for (uint64_t g = w0; g < p.lb.ngroups; g += nwarps) {
+    const uint32_t len2 = __ldg(p.lb.lens + g * 32 + lane);
+    const uint32_t idx = __ldg(p.lb.perm + g * 32 + lane);
+    uint32_t l1e = p.len1, l2e = len2, bound = 0;
+    jaro_bounds(l1e, l2e, bound);
+    if (__reduce_max_sync(0xffffffffu, l2e) <= 64) continue;  // scored by the fast kernel
+    const uint2* col = gdata + __ldg(p.lb.goff + g) * 32 + lane;
+    const double res = jaro32_long_fallback(pm_lane, col, p.len1, len2, p.epi);
+    if (idx != 0xFFFFFFFFu) reinterpret_cast<double*>(p.out)[idx] = res;
   }
 }
 
@@ -1109,8 +1146,10 @@ static cudaError_t launch_jaro32(const ScanLaunch& L) {
   p.two = 2;
   p.chunk = 16;  // groups per scheduler grab; 4...128 measured identical (1.99 ms): neither the atomic nor the tail matter
   p.counter = L.lb_counter;
+  p.flag = L.lb_flag;
   p.epi = L.epi;
   e = cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), L.stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(p.flag, 0, sizeof(unsigned long long), L.stream);
   if (e != cudaSuccess) return e;
   uint64_t grid = (uint64_t)L.sm_count * ctas_per_sm;
   const uint64_t nchunks = (L.lb.ngroups + p.chunk - 1) / p.chunk;
@@ -1118,6 +1157,15 @@ static cudaError_t launch_jaro32(const ScanLaunch& L) {
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
   kern<<<(uint32_t)grid, NT, smem, L.stream>>>(p);
+  g_launches.fetch_add(1);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  // groups with candidates beyond 64 characters (none in BASELINE config 4): a no-op launch unless the flag was raised
+  e = cudaFuncSetAttribute(jaro32_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  uint64_t lgrid = (uint64_t)L.sm_count * 2;
+  const uint64_t lneed = (L.lb.ngroups + 7) / 8;
+  if (lgrid > lneed) lgrid = lneed;
+  jaro32_long_kernel<<<(uint32_t)lgrid, 256, smem, L.stream>>>(p);
   g_launches.fetch_add(1);
   return cudaGetLastError();
 }

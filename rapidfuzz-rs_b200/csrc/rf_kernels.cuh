@@ -59,6 +59,7 @@ struct ScanLaunch {
   CorpusView corpus;
   LbView lb;
   unsigned long long* lb_counter;  // 8 bytes of device scratch for the chunk scheduler (one per in-flight launch)
+  unsigned long long* lb_flag;     // 8 more bytes: scan_jaro32_kernel -> jaro32_long_kernel hand-over flag
   QueryView query;
   Epi epi;
   void* out;          // uint32_t[n] or double[n]

@@ -909,7 +909,8 @@ static cudaError_t launch_lb_inst(const ScanLaunch& L, const void* tab) {
 //   LO: 0 = no character of the row is past the window radius (lo stays), 1 = all are (lo shifts every step),
 //       2 = mixed (per-character test);  LENP: the row may extend past this lane's candidate.
 struct Jaro32Dev {
-  uint32_t P, hi, lo, M;
+  uint32_t P, win, M;  // win = the window mask hi & lo of jaro32_rows: both shift by one per character, so
+                       // win' = 2*win + (j < bound) -- one FMA-pipe op, and the match mask is ONE LOP3 (X & win & ~P)
   uint64_t T;
   template <int K>
   __device__ __forceinline__ uint32_t look(uint32_t w, uint32_t pm_lane_saddr) const {
@@ -918,35 +919,37 @@ struct Jaro32Dev {
     asm("ld.shared.u32 %0, [%1];" : "=r"(X) : "r"(addr));
     return X;
   }
+  // rb = max(bound - j0, 0) for the row (LO == 2 only): character K of the row is before the radius iff K < rb
   template <int LO, bool LENP, int K>
-  __device__ __forceinline__ void flag_step(uint32_t w, uint32_t j, uint32_t len2, uint32_t bound, uint32_t pm_lane_saddr,
+  __device__ __forceinline__ void flag_step(uint32_t w, uint32_t j, uint32_t len2, uint32_t rb, uint32_t pm_lane_saddr,
                                             uint32_t two, uint32_t& t8) {
-    const uint32_t X = look<K>(w, pm_lane_saddr);
+    const uint32_t X = look<(K & 3)>(w, pm_lane_saddr);
     uint32_t m;
-    if (LO == 0) asm("lop3.b32 %0, %1, %2, %3, 0x40;" : "=r"(m) : "r"(X), "r"(hi), "r"(P));  // X & hi & ~P in ONE LOP3
-    else m = X & (hi & lo) & ~P;
+    asm("lop3.b32 %0, %1, %2, %3, 0x40;" : "=r"(m) : "r"(X), "r"(win), "r"(P));  // X & win & ~P
     if (LENP) m = (j < len2) ? m : 0u;
     P |= m & (0u - m);
     // row-local text flags, first character in the top bit: t8 = t8 * 2 + (m != 0).  The flag is the carry of
     // m + 0xFFFFFFFF (IADD3) consumed by an IMAD.X -- one ALU-pipe op instead of a predicate-setting LOP3 + SEL.
     asm("{\n\t.reg .u32 d;\n\tadd.cc.u32 d, %1, 0xFFFFFFFF;\n\tmadc.lo.u32 %0, %0, %2, 0;\n\t}" : "+r"(t8) : "r"(m), "r"(two));
-    hi = hi * two + (two >> 1);
-    if (LO == 1) lo = lo * two;
-    if (LO == 2) lo = (j >= bound) ? lo << 1 : lo;
+    if (LO == 0) win = win * two + (two >> 1);
+    if (LO == 1) win = win * two;
+    if (LO == 2)  // carry of rb + (2^32 - 1 - K) is set iff K < rb
+      asm("{\n\t.reg .u32 d;\n\tadd.cc.u32 d, %1, %3;\n\tmadc.lo.u32 %0, %0, %2, 0;\n\t}" : "+r"(win) : "r"(rb), "r"(two), "n"(0xFFFFFFFFu - (uint32_t)K));
   }
   template <int LO, bool LENP>
   __device__ __forceinline__ void flag_row(uint2 v, uint32_t r, uint32_t len2, uint32_t bound, uint32_t pm_lane_saddr,
                                            uint32_t two) {
     uint32_t t8 = 0;
     const uint32_t j0 = r * 8u;
-    flag_step<LO, LENP, 0>(v.x, j0 + 0, len2, bound, pm_lane_saddr, two, t8);
-    flag_step<LO, LENP, 1>(v.x, j0 + 1, len2, bound, pm_lane_saddr, two, t8);
-    flag_step<LO, LENP, 2>(v.x, j0 + 2, len2, bound, pm_lane_saddr, two, t8);
-    flag_step<LO, LENP, 3>(v.x, j0 + 3, len2, bound, pm_lane_saddr, two, t8);
-    flag_step<LO, LENP, 0>(v.y, j0 + 4, len2, bound, pm_lane_saddr, two, t8);
-    flag_step<LO, LENP, 1>(v.y, j0 + 5, len2, bound, pm_lane_saddr, two, t8);
-    flag_step<LO, LENP, 2>(v.y, j0 + 6, len2, bound, pm_lane_saddr, two, t8);
-    flag_step<LO, LENP, 3>(v.y, j0 + 7, len2, bound, pm_lane_saddr, two, t8);
+    const uint32_t rb = bound > j0 ? bound - j0 : 0u;
+    flag_step<LO, LENP, 0>(v.x, j0 + 0, len2, rb, pm_lane_saddr, two, t8);
+    flag_step<LO, LENP, 1>(v.x, j0 + 1, len2, rb, pm_lane_saddr, two, t8);
+    flag_step<LO, LENP, 2>(v.x, j0 + 2, len2, rb, pm_lane_saddr, two, t8);
+    flag_step<LO, LENP, 3>(v.x, j0 + 3, len2, rb, pm_lane_saddr, two, t8);
+    flag_step<LO, LENP, 4>(v.y, j0 + 4, len2, rb, pm_lane_saddr, two, t8);
+    flag_step<LO, LENP, 5>(v.y, j0 + 5, len2, rb, pm_lane_saddr, two, t8);
+    flag_step<LO, LENP, 6>(v.y, j0 + 6, len2, rb, pm_lane_saddr, two, t8);
+    flag_step<LO, LENP, 7>(v.y, j0 + 7, len2, rb, pm_lane_saddr, two, t8);
     T = (T << 8) | t8;  // rows pile up from the bottom byte; align_T() moves row 0 to the top byte
   }
   __device__ __forceinline__ void align_T(uint32_t nrows) { T = nrows ? T << (8u * (8u - nrows)) : 0ull; }
@@ -1002,6 +1005,7 @@ __global__ void __launch_bounds__(NT) scan_jaro32_kernel(const __grid_constant__
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t* __restrict__ pm_lane = pm + lane;
+  const bool zero_ok = pm[0] == 0u;  // PM[0]: no query element is the zero byte
   const uint64_t total_warps = (uint64_t)gridDim.x * (NT / 32);
   const uint64_t ngroups = p.lb.ngroups;
   const uint64_t nchunks = (ngroups + p.chunk - 1) / p.chunk;
@@ -1038,13 +1042,17 @@ __global__ void __launch_bounds__(NT) scan_jaro32_kernel(const __grid_constant__
         const uint32_t pm_lane_saddr = smem_u32(pm_lane);
         const uint32_t nrows = (l2max + 7u) >> 3;
         const uint32_t l2min = __reduce_min_sync(0xffffffffu, l2e);
-        const uint32_t bmin = __reduce_min_sync(0xffffffffu, bound), bmax = __reduce_max_sync(0xffffffffu, bound);
+        // (a radius of 64 or more is never reached here; it also tames the wrapped radius of 1 x 1 / empty / padding lanes)
+        const uint32_t bcl = bound < 64u ? bound : 64u;
+        const uint32_t bmin = __reduce_min_sync(0xffffffffu, bcl), bmax = __reduce_max_sync(0xffffffffu, bcl);
         Jaro32Dev J;
-        J.P = 0; J.M = 0; J.T = 0; J.lo = 0xFFFFFFFFu;
-        J.hi = (bound + 1 < 32) ? ((1u << (bound + 1)) - 1u) : 0xFFFFFFFFu;
+        J.P = 0; J.M = 0; J.T = 0;
+        J.win = (bound + 1 < 32) ? ((1u << (bound + 1)) - 1u) : 0xFFFFFFFFu;
         // pass 1: flags.  The rows fall into at most four warp-uniform segments, each with its own specialised
         // row body: before every lane's window radius, straddling it, past it, and the ragged tail.
-        const uint32_t rF = l2min >> 3;                                      // rows inside every lane's candidate
+        // rows inside every lane's candidate.  The layout pads candidates with zero bytes: when the query holds no zero
+        // byte (PM[0] == 0) a padding character matches nothing, flags nothing and needs no length test at all
+        const uint32_t rF = zero_ok ? nrows : (l2min >> 3);
         const uint32_t rA = (bmin < l2min ? bmin : l2min) >> 3;              // ... and before every lane's radius
         uint32_t rB = (bmax + 7u) >> 3;                                      // first row past every lane's radius
         rB = rB < rF ? rB : rF;

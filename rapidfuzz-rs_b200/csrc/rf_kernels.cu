@@ -2366,6 +2366,7 @@ struct WfParams {
   void* out;
   int out_f64;
   Epi epi;
+  LbView lb;          // wf_lb_kernel
 };
 
 __global__ void __launch_bounds__(128) wf_kernel(const __grid_constant__ WfParams p) {
@@ -2390,8 +2391,58 @@ __global__ void __launch_bounds__(128) wf_kernel(const __grid_constant__ WfParam
   }
 }
 
+// Queries of at most 64 elements over the interleaved layout: warp per group of equal-length candidates, the cost row
+// of every thread in shared memory (thread-strided, 64-bit cells as in the reference's usize arithmetic).
+constexpr int WF_NT = 128;
+__global__ void __launch_bounds__(WF_NT) wf_lb_kernel(const __grid_constant__ WfParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* rows = reinterpret_cast<uint64_t*>(smem_raw);  // [len1 + 1][WF_NT]
+  uint8_t* q = reinterpret_cast<uint8_t*>(rows + (size_t)(p.len1 + 1) * WF_NT);
+  const uint32_t tid = threadIdx.x, lane = tid & 31u;
+  for (uint32_t i = tid; i < p.len1; i += WF_NT) q[i] = p.qbytes[i];
+  __syncthreads();
+  uint64_t* my_row = rows + tid;
+  const uint2* __restrict__ gdata = reinterpret_cast<const uint2*>(p.lb.gdata);
+  const uint64_t nwarps = (uint64_t)gridDim.x * (WF_NT / 32), w0 = (uint64_t)blockIdx.x * (WF_NT / 32) + (tid >> 5);
+  for (uint64_t g = w0; g < p.lb.ngroups; g += nwarps) {
+    const uint32_t len2 = __ldg(p.lb.lens + g * 32 + lane);
+    const uint32_t idx = __ldg(p.lb.perm + g * 32 + lane);
+    if (idx == 0xFFFFFFFFu) continue;
+    const uint8_t* col = reinterpret_cast<const uint8_t*>(gdata + __ldg(p.lb.goff + g) * 32 + lane);
+    const uint64_t raw = weighted_wagner_fischer([&](uint32_t i) -> uint32_t { return q[i]; },
+                                                 [&](uint32_t j) -> uint32_t { return col[(size_t)(j >> 3) * 256 + (j & 7u)]; },
+                                                 p.len1, len2, p.epi.w_ins, p.epi.w_del, p.epi.w_sub,
+                                                 [&](uint32_t i) -> uint64_t& { return my_row[(size_t)i * WF_NT]; });
+    if (p.out_f64) reinterpret_cast<double*>(p.out)[idx] = finish_norm(p.epi, raw, p.len1, len2);
+    else reinterpret_cast<uint32_t*>(p.out)[idx] = finish_int(p.epi, raw, p.len1, len2);
+  }
+}
+
 cudaError_t launch_wf(const ScanLaunch& L) {
   if (L.query.len1 > 2048) return cudaErrorNotSupported;
+  if (L.lb.gdata != nullptr && L.query.len1 <= 64) {
+    WfParams q{};
+    q.qbytes = L.query.qbytes;
+    q.len1 = L.query.len1;
+    q.out = L.out;
+    q.out_f64 = L.out_is_f64;
+    q.epi = L.epi;
+    q.lb = L.lb;
+    const size_t smem = (size_t)(q.len1 + 1) * WF_NT * sizeof(uint64_t) + q.len1 + 16;
+    cudaError_t e = cudaFuncSetAttribute(wf_lb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int ctas_per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, wf_lb_kernel, WF_NT, smem);
+    if (e != cudaSuccess) return e;
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    uint64_t grid = (uint64_t)L.sm_count * ctas_per_sm;
+    const uint64_t need = (L.lb.ngroups + WF_NT / 32 - 1) / (WF_NT / 32);
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    wf_lb_kernel<<<(uint32_t)grid, WF_NT, smem, L.stream>>>(q);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+  }
   WfParams p{};
   p.chars = L.corpus.chars;
   p.off32 = L.corpus.off32;
@@ -2431,7 +2482,11 @@ struct DlParams {
   void* out;
   int out_f64;
   Epi epi;
+  LbView lb;                    // dl_lb_kernel: the interleaved layout
+  unsigned long long* flag;     // dl_lb_kernel raises it for candidates it leaves to dl_kernel (longer than kDlLbMaxLen)
+  int only_long;                // dl_kernel: score only those, and only when the flag is up
 };
+constexpr uint32_t kDlLbMaxLen = 32000;  // 16-bit DP cells
 
 __global__ void dl_init_kernel(int32_t* last_row, uint64_t count) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x) last_row[i] = -1;
@@ -2447,10 +2502,12 @@ __global__ void __launch_bounds__(128) dl_kernel(const __grid_constant__ DlParam
   int32_t* rows = p.scratch + t;
   int32_t* last = p.scratch + (size_t)3 * rowlen * T + t;
   const bool off64 = p.off64 != nullptr;
+  if (p.only_long && *reinterpret_cast<const volatile unsigned long long*>(p.flag) == 0ull) return;
   for (uint64_t c = t; c < p.n; c += T) {
     const uint64_t o0 = off64 ? p.off64[c] : (uint64_t)p.off32[c];
     const uint64_t o1 = off64 ? p.off64[c + 1] : (uint64_t)p.off32[c + 1];
     const uint32_t len2 = (uint32_t)(o1 - o0);
+    if (p.only_long && len2 <= kDlLbMaxLen) continue;
     const uint8_t* txt = p.chars + o0;
     const uint32_t raw = damerau_zhao([&](uint32_t i) -> uint32_t { return txt[i]; }, len2,
                                       [&](uint32_t j) -> uint32_t { return dl_q[j]; }, p.len1,
@@ -2461,9 +2518,81 @@ __global__ void __launch_bounds__(128) dl_kernel(const __grid_constant__ DlParam
   }
 }
 
+// Damerau-Levenshtein for queries of at most 64 elements over the interleaved layout: warp per group of 32 equal-length
+// candidates (no divergence between the lanes' DP loops), the three DP rows and the last-row table of every thread in
+// SHARED memory as 16-bit cells, thread-strided (cell e of thread t at [e * NT + t]: conflict-free).  Only symbols of
+// the query are ever looked up in the last-row table, so it is indexed by the query's symbol ids (at most 64 + one
+// dummy slot for every other symbol) instead of 256 entries.  ~70 KB per 128-thread CTA, 3 CTAs per SM.
+constexpr int DL_NT = 128;
+__global__ void __launch_bounds__(DL_NT) dl_lb_kernel(const __grid_constant__ DlParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const uint32_t len1 = p.len1, rowlen = len1 + 2;
+  int16_t* rows = reinterpret_cast<int16_t*>(smem_raw);              // [3 * rowlen][DL_NT]
+  int16_t* last = rows + (size_t)3 * rowlen * DL_NT;                 // [len1 + 1][DL_NT]
+  uint8_t* qmap = reinterpret_cast<uint8_t*>(last + (size_t)(len1 + 1) * DL_NT);  // [256] symbol -> id (0 = not in the query)
+  uint8_t* q = qmap + 256;                                           // [len1]
+  const uint32_t tid = threadIdx.x, lane = tid & 31u;
+  for (uint32_t i = tid; i < 256; i += DL_NT) qmap[i] = 0;
+  for (uint32_t i = tid; i < len1; i += DL_NT) q[i] = p.qbytes[i];
+  __syncthreads();
+  if (tid == 0) {  // ids in order of first occurrence
+    uint32_t d = 0;
+    for (uint32_t i = 0; i < len1; ++i)
+      if (!qmap[q[i]]) qmap[q[i]] = (uint8_t)++d;
+  }
+  for (uint32_t e = 0; e <= len1; ++e) last[(size_t)e * DL_NT + tid] = -1;
+  __syncthreads();
+  int16_t* my_rows = rows + tid;
+  int16_t* my_last = last + tid;
+  const uint2* __restrict__ gdata = reinterpret_cast<const uint2*>(p.lb.gdata);
+  const uint64_t nwarps = (uint64_t)gridDim.x * (DL_NT / 32), w0 = (uint64_t)blockIdx.x * (DL_NT / 32) + (tid >> 5);
+  for (uint64_t g = w0; g < p.lb.ngroups; g += nwarps) {
+    const uint32_t len2 = __ldg(p.lb.lens + g * 32 + lane);
+    const uint32_t idx = __ldg(p.lb.perm + g * 32 + lane);
+    if (idx == 0xFFFFFFFFu) continue;
+    if (len2 > kDlLbMaxLen) { *p.flag = 1ull; continue; }
+    const uint8_t* col = reinterpret_cast<const uint8_t*>(gdata + __ldg(p.lb.goff + g) * 32 + lane);
+    const uint32_t raw = damerau_zhao([&](uint32_t i) -> uint32_t { return col[(size_t)(i >> 3) * 256 + (i & 7u)]; }, len2,
+                                      [&](uint32_t j) -> uint32_t { return q[j]; }, len1,
+                                      [&](uint32_t k, uint32_t j) -> int16_t& { return my_rows[(k * rowlen + j) * DL_NT]; },
+                                      [&](uint32_t ch) -> int16_t& { return my_last[(uint32_t)qmap[ch] * DL_NT]; });
+    if (p.out_f64) reinterpret_cast<double*>(p.out)[idx] = finish_norm(p.epi, raw, len1, len2);
+    else reinterpret_cast<uint32_t*>(p.out)[idx] = finish_int(p.epi, raw, len1, len2);
+  }
+}
+
 cudaError_t launch_dl(const ScanLaunch& L) {
   if (L.query.len1 > 2048) return cudaErrorNotSupported;
+  const bool use_lb = L.lb.gdata != nullptr && L.query.len1 <= 64 && L.lb_flag != nullptr;
+  if (use_lb) {
+    DlParams q{};
+    q.qbytes = L.query.qbytes;
+    q.len1 = L.query.len1;
+    q.out = L.out;
+    q.out_f64 = L.out_is_f64;
+    q.epi = L.epi;
+    q.lb = L.lb;
+    q.flag = L.lb_flag;
+    const size_t smem = ((size_t)3 * (q.len1 + 2) + q.len1 + 1) * DL_NT * sizeof(int16_t) + 256 + q.len1 + 16;
+    cudaError_t e = cudaFuncSetAttribute(dl_lb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(q.flag, 0, sizeof(unsigned long long), L.stream);
+    if (e != cudaSuccess) return e;
+    int ctas_per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, dl_lb_kernel, DL_NT, smem);
+    if (e != cudaSuccess) return e;
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    uint64_t grid = (uint64_t)L.sm_count * ctas_per_sm;
+    const uint64_t need = (L.lb.ngroups + DL_NT / 32 - 1) / (DL_NT / 32);
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    dl_lb_kernel<<<(uint32_t)grid, DL_NT, smem, L.stream>>>(q);
+    g_launches.fetch_add(1);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
   DlParams p{};
+  p.only_long = use_lb ? 1 : 0;
+  p.flag = L.lb_flag;
   p.chars = L.corpus.chars;
   p.off32 = L.corpus.off32;
   p.off64 = L.corpus.off64;
@@ -2474,7 +2603,7 @@ cudaError_t launch_dl(const ScanLaunch& L) {
   p.out_f64 = L.out_is_f64;
   p.epi = L.epi;
   uint64_t blocks = (p.n + 127) / 128;
-  const uint64_t max_blocks = (uint64_t)L.sm_count * 4;
+  const uint64_t max_blocks = (uint64_t)L.sm_count * (p.only_long ? 1 : 4);  // the rare leftovers: a small grid (scratch!)
   if (blocks > max_blocks) blocks = max_blocks;
   if (blocks < 1) blocks = 1;
   p.T = (uint32_t)blocks * 128u;

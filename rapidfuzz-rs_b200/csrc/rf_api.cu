@@ -561,7 +561,7 @@ static rf_status score_view(const rf_batch* b, const CorpusView& cv, const LbAll
   if (!g.ok) return fail(RF_ERR_CUDA, "cudaSetDevice failed");
   L.corpus = cv;
   const Family fam0 = family_of(L.epi.metric, L.epi.wclass);
-  const bool use_lb = lb && lb->gdata && g_w1_path.load() != 1 && fam0 != F_SIMPLE &&
+  const bool use_lb = lb && lb->gdata && g_w1_path.load() != 1 && (fam0 != F_SIMPLE || L.epi.metric == M_HAMMING) &&
                       ((fam0 != F_DL && fam0 != F_WF) || b->len1 <= 64);  // the two DP kernels: shared-memory rows up to 64
   if (use_lb) {
     L.lb = LbView{lb->perm, lb->lens, lb->goff, lb->gdata, lb->ngroups};

@@ -2286,6 +2286,7 @@ struct SimpleParams {
   int out_f64;
   uint32_t* err_flag;     // set to 1 when Hamming without pad meets a candidate of another length (may be NULL)
   Epi epi;
+  LbView lb;              // hamming_lb_kernel
 };
 
 __global__ void __launch_bounds__(256) simple_kernel(const __grid_constant__ SimpleParams p) {
@@ -2329,7 +2330,70 @@ __global__ void __launch_bounds__(256) simple_kernel(const __grid_constant__ Sim
   }
 }
 
+// Hamming over the interleaved layout: warp per group, every row load is 256 contiguous bytes (the CSR kernel's
+// 16-byte per-thread loads at a 36-byte stride touch every sector several times), four rows in flight per lane.
+__global__ void __launch_bounds__(256) hamming_lb_kernel(const __grid_constant__ SimpleParams p) {
+  extern __shared__ __align__(16) uint32_t simple_q[];
+  const uint32_t qwords = (p.len1 + 3) / 4 + 4;
+  for (uint32_t i = threadIdx.x; i < qwords; i += blockDim.x) simple_q[i] = reinterpret_cast<const uint32_t*>(p.qbytes)[i];
+  __syncthreads();
+  const uint2* q2 = reinterpret_cast<const uint2*>(simple_q);
+  const uint32_t lane = threadIdx.x & 31u, len1 = p.len1;
+  const uint2* __restrict__ gdata = reinterpret_cast<const uint2*>(p.lb.gdata);
+  const uint64_t nwarps = (uint64_t)gridDim.x * 8, w0 = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  auto diff2 = [](uint2 a, uint2 b) -> uint32_t { return differing_bytes(a.x, b.x) + differing_bytes(a.y, b.y); };
+  for (uint64_t g = w0; g < p.lb.ngroups; g += nwarps) {
+    const uint32_t len2 = __ldg(p.lb.lens + g * 32 + lane);
+    const uint32_t idx = __ldg(p.lb.perm + g * 32 + lane);
+    const uint2* col = gdata + __ldg(p.lb.goff + g) * 32 + lane;
+    if (idx == 0xFFFFFFFFu) continue;
+    const uint32_t mn = len1 < len2 ? len1 : len2, mx = len1 < len2 ? len2 : len1;
+    bool none = false;
+    uint32_t dist = mx - mn;  // with pad: the excess counts as mismatches (hamming.rs:156-158)
+    if (!p.epi.pad && len2 != len1) {
+      none = true;
+      if (p.err_flag) atomicOr(p.err_flag, 1u);
+    } else {
+      const uint32_t nfull = mn >> 3;
+      uint32_t r = 0;
+      for (; r + 4 <= nfull; r += 4) {
+        const uint2 a = __ldcs(col + (size_t)r * 32), b = __ldcs(col + (size_t)(r + 1) * 32);
+        const uint2 c = __ldcs(col + (size_t)(r + 2) * 32), d = __ldcs(col + (size_t)(r + 3) * 32);
+        dist += diff2(a, q2[r]) + diff2(b, q2[r + 1]) + diff2(c, q2[r + 2]) + diff2(d, q2[r + 3]);
+      }
+      for (; r < nfull; ++r) dist += diff2(__ldcs(col + (size_t)r * 32), q2[r]);
+      const uint32_t rem = mn & 7u;
+      if (rem) {
+        uint2 v = __ldcs(col + (size_t)r * 32), qv = q2[r];
+        const uint64_t mask = (1ull << (8 * rem)) - 1ull;
+        const uint32_t ml = (uint32_t)mask, mh = (uint32_t)(mask >> 32);
+        dist += differing_bytes(v.x & ml, qv.x & ml) + differing_bytes(v.y & mh, qv.y & mh);
+      }
+    }
+    if (p.out_f64) reinterpret_cast<double*>(p.out)[idx] = none ? qnan() : finish_norm(p.epi, dist, len1, len2);
+    else reinterpret_cast<uint32_t*>(p.out)[idx] = none ? NONE_U32 : finish_int(p.epi, dist, len1, len2);
+  }
+}
+
 cudaError_t launch_simple(const ScanLaunch& L, uint32_t* err_flag) {
+  if (L.lb.gdata != nullptr && L.epi.metric == M_HAMMING) {
+    SimpleParams q{};
+    q.qbytes = L.query.qbytes;
+    q.len1 = L.query.len1;
+    q.out = L.out;
+    q.out_f64 = L.out_is_f64;
+    q.err_flag = err_flag;
+    q.epi = L.epi;
+    q.lb = L.lb;
+    const size_t smem = ((size_t)(q.len1 + 3) / 4 + 4) * 4 + 8;
+    uint64_t blocks = (L.lb.ngroups + 7) / 8;
+    const uint64_t max_blocks = (uint64_t)L.sm_count * 8;
+    if (blocks > max_blocks) blocks = max_blocks;
+    if (blocks < 1) blocks = 1;
+    hamming_lb_kernel<<<(uint32_t)blocks, 256, smem, L.stream>>>(q);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+  }
   SimpleParams p{};
   p.chars = L.corpus.chars;
   p.off32 = L.corpus.off32;

@@ -211,6 +211,13 @@ if __name__ == "__main__":
             one_vs_many("C2-shape " + m + " " + kind, m, kind, 2, 32, int(1e8 * scale), 8, 64, 16, None, False, lambda l: l + 8)
         one_vs_many("C2-shape indel distance (query len 64)", "indel", "distance", 2, 64, int(1e8 * scale), 8, 64, 16, None, False,
                     lambda l: l + 8)
+    if "mw" in which:   # off-config shapes: longer queries without a (small) cutoff, 64-bit-word variants of the other metrics
+        one_vs_many("C3-shape levenshtein, no cutoff", "levenshtein", "distance", 3, 256, int(1e7 * scale), 64, 256, 48, None, False, lambda l: l + 8, steps=5)
+        one_vs_many("C3-shape levenshtein, cutoff 100", "levenshtein", "distance", 3, 256, int(1e7 * scale), 64, 256, 48, 100, False, lambda l: l + 8, steps=5)
+        one_vs_many("C3-shape indel, no cutoff", "indel", "distance", 3, 256, int(1e7 * scale), 64, 256, 48, None, False, lambda l: l + 8, steps=5)
+        one_vs_many("C3-shape jaro_winkler (query 256)", "jaro_winkler", "similarity", 3, 256, int(1e7 * scale), 64, 256, 48, None, True, lambda l: l + 12, steps=3)
+        one_vs_many("C2-shape jaro_winkler (query 48)", "jaro_winkler", "similarity", 2, 48, int(1e8 * scale), 8, 64, 16, None, True, lambda l: l + 12, steps=5)
+        one_vs_many("C2-shape osa (query 48)", "osa", "distance", 2, 48, int(1e8 * scale), 8, 64, 16, None, False, lambda l: l + 8, steps=5)
     if "simple" in which:   # HBM-bound metrics: bytes = len + 4 + 4 per pair
         for m, kind in (("hamming", "distance"), ("prefix", "similarity"), ("postfix", "similarity")):
             q = rf.synth_query(2, 32)

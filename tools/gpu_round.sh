@@ -1,4 +1,8 @@
 #!/bin/bash
+# Dev helper run under gpurun.  Output -> gpurun_out/
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "hamming or golden or simple or prefix or compaction or cpp" > gpurun_out/pytest_ham.log 2>&1; tail -3 gpurun_out/pytest_ham.log
-timeout 600 python tools/bench_configs.py simple > gpurun_out/cfg_simple2.jsonl 2> gpurun_out/cfg_simple2.err; tail -2 gpurun_out/cfg_simple2.err; cut -c1-300 gpurun_out/cfg_simple2.jsonl
+timeout 1500 python -m pytest tests -m gpu -x -q --durations=5 > gpurun_out/pytest_gpu_all.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu_all.log
+tail -10 gpurun_out/pytest_gpu_all.log | cut -c1-200
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/smoke.log; tail -2 gpurun_out/smoke.log
+timeout 900 compute-sanitizer --tool memcheck python tools/sanitize_smoke.py > gpurun_out/san_mem.log 2>&1; tail -3 gpurun_out/san_mem.log
+timeout 900 compute-sanitizer --tool racecheck python tools/sanitize_smoke.py > gpurun_out/san_race.log 2>&1; tail -3 gpurun_out/san_race.log

@@ -63,5 +63,19 @@ b._score("distance", corpus3, rf.Args().score_cutoff(63))
 b._score("distance", corpus3, rf.Args().score_cutoff(100))
 b.stream("distance", c3, o3, rf.Args().score_cutoff(32))
 b.close()
+# DP metrics / Hamming over the interleaved layout, and the hand-over kernels for long candidates
+lens = np.array([0, 1, 9, 40, 64, 70, 200, 33] * 20)
+lens[7] = 33000   # ONE candidate past the 16-bit DP cells (a 33000 x 64 DP under the sanitizer is slow)
+cl = np.random.default_rng(3).integers(97, 101, int(lens.sum())).astype(np.uint8)
+ol = np.zeros(len(lens) + 1, np.uint64); ol[1:] = np.cumsum(lens)
+corpus_l = rf.Corpus(cl, ol)
+for qq in (q, rf.synth_query(2, 64), rf.synth_query(2, 70)):
+    for m, a in (("damerau_levenshtein", None), ("levenshtein", rf.Args().weights(1, 2, 3)), ("hamming", rf.Args().pad(True)),
+                 ("jaro_winkler", None), ("jaro", rf.Args().score_cutoff(0.7))):
+        b = bc(m, qq)
+        b._score("distance", corpus_l, a)
+        b._score("distance", corpus, a)
+        b.close()
+corpus_l.close()
 corpus.close(); corpus3.close()
 print("sanitize smoke done")

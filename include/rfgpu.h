@@ -243,7 +243,12 @@ rf_status rf_synth_corpus_u8(uint64_t seed, const uint8_t* query, uint32_t query
  *   "banded_levenshtein" (default 1): multi-word Levenshtein distance with score_cutoff <= 63 edits uses the
  *        one-thread-per-candidate 64-bit Ukkonen-band kernel; 0 = always the multi-word block kernel;
  *   "stream_chunk_mb" (default 64), "stream_chunk_kcand" (default 2048): chunk size of rf_batch_stream_* in
- *        MiB of candidate bytes / thousands (x1024) of candidates, whichever is hit first. */
+ *        MiB of candidate bytes / thousands (x1024) of candidates, whichever is hit first;
+ *   "compact_u32_corpus" (default 1): rf_corpus_create_u32 renames corpora of at most 255 distinct symbols to
+ *        bytes once at creation (0 = keep u32 elements and rename per scoring call);
+ *   "cdist_slices" (default 0 = automatic, 1..256): corpus slices of rf_cdist_topk_* (work units = slices x queries);
+ *   "cdist_skip" (default 1): rf_cdist_topk_* skips groups whose length alone puts them beyond the running k-th
+ *        distance (0 = score every candidate; for measurements). */
 rf_status rf_set_option(const char* name, int value);
 
 /* kernel launches issued by this library in this process so far (bench.py reports the delta) */

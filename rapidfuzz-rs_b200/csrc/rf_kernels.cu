@@ -451,12 +451,14 @@ __device__ __forceinline__ uint32_t lcs_w1_u64_fast(uint32_t pm_lane_saddr, Rd r
 //   HP<<1|1, HN<<1 = IMAD.WIDE.U32 lo * 2 + {1|0}  (the product's high word is the bit that crosses) ; hi*2 + carry (IMAD)
 // The match table is SPLIT: low words at pm_lo[ch*32 + lane], high words 32 KB further (one IDP.4A address, two LDS).
 constexpr uint32_t kSplitHi = 256u * 32u * 4u;  // byte distance between the low-word and the high-word table
-template <class Rd>
-__device__ __forceinline__ uint32_t lev_w1_u64_fast(uint32_t pm_lane_saddr, Rd rd, uint32_t len2, uint32_t len1, uint32_t two) {
+// OSA = true adds the transposition term of osa.rs:84-135 on the halves (TR = (((~D0_prev) & X) << 1) & X_prev).
+template <bool OSA, class Rd>
+__device__ __forceinline__ uint32_t myers_w1_u64_fast(uint32_t pm_lane_saddr, Rd rd, uint32_t len2, uint32_t len1, uint32_t two) {
   static_assert(Rd::kRow8, "interleaved rows only");
   const uint32_t one = two >> 1;
   const uint64_t vp0 = ~0ull << (64u - len1);
   uint32_t VPl = (uint32_t)vp0, VPh = (uint32_t)(vp0 >> 32), VNl = 0, VNh = 0;
+  uint32_t D0pl = 0, D0ph = 0, Xpl = 0, Xph = 0;  // OSA only: previous column's D0 and match mask
 #define RF_LEV64_STEP(K)                                                                              \
   {                                                                                                   \
     uint32_t Xl, Xh, sl, sh, c;                                                                       \
@@ -466,8 +468,17 @@ __device__ __forceinline__ uint32_t lev_w1_u64_fast(uint32_t pm_lane_saddr, Rd r
     /* 64-bit (X & VP) + VP: IADD3 (carry out) + IMAD.X (VPh * 1 + (Xh & VPh) + carry) */             \
     asm("{\n\tadd.cc.u32 %0, %2, %3;\n\tmadc.lo.u32 %1, %4, %5, %6;\n\t}"                            \
         : "=r"(sl), "=r"(sh) : "r"(Xl & VPl), "r"(VPl), "r"(VPh), "r"(one), "r"(Xh & VPh));           \
-    const uint32_t D0l = ((sl ^ VPl) | Xl) | VNl;                                                     \
-    const uint32_t D0h = ((sh ^ VPh) | Xh) | VNh;                                                     \
+    uint32_t D0l = ((sl ^ VPl) | Xl) | VNl;                                                           \
+    uint32_t D0h = ((sh ^ VPh) | Xh) | VNh;                                                           \
+    if constexpr (OSA) {                                                                              \
+      uint32_t tl = ~D0pl & Xl, th = ~D0ph & Xh, tc;                                                  \
+      asm("{\n\t.reg .b64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}"                \
+          : "=r"(tl), "=r"(tc) : "r"(tl), "r"(two));                                                  \
+      th = th * two + tc;                                                                             \
+      D0l |= tl & Xpl;                                                                                \
+      D0h |= th & Xph;                                                                                \
+      D0pl = D0l; D0ph = D0h; Xpl = Xl; Xph = Xh;                                                     \
+    }                                                                                                 \
     uint32_t HPl = VNl | ~(D0l | VPl), HPh = VNh | ~(D0h | VPh);                                      \
     uint32_t HNl = D0l & VPl, HNh = D0h & VPh;                                                        \
     asm("mul.hi.u32 %0, %1, %2;" : "=r"(c) : "r"(HPl), "r"(two));                                     \
@@ -526,6 +537,10 @@ __device__ __forceinline__ uint32_t lev_w1_u64_fast(uint32_t pm_lane_saddr, Rd r
 #undef RF_LEV64_STEP
   return len2 + (uint32_t)__popc(VPl) + (uint32_t)__popc(VPh) - (uint32_t)__popc(VNl) - (uint32_t)__popc(VNh);
 }
+template <class Rd>
+__device__ __forceinline__ uint32_t lev_w1_u64_fast(uint32_t pm_lane_saddr, Rd rd, uint32_t len2, uint32_t len1, uint32_t two) {
+  return myers_w1_u64_fast<false>(pm_lane_saddr, rd, len2, len1, two);
+}
 
 // One candidate: raw bit-parallel kernel + score algebra.  pm_lane = &pm[lane] of the lane-replicated table.
 // SPLIT64 (F_LEV, 64-bit words, interleaved rows only): pm_lane points into the split low/high table of lev_w1_u64_fast.
@@ -554,6 +569,7 @@ __device__ __forceinline__ void score_one(const W* __restrict__ pm_lane, const S
       else if constexpr (FAM == F_LEV && SPLIT64) raw = lev_w1_u64_fast(smem_u32(pm_lane), src.reader(), len2, len1, two);
       else if constexpr (FAM == F_LEV) raw = lev_w1<W>(tab, src.reader(), len2, len1);
       else if constexpr (FAM == F_OSA && sizeof(W) == 4) raw = myers_w1_u32_fast<true>(smem_u32(pm_lane), src.reader(), len2, len1, two);
+      else if constexpr (FAM == F_OSA && SPLIT64) raw = myers_w1_u64_fast<true>(smem_u32(pm_lane), src.reader(), len2, len1, two);
       else if constexpr (FAM == F_OSA) raw = osa_w1<W>(tab, src.reader(), len2, len1);
       else if constexpr (FAM == F_LCS && sizeof(W) == 4 && decltype(src.reader())::kRow8) raw = lcs_w1_u32_fast(smem_u32(pm_lane), src.reader(), len2, two);
       else if constexpr (FAM == F_LCS && SPLIT64) raw = lcs_w1_u64_fast(smem_u32(pm_lane), src.reader(), len2, two);
@@ -787,7 +803,7 @@ struct LbParams {
 template <int FAM, class W, int NT, bool RAWDIST>
 __global__ void __launch_bounds__(NT) scan_lb_kernel(const __grid_constant__ LbParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr bool SPLIT64 = ((FAM == F_LEV || FAM == F_LCS) && sizeof(W) == 8);  // low / high words in two 32 KB tables (lev_w1_u64_fast, lcs_w1_u64_fast)
+  constexpr bool SPLIT64 = ((FAM == F_LEV || FAM == F_LCS || FAM == F_OSA) && sizeof(W) == 8);  // low / high words in two 32 KB tables (lev_w1_u64_fast, lcs_w1_u64_fast)
   W* pm = reinterpret_cast<W*>(smem_raw);
   {
     const W* __restrict__ t = reinterpret_cast<const W*>(p.tab);
@@ -842,6 +858,7 @@ __global__ void __launch_bounds__(NT) scan_lb_kernel(const __grid_constant__ LbP
         if constexpr (FAM == F_LEV && sizeof(W) == 4) raw = lev_w1_u32_fast(smem_u32(pm_lane), src.reader(), len2, p.len1, p.two);
         else if constexpr (FAM == F_OSA && sizeof(W) == 4) raw = myers_w1_u32_fast<true>(smem_u32(pm_lane), src.reader(), len2, p.len1, p.two);
         else if constexpr (FAM == F_LEV && SPLIT64) raw = lev_w1_u64_fast(smem_u32(pm_lane), src.reader(), len2, p.len1, p.two);
+        else if constexpr (FAM == F_OSA && SPLIT64) raw = myers_w1_u64_fast<true>(smem_u32(pm_lane), src.reader(), len2, p.len1, p.two);
         else {
           auto tab = [&](uint32_t ch) -> W { return pm_lane[ch * 32u]; };
           if constexpr (FAM == F_LEV) raw = lev_w1<W>(tab, src.reader(), len2, p.len1);

@@ -21,6 +21,11 @@
 #else
 #define RF_HD inline
 #endif
+#if defined(__CUDA_ARCH__)
+#define RF_UNROLL _Pragma("unroll")
+#else
+#define RF_UNROLL  // host pass / plain C++ (the CPU tests of this header): gcc does not know the pragma
+#endif
 
 namespace rfk {
 
@@ -112,14 +117,14 @@ struct ByteReader16 {
     const uint32_t W[8] = {cur[0], cur[1], cur[2], cur[3], nxt[0], nxt[1], nxt[2], nxt[3]};
     uint32_t A[6], B[5];
     const bool s2 = (wsel & 2u) != 0, s1 = (wsel & 1u) != 0;
-#pragma unroll
+RF_UNROLL
     for (int i = 0; i < 6; ++i) A[i] = s2 ? W[i + 2] : W[i];
-#pragma unroll
+RF_UNROLL
     for (int i = 0; i < 5; ++i) B[i] = s1 ? A[i + 1] : A[i];
     Bytes16 r;
-#pragma unroll
+RF_UNROLL
     for (int i = 0; i < 4; ++i) r.w[i] = funnel_r(B[i], B[i + 1], sh);
-#pragma unroll
+RF_UNROLL
     for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
     return r;
   }
@@ -488,7 +493,7 @@ RF_HD double jaro_similarity_generic(const PMW& pmw, const Bytes& bytes, uint32_
   constexpr int PW = MAXQ / 64;
   uint64_t P[PW];
   uint8_t matched[MAXQ];
-#pragma unroll
+RF_UNROLL
   for (int i = 0; i < PW; ++i) P[i] = 0;
   const uint32_t words = (len1_orig + 63) / 64;
   uint32_t cc = 0;
@@ -597,7 +602,7 @@ RF_HD Jaro32Result jaro32_rows(const Tab& tab, const Row& row, uint32_t len2, ui
   for (uint32_t r = 0; r < nrows; ++r) {
     const uint2 v = row(r);
     uint32_t t8 = 0;
-#pragma unroll
+RF_UNROLL
     for (int t = 0; t < 8; ++t) {
       const uint32_t j = r * 8u + (uint32_t)t;
       const uint32_t ch = ((t < 4 ? v.x : v.y) >> (8 * (t & 3))) & 0xffu;
@@ -616,7 +621,7 @@ RF_HD Jaro32Result jaro32_rows(const Tab& tab, const Row& row, uint32_t len2, ui
   for (uint32_t r = 0; r < nrows; ++r) {
     const uint2 v = row(r);
     const uint32_t t8 = (uint32_t)(T >> (8 * r)) & 0xffu;
-#pragma unroll
+RF_UNROLL
     for (int t = 0; t < 8; ++t) {
       const uint32_t ch = ((t < 4 ? v.x : v.y) >> (8 * (t & 3))) & 0xffu;
       const uint32_t pbit = P & (0u - P);

@@ -450,7 +450,6 @@ __device__ __forceinline__ uint32_t lcs_w1_u64_fast(uint32_t pm_lane_saddr, Rd r
 //   sum  = IMAD.WIDE.U32 (X&VP).lo * 1 + VP  ;  sum.hi += (X&VP).hi        (IMAD)
 //   HP<<1|1, HN<<1 = IMAD.WIDE.U32 lo * 2 + {1|0}  (the product's high word is the bit that crosses) ; hi*2 + carry (IMAD)
 // The match table is SPLIT: low words at pm_lo[ch*32 + lane], high words 32 KB further (one IDP.4A address, two LDS).
-constexpr uint32_t kSplitHi = 256u * 32u * 4u;  // byte distance between the low-word and the high-word table
 // OSA = true adds the transposition term of osa.rs:84-135 on the halves (TR = (((~D0_prev) & X) << 1) & X_prev).
 template <bool OSA, class Rd>
 __device__ __forceinline__ uint32_t myers_w1_u64_fast(uint32_t pm_lane_saddr, Rd rd, uint32_t len2, uint32_t len1, uint32_t two) {
@@ -802,7 +801,7 @@ struct LbParams {
 // score algebra (a dozen uniform loads and branches on Epi) is compiled out.
 template <int FAM, class W, int NT, bool RAWDIST>
 __global__ void __launch_bounds__(NT) scan_lb_kernel(const __grid_constant__ LbParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr bool SPLIT64 = ((FAM == F_LEV || FAM == F_LCS || FAM == F_OSA) && sizeof(W) == 8);  // low / high words in two 32 KB tables (lev_w1_u64_fast, lcs_w1_u64_fast)
   W* pm = reinterpret_cast<W*>(smem_raw);
   {
@@ -1013,7 +1012,7 @@ __device__ __noinline__ double jaro32_long_fallback(const uint32_t* __restrict__
 
 template <int NT>
 __global__ void __launch_bounds__(NT) scan_jaro32_kernel(const __grid_constant__ LbParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   uint32_t* pm = reinterpret_cast<uint32_t*>(smem_raw);
   {
     const uint32_t* __restrict__ t = reinterpret_cast<const uint32_t*>(p.tab);
@@ -1128,7 +1127,7 @@ __global__ void __launch_bounds__(NT) scan_jaro32_kernel(const __grid_constant__
 // The groups scan_jaro32_kernel skipped: the generic per-lane routine (any candidate length).
 __global__ void __launch_bounds__(256) jaro32_long_kernel(const __grid_constant__ LbParams p) {
   if (*reinterpret_cast<const volatile unsigned long long*>(p.flag) == 0ull) return;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   uint32_t* pm = reinterpret_cast<uint32_t*>(smem_raw);
   {
     const uint32_t* __restrict__ t = reinterpret_cast<const uint32_t*>(p.tab);
@@ -1610,7 +1609,7 @@ struct WarpTopK {
 template <class W, int KR>
 __global__ void __launch_bounds__(CD_NT) cdist_scan_kernel(const __grid_constant__ CdistParams p) {
   constexpr int NW = CD_NT / 32;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   W* pm = reinterpret_cast<W*>(smem_raw);
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw + sizeof(W) * 8192);  // NW * k
   unsigned long long* best = keys + NW * CD_KMAX;                                                  // CD_KMAX
@@ -1737,7 +1736,7 @@ __global__ void __launch_bounds__(CD_NT) cdist_scan_kernel(const __grid_constant
 __global__ void __launch_bounds__(CD_NT) cdist_merge_kernel(const unsigned long long* __restrict__ scratch, uint32_t parts,
                                                             uint32_t k, uint32_t* __restrict__ out_idx,
                                                             uint32_t* __restrict__ out_dist) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);  // parts*k
   unsigned long long* best = keys + (size_t)parts * k;
   unsigned long long* wmin = best + CD_KMAX;
@@ -2476,7 +2475,7 @@ __global__ void __launch_bounds__(128) wf_kernel(const __grid_constant__ WfParam
 // of every thread in shared memory (thread-strided, 64-bit cells as in the reference's usize arithmetic).
 constexpr int WF_NT = 128;
 __global__ void __launch_bounds__(WF_NT) wf_lb_kernel(const __grid_constant__ WfParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* rows = reinterpret_cast<uint64_t*>(smem_raw);  // [len1 + 1][WF_NT]
   uint8_t* q = reinterpret_cast<uint8_t*>(rows + (size_t)(p.len1 + 1) * WF_NT);
   const uint32_t tid = threadIdx.x, lane = tid & 31u;
@@ -2606,7 +2605,7 @@ __global__ void __launch_bounds__(128) dl_kernel(const __grid_constant__ DlParam
 // dummy slot for every other symbol) instead of 256 entries.  ~70 KB per 128-thread CTA, 3 CTAs per SM.
 constexpr int DL_NT = 128;
 __global__ void __launch_bounds__(DL_NT) dl_lb_kernel(const __grid_constant__ DlParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const uint32_t len1 = p.len1, rowlen = len1 + 2;
   int16_t* rows = reinterpret_cast<int16_t*>(smem_raw);              // [3 * rowlen][DL_NT]
   int16_t* last = rows + (size_t)3 * rowlen * DL_NT;                 // [len1 + 1][DL_NT]

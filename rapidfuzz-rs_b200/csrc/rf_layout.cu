@@ -5,7 +5,7 @@
 // inside blocks of LB_BLOCK (so results still scatter into an L2-resident window of the output) and storing
 // each group of 32 equal-length candidates word-interleaved gives both, once, at corpus creation.
 #include <cub/device/device_scan.cuh>
-#include <cub/iterator/transform_input_iterator.cuh>
+#include <thrust/iterator/transform_iterator.h>
 #include <mutex>
 #include <vector>
 #include "rf_kernels.cuh"
@@ -205,7 +205,7 @@ cudaError_t lb_build(const CorpusView& c, cudaStream_t st, LbAlloc* out) {
     LB_TRY(cudaGetLastError());
   }
   {
-    cub::TransformInputIterator<uint64_t, CastU64, const uint32_t*> in(grows, CastU64());
+    auto in = thrust::make_transform_iterator(grows, CastU64());
     LB_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, a.goff, (int64_t)(ngroups + 1), st));
     LB_TRY(dev_alloc(&tmp, tmp_bytes, st));
     LB_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, in, a.goff, (int64_t)(ngroups + 1), st));

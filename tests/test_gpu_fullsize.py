@@ -126,3 +126,42 @@ def test_corpus_beyond_4gib_uses_64bit_offsets():
     exp = orc.batch("levenshtein", "distance", q3, chars[int(offsets[n - m]):], offsets[n - m:] - offsets[n - m], nthreads=0, cutoff=40)
     assert np.array_equal(bd[-m:], exp)
     corpus.close()
+
+
+def test_config5_full_size_corpus_cdist_topk():
+    """config 5's corpus at full size (10^7 candidates len 8-64, ~440 MB of layout: several L2-sized slices) against 2 000
+    queries: the per-query top-10 must be sorted by (distance, index) with distinct indices, every listed distance must
+    be the true distance of that pair (oracle on the listed candidates), no distance may undercut the length bound, the
+    planted near-matches of query 0 lead its list, one slice vs automatic slices must agree on every entry, and five
+    queries are checked against the oracle's top-10 over the WHOLE corpus."""
+    n, nq, k = 10_000_000, 2000, 10
+    qs = [rf.synth_query(5 + i, 32) for i in range(nq)]
+    chars, offsets = rf.synth_corpus(5, qs[0], n, 8, 64, 16)
+    lens = np.diff(offsets.astype(np.int64))
+    corpus = rf.Corpus(chars, offsets)
+    q_chars = np.concatenate(qs)
+    q_off = np.arange(nq + 1, dtype=np.uint64) * 32
+    idx, dist = rf.cdist_topk((q_chars, q_off), corpus, k=k)
+    L = _ffi.lib()
+    _ffi.check(L.rf_set_option(b"cdist_slices", 1))
+    try:
+        idx1, dist1 = rf.cdist_topk((q_chars[: 200 * 32], q_off[:201]), corpus, k=k)
+    finally:
+        _ffi.check(L.rf_set_option(b"cdist_slices", 0))
+    assert np.array_equal(idx1, idx[:200]) and np.array_equal(dist1, dist[:200])
+    key = dist.astype(np.int64) * (1 << 32) + idx.astype(np.int64)
+    assert np.all(key[:, 1:] > key[:, :-1])                                   # sorted by (distance, index), indices distinct
+    assert idx.max() < n
+    assert np.all(dist >= np.abs(lens[idx.astype(np.int64)] - 32))            # d >= |len2 - len1|
+    assert dist[0, 0] == 0 or dist[0, 0] <= 16                                # query 0's planted near-matches
+    for qi in list(range(0, nq, 97)):                                         # listed distances are the true distances
+        sel = idx[qi].astype(np.int64)
+        sub_chars = np.concatenate([chars[int(offsets[j]):int(offsets[j + 1])] for j in sel])
+        sub_off = np.zeros(k + 1, np.uint64)
+        sub_off[1:] = np.cumsum(lens[sel])
+        assert np.array_equal(orc.batch("levenshtein", "distance", qs[qi], sub_chars, sub_off, nthreads=0), dist[qi])
+    for qi in (0, 1, 777, 1500, nq - 1):                                      # complete: the oracle's top-10 over the whole corpus
+        d = orc.batch("levenshtein", "distance", qs[qi], chars, offsets, nthreads=0).astype(np.int64)
+        best = np.sort(d * (1 << 32) + np.arange(n))[:k]
+        assert np.array_equal(idx[qi], (best & 0xFFFFFFFF).astype(np.uint32)) and np.array_equal(dist[qi], (best >> 32).astype(np.uint32))
+    corpus.close()

@@ -1,7 +1,6 @@
 #!/bin/bash
-# Dev helper run under gpurun.  Output -> gpurun_out/
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q --durations=4 > gpurun_out/pytest_gpu_all.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu_all.log
-tail -9 gpurun_out/pytest_gpu_all.log | cut -c1-200
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/smoke.log; tail -2 gpurun_out/smoke.log
-timeout 600 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; tail -2 gpurun_out/bench_final.err; cut -c1-300 gpurun_out/bench_final.json
+RF_CFG_SCALE=0.3 timeout 300 ncu --set full --import-source on --clock-control none -k regex:scan_jaro32 -s 3 -c 1 -f -o gpurun_out/j32 python tools/bench_configs.py c4 > gpurun_out/ncu_j32.log 2>&1
+python tools/ncu_summary.py gpurun_out/j32.ncu-rep > gpurun_out/j32_summary.txt 2>&1; head -24 gpurun_out/j32_summary.txt
+RF_CFG_SCALE=0.1 timeout 300 ncu --set full --import-source on --clock-control none -k regex:cdist_scan -s 1 -c 1 -f -o gpurun_out/cdist python tools/bench_configs.py c5 > gpurun_out/ncu_cdist.log 2>&1
+python tools/ncu_summary.py gpurun_out/cdist.ncu-rep > gpurun_out/cdist_summary.txt 2>&1; head -24 gpurun_out/cdist_summary.txt

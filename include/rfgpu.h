@@ -100,7 +100,11 @@ rf_status rf_corpus_create_device_u8(const uint8_t* d_chars, const uint64_t* d_o
 /* u32 elements (Rust `char`, u32: the reference accepts any HashableChar, details/common.rs:29-37).  Such a
  * corpus is scored by comparators made with rf_batch_create_u32; results are exact (see there).  A corpus whose
  * elements take at most 255 distinct values is renamed to bytes once, here, and then costs and scores like a u8
- * corpus (rf_set_option("compact_u32_corpus", 0) turns that off). */
+ * corpus (rf_set_option("compact_u32_corpus", 0) turns that off).
+ * Other element widths (u16, i8 ... i32, and 64-bit elements whose values fit): the reference compares elements
+ * numerically (HashableChar::hash_char), so widen them to u32 BY VALUE -- zero-extend unsigned types, keep the
+ * two's-complement 32-bit pattern of negative values -- on both the query and the candidate side (what the Python
+ * mirror's widen_elems does); do not mix negative values with unsigned values >= 2^31 in one comparison. */
 rf_status rf_corpus_create_u32(const uint32_t* elems, const uint64_t* offsets, uint64_t n, int device, rf_corpus** out);
 /* Waits for the device to drain first (asynchronous *_device calls may still be reading the corpus). */
 rf_status rf_corpus_destroy(rf_corpus* c);

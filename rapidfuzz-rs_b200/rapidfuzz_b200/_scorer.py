@@ -79,6 +79,28 @@ class Args:
         return r
 
 
+def widen_elems(a):
+    """Integer elements of any width -> what the C ABI takes: uint8 as is, everything else as uint32 holding the VALUE
+    (the reference compares elements numerically -- HashableChar::hash_char, details/common.rs:29-37 -- so a signed -1
+    must not meet an unsigned 255).  Negative values keep their two's-complement 32-bit pattern; the one ambiguity of
+    that encoding (a negative i32 vs a u32 >= 2^31 with the same bits) and values outside [-2^31, 2^32) are rejected
+    per array / not representable: 64-bit elements are accepted when every value fits."""
+    a = np.ascontiguousarray(a)
+    if a.dtype == np.uint8 or a.dtype == np.uint32:
+        return a
+    if a.dtype == np.bool_:
+        return a.astype(np.uint8)
+    if not np.issubdtype(a.dtype, np.integer):
+        raise TypeError("elements must be integers, bytes or str, not %s" % a.dtype)
+    if a.size:
+        lo, hi = int(a.min()), int(a.max())
+        if lo < -(1 << 31) or hi >= (1 << 32):
+            raise NotImplementedError("element values outside [-2^31, 2^32) (64-bit symbols) are not supported")
+        if lo < 0 and hi >= (1 << 31):
+            raise NotImplementedError("negative values and values >= 2^31 in one sequence are ambiguous as 32-bit symbols")
+    return (a.astype(np.int64) & 0xFFFFFFFF).astype(np.uint32)
+
+
 def _as_query(q):
     if isinstance(q, str):
         if any(ord(ch) > 255 for ch in q):   # code points, like Rust's .chars(): u32-element comparator
@@ -86,10 +108,7 @@ def _as_query(q):
         q = q.encode("latin-1")
     if isinstance(q, (bytes, bytearray)):
         return np.frombuffer(bytes(q), dtype=np.uint8)
-    q = np.ascontiguousarray(q)
-    if q.dtype == np.uint32:
-        return q
-    return q.astype(np.uint8)
+    return widen_elems(q)
 
 
 class BatchComparatorBase:
@@ -108,6 +127,9 @@ class BatchComparatorBase:
         self.query = q
 
     def close(self):
+        if getattr(self, "_wide_twin", None) is not None:
+            self._wide_twin.close()
+            self._wide_twin = None
         if getattr(self, "_h", None):
             _ffi.lib().rf_batch_destroy(self._h)
             self._h = None
@@ -135,6 +157,10 @@ class BatchComparatorBase:
                 corpus = Corpus.from_unicode([s2], self.device) if wide else Corpus.from_strings([s2], self.device)
         else:
             corpus = s2
+            if getattr(corpus, "wide", False) and self.query.dtype != np.uint32:   # byte query, u32-element corpus
+                if getattr(self, "_wide_twin", None) is None:
+                    self._wide_twin = type(self)(self.query.astype(np.uint32), self.device)
+                return self._wide_twin._score(kind, corpus, args)
         is_f = bool(_ffi.lib().rf_result_is_float(_ffi.METRICS[self.METRIC], _ffi.KINDS[kind]))
         ca = args._c(is_f)
         n = len(corpus)

@@ -38,7 +38,16 @@ class Corpus:
         _ffi.check(_ffi.lib().rf_corpus_create_u32(elems.ctypes.data, offsets.ctypes.data, len(offsets) - 1, device, C.byref(h)))
         self._h = h
         self.device = device
+        self.wide = True     # needs comparators created from u32 queries (BatchComparatorBase widens a byte query itself)
         return self
+
+    @classmethod
+    def from_elems(cls, elems, offsets, device=0):
+        """Candidates with integer elements of any width (u8 ... i32, 64-bit when the values fit): widened to the C ABI's
+        u8 / u32 by VALUE (see _scorer.widen_elems), so signed and unsigned sequences compare like in the reference."""
+        from ._scorer import widen_elems
+        e = widen_elems(elems)
+        return cls(e, offsets, device) if e.dtype == np.uint8 else cls.from_u32(e, offsets, device)
 
     @classmethod
     def from_unicode(cls, strings, device=0):

@@ -407,6 +407,38 @@ def test_u32_corpus_alphabet_compaction(distinct):
             assert_same(v, results[(0, qi, m)], ("compact == per-query", qi, m))
 
 
+def test_integer_elements_of_other_widths_compare_by_value():
+    """HashableChar covers u8...u64 / i8...i64 (details/common.rs:29-37) and compares numerically: the Python mirror widens
+    every integer array to the ABI's u8 / u32 BY VALUE, so i16 -1 never meets u16 65535 or u8 255, i8 / u16 / i32 sequences
+    score like their value-renamed u32 images, and a byte query works against a wide corpus."""
+    rng = np.random.default_rng(31)
+    vals = np.array([-300, -1, 0, 5, 97, 255, 256, 40000], dtype=np.int64)
+    lens = rng.integers(0, 40, 800)
+    cand = vals[rng.integers(0, len(vals), int(lens.sum()))]
+    off = np.zeros(len(lens) + 1, np.uint64)
+    off[1:] = np.cumsum(lens)
+    q = vals[rng.integers(0, len(vals), 20)]
+    ids = {int(v): i + 1 for i, v in enumerate(vals)}                      # reference semantics == equality of VALUES
+    ren = lambda a: np.array([ids[int(x)] for x in a], dtype=np.uint32)
+    corpus = rf.Corpus.from_elems(cand.astype(np.int32), off)
+    for m, kind in (("levenshtein", "distance"), ("jaro_winkler", "similarity"), ("indel", "normalized_similarity")):
+        exp = orc.batch(m, kind, ren(q), ren(cand), off, nthreads=0)
+        assert_same(gpu_batch(m, kind, q.astype(np.int32), corpus), exp, ("i32", m))
+        assert_same(gpu_batch(m, kind, q.astype(np.int64), corpus), exp, ("i64 values that fit", m))
+    corpus.close()
+    # u16 vs i16: 65535 and -1 share 16 bits but not the value
+    cu = rf.Corpus.from_elems(np.array([65535, 7, 65535], dtype=np.uint16), np.array([0, 3], np.uint64))
+    assert gpu_batch("levenshtein", "distance", np.array([-1, 7, -1], dtype=np.int16), cu)[0] == 2
+    assert gpu_batch("levenshtein", "distance", np.array([65535, 7, 65535], dtype=np.uint16), cu)[0] == 0
+    assert gpu_batch("levenshtein", "distance", np.array([7], dtype=np.uint8), cu)[0] == 2          # byte query, wide corpus
+    cu.close()
+    c8 = rf.Corpus.from_elems(np.array([255, 7], dtype=np.uint8), np.array([0, 2], np.uint64))
+    assert gpu_batch("levenshtein", "distance", np.array([-1, 7], dtype=np.int8), c8)[0] == 1      # i8 -1 is not u8 255
+    c8.close()
+    with pytest.raises(NotImplementedError):
+        rf.Corpus.from_elems(np.array([1 << 40], dtype=np.uint64), np.array([0, 1], np.uint64))
+
+
 def test_u32_host_mirror_and_limits():
     assert rf.distance.levenshtein.distance("Иванко", "Петрунко") == 5            # levenshtein.rs:2164-2169
     assert rf.distance.indel.distance("Иванко", "Петрунко") == 8                  # indel.rs:851-857

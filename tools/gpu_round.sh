@@ -1,3 +1,6 @@
 #!/bin/bash
+# Dev helper run under gpurun.  Output -> gpurun_out/
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "widths or u32 or mirror or golden or compaction" > gpurun_out/pytest_widths.log 2>&1; tail -4 gpurun_out/pytest_widths.log | cut -c1-250
+timeout 900 python -m pytest tests -m gpu -x -q --durations=3 > gpurun_out/pytest_gpu_all.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu_all.log
+tail -7 gpurun_out/pytest_gpu_all.log | cut -c1-200
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/smoke.log; tail -2 gpurun_out/smoke.log

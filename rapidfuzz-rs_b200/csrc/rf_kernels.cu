@@ -222,6 +222,22 @@ __device__ __forceinline__ uint32_t myers_w1_u32_fast(uint32_t pm_lane_saddr, Rd
 #else
 #define RF_LEV32_ADDR(K) addr = __dp4a(w, 0x80u << (8 * (K)), pm_lane_saddr);
 #endif
+  // (HP << 1) | 1.  Default: one LOP3 (HP = VN | ~(D0 | VP)) + one IMAD.  RF_LEV_HP_ARITH (experiment):
+  // VN and ~(D0 | VP) are disjoint and D0 | VP = D0 + VP - HN, so 2 HP + 1 = 2 (VN + HN - D0 - VP) - 1 -- four IMADs, no LOP3.
+#ifdef RF_LEV_HP_ARITH
+  const uint32_t minus1 = one - two;
+#define RF_LEV32_HPHN                                                                \
+    uint32_t HN = D0 & VP;                                                           \
+    const uint32_t b2 = (VP * minus1 + VN) * two + minus1;                           \
+    uint32_t HP = (D0 * minus1 + HN) * two + b2;                                     \
+    HN = HN * two;
+#else
+#define RF_LEV32_HPHN                                                                \
+    uint32_t HP = VN | ~(D0 | VP);                                                   \
+    uint32_t HN = D0 & VP;                                                           \
+    HP = HP * two + one;                                                             \
+    HN = HN * two;
+#endif
 #define RF_LEV32_STEP(K)                                                             \
   {                                                                                  \
     uint32_t addr, X;                                                                \
@@ -233,10 +249,7 @@ __device__ __forceinline__ uint32_t myers_w1_u32_fast(uint32_t pm_lane_saddr, Rd
       D0p = D0;                                                                      \
       Xp = X;                                                                        \
     }                                                                                \
-    uint32_t HP = VN | ~(D0 | VP);                                                   \
-    uint32_t HN = D0 & VP;                                                           \
-    HP = HP * two + one;                                                             \
-    HN = HN * two;                                                                   \
+    RF_LEV32_HPHN                                                                    \
     VP = HN | ~(D0 | HP);                                                            \
     VN = HP & D0;                                                                    \
   }
@@ -323,6 +336,7 @@ __device__ __forceinline__ uint32_t myers_w1_u32_fast(uint32_t pm_lane_saddr, Rd
     }
   }
 #undef RF_LEV32_STEP
+#undef RF_LEV32_HPHN
 #undef RF_LEV32_ADDR
   return len2 + (uint32_t)__popc(VP) - (uint32_t)__popc(VN);
 }

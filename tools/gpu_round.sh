@@ -1,6 +1,5 @@
 #!/bin/bash
 # Dev helper run under gpurun.  Output -> gpurun_out/
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q --durations=3 > gpurun_out/pytest_gpu_all.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu_all.log
-tail -7 gpurun_out/pytest_gpu_all.log | cut -c1-200
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/smoke.log; tail -2 gpurun_out/smoke.log
+RF_LIB_PATH=$PWD/rapidfuzz-rs_b200/lib/librfgpu_hparith.so timeout 120 python bench.py --steps 100 --no-cpu-baseline --e2e-steps 1 > gpurun_out/bench_hparith.json 2> gpurun_out/bench_hparith.err
+python -c "import json;d=json.load(open('gpurun_out/bench_hparith.json'));print('HP-arith variant: ms_per_step', d['ms_per_step'], 'matches oracle sample', d['config']['results_match_oracle_sample'])"

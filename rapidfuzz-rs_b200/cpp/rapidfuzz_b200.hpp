@@ -18,6 +18,7 @@
 #include <stdexcept>
 #include <string>
 #include <string_view>
+#include <type_traits>
 #include <vector>
 
 #include "rfgpu.h"
@@ -33,6 +34,33 @@ inline void check(rf_status s) {
 }
 
 // Packed candidates resident in one GPU's HBM.
+// Integer elements of other widths (the reference takes any HashableChar, details/common.rs:29-37, and compares them
+// numerically): widened to the ABI's u32 BY VALUE -- unsigned types zero-extended, negative values keep their
+// two's-complement 32-bit pattern -- so a signed -1 never meets an unsigned 255 / 65535.  64-bit element types are
+// accepted when every value fits [-2^31, 2^32); a sequence must not mix negative values with values >= 2^31.
+template <class T>
+inline std::vector<uint32_t> widen_elements(const T* elems, size_t count) {
+  static_assert(std::is_integral_v<T>, "elements must be integers");
+  std::vector<uint32_t> out(count);
+  bool neg = false, big = false;
+  for (size_t i = 0; i < count; ++i) {
+    const T v = elems[i];
+    if constexpr (std::is_signed_v<T>) {
+      if (v < 0) {
+        neg = true;
+        if (static_cast<long long>(v) < -(1ll << 31)) throw Error(RF_ERR_UNSUPPORTED, "element below -2^31");
+      }
+    }
+    if constexpr (sizeof(T) > 4) {
+      if (v > 0 && static_cast<unsigned long long>(v) >= (1ull << 32)) throw Error(RF_ERR_UNSUPPORTED, "element of 2^32 or more");
+    }
+    if (v > 0 && static_cast<unsigned long long>(v) >= (1ull << 31)) big = true;
+    out[i] = static_cast<uint32_t>(static_cast<long long>(v));
+  }
+  if (neg && big) throw Error(RF_ERR_UNSUPPORTED, "negative values and values >= 2^31 in one sequence");
+  return out;
+}
+
 class Corpus {
  public:
   Corpus(const uint8_t* chars, const uint64_t* offsets, uint64_t n, int device = 0) {
@@ -53,6 +81,12 @@ class Corpus {
     Corpus c;
     check(rf_corpus_create_u32(elems, offsets, n, device, &c.h_));
     return c;
+  }
+  // integer elements of any other width, widened by value (widen_elements)
+  template <class T>
+  static Corpus from_elements(const T* elems, const uint64_t* offsets, uint64_t n, int device = 0) {
+    const std::vector<uint32_t> w = widen_elements(elems, (size_t)offsets[n]);
+    return from_u32(w.data(), offsets, n, device);
   }
   // corpus file written by rf_corpus_file_write (mmap + upload)
   static Corpus from_file(const std::string& path, int device = 0) {
@@ -165,6 +199,11 @@ struct MetricModule {
     }
     explicit BatchComparator(std::u32string_view query, int device = 0) : device_(device) {  // char / u32 elements
       check(rf_batch_create_u32(M, reinterpret_cast<const uint32_t*>(query.data()), (uint32_t)query.size(), device, &h_));
+    }
+    template <class T, class = std::enable_if_t<std::is_integral_v<T> && !std::is_same_v<T, char> && !std::is_same_v<T, char32_t>>>
+    BatchComparator(const T* query, size_t len, int device = 0) : device_(device) {  // other integer widths, by value
+      const std::vector<uint32_t> w = widen_elements(query, len);
+      check(rf_batch_create_u32(M, w.data(), (uint32_t)w.size(), device, &h_));
     }
     BatchComparator(BatchComparator&& o) noexcept : h_(o.h_), device_(o.device_) { o.h_ = nullptr; }
     BatchComparator(const BatchComparator&) = delete;

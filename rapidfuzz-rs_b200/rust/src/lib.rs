@@ -137,6 +137,40 @@ impl Corpus {
 }
 impl Drop for Corpus { fn drop(&mut self) { unsafe { rf_corpus_destroy(self.h); } } }
 
+/// Many-vs-many (new on this side): for every query the `k` best candidates of `corpus` by (Levenshtein distance, index);
+/// rows with fewer than `k` hits are shorter.  Queries of at most 64 bytes.
+pub fn cdist_topk<I, S>(queries: I, corpus: &Corpus, k: u32, score_cutoff: Option<u64>) -> Vec<Vec<(u32, u32)>>
+where I: IntoIterator<Item = S>, S: AsRef<[u8]> {
+    let mut chars = Vec::new();
+    let mut offsets = vec![0u64];
+    for q in queries { chars.extend_from_slice(q.as_ref()); offsets.push(chars.len() as u64); }
+    let nq = offsets.len() - 1;
+    let mut a: rf_args = unsafe { std::mem::zeroed() };
+    unsafe { rf_args_default(&mut a) };
+    if let Some(c) = score_cutoff { a.has_cutoff = 1; a.cutoff_u = c; }
+    let mut idx = vec![u32::MAX; nq * k as usize];
+    let mut dist = vec![u32::MAX; nq * k as usize];
+    check(unsafe { rf_cdist_topk_u8(chars.as_ptr(), offsets.as_ptr(), nq as u32, corpus.h, &a, k, idx.as_mut_ptr(), dist.as_mut_ptr()) });
+    (0..nq).map(|q| (0..k as usize).map(|i| (idx[q * k as usize + i], dist[q * k as usize + i]))
+                                   .take_while(|&(i, _)| i != u32::MAX).collect()).collect()
+}
+
+/// Elements of the other `HashableChar` integer types (src/details/common.rs:29-37) widened to the ABI's u32 BY VALUE
+/// (the reference compares elements numerically): unsigned types zero-extend, negative values keep their
+/// two's-complement 32-bit pattern.  `None` when a value does not fit or the sequence would be ambiguous.
+pub fn widen_elements<T: Copy + Into<i128>>(elems: &[T]) -> Option<Vec<u32>> {
+    let (mut neg, mut big) = (false, false);
+    let mut out = Vec::with_capacity(elems.len());
+    for &e in elems {
+        let v: i128 = e.into();
+        if v < -(1i128 << 31) || v >= (1i128 << 32) { return None; }
+        neg |= v < 0;
+        big |= v >= (1i128 << 31);
+        out.push((v as i64) as u32);
+    }
+    if neg && big { None } else { Some(out) }
+}
+
 /// `NoScoreCutoff` / `WithScoreCutoff<T>` exactly as in src/common.rs:4-86: the cutoff type picks the output type.
 #[derive(Default, Copy, Clone)] pub struct NoScoreCutoff;
 #[derive(Default, Copy, Clone)] pub struct WithScoreCutoff<T>(pub T);

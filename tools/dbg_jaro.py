@@ -1,3 +1,5 @@
+"""Dev helper: Jaro similarity of short queries against mixed-length groups (incl. padding lanes) vs the oracle, with a
+per-length breakdown of the mismatches -- found the wrapped-radius bug of the segment bounds (run under gpurun)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "rapidfuzz-rs_b200")); sys.path.insert(0, os.path.join(ROOT, "tests"))

@@ -131,8 +131,9 @@ def cpu_oracle_rate(n_sample, threads, reps=1):
     """Times the CPU oracle (port of the reference path) on the first n_sample candidates of the workload."""
     from oracle import oracle as orc
     import rapidfuzz_b200 as rf
-    q = rf.synth_query(SEED, QUERY_LEN)
-    chars, offsets = rf.synth_corpus(SEED, q, n_sample, MIN_LEN, MAX_LEN, KMAX)
+    import synth
+    q = synth.synth_query(SEED, QUERY_LEN)
+    chars, offsets = synth.synth_corpus(SEED, q, n_sample, MIN_LEN, MAX_LEN, KMAX)
     orc.batch("levenshtein", "distance", q, chars[: int(offsets[1000])], offsets[:1001], nthreads=threads)  # warm
     best = None
     for _ in range(reps):
@@ -151,10 +152,11 @@ def run_reference(args):
         return
     from oracle import oracle as orc
     import rapidfuzz_b200 as rf
+    import synth
     threads = host_threads()
     n_sample = min(args.n, 4_000_000 * max(1, min(threads, 16)))
-    q = rf.synth_query(SEED, QUERY_LEN)
-    chars, offsets = rf.synth_corpus(SEED, q, n_sample, MIN_LEN, MAX_LEN, KMAX)
+    q = synth.synth_query(SEED, QUERY_LEN)
+    chars, offsets = synth.synth_corpus(SEED, q, n_sample, MIN_LEN, MAX_LEN, KMAX)
     for _ in range(args.warmup):
         orc.batch("levenshtein", "distance", q, chars, offsets, nthreads=threads)
     t0 = time.perf_counter()
@@ -193,6 +195,7 @@ def main():
 
     import torch
     import rapidfuzz_b200 as rf
+    import synth
     from rapidfuzz_b200 import _ffi
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
@@ -208,9 +211,9 @@ def main():
     gen_threads = max(1, host_threads() // world)
 
     # ---- synthetic shard of this rank, generated into pinned host memory
-    q = rf.synth_query(SEED, QUERY_LEN)
+    q = synth.synth_query(SEED, QUERY_LEN)
     t_gen = time.perf_counter()
-    chars, offsets64 = rf.synth_corpus(SEED + 7919 * rank, q, n, MIN_LEN, MAX_LEN, KMAX, nthreads=gen_threads, pinned=True)
+    chars, offsets64 = synth.synth_corpus(SEED + 7919 * rank, q, n, MIN_LEN, MAX_LEN, KMAX, nthreads=gen_threads, pinned=True)
     total = int(offsets64[n])
     assert total < 2**32 - 16
     off32_t = torch.empty(n + 1, dtype=torch.int32).pin_memory()

@@ -224,15 +224,6 @@ const void* rf_corpus_file_offsets(const rf_corpus_file* f);
 const uint8_t* rf_corpus_file_chars(const rf_corpus_file* f);
 rf_status rf_corpus_create_from_file(const char* path, int device, rf_corpus** out);
 
-/* ---- synthetic workload generator (SplitMix64, 62-symbol alphanumeric ASCII,
- * lengths uniform in [min_len,max_len], 1/64 of the candidates = query with <= kmax random edits).
- * Host-side utility used by bench.py and the tests; writes offsets[n+1] and, if chars != NULL, the bytes.
- * Call once with chars == NULL to size the buffer (offsets[n] = total). */
-rf_status rf_synth_query_u8(uint64_t seed, uint32_t len, uint8_t* out);
-rf_status rf_synth_corpus_u8(uint64_t seed, const uint8_t* query, uint32_t query_len, uint64_t n,
-                             uint32_t min_len, uint32_t max_len, uint32_t kmax, uint64_t* offsets,
-                             uint8_t* chars, int nthreads);
-
 /* tuning knobs (process-wide):
  *   "build_interleaved_layout" (default 1): corpora created afterwards also keep the length-bucketed,
  *        warp-interleaved copy that the fastest single-word kernel reads (about +1.2x corpus memory);

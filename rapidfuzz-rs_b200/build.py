@@ -10,7 +10,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "librfgpu.so")
 NVCC = os.environ.get("RF_NVCC", "/usr/local/cuda/bin/nvcc")
 HOSTCXX = os.environ.get("RF_HOSTCXX", "/usr/bin/g++")
-SOURCES = ["rf_kernels.cu", "rf_layout.cu", "rf_select.cu", "rf_api.cu", "rf_synth.cpp", "rf_io.cpp"]
+SOURCES = ["rf_kernels.cu", "rf_layout.cu", "rf_select.cu", "rf_api.cu", "rf_io.cpp"]
 HEADERS = ["rf_core.cuh", "rf_kernels.cuh", os.path.join("..", "..", "include", "rfgpu.h")]
 
 

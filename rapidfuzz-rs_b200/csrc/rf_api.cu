@@ -183,10 +183,50 @@ __global__ void fill_tail_u32(uint32_t* p, uint64_t from, uint32_t v) { p[from +
 __global__ void fill_tail_u64(uint64_t* p, uint64_t from, uint64_t v) { p[from + threadIdx.x] = v; }
 __global__ void narrow_offsets(const uint64_t* __restrict__ in, uint32_t* __restrict__ out, uint64_t n1) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n1; i += (uint64_t)gridDim.x * blockDim.x)
-    out[i] = (uint32_t)in[i];
+    out[i] = in[i] > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)in[i];  // saturate: check_offsets then rejects it (> total)
+}
+
+// CSR sanity: starts must be non-decreasing and end at `total`.  A corrupt / crafted offset array would otherwise send
+// the layout builder and the scan kernels out of bounds (sticky CUDA error = the whole process poisoned).
+__global__ void check_offsets_kernel(const uint32_t* __restrict__ o32, const uint64_t* __restrict__ o64, uint64_t n,
+                                     uint64_t total, uint32_t* __restrict__ bad) {
+  uint32_t b = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t a = o64 ? o64[i] : (uint64_t)o32[i], z = o64 ? o64[i + 1] : (uint64_t)o32[i + 1];
+    if (z < a || z > total) b = 1;
+  }
+  if (__any_sync(0xffffffffu, b) && (threadIdx.x & 31u) == 0) atomicOr(bad, 1u);
+}
+
+// synchronises `st`; RF_ERR_INVALID_ARG when the offsets are not a valid CSR index of `total` elements
+static rf_status check_offsets(const void* d_off, bool is64, uint64_t n, uint64_t total, cudaStream_t st) {
+  if (n == 0) return RF_OK;
+  uint32_t* d_bad = nullptr;
+  RF_CUDA(dev_alloc(&d_bad, 16, st));
+  cudaError_t e = cudaMemsetAsync(d_bad, 0, 16, st);
+  uint32_t bad = 0;
+  if (e == cudaSuccess) {
+    const uint64_t blocks = (n + 255) / 256;
+    const uint32_t grid = (uint32_t)(blocks < 148 * 16 ? blocks : 148 * 16);
+    check_offsets_kernel<<<grid, 256, 0, st>>>(is64 ? nullptr : (const uint32_t*)d_off, is64 ? (const uint64_t*)d_off : nullptr, n,
+                                               total, d_bad);
+    rfk::count_launches(1);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  dev_free(d_bad, st);
+  if (e != cudaSuccess) return cuda_fail(e, "offset validation");
+  if (bad) return fail(RF_ERR_INVALID_ARG, "offsets are not non-decreasing CSR starts ending at offsets[n]");
+  return RF_OK;
 }
 
 static rf_status corpus_finish(rf_corpus* c, cudaStream_t st) {
+  {
+    rf_status vs = check_offsets(c->d_off32 ? (const void*)c->d_off32 : (const void*)c->d_off64, c->d_off32 == nullptr, c->n,
+                                 c->total, st);
+    if (vs != RF_OK) return vs;
+  }
   if (c->d_off32) fill_tail_u32<<<1, 16, 0, st>>>(c->d_off32, c->n + 1, (uint32_t)c->total);
   else fill_tail_u64<<<1, 16, 0, st>>>(c->d_off64, c->n + 1, c->total);
   RF_CUDA(cudaGetLastError());
@@ -339,6 +379,10 @@ rf_status rf_corpus_create_u32(const uint32_t* elems, const uint64_t* offsets, u
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   dev_free(tmp64, st);
   if (e != cudaSuccess) { rf_corpus_destroy(c); return cuda_fail(e, "u32 corpus upload"); }
+  {
+    rf_status vs = check_offsets(off64 ? (const void*)c->d_off64 : (const void*)c->d_off32, off64, n, total, st);
+    if (vs != RF_OK) { rf_corpus_destroy(c); return vs; }
+  }
   if (g_compact32.load() && total) {
     rf_status s = compact_u32_corpus(c, st);
     if (s != RF_OK) { rf_corpus_destroy(c); return s; }
@@ -750,10 +794,9 @@ static const rf_batch* compact_sub(const rf_batch* b, const rf_corpus* c) {
   }
   rf_batch* sub = nullptr;
   if (batch_create_bytes(b->metric, renamed.data(), (uint32_t)renamed.size(), b->device, &sub) != RF_OK) return nullptr;
-  if (b->subs.size() >= 64) {  // bound the cache: comparators are cheap to rebuild
-    for (auto& kv : b->subs) rf_batch_destroy(kv.second);
-    b->subs.clear();
-  }
+  // Never evicted while the parent lives: a concurrent (or still enqueued, asynchronous) scoring call on the same
+  // rf_batch may be using any cached entry.  One entry per distinct compact corpus ever scored (~100 KB of device
+  // memory each); all are released by rf_batch_destroy.
   b->subs.emplace(c->dict_serial, sub);
   return sub;
 }
@@ -964,6 +1007,7 @@ constexpr int kSlots = 3;
 struct StreamSlot {
   cudaStream_t st = nullptr;
   uint8_t* d_chars = nullptr;
+  uint8_t* d_renamed = nullptr;  // u32-query comparators: the chunk renamed to the query's byte alphabet (lazily allocated)
   void* d_offs = nullptr;
   void* d_out = nullptr;
 };
@@ -986,6 +1030,7 @@ StreamCtx* stream_ctx(int device) {
 void stream_ctx_release(StreamCtx* x) {
   for (auto& s : x->slot) {
     if (s.d_chars) cudaFree(s.d_chars);
+    if (s.d_renamed) cudaFree(s.d_renamed);
     if (s.d_offs) cudaFree(s.d_offs);
     if (s.d_out) cudaFree(s.d_out);
     if (s.st) cudaStreamDestroy(s.st);
@@ -1059,8 +1104,23 @@ rf_status stream_impl(const rf_batch* b, const uint8_t* chars, const OffT* offse
     if (B1 > B0) e = cudaMemcpyAsync(sl.d_chars, chars + B0, B1 - B0, cudaMemcpyHostToDevice, sl.st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(sl.d_offs, offsets + i0, (cn + 1) * osz, cudaMemcpyHostToDevice, sl.st);
     if (e != cudaSuccess) { s = cuda_fail(e, "chunk upload"); break; }
+    const uint8_t* d_src = sl.d_chars;
+    if (b->wide && B1 > B0) {
+      // comparator made by rf_batch_create_u32: its tables are over renamed bytes 1..D, so the candidates' bytes go
+      // through the same renaming first (exactly what score_device does for a resident corpus)
+      if (!sl.d_renamed) {
+        if ((e = cudaMalloc(&sl.d_renamed, cap_bytes + 256)) == cudaSuccess) e = cudaMemsetAsync(sl.d_renamed, 0, cap_bytes + 256, sl.st);
+        if (e != cudaSuccess) { s = cuda_fail(e, "streaming buffers"); break; }
+      }
+      const uint64_t cb = B1 - B0, blocks = ((cb + 3) / 4 + 255) / 256;
+      const uint32_t grid = (uint32_t)(blocks < 148 * 16 ? blocks : 148 * 16);
+      remap_kernel<uint8_t><<<grid, 256, 0, sl.st>>>(sl.d_chars, cb, b->d_alpha_keys, b->d_alpha_codes, (uint32_t*)sl.d_renamed);
+      rfk::count_launches(1);
+      if ((e = cudaGetLastError()) != cudaSuccess) { s = cuda_fail(e, "alphabet renaming"); break; }
+      d_src = sl.d_renamed;
+    }
     // the kernels index chars with the caller's absolute offsets: hand them the slot shifted back by B0
-    CorpusView cv{sl.d_chars - B0, osz == 4 ? (const uint32_t*)sl.d_offs : nullptr,
+    CorpusView cv{d_src - B0, osz == 4 ? (const uint32_t*)sl.d_offs : nullptr,
                   osz == 8 ? (const uint64_t*)sl.d_offs : nullptr, cn, B1 - (uint64_t)offsets[i0]};
     s = score_view(b, cv, nullptr, b->device, kind, args, sl.d_out, want_f64, sl.st);
     if (s != RF_OK) break;
@@ -1102,6 +1162,8 @@ static rf_status cdist_impl(const uint8_t* q_chars, const uint64_t* q_offsets, u
                             const rf_args* args, uint32_t k, uint32_t* idx_out, uint32_t* dist_out, bool out_on_device,
                             cudaStream_t user_stream) {
   if (!c) return fail(RF_ERR_INVALID_ARG, "NULL corpus");
+  if (c->d_elems32 || c->compact32)
+    return fail(RF_ERR_UNSUPPORTED, "rf_cdist_topk_u8 needs a u8 corpus (this one was made by rf_corpus_create_u32; use rf_cdist_topk_u32)");
   if (nq == 0) return RF_OK;
   if (!q_offsets || !idx_out || !dist_out) return fail(RF_ERR_INVALID_ARG, "NULL argument");
   if (k == 0 || k > 64) return fail(RF_ERR_INVALID_ARG, "k must be in 1..64");

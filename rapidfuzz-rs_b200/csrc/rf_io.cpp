@@ -160,6 +160,25 @@ rf_status rf_corpus_file_open(const char* path, rf_corpus_file** out) {
     rf_corpus_file_close(cf);
     return io_fail(RF_ERR_INVALID_ARG, "corpus file: offsets do not match the header");
   }
+  // full integrity check of the CSR index (parallel; one pass over the offsets): the mapping is handed to the scan
+  // kernels as is by rf_batch_stream_*, and a decreasing or out-of-range start would send them out of bounds
+  {
+    const uint64_t n = h->n, total = h->total;
+    int bad = 0;
+    if (h->offset_width == 4) {
+      const uint32_t* o = (const uint32_t*)cf->offsets;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+      for (int64_t i = 0; i < (int64_t)n; ++i) bad |= (o[i + 1] < o[i]) | ((uint64_t)o[i + 1] > total);
+    } else {
+      const uint64_t* o = (const uint64_t*)cf->offsets;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+      for (int64_t i = 0; i < (int64_t)n; ++i) bad |= (o[i + 1] < o[i]) | (o[i + 1] > total);
+    }
+    if (bad) {
+      rf_corpus_file_close(cf);
+      return io_fail(RF_ERR_INVALID_ARG, "corpus file: offsets are not non-decreasing CSR starts");
+    }
+  }
   madvise(map, (size_t)st.st_size, MADV_SEQUENTIAL);
   *out = cf;
   return RF_OK;

@@ -81,8 +81,6 @@ SYMBOLS = {
     "rf_corpus_file_offsets": (_vp, [_vp]),
     "rf_corpus_file_chars": (_vp, [_vp]),
     "rf_corpus_create_from_file": (_int, [C.c_char_p, _int, C.POINTER(_vp)]),
-    "rf_synth_query_u8": (_int, [_u64, _u32, _vp]),
-    "rf_synth_corpus_u8": (_int, [_u64, _vp, _u32, _u64, _u32, _u32, _u32, _vp, _vp, _int]),
     "rf_kernel_launch_count": (_u64, []),
     "rf_set_option": (_int, [C.c_char_p, _int]),
 }

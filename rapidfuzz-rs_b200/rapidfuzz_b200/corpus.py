@@ -161,35 +161,6 @@ class CorpusFile:
         self.close()
 
 
-def synth_query(seed, length):
-    out = np.empty(length, dtype=np.uint8)
-    _ffi.check(_ffi.lib().rf_synth_query_u8(seed, length, out.ctypes.data))
-    return out
-
-
-def synth_corpus(seed, query, n, min_len, max_len, kmax, nthreads=0, pinned=False):
-    """Deterministic synthetic candidates. Returns (chars u8, offsets u64)."""
-    query = np.ascontiguousarray(query, dtype=np.uint8)
-    l = _ffi.lib()
-    if pinned:
-        import torch
-        offsets_t = torch.empty(n + 1, dtype=torch.int64).pin_memory()
-        offsets = offsets_t.numpy().view(np.uint64)
-    else:
-        offsets = np.empty(n + 1, dtype=np.uint64)
-    _ffi.check(l.rf_synth_corpus_u8(seed, query.ctypes.data, len(query), n, min_len, max_len, kmax,
-                                    offsets.ctypes.data, None, nthreads))
-    total = int(offsets[n])
-    if pinned:
-        chars_t = torch.empty(max(total, 1), dtype=torch.uint8).pin_memory()
-        chars = chars_t.numpy()[:total]
-    else:
-        chars = np.empty(total, dtype=np.uint8)
-    _ffi.check(l.rf_synth_corpus_u8(seed, query.ctypes.data, len(query), n, min_len, max_len, kmax,
-                                    offsets.ctypes.data, chars.ctypes.data, nthreads))
-    return chars, offsets
-
-
 def cdist_topk(queries, corpus, k=10, score_cutoff=None):
     """Many-vs-many Levenshtein: for every query the k best candidates of `corpus` by (distance, index).
     New on this side (the reference has no cdist).  queries: list of bytes/str, or (chars u8, offsets u64).

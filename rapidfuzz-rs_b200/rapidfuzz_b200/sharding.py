@@ -57,20 +57,18 @@ def all_gather_scores(local_scores, group=None):
 
 def merge_topk(idx_parts, dist_parts, shard_starts, k):
     """Merge per-shard top-k lists ([nq,k] each, shard-local indices, 0xFFFFFFFF padding) into the global
-    top-k by (distance, global index)."""
-    NONE = np.uint64(0xFFFFFFFF)
-    keys = []
+    top-k by (distance, global index).  Returns (idx uint64 [nq,k] GLOBAL indices, UINT64_MAX = none; dist uint32,
+    0xFFFFFFFF = none) -- the same contract as rf_topk_merge_device, valid for sharded corpora of 2^32 candidates and more."""
+    NONE32, NONE64 = np.uint32(0xFFFFFFFF), np.uint64(0xFFFFFFFFFFFFFFFF)
+    gi, gd = [], []
     for idx, dist, lo in zip(idx_parts, dist_parts, shard_starts):
-        idx = np.asarray(idx).astype(np.uint64)
-        dist = np.asarray(dist).astype(np.uint64)
-        valid = idx != NONE
-        key = (dist << np.uint64(32)) | (idx + np.uint64(lo))
-        keys.append(np.where(valid, key, np.uint64(0xFFFFFFFFFFFFFFFF)))
-    allk = np.sort(np.concatenate(keys, axis=1), axis=1)[:, :k]
-    none = allk == np.uint64(0xFFFFFFFFFFFFFFFF)
-    out_idx = np.where(none, NONE, allk & NONE).astype(np.uint32)
-    out_dist = np.where(none, NONE, allk >> np.uint64(32)).astype(np.uint32)
-    return out_idx, out_dist
+        idx = np.asarray(idx).astype(np.uint32)
+        valid = idx != NONE32
+        gi.append(np.where(valid, idx.astype(np.uint64) + np.uint64(lo), NONE64))
+        gd.append(np.where(valid, np.asarray(dist).astype(np.uint32), NONE32))
+    gi, gd = np.concatenate(gi, axis=1), np.concatenate(gd, axis=1)
+    order = np.lexsort((gi, gd), axis=1)[:, :k]      # primary key distance, ties by global index; padding sorts last
+    return np.take_along_axis(gi, order, axis=1), np.take_along_axis(gd, order, axis=1)
 
 
 def cdist_topk_device(q_chars, q_offsets, corpus, k=10, score_cutoff=None, device=None):

@@ -3,13 +3,15 @@
 // (rapidfuzz-benches/benches/bench_levenshtein.rs:8-14), candidate lengths uniform in [min_len, max_len],
 // and 1/64 of the candidates planted as the query with k ~ U[0,kmax] random edits so that cutoff
 // configurations have non-trivial hits.  Host code only (OpenMP); used by bench.py and the tests.
+// NOT part of the product: its own tiny library (synth/librfsynth.so), so that the CPU reference arm of bench.py
+// never maps librfgpu.so.
 #include <stdint.h>
 #include <string.h>
 #include <vector>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
-#include "../../include/rfgpu.h"
+#include "rfsynth.h"
 
 static const char ALPHA[63] = "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789";
 
@@ -47,15 +49,15 @@ static uint32_t planted(uint64_t seed, uint64_t i, const uint8_t* q, uint32_t ql
 
 extern "C" {
 
-rf_status rf_synth_query_u8(uint64_t seed, uint32_t len, uint8_t* out) {
-  if (len && !out) return RF_ERR_INVALID_ARG;
+int rf_synth_query_u8(uint64_t seed, uint32_t len, uint8_t* out) {
+  if (len && !out) return 1;
   for (uint32_t j = 0; j < len; ++j) out[j] = alpha_of(rnd(seed ^ 0x51554552ull /* "QUER" */, 0, j) & 0xff);
-  return RF_OK;
+  return 0;
 }
 
-rf_status rf_synth_corpus_u8(uint64_t seed, const uint8_t* query, uint32_t query_len, uint64_t n, uint32_t min_len,
+int rf_synth_corpus_u8(uint64_t seed, const uint8_t* query, uint32_t query_len, uint64_t n, uint32_t min_len,
                              uint32_t max_len, uint32_t kmax, uint64_t* offsets, uint8_t* chars, int nthreads) {
-  if (!offsets || max_len < min_len || (query_len && !query)) return RF_ERR_INVALID_ARG;
+  if (!offsets || max_len < min_len || (query_len && !query)) return 1;
 #ifdef _OPENMP
   if (nthreads <= 0) nthreads = omp_get_max_threads();
 #else
@@ -78,7 +80,7 @@ rf_status rf_synth_corpus_u8(uint64_t seed, const uint8_t* query, uint32_t query
     }
     uint64_t acc = 0;
     for (uint64_t i = 0; i < n; ++i) { acc += offsets[i + 1]; offsets[i + 1] = acc; }
-    return RF_OK;
+    return 0;
   }
   // pass 2: bytes (offsets must come from pass 1)
 #pragma omp parallel num_threads(nthreads)
@@ -99,7 +101,7 @@ rf_status rf_synth_corpus_u8(uint64_t seed, const uint8_t* query, uint32_t query
       }
     }
   }
-  return RF_OK;
+  return 0;
 }
 
 }  // extern "C"

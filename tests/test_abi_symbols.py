@@ -8,6 +8,7 @@ import re
 import numpy as np
 
 import rapidfuzz_b200 as rf
+import synth
 from rapidfuzz_b200 import _ffi
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -61,14 +62,14 @@ def test_product_never_imports_oracle():
 
 
 def test_synth_is_deterministic_and_shaped():
-    q = rf.synth_query(2, 32)
-    assert bytes(q) == bytes(rf.synth_query(2, 32)) and len(q) == 32
-    c1, o1 = rf.synth_corpus(2, q, 20000, 8, 64, 16, nthreads=1)
-    c2, o2 = rf.synth_corpus(2, q, 20000, 8, 64, 16, nthreads=4)
+    q = synth.synth_query(2, 32)
+    assert bytes(q) == bytes(synth.synth_query(2, 32)) and len(q) == 32
+    c1, o1 = synth.synth_corpus(2, q, 20000, 8, 64, 16, nthreads=1)
+    c2, o2 = synth.synth_corpus(2, q, 20000, 8, 64, 16, nthreads=4)
     assert np.array_equal(c1, c2) and np.array_equal(o1, o2)
     lens = np.diff(o1.astype(np.int64))
     assert lens.min() >= 8 and lens.max() <= 64 and abs(lens.mean() - 36) < 1.0
     alnum = set(b"abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789")
     assert set(np.unique(c1).tolist()) <= alnum
-    c3, _ = rf.synth_corpus(3, q, 20000, 8, 64, 16)
+    c3, _ = synth.synth_corpus(3, q, 20000, 8, 64, 16)
     assert not np.array_equal(c1[:1000], c3[:1000])

@@ -7,6 +7,7 @@ import pytest
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 
 import rapidfuzz_b200 as rf
+import synth
 from rapidfuzz_b200 import _ffi
 from oracle import oracle as orc
 from gpu_util import gpu_batch
@@ -20,8 +21,8 @@ def _bc(metric, q):
 def test_config2_full_size_1e8():
     """config 2: 1 query len 32 vs 10^8 candidates len 8-64."""
     n = 100_000_000
-    q = rf.synth_query(2, 32)
-    chars, offsets = rf.synth_corpus(2, q, n, 8, 64, 16)
+    q = synth.synth_query(2, 32)
+    chars, offsets = synth.synth_corpus(2, q, n, 8, 64, 16)
     lens = np.diff(offsets.astype(np.int64))
     corpus = rf.Corpus(chars, offsets)
     d = gpu_batch("levenshtein", "distance", q, corpus)                       # interleaved-layout kernel
@@ -53,8 +54,8 @@ def test_config3_full_size_1e7_banded_equals_block():
     """config 3: query len 256 vs 10^7 candidates len 64-256, score_cutoff 32: the one-word sliding band and the
     multi-word block kernel are different algorithms and must return the same Option for every candidate."""
     n = 10_000_000
-    q = rf.synth_query(3, 256)
-    chars, offsets = rf.synth_corpus(3, q, n, 64, 256, 48)
+    q = synth.synth_query(3, 256)
+    chars, offsets = synth.synth_corpus(3, q, n, 64, 256, 48)
     lens = np.diff(offsets.astype(np.int64))
     corpus = rf.Corpus(chars, offsets)
     band = gpu_batch("levenshtein", "distance", q, corpus, cutoff=32)
@@ -78,8 +79,8 @@ def test_config4_full_size_1e8_jaro_winkler():
     """config 4: Jaro-Winkler normalized_similarity, 10^8 candidates: 32-bit row kernel vs the generic per-lane
     routine on every candidate (bit-identical f64), oracle within 1e-6 (and in fact exactly) on a sample."""
     n = 100_000_000
-    q = rf.synth_query(4, 32)
-    chars, offsets = rf.synth_corpus(4, q, n, 8, 64, 16)
+    q = synth.synth_query(4, 32)
+    chars, offsets = synth.synth_corpus(4, q, n, 8, 64, 16)
     corpus = rf.Corpus(chars, offsets)
     fast = gpu_batch("jaro_winkler", "normalized_similarity", q, corpus)
     _ffi.check(_ffi.lib().rf_set_option(b"jaro32", 0))
@@ -101,8 +102,8 @@ def test_corpus_beyond_4gib_uses_64bit_offsets():
     path (interleaved layout built from u64 offsets), CSR path and the streaming pipeline (chunk bases beyond
     2^32) must agree with each other everywhere and with the oracle at both ends of the corpus."""
     n = 125_000_000
-    q = rf.synth_query(6, 32)
-    chars, offsets = rf.synth_corpus(6, q, n, 8, 64, 16)
+    q = synth.synth_query(6, 32)
+    chars, offsets = synth.synth_corpus(6, q, n, 8, 64, 16)
     assert int(offsets[n]) >= 2**32
     corpus = rf.Corpus(chars, offsets)
     d = gpu_batch("levenshtein", "distance", q, corpus)
@@ -121,7 +122,7 @@ def test_corpus_beyond_4gib_uses_64bit_offsets():
     tail = orc.batch("levenshtein", "distance", q, chars[int(offsets[n - m]):], offsets[n - m:] - offsets[n - m], nthreads=0)
     assert np.array_equal(d[-m:], tail)
     # multi-word banded path reads the same u64 offsets
-    q3 = rf.synth_query(7, 100)
+    q3 = synth.synth_query(7, 100)
     bd = gpu_batch("levenshtein", "distance", q3, corpus, cutoff=40)
     exp = orc.batch("levenshtein", "distance", q3, chars[int(offsets[n - m]):], offsets[n - m:] - offsets[n - m], nthreads=0, cutoff=40)
     assert np.array_equal(bd[-m:], exp)
@@ -135,8 +136,8 @@ def test_config5_full_size_corpus_cdist_topk():
     planted near-matches of query 0 lead its list, one slice vs automatic slices must agree on every entry, and five
     queries are checked against the oracle's top-10 over the WHOLE corpus."""
     n, nq, k = 10_000_000, 2000, 10
-    qs = [rf.synth_query(5 + i, 32) for i in range(nq)]
-    chars, offsets = rf.synth_corpus(5, qs[0], n, 8, 64, 16)
+    qs = [synth.synth_query(5 + i, 32) for i in range(nq)]
+    chars, offsets = synth.synth_corpus(5, qs[0], n, 8, 64, 16)
     lens = np.diff(offsets.astype(np.int64))
     corpus = rf.Corpus(chars, offsets)
     q_chars = np.concatenate(qs)

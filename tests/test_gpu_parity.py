@@ -11,6 +11,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 import rapidfuzz_b200 as rf
+import synth
 from rapidfuzz_b200 import _ffi
 from oracle import oracle as orc
 from gpu_util import make_corpus, check, gpu_batch, assert_same
@@ -37,8 +38,8 @@ EDGE_LENS = [0, 1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 31, 32, 33, 63, 64, 65, 66, 
 
 def test_config1_levenshtein_1000():
     """BASELINE config 1: 1 ASCII query len 32 vs 1000 candidates len 8-64, bit-exact."""
-    q = rf.synth_query(1, 32)
-    chars, offsets = rf.synth_corpus(1, q, 1000, 8, 64, 16)
+    q = synth.synth_query(1, 32)
+    chars, offsets = synth.synth_corpus(1, q, 1000, 8, 64, 16)
     check("levenshtein", "distance", q, chars, offsets)
 
 
@@ -146,8 +147,8 @@ def test_config3_shape_banded_vs_oracle():
     for seed, qlen, lo, hi, kmax, n, cut in ((3, 256, 64, 256, 48, 300_000, 32), (13, 1000, 900, 1100, 80, 20_000, 63),
                                             (23, 65, 1, 130, 10, 50_000, 7), (33, 300, 280, 320, 5, 40_000, 0),
                                             (43, 3000, 2990, 3010, 20, 3_000, 20)):
-        q = rf.synth_query(seed, qlen)
-        chars, offsets = rf.synth_corpus(seed, q, n, lo, hi, kmax)
+        q = synth.synth_query(seed, qlen)
+        chars, offsets = synth.synth_corpus(seed, q, n, lo, hi, kmax)
         corpus = rf.Corpus(chars, offsets)
         got = gpu_batch("levenshtein", "distance", q, corpus, cutoff=cut)
         exp = orc.batch("levenshtein", "distance", q, chars, offsets, nthreads=0, cutoff=cut)
@@ -550,9 +551,9 @@ def test_large_corpus_properties():
     """2e6 synthetic candidates (config-2 shape): GPU vs multi-threaded oracle, plus size-independent
     properties: d(q,q-planted)==0 hits exist, |len1-len2| <= d <= max(len1,len2), d(q,c) symmetric under
     swapping roles for a sample, normalized_similarity == 1 - d/max."""
-    q = rf.synth_query(2, 32)
+    q = synth.synth_query(2, 32)
     n = 2_000_000
-    chars, offsets = rf.synth_corpus(2, q, n, 8, 64, 16)
+    chars, offsets = synth.synth_corpus(2, q, n, 8, 64, 16)
     corpus = rf.Corpus(chars, offsets)
     d = gpu_batch("levenshtein", "distance", q, corpus)
     exp = orc.batch("levenshtein", "distance", q, chars, offsets, nthreads=0)
@@ -607,8 +608,8 @@ def test_streaming_matches_oracle(chunk_mb, chunk_kcand):
                 exp = orc.batch(m, kind, q, chars, offsets, nthreads=0, **kw)
                 assert_same(got, exp, ("stream", m, kind, kw, off.dtype))
         # multi-word query + cutoff (config 3 shape) and multi-word Jaro through the same pipeline
-        q3 = rf.synth_query(3, 256)
-        c3, o3 = rf.synth_corpus(3, q3, 30000, 64, 256, 48)
+        q3 = synth.synth_query(3, 256)
+        c3, o3 = synth.synth_corpus(3, q3, 30000, 64, 256, 48)
         assert_same(_stream("levenshtein", "distance", q3, c3, o3, cutoff=32),
                     orc.batch("levenshtein", "distance", q3, c3, o3, nthreads=0, cutoff=32), "stream mw")
         assert_same(_stream("jaro", "similarity", q3[:100], c3[: int(o3[2000])], o3[:2001]),
@@ -625,8 +626,8 @@ def test_streaming_matches_oracle(chunk_mb, chunk_kcand):
 
 def test_streaming_large_equals_resident():
     """5e6 config-2 candidates: the streaming entry point and the resident-corpus path agree bit for bit."""
-    q = rf.synth_query(2, 32)
-    chars, offsets = rf.synth_corpus(2, q, 5_000_000, 8, 64, 16)
+    q = synth.synth_query(2, 32)
+    chars, offsets = synth.synth_corpus(2, q, 5_000_000, 8, 64, 16)
     corpus = rf.Corpus(chars, offsets)
     d = gpu_batch("levenshtein", "distance", q, corpus)
     corpus.close()
@@ -638,8 +639,8 @@ def test_streaming_large_equals_resident():
 
 def test_corpus_file_to_gpu(tmp_path):
     """Corpus file -> resident corpus (rf_corpus_create_from_file) and -> streaming scan straight from the mapping."""
-    q = rf.synth_query(4, 32)
-    chars, offsets = rf.synth_corpus(4, q, 50_000, 0, 64, 16)
+    q = synth.synth_query(4, 32)
+    chars, offsets = synth.synth_corpus(4, q, 50_000, 0, 64, 16)
     path = str(tmp_path / "c.rfc")
     rf.write_corpus_file(path, chars, offsets)
     exp = orc.batch("levenshtein", "distance", q, chars, offsets, nthreads=0)
@@ -665,8 +666,8 @@ def _bc(metric, q):
 def test_extract_and_filter_vs_oracle(n):
     """On-device post-processing: k best by (score best-first, index ascending) and cutoff compaction in index
     order, against the oracle's full score vector sorted / filtered with numpy."""
-    q = rf.synth_query(9, 32)
-    chars, offsets = rf.synth_corpus(9, q, n, 8, 64, 16)
+    q = synth.synth_query(9, 32)
+    chars, offsets = synth.synth_corpus(9, q, n, 8, 64, 16)
     corpus = rf.Corpus(chars, offsets)
     idxs = np.arange(n)
     for metric, kind, cut in (("levenshtein", "distance", None), ("levenshtein", "distance", 12),
@@ -722,9 +723,9 @@ def test_cdist_topk_vs_oracle_full_matrix(qlens, n, k):
     queries = []
     for rep in range(12):
         for ql in qlens:
-            queries.append(rf.synth_query(1000 + rep, ql))
-    base = queries[0] if len(queries[0]) else rf.synth_query(5, 32)
-    chars, offsets = rf.synth_corpus(5, base, n, 8, 64, 16)
+            queries.append(synth.synth_query(1000 + rep, ql))
+    base = queries[0] if len(queries[0]) else synth.synth_query(5, 32)
+    chars, offsets = synth.synth_corpus(5, base, n, 8, 64, 16)
     corpus = rf.Corpus(chars, offsets)
     for cutoff in (None, 20, 3):
         idx, dist = rf.cdist_topk(queries, corpus, k=k, score_cutoff=cutoff)
@@ -739,8 +740,8 @@ def test_cdist_work_decomposition_is_invisible(slices, skip):
     """The (slice, query) work units, the merge of several slices and the skipping of groups by length against the
     running k-th bound must not change a single entry: 330 queries of mixed length (more units than CTAs when there is
     one slice), ties on the distance decided by the index, with and without a cutoff."""
-    queries = [rf.synth_query(2000 + i, (8, 20, 32, 32, 32, 47, 64, 3)[i % 8]) for i in range(330)]
-    chars, offsets = rf.synth_corpus(11, queries[2], 40000, 1, 64, 16)
+    queries = [synth.synth_query(2000 + i, (8, 20, 32, 32, 32, 47, 64, 3)[i % 8]) for i in range(330)]
+    chars, offsets = synth.synth_corpus(11, queries[2], 40000, 1, 64, 16)
     corpus = rf.Corpus(chars, offsets)
     L = _ffi.lib()
     _ffi.check(L.rf_set_option(b"cdist_slices", slices))
@@ -764,11 +765,11 @@ def test_sharded_cdist_device_merge(world, k):
     on the device (rf_topk_merge_device).  Must equal the oracle's global top-k, ties by GLOBAL index."""
     import torch
     from rapidfuzz_b200 import sharding
-    queries = [rf.synth_query(3000 + i, (32, 12, 50)[i % 3]) for i in range(40)]
+    queries = [synth.synth_query(3000 + i, (32, 12, 50)[i % 3]) for i in range(40)]
     q_off = np.zeros(len(queries) + 1, dtype=np.uint64)
     q_off[1:] = np.cumsum([len(q) for q in queries])
     q_chars = np.concatenate(queries)
-    chars, offsets = rf.synth_corpus(12, queries[0], 30000, 1, 64, 16)
+    chars, offsets = synth.synth_corpus(12, queries[0], 30000, 1, 64, 16)
     for cutoff in (None, 14):
         parts, starts = [], []
         for r in range(world):

@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 import rapidfuzz_b200 as rf
+import synth
 from rapidfuzz_b200 import _ffi
 
 
@@ -22,8 +23,8 @@ def test_pack_strings_matches_python_join():
 
 @pytest.mark.parametrize("n", [0, 1, 1000])
 def test_corpus_file_round_trip(tmp_path, n):
-    q = rf.synth_query(1, 32)
-    chars, offsets = rf.synth_corpus(1, q, n, 0, 64, 16)
+    q = synth.synth_query(1, 32)
+    chars, offsets = synth.synth_corpus(1, q, n, 0, 64, 16)
     path = str(tmp_path / "c.rfc")
     rf.write_corpus_file(path, chars, offsets)
     assert os.path.getsize(path) % 1 == 0 and os.path.getsize(path) >= 64
@@ -44,8 +45,8 @@ def test_corpus_file_rejects_garbage(tmp_path):
     with pytest.raises(rf.RfError):
         rf.CorpusFile(str(tmp_path / "missing.rfc"))
     # truncated file
-    q = rf.synth_query(1, 8)
-    chars, offsets = rf.synth_corpus(1, q, 100, 1, 20, 4)
+    q = synth.synth_query(1, 8)
+    chars, offsets = synth.synth_corpus(1, q, 100, 1, 20, 4)
     good = tmp_path / "good.rfc"
     rf.write_corpus_file(str(good), chars, offsets)
     (tmp_path / "cut.rfc").write_bytes(good.read_bytes()[:-5])
@@ -56,3 +57,12 @@ def test_corpus_file_rejects_garbage(tmp_path):
     bad[5] = bad[6] + 1
     with pytest.raises(rf.RfError):
         rf.write_corpus_file(str(tmp_path / "x.rfc"), chars, bad)
+    # ... and a file whose index was corrupted afterwards is refused at open time (rf_io.cpp:157)
+    raw = bytearray(good.read_bytes())
+    width = 4 if len(chars) < 2**32 - 16 else 8
+    pos = 64 + 5 * width                      # offsets[5], behind the 64-byte header
+    raw[pos:pos + width] = (int(offsets[7]) + 3).to_bytes(width, "little")
+    (tmp_path / "corrupt.rfc").write_bytes(bytes(raw))
+    with pytest.raises(rf.RfError) as ei:
+        rf.CorpusFile(str(tmp_path / "corrupt.rfc"))
+    assert ei.value.status == _ffi.RF_ERR_INVALID_ARG

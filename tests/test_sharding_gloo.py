@@ -11,6 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 import rapidfuzz_b200 as rf
+import synth
 from rapidfuzz_b200 import sharding
 from oracle import oracle as orc
 
@@ -66,14 +67,18 @@ def test_merge_topk_pads_and_orders():
     i1 = np.array([[2, 0xFFFFFFFF, 0xFFFFFFFF]], dtype=np.uint32)
     d1 = np.array([[1, 0xFFFFFFFF, 0xFFFFFFFF]], dtype=np.uint32)
     gi, gd = sharding.merge_topk([i0, i1], [d0, d1], [0, 100], 4)
-    assert gi.tolist() == [[5, 102, 7, 0xFFFFFFFF]] and gd.tolist() == [[1, 1, 3, 0xFFFFFFFF]]
+    assert gi.dtype == np.uint64 and gd.dtype == np.uint32
+    assert gi.tolist() == [[5, 102, 7, 0xFFFFFFFFFFFFFFFF]] and gd.tolist() == [[1, 1, 3, 0xFFFFFFFF]]
+    # shard starts beyond 2^32 must not spill into the distance (the old 32-bit packed key did)
+    gi, gd = sharding.merge_topk([i0, i1], [d0, d1], [0, 2**32 + 100], 4)
+    assert gi.tolist() == [[5, 2**32 + 102, 7, 0xFFFFFFFFFFFFFFFF]] and gd.tolist() == [[1, 1, 3, 0xFFFFFFFF]]
 
 
 @pytest.mark.timeout(300)
 def test_world2_gloo_gather_equals_single_process():
-    q = rf.synth_query(2, 32)
-    chars, offsets = rf.synth_corpus(2, q, 5001, 8, 64, 16)
-    qs = [rf.synth_query(100 + i, 32) for i in range(3)]
+    q = synth.synth_query(2, 32)
+    chars, offsets = synth.synth_corpus(2, q, 5001, 8, 64, 16)
+    qs = [synth.synth_query(100 + i, 32) for i in range(3)]
     k, world = 10, 2
     mgr = mp.Manager()
     ret = mgr.dict()
@@ -87,5 +92,5 @@ def test_world2_gloo_gather_equals_single_process():
         d = orc.batch("levenshtein", "distance", qq, chars, offsets).astype(np.int64)
         keys = np.sort(d * (1 << 32) + np.arange(n))[:k]
         for r in range(world):
-            assert np.array_equal(ret[r][1][qi], (keys & 0xFFFFFFFF).astype(np.uint32))
+            assert np.array_equal(ret[r][1][qi], (keys & 0xFFFFFFFF).astype(np.uint64))
             assert np.array_equal(ret[r][2][qi], (keys >> 32).astype(np.uint32))

@@ -20,6 +20,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 import rapidfuzz_b200 as rf
+import synth
 from rapidfuzz_b200 import sharding
 
 
@@ -50,10 +51,10 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     nq, n, k = a.queries, a.candidates, a.k
-    qs = [rf.synth_query(5 + i, 32) for i in range(nq)]
+    qs = [synth.synth_query(5 + i, 32) for i in range(nq)]
     q_chars = np.concatenate(qs)
     q_off = np.arange(nq + 1, dtype=np.uint64) * 32
-    chars, offsets = rf.synth_corpus(5, qs[0], n, 8, 64, 16)          # same corpus on every rank, each keeps its shard
+    chars, offsets = synth.synth_corpus(5, qs[0], n, 8, 64, 16)          # same corpus on every rank, each keeps its shard
     c_loc, o_loc, lo = sharding.local_shard(chars, offsets, world, rank)
     corpus = rf.Corpus(c_loc, o_loc, device=local)
     t_scan, t_all = [], []

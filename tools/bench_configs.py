@@ -14,6 +14,7 @@ sys.path.insert(0, os.path.join(ROOT, "rapidfuzz-rs_b200"))
 import numpy as np
 import torch
 import rapidfuzz_b200 as rf
+import synth
 from rapidfuzz_b200 import _ffi
 from oracle import oracle as orc
 
@@ -40,8 +41,8 @@ def timed(fn, steps, warmup=3):
 
 
 def one_vs_many(name, metric, kind, seed, qlen, n, lo, hi, kmax, cutoff, out_f64, bytes_per_pair_fn, steps=20, tol=0.0):
-    q = rf.synth_query(seed, qlen)
-    chars, offsets = rf.synth_corpus(seed, q, n, lo, hi, kmax)
+    q = synth.synth_query(seed, qlen)
+    chars, offsets = synth.synth_corpus(seed, q, n, lo, hi, kmax)
     corpus = rf.Corpus(chars, offsets)
     cls = type("B", (rf._scorer.BatchComparatorBase,), {"METRIC": metric})
     b = cls(q)
@@ -74,11 +75,11 @@ def one_vs_many(name, metric, kind, seed, qlen, n, lo, hi, kmax, cutoff, out_f64
 
 
 def cdist(nq, n, k=10, steps=2):
-    q0 = rf.synth_query(5, 32)
-    qs = [rf.synth_query(5 + i, 32) for i in range(nq)]
+    q0 = synth.synth_query(5, 32)
+    qs = [synth.synth_query(5 + i, 32) for i in range(nq)]
     q_chars = np.concatenate(qs)
     q_off = (np.arange(nq + 1, dtype=np.uint64) * 32)
-    chars, offsets = rf.synth_corpus(5, q0, n, 8, 64, 16)
+    chars, offsets = synth.synth_corpus(5, q0, n, 8, 64, 16)
     corpus = rf.Corpus(chars, offsets)
     idx = torch.empty((nq, k), dtype=torch.int32, device="cuda")
     dist = torch.empty((nq, k), dtype=torch.int32, device="cuda")
@@ -108,8 +109,8 @@ def cdist(nq, n, k=10, steps=2):
 
 def extract_filter(n):
     """config-2 shape: scan + on-device top-10 / cutoff compaction, host wall clock (includes the k-entry D2H)."""
-    q = rf.synth_query(2, 32)
-    chars, offsets = rf.synth_corpus(2, q, n, 8, 64, 16)
+    q = synth.synth_query(2, 32)
+    chars, offsets = synth.synth_corpus(2, q, n, 8, 64, 16)
     corpus = rf.Corpus(chars, offsets)
     b = type("B", (rf._scorer.BatchComparatorBase,), {"METRIC": "levenshtein"})(q)
     exp = orc.batch("levenshtein", "distance", q, chars, offsets, nthreads=0)
@@ -140,8 +141,8 @@ def extract_filter(n):
 def widen(n):
     """The steps either side of the path: u32 elements, packing, corpus files."""
     import tempfile
-    q = rf.synth_query(2, 32)
-    chars, offsets = rf.synth_corpus(2, q, n, 8, 64, 16)
+    q = synth.synth_query(2, 32)
+    chars, offsets = synth.synth_corpus(2, q, n, 8, 64, 16)
     # --- u32 elements: same strings as code points (+0x400 so that nothing is a byte), alphabet renaming per call
     elems = chars.astype(np.uint32) + 0x400
     q32 = q.astype(np.uint32) + 0x400
@@ -220,9 +221,9 @@ if __name__ == "__main__":
         one_vs_many("C2-shape osa (query 48)", "osa", "distance", 2, 48, int(1e8 * scale), 8, 64, 16, None, False, lambda l: l + 8, steps=5)
     if "simple" in which:   # HBM-bound metrics: bytes = len + 4 + 4 per pair
         for m, kind in (("hamming", "distance"), ("prefix", "similarity"), ("postfix", "similarity")):
-            q = rf.synth_query(2, 32)
+            q = synth.synth_query(2, 32)
             n = int(1e8 * scale)
-            chars, offsets = rf.synth_corpus(2, q, n, 8, 64, 16)
+            chars, offsets = synth.synth_corpus(2, q, n, 8, 64, 16)
             corpus = rf.Corpus(chars, offsets)
             b = type("B", (rf._scorer.BatchComparatorBase,), {"METRIC": m})(q)
             out = torch.empty(n, dtype=torch.int32, device="cuda")
@@ -239,9 +240,9 @@ if __name__ == "__main__":
             b.close(); corpus.close()
     if "dp" in which:   # the O(len1*len2) DP metrics: generic Levenshtein weights (Wagner-Fischer) and Damerau-Levenshtein
         for m, w in (("levenshtein", (1, 2, 3)), ("damerau_levenshtein", None)):
-            q = rf.synth_query(2, 32)
+            q = synth.synth_query(2, 32)
             n = int(1e7 * scale)
-            chars, offsets = rf.synth_corpus(2, q, n, 8, 64, 16)
+            chars, offsets = synth.synth_corpus(2, q, n, 8, 64, 16)
             corpus = rf.Corpus(chars, offsets)
             b = type("B", (rf._scorer.BatchComparatorBase,), {"METRIC": m})(q)
             out = torch.empty(n, dtype=torch.int32, device="cuda")

@@ -5,6 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "rapidfuzz-rs_b200"))
 import numpy as np
 import rapidfuzz_b200 as rf
+import synth
 from rapidfuzz_b200 import _ffi
 from rapidfuzz_b200._scorer import BatchComparatorBase
 
@@ -12,13 +13,13 @@ def bc(metric, q):
     return type("B", (BatchComparatorBase,), {"METRIC": metric})(q)
 
 L = _ffi.lib()
-q = rf.synth_query(1, 32)
-chars, offsets = rf.synth_corpus(1, q, 3000, 0, 64, 16)
+q = synth.synth_query(1, 32)
+chars, offsets = synth.synth_corpus(1, q, 3000, 0, 64, 16)
 corpus = rf.Corpus(chars, offsets)
 for path in (0, 1, 2):
     _ffi.check(L.rf_set_option(b"single_word_path", path))
     for m in ("levenshtein", "indel", "osa", "lcs_seq", "jaro_winkler"):
-        for qq in (q, rf.synth_query(2, 50)):
+        for qq in (q, synth.synth_query(2, 50)):
             b = bc(m, qq)
             b._score("distance", corpus, None)
             b._score("normalized_similarity", corpus, rf.Args().score_cutoff(0.5))
@@ -29,15 +30,15 @@ b.extract("distance", corpus, k=10)
 b.filter("distance", corpus, rf.Args().score_cutoff(10))
 b.stream("distance", chars, offsets.astype(np.uint32))
 b.close()
-rf.cdist_topk([q, rf.synth_query(3, 20), rf.synth_query(4, 64)], corpus, k=10)
+rf.cdist_topk([q, synth.synth_query(3, 20), synth.synth_query(4, 64)], corpus, k=10)
 rf.cdist_topk([q], corpus, k=40, score_cutoff=30)
 for sl in (3, 17, 0):   # several corpus slices -> cdist_merge_kernel; 0 = automatic
     _ffi.check(L.rf_set_option(b"cdist_slices", sl))
-    rf.cdist_topk([rf.synth_query(10 + i, (8, 32, 47, 64)[i % 4]) for i in range(40)], corpus, k=10)
+    rf.cdist_topk([synth.synth_query(10 + i, (8, 32, 47, 64)[i % 4]) for i in range(40)], corpus, k=10)
 try:   # sharded merge (rf_topk_merge_device), three shards on one GPU
     import torch
     from rapidfuzz_b200 import sharding
-    qs = [rf.synth_query(20 + i, 32) for i in range(8)]
+    qs = [synth.synth_query(20 + i, 32) for i in range(8)]
     qo = np.arange(9, dtype=np.uint64) * 32
     parts, starts = [], []
     for r in range(3):
@@ -50,8 +51,8 @@ try:   # sharded merge (rf_topk_merge_device), three shards on one GPU
     torch.cuda.synchronize()
 except ImportError:
     pass
-q3 = rf.synth_query(3, 256)
-c3, o3 = rf.synth_corpus(3, q3, 2000, 64, 256, 48)
+q3 = synth.synth_query(3, 256)
+c3, o3 = synth.synth_corpus(3, q3, 2000, 64, 256, 48)
 corpus3 = rf.Corpus(c3, o3)
 for m in ("levenshtein", "indel", "osa", "jaro"):
     b = bc(m, q3)
@@ -69,7 +70,7 @@ lens[7] = 33000   # ONE candidate past the 16-bit DP cells (a 33000 x 64 DP unde
 cl = np.random.default_rng(3).integers(97, 101, int(lens.sum())).astype(np.uint8)
 ol = np.zeros(len(lens) + 1, np.uint64); ol[1:] = np.cumsum(lens)
 corpus_l = rf.Corpus(cl, ol)
-for qq in (q, rf.synth_query(2, 64), rf.synth_query(2, 70)):
+for qq in (q, synth.synth_query(2, 64), synth.synth_query(2, 70)):
     for m, a in (("damerau_levenshtein", None), ("levenshtein", rf.Args().weights(1, 2, 3)), ("hamming", rf.Args().pad(True)),
                  ("jaro_winkler", None), ("jaro", rf.Args().score_cutoff(0.7))):
         b = bc(m, qq)

@@ -29,7 +29,8 @@ typedef enum rf_status {
   RF_ERR_UNSUPPORTED = 2, /* e.g. query longer than RF_MAX_QUERY_LEN; generic (non-uniform, non-indel) Levenshtein weights
                              with a query longer than 2048; u32 query with more than 255 distinct symbols */
   RF_ERR_CUDA = 3,
-  RF_ERR_OOM = 4
+  RF_ERR_OOM = 4,
+  RF_ERR_NCCL = 5 /* a collective of the sharded (multi-GPU) entry points failed */
 } rf_status;
 
 /* metric modules: distance/{levenshtein,indel,lcs_seq,osa,jaro,jaro_winkler,hamming,prefix,postfix,damerau_levenshtein}.rs and
@@ -76,7 +77,9 @@ typedef struct rf_args {
                              * entry points only write the sentinel.  1: the excess length counts as mismatches. */
 } rf_args;
 
-#define RF_MAX_QUERY_LEN 16384u
+/* Queries may have up to RF_MAX_QUERY_LEN elements (the reference has no limit; its longest own test is 106 514 x
+ * 107 244, levenshtein.rs:2139-2161).  The bound only keeps the per-query match tables (2 x 32 B per element) sane. */
+#define RF_MAX_QUERY_LEN 4194304u
 
 typedef struct rf_corpus rf_corpus; /* packed candidates resident in one GPU's HBM */
 typedef struct rf_batch rf_batch;   /* one cached query == one BatchComparator */
@@ -204,6 +207,64 @@ rf_status rf_topk_merge_device(const uint32_t* idx_parts, const uint32_t* dist_p
                                const uint64_t* index_base_device, uint32_t parts, uint32_t nq, uint32_t k,
                                uint64_t* idx_out_device, uint32_t* dist_out_device, int device, void* stream);
 
+/* ---- sharded corpora: ONE process, several GPUs of one box.  The reference's BatchComparator is
+ * plain data, Clone + Send + Sync (levenshtein.rs:1635-1639), i.e. a Rust host may drive it from any thread over any
+ * slice of the candidates; here the split is the library's: contiguous candidate ranges balanced by BYTES, one
+ * resident shard per listed device (uploaded and laid out concurrently), the query's tables replicated, per-device
+ * streams.  Pairs are independent, so the scan has no exchange step; the collectives are the final ones only:
+ *   - *_allgather_device: NCCL all-gather of the per-shard score vectors (grouped ncclBroadcast = all-gather-v, in
+ *     place), every device ends with all n scores in candidate order;
+ *   - rf_sharded_cdist_topk_u8: ncclAllGather of the per-shard [nq][k] lists + rf_topk_merge_device.
+ * Host-destined results (rf_sharded_score_*, rf_sharded_extract_*) need no collective: every device writes its slice of
+ * the caller's vector.  Results are identical to the single-GPU entry points on the whole corpus (global candidate
+ * indices, u64).  A failing collective returns RF_ERR_NCCL.  `devices` may list a device more than once (one-GPU test
+ * boxes): such a list cannot form an NCCL communicator and the same gathers run as event-ordered device copies
+ * (rf_set_option("sharded_collective", 1) forces that path for any list; rf_sharded_corpus_uses_nccl tells which).
+ * Handles are immutable; concurrent calls are safe (collectives on one corpus are serialised internally). */
+typedef struct rf_sharded_corpus rf_sharded_corpus;
+typedef struct rf_sharded_batch rf_sharded_batch;
+rf_status rf_corpus_create_sharded_u8(const uint8_t* chars, const uint64_t* offsets, uint64_t n, const int* devices, int ndev,
+                                      rf_sharded_corpus** out);
+rf_status rf_sharded_corpus_destroy(rf_sharded_corpus* c);
+uint64_t rf_sharded_corpus_size(const rf_sharded_corpus* c);
+int rf_sharded_corpus_shards(const rf_sharded_corpus* c);
+/* candidates [*first, *end) live on shard `shard` */
+rf_status rf_sharded_corpus_shard_range(const rf_sharded_corpus* c, int shard, uint64_t* first, uint64_t* end);
+/* the shard as a plain corpus (owned by the sharded handle), usable with every single-GPU entry point */
+const rf_corpus* rf_sharded_corpus_shard(const rf_sharded_corpus* c, int shard);
+int rf_sharded_corpus_uses_nccl(const rf_sharded_corpus* c);
+/* BatchComparator::new(query), replicated on every listed device (same list, same order, as the corpus) */
+rf_status rf_sharded_batch_create_u8(rf_metric metric, const uint8_t* query, uint32_t query_len, const int* devices, int ndev,
+                                     rf_sharded_batch** out);
+rf_status rf_sharded_batch_create_u32(rf_metric metric, const uint32_t* query, uint32_t query_len, const int* devices, int ndev,
+                                      rf_sharded_batch** out);
+rf_status rf_sharded_batch_destroy(rf_sharded_batch* b);
+/* == rf_batch_score_* over the whole sharded corpus; out_host[n] in candidate order */
+rf_status rf_sharded_score_u32(const rf_sharded_batch* b, const rf_sharded_corpus* c, rf_kind kind, const rf_args* args,
+                               uint32_t* out_host);
+rf_status rf_sharded_score_f64(const rf_sharded_batch* b, const rf_sharded_corpus* c, rf_kind kind, const rf_args* args,
+                               double* out_host);
+/* scores + all-gather: out_device[i] is a buffer of n results on devices[i]; all of them hold every score on return */
+rf_status rf_sharded_score_u32_allgather_device(const rf_sharded_batch* b, const rf_sharded_corpus* c, rf_kind kind,
+                                                const rf_args* args, uint32_t* const* out_device);
+rf_status rf_sharded_score_f64_allgather_device(const rf_sharded_batch* b, const rf_sharded_corpus* c, rf_kind kind,
+                                                const rf_args* args, double* const* out_device);
+/* == rf_batch_extract_* over the whole sharded corpus (global u64 indices) */
+rf_status rf_sharded_extract_u32(const rf_sharded_batch* b, const rf_sharded_corpus* c, rf_kind kind, const rf_args* args, uint32_t k,
+                                 uint64_t* idx_out, uint32_t* score_out, uint32_t* n_out);
+rf_status rf_sharded_extract_f64(const rf_sharded_batch* b, const rf_sharded_corpus* c, rf_kind kind, const rf_args* args, uint32_t k,
+                                 uint64_t* idx_out, double* score_out, uint32_t* n_out);
+/* == rf_cdist_topk_u8 over the whole sharded corpus: [nq][k] global indices (UINT64_MAX = none) and distances
+ * (UINT32_MAX = none), host buffers.  shards * k <= 25600. */
+rf_status rf_sharded_cdist_topk_u8(const uint8_t* q_chars, const uint64_t* q_offsets, uint32_t nq, const rf_sharded_corpus* c,
+                                   const rf_args* args, uint32_t k, uint64_t* idx_host, uint32_t* dist_host);
+/* == rf_batch_stream_* with the candidate range split by bytes over the batch's devices: every device runs its own
+ * chunked H2D / scan / D2H pipeline over its own PCIe link, concurrently */
+rf_status rf_sharded_stream_u32(const rf_sharded_batch* b, const uint8_t* chars, const uint64_t* offsets, uint64_t n, rf_kind kind,
+                                const rf_args* args, uint32_t* out_host);
+rf_status rf_sharded_stream_f64(const rf_sharded_batch* b, const uint8_t* chars, const uint64_t* offsets, uint64_t n, rf_kind kind,
+                                const rf_args* args, double* out_host);
+
 /* ---- packing and corpus files (host-side; the step before the scoring path).  The reference takes one iterator
  * per candidate (levenshtein.rs:1750-1762); callers holding a Vec<String> pack it once:
  *   rf_pack_u8: n strings given as (pointer, length) -> CSR offsets[n+1] (+ chars[offsets[n]] when chars_out != NULL;
@@ -235,6 +296,9 @@ rf_status rf_corpus_create_from_file(const char* path, int device, rf_corpus** o
  *            Jaro-Winkler, which need random access to the candidate, stay on 0);
  *   "jaro32" (default 1): Jaro / Jaro-Winkler queries of at most 32 elements use the row-wise 32-bit kernel
  *        (interleaved layout only); 0 = the generic per-lane routine;
+ *   "multi_word_path" (default 0): queries of 65..512 elements on a resident corpus: 0 = one thread per candidate, the
+ *        whole bit-vector column in registers (interleaved layout), 1 = the sub-warp shuffle kernel (what longer
+ *        queries, corpora without the interleaved copy and the streaming entry points use);
  *   "banded_levenshtein" (default 1): multi-word Levenshtein distance with score_cutoff <= 63 edits uses the
  *        one-thread-per-candidate 64-bit Ukkonen-band kernel; 0 = always the multi-word block kernel;
  *   "stream_chunk_mb" (default 64), "stream_chunk_kcand" (default 2048): chunk size of rf_batch_stream_* in
@@ -242,6 +306,8 @@ rf_status rf_corpus_create_from_file(const char* path, int device, rf_corpus** o
  *   "compact_u32_corpus" (default 1): rf_corpus_create_u32 renames corpora of at most 255 distinct symbols to
  *        bytes once at creation (0 = keep u32 elements and rename per scoring call);
  *   "cdist_slices" (default 0 = automatic, 1..256): corpus slices of rf_cdist_topk_* (work units = slices x queries);
+ *   "sharded_collective" (default 0): 0 = NCCL for the gathers of the sharded entry points when the device list has no
+ *        duplicates, 1 = event-ordered device-to-device copies;
  *   "cdist_skip" (default 1): rf_cdist_topk_* skips groups whose length alone puts them beyond the running k-th
  *        distance (0 = score every candidate; for measurements). */
 rf_status rf_set_option(const char* name, int value);

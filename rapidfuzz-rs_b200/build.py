@@ -10,8 +10,8 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "librfgpu.so")
 NVCC = os.environ.get("RF_NVCC", "/usr/local/cuda/bin/nvcc")
 HOSTCXX = os.environ.get("RF_HOSTCXX", "/usr/bin/g++")
-SOURCES = ["rf_kernels.cu", "rf_layout.cu", "rf_select.cu", "rf_api.cu", "rf_io.cpp"]
-HEADERS = ["rf_core.cuh", "rf_kernels.cuh", os.path.join("..", "..", "include", "rfgpu.h")]
+SOURCES = ["rf_kernels.cu", "rf_layout.cu", "rf_select.cu", "rf_api.cu", "rf_sharded.cu", "rf_io.cpp"]
+HEADERS = ["rf_core.cuh", "rf_kernels.cuh", "rf_internal.h", os.path.join("..", "..", "include", "rfgpu.h")]
 
 
 def needs_build():
@@ -31,7 +31,7 @@ def build(force=False, verbose=False):
            # Rust never contracts a*b+c; the f64 Jaro/normalisation epilogues must match it bit for bit
            "--fmad=false",
            "-Xcompiler", "-fPIC,-fopenmp,-ffp-contract=off,-Wall",
-           "-shared", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lgomp"]
+           "-shared", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lgomp", "-lnccl"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     if os.environ.get("RF_DEBUG_MW"):

@@ -16,6 +16,7 @@
 #include <unordered_map>
 #include "../../include/rfgpu.h"
 #include "rf_kernels.cuh"
+#include "rf_internal.h"
 
 using namespace rfk;
 
@@ -23,12 +24,15 @@ static thread_local std::string g_last_error;
 // tuning knobs (rf_set_option)
 static std::atomic<int> g_build_lb{1};   // build the length-bucketed interleaved layout at corpus creation
 static std::atomic<int> g_w1_path{0};    // 0: interleaved-layout kernel when available, 1: CSR/TMA-tile kernel
+static std::atomic<int> g_mw_path{0};    // queries of 65..512 on a resident corpus: 0 register kernel (scan_lbn), 1 shuffle kernel (scan_mw)
 static std::atomic<int> g_band{1};       // multi-word Levenshtein with cutoff <= 63: banded kernel (0: block kernel)
 static std::atomic<int> g_stream_mb{64};      // rf_batch_stream_*: chunk size in candidate bytes (MiB)
 static std::atomic<int> g_stream_kcand{2048}; // rf_batch_stream_*: chunk size in candidates (x1024)
 static std::atomic<int> g_compact32{1};       // rf_corpus_create_u32: keep corpora with <= 255 distinct symbols as renamed bytes
 static std::atomic<int> g_cdist_slices{0};    // rf_cdist_topk_*: corpus slices (0: automatic)
 static std::atomic<int> g_cdist_skip{1};      // rf_cdist_topk_*: skip groups by length against the running k-th bound
+
+void rf__set_sharded_collective(int mode);  // rf_sharded.cu
 
 static rf_status fail(rf_status s, const std::string& msg) {
   g_last_error = msg;
@@ -84,41 +88,6 @@ static unsigned long long* counter_slot(int device) {
   return pools[device] + (next[device]++ % kSlots);
 }
 
-struct rf_corpus {
-  int device = 0;
-  uint64_t n = 0, total = 0;
-  uint8_t* d_chars = nullptr;     // u8 elements ...
-  uint32_t* d_elems32 = nullptr;  // ... or u32 elements (rf_corpus_create_u32); exactly one of the two is set
-  uint32_t* d_off32 = nullptr;
-  uint64_t* d_off64 = nullptr;
-  LbAlloc lb;  // length-bucketed interleaved copy for the single-word kernels
-  // rf_corpus_create_u32 with at most 255 distinct symbols in the whole corpus: the symbols are renamed to the bytes
-  // 1..D ONCE at creation and the corpus is kept (and scored) as a u8 corpus; d_elems32 is released.  The dictionary
-  // stays on the host: a u32 comparator renames its query through it (absent symbols -> 0, which matches nothing).
-  bool compact32 = false;
-  uint64_t dict_serial = 0;
-  std::vector<uint32_t> dict_keys;   // [kAlphaSlots] open addressing (alpha_hash)
-  std::vector<uint8_t> dict_codes;   // [kAlphaSlots] 0 = empty slot
-};
-
-struct rf_batch {
-  int device = 0;
-  rf_metric metric = RF_LEVENSHTEIN;
-  std::vector<uint8_t> s1;
-  uint32_t len1 = 0, words = 0;
-  uint8_t* d_blob = nullptr;  // all tables in one allocation
-  QueryView view{};
-  // rf_batch_create_u32: the query's distinct symbols are renamed to the bytes 1..D (D <= 255); candidates are
-  // renamed on the device per scoring call (symbols the query does not contain become 0, which matches nothing).
-  // Every metric here depends only on which (query, candidate) positions are equal, so the result is exact.
-  bool wide = false;
-  std::vector<uint32_t> s1w;         // the u32 query as given
-  mutable std::mutex sub_mu;         // byte comparators of this query against compact u32 corpora, by dictionary
-  mutable std::unordered_map<uint64_t, rf_batch*> subs;
-  uint32_t* d_alpha_keys = nullptr;  // [kAlphaSlots] open-addressing table: symbol ...
-  uint8_t* d_alpha_codes = nullptr;  // ... -> byte code, 0 = empty slot
-};
-
 extern "C" {
 
 void rf_args_default(rf_args* a) {
@@ -135,6 +104,7 @@ const char* rf_status_string(rf_status s) {
     case RF_ERR_UNSUPPORTED: return "unsupported";
     case RF_ERR_CUDA: return "CUDA error";
     case RF_ERR_OOM: return "out of device memory";
+    case RF_ERR_NCCL: return "NCCL error";
   }
   return "unknown";
 }
@@ -157,12 +127,14 @@ rf_status rf_set_option(const char* name, int value) {
   if (!strcmp(name, "build_interleaved_layout")) { g_build_lb.store(value ? 1 : 0); return RF_OK; }
   if (!strcmp(name, "single_word_path")) { g_w1_path.store(value); return RF_OK; }
   if (!strcmp(name, "jaro32")) { set_jaro32(value ? 1 : 0); return RF_OK; }
+  if (!strcmp(name, "multi_word_path")) { g_mw_path.store(value ? 1 : 0); return RF_OK; }
   if (!strcmp(name, "banded_levenshtein")) { g_band.store(value ? 1 : 0); return RF_OK; }
   if (!strcmp(name, "stream_chunk_mb")) { if (value < 1) return fail(RF_ERR_INVALID_ARG, "stream_chunk_mb < 1"); g_stream_mb.store(value); return RF_OK; }
   if (!strcmp(name, "stream_chunk_kcand")) { if (value < 1) return fail(RF_ERR_INVALID_ARG, "stream_chunk_kcand < 1"); g_stream_kcand.store(value); return RF_OK; }
   if (!strcmp(name, "cdist_slices")) { if (value < 0 || value > 256) return fail(RF_ERR_INVALID_ARG, "cdist_slices not in 0..256"); g_cdist_slices.store(value); return RF_OK; }
   if (!strcmp(name, "compact_u32_corpus")) { g_compact32.store(value ? 1 : 0); return RF_OK; }
   if (!strcmp(name, "cdist_skip")) { g_cdist_skip.store(value ? 1 : 0); return RF_OK; }
+  if (!strcmp(name, "sharded_collective")) { rf__set_sharded_collective(value ? 1 : 0); return RF_OK; }
   return fail(RF_ERR_INVALID_ARG, std::string("unknown option: ") + name);
 }
 
@@ -185,21 +157,40 @@ __global__ void narrow_offsets(const uint64_t* __restrict__ in, uint32_t* __rest
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n1; i += (uint64_t)gridDim.x * blockDim.x)
     out[i] = in[i] > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)in[i];  // saturate: check_offsets then rejects it (> total)
 }
+// offsets of a sub-range of a larger CSR (sharded corpora): out = in - base, as u32 or u64; values below the base wrap to
+// huge ones and saturate, which check_offsets rejects
+__global__ void rebase_offsets(const uint64_t* __restrict__ in, uint64_t base, uint32_t* __restrict__ out32,
+                               uint64_t* __restrict__ out64, uint64_t n1) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n1; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t v = in[i] - base;
+    if (out64) out64[i] = v;
+    else out32[i] = v > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)v;
+  }
+}
 
 // CSR sanity: starts must be non-decreasing and end at `total`.  A corrupt / crafted offset array would otherwise send
 // the layout builder and the scan kernels out of bounds (sticky CUDA error = the whole process poisoned).
 __global__ void check_offsets_kernel(const uint32_t* __restrict__ o32, const uint64_t* __restrict__ o64, uint64_t n,
                                      uint64_t total, uint32_t* __restrict__ bad) {
   uint32_t b = 0;
+  unsigned long long mx = 0;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t a = o64 ? o64[i] : (uint64_t)o32[i], z = o64 ? o64[i + 1] : (uint64_t)o32[i + 1];
     if (z < a || z > total) b = 1;
+    else if (z - a > mx) mx = z - a;
   }
   if (__any_sync(0xffffffffu, b) && (threadIdx.x & 31u) == 0) atomicOr(bad, 1u);
+  for (int d = 16; d >= 1; d >>= 1) {
+    const unsigned long long o = __shfl_xor_sync(0xffffffffu, mx, d);
+    mx = o > mx ? o : mx;
+  }
+  if ((threadIdx.x & 31u) == 0 && mx) atomicMax(reinterpret_cast<unsigned long long*>(bad) + 1, mx);  // longest candidate
 }
 
 // synchronises `st`; RF_ERR_INVALID_ARG when the offsets are not a valid CSR index of `total` elements
-static rf_status check_offsets(const void* d_off, bool is64, uint64_t n, uint64_t total, cudaStream_t st) {
+static rf_status check_offsets(const void* d_off, bool is64, uint64_t n, uint64_t total, cudaStream_t st,
+                               uint64_t* max_len = nullptr) {
+  if (max_len) *max_len = 0;
   if (n == 0) return RF_OK;
   uint32_t* d_bad = nullptr;
   RF_CUDA(dev_alloc(&d_bad, 16, st));
@@ -213,8 +204,11 @@ static rf_status check_offsets(const void* d_off, bool is64, uint64_t n, uint64_
     rfk::count_launches(1);
     e = cudaGetLastError();
   }
-  if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, st);
+  unsigned long long res[2] = {0, 0};
+  if (e == cudaSuccess) e = cudaMemcpyAsync(res, d_bad, 16, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  bad = (uint32_t)res[0];
+  if (max_len) *max_len = res[1];
   dev_free(d_bad, st);
   if (e != cudaSuccess) return cuda_fail(e, "offset validation");
   if (bad) return fail(RF_ERR_INVALID_ARG, "offsets are not non-decreasing CSR starts ending at offsets[n]");
@@ -224,7 +218,7 @@ static rf_status check_offsets(const void* d_off, bool is64, uint64_t n, uint64_
 static rf_status corpus_finish(rf_corpus* c, cudaStream_t st) {
   {
     rf_status vs = check_offsets(c->d_off32 ? (const void*)c->d_off32 : (const void*)c->d_off64, c->d_off32 == nullptr, c->n,
-                                 c->total, st);
+                                 c->total, st, &c->max_len);
     if (vs != RF_OK) return vs;
   }
   if (c->d_off32) fill_tail_u32<<<1, 16, 0, st>>>(c->d_off32, c->n + 1, (uint32_t)c->total);
@@ -237,16 +231,20 @@ static rf_status corpus_finish(rf_corpus* c, cudaStream_t st) {
   return RF_OK;
 }
 
+// base != 0: offsets[0..n] are a sub-range of a larger CSR index (u64 only); chars is the larger array's start
 static rf_status corpus_create_host(const uint8_t* chars, const void* offsets, bool in64, uint64_t n, int device,
-                                    rf_corpus** out) {
+                                    rf_corpus** out, uint64_t base = 0) {
   if (!out) return fail(RF_ERR_INVALID_ARG, "out is NULL");
   *out = nullptr;
   if (!offsets) return fail(RF_ERR_INVALID_ARG, "offsets is NULL");
   if (n >= 0xFFFFFFFFull) return fail(RF_ERR_UNSUPPORTED, "more than 2^32-2 candidates in one corpus");
   const uint64_t first = in64 ? ((const uint64_t*)offsets)[0] : ((const uint32_t*)offsets)[0];
-  const uint64_t total = in64 ? ((const uint64_t*)offsets)[n] : ((const uint32_t*)offsets)[n];
-  if (first != 0) return fail(RF_ERR_INVALID_ARG, "offsets[0] must be 0");
+  const uint64_t last = in64 ? ((const uint64_t*)offsets)[n] : ((const uint32_t*)offsets)[n];
+  if (first != base) return fail(RF_ERR_INVALID_ARG, "offsets[0] must be 0");
+  if (last < base) return fail(RF_ERR_INVALID_ARG, "offsets are not non-decreasing CSR starts ending at offsets[n]");
+  const uint64_t total = last - base;
   if (total && !chars) return fail(RF_ERR_INVALID_ARG, "chars is NULL");
+  chars = chars ? chars + base : chars;
   if (rf_device_count() <= device || device < 0) return fail(RF_ERR_CUDA, "no such CUDA device");
   DeviceGuard g(device);
   if (!g.ok) return fail(RF_ERR_CUDA, "cudaSetDevice failed");
@@ -264,7 +262,14 @@ static rf_status corpus_create_host(const uint8_t* chars, const void* offsets, b
   if (total) e = cudaMemcpyAsync(c->d_chars, chars, total, cudaMemcpyHostToDevice, st);
   uint64_t* tmp64 = nullptr;
   if (e == cudaSuccess) {
-    if (off64 == in64) {
+    if (base != 0) {  // sub-range (always u64 on the host): upload, then subtract the base on the GPU
+      e = dev_alloc(&tmp64, (n + 1) * 8, st);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(tmp64, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, st);
+      if (e == cudaSuccess) {
+        rebase_offsets<<<1024, 256, 0, st>>>(tmp64, base, c->d_off32, c->d_off64, n + 1);
+        e = cudaGetLastError();
+      }
+    } else if (off64 == in64) {
       e = cudaMemcpyAsync(off64 ? (void*)c->d_off64 : (void*)c->d_off32, offsets, (n + 1) * (in64 ? 8 : 4),
                           cudaMemcpyHostToDevice, st);
     } else if (in64) {  // u64 on the host, u32 on the device: upload then narrow on the GPU
@@ -380,7 +385,7 @@ rf_status rf_corpus_create_u32(const uint32_t* elems, const uint64_t* offsets, u
   dev_free(tmp64, st);
   if (e != cudaSuccess) { rf_corpus_destroy(c); return cuda_fail(e, "u32 corpus upload"); }
   {
-    rf_status vs = check_offsets(off64 ? (const void*)c->d_off64 : (const void*)c->d_off32, off64, n, total, st);
+    rf_status vs = check_offsets(off64 ? (const void*)c->d_off64 : (const void*)c->d_off32, off64, n, total, st, &c->max_len);
     if (vs != RF_OK) { rf_corpus_destroy(c); return vs; }
   }
   if (g_compact32.load() && total) {
@@ -452,7 +457,11 @@ static rf_status batch_create_bytes(rf_metric metric, const uint8_t* query, uint
   const size_t szp8 = (szp + 7) & ~(size_t)7;
   const size_t szq = (size_t)kQuotDim * kQuotDim * sizeof(double);  // exact a/b for a,b <= 64 (Jaro epilogue)
   const size_t szb = ((size_t)query_len + 15) / 16 * 16 + 16;      // the query bytes themselves (hamming / prefix / postfix)
-  std::vector<uint8_t> blob(2 * sz32 + 2 * sz64 + szw + szp8 + szq + szb, 0);
+  // queries of 65..512 elements: the match vectors as integers of `limbs` 32-bit limbs (scan_lbn_kernel)
+  const uint32_t limbs = (query_len > 64 && query_len <= 512) ? 4 * ((query_len + 127) / 128) : 0;
+  const size_t szn = (size_t)256 * limbs * sizeof(uint32_t);
+  const size_t off_n = 2 * sz32 + 2 * sz64 + szw + szp8 + szq + szb;
+  std::vector<uint8_t> blob(off_n + 2 * szn, 0);
   if (query_len) memcpy(blob.data() + 2 * sz32 + 2 * sz64 + szw + szp8 + szq, query, query_len);
   uint32_t* t32t = (uint32_t*)blob.data();
   uint32_t* t32b = t32t + 256;
@@ -478,6 +487,20 @@ static rf_status batch_create_bytes(rf_metric metric, const uint8_t* query, uint
     for (int a = 0; a < kQuotDim; ++a)
       for (int d = 1; d < kQuotDim; ++d) quot[a * kQuotDim + d] = (double)a / (double)d;
   }
+  if (limbs) {
+    uint32_t* top = (uint32_t*)(blob.data() + off_n);
+    uint32_t* bot = top + (size_t)256 * limbs;
+    const uint32_t sh = 32 * limbs - query_len, ws = sh / 32, bs = sh % 32;
+    for (int ch = 0; ch < 256; ++ch) {
+      uint32_t* bt = bot + (size_t)ch * limbs;
+      for (uint32_t j = 0; j < limbs && j < 2 * words; ++j) bt[j] = (uint32_t)(pmw[(size_t)ch * words + j / 2] >> (32 * (j % 2)));
+      uint32_t* tp = top + (size_t)ch * limbs;
+      for (uint32_t i = ws; i < limbs; ++i) {
+        const uint32_t a = bt[i - ws], c = (i > ws) ? bt[i - ws - 1] : 0u;
+        tp[i] = bs ? ((a << bs) | (c >> (32 - bs))) : a;
+      }
+    }
+  }
   cudaError_t e = cudaMalloc(&b->d_blob, blob.size());
   // NOT cudaMemcpy: from pageable memory it may return once the data is staged, before the DMA has landed, and the
   // scoring kernels run on non-blocking streams that do not order against the legacy stream.
@@ -494,6 +517,9 @@ static rf_status batch_create_bytes(rf_metric metric, const uint8_t* query, uint
   b->view.band_stride = bstride;
   b->view.quot = (const double*)(b->d_blob + 2 * sz32 + 2 * sz64 + szw + szp8);
   b->view.qbytes = b->d_blob + 2 * sz32 + 2 * sz64 + szw + szp8 + szq;
+  b->view.limbs = limbs;
+  b->view.pmn_top = limbs ? (const uint32_t*)(b->d_blob + off_n) : nullptr;
+  b->view.pmn_bot = limbs ? b->view.pmn_top + (size_t)256 * limbs : nullptr;
   *out = b;
   return RF_OK;
 }
@@ -633,9 +659,14 @@ static rf_status score_view(const rf_batch* b, const CorpusView& cv, const LbAll
     e = !use_lb ? launch_scan_w1(L) : path == 2 ? launch_scan_lbr(L) : launch_scan_lb(L);
   }
   else if (fam == F_JARO) e = launch_jaro_mw(L);
+  else if (use_lb && L.query.limbs && g_mw_path.load() == 0 &&
+           !(g_band.load() && L.epi.metric == M_LEVENSHTEIN && L.epi.wclass == WC_UNIFORM && L.epi.kind == K_DISTANCE &&
+             L.epi.has_cutoff && L.epi.cutoff_u / L.epi.w_ins <= 63))
+    e = launch_scan_lbn(L);  // 65..512 elements on a resident corpus: thread per candidate, column in registers
   else if (g_band.load() && L.epi.metric == M_LEVENSHTEIN && L.epi.wclass == WC_UNIFORM && L.epi.kind == K_DISTANCE &&
            L.epi.has_cutoff && L.epi.cutoff_u / L.epi.w_ins <= 63)
     e = launch_scan_band(L, (uint32_t)(L.epi.cutoff_u / L.epi.w_ins));  // small cutoff: 64-bit Ukkonen band per thread
+  else if (L.query.words > 256) e = launch_scan_long(L);  // beyond 16 384 elements: column in stripes, carries through scratch
   else e = launch_scan_mw(L);
   if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
   return RF_OK;
@@ -812,7 +843,7 @@ static rf_status score_device(const rf_batch* b, const rf_corpus* c, rf_kind kin
     if (b->device != c->device) return fail(RF_ERR_INVALID_ARG, "batch and corpus live on different devices");
     const rf_batch* sub = compact_sub(b, c);
     if (!sub) return RF_ERR_CUDA;  // message set by the failing call
-    return score_view(sub, CorpusView{c->d_chars, c->d_off32, c->d_off64, c->n, c->total}, &c->lb, c->device, kind, args,
+    return score_view(sub, CorpusView{c->d_chars, c->d_off32, c->d_off64, c->n, c->total, c->max_len}, &c->lb, c->device, kind, args,
                       out_dev, want_f64, st, d_err);
   }
   if (b->wide) {
@@ -833,13 +864,13 @@ static rf_status score_device(const rf_batch* b, const rf_corpus* c, rf_kind kin
       e = cudaGetLastError();
       rfk::count_launches(1);
     }
-    rf_status s = (e == cudaSuccess) ? score_view(b, CorpusView{d_bytes, c->d_off32, c->d_off64, c->n, c->total}, nullptr, c->device,
+    rf_status s = (e == cudaSuccess) ? score_view(b, CorpusView{d_bytes, c->d_off32, c->d_off64, c->n, c->total, c->max_len}, nullptr, c->device,
                                                   kind, args, out_dev, want_f64, st, d_err)
                                      : cuda_fail(e, "alphabet renaming");
     dev_free(d_bytes, st);
     return s;
   }
-  return score_view(b, CorpusView{c->d_chars, c->d_off32, c->d_off64, c->n, c->total}, &c->lb, c->device, kind, args,
+  return score_view(b, CorpusView{c->d_chars, c->d_off32, c->d_off64, c->n, c->total, c->max_len}, &c->lb, c->device, kind, args,
                     out_dev, want_f64, st, d_err);
 }
 
@@ -1061,7 +1092,7 @@ cudaError_t stream_ctx_prepare(StreamCtx* x, uint64_t cap_bytes, uint64_t cap_n)
 
 template <class OffT>
 rf_status stream_impl(const rf_batch* b, const uint8_t* chars, const OffT* offsets, uint64_t n, rf_kind kind,
-                      const rf_args* args, void* out_host, bool want_f64) {
+                      const rf_args* args, void* out_host, bool want_f64, bool sub_range = false) {
   if (!b) return fail(RF_ERR_INVALID_ARG, "NULL handle");
   if ((int)kind < 0 || (int)kind > 3) return fail(RF_ERR_INVALID_ARG, "unknown kind");
   if ((rf_result_is_float(b->metric, kind) != 0) != want_f64)
@@ -1069,7 +1100,7 @@ rf_status stream_impl(const rf_batch* b, const uint8_t* chars, const OffT* offse
                                              : "this (metric, kind) yields f64 results; use the _f64 entry point");
   if (n == 0) return RF_OK;
   if (!offsets || !out_host) return fail(RF_ERR_INVALID_ARG, "NULL argument");
-  if (offsets[0] != 0) return fail(RF_ERR_INVALID_ARG, "offsets[0] must be 0");
+  if (offsets[0] != 0 && !sub_range) return fail(RF_ERR_INVALID_ARG, "offsets[0] must be 0");
   if (offsets[n] && !chars) return fail(RF_ERR_INVALID_ARG, "chars is NULL");
   if (rf_device_count() <= b->device) return fail(RF_ERR_CUDA, "no such CUDA device");
   DeviceGuard g(b->device);
@@ -1304,3 +1335,35 @@ rf_status rf_topk_merge_device(const uint32_t* idx_parts, const uint32_t* dist_p
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ internal (rf_sharded.cu)
+namespace rfi {
+rf_status fail(rf_status s, const std::string& msg) { return ::fail(s, msg); }
+rf_status cuda_fail(cudaError_t e, const char* what) { return ::cuda_fail(e, what); }
+const std::string& last_error() { return g_last_error; }
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+rf_status score_device(const rf_batch* b, const rf_corpus* c, rf_kind kind, const rf_args* args, void* out_dev, bool want_f64,
+                       cudaStream_t st, uint32_t* d_err) {
+  return ::score_device(b, c, kind, args, out_dev, want_f64, st, d_err);
+}
+rf_status cdist(const uint8_t* q_chars, const uint64_t* q_offsets, uint32_t nq, const rf_corpus* c, const rf_args* args, uint32_t k,
+                uint32_t* idx_out, uint32_t* dist_out, bool out_on_device, cudaStream_t stream) {
+  return ::cdist_impl(q_chars, q_offsets, nq, c, args, k, idx_out, dist_out, out_on_device, stream);
+}
+rf_status select_host(const rf_batch* b, const rf_corpus* c, rf_kind kind, const rf_args* args, bool want_f64, bool filter, uint32_t k,
+                      uint64_t cap, uint32_t* idx_out, void* score_out, uint32_t* n32_out, uint64_t* n64_out) {
+  return ::select_host(b, c, kind, args, want_f64, filter, k, cap, idx_out, score_out, n32_out, n64_out);
+}
+rf_status stream_u64(const rf_batch* b, const uint8_t* chars, const uint64_t* offsets, uint64_t n, rf_kind kind, const rf_args* args,
+                     void* out_host, bool want_f64) {
+  return stream_impl(b, chars, offsets, n, kind, args, out_host, want_f64, true);
+}
+rf_status stream_u32(const rf_batch* b, const uint8_t* chars, const uint32_t* offsets, uint64_t n, rf_kind kind, const rf_args* args,
+                     void* out_host, bool want_f64) {
+  return stream_impl(b, chars, offsets, n, kind, args, out_host, want_f64, true);
+}
+int sm_count_of(int device) { return ::sm_count_of(device); }
+rf_status corpus_create_sub(const uint8_t* chars, const uint64_t* offsets, uint64_t lo, uint64_t hi, int device, rf_corpus** out) {
+  return ::corpus_create_host(chars, offsets + lo, true, hi - lo, device, out, offsets[lo]);
+}
+}  // namespace rfi

@@ -2079,6 +2079,555 @@ cudaError_t launch_scan_mw(const ScanLaunch& L) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------ lbn
+// Multi-word queries of 65..512 elements over the interleaved layout: ONE THREAD per candidate, warp per group of 32
+// equal-length candidates like scan_lb_kernel, the whole column of the bit-parallel recurrence in registers.
+// (The reference walks the 64-bit blocks of the column one by one with the carries in locals, hyrroe2003_block,
+// levenshtein.rs:838-875 / lcs_blockwise, lcs_seq.rs:267-341; scan_mw_kernel spreads the blocks over the lanes of a
+// sub-warp and pays a shuffle per step.)  Formulation: the column is ONE integer of L = 4Q 32-bit limbs (Q = 1..4),
+// pattern TOP-aligned in it, so the single-word recurrence of lev_w1 applies unchanged and the distance is
+// n + popc(VP) - popc(VN) at the end -- no per-block score bookkeeping (levenshtein.rs:885-895).  Per limb and text
+// character: 7 LOP3 + 1 IADD3.X (the add of the recurrence as one carry chain) on the ALU pipe, the two 1-bit shifts
+// as IMAD.WIDE (bit 31 falls out as the product's high word) + add on the FMA pipe.
+// Match table in shared memory: Q planes of 32 KB, plane q holds limbs 4q..4q+3 of every symbol as one 16-byte
+// vector, replicated 8x ([ch][slot][4 limbs], slot = lane & 7) so that each quarter-warp of an LDS.128 hits 8
+// different bank groups whatever the 8 symbols are: conflict-free gather, one IDP.4A address for all planes.
+template <int L>
+__device__ __forceinline__ void add_chain(uint32_t (&s)[L], const uint32_t (&a)[L], const uint32_t (&b)[L]);
+template <>
+__device__ __forceinline__ void add_chain<4>(uint32_t (&s)[4], const uint32_t (&a)[4], const uint32_t (&b)[4]) {
+  asm("{\n\t"
+      "add.cc.u32 %0, %4, %8;\n\t"
+      "addc.cc.u32 %1, %5, %9;\n\t"
+      "addc.cc.u32 %2, %6, %10;\n\t"
+      "addc.u32 %3, %7, %11;\n\t"
+      "}"
+      : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]),
+        "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]));
+}
+template <>
+__device__ __forceinline__ void add_chain<8>(uint32_t (&s)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+  asm("{\n\t"
+      "add.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32 %7, %15, %23;\n\t"
+      "}"
+      : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+        "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+}
+template <>
+__device__ __forceinline__ void add_chain<12>(uint32_t (&s)[12], const uint32_t (&a)[12], const uint32_t (&b)[12]) {
+  asm("{\n\t"
+      "add.cc.u32 %0, %12, %24;\n\t"
+      "addc.cc.u32 %1, %13, %25;\n\t"
+      "addc.cc.u32 %2, %14, %26;\n\t"
+      "addc.cc.u32 %3, %15, %27;\n\t"
+      "addc.cc.u32 %4, %16, %28;\n\t"
+      "addc.cc.u32 %5, %17, %29;\n\t"
+      "addc.cc.u32 %6, %18, %30;\n\t"
+      "addc.cc.u32 %7, %19, %31;\n\t"
+      "addc.cc.u32 %8, %20, %32;\n\t"
+      "addc.cc.u32 %9, %21, %33;\n\t"
+      "addc.cc.u32 %10, %22, %34;\n\t"
+      "addc.u32 %11, %23, %35;\n\t"
+      "}"
+      : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7]), "=r"(s[8]), "=r"(s[9]), "=r"(s[10]), "=r"(s[11])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(a[8]), "r"(a[9]), "r"(a[10]), "r"(a[11]),
+        "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]), "r"(b[8]), "r"(b[9]), "r"(b[10]), "r"(b[11]));
+}
+template <>
+__device__ __forceinline__ void add_chain<16>(uint32_t (&s)[16], const uint32_t (&a)[16], const uint32_t (&b)[16]) {
+  asm("{\n\t"
+      "add.cc.u32 %0, %16, %32;\n\t"
+      "addc.cc.u32 %1, %17, %33;\n\t"
+      "addc.cc.u32 %2, %18, %34;\n\t"
+      "addc.cc.u32 %3, %19, %35;\n\t"
+      "addc.cc.u32 %4, %20, %36;\n\t"
+      "addc.cc.u32 %5, %21, %37;\n\t"
+      "addc.cc.u32 %6, %22, %38;\n\t"
+      "addc.cc.u32 %7, %23, %39;\n\t"
+      "addc.cc.u32 %8, %24, %40;\n\t"
+      "addc.cc.u32 %9, %25, %41;\n\t"
+      "addc.cc.u32 %10, %26, %42;\n\t"
+      "addc.cc.u32 %11, %27, %43;\n\t"
+      "addc.cc.u32 %12, %28, %44;\n\t"
+      "addc.cc.u32 %13, %29, %45;\n\t"
+      "addc.cc.u32 %14, %30, %46;\n\t"
+      "addc.u32 %15, %31, %47;\n\t"
+      "}"
+      : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7]), "=r"(s[8]), "=r"(s[9]), "=r"(s[10]), "=r"(s[11]), "=r"(s[12]), "=r"(s[13]), "=r"(s[14]), "=r"(s[15])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(a[8]), "r"(a[9]), "r"(a[10]), "r"(a[11]), "r"(a[12]), "r"(a[13]), "r"(a[14]), "r"(a[15]),
+        "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]), "r"(b[8]), "r"(b[9]), "r"(b[10]), "r"(b[11]), "r"(b[12]), "r"(b[13]), "r"(b[14]), "r"(b[15]));
+}
+
+template <int OFF>
+__device__ __forceinline__ void lds128_off(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+  asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+%5];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr), "n"(OFF));
+}
+template <int Q>
+__device__ __forceinline__ void pmn_load(uint32_t addr, uint32_t (&X)[4 * Q]) {
+  lds128_off<0>(addr, X[0], X[1], X[2], X[3]);
+  if constexpr (Q > 1) lds128_off<32768>(addr, X[4], X[5], X[6], X[7]);
+  if constexpr (Q > 2) lds128_off<65536>(addr, X[8], X[9], X[10], X[11]);
+  if constexpr (Q > 3) lds128_off<98304>(addr, X[12], X[13], X[14], X[15]);
+}
+// x * 2 as {low word, bit that falls out}: IMAD.WIDE.U32 (`two` is opaque to ptxas, so it stays on the FMA pipe)
+__device__ __forceinline__ void mul2_wide(uint32_t x, uint32_t two, uint32_t& lo, uint32_t& hi) {
+  asm("{\n\t.reg .b64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo), "=r"(hi) : "r"(x), "r"(two));
+}
+
+template <int Q, bool OSA>
+struct LevNStep {
+  static constexpr int L = 4 * Q;
+  uint32_t VP[L], VN[L];
+  uint32_t D0p[OSA ? L : 1], Xp[OSA ? L : 1];
+  uint32_t base, two;
+  __device__ __forceinline__ void init(uint32_t len1, uint32_t base_, uint32_t two_) {
+    base = base_;
+    two = two_;
+    const uint32_t sh = 32u * L - len1;  // unused low bits
+#pragma unroll
+    for (int i = 0; i < L; ++i) {
+      VP[i] = (32u * (i + 1) <= sh) ? 0u : (32u * i >= sh ? 0xFFFFFFFFu : 0xFFFFFFFFu << (sh - 32u * i));
+      VN[i] = 0;
+    }
+    if constexpr (OSA) {
+#pragma unroll
+      for (int i = 0; i < L; ++i) { D0p[i] = 0; Xp[i] = 0; }
+    }
+  }
+  template <int K>
+  __device__ __forceinline__ void step(uint32_t w) {
+    uint32_t X[L], T[L], S[L];
+    pmn_load<Q>(__dp4a(w, 0x80u << (8 * K), base), X);
+#pragma unroll
+    for (int i = 0; i < L; ++i) T[i] = X[i] & VP[i];
+    add_chain<L>(S, T, VP);
+    uint32_t cp = two >> 1, cn = 0, ct = 0;  // +1 enters row 0 (through the unused low bits)
+#pragma unroll
+    for (int i = 0; i < L; ++i) {
+      uint32_t D0 = ((S[i] ^ VP[i]) | X[i]) | VN[i];
+      if constexpr (OSA) {  // TR = (((~D0_prev) & X) << 1) & X_prev  (osa.rs:84-135), the shift across the limbs
+        const uint32_t t = ~D0p[i] & X[i];
+        uint32_t lo, hi;
+        if (i < L - 1) { mul2_wide(t, two, lo, hi); lo += ct; ct = hi; }
+        else lo = t * two + ct;
+        D0 |= lo & Xp[i];
+        D0p[i] = D0;
+        Xp[i] = X[i];
+      }
+      const uint32_t HP = VN[i] | ~(D0 | VP[i]);
+      const uint32_t HN = D0 & VP[i];
+      uint32_t HPs, HNs;
+      if (i < L - 1) {
+        uint32_t lo, hi;
+        mul2_wide(HP, two, lo, hi);
+        HPs = lo + cp;
+        cp = hi;
+        mul2_wide(HN, two, lo, hi);
+        HNs = lo + cn;
+        cn = hi;
+      } else {
+        HPs = HP * two + cp;
+        HNs = HN * two + cn;
+      }
+      VP[i] = HNs | ~(D0 | HPs);
+      VN[i] = HPs & D0;
+    }
+  }
+  __device__ __forceinline__ uint32_t result(uint32_t len2) const {
+    uint32_t r = len2;
+#pragma unroll
+    for (int i = 0; i < L; ++i) r += (uint32_t)__popc(VP[i]) - (uint32_t)__popc(VN[i]);
+    return r;
+  }
+};
+
+// LCS length (lcs_seq.rs:199-261, :267-341) on the same limbs, bottom-aligned table: S = (S + U) | (S & ~U), U = S & X.
+template <int Q>
+struct LcsNStep {
+  static constexpr int L = 4 * Q;
+  uint32_t S[L];
+  uint32_t base;
+  __device__ __forceinline__ void init(uint32_t, uint32_t base_, uint32_t) {
+    base = base_;
+#pragma unroll
+    for (int i = 0; i < L; ++i) S[i] = 0xFFFFFFFFu;
+  }
+  template <int K>
+  __device__ __forceinline__ void step(uint32_t w) {
+    uint32_t X[L], U[L], A[L];
+    pmn_load<Q>(__dp4a(w, 0x80u << (8 * K), base), X);
+#pragma unroll
+    for (int i = 0; i < L; ++i) U[i] = S[i] & X[i];
+    add_chain<L>(A, S, U);
+#pragma unroll
+    for (int i = 0; i < L; ++i) S[i] = A[i] | (S[i] & ~U[i]);
+  }
+  __device__ __forceinline__ uint32_t result(uint32_t) const {
+    uint32_t r = 0;
+#pragma unroll
+    for (int i = 0; i < L; ++i) r += (uint32_t)__popc(~S[i]);
+    return r;
+  }
+};
+
+template <int FAM, int Q, int NT>
+__global__ void __launch_bounds__(NT) scan_lbn_kernel(const __grid_constant__ LbParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int L = 4 * Q;
+  {
+    // p.tab: [256][L] u32 limbs of the (top- or bottom-aligned) match vectors -> Q planes, 8 replicas per symbol
+    const uint32_t* __restrict__ t = reinterpret_cast<const uint32_t*>(p.tab);
+    uint32_t* pm32 = reinterpret_cast<uint32_t*>(smem_raw);
+    for (uint32_t i = threadIdx.x; i < 256u * L * 8u; i += NT) {
+      const uint32_t ch = i / (L * 8u), r = i % (L * 8u), slot = r / L, limb = r % L;
+      pm32[(limb >> 2) * 8192u + ch * 32u + slot * 4u + (limb & 3u)] = t[ch * L + limb];
+    }
+  }
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t base = smem_u32(smem_raw) + (lane & 7u) * 16u;
+  const uint64_t total_warps = (uint64_t)gridDim.x * (NT / 32);
+  const uint64_t ngroups = p.lb.ngroups;
+  const uint64_t nchunks = (ngroups + p.chunk - 1) / p.chunk;
+  const uint2* __restrict__ gdata = reinterpret_cast<const uint2*>(p.lb.gdata);
+  uint64_t chunk = (uint64_t)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
+  while (chunk < nchunks) {
+    unsigned long long next_chunk = 0;
+    if (lane == 0) next_chunk = total_warps + atomicAdd(p.counter, 1ull);
+    const uint64_t g0 = chunk * p.chunk;
+    const uint32_t ng = (uint32_t)((g0 + p.chunk < ngroups) ? p.chunk : ngroups - g0);
+    const uint32_t* lens_p = p.lb.lens + g0 * 32 + lane;
+    const uint32_t* perm_p = p.lb.perm + g0 * 32 + lane;
+    const uint2* grp = gdata + __ldg(p.lb.goff + g0) * 32 + lane;
+    uint32_t len_n = __ldg(lens_p);
+    uint2 first_n = ld_row8<true>(grp);
+    uint2 second_n = ld_row8<true>(grp + 32);
+    for (uint32_t gi = 0; gi < ng; ++gi) {
+      const uint32_t len2 = len_n;
+      const uint32_t idx = __ldg(perm_p);
+      const LaneSrcT<true> src{grp, first_n, second_n};
+      grp += ((__reduce_max_sync(0xffffffffu, len2) + 7u) >> 3) * 32u;
+      lens_p += 32;
+      perm_p += 32;
+      if (gi + 1 < ng) {
+        len_n = __ldg(lens_p);
+        first_n = ld_row8<true>(grp);
+        second_n = ld_row8<true>(grp + 32);
+      }
+      uint32_t raw;
+      if constexpr (FAM == F_LCS) {
+        LcsNStep<Q> st;
+        st.init(p.len1, base, p.two);
+        walk_rows8(src.reader(), len2, st);
+        raw = st.result(len2);
+      } else {
+        LevNStep<Q, FAM == F_OSA> st;
+        st.init(p.len1, base, p.two);
+        walk_rows8(src.reader(), len2, st);
+        raw = st.result(len2);
+      }
+      if (idx != 0xFFFFFFFFu) {
+        if (p.out_f64) reinterpret_cast<double*>(p.out)[idx] = finish_norm(p.epi, raw, p.len1, len2);
+        else reinterpret_cast<uint32_t*>(p.out)[idx] = finish_int(p.epi, raw, p.len1, len2);
+      }
+    }
+    chunk = __shfl_sync(0xffffffffu, next_chunk, 0);
+  }
+}
+
+template <int FAM, int Q>
+static cudaError_t launch_lbn_inst(const ScanLaunch& L, const void* tab) {
+  constexpr int NT = 256;
+  auto kern = scan_lbn_kernel<FAM, Q, NT>;
+  const size_t smem = (size_t)Q * 32768;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
+  int ctas_per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, NT, smem);
+  if (e != cudaSuccess) return e;
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  LbParams p{};
+  p.lb = L.lb;
+  p.tab = tab;
+  p.len1 = L.query.len1;
+  p.out = L.out;
+  p.out_f64 = L.out_is_f64;
+  p.two = 2;
+  p.chunk = 4;
+  p.counter = L.lb_counter;
+  p.epi = L.epi;
+  e = cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), L.stream);
+  if (e != cudaSuccess) return e;
+  uint64_t grid = (uint64_t)L.sm_count * ctas_per_sm;
+  const uint64_t nchunks = (L.lb.ngroups + p.chunk - 1) / p.chunk;
+  const uint64_t need = (nchunks + NT / 32 - 1) / (NT / 32);
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  kern<<<(uint32_t)grid, NT, smem, L.stream>>>(p);
+  g_launches.fetch_add(1);
+  return cudaGetLastError();
+}
+
+template <int FAM>
+static cudaError_t launch_lbn_fam(const ScanLaunch& L, const void* tab) {
+  switch (L.query.limbs / 4) {
+    case 1: return launch_lbn_inst<FAM, 1>(L, tab);
+    case 2: return launch_lbn_inst<FAM, 2>(L, tab);
+    case 3: return launch_lbn_inst<FAM, 3>(L, tab);
+    case 4: return launch_lbn_inst<FAM, 4>(L, tab);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t launch_scan_lbn(const ScanLaunch& L) {
+  if (!L.query.pmn_top || !L.lb.gdata) return cudaErrorInvalidValue;
+  switch (family_of(L.epi.metric, L.epi.wclass)) {
+    case F_LEV: return launch_lbn_fam<F_LEV>(L, L.query.pmn_top);
+    case F_OSA: return launch_lbn_fam<F_OSA>(L, L.query.pmn_top);
+    case F_LCS: return launch_lbn_fam<F_LCS>(L, L.query.pmn_bot);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ long
+// Queries beyond 16 384 elements (the reference has no limit: its own test_large_band runs 106 514 x 107 244,
+// levenshtein.rs:2139-2161).  One warp per candidate, the column cut into STRIPES of 256 64-bit blocks (lane l owns
+// blocks 8l..8l+7 of the stripe, columns skewed across the lanes exactly as in scan_mw_kernel).  A stripe is run over
+// the whole candidate; the horizontal deltas leaving its bottom row (hp, hn, OSA's transposition bit / the LCS add
+// carry: one byte per column) are parked in a per-warp scratch line and enter the next stripe's top row, which plays
+// the role of the reference's hp_carry / hn_carry between blocks (levenshtein.rs:838-875) at stripe granularity.
+struct LongParams {
+  const uint8_t* chars;
+  const uint32_t* off32;
+  const uint64_t* off64;
+  uint64_t n;
+  const uint64_t* pm;  // [256][words]
+  uint32_t len1;
+  uint32_t words;
+  uint8_t* scratch;         // [warps][stride] carry bytes
+  uint64_t stride;
+  void* out;
+  int out_f64;
+  Epi epi;
+};
+
+template <int FAM>
+__global__ void __launch_bounds__(128) scan_long_kernel(const __grid_constant__ LongParams p) {
+  constexpr int WPL = 8;
+  constexpr uint32_t SW = 32 * WPL;  // blocks per stripe
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint64_t warp_global = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const uint64_t total_warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+  const uint32_t words = p.words;
+  const uint32_t nstripes = (words + SW - 1) / SW;
+  const uint32_t last_bit = (p.len1 - 1u) & 63u;
+  const bool off64 = p.off64 != nullptr;
+  const uint64_t* __restrict__ pm = p.pm;
+  uint8_t* carry = p.scratch + warp_global * p.stride;
+  const bool lev_cut = (FAM == F_LEV) && p.epi.metric == M_LEVENSHTEIN && p.epi.kind == K_DISTANCE && p.epi.has_cutoff &&
+                       p.epi.wclass == WC_UNIFORM;
+  const uint64_t cut64 = lev_cut ? p.epi.cutoff_u / p.epi.w_ins : 0;
+
+  for (uint64_t c = warp_global; c < p.n; c += total_warps) {
+    const uint64_t o0 = off64 ? p.off64[c] : (uint64_t)p.off32[c];
+    const uint64_t o1 = off64 ? p.off64[c + 1] : (uint64_t)p.off32[c + 1];
+    const uint32_t len2 = (uint32_t)(o1 - o0);
+    const uint32_t diff = p.len1 > len2 ? p.len1 - len2 : len2 - p.len1;
+    if (lev_cut && (uint64_t)diff > cut64) {  // levenshtein.rs:1045-1047
+      if (lane == 0) {
+        if (p.out_f64) reinterpret_cast<double*>(p.out)[c] = qnan();
+        else reinterpret_cast<uint32_t*>(p.out)[c] = NONE_U32;
+      }
+      continue;
+    }
+    if (len2 == 0) {
+      const uint32_t raw0 = (FAM == F_LCS) ? 0u : p.len1;
+      if (lane == 0) {
+        if (p.out_f64) reinterpret_cast<double*>(p.out)[c] = finish_norm(p.epi, raw0, p.len1, 0);
+        else reinterpret_cast<uint32_t*>(p.out)[c] = finish_int(p.epi, raw0, p.len1, 0);
+      }
+      continue;
+    }
+    const uint8_t* __restrict__ txt = p.chars + o0;
+    int32_t score = 0;
+    uint32_t lcs_cnt = 0;
+    for (uint32_t s = 0; s < nstripes; ++s) {
+      const uint32_t sw0 = s * SW;                                       // first block of the stripe
+      const uint32_t swords = words - sw0 < SW ? words - sw0 : SW;      // blocks in this stripe
+      const uint32_t act = (swords + WPL - 1) / WPL;                     // lanes that own at least one block
+      const uint32_t w0 = sw0 + lane * WPL;
+      const bool last_stripe = s + 1 == nstripes;
+      const uint32_t last_owner = (swords - 1) / WPL, last_k = (swords - 1) % WPL;
+      const uint32_t steps = len2 + act - 1u;
+      uint64_t VP[WPL], VN[WPL], D0[WPL], PMo[WPL], Xc[WPL], Xn[WPL];
+#pragma unroll
+      for (int k = 0; k < WPL; ++k) {
+        VP[k] = ~0ull;  // LCS: VP plays the role of S
+        VN[k] = 0; D0[k] = 0; PMo[k] = 0; Xc[k] = 0; Xn[k] = 0;
+      }
+      // lane 0 feeds the text and the carries entering the stripe's top row, both fetched three columns ahead
+      const uint32_t top0 = (FAM == F_LCS) ? 0u : 1u;  // matrix top row: horizontal delta +1 (Levenshtein / OSA), no carry (LCS)
+      uint32_t ch_cur = 0, c1 = 0, c2 = 0, in0 = top0, in1 = top0, in2 = top0;
+      if (lane == 0) {
+        ch_cur = txt[0];
+        c1 = len2 > 1 ? txt[1] : 0;
+        c2 = len2 > 2 ? txt[2] : 0;
+        if (s > 0) {
+          in0 = __ldcg(carry + 0);
+          in1 = len2 > 1 ? __ldcg(carry + 1) : 0;
+          in2 = len2 > 2 ? __ldcg(carry + 2) : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < WPL; ++k) Xc[k] = (w0 + k < words) ? __ldg(pm + (uint64_t)ch_cur * words + w0 + k) : 0ull;
+      }
+      uint32_t cout = 0;
+      for (uint32_t t = 0; t < steps; ++t) {
+        const uint32_t pk_in = __shfl_up_sync(0xffffffffu, ch_cur | (cout << 8), 1);
+        uint32_t ch_nxt, cin;
+        if (lane == 0) {
+          ch_nxt = c1;
+          c1 = c2;
+          c2 = (t + 3 < len2) ? (uint32_t)txt[t + 3] : 0u;
+          cin = in0;
+          in0 = in1;
+          in1 = in2;
+          in2 = (s > 0 && t + 3 < len2) ? (uint32_t)__ldcg(carry + t + 3) : top0;
+        } else {
+          ch_nxt = pk_in & 0xffu;
+          cin = pk_in >> 8;
+        }
+#pragma unroll
+        for (int k = 0; k < WPL; ++k) Xn[k] = (w0 + k < words) ? __ldg(pm + (uint64_t)ch_nxt * words + w0 + k) : 0ull;
+        const int32_t j = (int32_t)t - (int32_t)lane;  // text column handled by this lane in this step
+        const bool active = (lane < act) && j >= 0 && j < (int32_t)len2;
+        if (active) {
+          if constexpr (FAM == F_LCS) {
+            uint64_t cy = cin & 1u;
+#pragma unroll
+            for (int k = 0; k < WPL; ++k) {
+              if (w0 + k < words) {
+                const uint64_t S = VP[k];
+                const uint64_t u = S & Xc[k];
+                const uint64_t x1 = S + u;
+                const uint64_t x2 = x1 + cy;
+                cy = (uint64_t)(x1 < S) | (uint64_t)(x2 < x1);
+                VP[k] = x2 | (S - u);
+              }
+            }
+            cout = (uint32_t)cy;
+          } else {
+            uint64_t hp_c = cin & 1u, hn_c = (cin >> 1) & 1u, tr_c = (cin >> 2) & 1u;
+#pragma unroll
+            for (int k = 0; k < WPL; ++k) {
+              if (w0 + k < words) {
+                const uint64_t X0 = Xc[k];
+                const uint64_t X = X0 | hn_c;
+                uint64_t d0 = ((((X & VP[k]) + VP[k]) ^ VP[k]) | X) | VN[k];
+                if constexpr (FAM == F_OSA) {
+                  const uint64_t nd = (~D0[k]) & X0;
+                  d0 |= ((nd << 1) | tr_c) & PMo[k];
+                  tr_c = nd >> 63;
+                  D0[k] = d0;
+                  PMo[k] = X0;
+                }
+                uint64_t HP = VN[k] | ~(d0 | VP[k]);
+                uint64_t HN = d0 & VP[k];
+                if (last_stripe && lane == last_owner && k == (int)last_k)
+                  score += (int32_t)((HP >> last_bit) & 1u) - (int32_t)((HN >> last_bit) & 1u);
+                const uint64_t hp_o = HP >> 63, hn_o = HN >> 63;
+                HP = (HP << 1) | hp_c;
+                HN = (HN << 1) | hn_c;
+                VP[k] = HN | ~(d0 | HP);
+                VN[k] = HP & d0;
+                hp_c = hp_o;
+                hn_c = hn_o;
+              }
+            }
+            cout = (uint32_t)hp_c | ((uint32_t)hn_c << 1) | ((uint32_t)tr_c << 2);
+          }
+          // the stripe's bottom row: park the deltas of column j for the next stripe (read there >= 29 steps of this
+          // loop later at the earliest for the same column -- it runs after this stripe has finished)
+          if (!last_stripe && lane == act - 1u) __stcg(carry + j, (uint8_t)cout);
+        }
+        ch_cur = ch_nxt;
+#pragma unroll
+        for (int k = 0; k < WPL; ++k) Xc[k] = Xn[k];
+      }
+      if constexpr (FAM == F_LCS) {
+#pragma unroll
+        for (int k = 0; k < WPL; ++k)
+          if (lane < act && w0 + k < words) lcs_cnt += (uint32_t)__popcll(~VP[k]);
+      }
+      if (last_stripe) score = __shfl_sync(0xffffffffu, score, last_owner);
+      __syncwarp();  // orders this stripe's carry stores before the next stripe's loads (same warp)
+    }
+    uint32_t raw;
+    if constexpr (FAM == F_LCS) {
+      for (uint32_t d = 16; d >= 1; d >>= 1) lcs_cnt += __shfl_xor_sync(0xffffffffu, lcs_cnt, d);
+      raw = lcs_cnt;
+    } else {
+      raw = (uint32_t)((int32_t)p.len1 + score);
+    }
+    if (lane == 0) {
+      if (p.out_f64) reinterpret_cast<double*>(p.out)[c] = finish_norm(p.epi, raw, p.len1, len2);
+      else reinterpret_cast<uint32_t*>(p.out)[c] = finish_int(p.epi, raw, p.len1, len2);
+    }
+  }
+}
+
+template <int FAM>
+static cudaError_t launch_long_fam(const ScanLaunch& L) {
+  LongParams p{};
+  p.chars = L.corpus.chars;
+  p.off32 = L.corpus.off32;
+  p.off64 = L.corpus.off64;
+  p.n = L.corpus.n;
+  p.pm = L.query.pm_words;
+  p.len1 = L.query.len1;
+  p.words = L.query.words;
+  p.out = L.out;
+  p.out_f64 = L.out_is_f64;
+  p.epi = L.epi;
+  // one carry byte per column and warp; no candidate is longer than the corpus.  The scratch is capped at 1 GiB, the
+  // grid follows (a warp per candidate up to that many warps)
+  uint64_t max_len = L.corpus.max_len ? L.corpus.max_len : L.corpus.total;
+  if (max_len > L.corpus.total) max_len = L.corpus.total;
+  p.stride = (max_len + 63) / 64 * 64 + 64;
+  uint64_t warps = (1ull << 30) / p.stride;
+  const uint64_t cap = (uint64_t)L.sm_count * 16;  // 4 CTAs of 4 warps per SM
+  if (warps > cap) warps = cap;
+  if (warps > p.n) warps = p.n;
+  if (warps < 1) warps = 1;
+  const uint32_t blocks = (uint32_t)((warps + 3) / 4);
+  cudaError_t e = dev_alloc(&p.scratch, (uint64_t)blocks * 4 * p.stride, L.stream);
+  if (e != cudaSuccess) return e;
+  scan_long_kernel<FAM><<<blocks, 128, 0, L.stream>>>(p);
+  g_launches.fetch_add(1);
+  e = cudaGetLastError();
+  dev_free(p.scratch, L.stream);
+  return e;
+}
+
+cudaError_t launch_scan_long(const ScanLaunch& L) {
+  switch (family_of(L.epi.metric, L.epi.wclass)) {
+    case F_LEV: return launch_long_fam<F_LEV>(L);
+    case F_OSA: return launch_long_fam<F_OSA>(L);
+    case F_LCS: return launch_long_fam<F_LCS>(L);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ band
 // Levenshtein distance with score_cutoff k <= 63 for multi-word queries (BASELINE config 3).  The Ukkonen band
 // of a cutoff-k problem has at most k+1 diagonals, so one 64-bit sliding window per candidate (LevBand64,

@@ -14,6 +14,7 @@ struct CorpusView {
   const uint64_t* off64;
   uint64_t n;
   uint64_t total;
+  uint64_t max_len;  // longest candidate, 0 = unknown (sizes per-warp scratch of the long-query kernels)
 };
 
 // One cached query (BatchComparator::new): compact match tables in device memory.
@@ -29,6 +30,11 @@ struct QueryView {
   uint32_t band_stride;      // (2*(words+2)) | 1
   const uint8_t* qbytes;     // the query itself, zero-padded to a multiple of 16 plus 16 (hamming / prefix / postfix)
   const double* quot;        // [65][65] exactly rounded a/b (b >= 1): the Jaro formula's quotients without divisions
+  // queries of 65..512 elements (scan_lbn_kernel): the match vectors as ONE integer of `limbs` = 4*ceil(len1/128)
+  // 32-bit limbs, little endian; top-aligned (PM << (32*limbs - len1): Levenshtein / OSA) and bottom-aligned (LCS family)
+  const uint32_t* pmn_top;   // [256][limbs] or null
+  const uint32_t* pmn_bot;   // [256][limbs] or null
+  uint32_t limbs;
 };
 
 // Length-bucketed, warp-interleaved copy of the corpus (built once at corpus creation, rf_layout.cu):
@@ -74,8 +80,12 @@ cudaError_t launch_scan_w1(const ScanLaunch& L);
 cudaError_t launch_scan_lb(const ScanLaunch& L);
 // Same layout, rows streamed by per-warp TMA bulk copies into a shared-memory ring (sequential metrics; Jaro falls back).
 cudaError_t launch_scan_lbr(const ScanLaunch& L);
+// Multi-word path, query 65..512, interleaved layout: thread per candidate, the whole column in registers.
+cudaError_t launch_scan_lbn(const ScanLaunch& L);
 // Multi-word path (query > 64): sub-warp per candidate, carries propagated with warp shuffles.
 cudaError_t launch_scan_mw(const ScanLaunch& L);
+// Queries beyond 16 384 elements: warp per candidate, the column in stripes of 256 blocks with the carries parked in scratch.
+cudaError_t launch_scan_long(const ScanLaunch& L);
 // Levenshtein distance with a cutoff of at most 63 unit edits, any query length: one 64-bit sliding band per candidate.
 cudaError_t launch_scan_band(const ScanLaunch& L, uint32_t cut);
 // Hamming / Prefix / Postfix (any query length): thread per candidate over the CSR corpus.

@@ -1,0 +1,523 @@
+// rf_sharded.cu -- one process, several GPUs: the candidate corpus sharded by candidate across the devices of one box
+// (SURVEY section 8e), behind the C ABI (include/rfgpu.h, "sharded" section).
+//
+// The reference's BatchComparator is plain data, Clone + Send + Sync (levenshtein.rs:1635-1639): a Rust host may drive it
+// from any thread over any slice of candidates.  Here the split is the library's job: contiguous candidate ranges
+// balanced by BYTES, one resident shard per device, the query's tables replicated, per-device streams.  Pairs are
+// independent, so the scan itself has no exchange step; the only collectives are the final ones the north star names:
+//   * all-gather of the per-shard score vectors when the caller wants the full vector on every device
+//     (shards have unequal counts -> one grouped ncclBroadcast per shard = all-gather-v, in place), and
+//   * all-gather of the per-shard top-k lists (equal sizes -> ncclAllGather, in place) + rf_topk_merge_device.
+// Host-destined results need no collective at all: every device copies its slice straight into the caller's vector.
+// Devices listed more than once (tests on a one-GPU box) cannot form an NCCL communicator; the same gathers then run
+// as device-to-device copies ordered by events ("sharded_collective" = 1 forces that path everywhere, for A/B timing).
+#include <cuda_runtime.h>
+#include <nccl.h>
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "rf_internal.h"
+
+using namespace rfk;
+
+static std::atomic<int> g_coll_mode{0};  // 0: NCCL when the devices are distinct, 1: always copies
+void rf__set_sharded_collective(int mode) { g_coll_mode.store(mode); }
+
+struct rf_sharded_corpus {
+  std::vector<int> devices;
+  std::vector<rf_corpus*> shard;
+  std::vector<uint64_t> lo;  // [ndev + 1] first candidate of every shard
+  uint64_t n = 0, total = 0;
+  bool distinct = true;
+  std::vector<cudaStream_t> streams;  // one per shard, on its device
+  std::vector<cudaEvent_t> events;
+  std::mutex coll_mu;                 // collectives on one set of communicators are issued by one thread at a time
+  bool comm_ready = false;
+  std::vector<ncclComm_t> comms;
+};
+
+struct rf_sharded_batch {
+  std::vector<int> devices;
+  std::vector<rf_batch*> per;
+  rf_metric metric = RF_LEVENSHTEIN;
+};
+
+namespace {
+
+struct DevGuard {
+  int prev = -1;
+  explicit DevGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    cudaSetDevice(dev);
+  }
+  ~DevGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+rf_status nccl_fail(ncclResult_t r, const char* what) {
+  return rfi::fail(RF_ERR_NCCL, std::string(what) + ": " + ncclGetErrorString(r));
+}
+
+// runs fn(i) for every shard on its own host thread (the per-shard entry points synchronise internally); the first
+// failure's status and message are re-raised on the calling thread
+template <class Fn>
+rf_status for_each_shard(size_t count, Fn fn) {
+  std::vector<rf_status> st(count, RF_OK);
+  std::vector<std::string> msg(count);
+  if (count == 1) {
+    return fn(0);
+  }
+  std::vector<std::thread> th;
+  th.reserve(count);
+  for (size_t i = 0; i < count; ++i)
+    th.emplace_back([&, i] {
+      st[i] = fn(i);
+      if (st[i] != RF_OK) msg[i] = rfi::last_error();
+    });
+  for (auto& t : th) t.join();
+  for (size_t i = 0; i < count; ++i)
+    if (st[i] != RF_OK) return rfi::fail(st[i], "shard " + std::to_string(i) + ": " + msg[i]);
+  return RF_OK;
+}
+
+bool use_nccl(const rf_sharded_corpus* c) { return c->distinct && g_coll_mode.load() == 0; }
+
+rf_status ensure_comms(rf_sharded_corpus* c) {
+  if (c->comm_ready) return RF_OK;
+  c->comms.assign(c->devices.size(), nullptr);
+  ncclResult_t r = ncclCommInitAll(c->comms.data(), (int)c->devices.size(), c->devices.data());
+  if (r != ncclSuccess) {
+    c->comms.clear();
+    return nccl_fail(r, "ncclCommInitAll");
+  }
+  c->comm_ready = true;
+  return RF_OK;
+}
+
+// In-place all-gather-v over the shards' streams: bufs[i] is device i's copy of the whole buffer; the bytes
+// [off[r], off[r+1]) are valid on device r and land on every device.  Work already enqueued on streams[r] (the scan that
+// produced shard r's slice) is ordered before the transfer.
+rf_status allgatherv_inplace(rf_sharded_corpus* c, void* const* bufs, const uint64_t* off) {
+  const int nd = (int)c->devices.size();
+  if (nd == 1) return RF_OK;
+  std::lock_guard<std::mutex> lk(c->coll_mu);
+  if (use_nccl(c)) {
+    rf_status s = ensure_comms(c);
+    if (s != RF_OK) return s;
+    ncclResult_t r = ncclGroupStart();
+    if (r != ncclSuccess) return nccl_fail(r, "ncclGroupStart");
+    for (int root = 0; root < nd && r == ncclSuccess; ++root) {
+      const uint64_t bytes = off[root + 1] - off[root];
+      if (!bytes) continue;
+      for (int i = 0; i < nd && r == ncclSuccess; ++i) {
+        char* p = (char*)bufs[i] + off[root];
+        r = ncclBroadcast(p, p, bytes, ncclUint8, root, c->comms[i], c->streams[i]);
+      }
+    }
+    ncclResult_t r2 = ncclGroupEnd();
+    if (r != ncclSuccess) return nccl_fail(r, "ncclBroadcast");
+    if (r2 != ncclSuccess) return nccl_fail(r2, "ncclGroupEnd");
+    return RF_OK;
+  }
+  // copies: device i pulls every other shard's slice once that shard's stream has produced it
+  for (int r = 0; r < nd; ++r) {
+    DevGuard g(c->devices[r]);
+    cudaError_t e = cudaEventRecord(c->events[r], c->streams[r]);
+    if (e != cudaSuccess) return rfi::cuda_fail(e, "cudaEventRecord");
+  }
+  for (int i = 0; i < nd; ++i) {
+    DevGuard g(c->devices[i]);
+    for (int r = 0; r < nd; ++r) {
+      if (r == i) continue;
+      const uint64_t bytes = off[r + 1] - off[r];
+      if (!bytes) continue;
+      cudaError_t e = cudaStreamWaitEvent(c->streams[i], c->events[r], 0);
+      if (e == cudaSuccess)
+        e = cudaMemcpyPeerAsync((char*)bufs[i] + off[r], c->devices[i], (const char*)bufs[r] + off[r], c->devices[r], bytes,
+                                c->streams[i]);
+      if (e != cudaSuccess) return rfi::cuda_fail(e, "peer copy");
+    }
+  }
+  return RF_OK;
+}
+
+rf_status sync_all(const rf_sharded_corpus* c) {
+  rf_status s = RF_OK;
+  for (size_t i = 0; i < c->devices.size(); ++i) {
+    DevGuard g(c->devices[i]);
+    cudaError_t e = cudaStreamSynchronize(c->streams[i]);
+    if (e != cudaSuccess && s == RF_OK) s = rfi::cuda_fail(e, "sharded stream synchronize");
+  }
+  return s;
+}
+
+rf_status check_pair(const rf_sharded_batch* b, const rf_sharded_corpus* c) {
+  if (!b || !c) return rfi::fail(RF_ERR_INVALID_ARG, "NULL handle");
+  if (b->devices != c->devices) return rfi::fail(RF_ERR_INVALID_ARG, "sharded batch and sharded corpus were made for different device lists");
+  return RF_OK;
+}
+
+// byte-balanced contiguous ranges: boundary s = first candidate starting at or after total * s / parts
+void split_by_bytes(const uint64_t* offsets, uint64_t n, size_t parts, std::vector<uint64_t>* lo) {
+  lo->assign(parts + 1, 0);
+  const uint64_t base = offsets[0], total = offsets[n] - base;
+  for (size_t s = 1; s < parts; ++s) {
+    uint64_t b;
+    if (total == 0) b = n * s / parts;
+    else b = (uint64_t)(std::lower_bound(offsets, offsets + n, base + (uint64_t)((unsigned __int128)total * s / parts)) - offsets);
+    (*lo)[s] = std::max(b, (*lo)[s - 1]);
+  }
+  (*lo)[parts] = n;
+}
+
+}  // namespace
+
+extern "C" {
+
+rf_status rf_corpus_create_sharded_u8(const uint8_t* chars, const uint64_t* offsets, uint64_t n, const int* devices, int ndev,
+                                      rf_sharded_corpus** out) {
+  if (!out) return rfi::fail(RF_ERR_INVALID_ARG, "out is NULL");
+  *out = nullptr;
+  if (!offsets) return rfi::fail(RF_ERR_INVALID_ARG, "offsets is NULL");
+  if (!devices || ndev < 1 || ndev > 64) return rfi::fail(RF_ERR_INVALID_ARG, "devices / ndev (1..64)");
+  if (offsets[0] != 0) return rfi::fail(RF_ERR_INVALID_ARG, "offsets[0] must be 0");
+  const int have = rf_device_count();
+  for (int i = 0; i < ndev; ++i)
+    if (devices[i] < 0 || devices[i] >= have) return rfi::fail(RF_ERR_CUDA, "no such CUDA device");
+  rf_sharded_corpus* c = new (std::nothrow) rf_sharded_corpus();
+  if (!c) return rfi::fail(RF_ERR_OOM, "host allocation failed");
+  c->devices.assign(devices, devices + ndev);
+  c->n = n;
+  c->total = offsets[n];
+  for (int i = 0; i < ndev; ++i)
+    for (int j = 0; j < i; ++j)
+      if (devices[i] == devices[j]) c->distinct = false;
+  split_by_bytes(offsets, n, (size_t)ndev, &c->lo);
+  c->shard.assign(ndev, nullptr);
+  c->streams.assign(ndev, nullptr);
+  c->events.assign(ndev, nullptr);
+  rf_status s = RF_OK;
+  for (int i = 0; i < ndev && s == RF_OK; ++i) {
+    DevGuard g(devices[i]);
+    cudaError_t e = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->events[i], cudaEventDisableTiming);
+    if (e != cudaSuccess) s = rfi::cuda_fail(e, "sharded corpus streams");
+  }
+  // every shard uploads and builds its layout on its own device concurrently (one host thread per shard)
+  if (s == RF_OK)
+    s = for_each_shard((size_t)ndev, [&](size_t i) {
+      return rfi::corpus_create_sub(chars, offsets, c->lo[i], c->lo[i + 1], c->devices[i], &c->shard[i]);
+    });
+  if (s != RF_OK) {
+    const std::string keep = rfi::last_error();
+    rf_sharded_corpus_destroy(c);
+    return rfi::fail(s, keep);
+  }
+  *out = c;
+  return RF_OK;
+}
+
+rf_status rf_sharded_corpus_destroy(rf_sharded_corpus* c) {
+  if (!c) return RF_OK;
+  for (rf_corpus* s : c->shard) rf_corpus_destroy(s);
+  if (c->comm_ready)
+    for (ncclComm_t cm : c->comms)
+      if (cm) ncclCommDestroy(cm);
+  for (size_t i = 0; i < c->devices.size(); ++i) {
+    DevGuard g(c->devices[i]);
+    if (c->events[i]) cudaEventDestroy(c->events[i]);
+    if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
+  }
+  delete c;
+  return RF_OK;
+}
+
+uint64_t rf_sharded_corpus_size(const rf_sharded_corpus* c) { return c ? c->n : 0; }
+int rf_sharded_corpus_shards(const rf_sharded_corpus* c) { return c ? (int)c->devices.size() : 0; }
+rf_status rf_sharded_corpus_shard_range(const rf_sharded_corpus* c, int shard, uint64_t* first, uint64_t* end) {
+  if (!c || shard < 0 || shard >= (int)c->devices.size()) return rfi::fail(RF_ERR_INVALID_ARG, "no such shard");
+  if (first) *first = c->lo[shard];
+  if (end) *end = c->lo[shard + 1];
+  return RF_OK;
+}
+const rf_corpus* rf_sharded_corpus_shard(const rf_sharded_corpus* c, int shard) {
+  return (c && shard >= 0 && shard < (int)c->devices.size()) ? c->shard[shard] : nullptr;
+}
+int rf_sharded_corpus_uses_nccl(const rf_sharded_corpus* c) { return (c && c->devices.size() > 1 && use_nccl(c)) ? 1 : 0; }
+
+static rf_status sharded_batch_create(rf_metric metric, const void* query, uint32_t query_len, bool wide, const int* devices, int ndev,
+                                      rf_sharded_batch** out) {
+  if (!out) return rfi::fail(RF_ERR_INVALID_ARG, "out is NULL");
+  *out = nullptr;
+  if (!devices || ndev < 1 || ndev > 64) return rfi::fail(RF_ERR_INVALID_ARG, "devices / ndev (1..64)");
+  rf_sharded_batch* b = new (std::nothrow) rf_sharded_batch();
+  if (!b) return rfi::fail(RF_ERR_OOM, "host allocation failed");
+  b->devices.assign(devices, devices + ndev);
+  b->metric = metric;
+  b->per.assign(ndev, nullptr);
+  for (int i = 0; i < ndev; ++i) {
+    rf_status s = wide ? rf_batch_create_u32(metric, (const uint32_t*)query, query_len, devices[i], &b->per[i])
+                       : rf_batch_create_u8(metric, (const uint8_t*)query, query_len, devices[i], &b->per[i]);
+    if (s != RF_OK) {
+      const std::string keep = rfi::last_error();
+      rf_sharded_batch_destroy(b);
+      return rfi::fail(s, keep);
+    }
+  }
+  *out = b;
+  return RF_OK;
+}
+
+rf_status rf_sharded_batch_create_u8(rf_metric metric, const uint8_t* query, uint32_t query_len, const int* devices, int ndev,
+                                     rf_sharded_batch** out) {
+  return sharded_batch_create(metric, query, query_len, false, devices, ndev, out);
+}
+rf_status rf_sharded_batch_create_u32(rf_metric metric, const uint32_t* query, uint32_t query_len, const int* devices, int ndev,
+                                      rf_sharded_batch** out) {
+  return sharded_batch_create(metric, query, query_len, true, devices, ndev, out);
+}
+rf_status rf_sharded_batch_destroy(rf_sharded_batch* b) {
+  if (!b) return RF_OK;
+  for (rf_batch* p : b->per) rf_batch_destroy(p);
+  delete b;
+  return RF_OK;
+}
+
+// ---- scoring into the caller's HOST vector: no collective, every device downloads its own slice
+static rf_status sharded_score_host(const rf_sharded_batch* b, const rf_sharded_corpus* cc, rf_kind kind, const rf_args* args,
+                                    void* out_host, bool want_f64) {
+  rf_status s = check_pair(b, cc);
+  if (s != RF_OK) return s;
+  rf_sharded_corpus* c = const_cast<rf_sharded_corpus*>(cc);
+  if (c->n && !out_host) return rfi::fail(RF_ERR_INVALID_ARG, "out is NULL");
+  const size_t nd = c->devices.size(), esz = want_f64 ? 8 : 4;
+  std::vector<uint8_t*> d_out(nd, nullptr);
+  std::vector<uint32_t> differing(nd, 0);
+  for (size_t i = 0; i < nd && s == RF_OK; ++i) {
+    const uint64_t cnt = c->lo[i + 1] - c->lo[i];
+    DevGuard g(c->devices[i]);
+    cudaStream_t st = c->streams[i];
+    const size_t bytes = (size_t)cnt * esz;
+    cudaError_t e = dev_alloc(&d_out[i], bytes + 16, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_out[i] + bytes, 0, 16, st);
+    if (e != cudaSuccess) { s = rfi::cuda_fail(e, "result buffer"); break; }
+    s = rfi::score_device(b->per[i], c->shard[i], kind, args, cnt ? d_out[i] : nullptr, want_f64, st, (uint32_t*)(d_out[i] + bytes));
+    if (s != RF_OK) break;
+    if (cnt) e = cudaMemcpyAsync((uint8_t*)out_host + c->lo[i] * esz, d_out[i], bytes, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&differing[i], d_out[i] + bytes, 4, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) s = rfi::cuda_fail(e, "result download");
+  }
+  const std::string keep = s != RF_OK ? rfi::last_error() : std::string();
+  rf_status s2 = sync_all(c);
+  for (size_t i = 0; i < nd; ++i) {
+    DevGuard g(c->devices[i]);
+    dev_free(d_out[i], c->streams[i]);
+  }
+  if (s != RF_OK) return rfi::fail(s, keep);
+  if (s2 != RF_OK) return s2;
+  for (size_t i = 0; i < nd; ++i)
+    if (differing[i]) return rfi::fail(RF_ERR_INVALID_ARG, "Differing length arguments provided");  // hamming::Error
+  return RF_OK;
+}
+
+rf_status rf_sharded_score_u32(const rf_sharded_batch* b, const rf_sharded_corpus* c, rf_kind kind, const rf_args* args,
+                               uint32_t* out_host) {
+  return sharded_score_host(b, c, kind, args, out_host, false);
+}
+rf_status rf_sharded_score_f64(const rf_sharded_batch* b, const rf_sharded_corpus* c, rf_kind kind, const rf_args* args,
+                               double* out_host) {
+  return sharded_score_host(b, c, kind, args, out_host, true);
+}
+
+// ---- scoring + all-gather: out_device[i] (on devices[i]) receives ALL n scores
+static rf_status sharded_score_allgather(const rf_sharded_batch* b, const rf_sharded_corpus* cc, rf_kind kind, const rf_args* args,
+                                         void* const* out_device, bool want_f64) {
+  rf_status s = check_pair(b, cc);
+  if (s != RF_OK) return s;
+  rf_sharded_corpus* c = const_cast<rf_sharded_corpus*>(cc);
+  if (c->n == 0) return RF_OK;
+  if (!out_device) return rfi::fail(RF_ERR_INVALID_ARG, "out_device is NULL");
+  const size_t nd = c->devices.size(), esz = want_f64 ? 8 : 4;
+  std::vector<uint64_t> off(nd + 1);
+  for (size_t i = 0; i <= nd; ++i) off[i] = c->lo[i] * esz;
+  for (size_t i = 0; i < nd; ++i) {
+    if (!out_device[i]) return rfi::fail(RF_ERR_INVALID_ARG, "out_device[i] is NULL");
+    const uint64_t cnt = c->lo[i + 1] - c->lo[i];
+    DevGuard g(c->devices[i]);
+    s = rfi::score_device(b->per[i], c->shard[i], kind, args, cnt ? (uint8_t*)out_device[i] + off[i] : nullptr, want_f64,
+                          c->streams[i], nullptr);
+    if (s != RF_OK) break;
+  }
+  if (s == RF_OK) s = allgatherv_inplace(c, out_device, off.data());
+  const std::string keep = s != RF_OK ? rfi::last_error() : std::string();
+  rf_status s2 = sync_all(c);
+  if (s != RF_OK) return rfi::fail(s, keep);
+  return s2;
+}
+
+rf_status rf_sharded_score_u32_allgather_device(const rf_sharded_batch* b, const rf_sharded_corpus* c, rf_kind kind,
+                                                const rf_args* args, uint32_t* const* out_device) {
+  return sharded_score_allgather(b, c, kind, args, (void* const*)out_device, false);
+}
+rf_status rf_sharded_score_f64_allgather_device(const rf_sharded_batch* b, const rf_sharded_corpus* c, rf_kind kind,
+                                                const rf_args* args, double* const* out_device) {
+  return sharded_score_allgather(b, c, kind, args, (void* const*)out_device, true);
+}
+
+// ---- k best of the whole sharded corpus: per-shard selection on the devices, k entries per shard to the host, merged
+// by (score best-first, global index ascending)
+static rf_status sharded_extract(const rf_sharded_batch* b, const rf_sharded_corpus* c, rf_kind kind, const rf_args* args, uint32_t k,
+                                 uint64_t* idx_out, void* score_out, uint32_t* n_out, bool want_f64) {
+  rf_status s = check_pair(b, c);
+  if (s != RF_OK) return s;
+  if (k == 0 || k > 1024) return rfi::fail(RF_ERR_INVALID_ARG, "k must be in 1..1024");
+  if (!idx_out || !score_out || !n_out) return rfi::fail(RF_ERR_INVALID_ARG, "NULL output");
+  *n_out = 0;
+  const size_t nd = c->devices.size(), esz = want_f64 ? 8 : 4;
+  std::vector<std::vector<uint32_t>> idx(nd, std::vector<uint32_t>(k));
+  std::vector<std::vector<uint8_t>> sc(nd, std::vector<uint8_t>((size_t)k * esz));
+  std::vector<uint32_t> cnt(nd, 0);
+  s = for_each_shard(nd, [&](size_t i) {
+    return rfi::select_host(b->per[i], c->shard[i], kind, args, want_f64, false, k, 0, idx[i].data(), sc[i].data(), &cnt[i], nullptr);
+  });
+  if (s != RF_OK) return s;
+  const rf_kind ek = (b->metric == RF_RATIO) ? RF_NORMALIZED_SIMILARITY : kind;
+  const bool desc = ek == RF_SIMILARITY || ek == RF_NORMALIZED_SIMILARITY;
+  struct Ent { double key; uint64_t gidx; size_t shard; uint32_t pos; };
+  std::vector<Ent> all;
+  for (size_t i = 0; i < nd; ++i)
+    for (uint32_t j = 0; j < cnt[i]; ++j) {
+      const double v = want_f64 ? ((const double*)sc[i].data())[j] : (double)((const uint32_t*)sc[i].data())[j];
+      all.push_back(Ent{desc ? -v : v, c->lo[i] + idx[i][j], i, j});
+    }
+  std::sort(all.begin(), all.end(), [](const Ent& a, const Ent& z) { return a.key != z.key ? a.key < z.key : a.gidx < z.gidx; });
+  const size_t m = std::min<size_t>(all.size(), k);
+  for (size_t t = 0; t < m; ++t) {
+    idx_out[t] = all[t].gidx;
+    memcpy((uint8_t*)score_out + t * esz, sc[all[t].shard].data() + (size_t)all[t].pos * esz, esz);
+  }
+  *n_out = (uint32_t)m;
+  return RF_OK;
+}
+
+rf_status rf_sharded_extract_u32(const rf_sharded_batch* b, const rf_sharded_corpus* c, rf_kind kind, const rf_args* args, uint32_t k,
+                                 uint64_t* idx_out, uint32_t* score_out, uint32_t* n_out) {
+  return sharded_extract(b, c, kind, args, k, idx_out, score_out, n_out, false);
+}
+rf_status rf_sharded_extract_f64(const rf_sharded_batch* b, const rf_sharded_corpus* c, rf_kind kind, const rf_args* args, uint32_t k,
+                                 uint64_t* idx_out, double* score_out, uint32_t* n_out) {
+  return sharded_extract(b, c, kind, args, k, idx_out, score_out, n_out, true);
+}
+
+// ---- many-vs-many top-k over the sharded corpus: per-shard scan -> all-gather of the lists -> merge on the device
+rf_status rf_sharded_cdist_topk_u8(const uint8_t* q_chars, const uint64_t* q_offsets, uint32_t nq, const rf_sharded_corpus* cc,
+                                   const rf_args* args, uint32_t k, uint64_t* idx_host, uint32_t* dist_host) {
+  if (!cc) return rfi::fail(RF_ERR_INVALID_ARG, "NULL corpus");
+  if (nq == 0) return RF_OK;
+  if (!idx_host || !dist_host) return rfi::fail(RF_ERR_INVALID_ARG, "NULL output");
+  if (k == 0 || k > 64) return rfi::fail(RF_ERR_INVALID_ARG, "k must be in 1..64");
+  rf_sharded_corpus* c = const_cast<rf_sharded_corpus*>(cc);
+  const size_t nd = c->devices.size();
+  if ((uint64_t)nd * k > 25600) return rfi::fail(RF_ERR_UNSUPPORTED, "shards * k must not exceed 25600");
+  const size_t kk = (size_t)nq * k, part = 2 * kk;  // u32 words per shard: [idx nq*k][dist nq*k]
+  std::vector<uint32_t*> d_parts(nd, nullptr);       // on every device: [nd][2][nq][k]
+  uint64_t* d_base = nullptr;                         // device 0: first candidate of every shard
+  uint64_t* d_oidx = nullptr;
+  uint32_t* d_odist = nullptr;
+  rf_status s = RF_OK;
+  for (size_t i = 0; i < nd && s == RF_OK; ++i) {
+    DevGuard g(c->devices[i]);
+    cudaError_t e = dev_alloc(&d_parts[i], nd * part * 4, c->streams[i]);
+    if (e != cudaSuccess) s = rfi::cuda_fail(e, "cdist lists");
+  }
+  // the scans run concurrently, one host thread per shard (rf_cdist_topk_u8_device returns after its stream has drained)
+  if (s == RF_OK)
+    s = for_each_shard(nd, [&](size_t i) {
+      DevGuard g(c->devices[i]);
+      uint32_t* mine = d_parts[i] + i * part;
+      return rfi::cdist(q_chars, q_offsets, nq, c->shard[i], args, k, mine, mine + kk, true, c->streams[i]);
+    });
+  if (s == RF_OK) {
+    std::vector<uint64_t> off(nd + 1);
+    for (size_t i = 0; i <= nd; ++i) off[i] = i * part * 4;
+    if (nd > 1 && use_nccl(c)) {  // equal parts: one in-place ncclAllGather per device
+      std::lock_guard<std::mutex> lk(c->coll_mu);
+      s = ensure_comms(c);
+      if (s == RF_OK) {
+        ncclResult_t r = ncclGroupStart();
+        for (size_t i = 0; i < nd && r == ncclSuccess; ++i)
+          r = ncclAllGather(d_parts[i] + i * part, d_parts[i], part, ncclUint32, c->comms[i], c->streams[i]);
+        ncclResult_t r2 = ncclGroupEnd();
+        if (r != ncclSuccess) s = nccl_fail(r, "ncclAllGather");
+        else if (r2 != ncclSuccess) s = nccl_fail(r2, "ncclGroupEnd");
+      }
+    } else {
+      s = allgatherv_inplace(c, (void* const*)d_parts.data(), off.data());
+    }
+  }
+  if (s == RF_OK) {  // merge on the first device; its stream is ordered behind the gather
+    DevGuard g(c->devices[0]);
+    cudaStream_t st = c->streams[0];
+    cudaError_t e = dev_alloc(&d_base, nd * 8, st);
+    if (e == cudaSuccess) e = dev_alloc(&d_oidx, kk * 8, st);
+    if (e == cudaSuccess) e = dev_alloc(&d_odist, kk * 4, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_base, c->lo.data(), nd * 8, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) s = rfi::cuda_fail(e, "cdist merge buffers");
+    if (s == RF_OK)
+      s = rf_topk_merge_device(d_parts[0], d_parts[0] + kk, part, d_base, (uint32_t)nd, nq, k, d_oidx, d_odist, c->devices[0], st);
+    if (s == RF_OK) {
+      e = cudaMemcpyAsync(idx_host, d_oidx, kk * 8, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(dist_host, d_odist, kk * 4, cudaMemcpyDeviceToHost, st);
+      if (e != cudaSuccess) s = rfi::cuda_fail(e, "cdist result download");
+    }
+  }
+  const std::string keep = s != RF_OK ? rfi::last_error() : std::string();
+  rf_status s2 = sync_all(c);
+  {
+    DevGuard g(c->devices[0]);
+    dev_free(d_base, c->streams[0]);
+    dev_free(d_oidx, c->streams[0]);
+    dev_free(d_odist, c->streams[0]);
+  }
+  for (size_t i = 0; i < nd; ++i) {
+    DevGuard g(c->devices[i]);
+    dev_free(d_parts[i], c->streams[i]);
+  }
+  if (s != RF_OK) return rfi::fail(s, keep);
+  return s2;
+}
+
+// ---- streaming from host memory over several devices: the candidate range is split by bytes, every device runs its own
+// chunked H2D / scan / D2H pipeline (rf_batch_stream_*) on its own PCIe link, results land in the caller's vector
+static rf_status sharded_stream(const rf_sharded_batch* b, const uint8_t* chars, const uint64_t* offsets, uint64_t n, rf_kind kind,
+                                const rf_args* args, void* out_host, bool want_f64) {
+  if (!b) return rfi::fail(RF_ERR_INVALID_ARG, "NULL handle");
+  if (n == 0) return RF_OK;
+  if (!offsets || !out_host) return rfi::fail(RF_ERR_INVALID_ARG, "NULL argument");
+  if (offsets[0] != 0) return rfi::fail(RF_ERR_INVALID_ARG, "offsets[0] must be 0");
+  const size_t nd = b->devices.size(), esz = want_f64 ? 8 : 4;
+  std::vector<uint64_t> lo;
+  split_by_bytes(offsets, n, nd, &lo);
+  return for_each_shard(nd, [&](size_t i) {
+    if (lo[i + 1] == lo[i]) return RF_OK;
+    return rfi::stream_u64(b->per[i], chars, offsets + lo[i], lo[i + 1] - lo[i], kind, args, (uint8_t*)out_host + lo[i] * esz, want_f64);
+  });
+}
+rf_status rf_sharded_stream_u32(const rf_sharded_batch* b, const uint8_t* chars, const uint64_t* offsets, uint64_t n, rf_kind kind,
+                                const rf_args* args, uint32_t* out_host) {
+  return sharded_stream(b, chars, offsets, n, kind, args, out_host, false);
+}
+rf_status rf_sharded_stream_f64(const rf_sharded_batch* b, const uint8_t* chars, const uint64_t* offsets, uint64_t n, rf_kind kind,
+                                const rf_args* args, double* out_host) {
+  return sharded_stream(b, chars, offsets, n, kind, args, out_host, true);
+}
+
+}  // extern "C"

@@ -9,12 +9,12 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.environ.get("RF_LIB_PATH") or os.path.join(_ROOT, "lib", "librfgpu.so")  # RF_LIB_PATH: dev A/B builds
 
-RF_OK, RF_ERR_INVALID_ARG, RF_ERR_UNSUPPORTED, RF_ERR_CUDA, RF_ERR_OOM = range(5)
+RF_OK, RF_ERR_INVALID_ARG, RF_ERR_UNSUPPORTED, RF_ERR_CUDA, RF_ERR_OOM, RF_ERR_NCCL = range(6)
 METRICS = {"levenshtein": 0, "indel": 1, "lcs_seq": 2, "osa": 3, "jaro": 4, "jaro_winkler": 5, "ratio": 6,
            "hamming": 7, "prefix": 8, "postfix": 9, "damerau_levenshtein": 10}
 KINDS = {"distance": 0, "similarity": 1, "normalized_distance": 2, "normalized_similarity": 3}
 NONE_U32 = 0xFFFFFFFF
-RF_MAX_QUERY_LEN = 16384
+RF_MAX_QUERY_LEN = 4194304
 
 
 class RfArgs(C.Structure):
@@ -71,6 +71,25 @@ SYMBOLS = {
     "rf_cdist_topk_u8": (_int, [_vp, _vp, _u32, _vp, _PA, _u32, _vp, _vp]),
     "rf_cdist_topk_u8_device": (_int, [_vp, _vp, _u32, _vp, _PA, _u32, _vp, _vp, _vp]),
     "rf_topk_merge_device": (_int, [_vp, _vp, _u64, _vp, _u32, _u32, _u32, _vp, _vp, _int, _vp]),
+    "rf_corpus_create_sharded_u8": (_int, [_vp, _vp, _u64, _vp, _int, C.POINTER(_vp)]),
+    "rf_sharded_corpus_destroy": (_int, [_vp]),
+    "rf_sharded_corpus_size": (_u64, [_vp]),
+    "rf_sharded_corpus_shards": (_int, [_vp]),
+    "rf_sharded_corpus_shard_range": (_int, [_vp, _int, C.POINTER(_u64), C.POINTER(_u64)]),
+    "rf_sharded_corpus_shard": (_vp, [_vp, _int]),
+    "rf_sharded_corpus_uses_nccl": (_int, [_vp]),
+    "rf_sharded_batch_create_u8": (_int, [_int, _vp, _u32, _vp, _int, C.POINTER(_vp)]),
+    "rf_sharded_batch_create_u32": (_int, [_int, _vp, _u32, _vp, _int, C.POINTER(_vp)]),
+    "rf_sharded_batch_destroy": (_int, [_vp]),
+    "rf_sharded_score_u32": (_int, [_vp, _vp, _int, _PA, _vp]),
+    "rf_sharded_score_f64": (_int, [_vp, _vp, _int, _PA, _vp]),
+    "rf_sharded_score_u32_allgather_device": (_int, [_vp, _vp, _int, _PA, _vp]),
+    "rf_sharded_score_f64_allgather_device": (_int, [_vp, _vp, _int, _PA, _vp]),
+    "rf_sharded_extract_u32": (_int, [_vp, _vp, _int, _PA, _u32, _vp, _vp, _vp]),
+    "rf_sharded_extract_f64": (_int, [_vp, _vp, _int, _PA, _u32, _vp, _vp, _vp]),
+    "rf_sharded_cdist_topk_u8": (_int, [_vp, _vp, _u32, _vp, _PA, _u32, _vp, _vp]),
+    "rf_sharded_stream_u32": (_int, [_vp, _vp, _vp, _u64, _int, _PA, _vp]),
+    "rf_sharded_stream_f64": (_int, [_vp, _vp, _vp, _u64, _int, _PA, _vp]),
     "rf_pack_u8": (_int, [_vp, _vp, _u64, _vp, _vp, _int]),
     "rf_corpus_file_write": (_int, [C.c_char_p, _vp, _vp, _u64]),
     "rf_corpus_file_open": (_int, [C.c_char_p, C.POINTER(_vp)]),
@@ -96,11 +115,28 @@ def build():
     return mod.build()
 
 
+def _preload_nccl():
+    """librfgpu.so needs libnccl.so.2 (sharded entry points).  PyTorch bundles its own copy under nvidia/nccl/lib; if that
+    one is present, map it first (RTLD_GLOBAL) so that this library and a later `import torch` share ONE NCCL instead of
+    the system copy shadowing torch's.  Without the bundled copy the loader picks the system libnccl.so.2."""
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia")
+        for base in (spec.submodule_search_locations if spec else []):
+            p = os.path.join(base, "nccl", "lib", "libnccl.so.2")
+            if os.path.exists(p):
+                C.CDLL(p, mode=C.RTLD_GLOBAL)
+                return
+    except Exception:
+        pass
+
+
 def lib():
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             build()
+        _preload_nccl()
         l = C.CDLL(LIB_PATH)
         for name, (res, args) in SYMBOLS.items():
             f = getattr(l, name)

@@ -143,3 +143,157 @@ def all_gather_topk(idx_local, dist_local, shard_start, k, group=None):
     idx_parts = [p[0].cpu().numpy().astype(np.uint32) for p in parts]
     dist_parts = [p[1].cpu().numpy().astype(np.uint32) for p in parts]
     return merge_topk(idx_parts, dist_parts, [int(s.item()) for s in starts], k)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# One process, several GPUs: mirrors of the C ABI's sharded handles (include/rfgpu.h, rf_sharded.cu).  Unlike the
+# functions above (one process per GPU, torch.distributed), these need no PyTorch: the library owns the split, the
+# per-device streams and the NCCL communicator.
+class ShardedCorpus:
+    """rf_corpus_create_sharded_u8: the candidates split by bytes over `devices` (one resident shard per entry)."""
+
+    def __init__(self, chars, offsets, devices):
+        import ctypes as C
+        from . import _ffi
+        chars = np.ascontiguousarray(chars, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        self.devices = [int(d) for d in devices]
+        dv = (C.c_int * len(self.devices))(*self.devices)
+        h = C.c_void_p()
+        _ffi.check(_ffi.lib().rf_corpus_create_sharded_u8(chars.ctypes.data, offsets.ctypes.data, len(offsets) - 1, dv,
+                                                         len(self.devices), C.byref(h)))
+        self._h = h
+
+    def __len__(self):
+        from . import _ffi
+        return int(_ffi.lib().rf_sharded_corpus_size(self._h))
+
+    @property
+    def uses_nccl(self):
+        from . import _ffi
+        return bool(_ffi.lib().rf_sharded_corpus_uses_nccl(self._h))
+
+    def shard_ranges(self):
+        import ctypes as C
+        from . import _ffi
+        out = []
+        for i in range(len(self.devices)):
+            a, b = C.c_uint64(), C.c_uint64()
+            _ffi.check(_ffi.lib().rf_sharded_corpus_shard_range(self._h, i, C.byref(a), C.byref(b)))
+            out.append((a.value, b.value))
+        return out
+
+    def close(self):
+        from . import _ffi
+        if getattr(self, "_h", None):
+            _ffi.lib().rf_sharded_corpus_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ShardedBatchComparator:
+    """rf_sharded_batch_create_*: one BatchComparator replicated on every device of the list."""
+
+    def __init__(self, metric, query, devices):
+        import ctypes as C
+        from . import _ffi
+        from ._scorer import _as_query
+        q = _as_query(query)
+        self.metric, self.query, self.devices = metric, q, [int(d) for d in devices]
+        dv = (C.c_int * len(self.devices))(*self.devices)
+        h = C.c_void_p()
+        fn = _ffi.lib().rf_sharded_batch_create_u32 if q.dtype == np.uint32 else _ffi.lib().rf_sharded_batch_create_u8
+        _ffi.check(fn(_ffi.METRICS[metric], q.ctypes.data, len(q), dv, len(self.devices), C.byref(h)))
+        self._h = h
+
+    def _is_f(self, kind):
+        from . import _ffi
+        return bool(_ffi.lib().rf_result_is_float(_ffi.METRICS[self.metric], _ffi.KINDS[kind]))
+
+    def score(self, kind, corpus, args=None):
+        """Raw sentinel-carrying scores of the whole sharded corpus (host vector; no collective)."""
+        import ctypes as C
+        from . import _ffi
+        from ._scorer import Args
+        is_f = self._is_f(kind)
+        ca = (args if args is not None else Args())._c(is_f)
+        out = np.empty(len(corpus), dtype=np.float64 if is_f else np.uint32)
+        fn = _ffi.lib().rf_sharded_score_f64 if is_f else _ffi.lib().rf_sharded_score_u32
+        _ffi.check(fn(self._h, corpus._h, _ffi.KINDS[kind], C.byref(ca), out.ctypes.data))
+        return out
+
+    def score_allgather(self, kind, corpus, out_ptrs, args=None):
+        """rf_sharded_score_*_allgather_device: out_ptrs[i] = device pointer of an n-element buffer on devices[i]."""
+        import ctypes as C
+        from . import _ffi
+        from ._scorer import Args
+        is_f = self._is_f(kind)
+        ca = (args if args is not None else Args())._c(is_f)
+        arr = (C.c_void_p * len(out_ptrs))(*[int(p) for p in out_ptrs])
+        fn = _ffi.lib().rf_sharded_score_f64_allgather_device if is_f else _ffi.lib().rf_sharded_score_u32_allgather_device
+        _ffi.check(fn(self._h, corpus._h, _ffi.KINDS[kind], C.byref(ca), arr))
+
+    def extract(self, kind, corpus, k=5, args=None):
+        import ctypes as C
+        from . import _ffi
+        from ._scorer import Args
+        is_f = self._is_f(kind)
+        ca = (args if args is not None else Args())._c(is_f)
+        idx = np.empty(k, dtype=np.uint64)
+        score = np.empty(k, dtype=np.float64 if is_f else np.uint32)
+        m = C.c_uint32(0)
+        fn = _ffi.lib().rf_sharded_extract_f64 if is_f else _ffi.lib().rf_sharded_extract_u32
+        _ffi.check(fn(self._h, corpus._h, _ffi.KINDS[kind], C.byref(ca), k, idx.ctypes.data, score.ctypes.data, C.byref(m)))
+        return idx[: m.value], score[: m.value]
+
+    def stream(self, kind, chars, offsets, args=None, out=None):
+        """rf_sharded_stream_*: host-resident candidates, split by bytes over the devices, one PCIe pipeline each."""
+        import ctypes as C
+        from . import _ffi
+        from ._scorer import Args
+        chars = np.ascontiguousarray(chars, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        is_f = self._is_f(kind)
+        ca = (args if args is not None else Args())._c(is_f)
+        if out is None:
+            out = np.empty(n, dtype=np.float64 if is_f else np.uint32)
+        fn = _ffi.lib().rf_sharded_stream_f64 if is_f else _ffi.lib().rf_sharded_stream_u32
+        _ffi.check(fn(self._h, chars.ctypes.data, offsets.ctypes.data, n, _ffi.KINDS[kind], C.byref(ca), out.ctypes.data))
+        return out
+
+    def close(self):
+        from . import _ffi
+        if getattr(self, "_h", None):
+            _ffi.lib().rf_sharded_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def sharded_cdist_topk(q_chars, q_offsets, corpus, k=10, score_cutoff=None):
+    """rf_sharded_cdist_topk_u8: (idx uint64 [nq,k] global indices, dist uint32 [nq,k]); padding = all ones."""
+    import ctypes as C
+    from . import _ffi
+    q_chars = np.ascontiguousarray(q_chars, dtype=np.uint8)
+    q_offsets = np.ascontiguousarray(q_offsets, dtype=np.uint64)
+    nq = len(q_offsets) - 1
+    a = _ffi.RfArgs()
+    _ffi.lib().rf_args_default(C.byref(a))
+    if score_cutoff is not None:
+        a.has_cutoff = 1
+        a.cutoff_u = int(score_cutoff)
+    idx = np.empty((nq, k), dtype=np.uint64)
+    dist = np.empty((nq, k), dtype=np.uint32)
+    _ffi.check(_ffi.lib().rf_sharded_cdist_topk_u8(q_chars.ctypes.data, q_offsets.ctypes.data, nq, corpus._h, C.byref(a), k,
+                                                  idx.ctypes.data, dist.ctypes.data))
+    return idx, dist

@@ -97,7 +97,7 @@ def test_lev_similarity_cutoff_is_none_not_wrapped():
     assert r.tolist() == [4, 6, None]
 
 
-@pytest.mark.parametrize("qlen", [65, 66, 100, 128, 129, 200, 256, 300, 700, 2048, 2100, 5000])
+@pytest.mark.parametrize("qlen", [65, 66, 100, 128, 129, 200, 256, 300, 512, 513, 700, 2048, 2100, 5000])
 def test_multi_word_integer_metrics(qlen):
     rng = np.random.default_rng(300 + qlen)
     q = (rng.integers(0, 4, qlen) + 97).astype(np.uint8)

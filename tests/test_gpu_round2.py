@@ -95,3 +95,188 @@ def test_compact_sub_cache_survives_many_corpora():
     for c, _ in corpora:
         c.close()
     b.close()
+
+
+# ------------------------------------------------------------------------------------------------ sharded C ABI
+def _device_lists():
+    """One-GPU boxes exercise the split / gather / merge logic with a repeated device (copy-based gathers); with two or
+    more GPUs the same tests also run over distinct devices, i.e. through NCCL."""
+    n = _ffi.lib().rf_device_count()
+    lists = [[0], [0, 0, 0]]
+    if n >= 2:
+        lists.append(list(range(min(n, 8))))
+    return lists
+
+
+@pytest.mark.parametrize("devices", _device_lists() if True else [], ids=lambda d: "dev" + "".join(map(str, d)))
+def test_sharded_corpus_equals_single_gpu_equals_oracle(devices):
+    """the multi-GPU split behind the C ABI.  sharded == single-GPU == oracle for scores (host vector and
+    all-gathered device vectors), extract and cdist top-k with global indices."""
+    import torch
+    from rapidfuzz_b200 import sharding
+    rng = np.random.default_rng(len(devices))
+    q = synth.synth_query(2, 32)
+    chars, offsets = synth.synth_corpus(2, q, 120_001, 8, 64, 16)
+    sc = sharding.ShardedCorpus(chars, offsets, devices)
+    assert len(sc) == 120_001 and sc.uses_nccl == (len(devices) > 1 and len(set(devices)) == len(devices))
+    rg = sc.shard_ranges()
+    assert rg[0][0] == 0 and rg[-1][1] == 120_001 and all(a[1] == b[0] for a, b in zip(rg[:-1], rg[1:]))
+    byts = [int(offsets[b] - offsets[a]) for a, b in rg]
+    assert max(byts) - min(byts) <= 2 * 64
+    single = rf.Corpus(chars, offsets)
+    for metric, kind, cut in (("levenshtein", "distance", None), ("levenshtein", "distance", 9), ("indel", "normalized_similarity", None),
+                              ("jaro_winkler", "similarity", 0.6), ("lcs_seq", "similarity", None)):
+        sb = sharding.ShardedBatchComparator(metric, q, devices)
+        a = Args().score_cutoff(cut) if cut is not None else Args()
+        got = sb.score(kind, sc, a)
+        kw = {} if cut is None else {"cutoff": cut}
+        exp = orc.batch(metric, kind, q, chars, offsets, nthreads=0, **kw)
+        assert_same(got, exp, ("sharded score", metric, kind, cut, devices))
+        assert_same(gpu_batch(metric, kind, q, single, **kw), exp, "single")
+        # all-gather: every device ends with the whole vector
+        dt = torch.float64 if got.dtype == np.float64 else torch.int32
+        bufs = [torch.full((len(sc),), -1, dtype=dt, device="cuda:%d" % d) for d in devices]
+        sb.score_allgather(kind, sc, [b.data_ptr() for b in bufs], a)
+        for b in bufs:
+            gb = b.cpu().numpy()
+            assert_same(gb if got.dtype == np.float64 else gb.view(np.uint32), exp, ("allgather", metric, devices))
+        # extract: k best with global indices
+        gi, gs = sb.extract(kind, sc, k=7, args=a)
+        desc = kind in ("similarity", "normalized_similarity")
+        valid = ~np.isnan(exp) if exp.dtype == np.float64 else (exp != 0xFFFFFFFF)
+        keyv = np.where(valid, -exp.astype(np.float64) if desc else exp.astype(np.float64), np.inf)
+        order = np.lexsort((np.arange(len(exp)), keyv))[:7]
+        order = order[valid[order]]
+        assert np.array_equal(gi, order.astype(np.uint64)) and np.array_equal(gs, exp[order]), (metric, kind)
+        sb.close()
+    # many-vs-many top-k over the shards == the oracle's global top-k
+    qs = [synth.synth_query(100 + i, L) for i, L in enumerate((32, 20, 7, 32, 1))]
+    q_chars = np.concatenate(qs)
+    q_off = np.zeros(len(qs) + 1, dtype=np.uint64)
+    q_off[1:] = np.cumsum([len(x) for x in qs])
+    for k, cut in ((10, None), (3, 14)):
+        gi, gd = sharding.sharded_cdist_topk(q_chars, q_off, sc, k=k, score_cutoff=cut)
+        for qi, qq in enumerate(qs):
+            d = orc.batch("levenshtein", "distance", qq, chars, offsets, nthreads=0).astype(np.int64)
+            keys = np.sort(d * (1 << 32) + np.arange(len(d)))
+            if cut is not None:
+                keys = keys[(keys >> 32) <= cut]
+            keys = keys[:k]
+            m = len(keys)
+            assert np.array_equal(gi[qi][:m], (keys & 0xFFFFFFFF).astype(np.uint64)) and np.array_equal(gd[qi][:m], (keys >> 32).astype(np.uint32))
+            assert np.all(gi[qi][m:] == np.uint64(0xFFFFFFFFFFFFFFFF)) and np.all(gd[qi][m:] == 0xFFFFFFFF)
+    single.close()
+    sc.close()
+
+
+@pytest.mark.parametrize("devices", _device_lists(), ids=lambda d: "dev" + "".join(map(str, d)))
+def test_sharded_stream_and_edge_shapes(devices):
+    from rapidfuzz_b200 import sharding
+    rng = np.random.default_rng(5)
+    q = (rng.integers(0, 5, 29) + 97).astype(np.uint8)
+    chars, offsets = make_corpus(rng, 30_000, [0, 1, 3, 8, 20, 33, 64, 70, 300], alphabet=5, query=q)
+    sb = sharding.ShardedBatchComparator("levenshtein", q, devices)
+    exp = orc.batch("levenshtein", "distance", q, chars, offsets, nthreads=0)
+    assert_same(sb.stream("distance", chars, offsets), exp, "sharded stream")
+    # fewer candidates than shards, empty corpus, all-empty candidates
+    for n in (0, 1, 2):
+        sc = sharding.ShardedCorpus(chars[: int(offsets[n])], offsets[: n + 1], devices)
+        assert_same(sb.score("distance", sc), exp[:n], ("tiny", n))
+        gi, gd = sharding.sharded_cdist_topk(q, np.array([0, len(q)], np.uint64), sc, k=2)
+        order = np.lexsort((np.arange(n), exp[:n]))[:2]
+        assert np.array_equal(gi[0][: len(order)], order.astype(np.uint64))
+        sc.close()
+    z = np.zeros(6, np.uint64)
+    sc = sharding.ShardedCorpus(np.zeros(0, np.uint8), z, devices)
+    assert_same(sb.score("distance", sc), np.full(5, 29, np.uint32), "empties")
+    sc.close()
+    # mismatched device lists are refused
+    if len(devices) > 1:
+        other = sharding.ShardedBatchComparator("levenshtein", q, devices[:1])
+        sc = sharding.ShardedCorpus(chars, offsets, devices)
+        with pytest.raises(rf.RfError) as ei:
+            other.score("distance", sc)
+        assert ei.value.status == _ffi.RF_ERR_INVALID_ARG
+        other.close()
+        sc.close()
+    sb.close()
+
+
+# ------------------------------------------------------------------------------------------------ long / multi-word queries
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.timeout(900)
+def test_ocr_large_band_on_gpu():
+    """the reference's own test_large_band (levenshtein.rs:2139-2161: 106 514 x 107 244 -> 5278, None at
+    cutoff 2500, 5278 with score_hint 0) through rf_batch_score_u32, i.e. the long-query stripe kernel."""
+    z = np.load(os.path.join(GOLD, "ocr.npz"))
+    a, b = z["OCR_EXAMPLE1"], z["OCR_EXAMPLE2"]
+    assert len(a) == 106514 and len(b) == 107244
+    lev = rf.distance.levenshtein.BatchComparator(a)
+    assert lev.distance(b) == 5278
+    assert lev.distance_with_args(b, rf.Args().score_cutoff(2500)) is None
+    assert lev.distance_with_args(b, rf.Args().score_hint(0)) == 5278
+    assert lev.distance_with_args(b, rf.Args().score_cutoff(5278).score_hint(31)) == 5278
+    assert lev.distance_with_args(b, rf.Args().score_cutoff(5277)) is None
+    # the same query against a ragged corpus, every integer family, vs the oracle (which runs the reference's block + band code)
+    cands = [b, a, b[:50000], np.zeros(0, np.uint8), a[:200], a[1000:90000], b[::-1].copy()]
+    chars = np.concatenate(cands).astype(np.uint8)
+    offsets = np.zeros(len(cands) + 1, np.uint64)
+    offsets[1:] = np.cumsum([len(c) for c in cands])
+    corpus = rf.Corpus(chars, offsets)
+    for m, kind, kw in (("levenshtein", "distance", {}), ("levenshtein", "normalized_similarity", {}), ("indel", "distance", {}),
+                        ("lcs_seq", "similarity", {}), ("osa", "distance", {}), ("levenshtein", "distance", {"cutoff": 60000}),
+                        ("levenshtein", "distance", {"cutoff": 40})):
+        got = gpu_batch(m, kind, a, corpus, **kw)
+        exp = orc.batch(m, kind, a, chars, offsets, nthreads=0, **kw)
+        assert_same(got, exp, ("ocr", m, kind, kw))
+    corpus.close()
+    lev.close()
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("qlen", [16384, 16385, 16449, 20000, 32768, 40001])
+def test_queries_beyond_16384_vs_oracle(qlen):
+    """The 16 384 cap of round 1 is gone: stripes of 256 blocks, carries parked between stripes (1, 2 and 3 stripes,
+    stripe ends on and off block boundaries)."""
+    rng = np.random.default_rng(qlen)
+    q = (rng.integers(0, 4, qlen) + 97).astype(np.uint8)
+    lens = [0, 1, 63, 64, 65, 5000, qlen - 1, qlen, qlen + 1, qlen + 777]
+    chars, offsets = make_corpus(rng, 40, lens, alphabet=4, query=q, near_frac=0.5)
+    corpus = rf.Corpus(chars, offsets)
+    for m in ("levenshtein", "indel", "lcs_seq", "osa"):
+        check(m, "distance", q, chars, offsets, corpus)
+    check("levenshtein", "normalized_similarity", q, chars, offsets, corpus, cutoff=0.9)
+    check("levenshtein", "distance", q, chars, offsets, corpus, cutoff=1000)
+    check("levenshtein", "distance", q, chars, offsets, corpus, cutoff=12)      # banded kernel: any query length
+    check("levenshtein", "distance", q, chars, offsets, corpus, weights=(1, 1, 2))
+    check("ratio", "similarity", q, chars, offsets, corpus)
+    corpus.close()
+
+
+@pytest.mark.parametrize("qlen", [65, 96, 127, 128, 129, 191, 192, 193, 255, 256, 257, 320, 383, 384, 385, 448, 511, 512, 513])
+def test_register_column_kernel_vs_shuffle_kernel_vs_oracle(qlen):
+    """queries of 65..512 elements on a resident corpus run one thread per candidate with the whole
+    bit-vector column in registers (scan_lbn_kernel, 4/8/12/16 limbs); multi_word_path=1 is the sub-warp shuffle
+    kernel.  Both must equal the oracle, limb and plane boundaries included."""
+    rng = np.random.default_rng(1000 + qlen)
+    q = (rng.integers(0, 5, qlen) + 97).astype(np.uint8)
+    lens = [0, 1, 7, 8, 9, 63, 64, 65, 127, 128, 129, 255, 256, 257, 511, 512, 513, 700, qlen - 1, qlen, qlen + 1]
+    chars, offsets = make_corpus(rng, 3000, lens, alphabet=5, query=q, near_frac=0.5, high_bytes=True)
+    corpus = rf.Corpus(chars, offsets)
+    try:
+        for path in (0, 1):
+            _ffi.check(_ffi.lib().rf_set_option(b"multi_word_path", path))
+            for m in ("levenshtein", "indel", "lcs_seq", "osa"):
+                check(m, "distance", q, chars, offsets, corpus)
+            check("levenshtein", "normalized_distance", q, chars, offsets, corpus)
+            check("levenshtein", "distance", q, chars, offsets, corpus, cutoff=70)
+            check("levenshtein", "similarity", q, chars, offsets, corpus)
+            check("osa", "normalized_similarity", q, chars, offsets, corpus, cutoff=0.5)
+            check("ratio", "similarity", q, chars, offsets, corpus, cutoff=0.3)
+            check("levenshtein", "distance", q, chars, offsets, corpus, weights=(2, 2, 2))
+            check("levenshtein", "distance", q, chars, offsets, corpus, weights=(1, 1, 2))
+    finally:
+        _ffi.check(_ffi.lib().rf_set_option(b"multi_word_path", 0))
+        corpus.close()

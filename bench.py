@@ -143,6 +143,52 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+ORIG_AFFINITY = None
+
+
+def numa_bind_to_gpu(index):
+    """Place this rank's host buffers on the NUMA node its GPU hangs off: set_mempolicy(MPOL_PREFERRED, node) for all later
+    page allocations (the pinned buffers), and CPU affinity narrowed to that node's cores when the cgroup allows any of
+    them.  Round 1's 8-GPU run had every rank's pinned memory on one node (e2e efficiency 0.37).  Best effort: a
+    container may refuse the syscall; what happened is reported in the JSON line."""
+    info = {"gpu_numa_node": None, "mempolicy": "unchanged", "affinity": "unchanged"}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        path = "/sys/bus/pci/devices/%s:%s/numa_node" % (dom[-4:].lower(), rest.lower())
+        node = int(open(path).read().strip())
+        info["gpu_numa_node"] = node
+        if node < 0:
+            return info
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
+        info["numa_nodes"] = len(nodes)
+        if len(nodes) < 2:
+            return info
+        libc = C.CDLL(None, use_errno=True)
+        mask = C.c_ulong(1 << node)
+        rc = libc.syscall(238, 1, C.byref(mask), 64)      # set_mempolicy(MPOL_PREFERRED, &mask, maxnode)
+        info["mempolicy"] = "preferred node %d" % node if rc == 0 else "refused (errno %d)" % C.get_errno()
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        both = cpus & allowed
+        if both and both != allowed:
+            global ORIG_AFFINITY
+            ORIG_AFFINITY = allowed
+            os.sched_setaffinity(0, both)
+            info["affinity"] = "%d of the node's %d cores" % (len(both), len(cpus))
+        elif not both:
+            info["affinity"] = "none of the node's cores is in this cgroup (allowed: %d cpus)" % len(allowed)
+    except Exception as e:
+        info["error"] = "%s: %s" % (type(e).__name__, e)
+    return info
+
+
 def host_threads():
     """All host threads this process may use (torchrun exports OMP_NUM_THREADS=1; the CPU arm must not obey it)."""
     try:
@@ -413,6 +459,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    numa = numa_bind_to_gpu(local_rank) if os.environ.get("RF_BENCH_NUMA", "1") != "0" else {"disabled": True}
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -536,27 +583,44 @@ def main():
     corpus = None
     del out_dev
 
-    def e2e_step():
+    lens8_t = torch.empty(n, dtype=torch.uint8).pin_memory()
+    lens8 = lens8_t.numpy()
+    np.copyto(lens8, np.diff(offsets64.view(np.int64)), casting="unsafe")
+    out8_t = torch.empty(n, dtype=torch.uint8).pin_memory()
+    out8 = out8_t.numpy()
+
+    def e2e_step_csr():
         b2 = create_batch()
         _ffi.check(L.rf_batch_stream_u32_off32(b2, chars.ctypes.data, offsets32.ctypes.data, n, _ffi.KINDS["distance"],
                                                None, out_host.ctypes.data))
         L.rf_batch_destroy(b2)
 
-    e2e_step()   # warm-up: allocates the per-device chunk buffers
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    h2d = int(total + 4 * (n + 1) + 2 * 256 * 4 + 2 * 256 * 8 + 256 * 8)
-    d2h = int(4 * n)
+    def e2e_step():   # one length byte per candidate in, one score byte per candidate out (query len 32, candidates <= 64)
+        b2 = create_batch()
+        _ffi.check(L.rf_batch_stream_u8_len8(b2, chars.ctypes.data, lens8.ctypes.data, n, _ffi.KINDS["distance"],
+                                             None, out8.ctypes.data))
+        L.rf_batch_destroy(b2)
+
+    def wall(fn):
+        fn()   # warm-up: allocates the per-device chunk buffers
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            fn()
+        barrier()
+        return (time.perf_counter() - t0) / e2e_steps
+    e2e_csr_s = wall(e2e_step_csr)
+    e2e_s = wall(e2e_step)
+    tables = 2 * 256 * 4 + 2 * 256 * 8 + 256 * 8
+    h2d_csr, d2h_csr = int(total + 4 * (n + 1) + tables), int(4 * n)
+    h2d, d2h = int(total + n + tables), int(n)
     if ok is not None:
         from oracle import oracle as orc
         m = min(n, 200_000)
         exp = orc.batch("levenshtein", "distance", q, chars[: int(offsets64[m])], offsets64[: m + 1], nthreads=0)
         ok = ok and bool(np.array_equal(out_host[:m], exp))
         ok = ok and bool(np.array_equal(out_host[n - m_tail:], tail_dev.cpu().numpy().view(np.uint32)))
+        ok = ok and bool(np.array_equal(out8, out_host.astype(np.uint8)) and int(out_host.max()) <= 254)   # byte results == u32 results, all n
     # secondary: upload + build a RESIDENT corpus (CSR + interleaved layout), score once, download, destroy
     out_host[:] = 0
     barrier()
@@ -576,9 +640,9 @@ def main():
 
     # ---- aggregate over ranks (device time: max over ranks; pairs: sum over ranks)
     if dist is not None:
-        t = torch.tensor([ms, e2e_s, resident_s], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms, e2e_s, resident_s, e2e_csr_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s, resident_s = float(t[0]), float(t[1]), float(t[2])
+        ms, e2e_s, resident_s, e2e_csr_s = float(t[0]), float(t[1]), float(t[2]), float(t[3])
         cnt = torch.tensor([n, total], dtype=torch.int64, device="cuda")
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         n_all = int(cnt[0])
@@ -598,13 +662,17 @@ def main():
             "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": config2_dict(n),
-            "run": {"mean_len": total / n, "host_gen_s": round(t_gen, 2), "results_match_oracle_sample": ok},
+            "run": {"mean_len": total / n, "host_gen_s": round(t_gen, 2), "results_match_oracle_sample": ok, "numa_rank0": numa},
             "clocks": clk.summary(),
             "e2e": {"value": n_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                     "h2d_gbs": h2d / e2e_s / 1e9,
-                    "what": "rf_batch_create_u8 + rf_batch_stream_u32_off32 (pinned host chars+offsets -> chunked H2D / "
-                            "scan / D2H pipeline -> pinned host results) + rf_batch_destroy, per step; PCIe-bound",
+                    "what": "rf_batch_create_u8 + rf_batch_stream_u8_len8 (pinned host chars + one length byte per candidate -> "
+                            "chunked H2D / prefix sum / scan / narrow / D2H pipeline -> pinned host byte scores) + rf_batch_destroy, "
+                            "per step; PCIe-bound",
+                    "csr_u32": {"value": n_all / e2e_csr_s, "ms_per_step": e2e_csr_s * 1e3, "h2d_bytes_per_step": h2d_csr,
+                                "d2h_bytes_per_step": d2h_csr, "h2d_gbs": h2d_csr / e2e_csr_s / 1e9,
+                                "what": "the same through rf_batch_stream_u32_off32: u32 CSR starts in, u32 scores out (round 1's e2e)"},
                     "resident_corpus_build_and_score_ms": resident_s * 1e3},
             "gpu_launches": launches,
             "roofline": roofline(alg_bytes, ms_per_step, "scan_lb_kernel<F_LEV,u32,256,RAWDIST>", traffic,
@@ -613,6 +681,8 @@ def main():
             "configs": sub,
         }
         if not args.no_cpu_baseline:
+            if ORIG_AFFINITY:   # the CPU leg gets every core this job may use, not only the GPU-local ones
+                os.sched_setaffinity(0, ORIG_AFFINITY)
             threads = host_threads()
             n_sample = min(n, 2_000_000 * max(1, min(threads, 32)))
             rate, secs = cpu_oracle_rate(n_sample, threads)

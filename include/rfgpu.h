@@ -185,6 +185,16 @@ rf_status rf_batch_stream_f64(const rf_batch* b, const uint8_t* chars, const uin
 rf_status rf_batch_stream_f64_off32(const rf_batch* b, const uint8_t* chars, const uint32_t* offsets, uint64_t n,
                                     rf_kind kind, const rf_args* args, double* out_host);
 
+/* Fewer bytes on the link (the call is PCIe-bound): candidates of at most 255 elements described by ONE length byte each
+ * instead of a CSR start (lens[i] = length of candidate i, chars = the candidates back to back; the starts are rebuilt
+ * on the device by a prefix sum), integer-valued (metric, kind) only.  _u8_: the scores come back as one byte each,
+ * None = 0xFF; a score above 254 anywhere makes the call return RF_ERR_INVALID_ARG (use the _u32_ variant then).
+ * Chunk boundaries fall on multiples of 4096 candidates. */
+rf_status rf_batch_stream_u32_len8(const rf_batch* b, const uint8_t* chars, const uint8_t* lens, uint64_t n, rf_kind kind,
+                                   const rf_args* args, uint32_t* out_host);
+rf_status rf_batch_stream_u8_len8(const rf_batch* b, const uint8_t* chars, const uint8_t* lens, uint64_t n, rf_kind kind,
+                                  const rf_args* args, uint8_t* out_host);
+
 /* ---- many-vs-many (new on this side; the reference has no cdist -- SURVEY fact 3): for each of nq queries
  * the k best candidates by (distance ascending, index ascending); fewer than k hits are padded with
  * (UINT32_MAX, UINT32_MAX).  Levenshtein distance (unit weights), queries of length <= 64, k <= 64; with

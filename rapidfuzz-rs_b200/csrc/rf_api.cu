@@ -435,8 +435,6 @@ static rf_status batch_create_bytes(rf_metric metric, const uint8_t* query, uint
   if ((int)metric < 0 || (int)metric > (int)RF_DAMERAU_LEVENSHTEIN) return fail(RF_ERR_INVALID_ARG, "unknown metric");
   if (query_len && !query) return fail(RF_ERR_INVALID_ARG, "query is NULL");
   if (query_len > RF_MAX_QUERY_LEN) return fail(RF_ERR_UNSUPPORTED, "query longer than RF_MAX_QUERY_LEN");
-  if ((metric == RF_JARO || metric == RF_JARO_WINKLER) && query_len > 2048)
-    return fail(RF_ERR_UNSUPPORTED, "Jaro / Jaro-Winkler queries longer than 2048 elements");
   if (rf_device_count() <= device || device < 0) return fail(RF_ERR_CUDA, "no such CUDA device");
   DeviceGuard g(device);
   if (!g.ok) return fail(RF_ERR_CUDA, "cudaSetDevice failed");
@@ -1039,6 +1037,10 @@ struct StreamSlot {
   cudaStream_t st = nullptr;
   uint8_t* d_chars = nullptr;
   uint8_t* d_renamed = nullptr;  // u32-query comparators: the chunk renamed to the query's byte alphabet (lazily allocated)
+  uint8_t* d_lens = nullptr;     // *_len8 entry points: the chunk's u8 lengths, the scan's temporary storage, the narrowed results
+  void* d_scan_tmp = nullptr;
+  size_t scan_tmp_bytes = 0;
+  uint8_t* d_out8 = nullptr;
   void* d_offs = nullptr;
   void* d_out = nullptr;
 };
@@ -1062,6 +1064,9 @@ void stream_ctx_release(StreamCtx* x) {
   for (auto& s : x->slot) {
     if (s.d_chars) cudaFree(s.d_chars);
     if (s.d_renamed) cudaFree(s.d_renamed);
+    if (s.d_lens) cudaFree(s.d_lens);
+    if (s.d_scan_tmp) cudaFree(s.d_scan_tmp);
+    if (s.d_out8) cudaFree(s.d_out8);
     if (s.d_offs) cudaFree(s.d_offs);
     if (s.d_out) cudaFree(s.d_out);
     if (s.st) cudaStreamDestroy(s.st);
@@ -1165,6 +1170,127 @@ rf_status stream_impl(const rf_batch* b, const uint8_t* chars, const OffT* offse
   }
   return s;
 }
+
+// u32 results of a chunk -> bytes (None 0xFFFFFFFF -> 0xFF); any other value above 254 raises the overflow flag
+__global__ void __launch_bounds__(256) narrow_results_u8(const uint32_t* __restrict__ in, uint64_t n, uint8_t* __restrict__ out,
+                                                         uint32_t* __restrict__ overflow) {
+  const uint64_t nq = (n + 3) / 4;
+  for (uint64_t qd = (uint64_t)blockIdx.x * 256 + threadIdx.x; qd < nq; qd += (uint64_t)gridDim.x * 256) {
+    uint32_t packed = 0;
+    bool over = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint64_t i = qd * 4 + j;
+      uint32_t v = i < n ? in[i] : 0u;
+      if (v == 0xFFFFFFFFu) v = 0xFFu;
+      else if (v > 254u) { over = true; v = 0xFFu; }
+      packed |= v << (8 * j);
+    }
+    reinterpret_cast<uint32_t*>(out)[qd] = packed;
+    if (over) atomicOr(overflow, 1u);
+  }
+}
+
+// rf_batch_stream_*_len8: the candidates' lengths cross PCIe as ONE byte each instead of a 4- or 8-byte CSR start (the
+// starts of a chunk are rebuilt on the device by a prefix sum), and the results can come back as one byte each: 36.9 + 1
+// instead of 39.9 + 4 bytes per config-2 pair on the host side of the link.
+rf_status stream_len8_impl(const rf_batch* b, const uint8_t* chars, const uint8_t* lens, uint64_t n, rf_kind kind,
+                           const rf_args* args, void* out_host, bool out_u8) {
+  if (!b) return fail(RF_ERR_INVALID_ARG, "NULL handle");
+  if ((int)kind < 0 || (int)kind > 3) return fail(RF_ERR_INVALID_ARG, "unknown kind");
+  if (rf_result_is_float(b->metric, kind)) return fail(RF_ERR_INVALID_ARG, "this (metric, kind) yields f64 results; the _len8 entry points return integer scores");
+  if (n == 0) return RF_OK;
+  if (!lens || !out_host) return fail(RF_ERR_INVALID_ARG, "NULL argument");
+  if (rf_device_count() <= b->device) return fail(RF_ERR_CUDA, "no such CUDA device");
+  DeviceGuard g(b->device);
+  if (!g.ok) return fail(RF_ERR_CUDA, "cudaSetDevice failed");
+  StreamCtx* x = stream_ctx(b->device);
+  std::lock_guard<std::mutex> lk(x->mu);
+  const uint64_t cap_bytes = (uint64_t)(g_stream_mb.load() > 0 ? g_stream_mb.load() : 1) << 20;
+  const uint64_t cap_n = (uint64_t)(g_stream_kcand.load() > 0 ? g_stream_kcand.load() : 1) << 10;
+  cudaError_t e = stream_ctx_prepare(x, cap_bytes, cap_n);
+  if (e != cudaSuccess) return cuda_fail(e, "streaming buffers");
+  for (auto& sl : x->slot) {
+    if (sl.d_lens) continue;
+    sl.scan_tmp_bytes = lens_to_offsets_tmp_bytes(cap_n);
+    if ((e = cudaMalloc(&sl.d_lens, cap_n + 64)) != cudaSuccess) break;
+    if ((e = cudaMalloc(&sl.d_scan_tmp, sl.scan_tmp_bytes ? sl.scan_tmp_bytes : 16)) != cudaSuccess) break;
+    if ((e = cudaMalloc(&sl.d_out8, cap_n + 64)) != cudaSuccess) break;
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "streaming buffers");
+  uint32_t* d_over = nullptr;
+  if ((e = cudaMalloc(&d_over, 16)) != cudaSuccess) return cuda_fail(e, "streaming buffers");
+  if ((e = cudaMemset(d_over, 0, 16)) != cudaSuccess) { cudaFree(d_over); return cuda_fail(e, "streaming buffers"); }
+  constexpr uint64_t kBlock = 4096;  // chunk boundaries fall on multiples of kBlock candidates: the host only sums lengths block-wise
+  rf_status s = RF_OK;
+  uint64_t i0 = 0, pos = 0;  // pos = byte position of candidate i0
+  int k = 0;
+  while (i0 < n && s == RF_OK) {
+    const uint64_t B0 = pos & ~15ull;
+    uint64_t i1 = i0, bytes = pos - B0;
+    while (i1 < n && i1 - i0 < cap_n) {
+      const uint64_t j1 = (n - i1 < kBlock) ? n : i1 + kBlock;
+      if (j1 - i0 > cap_n) break;
+      uint64_t sum = 0;
+      for (uint64_t j = i1; j < j1; ++j) sum += lens[j];   // auto-vectorised byte sum
+      if (bytes + sum > cap_bytes) break;
+      bytes += sum;
+      i1 = j1;
+    }
+    if (i1 == i0) { s = fail(RF_ERR_UNSUPPORTED, "stream_chunk_mb / stream_chunk_kcand too small for one block of 4096 candidates"); break; }
+    const uint64_t cn = i1 - i0, B1 = B0 + bytes;
+    StreamSlot& sl = x->slot[k];
+    k = (k + 1) % kSlots;
+    if (B1 > B0) {
+      if (!chars) { s = fail(RF_ERR_INVALID_ARG, "chars is NULL"); break; }
+      e = cudaMemcpyAsync(sl.d_chars, chars + B0, B1 - B0, cudaMemcpyHostToDevice, sl.st);
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(sl.d_lens, lens + i0, cn, cudaMemcpyHostToDevice, sl.st);
+    if (e == cudaSuccess) e = lens_to_offsets(sl.d_lens, cn, (uint32_t)(pos - B0), (uint32_t*)sl.d_offs, sl.d_scan_tmp, sl.scan_tmp_bytes, sl.st);
+    if (e != cudaSuccess) { s = cuda_fail(e, "chunk upload"); break; }
+    rfk::count_launches(1);
+    const uint8_t* d_src = sl.d_chars;
+    if (b->wide && B1 > B0) {
+      if (!sl.d_renamed) {
+        if ((e = cudaMalloc(&sl.d_renamed, cap_bytes + 256)) == cudaSuccess) e = cudaMemsetAsync(sl.d_renamed, 0, cap_bytes + 256, sl.st);
+        if (e != cudaSuccess) { s = cuda_fail(e, "streaming buffers"); break; }
+      }
+      const uint64_t cb = B1 - B0, blocks = ((cb + 3) / 4 + 255) / 256;
+      const uint32_t grid = (uint32_t)(blocks < 148 * 16 ? blocks : 148 * 16);
+      remap_kernel<uint8_t><<<grid, 256, 0, sl.st>>>(sl.d_chars, cb, b->d_alpha_keys, b->d_alpha_codes, (uint32_t*)sl.d_renamed);
+      rfk::count_launches(1);
+      if ((e = cudaGetLastError()) != cudaSuccess) { s = cuda_fail(e, "alphabet renaming"); break; }
+      d_src = sl.d_renamed;
+    }
+    CorpusView cv{d_src, (const uint32_t*)sl.d_offs, nullptr, cn, bytes - (pos - B0), 255};
+    s = score_view(b, cv, nullptr, b->device, kind, args, sl.d_out, false, sl.st);
+    if (s != RF_OK) break;
+    if (out_u8) {
+      const uint64_t blocks = ((cn + 3) / 4 + 255) / 256;
+      narrow_results_u8<<<(uint32_t)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, sl.st>>>((const uint32_t*)sl.d_out, cn, sl.d_out8, d_over);
+      rfk::count_launches(1);
+      if ((e = cudaGetLastError()) == cudaSuccess)
+        e = cudaMemcpyAsync((uint8_t*)out_host + i0, sl.d_out8, cn, cudaMemcpyDeviceToHost, sl.st);
+    } else {
+      e = cudaMemcpyAsync((uint8_t*)out_host + i0 * 4, sl.d_out, cn * 4, cudaMemcpyDeviceToHost, sl.st);
+    }
+    if (e != cudaSuccess) { s = cuda_fail(e, "chunk download"); break; }
+    pos = B1;
+    i0 = i1;
+  }
+  for (auto& sl : x->slot) {
+    e = cudaStreamSynchronize(sl.st);
+    if (e != cudaSuccess && s == RF_OK) s = cuda_fail(e, "streaming scan");
+  }
+  uint32_t over = 0;
+  if (s == RF_OK && out_u8) {
+    e = cudaMemcpy(&over, d_over, 4, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) s = cuda_fail(e, "streaming scan");
+    else if (over) s = fail(RF_ERR_INVALID_ARG, "a score above 254 does not fit the u8 result; use rf_batch_stream_u32_len8");
+  }
+  cudaFree(d_over);
+  return s;
+}
 }  // namespace
 
 extern "C" {
@@ -1183,6 +1309,14 @@ rf_status rf_batch_stream_f64(const rf_batch* b, const uint8_t* chars, const uin
 rf_status rf_batch_stream_f64_off32(const rf_batch* b, const uint8_t* chars, const uint32_t* offsets, uint64_t n,
                                     rf_kind kind, const rf_args* args, double* out_host) {
   return stream_impl(b, chars, offsets, n, kind, args, out_host, true);
+}
+rf_status rf_batch_stream_u32_len8(const rf_batch* b, const uint8_t* chars, const uint8_t* lens, uint64_t n, rf_kind kind,
+                                   const rf_args* args, uint32_t* out_host) {
+  return stream_len8_impl(b, chars, lens, n, kind, args, out_host, false);
+}
+rf_status rf_batch_stream_u8_len8(const rf_batch* b, const uint8_t* chars, const uint8_t* lens, uint64_t n, rf_kind kind,
+                                  const rf_args* args, uint8_t* out_host) {
+  return stream_len8_impl(b, chars, lens, n, kind, args, out_host, true);
 }
 }  // extern "C"
 

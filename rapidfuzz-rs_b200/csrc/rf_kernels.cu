@@ -2079,6 +2079,43 @@ cudaError_t launch_scan_mw(const ScanLaunch& L) {
   }
 }
 
+// Row walker with a SMALL loop body for steps of 100+ instructions (the multi-limb kernels): walk_rows8's four-row
+// unrolling puts 32 steps = 54 KB of code into the loop, which thrashes the 32 KB L1.5 instruction cache (ncu:
+// "no_instruction" was the top stall, issue 35 %).  Here one row (or one 4-character word, WORD_LOOP) per iteration,
+// still two rows in flight + the L2 prefetch; the ragged tail is a rolled loop with a run-time byte selector.
+template <bool WORD_LOOP, class Rd, class St>
+__device__ __forceinline__ void walk_rows8_compact(Rd rd, uint32_t len2, St& st) {
+  static_assert(Rd::kRow8, "interleaved rows only");
+  uint2 A = rd.q0, B = rd.q1;
+  const uint2* p = rd.p;
+  const uint32_t nfull = len2 >> 3;
+#pragma unroll 1
+  for (uint32_t i = 0; i < nfull; ++i) {
+    if constexpr (Rd::kStream) prefetch_l2(p + 32 * kPfDist);
+    const uint2 C = ld_row8<Rd::kStream>(p);
+    p += 32;
+    if constexpr (WORD_LOOP) {
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t w = h ? A.y : A.x;
+        st.template step<0>(w); st.template step<1>(w); st.template step<2>(w); st.template step<3>(w);
+      }
+    } else {
+      { const uint32_t w = A.x; st.template step<0>(w); st.template step<1>(w); st.template step<2>(w); st.template step<3>(w); }
+      { const uint32_t w = A.y; st.template step<0>(w); st.template step<1>(w); st.template step<2>(w); st.template step<3>(w); }
+    }
+    A = B;
+    B = C;
+  }
+  const uint32_t rem = len2 & 7u;
+  uint32_t w = A.x;
+#pragma unroll 1
+  for (uint32_t k = 0; k < rem; ++k) {
+    if (k == 4) w = A.y;
+    st.step_sel(w, 0x80u << (8u * (k & 3u)));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ lbn
 // Multi-word queries of 65..512 elements over the interleaved layout: ONE THREAD per candidate, warp per group of 32
 // equal-length candidates like scan_lb_kernel, the whole column of the bit-parallel recurrence in registers.
@@ -2204,9 +2241,10 @@ struct LevNStep {
     }
   }
   template <int K>
-  __device__ __forceinline__ void step(uint32_t w) {
+  __device__ __forceinline__ void step(uint32_t w) { step_sel(w, 0x80u << (8 * K)); }
+  __device__ __forceinline__ void step_sel(uint32_t w, uint32_t sel) {  // sel = 0x80 << (8 * byte index)
     uint32_t X[L], T[L], S[L];
-    pmn_load<Q>(__dp4a(w, 0x80u << (8 * K), base), X);
+    pmn_load<Q>(__dp4a(w, sel, base), X);
 #pragma unroll
     for (int i = 0; i < L; ++i) T[i] = X[i] & VP[i];
     add_chain<L>(S, T, VP);
@@ -2262,9 +2300,10 @@ struct LcsNStep {
     for (int i = 0; i < L; ++i) S[i] = 0xFFFFFFFFu;
   }
   template <int K>
-  __device__ __forceinline__ void step(uint32_t w) {
+  __device__ __forceinline__ void step(uint32_t w) { step_sel(w, 0x80u << (8 * K)); }
+  __device__ __forceinline__ void step_sel(uint32_t w, uint32_t sel) {
     uint32_t X[L], U[L], A[L];
-    pmn_load<Q>(__dp4a(w, 0x80u << (8 * K), base), X);
+    pmn_load<Q>(__dp4a(w, sel, base), X);
 #pragma unroll
     for (int i = 0; i < L; ++i) U[i] = S[i] & X[i];
     add_chain<L>(A, S, U);
@@ -2327,12 +2366,12 @@ __global__ void __launch_bounds__(NT) scan_lbn_kernel(const __grid_constant__ Lb
       if constexpr (FAM == F_LCS) {
         LcsNStep<Q> st;
         st.init(p.len1, base, p.two);
-        walk_rows8(src.reader(), len2, st);
+        walk_rows8_compact<false>(src.reader(), len2, st);
         raw = st.result(len2);
       } else {
         LevNStep<Q, FAM == F_OSA> st;
         st.init(p.len1, base, p.two);
-        walk_rows8(src.reader(), len2, st);
+        walk_rows8_compact<(Q > 2 || FAM == F_OSA)>(src.reader(), len2, st);
         raw = st.result(len2);
       }
       if (idx != 0xFFFFFFFFu) {
@@ -3290,7 +3329,149 @@ __global__ void __launch_bounds__(128) jaro_mw_kernel(const __grid_constant__ Mw
   }
 }
 
+// Jaro / Jaro-Winkler with a query beyond 2048 elements (jaro.rs:286-337, :370-420 have no cap): one WARP per
+// candidate.  The pattern flags P (one bit per query element) and the matched text characters (at most len1 of them,
+// see jaro_similarity_generic) live in a per-warp scratch line; per text character the lanes search the window's
+// blocks 32 at a time for the first free match (ballot), the transposition pass ranks the flagged positions with a
+// warp prefix sum over the blocks' popcounts.
+struct JaroLongParams {
+  const uint8_t* chars;
+  const uint32_t* off32;
+  const uint64_t* off64;
+  uint64_t n;
+  const uint64_t* pm;  // [256][words]
+  uint32_t len1;
+  uint32_t words;
+  uint8_t* scratch;    // [warps][stride]: words u64 flags, then len1 matched bytes
+  uint64_t stride;
+  void* out;
+  Epi epi;
+};
+
+__global__ void __launch_bounds__(128) jaro_long_kernel(const __grid_constant__ JaroLongParams p) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint64_t warp_global = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const uint64_t total_warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+  const bool off64 = p.off64 != nullptr;
+  const uint64_t* __restrict__ pm = p.pm;
+  const uint32_t words = p.words;
+  unsigned long long* P = reinterpret_cast<unsigned long long*>(p.scratch + warp_global * p.stride);
+  uint8_t* matched = reinterpret_cast<uint8_t*>(P + words);
+  for (uint64_t c = warp_global; c < p.n; c += total_warps) {
+    const uint64_t o0 = off64 ? p.off64[c] : (uint64_t)p.off32[c];
+    const uint64_t o1 = off64 ? p.off64[c + 1] : (uint64_t)p.off32[c + 1];
+    const uint32_t len2_orig = (uint32_t)(o1 - o0), len1_orig = p.len1;
+    const uint8_t* __restrict__ txt = p.chars + o0;
+    auto jaro = [&](double cutoff) -> double {  // warp-uniform: every lane returns the same value
+      if (cutoff > 1.0) return 0.0;
+      if (len1_orig == 0 && len2_orig == 0) return 1.0;
+      if (!jaro_length_filter(len1_orig, len2_orig, cutoff)) return 0.0;
+      if (len1_orig == 1 && len2_orig == 1) return (__ldg(pm + (uint64_t)txt[0] * words) & 1u) ? 1.0 : 0.0;
+      uint32_t len1 = len1_orig, len2 = len2_orig, bound;
+      jaro_bounds(len1, len2, bound);
+      for (uint32_t w = lane; w < words; w += 32) __stcg(P + w, 0ull);
+      __syncwarp();
+      uint32_t cc = 0;
+      for (uint32_t j0 = 0; j0 < len2; j0 += 32) {
+        const uint32_t my_ch = (j0 + lane < len2) ? (uint32_t)txt[j0 + lane] : 0u;  // 32 text characters per load
+        const uint32_t jn = len2 - j0 < 32 ? len2 - j0 : 32;
+        for (uint32_t jj = 0; jj < jn; ++jj) {
+          const uint32_t j = j0 + jj;
+          const uint32_t ch = __shfl_sync(0xffffffffu, my_ch, jj);
+          const uint32_t lo = j > bound ? j - bound : 0;
+          uint32_t hi = j + bound;
+          if (hi >= len1) hi = len1 - 1;
+          if (lo > hi) continue;
+          const uint32_t w0 = lo / 64, w1 = hi / 64;
+          for (uint32_t wb = w0; wb <= w1; wb += 32) {
+            const uint32_t w = wb + lane;
+            unsigned long long m = 0;
+            if (w <= w1 && w < words) {
+              m = __ldg(pm + (uint64_t)ch * words + w) & ~__ldcg(P + w);
+              if (w == w0) m &= ~0ull << (lo % 64);
+              if (w == w1) m &= ~0ull >> (63 - (hi % 64));
+            }
+            const uint32_t ball = __ballot_sync(0xffffffffu, m != 0);
+            if (ball) {
+              if (lane == (uint32_t)__ffs(ball) - 1u) {
+                __stcg(P + w, __ldcg(P + w) | (m & (0ull - m)));
+                matched[cc] = (uint8_t)ch;
+              }
+              ++cc;
+              __syncwarp();
+              break;
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (!jaro_common_char_filter(len1_orig, len2_orig, cc, cutoff)) return 0.0;
+      uint32_t tr = 0, running = 0;
+      for (uint32_t wb = 0; wb < words; wb += 32) {
+        const uint32_t w = wb + lane;
+        unsigned long long pw = (w < words) ? __ldcg(P + w) : 0ull;
+        const uint32_t cnt = (uint32_t)__popcll(pw);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= (uint32_t)d) incl += t;
+        }
+        uint32_t k = running + incl - cnt;
+        while (pw) {
+          const unsigned long long bit = pw & (0ull - pw);
+          tr += (__ldg(pm + (uint64_t)__ldcg(matched + k) * words + w) & bit) == 0;
+          ++k;
+          pw ^= bit;
+        }
+        running += __shfl_sync(0xffffffffu, incl, 31);
+      }
+      for (uint32_t d = 16; d >= 1; d >>= 1) tr += __shfl_xor_sync(0xffffffffu, tr, d);
+      return jaro_calculate_similarity(len1_orig, len2_orig, cc, tr);
+    };
+    double r;
+    if (p.epi.metric == M_JARO) {
+      r = finish_float(p.epi, jaro);
+    } else {
+      uint32_t prefix = 0;
+      while (prefix < 4 && prefix < len1_orig && prefix < len2_orig &&
+             ((__ldg(pm + (uint64_t)txt[prefix] * words) >> prefix) & 1u)) ++prefix;
+      const double pw = p.epi.prefix_weight;
+      auto jw = [&](double cut) { return jaro_winkler_from(jaro, prefix, pw, cut); };
+      r = finish_float(p.epi, jw);
+    }
+    if (lane == 0) reinterpret_cast<double*>(p.out)[c] = r;
+    __syncwarp();
+  }
+}
+
+static cudaError_t launch_jaro_long(const ScanLaunch& L) {
+  JaroLongParams p{};
+  p.chars = L.corpus.chars;
+  p.off32 = L.corpus.off32;
+  p.off64 = L.corpus.off64;
+  p.n = L.corpus.n;
+  p.pm = L.query.pm_words;
+  p.len1 = L.query.len1;
+  p.words = L.query.words;
+  p.out = L.out;
+  p.epi = L.epi;
+  p.stride = ((uint64_t)p.words * 8 + p.len1 + 63) / 64 * 64;
+  uint64_t warps = (uint64_t)L.sm_count * 16;
+  if (warps > p.n) warps = p.n;
+  if (warps < 1) warps = 1;
+  const uint32_t blocks = (uint32_t)((warps + 3) / 4);
+  cudaError_t e = dev_alloc(&p.scratch, (uint64_t)blocks * 4 * p.stride, L.stream);
+  if (e != cudaSuccess) return e;
+  jaro_long_kernel<<<blocks, 128, 0, L.stream>>>(p);
+  g_launches.fetch_add(1);
+  e = cudaGetLastError();
+  dev_free(p.scratch, L.stream);
+  return e;
+}
+
 cudaError_t launch_jaro_mw(const ScanLaunch& L) {
+  if (L.query.len1 > 2048) return launch_jaro_long(L);
   MwParams p{};
   p.chars = L.corpus.chars;
   p.off32 = L.corpus.off32;

@@ -61,6 +61,11 @@ struct LbAlloc {  // owning pointers of an LbView
 cudaError_t lb_build(const CorpusView& c, cudaStream_t stream, LbAlloc* out);
 void lb_free(LbAlloc* a, cudaStream_t stream);
 
+// u8 candidate lengths of a streaming chunk -> its u32 CSR starts (cn + 1 entries, first = init); rf_layout.cu
+size_t lens_to_offsets_tmp_bytes(uint64_t cap_n);
+cudaError_t lens_to_offsets(const uint8_t* d_lens, uint64_t cn, uint32_t init, uint32_t* d_off, void* tmp, size_t tmp_bytes,
+                            cudaStream_t st);
+
 struct ScanLaunch {
   CorpusView corpus;
   LbView lb;

@@ -5,6 +5,7 @@
 // inside blocks of LB_BLOCK (so results still scatter into an L2-resident window of the output) and storing
 // each group of 32 equal-length candidates word-interleaved gives both, once, at corpus creation.
 #include <cub/device/device_scan.cuh>
+#include <thrust/iterator/counting_iterator.h>
 #include <thrust/iterator/transform_iterator.h>
 #include <mutex>
 #include <vector>
@@ -120,6 +121,25 @@ __global__ void lb_fill_kernel(const uint8_t* __restrict__ chars, const uint32_t
       dst[(size_t)k * 32] = v;
     }
   }
+}
+
+// candidate lengths (u8, as they cross PCIe in rf_batch_stream_*_len8) -> CSR starts of a chunk: off[i] = init + sum_{k<i} len[k],
+// i = 0..cn (cn + 1 entries)
+struct LenAt {
+  const uint8_t* lens;
+  uint64_t cn;
+  __host__ __device__ uint32_t operator()(uint64_t i) const { return i < cn ? (uint32_t)lens[i] : 0u; }
+};
+size_t lens_to_offsets_tmp_bytes(uint64_t cap_n) {
+  size_t bytes = 0;
+  auto in = thrust::make_transform_iterator(thrust::make_counting_iterator<uint64_t>(0), LenAt{nullptr, 0});
+  cub::DeviceScan::ExclusiveScan(nullptr, bytes, in, (uint32_t*)nullptr, cub::Sum(), 0u, (int64_t)(cap_n + 1), (cudaStream_t)0);
+  return bytes;
+}
+cudaError_t lens_to_offsets(const uint8_t* d_lens, uint64_t cn, uint32_t init, uint32_t* d_off, void* tmp, size_t tmp_bytes,
+                            cudaStream_t st) {
+  auto in = thrust::make_transform_iterator(thrust::make_counting_iterator<uint64_t>(0), LenAt{d_lens, cn});
+  return cub::DeviceScan::ExclusiveScan(tmp, tmp_bytes, in, d_off, cub::Sum(), init, (int64_t)(cn + 1), st);
 }
 
 struct CastU64 {

@@ -225,6 +225,22 @@ class BatchComparatorBase:
                                              C.byref(ca), out.ctypes.data))
         return out
 
+    def stream_len8(self, kind, chars, lens, args=None, out=None, u8_results=False):
+        """rf_batch_stream_{u32,u8}_len8: host-resident candidates described by one LENGTH byte each (<= 255 elements),
+        integer-valued kinds; with u8_results the scores come back as bytes (0xFF == None, scores must be <= 254)."""
+        args = args if args is not None else Args()
+        chars = np.ascontiguousarray(chars, dtype=np.uint8)
+        lens = np.ascontiguousarray(lens, dtype=np.uint8)
+        n = len(lens)
+        ca = args._c(False)
+        dt = np.uint8 if u8_results else np.uint32
+        if out is None:
+            out = np.empty(n, dtype=dt)
+        assert out.dtype == dt and len(out) >= n and out.flags.c_contiguous
+        fn = _ffi.lib().rf_batch_stream_u8_len8 if u8_results else _ffi.lib().rf_batch_stream_u32_len8
+        _ffi.check(fn(self._h, chars.ctypes.data, lens.ctypes.data, n, _ffi.KINDS[kind], C.byref(ca), out.ctypes.data))
+        return out
+
     def score_into(self, kind, corpus, out_ptr, args=None, stream=0):
         """Device-pointer variant (rf_batch_score_*_device): results stay on the GPU at `out_ptr`
         (u32[n] or f64[n]); enqueued on `stream` (a cudaStream_t as int), no synchronisation."""

@@ -2215,6 +2215,12 @@ __device__ __forceinline__ void pmn_load(uint32_t addr, uint32_t (&X)[4 * Q]) {
   if constexpr (Q > 2) lds128_off<65536>(addr, X[8], X[9], X[10], X[11]);
   if constexpr (Q > 3) lds128_off<98304>(addr, X[12], X[13], X[14], X[15]);
 }
+template <int LUT>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+  return d;
+}
 // x * 2 as {low word, bit that falls out}: IMAD.WIDE.U32 (`two` is opaque to ptxas, so it stays on the FMA pipe)
 __device__ __forceinline__ void mul2_wide(uint32_t x, uint32_t two, uint32_t& lo, uint32_t& hi) {
   asm("{\n\t.reg .b64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo), "=r"(hi) : "r"(x), "r"(two));
@@ -2251,7 +2257,9 @@ struct LevNStep {
     uint32_t cp = two >> 1, cn = 0, ct = 0;  // +1 enters row 0 (through the unused low bits)
 #pragma unroll
     for (int i = 0; i < L; ++i) {
-      uint32_t D0 = ((S[i] ^ VP[i]) | X[i]) | VN[i];
+      // the 7-LOP3 form of the step, pinned with explicit lop3 (left to itself ptxas re-associates D0 = D0' | VN into its
+      // three consumers and ends up with 8): D0' (1) D0 (1) HP (1) HN (1) VP' (1) VN' (1) + the AND above
+      uint32_t D0 = lop3<0xBE>(S[i], VP[i], X[i]) | VN[i];  // ((S ^ VP) | X) | VN
       if constexpr (OSA) {  // TR = (((~D0_prev) & X) << 1) & X_prev  (osa.rs:84-135), the shift across the limbs
         const uint32_t t = ~D0p[i] & X[i];
         uint32_t lo, hi;
@@ -2261,7 +2269,7 @@ struct LevNStep {
         D0p[i] = D0;
         Xp[i] = X[i];
       }
-      const uint32_t HP = VN[i] | ~(D0 | VP[i]);
+      const uint32_t HP = lop3<0xF1>(VN[i], D0, VP[i]);  // VN | ~(D0 | VP)
       const uint32_t HN = D0 & VP[i];
       uint32_t HPs, HNs;
       if (i < L - 1) {
@@ -2276,7 +2284,7 @@ struct LevNStep {
         HPs = HP * two + cp;
         HNs = HN * two + cn;
       }
-      VP[i] = HNs | ~(D0 | HPs);
+      VP[i] = lop3<0xF1>(HNs, D0, HPs);  // HN | ~(D0 | HP)
       VN[i] = HPs & D0;
     }
   }
@@ -2385,7 +2393,8 @@ __global__ void __launch_bounds__(NT) scan_lbn_kernel(const __grid_constant__ Lb
 
 template <int FAM, int Q>
 static cudaError_t launch_lbn_inst(const ScanLaunch& L, const void* tab) {
-  constexpr int NT = 256;
+  // 64 KB of table per CTA (Q = 2) lets 3 CTAs live on an SM: 320 threads each = 30 warps within the 64 K registers at 68
+  constexpr int NT = (Q == 2 && FAM != F_OSA) ? 320 : 256;
   auto kern = scan_lbn_kernel<FAM, Q, NT>;
   const size_t smem = (size_t)Q * 32768;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

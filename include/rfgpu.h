@@ -126,6 +126,11 @@ rf_status rf_batch_create_u8(rf_metric metric, const uint8_t* query, uint32_t qu
  * Works against u8 and u32 corpora; costs one extra pass over the candidates per call. */
 rf_status rf_batch_create_u32(rf_metric metric, const uint32_t* query, uint32_t query_len, int device, rf_batch** out);
 rf_status rf_batch_destroy(rf_batch* b);
+/* Kernel-choice knobs of ONE comparator ("single_word_path", "multi_word_path", "banded_levenshtein", "jaro32"; see
+ * rf_set_option for their meaning).  A comparator copies the process-wide defaults when it is created; scoring calls
+ * read the comparator's copy only, so threads that want different kernels do not race on global state.  Call it
+ * before the comparator is shared between threads. */
+rf_status rf_batch_set_option(rf_batch* b, const char* name, int value);
 
 /* ---- scoring: one call == the user's loop `for c in candidates { scorer.<kind>_with_args(c, &args) }`.
  * Integer-valued: levenshtein/indel/lcs_seq/osa distance|similarity            -> u32 out[n]
@@ -295,7 +300,9 @@ const void* rf_corpus_file_offsets(const rf_corpus_file* f);
 const uint8_t* rf_corpus_file_chars(const rf_corpus_file* f);
 rf_status rf_corpus_create_from_file(const char* path, int device, rf_corpus** out);
 
-/* tuning knobs (process-wide):
+/* tuning knobs (process-wide DEFAULTS: "single_word_path", "multi_word_path", "banded_levenshtein" and "jaro32" are
+ * copied into every comparator at creation -- rf_batch_set_option changes one comparator; "build_interleaved_layout" and
+ * "compact_u32_corpus" act at corpus creation; the stream / cdist / sharded knobs are read once at the start of a call):
  *   "build_interleaved_layout" (default 1): corpora created afterwards also keep the length-bucketed,
  *        warp-interleaved copy that the fastest single-word kernel reads (about +1.2x corpus memory);
  *   "single_word_path" (default 0): which kernel scores queries of at most 64 elements:

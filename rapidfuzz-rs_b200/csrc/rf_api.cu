@@ -26,6 +26,9 @@ static std::atomic<int> g_build_lb{1};   // build the length-bucketed interleave
 static std::atomic<int> g_w1_path{0};    // 0: interleaved-layout kernel when available, 1: CSR/TMA-tile kernel
 static std::atomic<int> g_mw_path{0};    // queries of 65..512 on a resident corpus: 0 register kernel (scan_lbn), 1 shuffle kernel (scan_mw)
 static std::atomic<int> g_band{1};       // multi-word Levenshtein with cutoff <= 63: banded kernel (0: block kernel)
+static std::atomic<int> g_jaro32{1};     // Jaro / Jaro-Winkler, query <= 32: row-wise 32-bit kernel (0: generic per-lane routine)
+// The four knobs above are DEFAULTS: a comparator takes a snapshot of them when it is created (rf_batch::opt) and its
+// scoring calls read the snapshot only, so threads working with different settings never race on process-wide state.
 static std::atomic<int> g_stream_mb{64};      // rf_batch_stream_*: chunk size in candidate bytes (MiB)
 static std::atomic<int> g_stream_kcand{2048}; // rf_batch_stream_*: chunk size in candidates (x1024)
 static std::atomic<int> g_compact32{1};       // rf_corpus_create_u32: keep corpora with <= 255 distinct symbols as renamed bytes
@@ -126,7 +129,7 @@ rf_status rf_set_option(const char* name, int value) {
   if (!name) return fail(RF_ERR_INVALID_ARG, "name is NULL");
   if (!strcmp(name, "build_interleaved_layout")) { g_build_lb.store(value ? 1 : 0); return RF_OK; }
   if (!strcmp(name, "single_word_path")) { g_w1_path.store(value); return RF_OK; }
-  if (!strcmp(name, "jaro32")) { set_jaro32(value ? 1 : 0); return RF_OK; }
+  if (!strcmp(name, "jaro32")) { g_jaro32.store(value ? 1 : 0); return RF_OK; }
   if (!strcmp(name, "multi_word_path")) { g_mw_path.store(value ? 1 : 0); return RF_OK; }
   if (!strcmp(name, "banded_levenshtein")) { g_band.store(value ? 1 : 0); return RF_OK; }
   if (!strcmp(name, "stream_chunk_mb")) { if (value < 1) return fail(RF_ERR_INVALID_ARG, "stream_chunk_mb < 1"); g_stream_mb.store(value); return RF_OK; }
@@ -442,6 +445,7 @@ static rf_status batch_create_bytes(rf_metric metric, const uint8_t* query, uint
   if (!b) return fail(RF_ERR_OOM, "host allocation failed");
   b->device = device;
   b->metric = metric;
+  b->opt = rf_batch_opts{g_w1_path.load(), g_mw_path.load(), g_band.load(), g_jaro32.load()};
   b->s1.assign(query, query + query_len);
   b->len1 = query_len;
   b->words = (query_len + 63) / 64;
@@ -561,6 +565,17 @@ rf_status rf_batch_create_u32(rf_metric metric, const uint32_t* query, uint32_t 
   return RF_OK;
 }
 
+rf_status rf_batch_set_option(rf_batch* b, const char* name, int value) {
+  if (!b || !name) return fail(RF_ERR_INVALID_ARG, "NULL argument");
+  if (!strcmp(name, "single_word_path")) b->opt.w1_path = value;
+  else if (!strcmp(name, "multi_word_path")) b->opt.mw_path = value ? 1 : 0;
+  else if (!strcmp(name, "banded_levenshtein")) b->opt.band = value ? 1 : 0;
+  else if (!strcmp(name, "jaro32")) b->opt.jaro32 = value ? 1 : 0;
+  else return fail(RF_ERR_INVALID_ARG, std::string("not a per-comparator option: ") + name);
+  for (auto& kv : b->subs) rf_batch_set_option(kv.second, name, value);
+  return RF_OK;
+}
+
 rf_status rf_batch_destroy(rf_batch* b) {
   if (!b) return RF_OK;
   DeviceGuard g(b->device);
@@ -629,7 +644,8 @@ static rf_status score_view(const rf_batch* b, const CorpusView& cv, const LbAll
   if (!g.ok) return fail(RF_ERR_CUDA, "cudaSetDevice failed");
   L.corpus = cv;
   const Family fam0 = family_of(L.epi.metric, L.epi.wclass);
-  const bool use_lb = lb && lb->gdata && g_w1_path.load() != 1 && (fam0 != F_SIMPLE || L.epi.metric == M_HAMMING) &&
+  const rf_batch_opts opt = b->opt;  // per-comparator snapshot of the kernel-choice knobs
+  const bool use_lb = lb && lb->gdata && opt.w1_path != 1 && (fam0 != F_SIMPLE || L.epi.metric == M_HAMMING) &&
                       ((fam0 != F_DL && fam0 != F_WF) || b->len1 <= 64);  // the two DP kernels: shared-memory rows up to 64
   if (use_lb) {
     L.lb = LbView{lb->perm, lb->lens, lb->goff, lb->gdata, lb->ngroups};
@@ -642,6 +658,7 @@ static rf_status score_view(const rf_batch* b, const CorpusView& cv, const LbAll
   L.out_is_f64 = want_f64 ? 1 : 0;
   L.stream = st;
   L.sm_count = sm_count_of(device);
+  L.jaro32 = opt.jaro32;
   const Family fam = family_of(L.epi.metric, L.epi.wclass);
   cudaError_t e;
   if (fam == F_SIMPLE) e = launch_simple(L, d_err);
@@ -653,15 +670,15 @@ static rf_status score_view(const rf_batch* b, const CorpusView& cv, const LbAll
     e = launch_dl(L);
   }
   else if (b->len1 <= 64) {
-    const int path = g_w1_path.load();
+    const int path = opt.w1_path;
     e = !use_lb ? launch_scan_w1(L) : path == 2 ? launch_scan_lbr(L) : launch_scan_lb(L);
   }
   else if (fam == F_JARO) e = launch_jaro_mw(L);
-  else if (use_lb && L.query.limbs && g_mw_path.load() == 0 &&
-           !(g_band.load() && L.epi.metric == M_LEVENSHTEIN && L.epi.wclass == WC_UNIFORM && L.epi.kind == K_DISTANCE &&
+  else if (use_lb && L.query.limbs && opt.mw_path == 0 &&
+           !(opt.band && L.epi.metric == M_LEVENSHTEIN && L.epi.wclass == WC_UNIFORM && L.epi.kind == K_DISTANCE &&
              L.epi.has_cutoff && L.epi.cutoff_u / L.epi.w_ins <= 63))
     e = launch_scan_lbn(L);  // 65..512 elements on a resident corpus: thread per candidate, column in registers
-  else if (g_band.load() && L.epi.metric == M_LEVENSHTEIN && L.epi.wclass == WC_UNIFORM && L.epi.kind == K_DISTANCE &&
+  else if (opt.band && L.epi.metric == M_LEVENSHTEIN && L.epi.wclass == WC_UNIFORM && L.epi.kind == K_DISTANCE &&
            L.epi.has_cutoff && L.epi.cutoff_u / L.epi.w_ins <= 63)
     e = launch_scan_band(L, (uint32_t)(L.epi.cutoff_u / L.epi.w_ins));  // small cutoff: 64-bit Ukkonen band per thread
   else if (L.query.words > 256) e = launch_scan_long(L);  // beyond 16 384 elements: column in stripes, carries through scratch
@@ -823,6 +840,7 @@ static const rf_batch* compact_sub(const rf_batch* b, const rf_corpus* c) {
   }
   rf_batch* sub = nullptr;
   if (batch_create_bytes(b->metric, renamed.data(), (uint32_t)renamed.size(), b->device, &sub) != RF_OK) return nullptr;
+  sub->opt = b->opt;
   // Never evicted while the parent lives: a concurrent (or still enqueued, asynchronous) scoring call on the same
   // rf_batch may be using any cached entry.  One entry per distinct compact corpus ever scored (~100 KB of device
   // memory each); all are released by rf_batch_destroy.

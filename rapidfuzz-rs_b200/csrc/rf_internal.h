@@ -25,7 +25,14 @@ struct rf_corpus {
   std::vector<uint8_t> dict_codes;   // [kAlphaSlots] 0 = empty slot
 };
 
+// kernel-choice knobs, copied from the process-wide defaults (rf_set_option) when the comparator is created and changed
+// per comparator with rf_batch_set_option
+struct rf_batch_opts {
+  int w1_path = 0, mw_path = 0, band = 1, jaro32 = 1;
+};
+
 struct rf_batch {
+  rf_batch_opts opt;
   int device = 0;
   rf_metric metric = RF_LEVENSHTEIN;
   std::vector<uint8_t> s1;

@@ -22,7 +22,6 @@
 namespace rfk {
 
 static std::atomic<uint64_t> g_launches{0};
-static int g_jaro32 = 1;  // Jaro with query <= 32: row-wise 32-bit kernel (0: generic per-lane routine)
 uint64_t kernel_launch_count() { return g_launches.load(); }
 void count_launches(uint64_t n) { g_launches.fetch_add(n); }
 
@@ -1230,11 +1229,10 @@ cudaError_t launch_scan_lb(const ScanLaunch& L) {
       return w32 ? launch_lb_inst<F_LCS, uint32_t, 256>(L, L.query.tab32_bot)
                  : launch_lb_inst<F_LCS, uint64_t, 512>(L, L.query.tab64_bot);
     default:
-      if (L.query.len1 >= 1 && L.query.len1 <= 32 && g_jaro32) return launch_jaro32(L);
+      if (L.query.len1 >= 1 && L.query.len1 <= 32 && L.jaro32) return launch_jaro32(L);
       return launch_lb_inst<F_JARO, uint64_t, 512>(L, L.query.tab64_bot);
   }
 }
-void set_jaro32(int on) { g_jaro32 = on; }
 
 // ------------------------------------------------------------------------------------------------ lb ring (TMA)
 // Same work as scan_lb_kernel (warp per group of 32 equal-length candidates of the interleaved layout), but the

@@ -77,6 +77,7 @@ struct ScanLaunch {
   int out_is_f64;
   cudaStream_t stream;
   int sm_count;
+  int jaro32;         // Jaro / Jaro-Winkler, query <= 32: 1 = row-wise 32-bit kernel, 0 = generic per-lane routine
 };
 
 // Single-word path (query <= 64), CSR input: thread per candidate over TMA-staged tiles bucketed by length in-kernel.
@@ -152,7 +153,6 @@ cudaError_t launch_select(const SelectLaunch& L);
 void count_launches(uint64_t n);
 
 uint64_t kernel_launch_count();
-void set_jaro32(int on);  // tuning/testing: 0 = Jaro queries <= 32 use the generic per-lane routine
 
 // Stream-ordered device allocations from the device's default memory pool (release threshold = never), so that
 // creating / destroying multi-GB corpora repeatedly does not pay cudaMalloc / cudaFree page-table work each time.

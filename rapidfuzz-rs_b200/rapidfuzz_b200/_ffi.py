@@ -49,6 +49,7 @@ SYMBOLS = {
     "rf_batch_create_u8": (_int, [_int, _vp, _u32, _int, C.POINTER(_vp)]),
     "rf_batch_create_u32": (_int, [_int, _vp, _u32, _int, C.POINTER(_vp)]),
     "rf_batch_destroy": (_int, [_vp]),
+    "rf_batch_set_option": (_int, [_vp, C.c_char_p, _int]),
     "rf_batch_score_u32": (_int, [_vp, _vp, _int, _PA, _vp]),
     "rf_batch_score_f64": (_int, [_vp, _vp, _int, _PA, _vp]),
     "rf_batch_score_u32_device": (_int, [_vp, _vp, _int, _PA, _vp, _vp]),

@@ -350,3 +350,114 @@ def test_streaming_with_length_bytes_and_byte_results(chunk_mb, chunk_kcand):
     finally:
         _ffi.check(L.rf_set_option(b"stream_chunk_mb", 64))
         _ffi.check(L.rf_set_option(b"stream_chunk_kcand", 2048))
+
+
+# ------------------------------------------------------------------------------------------------ concurrency / options
+def test_eight_threads_share_handles():
+    """rfgpu.h promises that concurrent calls on shared handles are safe (BatchComparator is
+    Clone + Send + Sync in the reference, levenshtein.rs:1635-1639).  8 host threads share ONE corpus and the same
+    comparators and mix score / extract / filter / stream / cdist / u32-renaming calls (ctypes drops the GIL inside the
+    library); every result must equal the oracle."""
+    from rapidfuzz_b200 import sharding
+    q = synth.synth_query(21, 32)
+    q2 = synth.synth_query(22, 200)
+    chars, offsets = synth.synth_corpus(21, q, 200_000, 8, 64, 16)
+    lens = np.diff(offsets.astype(np.int64)).astype(np.uint8)
+    corpus = rf.Corpus(chars, offsets)
+    lev, jw, ind, mw = _bc("levenshtein", q), _bc("jaro_winkler", q), _bc("indel", q), _bc("levenshtein", q2)
+    wide = _bc("levenshtein", q.astype(np.uint32))
+    exp_lev = orc.batch("levenshtein", "distance", q, chars, offsets, nthreads=0)
+    exp_cut = orc.batch("levenshtein", "distance", q, chars, offsets, nthreads=0, cutoff=10)
+    exp_jw = orc.batch("jaro_winkler", "similarity", q, chars, offsets, nthreads=0)
+    exp_ind = orc.batch("indel", "normalized_similarity", q, chars, offsets, nthreads=0)
+    exp_mw = orc.batch("levenshtein", "distance", q2, chars, offsets, nthreads=0)
+    order = np.lexsort((np.arange(len(exp_lev)), exp_lev))[:9]
+    hits = np.nonzero(exp_cut != 0xFFFFFFFF)[0]
+    qs = [synth.synth_query(300 + i, 32) for i in range(4)]
+    exp_cd = []
+    for qq in qs:
+        d = orc.batch("levenshtein", "distance", qq, chars, offsets, nthreads=0).astype(np.int64)
+        exp_cd.append(np.sort(d * (1 << 32) + np.arange(len(d)))[:5])
+    errors = []
+
+    def work(tid):
+        try:
+            for it in range(6):
+                op = (tid + it) % 8
+                if op == 0:
+                    assert np.array_equal(lev.distance(corpus), exp_lev), "score"
+                elif op == 1:
+                    r = lev.distance_with_args(corpus, Args().score_cutoff(10))
+                    assert np.array_equal(r.filled(0xFFFFFFFF), exp_cut), "cutoff"
+                elif op == 2:
+                    assert np.array_equal(jw.similarity(corpus), exp_jw), "jaro_winkler"
+                elif op == 3:
+                    gi, gs = lev.extract("distance", corpus, k=9)
+                    assert np.array_equal(gi, order.astype(np.uint32)) and np.array_equal(gs, exp_lev[order]), "extract"
+                    fi, fs, tot = lev.filter("distance", corpus, Args().score_cutoff(10))
+                    assert tot == len(hits) and np.array_equal(fi, hits.astype(np.uint32)), "filter"
+                elif op == 4:
+                    assert np.array_equal(lev.stream("distance", chars, offsets), exp_lev), "stream"
+                    assert np.array_equal(lev.stream_len8("distance", chars, lens, u8_results=True), exp_lev.astype(np.uint8)), "len8"
+                elif op == 5:
+                    gi, gd = rf.cdist_topk([bytes(x) for x in qs], corpus, k=5)
+                    for qi, keys in enumerate(exp_cd):
+                        assert np.array_equal(gi[qi], (keys & 0xFFFFFFFF).astype(np.uint32)) and np.array_equal(gd[qi], (keys >> 32).astype(np.uint32)), "cdist"
+                elif op == 6:
+                    assert np.array_equal(ind.normalized_similarity(corpus), exp_ind), "indel"
+                    assert np.array_equal(wide.distance(corpus), exp_lev), "u32 query on a byte corpus"
+                else:
+                    assert np.array_equal(mw.distance(corpus), exp_mw), "multi-word"
+        except BaseException as e:   # noqa: BLE001 -- reported by the main thread
+            errors.append((tid, repr(e)))
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for b in (lev, jw, ind, mw, wide):
+        b.close()
+    corpus.close()
+
+
+def test_options_are_per_comparator():
+    """The kernel-choice knobs are copied into a comparator at creation (rf_batch_set_option changes one comparator):
+    two comparators with different settings give the same results side by side, and flipping the process-wide default
+    afterwards does not touch them."""
+    L = _ffi.lib()
+    q = synth.synth_query(5, 32)
+    q3 = synth.synth_query(6, 256)
+    chars, offsets = synth.synth_corpus(5, q, 50_000, 8, 64, 16)
+    c3, o3 = synth.synth_corpus(6, q3, 20_000, 64, 256, 48)
+    corpus, corpus3 = rf.Corpus(chars, offsets), rf.Corpus(c3, o3)
+    exp = orc.batch("levenshtein", "distance", q, chars, offsets, nthreads=0)
+    expj = orc.batch("jaro", "similarity", q, chars, offsets, nthreads=0)
+    exp3 = orc.batch("levenshtein", "distance", q3, c3, o3, nthreads=0, cutoff=40)
+    a, b, c = _bc("levenshtein", q), _bc("levenshtein", q), _bc("levenshtein", q)
+    _ffi.check(L.rf_batch_set_option(b._h, b"single_word_path", 1))
+    _ffi.check(L.rf_batch_set_option(c._h, b"single_word_path", 2))
+    j0, j1 = _bc("jaro", q), _bc("jaro", q)
+    _ffi.check(L.rf_batch_set_option(j1._h, b"jaro32", 0))
+    m0, m1, m2 = _bc("levenshtein", q3), _bc("levenshtein", q3), _bc("levenshtein", q3)
+    _ffi.check(L.rf_batch_set_option(m1._h, b"multi_word_path", 1))
+    _ffi.check(L.rf_batch_set_option(m2._h, b"banded_levenshtein", 0))
+    _ffi.check(L.rf_set_option(b"single_word_path", 1))     # a default flipped later must not reach existing comparators
+    try:
+        n0 = L.rf_kernel_launch_count()
+        for x in (a, b, c):
+            assert np.array_equal(x.distance(corpus), exp)
+        for x in (j0, j1):
+            assert np.array_equal(x.similarity(corpus), expj)
+        for x in (m0, m1, m2):
+            assert np.array_equal(x.distance_with_args(corpus3, Args().score_cutoff(40)).filled(0xFFFFFFFF), exp3)
+        assert L.rf_kernel_launch_count() > n0
+        with pytest.raises(rf.RfError):
+            _ffi.check(L.rf_batch_set_option(a._h, b"stream_chunk_mb", 1))
+    finally:
+        _ffi.check(L.rf_set_option(b"single_word_path", 0))
+    for x in (a, b, c, j0, j1, m0, m1, m2):
+        x.close()
+    corpus.close()
+    corpus3.close()

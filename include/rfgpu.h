@@ -109,6 +109,18 @@ rf_status rf_corpus_create_device_u8(const uint8_t* d_chars, const uint64_t* d_o
  * two's-complement 32-bit pattern of negative values -- on both the query and the candidate side (what the Python
  * mirror's widen_elems does); do not mix negative values with unsigned values >= 2^31 in one comparison. */
 rf_status rf_corpus_create_u32(const uint32_t* elems, const uint64_t* offsets, uint64_t n, int device, rf_corpus** out);
+/* Any element type of the reference (HashableChar: u8..u64, i8..i64, char = u32; details/common.rs:29-37).  Elements are
+ * compared BY VALUE like hash_char does: the library widens them to the u32 domain it scores in (unsigned zero-extended,
+ * signed as the two's-complement pattern of the value).  64-bit values outside [-2^31, 2^32) -> RF_ERR_UNSUPPORTED.  A
+ * comparison that would pair negative signed elements on one side with unsigned elements >= 2^31 on the other (equal
+ * 32-bit patterns, never equal in the reference: Hash::SIGNED vs Hash::UNSIGNED) is refused with RF_ERR_UNSUPPORTED at
+ * scoring time instead of being answered wrongly.  RF_ELEM_U8 is the plain byte path. */
+typedef enum rf_elem_type {
+  RF_ELEM_U8 = 0, RF_ELEM_U16 = 1, RF_ELEM_U32 = 2, RF_ELEM_U64 = 3,
+  RF_ELEM_I8 = 4, RF_ELEM_I16 = 5, RF_ELEM_I32 = 6, RF_ELEM_I64 = 7
+} rf_elem_type;
+rf_status rf_corpus_create_elems(const void* elems, rf_elem_type type, const uint64_t* offsets, uint64_t n, int device,
+                                 rf_corpus** out);
 /* Waits for the device to drain first (asynchronous *_device calls may still be reading the corpus). */
 rf_status rf_corpus_destroy(rf_corpus* c);
 uint64_t rf_corpus_size(const rf_corpus* c);        /* number of candidates */
@@ -125,6 +137,9 @@ rf_status rf_batch_create_u8(rf_metric metric, const uint8_t* query, uint32_t qu
  * the scores are identical to the reference's hashmap-based lookup (pattern_match_vector.rs:20-65, :226-280).
  * Works against u8 and u32 corpora; costs one extra pass over the candidates per call. */
 rf_status rf_batch_create_u32(rf_metric metric, const uint32_t* query, uint32_t query_len, int device, rf_batch** out);
+/* query of any element type (see rf_corpus_create_elems); the comparator scores u8 and u32 / typed corpora alike */
+rf_status rf_batch_create_elems(rf_metric metric, const void* query, rf_elem_type type, uint32_t query_len, int device,
+                                rf_batch** out);
 rf_status rf_batch_destroy(rf_batch* b);
 /* Kernel-choice knobs of ONE comparator ("single_word_path", "multi_word_path", "banded_levenshtein", "jaro32"; see
  * rf_set_option for their meaning).  A comparator copies the process-wide defaults when it is created; scoring calls
@@ -190,6 +205,12 @@ rf_status rf_batch_stream_f64(const rf_batch* b, const uint8_t* chars, const uin
 rf_status rf_batch_stream_f64_off32(const rf_batch* b, const uint8_t* chars, const uint32_t* offsets, uint64_t n,
                                     rf_kind kind, const rf_args* args, double* out_host);
 
+/* host-resident candidates with u32 elements (comparator from rf_batch_create_u32 / rf_batch_create_elems): a chunk
+ * crosses the link as 4-byte elements and is renamed to the query's byte alphabet on the device */
+rf_status rf_batch_stream_u32_elems32(const rf_batch* b, const uint32_t* elems, const uint64_t* offsets, uint64_t n, rf_kind kind,
+                                      const rf_args* args, uint32_t* out_host);
+rf_status rf_batch_stream_f64_elems32(const rf_batch* b, const uint32_t* elems, const uint64_t* offsets, uint64_t n, rf_kind kind,
+                                      const rf_args* args, double* out_host);
 /* Fewer bytes on the link (the call is PCIe-bound): candidates of at most 255 elements described by ONE length byte each
  * instead of a CSR start (lens[i] = length of candidate i, chars = the candidates back to back; the starts are rebuilt
  * on the device by a prefix sum), integer-valued (metric, kind) only.  _u8_: the scores come back as one byte each,
@@ -211,6 +232,13 @@ rf_status rf_cdist_topk_u8(const uint8_t* q_chars, const uint64_t* q_offsets, ui
 rf_status rf_cdist_topk_u8_device(const uint8_t* q_chars, const uint64_t* q_offsets, uint32_t nq,
                                   const rf_corpus* c, const rf_args* args, uint32_t k, uint32_t* idx_device,
                                   uint32_t* dist_device, void* stream);
+
+/* u32-element queries against a corpus made by rf_corpus_create_u32 that was renamed to bytes at creation (at most 255
+ * distinct symbols; a larger alphabet -> RF_ERR_UNSUPPORTED), or against a u8 corpus when every query symbol is a byte */
+rf_status rf_cdist_topk_u32(const uint32_t* q_elems, const uint64_t* q_offsets, uint32_t nq, const rf_corpus* c,
+                            const rf_args* args, uint32_t k, uint32_t* idx_host, uint32_t* dist_host);
+rf_status rf_cdist_topk_u32_device(const uint32_t* q_elems, const uint64_t* q_offsets, uint32_t nq, const rf_corpus* c,
+                                   const rf_args* args, uint32_t k, uint32_t* idx_device, uint32_t* dist_device, void* stream);
 
 /* Sharded corpora (one contiguous candidate range per GPU): global top-k from the per-shard
  * lists after ONE all-gather.  Part p's rows are idx_parts / dist_parts + p * part_stride, each [nq][k] as written

@@ -565,6 +565,77 @@ rf_status rf_batch_create_u32(rf_metric metric, const uint32_t* query, uint32_t 
   return RF_OK;
 }
 
+// Any HashableChar element type (details/common.rs:29-37) -> the u32 domain this library scores in, BY VALUE: unsigned
+// types zero-extend, signed types keep the two's-complement 32-bit pattern of the value.  *negative / *huge report whether
+// a negative value / an unsigned value >= 2^31 was seen (their 32-bit patterns would collide: the reference never equates
+// a negative signed with an unsigned element, Hash::SIGNED vs Hash::UNSIGNED).
+static rf_status widen_to_u32(const void* src, rf_elem_type t, uint64_t count, std::vector<uint32_t>* out, bool* negative, bool* huge) {
+  out->resize(count);
+  uint32_t* d = out->data();
+  int neg = 0, hug = 0, bad = 0;
+  switch (t) {
+    case RF_ELEM_U8: { const uint8_t* p = (const uint8_t*)src;
+#pragma omp parallel for schedule(static)
+      for (int64_t i = 0; i < (int64_t)count; ++i) d[i] = p[i]; break; }
+    case RF_ELEM_U16: { const uint16_t* p = (const uint16_t*)src;
+#pragma omp parallel for schedule(static)
+      for (int64_t i = 0; i < (int64_t)count; ++i) d[i] = p[i]; break; }
+    case RF_ELEM_U32: { const uint32_t* p = (const uint32_t*)src;
+#pragma omp parallel for schedule(static) reduction(| : hug)
+      for (int64_t i = 0; i < (int64_t)count; ++i) { d[i] = p[i]; hug |= p[i] >> 31; } break; }
+    case RF_ELEM_U64: { const uint64_t* p = (const uint64_t*)src;
+#pragma omp parallel for schedule(static) reduction(| : hug, bad)
+      for (int64_t i = 0; i < (int64_t)count; ++i) { d[i] = (uint32_t)p[i]; hug |= (int)((p[i] >> 31) & 1); bad |= (p[i] >> 32) != 0; } break; }
+    case RF_ELEM_I8: { const int8_t* p = (const int8_t*)src;
+#pragma omp parallel for schedule(static) reduction(| : neg)
+      for (int64_t i = 0; i < (int64_t)count; ++i) { d[i] = (uint32_t)(int32_t)p[i]; neg |= p[i] < 0; } break; }
+    case RF_ELEM_I16: { const int16_t* p = (const int16_t*)src;
+#pragma omp parallel for schedule(static) reduction(| : neg)
+      for (int64_t i = 0; i < (int64_t)count; ++i) { d[i] = (uint32_t)(int32_t)p[i]; neg |= p[i] < 0; } break; }
+    case RF_ELEM_I32: { const int32_t* p = (const int32_t*)src;
+#pragma omp parallel for schedule(static) reduction(| : neg)
+      for (int64_t i = 0; i < (int64_t)count; ++i) { d[i] = (uint32_t)p[i]; neg |= p[i] < 0; } break; }
+    case RF_ELEM_I64: { const int64_t* p = (const int64_t*)src;
+#pragma omp parallel for schedule(static) reduction(| : neg, bad)
+      for (int64_t i = 0; i < (int64_t)count; ++i) {
+        d[i] = (uint32_t)(int32_t)p[i]; neg |= p[i] < 0; bad |= (p[i] < -2147483648LL) | (p[i] > 4294967295LL); hug |= p[i] > 2147483647LL;
+      } break; }
+    default: return fail(RF_ERR_INVALID_ARG, "unknown element type");
+  }
+  if (bad) return fail(RF_ERR_UNSUPPORTED, "64-bit element values outside [-2^31, 2^32) are not supported");
+  *negative = neg != 0;
+  *huge = hug != 0;
+  return RF_OK;
+}
+
+rf_status rf_corpus_create_elems(const void* elems, rf_elem_type type, const uint64_t* offsets, uint64_t n, int device, rf_corpus** out) {
+  if (!out) return fail(RF_ERR_INVALID_ARG, "out is NULL");
+  *out = nullptr;
+  if (!offsets) return fail(RF_ERR_INVALID_ARG, "offsets is NULL");
+  if (type == RF_ELEM_U8) return rf_corpus_create_u8((const uint8_t*)elems, offsets, n, device, out);
+  if (offsets[n] && !elems) return fail(RF_ERR_INVALID_ARG, "elems is NULL");
+  std::vector<uint32_t> w;
+  bool neg = false, huge = false;
+  rf_status s = widen_to_u32(elems, type, offsets[n], &w, &neg, &huge);
+  if (s != RF_OK) return s;
+  s = rf_corpus_create_u32(w.data(), offsets, n, device, out);
+  if (s == RF_OK) { (*out)->has_negative = neg; (*out)->has_huge = huge; }
+  return s;
+}
+
+rf_status rf_batch_create_elems(rf_metric metric, const void* query, rf_elem_type type, uint32_t query_len, int device, rf_batch** out) {
+  if (!out) return fail(RF_ERR_INVALID_ARG, "out is NULL");
+  *out = nullptr;
+  if (query_len && !query) return fail(RF_ERR_INVALID_ARG, "query is NULL");
+  std::vector<uint32_t> w;
+  bool neg = false, huge = false;
+  rf_status s = widen_to_u32(query, type, query_len, &w, &neg, &huge);
+  if (s != RF_OK) return s;
+  s = rf_batch_create_u32(metric, w.data(), query_len, device, out);
+  if (s == RF_OK) { (*out)->has_negative = neg; (*out)->has_huge = huge; }
+  return s;
+}
+
 rf_status rf_batch_set_option(rf_batch* b, const char* name, int value) {
   if (!b || !name) return fail(RF_ERR_INVALID_ARG, "NULL argument");
   if (!strcmp(name, "single_word_path")) b->opt.w1_path = value;
@@ -855,6 +926,9 @@ static rf_status score_device(const rf_batch* b, const rf_corpus* c, rf_kind kin
   if (!b || !c) return fail(RF_ERR_INVALID_ARG, "NULL handle");
   if ((c->d_elems32 || c->compact32) && !b->wide)
     return fail(RF_ERR_INVALID_ARG, "a u32 corpus needs a comparator created with rf_batch_create_u32");
+  if ((b->has_negative && c->has_huge) || (b->has_huge && c->has_negative))
+    return fail(RF_ERR_UNSUPPORTED, "negative signed elements on one side and unsigned elements >= 2^31 on the other share 32-bit "
+                                    "patterns; the reference never equates them (Hash::SIGNED vs Hash::UNSIGNED)");
   if (c->compact32) {  // the corpus already is bytes in ITS alphabet: score with the query renamed through its dictionary
     if (b->device != c->device) return fail(RF_ERR_INVALID_ARG, "batch and corpus live on different devices");
     const rf_batch* sub = compact_sub(b, c);
@@ -1309,6 +1383,77 @@ rf_status stream_len8_impl(const rf_batch* b, const uint8_t* chars, const uint8_
   cudaFree(d_over);
   return s;
 }
+
+// rf_batch_stream_*_elems32: host-resident candidates with u32 elements.  A chunk is uploaded as 4-byte elements, renamed
+// to the query's byte alphabet on the device (remap_kernel) and scanned like a byte chunk.
+rf_status stream_elems32_impl(const rf_batch* b, const uint32_t* elems, const uint64_t* offsets, uint64_t n, rf_kind kind,
+                              const rf_args* args, void* out_host, bool want_f64) {
+  if (!b) return fail(RF_ERR_INVALID_ARG, "NULL handle");
+  if (!b->wide) return fail(RF_ERR_INVALID_ARG, "u32 candidates need a comparator created with rf_batch_create_u32");
+  if ((int)kind < 0 || (int)kind > 3) return fail(RF_ERR_INVALID_ARG, "unknown kind");
+  if ((rf_result_is_float(b->metric, kind) != 0) != want_f64)
+    return fail(RF_ERR_INVALID_ARG, want_f64 ? "this (metric, kind) yields u32 results; use the _u32 entry point"
+                                             : "this (metric, kind) yields f64 results; use the _f64 entry point");
+  if (n == 0) return RF_OK;
+  if (!offsets || !out_host) return fail(RF_ERR_INVALID_ARG, "NULL argument");
+  if (offsets[0] != 0) return fail(RF_ERR_INVALID_ARG, "offsets[0] must be 0");
+  if (offsets[n] && !elems) return fail(RF_ERR_INVALID_ARG, "elems is NULL");
+  if (rf_device_count() <= b->device) return fail(RF_ERR_CUDA, "no such CUDA device");
+  DeviceGuard g(b->device);
+  if (!g.ok) return fail(RF_ERR_CUDA, "cudaSetDevice failed");
+  StreamCtx* x = stream_ctx(b->device);
+  std::lock_guard<std::mutex> lk(x->mu);
+  const uint64_t cap_bytes = (uint64_t)(g_stream_mb.load() > 0 ? g_stream_mb.load() : 1) << 20;
+  const uint64_t cap_n = (uint64_t)(g_stream_kcand.load() > 0 ? g_stream_kcand.load() : 1) << 10;
+  const uint64_t cap_elems = cap_bytes / 4;  // the slot's char buffer holds the chunk's u32 elements
+  cudaError_t e = stream_ctx_prepare(x, cap_bytes, cap_n);
+  if (e != cudaSuccess) return cuda_fail(e, "streaming buffers");
+  const size_t rsz = want_f64 ? 8 : 4;
+  rf_status s = RF_OK;
+  uint64_t i0 = 0;
+  int k = 0;
+  while (i0 < n && s == RF_OK) {
+    const uint64_t E0 = offsets[i0] & ~3ull;  // element index, a multiple of 4: the renamed bytes stay 4-byte aligned
+    uint64_t hi = (n - i0 < cap_n) ? n : i0 + cap_n;
+    if (offsets[hi] - E0 > cap_elems) {
+      uint64_t lo = i0;
+      while (hi - lo > 1) {
+        const uint64_t mid = lo + (hi - lo) / 2;
+        if (offsets[mid] - E0 <= cap_elems) lo = mid; else hi = mid;
+      }
+      hi = lo;
+      if (hi == i0) { s = fail(RF_ERR_UNSUPPORTED, "a single candidate exceeds the streaming chunk size (raise stream_chunk_mb)"); break; }
+    }
+    const uint64_t i1 = hi, cn = i1 - i0, E1 = offsets[i1];
+    StreamSlot& sl = x->slot[k];
+    k = (k + 1) % kSlots;
+    if (!sl.d_renamed) {
+      if ((e = cudaMalloc(&sl.d_renamed, cap_bytes + 256)) == cudaSuccess) e = cudaMemsetAsync(sl.d_renamed, 0, cap_bytes + 256, sl.st);
+      if (e != cudaSuccess) { s = cuda_fail(e, "streaming buffers"); break; }
+    }
+    if (E1 > E0) e = cudaMemcpyAsync(sl.d_chars, elems + E0, (E1 - E0) * 4, cudaMemcpyHostToDevice, sl.st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(sl.d_offs, offsets + i0, (cn + 1) * 8, cudaMemcpyHostToDevice, sl.st);
+    if (e != cudaSuccess) { s = cuda_fail(e, "chunk upload"); break; }
+    if (E1 > E0) {
+      const uint64_t ce = E1 - E0, blocks = ((ce + 3) / 4 + 255) / 256;
+      const uint32_t grid = (uint32_t)(blocks < 148 * 16 ? blocks : 148 * 16);
+      remap_kernel<uint32_t><<<grid, 256, 0, sl.st>>>((const uint32_t*)sl.d_chars, ce, b->d_alpha_keys, b->d_alpha_codes, (uint32_t*)sl.d_renamed);
+      rfk::count_launches(1);
+      if ((e = cudaGetLastError()) != cudaSuccess) { s = cuda_fail(e, "alphabet renaming"); break; }
+    }
+    CorpusView cv{sl.d_renamed - E0, nullptr, (const uint64_t*)sl.d_offs, cn, E1 - offsets[i0], 0};
+    s = score_view(b, cv, nullptr, b->device, kind, args, sl.d_out, want_f64, sl.st);
+    if (s != RF_OK) break;
+    e = cudaMemcpyAsync((uint8_t*)out_host + i0 * rsz, sl.d_out, cn * rsz, cudaMemcpyDeviceToHost, sl.st);
+    if (e != cudaSuccess) { s = cuda_fail(e, "chunk download"); break; }
+    i0 = i1;
+  }
+  for (auto& sl : x->slot) {
+    e = cudaStreamSynchronize(sl.st);
+    if (e != cudaSuccess && s == RF_OK) s = cuda_fail(e, "streaming scan");
+  }
+  return s;
+}
 }  // namespace
 
 extern "C" {
@@ -1328,6 +1473,14 @@ rf_status rf_batch_stream_f64_off32(const rf_batch* b, const uint8_t* chars, con
                                     rf_kind kind, const rf_args* args, double* out_host) {
   return stream_impl(b, chars, offsets, n, kind, args, out_host, true);
 }
+rf_status rf_batch_stream_u32_elems32(const rf_batch* b, const uint32_t* elems, const uint64_t* offsets, uint64_t n, rf_kind kind,
+                                      const rf_args* args, uint32_t* out_host) {
+  return stream_elems32_impl(b, elems, offsets, n, kind, args, out_host, false);
+}
+rf_status rf_batch_stream_f64_elems32(const rf_batch* b, const uint32_t* elems, const uint64_t* offsets, uint64_t n, rf_kind kind,
+                                      const rf_args* args, double* out_host) {
+  return stream_elems32_impl(b, elems, offsets, n, kind, args, out_host, true);
+}
 rf_status rf_batch_stream_u32_len8(const rf_batch* b, const uint8_t* chars, const uint8_t* lens, uint64_t n, rf_kind kind,
                                    const rf_args* args, uint32_t* out_host) {
   return stream_len8_impl(b, chars, lens, n, kind, args, out_host, false);
@@ -1343,9 +1496,9 @@ extern "C" {
 // ------------------------------------------------------------------------------------------------ cdist
 static rf_status cdist_impl(const uint8_t* q_chars, const uint64_t* q_offsets, uint32_t nq, const rf_corpus* c,
                             const rf_args* args, uint32_t k, uint32_t* idx_out, uint32_t* dist_out, bool out_on_device,
-                            cudaStream_t user_stream) {
+                            cudaStream_t user_stream, bool queries_in_corpus_codes = false) {
   if (!c) return fail(RF_ERR_INVALID_ARG, "NULL corpus");
-  if (c->d_elems32 || c->compact32)
+  if (c->d_elems32 || (c->compact32 && !queries_in_corpus_codes))
     return fail(RF_ERR_UNSUPPORTED, "rf_cdist_topk_u8 needs a u8 corpus (this one was made by rf_corpus_create_u32; use rf_cdist_topk_u32)");
   if (nq == 0) return RF_OK;
   if (!q_offsets || !idx_out || !dist_out) return fail(RF_ERR_INVALID_ARG, "NULL argument");
@@ -1467,6 +1620,44 @@ rf_status rf_cdist_topk_u8_device(const uint8_t* q_chars, const uint64_t* q_offs
 rf_status rf_cdist_topk_u8(const uint8_t* q_chars, const uint64_t* q_offsets, uint32_t nq, const rf_corpus* c,
                            const rf_args* args, uint32_t k, uint32_t* idx_host, uint32_t* dist_host) {
   return cdist_impl(q_chars, q_offsets, nq, c, args, k, idx_host, dist_host, false, nullptr);
+}
+
+// u32-element queries against a u32 corpus that was renamed to bytes at creation (at most 255 distinct symbols, see
+// rf_corpus_create_u32): the queries are renamed through the corpus' dictionary on the host (symbols the corpus never
+// contains become 0, which matches nothing) and take the byte kernel.
+static rf_status cdist_u32_impl(const uint32_t* q_elems, const uint64_t* q_offsets, uint32_t nq, const rf_corpus* c,
+                                const rf_args* args, uint32_t k, uint32_t* idx_out, uint32_t* dist_out, bool on_device,
+                                cudaStream_t st) {
+  if (!c) return fail(RF_ERR_INVALID_ARG, "NULL corpus");
+  if (nq == 0) return RF_OK;
+  if (!q_offsets) return fail(RF_ERR_INVALID_ARG, "NULL argument");
+  if (q_offsets[nq] && !q_elems) return fail(RF_ERR_INVALID_ARG, "q_elems is NULL");
+  if (c->d_elems32)
+    return fail(RF_ERR_UNSUPPORTED, "rf_cdist_topk_u32: the corpus holds more than 255 distinct symbols (not renamed to bytes)");
+  std::vector<uint8_t> renamed(q_offsets[nq]);
+  for (uint64_t i = 0; i < q_offsets[nq]; ++i) {
+    const uint32_t x = q_elems[i];
+    if (c->compact32) {
+      uint32_t slot = alpha_hash(x);
+      while (c->dict_codes[slot] && c->dict_keys[slot] != x) slot = (slot + 1) & (kAlphaSlots - 1);
+      renamed[i] = c->dict_codes[slot];
+    } else {
+      renamed[i] = x < 256 ? (uint8_t)x : 0;  // a plain byte corpus: wider symbols match nothing ...
+    }
+  }
+  if (!c->compact32) {  // ... but 0 IS a byte there: give non-byte symbols a byte the corpus cannot equal is impossible in
+    for (uint64_t i = 0; i < q_offsets[nq]; ++i)  // general, so refuse them instead of guessing
+      if (q_elems[i] > 255) return fail(RF_ERR_UNSUPPORTED, "rf_cdist_topk_u32 on a u8 corpus: query symbols beyond 255");
+  }
+  return cdist_impl(renamed.data(), q_offsets, nq, c, args, k, idx_out, dist_out, on_device, st, true);
+}
+rf_status rf_cdist_topk_u32(const uint32_t* q_elems, const uint64_t* q_offsets, uint32_t nq, const rf_corpus* c,
+                            const rf_args* args, uint32_t k, uint32_t* idx_host, uint32_t* dist_host) {
+  return cdist_u32_impl(q_elems, q_offsets, nq, c, args, k, idx_host, dist_host, false, nullptr);
+}
+rf_status rf_cdist_topk_u32_device(const uint32_t* q_elems, const uint64_t* q_offsets, uint32_t nq, const rf_corpus* c,
+                                   const rf_args* args, uint32_t k, uint32_t* idx_device, uint32_t* dist_device, void* stream) {
+  return cdist_u32_impl(q_elems, q_offsets, nq, c, args, k, idx_device, dist_device, true, (cudaStream_t)stream);
 }
 
 rf_status rf_topk_merge_device(const uint32_t* idx_parts, const uint32_t* dist_parts, uint64_t part_stride,

@@ -13,6 +13,7 @@ RF_OK, RF_ERR_INVALID_ARG, RF_ERR_UNSUPPORTED, RF_ERR_CUDA, RF_ERR_OOM, RF_ERR_N
 METRICS = {"levenshtein": 0, "indel": 1, "lcs_seq": 2, "osa": 3, "jaro": 4, "jaro_winkler": 5, "ratio": 6,
            "hamming": 7, "prefix": 8, "postfix": 9, "damerau_levenshtein": 10}
 KINDS = {"distance": 0, "similarity": 1, "normalized_distance": 2, "normalized_similarity": 3}
+ELEM_TYPES = {"uint8": 0, "uint16": 1, "uint32": 2, "uint64": 3, "int8": 4, "int16": 5, "int32": 6, "int64": 7}
 NONE_U32 = 0xFFFFFFFF
 RF_MAX_QUERY_LEN = 4194304
 
@@ -42,12 +43,14 @@ SYMBOLS = {
     "rf_corpus_create_u8_off32": (_int, [_vp, _vp, _u64, _int, C.POINTER(_vp)]),
     "rf_corpus_create_device_u8": (_int, [_vp, _vp, _u64, _u64, _int, _vp, C.POINTER(_vp)]),
     "rf_corpus_create_u32": (_int, [_vp, _vp, _u64, _int, C.POINTER(_vp)]),
+    "rf_corpus_create_elems": (_int, [_vp, _int, _vp, _u64, _int, C.POINTER(_vp)]),
     "rf_corpus_destroy": (_int, [_vp]),
     "rf_corpus_size": (_u64, [_vp]),
     "rf_corpus_total_chars": (_u64, [_vp]),
     "rf_corpus_device": (_int, [_vp]),
     "rf_batch_create_u8": (_int, [_int, _vp, _u32, _int, C.POINTER(_vp)]),
     "rf_batch_create_u32": (_int, [_int, _vp, _u32, _int, C.POINTER(_vp)]),
+    "rf_batch_create_elems": (_int, [_int, _vp, _int, _u32, _int, C.POINTER(_vp)]),
     "rf_batch_destroy": (_int, [_vp]),
     "rf_batch_set_option": (_int, [_vp, C.c_char_p, _int]),
     "rf_batch_score_u32": (_int, [_vp, _vp, _int, _PA, _vp]),
@@ -69,10 +72,14 @@ SYMBOLS = {
     "rf_batch_stream_u32_off32": (_int, [_vp, _vp, _vp, _u64, _int, _PA, _vp]),
     "rf_batch_stream_f64": (_int, [_vp, _vp, _vp, _u64, _int, _PA, _vp]),
     "rf_batch_stream_f64_off32": (_int, [_vp, _vp, _vp, _u64, _int, _PA, _vp]),
+    "rf_batch_stream_u32_elems32": (_int, [_vp, _vp, _vp, _u64, _int, _PA, _vp]),
+    "rf_batch_stream_f64_elems32": (_int, [_vp, _vp, _vp, _u64, _int, _PA, _vp]),
     "rf_batch_stream_u32_len8": (_int, [_vp, _vp, _vp, _u64, _int, _PA, _vp]),
     "rf_batch_stream_u8_len8": (_int, [_vp, _vp, _vp, _u64, _int, _PA, _vp]),
     "rf_cdist_topk_u8": (_int, [_vp, _vp, _u32, _vp, _PA, _u32, _vp, _vp]),
     "rf_cdist_topk_u8_device": (_int, [_vp, _vp, _u32, _vp, _PA, _u32, _vp, _vp, _vp]),
+    "rf_cdist_topk_u32": (_int, [_vp, _vp, _u32, _vp, _PA, _u32, _vp, _vp]),
+    "rf_cdist_topk_u32_device": (_int, [_vp, _vp, _u32, _vp, _PA, _u32, _vp, _vp, _vp]),
     "rf_topk_merge_device": (_int, [_vp, _vp, _u64, _vp, _u32, _u32, _u32, _vp, _vp, _int, _vp]),
     "rf_corpus_create_sharded_u8": (_int, [_vp, _vp, _u64, _vp, _int, C.POINTER(_vp)]),
     "rf_sharded_corpus_destroy": (_int, [_vp]),

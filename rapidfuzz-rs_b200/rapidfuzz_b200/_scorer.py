@@ -126,6 +126,34 @@ class BatchComparatorBase:
         self.device = device
         self.query = q
 
+    @classmethod
+    def from_typed(cls, query, device=0):
+        """rf_batch_create_elems: an integer query of any width handed to the C ABI as it is."""
+        q = np.ascontiguousarray(query)
+        if q.dtype.name not in _ffi.ELEM_TYPES:
+            raise TypeError("unsupported element type %s" % q.dtype)
+        self = cls.__new__(cls)
+        h = C.c_void_p()
+        _ffi.check(_ffi.lib().rf_batch_create_elems(_ffi.METRICS[cls.METRIC], q.ctypes.data, _ffi.ELEM_TYPES[q.dtype.name], len(q),
+                                                   device, C.byref(h)))
+        self._h = h
+        self.device = device
+        self.query = np.zeros(0, np.uint32)   # marks the comparator as wide for _score
+        return self
+
+    def stream_elems32(self, kind, elems, offsets, args=None):
+        """rf_batch_stream_*_elems32: host-resident candidates with u32 elements (needs a u32 / typed comparator)."""
+        args = args if args is not None else Args()
+        elems = np.ascontiguousarray(elems, dtype=np.uint32)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        is_f = bool(_ffi.lib().rf_result_is_float(_ffi.METRICS[self.METRIC], _ffi.KINDS[kind]))
+        ca = args._c(is_f)
+        out = np.empty(n, dtype=np.float64 if is_f else np.uint32)
+        fn = _ffi.lib().rf_batch_stream_f64_elems32 if is_f else _ffi.lib().rf_batch_stream_u32_elems32
+        _ffi.check(fn(self._h, elems.ctypes.data, offsets.ctypes.data, n, _ffi.KINDS[kind], C.byref(ca), out.ctypes.data))
+        return out
+
     def close(self):
         if getattr(self, "_wide_twin", None) is not None:
             self._wide_twin.close()

@@ -50,6 +50,23 @@ class Corpus:
         return cls(e, offsets, device) if e.dtype == np.uint8 else cls.from_u32(e, offsets, device)
 
     @classmethod
+    def from_typed(cls, elems, offsets, device=0):
+        """rf_corpus_create_elems: integer elements of any width handed to the C ABI AS THEY ARE (u8 ... u64, i8 ... i64);
+        the library widens them by value (what from_elems does on the Python side)."""
+        elems = np.ascontiguousarray(elems)
+        if elems.dtype.name not in _ffi.ELEM_TYPES:
+            raise TypeError("unsupported element type %s" % elems.dtype)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        self = cls.__new__(cls)
+        h = C.c_void_p()
+        _ffi.check(_ffi.lib().rf_corpus_create_elems(elems.ctypes.data, _ffi.ELEM_TYPES[elems.dtype.name], offsets.ctypes.data,
+                                                    len(offsets) - 1, device, C.byref(h)))
+        self._h = h
+        self.device = device
+        self.wide = elems.dtype != np.uint8
+        return self
+
+    @classmethod
     def from_unicode(cls, strings, device=0):
         """Python str candidates as sequences of code points (what Rust's `.chars()` yields)."""
         cps = [np.fromiter((ord(ch) for ch in s), dtype=np.uint32, count=len(s)) for s in strings]
@@ -159,6 +176,23 @@ class CorpusFile:
 
     def __exit__(self, *a):
         self.close()
+
+
+def cdist_topk_u32(q_elems, q_offsets, corpus, k=10, score_cutoff=None):
+    """rf_cdist_topk_u32: u32-element queries (CSR) against a corpus made by Corpus.from_u32 / from_unicode."""
+    q_elems = np.ascontiguousarray(q_elems, dtype=np.uint32)
+    q_off = np.ascontiguousarray(q_offsets, dtype=np.uint64)
+    nq = len(q_off) - 1
+    a = _ffi.RfArgs()
+    _ffi.lib().rf_args_default(C.byref(a))
+    if score_cutoff is not None:
+        a.has_cutoff = 1
+        a.cutoff_u = int(score_cutoff)
+    idx = np.empty((nq, k), dtype=np.uint32)
+    dist = np.empty((nq, k), dtype=np.uint32)
+    _ffi.check(_ffi.lib().rf_cdist_topk_u32(q_elems.ctypes.data, q_off.ctypes.data, nq, corpus._h, C.byref(a), k,
+                                           idx.ctypes.data, dist.ctypes.data))
+    return idx, dist
 
 
 def cdist_topk(queries, corpus, k=10, score_cutoff=None):

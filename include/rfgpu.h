@@ -308,6 +308,26 @@ rf_status rf_sharded_stream_u32(const rf_sharded_batch* b, const uint8_t* chars,
 rf_status rf_sharded_stream_f64(const rf_sharded_batch* b, const uint8_t* chars, const uint64_t* offsets, uint64_t n, rf_kind kind,
                                 const rf_args* args, double* out_host);
 
+/* ---- one process per GPU (MPI / torchrun style hosts): a communicator over the ranks + scoring with the final
+ * all-gather of the score vectors (the path's only exchange step, north star: "NCCL all-gather only for the final score
+ * vector").  rank 0 calls rf_comm_unique_id and ships the 128 bytes to the other ranks by whatever means the host has;
+ * every rank then calls rf_comm_create_rank (collective).  rf_batch_score_*_allgather_device scores this rank's corpus
+ * and leaves ALL ranks' results in out_device, rank-major, in candidate order (out_capacity elements available;
+ * counts_out[nranks], optional, receives every rank's candidate count).  The shard is scanned in "allgather_chunks"
+ * pieces (default 4) and piece k travels over NVLink (grouped ncclBroadcast, in place, on an internal high-priority
+ * stream) while piece k+1 is being scanned; `stream` is ordered behind the last transfer.  Collective: every rank must
+ * make the same call. */
+typedef struct rf_comm rf_comm;
+rf_status rf_comm_unique_id(void* out128);
+rf_status rf_comm_create_rank(const void* id128, int nranks, int rank, int device, rf_comm** out);
+rf_status rf_comm_destroy(rf_comm* comm);
+int rf_comm_rank(const rf_comm* comm);
+int rf_comm_size(const rf_comm* comm);
+rf_status rf_batch_score_u32_allgather_device(const rf_batch* b, const rf_corpus* c, rf_comm* comm, rf_kind kind, const rf_args* args,
+                                              uint32_t* out_device, uint64_t out_capacity, uint64_t* counts_out, void* stream);
+rf_status rf_batch_score_f64_allgather_device(const rf_batch* b, const rf_corpus* c, rf_comm* comm, rf_kind kind, const rf_args* args,
+                                              double* out_device, uint64_t out_capacity, uint64_t* counts_out, void* stream);
+
 /* ---- packing and corpus files (host-side; the step before the scoring path).  The reference takes one iterator
  * per candidate (levenshtein.rs:1750-1762); callers holding a Vec<String> pack it once:
  *   rf_pack_u8: n strings given as (pointer, length) -> CSR offsets[n+1] (+ chars[offsets[n]] when chars_out != NULL;
@@ -353,6 +373,8 @@ rf_status rf_corpus_create_from_file(const char* path, int device, rf_corpus** o
  *   "cdist_slices" (default 0 = automatic, 1..256): corpus slices of rf_cdist_topk_* (work units = slices x queries);
  *   "sharded_collective" (default 0): 0 = NCCL for the gathers of the sharded entry points when the device list has no
  *        duplicates, 1 = event-ordered device-to-device copies;
+ *   "allgather_chunks" (default 4, 1..16): pieces a shard is scanned in by the *_allgather_device entry points; piece k is
+ *        gathered while piece k+1 is scanned (1 = scan everything, then gather);
  *   "cdist_skip" (default 1): rf_cdist_topk_* skips groups whose length alone puts them beyond the running k-th
  *        distance (0 = score every candidate; for measurements). */
 rf_status rf_set_option(const char* name, int value);

@@ -36,6 +36,7 @@ static std::atomic<int> g_cdist_slices{0};    // rf_cdist_topk_*: corpus slices 
 static std::atomic<int> g_cdist_skip{1};      // rf_cdist_topk_*: skip groups by length against the running k-th bound
 
 void rf__set_sharded_collective(int mode);  // rf_sharded.cu
+void rf__set_gather_chunks(int k);
 
 static rf_status fail(rf_status s, const std::string& msg) {
   g_last_error = msg;
@@ -138,6 +139,7 @@ rf_status rf_set_option(const char* name, int value) {
   if (!strcmp(name, "compact_u32_corpus")) { g_compact32.store(value ? 1 : 0); return RF_OK; }
   if (!strcmp(name, "cdist_skip")) { g_cdist_skip.store(value ? 1 : 0); return RF_OK; }
   if (!strcmp(name, "sharded_collective")) { rf__set_sharded_collective(value ? 1 : 0); return RF_OK; }
+  if (!strcmp(name, "allgather_chunks")) { if (value < 1 || value > 16) return fail(RF_ERR_INVALID_ARG, "allgather_chunks not in 1..16"); rf__set_gather_chunks(value); return RF_OK; }
   return fail(RF_ERR_INVALID_ARG, std::string("unknown option: ") + name);
 }
 
@@ -698,8 +700,18 @@ static rf_status make_epi(const rf_batch* b, rf_kind kind, const rf_args* args, 
 }
 
 // Scores the candidates described by `cv` (+ optional interleaved copy `lb`), all resident on `device`.
-static rf_status score_view(const rf_batch* b, const CorpusView& cv, const LbAlloc* lb, int device, rf_kind kind,
-                            const rf_args* args, void* out_dev, bool want_f64, cudaStream_t st, uint32_t* d_err = nullptr) {
+// [r0, r1): optional candidate sub-range (chunked launches of the overlapped scan + all-gather).  r0 must be a multiple of
+// LB_BLOCK; the results still land at out_dev[candidate index].
+static rf_status score_view(const rf_batch* b, const CorpusView& cv_in, const LbAlloc* lb, int device, rf_kind kind,
+                            const rf_args* args, void* out_dev, bool want_f64, cudaStream_t st, uint32_t* d_err = nullptr,
+                            uint64_t r0 = 0, uint64_t r1 = UINT64_MAX) {
+  CorpusView cv = cv_in;
+  if (r1 > cv.n) r1 = cv.n;
+  const bool ranged = r0 != 0 || r1 != cv.n;
+  if (ranged) {
+    if (r0 % LB_BLOCK != 0 || r0 > r1) return fail(RF_ERR_INVALID_ARG, "candidate range must start on a multiple of 65536");
+    if (r0 == r1) return RF_OK;
+  }
   if (!b) return fail(RF_ERR_INVALID_ARG, "NULL handle");
   if ((int)kind < 0 || (int)kind > 3) return fail(RF_ERR_INVALID_ARG, "unknown kind");
   if (b->device != device) return fail(RF_ERR_INVALID_ARG, "batch and corpus live on different devices");
@@ -718,8 +730,25 @@ static rf_status score_view(const rf_batch* b, const CorpusView& cv, const LbAll
   const rf_batch_opts opt = b->opt;  // per-comparator snapshot of the kernel-choice knobs
   const bool use_lb = lb && lb->gdata && opt.w1_path != 1 && (fam0 != F_SIMPLE || L.epi.metric == M_HAMMING) &&
                       ((fam0 != F_DL && fam0 != F_WF) || b->len1 <= 64);  // the two DP kernels: shared-memory rows up to 64
+  if (ranged) {
+    const bool dp = fam0 == F_DL || fam0 == F_WF || fam0 == F_SIMPLE;
+    if (use_lb && dp) return fail(RF_ERR_UNSUPPORTED, "candidate sub-ranges are not available for this metric on the interleaved layout");
+    if (!use_lb) {  // CSR kernels index candidates from 0: shift the view and the output
+      if (cv.off32) cv.off32 += r0; else cv.off64 += r0;
+      cv.n = r1 - r0;
+      out_dev = (uint8_t*)out_dev + r0 * (want_f64 ? 8 : 4);
+      L.corpus = cv;
+    }
+  }
   if (use_lb) {
     L.lb = LbView{lb->perm, lb->lens, lb->goff, lb->gdata, lb->ngroups};
+    if (ranged) {  // whole 65536-candidate blocks = whole groups; results are scattered through perm (absolute indices)
+      const uint64_t g0 = r0 / 32, g1 = (r1 + 31) / 32;
+      L.lb.perm += g0 * 32;
+      L.lb.lens += g0 * 32;
+      L.lb.goff += g0;
+      L.lb.ngroups = g1 - g0;
+    }
     L.lb_counter = counter_slot(device);
     L.lb_flag = counter_slot(device);
     if (!L.lb_counter || !L.lb_flag) return fail(RF_ERR_OOM, "scheduler scratch allocation failed");
@@ -1706,6 +1735,13 @@ rf_status stream_u32(const rf_batch* b, const uint8_t* chars, const uint32_t* of
   return stream_impl(b, chars, offsets, n, kind, args, out_host, want_f64, true);
 }
 int sm_count_of(int device) { return ::sm_count_of(device); }
+rf_status score_device_range(const rf_batch* b, const rf_corpus* c, rf_kind kind, const rf_args* args, void* out_dev, bool want_f64,
+                             cudaStream_t st, uint64_t r0, uint64_t r1) {
+  if (!b || !c) return ::fail(RF_ERR_INVALID_ARG, "NULL handle");
+  if (b->wide || c->d_elems32 || c->compact32) return ::fail(RF_ERR_UNSUPPORTED, "candidate sub-ranges need a byte comparator and a byte corpus");
+  return ::score_view(b, CorpusView{c->d_chars, c->d_off32, c->d_off64, c->n, c->total, c->max_len}, &c->lb, c->device, kind, args,
+                      out_dev, want_f64, st, nullptr, r0, r1);
+}
 rf_status corpus_create_sub(const uint8_t* chars, const uint64_t* offsets, uint64_t lo, uint64_t hi, int device, rf_corpus** out) {
   return ::corpus_create_host(chars, offsets + lo, true, hi - lo, device, out, offsets[lo]);
 }

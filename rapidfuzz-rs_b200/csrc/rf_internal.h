@@ -62,6 +62,10 @@ void set_last_error(const std::string& msg);
 // enqueue the scoring of every candidate of `c` on `st` (rf_batch_score_*_device)
 rf_status score_device(const rf_batch* b, const rf_corpus* c, rf_kind kind, const rf_args* args, void* out_dev, bool want_f64,
                        cudaStream_t st, uint32_t* d_err);
+// the same for the candidates [r0, r1) only (r0 a multiple of 65536; results at out_dev[candidate index]); byte comparator
+// + byte corpus, bit-parallel / Jaro metrics
+rf_status score_device_range(const rf_batch* b, const rf_corpus* c, rf_kind kind, const rf_args* args, void* out_dev, bool want_f64,
+                             cudaStream_t st, uint64_t r0, uint64_t r1);
 // rf_cdist_topk_u8[_device]
 rf_status cdist(const uint8_t* q_chars, const uint64_t* q_offsets, uint32_t nq, const rf_corpus* c, const rf_args* args, uint32_t k,
                 uint32_t* idx_out, uint32_t* dist_out, bool out_on_device, cudaStream_t stream);

@@ -28,7 +28,10 @@
 using namespace rfk;
 
 static std::atomic<int> g_coll_mode{0};  // 0: NCCL when the devices are distinct, 1: always copies
+static std::atomic<int> g_gather_chunks{4};  // scan + all-gather: the shard is scanned in this many pieces, piece k travels while piece k+1 is scanned
 void rf__set_sharded_collective(int mode) { g_coll_mode.store(mode); }
+void rf__set_gather_chunks(int k) { g_gather_chunks.store(k < 1 ? 1 : (k > 16 ? 16 : k)); }
+constexpr int kMaxChunks = 16;
 
 struct rf_sharded_corpus {
   std::vector<int> devices;
@@ -37,7 +40,9 @@ struct rf_sharded_corpus {
   uint64_t n = 0, total = 0;
   bool distinct = true;
   std::vector<cudaStream_t> streams;  // one per shard, on its device
+  std::vector<cudaStream_t> comm_streams;  // high priority: the gathers overlap the next piece's scan
   std::vector<cudaEvent_t> events;
+  std::vector<cudaEvent_t> chunk_events;   // [ndev][kMaxChunks + 1]
   std::mutex coll_mu;                 // collectives on one set of communicators are issued by one thread at a time
   bool comm_ready = false;
   std::vector<ncclComm_t> comms;
@@ -178,6 +183,91 @@ void split_by_bytes(const uint64_t* offsets, uint64_t n, size_t parts, std::vect
   (*lo)[parts] = n;
 }
 
+
+// ---- scan + all-gather with the transfer overlapped (both the one-process and the process-per-GPU form use this).
+// The local shard is scanned in K pieces of whole 65536-candidate blocks on the compute stream; as soon as piece k is
+// done (event) the high-priority communication stream broadcasts every rank's piece k in place (grouped ncclBroadcast =
+// all-gather-v) while piece k+1 is being scanned.  The compute stream finally waits for the last transfer.
+struct GatherLocal {
+  const rf_batch* b;
+  const rf_corpus* c;
+  int rank, device;
+  ncclComm_t comm;
+  cudaStream_t compute, comm_stream;
+  cudaEvent_t* ev;  // [kMaxChunks + 1]
+  void* out;        // this device's buffer for ALL ranks' results
+};
+
+bool chunkable(const rf_batch* b, const rf_corpus* c, const rf_args* a) {
+  if (b->wide || c->d_elems32 || c->compact32) return false;
+  switch (b->metric) {
+    case RF_LEVENSHTEIN:
+      if (!a) return true;
+      return a->insertion_cost == a->deletion_cost &&
+             (a->insertion_cost == a->substitution_cost || a->substitution_cost >= a->insertion_cost + a->deletion_cost);
+    case RF_INDEL: case RF_LCS_SEQ: case RF_OSA: case RF_JARO: case RF_JARO_WINKLER: case RF_RATIO: return true;
+    default: return false;
+  }
+}
+
+void piece_range(uint64_t n, int K, int k, uint64_t* a, uint64_t* z) {
+  const uint64_t per = ((n + K - 1) / K + LB_BLOCK - 1) / LB_BLOCK * LB_BLOCK;
+  *a = std::min<uint64_t>(n, (uint64_t)k * per);
+  *z = std::min<uint64_t>(n, (uint64_t)(k + 1) * per);
+}
+
+rf_status scan_allgather_nccl(GatherLocal* loc, int nloc, int nranks, const uint64_t* counts, rf_kind kind, const rf_args* args,
+                              bool want_f64) {
+  const size_t esz = want_f64 ? 8 : 4;
+  std::vector<uint64_t> lo(nranks + 1, 0);
+  for (int r = 0; r < nranks; ++r) lo[r + 1] = lo[r] + counts[r];
+  int K = g_gather_chunks.load();
+  for (int i = 0; i < nloc; ++i)
+    if (!chunkable(loc[i].b, loc[i].c, args)) K = 1;
+  if (nranks == 1) K = 1;
+  rf_status s = RF_OK;
+  for (int k = 0; k < K && s == RF_OK; ++k) {
+    for (int i = 0; i < nloc && s == RF_OK; ++i) {
+      GatherLocal& g = loc[i];
+      DevGuard dg(g.device);
+      uint64_t a, z;
+      piece_range(counts[g.rank], K, k, &a, &z);
+      void* mine = (uint8_t*)g.out + lo[g.rank] * esz;
+      if (z > a) {
+        s = (K == 1) ? rfi::score_device(g.b, g.c, kind, args, mine, want_f64, g.compute, nullptr)
+                     : rfi::score_device_range(g.b, g.c, kind, args, mine, want_f64, g.compute, a, z);
+        if (s != RF_OK) break;
+      }
+      cudaError_t e = cudaEventRecord(g.ev[k], g.compute);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(g.comm_stream, g.ev[k], 0);
+      if (e != cudaSuccess) s = rfi::cuda_fail(e, "scan/gather ordering");
+    }
+    if (s != RF_OK || nranks == 1) continue;
+    ncclResult_t r = ncclGroupStart();
+    if (r != ncclSuccess) return nccl_fail(r, "ncclGroupStart");
+    for (int i = 0; i < nloc && r == ncclSuccess; ++i) {
+      GatherLocal& g = loc[i];
+      for (int root = 0; root < nranks && r == ncclSuccess; ++root) {
+        uint64_t a, z;
+        piece_range(counts[root], K, k, &a, &z);
+        if (z == a) continue;
+        char* p = (char*)g.out + (lo[root] + a) * esz;
+        r = ncclBroadcast(p, p, (z - a) * esz, ncclUint8, root, g.comm, g.comm_stream);
+      }
+    }
+    ncclResult_t r2 = ncclGroupEnd();
+    if (r != ncclSuccess) return nccl_fail(r, "ncclBroadcast");
+    if (r2 != ncclSuccess) return nccl_fail(r2, "ncclGroupEnd");
+  }
+  for (int i = 0; i < nloc; ++i) {  // later work on the compute stream sees the gathered vector
+    GatherLocal& g = loc[i];
+    DevGuard dg(g.device);
+    cudaError_t e = cudaEventRecord(g.ev[kMaxChunks], g.comm_stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(g.compute, g.ev[kMaxChunks], 0);
+    if (e != cudaSuccess && s == RF_OK) s = rfi::cuda_fail(e, "scan/gather ordering");
+  }
+  return s;
+}
 }  // namespace
 
 extern "C" {
@@ -203,12 +293,19 @@ rf_status rf_corpus_create_sharded_u8(const uint8_t* chars, const uint64_t* offs
   split_by_bytes(offsets, n, (size_t)ndev, &c->lo);
   c->shard.assign(ndev, nullptr);
   c->streams.assign(ndev, nullptr);
+  c->comm_streams.assign(ndev, nullptr);
   c->events.assign(ndev, nullptr);
+  c->chunk_events.assign((size_t)ndev * (kMaxChunks + 1), nullptr);
   rf_status s = RF_OK;
   for (int i = 0; i < ndev && s == RF_OK; ++i) {
     DevGuard g(devices[i]);
+    int lo_pri = 0, hi_pri = 0;
+    cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);
     cudaError_t e = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->comm_streams[i], cudaStreamNonBlocking, hi_pri);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->events[i], cudaEventDisableTiming);
+    for (int k = 0; k <= kMaxChunks && e == cudaSuccess; ++k)
+      e = cudaEventCreateWithFlags(&c->chunk_events[(size_t)i * (kMaxChunks + 1) + k], cudaEventDisableTiming);
     if (e != cudaSuccess) s = rfi::cuda_fail(e, "sharded corpus streams");
   }
   // every shard uploads and builds its layout on its own device concurrently (one host thread per shard)
@@ -234,6 +331,9 @@ rf_status rf_sharded_corpus_destroy(rf_sharded_corpus* c) {
   for (size_t i = 0; i < c->devices.size(); ++i) {
     DevGuard g(c->devices[i]);
     if (c->events[i]) cudaEventDestroy(c->events[i]);
+    for (int k = 0; k <= kMaxChunks; ++k)
+      if (c->chunk_events[(size_t)i * (kMaxChunks + 1) + k]) cudaEventDestroy(c->chunk_events[(size_t)i * (kMaxChunks + 1) + k]);
+    if (c->comm_streams[i]) cudaStreamDestroy(c->comm_streams[i]);
     if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
   }
   delete c;
@@ -348,8 +448,26 @@ static rf_status sharded_score_allgather(const rf_sharded_batch* b, const rf_sha
   const size_t nd = c->devices.size(), esz = want_f64 ? 8 : 4;
   std::vector<uint64_t> off(nd + 1);
   for (size_t i = 0; i <= nd; ++i) off[i] = c->lo[i] * esz;
-  for (size_t i = 0; i < nd; ++i) {
+  for (size_t i = 0; i < nd; ++i)
     if (!out_device[i]) return rfi::fail(RF_ERR_INVALID_ARG, "out_device[i] is NULL");
+  if (nd > 1 && use_nccl(c)) {  // pieces of the scan overlap the transfer of the previous piece
+    std::lock_guard<std::mutex> lk(c->coll_mu);
+    s = ensure_comms(c);
+    if (s != RF_OK) return s;
+    std::vector<GatherLocal> loc(nd);
+    std::vector<uint64_t> counts(nd);
+    for (size_t i = 0; i < nd; ++i) {
+      counts[i] = c->lo[i + 1] - c->lo[i];
+      loc[i] = GatherLocal{b->per[i], c->shard[i], (int)i, c->devices[i], c->comms[i], c->streams[i], c->comm_streams[i],
+                           &c->chunk_events[i * (kMaxChunks + 1)], out_device[i]};
+    }
+    s = scan_allgather_nccl(loc.data(), (int)nd, (int)nd, counts.data(), kind, args, want_f64);
+    const std::string keep = s != RF_OK ? rfi::last_error() : std::string();
+    rf_status s2 = sync_all(c);
+    if (s != RF_OK) return rfi::fail(s, keep);
+    return s2;
+  }
+  for (size_t i = 0; i < nd; ++i) {
     const uint64_t cnt = c->lo[i + 1] - c->lo[i];
     DevGuard g(c->devices[i]);
     s = rfi::score_device(b->per[i], c->shard[i], kind, args, cnt ? (uint8_t*)out_device[i] + off[i] : nullptr, want_f64,
@@ -370,6 +488,107 @@ rf_status rf_sharded_score_u32_allgather_device(const rf_sharded_batch* b, const
 rf_status rf_sharded_score_f64_allgather_device(const rf_sharded_batch* b, const rf_sharded_corpus* c, rf_kind kind,
                                                 const rf_args* args, double* const* out_device) {
   return sharded_score_allgather(b, c, kind, args, (void* const*)out_device, true);
+}
+
+// ---- one process per GPU (MPI / torchrun style hosts): a communicator handle + the same overlapped scan + all-gather
+struct rf_comm {
+  int nranks = 1, rank = 0, device = 0;
+  ncclComm_t comm = nullptr;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev[kMaxChunks + 1] = {};
+  uint64_t* d_counts = nullptr;  // [nranks + 1]: all ranks' candidate counts, then mine
+  std::vector<uint64_t> counts;
+  const rf_corpus* counts_for = nullptr;
+  uint64_t counts_n = 0;
+  std::mutex mu;
+};
+
+rf_status rf_comm_unique_id(void* out128) {
+  if (!out128) return rfi::fail(RF_ERR_INVALID_ARG, "NULL argument");
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  ncclResult_t r = ncclGetUniqueId(&id);
+  if (r != ncclSuccess) return nccl_fail(r, "ncclGetUniqueId");
+  memcpy(out128, &id, 128);
+  return RF_OK;
+}
+
+rf_status rf_comm_create_rank(const void* id128, int nranks, int rank, int device, rf_comm** out) {
+  if (!out) return rfi::fail(RF_ERR_INVALID_ARG, "out is NULL");
+  *out = nullptr;
+  if (!id128 || nranks < 1 || rank < 0 || rank >= nranks) return rfi::fail(RF_ERR_INVALID_ARG, "id / nranks / rank");
+  if (device < 0 || device >= rf_device_count()) return rfi::fail(RF_ERR_CUDA, "no such CUDA device");
+  rf_comm* cm = new (std::nothrow) rf_comm();
+  if (!cm) return rfi::fail(RF_ERR_OOM, "host allocation failed");
+  cm->nranks = nranks;
+  cm->rank = rank;
+  cm->device = device;
+  DevGuard g(device);
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  ncclResult_t r = ncclCommInitRank(&cm->comm, nranks, id, rank);
+  if (r != ncclSuccess) { delete cm; return nccl_fail(r, "ncclCommInitRank"); }
+  int lo_pri = 0, hi_pri = 0;
+  cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);
+  cudaError_t e = cudaStreamCreateWithPriority(&cm->comm_stream, cudaStreamNonBlocking, hi_pri);
+  for (int k = 0; k <= kMaxChunks && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&cm->ev[k], cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaMalloc(&cm->d_counts, (size_t)(nranks + 1) * 8);
+  if (e != cudaSuccess) { rf_comm_destroy(cm); return rfi::cuda_fail(e, "communicator resources"); }
+  *out = cm;
+  return RF_OK;
+}
+
+rf_status rf_comm_destroy(rf_comm* cm) {
+  if (!cm) return RF_OK;
+  DevGuard g(cm->device);
+  if (cm->comm) ncclCommDestroy(cm->comm);
+  for (int k = 0; k <= kMaxChunks; ++k)
+    if (cm->ev[k]) cudaEventDestroy(cm->ev[k]);
+  if (cm->comm_stream) cudaStreamDestroy(cm->comm_stream);
+  if (cm->d_counts) cudaFree(cm->d_counts);
+  delete cm;
+  return RF_OK;
+}
+int rf_comm_rank(const rf_comm* cm) { return cm ? cm->rank : -1; }
+int rf_comm_size(const rf_comm* cm) { return cm ? cm->nranks : 0; }
+
+static rf_status comm_score_allgather(const rf_batch* b, const rf_corpus* c, rf_comm* cm, rf_kind kind, const rf_args* args,
+                                      void* out_device, uint64_t out_capacity, uint64_t* counts_out, bool want_f64, cudaStream_t st) {
+  if (!b || !c || !cm) return rfi::fail(RF_ERR_INVALID_ARG, "NULL handle");
+  if (c->device != cm->device || b->device != cm->device) return rfi::fail(RF_ERR_INVALID_ARG, "handles live on different devices");
+  std::lock_guard<std::mutex> lk(cm->mu);
+  DevGuard g(cm->device);
+  // every rank's candidate count (one tiny all-gather, cached per corpus)
+  if (cm->counts_for != c || cm->counts_n != c->n || (int)cm->counts.size() != cm->nranks) {
+    const uint64_t mine = c->n;
+    cm->counts.assign(cm->nranks, 0);
+    cudaError_t e = cudaMemcpyAsync(cm->d_counts + cm->nranks, &mine, 8, cudaMemcpyHostToDevice, cm->comm_stream);
+    if (e != cudaSuccess) return rfi::cuda_fail(e, "count exchange");
+    ncclResult_t r = ncclAllGather(cm->d_counts + cm->nranks, cm->d_counts, 1, ncclUint64, cm->comm, cm->comm_stream);
+    if (r != ncclSuccess) return nccl_fail(r, "ncclAllGather (counts)");
+    e = cudaMemcpyAsync(cm->counts.data(), cm->d_counts, (size_t)cm->nranks * 8, cudaMemcpyDeviceToHost, cm->comm_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cm->comm_stream);
+    if (e != cudaSuccess) return rfi::cuda_fail(e, "count exchange");
+    cm->counts_for = c;
+    cm->counts_n = c->n;
+  }
+  uint64_t total = 0;
+  for (int r = 0; r < cm->nranks; ++r) total += cm->counts[r];
+  if (counts_out) memcpy(counts_out, cm->counts.data(), (size_t)cm->nranks * 8);
+  if (total == 0) return RF_OK;
+  if (!out_device) return rfi::fail(RF_ERR_INVALID_ARG, "out_device is NULL");
+  if (out_capacity < total) return rfi::fail(RF_ERR_INVALID_ARG, "out_device holds fewer than the " + std::to_string(total) + " results of all ranks");
+  GatherLocal loc{b, c, cm->rank, cm->device, cm->comm, st, cm->comm_stream, cm->ev, out_device};
+  return scan_allgather_nccl(&loc, 1, cm->nranks, cm->counts.data(), kind, args, want_f64);
+}
+
+rf_status rf_batch_score_u32_allgather_device(const rf_batch* b, const rf_corpus* c, rf_comm* comm, rf_kind kind, const rf_args* args,
+                                              uint32_t* out_device, uint64_t out_capacity, uint64_t* counts_out, void* stream) {
+  return comm_score_allgather(b, c, comm, kind, args, out_device, out_capacity, counts_out, false, (cudaStream_t)stream);
+}
+rf_status rf_batch_score_f64_allgather_device(const rf_batch* b, const rf_corpus* c, rf_comm* comm, rf_kind kind, const rf_args* args,
+                                              double* out_device, uint64_t out_capacity, uint64_t* counts_out, void* stream) {
+  return comm_score_allgather(b, c, comm, kind, args, out_device, out_capacity, counts_out, true, (cudaStream_t)stream);
 }
 
 // ---- k best of the whole sharded corpus: per-shard selection on the devices, k entries per shard to the host, merged

@@ -100,6 +100,13 @@ SYMBOLS = {
     "rf_sharded_cdist_topk_u8": (_int, [_vp, _vp, _u32, _vp, _PA, _u32, _vp, _vp]),
     "rf_sharded_stream_u32": (_int, [_vp, _vp, _vp, _u64, _int, _PA, _vp]),
     "rf_sharded_stream_f64": (_int, [_vp, _vp, _vp, _u64, _int, _PA, _vp]),
+    "rf_comm_unique_id": (_int, [_vp]),
+    "rf_comm_create_rank": (_int, [_vp, _int, _int, _int, C.POINTER(_vp)]),
+    "rf_comm_destroy": (_int, [_vp]),
+    "rf_comm_rank": (_int, [_vp]),
+    "rf_comm_size": (_int, [_vp]),
+    "rf_batch_score_u32_allgather_device": (_int, [_vp, _vp, _vp, _int, _PA, _vp, _u64, _vp, _vp]),
+    "rf_batch_score_f64_allgather_device": (_int, [_vp, _vp, _vp, _int, _PA, _vp, _u64, _vp, _vp]),
     "rf_pack_u8": (_int, [_vp, _vp, _u64, _vp, _vp, _int]),
     "rf_corpus_file_write": (_int, [C.c_char_p, _vp, _vp, _u64]),
     "rf_corpus_file_open": (_int, [C.c_char_p, C.POINTER(_vp)]),

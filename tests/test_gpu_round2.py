@@ -574,3 +574,70 @@ def test_u32_streaming_and_cdist_entry_points():
         c2.close()
     finally:
         _ffi.check(L.rf_set_option(b"compact_u32_corpus", 1))
+
+
+# ------------------------------------------------------------------------------------------------ rf_comm (process-per-GPU form)
+def _comm_rank_worker(rank, nranks, uid, q, chars, offsets, out, errors, chunks):
+    try:
+        import torch
+        L = _ffi.lib()
+        n = len(offsets) - 1
+        lo, hi = (n * rank) // nranks // 3 * 3, (n * (rank + 1)) // nranks // 3 * 3 if rank + 1 < nranks else n   # unequal, unaligned shards
+        if rank == 0:
+            lo = 0
+        sub_off = (offsets[lo:hi + 1] - offsets[lo]).astype(np.uint64)
+        sub_chars = chars[int(offsets[lo]): int(offsets[hi])]
+        corpus = rf.Corpus(sub_chars, sub_off, device=rank)
+        comm = C.c_void_p()
+        _ffi.check(L.rf_comm_create_rank(uid, nranks, rank, rank, C.byref(comm)))
+        res = {}
+        for metric, kind, is_f in (("levenshtein", "distance", False), ("jaro_winkler", "similarity", True), ("hamming", "distance", False)):
+            b = _bc(metric, q, device=rank)
+            a = Args().pad(True)._c(is_f)
+            full = torch.full((n,), -1, dtype=torch.float64 if is_f else torch.int32, device="cuda:%d" % rank)
+            counts = (C.c_uint64 * nranks)()
+            fn = L.rf_batch_score_f64_allgather_device if is_f else L.rf_batch_score_u32_allgather_device
+            with torch.cuda.device(rank):
+                st = torch.cuda.current_stream().cuda_stream
+                for _ in range(2):   # the second call reuses the cached counts
+                    _ffi.check(fn(b._h, corpus._h, comm, _ffi.KINDS[kind], C.byref(a), full.data_ptr(), n, counts, st))
+                torch.cuda.synchronize()
+            res[metric] = full.cpu().numpy()
+            assert sum(counts) == n and counts[rank] == hi - lo
+            b.close()
+        out[rank] = res
+        L.rf_comm_destroy(comm)
+        corpus.close()
+    except BaseException as e:   # noqa: BLE001
+        errors.append((rank, repr(e)))
+
+
+@pytest.mark.parametrize("chunks", [4, 1, 16])
+def test_comm_allgather_overlapped_equals_oracle(chunks):
+    """rf_comm_* + rf_batch_score_*_allgather_device: every rank ends with ALL ranks' scores in candidate order; the shard
+    is scanned in pieces whose transfer overlaps the next piece's scan.  One rank per visible GPU (threads of this
+    process stand in for the host's processes); a single GPU runs the 1-rank form."""
+    L = _ffi.lib()
+    nranks = min(L.rf_device_count(), 8)
+    q = synth.synth_query(2, 32)
+    chars, offsets = synth.synth_corpus(2, q, 700_003, 8, 64, 16)
+    uid = C.create_string_buffer(128)
+    _ffi.check(L.rf_comm_unique_id(uid))
+    _ffi.check(L.rf_set_option(b"allgather_chunks", chunks))
+    out, errors = {}, []
+    try:
+        ths = [threading.Thread(target=_comm_rank_worker, args=(r, nranks, uid, q, chars, offsets, out, errors, chunks)) for r in range(nranks)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+    finally:
+        _ffi.check(L.rf_set_option(b"allgather_chunks", 4))
+    assert not errors, errors
+    exp = {"levenshtein": orc.batch("levenshtein", "distance", q, chars, offsets, nthreads=0),
+           "jaro_winkler": orc.batch("jaro_winkler", "similarity", q, chars, offsets, nthreads=0),
+           "hamming": orc.batch("hamming", "distance", q, chars, offsets, nthreads=0, pad=True)}
+    for r in range(nranks):
+        assert np.array_equal(out[r]["levenshtein"].view(np.uint32), exp["levenshtein"]), r
+        assert np.array_equal(out[r]["jaro_winkler"], exp["jaro_winkler"]), r
+        assert np.array_equal(out[r]["hamming"].view(np.uint32), exp["hamming"]), r

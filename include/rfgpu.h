@@ -313,9 +313,9 @@ rf_status rf_sharded_stream_f64(const rf_sharded_batch* b, const uint8_t* chars,
  * vector").  rank 0 calls rf_comm_unique_id and ships the 128 bytes to the other ranks by whatever means the host has;
  * every rank then calls rf_comm_create_rank (collective).  rf_batch_score_*_allgather_device scores this rank's corpus
  * and leaves ALL ranks' results in out_device, rank-major, in candidate order (out_capacity elements available;
- * counts_out[nranks], optional, receives every rank's candidate count).  The shard is scanned in "allgather_chunks"
- * pieces (default 4) and piece k travels over NVLink (grouped ncclBroadcast, in place, on an internal high-priority
- * stream) while piece k+1 is being scanned; `stream` is ordered behind the last transfer.  Collective: every rank must
+ * counts_out[nranks], optional, receives every rank's candidate count).  The transfer is a grouped ncclBroadcast, in place, on an internal
+ * high-priority stream ("allgather_chunks" > 1 scans the shard in pieces and sends piece k while piece k+1 is scanned);
+ * `stream` is ordered behind the last transfer.  Collective: every rank must
  * make the same call. */
 typedef struct rf_comm rf_comm;
 rf_status rf_comm_unique_id(void* out128);
@@ -371,10 +371,14 @@ rf_status rf_corpus_create_from_file(const char* path, int device, rf_corpus** o
  *   "compact_u32_corpus" (default 1): rf_corpus_create_u32 renames corpora of at most 255 distinct symbols to
  *        bytes once at creation (0 = keep u32 elements and rename per scoring call);
  *   "cdist_slices" (default 0 = automatic, 1..256): corpus slices of rf_cdist_topk_* (work units = slices x queries);
- *   "sharded_collective" (default 0): 0 = NCCL for the gathers of the sharded entry points when the device list has no
- *        duplicates, 1 = event-ordered device-to-device copies;
- *   "allgather_chunks" (default 4, 1..16): pieces a shard is scanned in by the *_allgather_device entry points; piece k is
- *        gathered while piece k+1 is scanned (1 = scan everything, then gather);
+ *   "sharded_collective" (default 0): the gathers of the one-process sharded entry points.  0 = automatic: the top-k lists
+ *        travel by NCCL; the score vectors of *_allgather_device by the copy engines over NVLink when every device pair
+ *        has peer access (DMA needs no SM, so piece k travels while piece k+1 is scanned), else by NCCL; a device
+ *        list with duplicates always uses copies.  1 = copies everywhere, 2 = NCCL everywhere;
+ *   "allgather_chunks" (default 0 = automatic, 1..16): pieces a shard is scanned in by the *_allgather_device entry points,
+ *        piece k gathered while piece k+1 is scanned (1 = scan everything, then gather).  Automatic = 4 on the
+ *        copy-engine path, 1 with NCCL: measured on 2 B200s, NCCL's broadcast kernels find no free CTA slot beside the
+ *        persistent scan kernel, so pieces buy nothing there;
  *   "cdist_skip" (default 1): rf_cdist_topk_* skips groups whose length alone puts them beyond the running k-th
  *        distance (0 = score every candidate; for measurements). */
 rf_status rf_set_option(const char* name, int value);

@@ -138,8 +138,8 @@ rf_status rf_set_option(const char* name, int value) {
   if (!strcmp(name, "cdist_slices")) { if (value < 0 || value > 256) return fail(RF_ERR_INVALID_ARG, "cdist_slices not in 0..256"); g_cdist_slices.store(value); return RF_OK; }
   if (!strcmp(name, "compact_u32_corpus")) { g_compact32.store(value ? 1 : 0); return RF_OK; }
   if (!strcmp(name, "cdist_skip")) { g_cdist_skip.store(value ? 1 : 0); return RF_OK; }
-  if (!strcmp(name, "sharded_collective")) { rf__set_sharded_collective(value ? 1 : 0); return RF_OK; }
-  if (!strcmp(name, "allgather_chunks")) { if (value < 1 || value > 16) return fail(RF_ERR_INVALID_ARG, "allgather_chunks not in 1..16"); rf__set_gather_chunks(value); return RF_OK; }
+  if (!strcmp(name, "sharded_collective")) { if (value < 0 || value > 2) return fail(RF_ERR_INVALID_ARG, "sharded_collective not in 0..2"); rf__set_sharded_collective(value); return RF_OK; }
+  if (!strcmp(name, "allgather_chunks")) { if (value < 0 || value > 16) return fail(RF_ERR_INVALID_ARG, "allgather_chunks not in 0..16"); rf__set_gather_chunks(value); return RF_OK; }
   return fail(RF_ERR_INVALID_ARG, std::string("unknown option: ") + name);
 }
 

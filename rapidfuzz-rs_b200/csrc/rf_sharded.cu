@@ -28,9 +28,11 @@
 using namespace rfk;
 
 static std::atomic<int> g_coll_mode{0};  // 0: NCCL when the devices are distinct, 1: always copies
-static std::atomic<int> g_gather_chunks{4};  // scan + all-gather: the shard is scanned in this many pieces, piece k travels while piece k+1 is scanned
-void rf__set_sharded_collective(int mode) { g_coll_mode.store(mode); }
-void rf__set_gather_chunks(int k) { g_gather_chunks.store(k < 1 ? 1 : (k > 16 ? 16 : k)); }
+// scan + all-gather: the shard is scanned in this many pieces, piece k travels while piece k+1 is scanned.  0 = automatic:
+// 4 on the copy-engine path (DMA overlaps the scan), 1 with NCCL (its kernels cannot run beside the persistent scan kernel)
+static std::atomic<int> g_gather_chunks{0};
+void rf__set_sharded_collective(int mode) { g_coll_mode.store(mode < 0 || mode > 2 ? 0 : mode); }
+void rf__set_gather_chunks(int k) { g_gather_chunks.store(k < 0 ? 0 : (k > 16 ? 16 : k)); }
 constexpr int kMaxChunks = 16;
 
 struct rf_sharded_corpus {
@@ -39,6 +41,7 @@ struct rf_sharded_corpus {
   std::vector<uint64_t> lo;  // [ndev + 1] first candidate of every shard
   uint64_t n = 0, total = 0;
   bool distinct = true;
+  bool peer_dma = true;               // every pair of devices has peer access enabled (NVLink DMA)
   std::vector<cudaStream_t> streams;  // one per shard, on its device
   std::vector<cudaStream_t> comm_streams;  // high priority: the gathers overlap the next piece's scan
   std::vector<cudaEvent_t> events;
@@ -94,6 +97,14 @@ rf_status for_each_shard(size_t count, Fn fn) {
 }
 
 bool use_nccl(const rf_sharded_corpus* c) { return c->distinct && g_coll_mode.load() == 0; }
+// the score-vector gather of the one-process form: copy engines over NVLink whenever every pair has peer access (the DMA
+// overlaps the scan), NCCL otherwise; "sharded_collective" = 2 forces NCCL, 1 forces copies
+bool gather_with_nccl(const rf_sharded_corpus* c) {
+  const int mode = g_coll_mode.load();
+  if (!c->distinct || mode == 1) return false;
+  if (mode == 2) return true;
+  return !c->peer_dma;
+}
 
 rf_status ensure_comms(rf_sharded_corpus* c) {
   if (c->comm_ready) return RF_OK;
@@ -216,12 +227,65 @@ void piece_range(uint64_t n, int K, int k, uint64_t* a, uint64_t* z) {
   *z = std::min<uint64_t>(n, (uint64_t)(k + 1) * per);
 }
 
+// The same with the copy engines instead of NCCL kernels (one process, peer access): device i PULLS piece k of every other
+// shard over NVLink on its communication stream as soon as that shard's compute stream has produced it.  DMA transfers
+// need no SM, so they overlap the persistent scan kernel of piece k+1 completely -- NCCL's broadcast kernels cannot: the
+// scan occupies every CTA slot, and the transfer of piece k only starts when piece k+1 retires (measured: no gain).
+rf_status scan_allgather_copies(rf_sharded_corpus* c, const rf_sharded_batch* b, rf_kind kind, const rf_args* args,
+                                void* const* out_device, bool want_f64) {
+  const int nd = (int)c->devices.size();
+  const size_t esz = want_f64 ? 8 : 4;
+  int K = g_gather_chunks.load();
+  if (K == 0) K = 4;
+  for (int i = 0; i < nd; ++i)
+    if (!chunkable(b->per[i], c->shard[i], args)) K = 1;
+  rf_status s = RF_OK;
+  auto ev = [&](int dev_i, int k) { return c->chunk_events[(size_t)dev_i * (kMaxChunks + 1) + k]; };
+  for (int k = 0; k < K && s == RF_OK; ++k) {
+    for (int i = 0; i < nd && s == RF_OK; ++i) {
+      DevGuard dg(c->devices[i]);
+      uint64_t a, z;
+      piece_range(c->lo[i + 1] - c->lo[i], K, k, &a, &z);
+      void* mine = (uint8_t*)out_device[i] + c->lo[i] * esz;
+      if (z > a)
+        s = (K == 1) ? rfi::score_device(b->per[i], c->shard[i], kind, args, mine, want_f64, c->streams[i], nullptr)
+                     : rfi::score_device_range(b->per[i], c->shard[i], kind, args, mine, want_f64, c->streams[i], a, z);
+      if (s != RF_OK) break;
+      const cudaError_t e = cudaEventRecord(ev(i, k), c->streams[i]);
+      if (e != cudaSuccess) s = rfi::cuda_fail(e, "cudaEventRecord");
+    }
+    for (int i = 0; i < nd && s == RF_OK; ++i) {
+      DevGuard dg(c->devices[i]);
+      for (int d = 1; d < nd && s == RF_OK; ++d) {
+        const int r = (i + d) % nd;  // staggered: at any moment every source serves a different destination
+        uint64_t a, z;
+        piece_range(c->lo[r + 1] - c->lo[r], K, k, &a, &z);
+        if (z == a) continue;
+        const uint64_t off = (c->lo[r] + a) * esz;
+        cudaError_t e = cudaStreamWaitEvent(c->comm_streams[i], ev(r, k), 0);
+        if (e == cudaSuccess)
+          e = cudaMemcpyPeerAsync((char*)out_device[i] + off, c->devices[i], (const char*)out_device[r] + off, c->devices[r],
+                                  (z - a) * esz, c->comm_streams[i]);
+        if (e != cudaSuccess) s = rfi::cuda_fail(e, "peer copy");
+      }
+    }
+  }
+  for (int i = 0; i < nd; ++i) {
+    DevGuard dg(c->devices[i]);
+    cudaError_t e = cudaEventRecord(ev(i, kMaxChunks), c->comm_streams[i]);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(c->streams[i], ev(i, kMaxChunks), 0);
+    if (e != cudaSuccess && s == RF_OK) s = rfi::cuda_fail(e, "scan/gather ordering");
+  }
+  return s;
+}
+
 rf_status scan_allgather_nccl(GatherLocal* loc, int nloc, int nranks, const uint64_t* counts, rf_kind kind, const rf_args* args,
                               bool want_f64) {
   const size_t esz = want_f64 ? 8 : 4;
   std::vector<uint64_t> lo(nranks + 1, 0);
   for (int r = 0; r < nranks; ++r) lo[r + 1] = lo[r] + counts[r];
   int K = g_gather_chunks.load();
+  if (K == 0) K = 1;
   for (int i = 0; i < nloc; ++i)
     if (!chunkable(loc[i].b, loc[i].c, args)) K = 1;
   if (nranks == 1) K = 1;
@@ -307,6 +371,21 @@ rf_status rf_corpus_create_sharded_u8(const uint8_t* chars, const uint64_t* offs
     for (int k = 0; k <= kMaxChunks && e == cudaSuccess; ++k)
       e = cudaEventCreateWithFlags(&c->chunk_events[(size_t)i * (kMaxChunks + 1) + k], cudaEventDisableTiming);
     if (e != cudaSuccess) s = rfi::cuda_fail(e, "sharded corpus streams");
+  }
+  // direct NVLink DMA between the shards' devices (without it cudaMemcpyPeerAsync stages through the host)
+  for (int i = 0; i < ndev && s == RF_OK; ++i) {
+    DevGuard g(devices[i]);
+    for (int j = 0; j < ndev; ++j) {
+      if (devices[j] == devices[i]) continue;
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, devices[i], devices[j]) == cudaSuccess && can) {
+        const cudaError_t e = cudaDeviceEnablePeerAccess(devices[j], 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) c->peer_dma = false;
+      } else {
+        c->peer_dma = false;
+      }
+      cudaGetLastError();
+    }
   }
   // every shard uploads and builds its layout on its own device concurrently (one host thread per shard)
   if (s == RF_OK)
@@ -450,7 +529,7 @@ static rf_status sharded_score_allgather(const rf_sharded_batch* b, const rf_sha
   for (size_t i = 0; i <= nd; ++i) off[i] = c->lo[i] * esz;
   for (size_t i = 0; i < nd; ++i)
     if (!out_device[i]) return rfi::fail(RF_ERR_INVALID_ARG, "out_device[i] is NULL");
-  if (nd > 1 && use_nccl(c)) {  // pieces of the scan overlap the transfer of the previous piece
+  if (nd > 1 && gather_with_nccl(c)) {
     std::lock_guard<std::mutex> lk(c->coll_mu);
     s = ensure_comms(c);
     if (s != RF_OK) return s;
@@ -467,14 +546,10 @@ static rf_status sharded_score_allgather(const rf_sharded_batch* b, const rf_sha
     if (s != RF_OK) return rfi::fail(s, keep);
     return s2;
   }
-  for (size_t i = 0; i < nd; ++i) {
-    const uint64_t cnt = c->lo[i + 1] - c->lo[i];
-    DevGuard g(c->devices[i]);
-    s = rfi::score_device(b->per[i], c->shard[i], kind, args, cnt ? (uint8_t*)out_device[i] + off[i] : nullptr, want_f64,
-                          c->streams[i], nullptr);
-    if (s != RF_OK) break;
+  {
+    std::lock_guard<std::mutex> lk(c->coll_mu);
+    s = scan_allgather_copies(c, b, kind, args, out_device, want_f64);
   }
-  if (s == RF_OK) s = allgatherv_inplace(c, out_device, off.data());
   const std::string keep = s != RF_OK ? rfi::last_error() : std::string();
   rf_status s2 = sync_all(c);
   if (s != RF_OK) return rfi::fail(s, keep);

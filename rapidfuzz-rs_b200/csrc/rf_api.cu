@@ -1442,7 +1442,7 @@ rf_status stream_elems32_impl(const rf_batch* b, const uint32_t* elems, const ui
   uint64_t i0 = 0;
   int k = 0;
   while (i0 < n && s == RF_OK) {
-    const uint64_t E0 = offsets[i0] & ~3ull;  // element index, a multiple of 4: the renamed bytes stay 4-byte aligned
+    const uint64_t E0 = offsets[i0] & ~15ull;  // element index, a multiple of 16: the renamed bytes keep the 16-byte alignment the tile kernels (TMA) need
     uint64_t hi = (n - i0 < cap_n) ? n : i0 + cap_n;
     if (offsets[hi] - E0 > cap_elems) {
       uint64_t lo = i0;

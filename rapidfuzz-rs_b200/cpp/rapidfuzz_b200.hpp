@@ -365,4 +365,90 @@ TopK cdist_topk(const Strings& queries, const Corpus& c, uint32_t k, const Args<
 }
 }  // namespace process
 
+// ONE process, several GPUs (rf_corpus_create_sharded_u8 ...): the corpus split by bytes over `devices`, results identical
+// to the single-GPU calls on the whole corpus.  The reference's comparator is Clone + Send + Sync plain data
+// (levenshtein.rs:1635-1639); these handles may be shared between threads the same way.
+namespace sharded {
+class Corpus {
+ public:
+  template <class Strings>
+  Corpus(const Strings& strings, std::vector<int> devices) : devices_(std::move(devices)) {
+    std::vector<uint8_t> chars;
+    std::vector<uint64_t> offsets{0};
+    for (const auto& s : strings) {
+      const std::string_view v(s);
+      chars.insert(chars.end(), v.begin(), v.end());
+      offsets.push_back(chars.size());
+    }
+    check(rf_corpus_create_sharded_u8(chars.data(), offsets.data(), offsets.size() - 1, devices_.data(), (int)devices_.size(), &h_));
+  }
+  Corpus(const Corpus&) = delete;
+  Corpus& operator=(const Corpus&) = delete;
+  ~Corpus() { rf_sharded_corpus_destroy(h_); }
+  uint64_t size() const { return rf_sharded_corpus_size(h_); }
+  const rf_sharded_corpus* handle() const { return h_; }
+  const std::vector<int>& devices() const { return devices_; }
+
+ private:
+  rf_sharded_corpus* h_ = nullptr;
+  std::vector<int> devices_;
+};
+
+// BatchComparator::new(query) of metric M, replicated on every device of the corpus
+template <rf_metric M>
+class BatchComparator {
+ public:
+  BatchComparator(std::string_view q, const std::vector<int>& devices) {
+    check(rf_sharded_batch_create_u8(M, (const uint8_t*)q.data(), (uint32_t)q.size(), devices.data(), (int)devices.size(), &h_));
+  }
+  BatchComparator(const BatchComparator&) = delete;
+  BatchComparator& operator=(const BatchComparator&) = delete;
+  ~BatchComparator() { rf_sharded_batch_destroy(h_); }
+  // integer-valued kinds; UINT32_MAX == None
+  std::vector<uint32_t> score_u32(const Corpus& c, rf_kind kind, const rf_args* a = nullptr) const {
+    std::vector<uint32_t> out(c.size());
+    check(rf_sharded_score_u32(h_, c.handle(), kind, a, out.data()));
+    return out;
+  }
+  std::vector<double> score_f64(const Corpus& c, rf_kind kind, const rf_args* a = nullptr) const {
+    std::vector<double> out(c.size());
+    check(rf_sharded_score_f64(h_, c.handle(), kind, a, out.data()));
+    return out;
+  }
+  std::vector<uint32_t> distance(const Corpus& c) const { return score_u32(c, RF_DISTANCE); }
+  // host-resident candidates: every device streams its part of the range over its own PCIe link
+  std::vector<uint32_t> stream_u32(const uint8_t* chars, const uint64_t* offsets, uint64_t n, rf_kind kind, const rf_args* a = nullptr) const {
+    std::vector<uint32_t> out(n);
+    check(rf_sharded_stream_u32(h_, chars, offsets, n, kind, a, out.data()));
+    return out;
+  }
+
+ private:
+  rf_sharded_batch* h_ = nullptr;
+};
+
+struct TopK {
+  uint32_t nq = 0, k = 0;
+  std::vector<uint64_t> index;     // [nq][k] GLOBAL candidate indices, UINT64_MAX = fewer than k hits
+  std::vector<uint32_t> distance;  // [nq][k]
+};
+template <class Strings>
+TopK cdist_topk(const Strings& queries, const Corpus& c, uint32_t k, const rf_args* a = nullptr) {
+  std::vector<uint8_t> chars;
+  std::vector<uint64_t> offsets{0};
+  for (const auto& q : queries) {
+    const std::string_view v(q);
+    chars.insert(chars.end(), v.begin(), v.end());
+    offsets.push_back(chars.size());
+  }
+  TopK r;
+  r.nq = (uint32_t)(offsets.size() - 1);
+  r.k = k;
+  r.index.resize((size_t)r.nq * k);
+  r.distance.resize((size_t)r.nq * k);
+  check(rf_sharded_cdist_topk_u8(chars.data(), offsets.data(), r.nq, c.handle(), a, k, r.index.data(), r.distance.data()));
+  return r;
+}
+}  // namespace sharded
+
 }  // namespace rapidfuzz_b200

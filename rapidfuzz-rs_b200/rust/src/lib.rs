@@ -28,6 +28,19 @@ pub struct rf_args {
 }
 #[repr(C)] pub struct rf_corpus { _p: [u8; 0] }
 #[repr(C)] pub struct rf_batch { _p: [u8; 0] }
+#[repr(C)] pub struct rf_sharded_corpus { _p: [u8; 0] }
+#[repr(C)] pub struct rf_sharded_batch { _p: [u8; 0] }
+#[repr(C)] pub struct rf_comm { _p: [u8; 0] }
+
+/// `rf_elem_type`: the reference's `HashableChar` element types (src/details/common.rs:29-37)
+pub const RF_ELEM_U8: c_int = 0;
+pub const RF_ELEM_U16: c_int = 1;
+pub const RF_ELEM_U32: c_int = 2;
+pub const RF_ELEM_U64: c_int = 3;
+pub const RF_ELEM_I8: c_int = 4;
+pub const RF_ELEM_I16: c_int = 5;
+pub const RF_ELEM_I32: c_int = 6;
+pub const RF_ELEM_I64: c_int = 7;
 
 pub const RF_LEVENSHTEIN: c_int = 0;
 pub const RF_INDEL: c_int = 1;
@@ -77,6 +90,33 @@ extern "C" {
     pub fn rf_batch_extract_f64(b: *const rf_batch, c: *const rf_corpus, kind: c_int, args: *const rf_args, k: u32, idx: *mut u32, score: *mut f64, n_out: *mut u32) -> c_int;
     pub fn rf_batch_filter_u32(b: *const rf_batch, c: *const rf_corpus, kind: c_int, args: *const rf_args, capacity: u64, idx: *mut u32, score: *mut u32, n_hits: *mut u64) -> c_int;
     pub fn rf_batch_filter_f64(b: *const rf_batch, c: *const rf_corpus, kind: c_int, args: *const rf_args, capacity: u64, idx: *mut u32, score: *mut f64, n_hits: *mut u64) -> c_int;
+    // any HashableChar element type, widened BY VALUE inside the library
+    pub fn rf_corpus_create_elems(elems: *const c_void, elem_type: c_int, offsets: *const u64, n: u64, device: c_int, out: *mut *mut rf_corpus) -> c_int;
+    pub fn rf_batch_create_elems(metric: c_int, query: *const c_void, elem_type: c_int, len: u32, device: c_int, out: *mut *mut rf_batch) -> c_int;
+    pub fn rf_batch_set_option(b: *mut rf_batch, name: *const c_char, value: c_int) -> c_int;
+    // fewer bytes on the link: one length byte per candidate in, one score byte per candidate out
+    pub fn rf_batch_stream_u32_len8(b: *const rf_batch, chars: *const u8, lens: *const u8, n: u64, kind: c_int, args: *const rf_args, out: *mut u32) -> c_int;
+    pub fn rf_batch_stream_u8_len8(b: *const rf_batch, chars: *const u8, lens: *const u8, n: u64, kind: c_int, args: *const rf_args, out: *mut u8) -> c_int;
+    pub fn rf_batch_stream_u32_elems32(b: *const rf_batch, elems: *const u32, offsets: *const u64, n: u64, kind: c_int, args: *const rf_args, out: *mut u32) -> c_int;
+    pub fn rf_cdist_topk_u32(q_elems: *const u32, q_offsets: *const u64, nq: u32, c: *const rf_corpus, args: *const rf_args, k: u32, idx: *mut u32, dist: *mut u32) -> c_int;
+    // ONE process, several GPUs: the corpus sharded by bytes over `devices`, results identical to the single-GPU calls
+    pub fn rf_corpus_create_sharded_u8(chars: *const u8, offsets: *const u64, n: u64, devices: *const c_int, ndev: c_int, out: *mut *mut rf_sharded_corpus) -> c_int;
+    pub fn rf_sharded_corpus_destroy(c: *mut rf_sharded_corpus) -> c_int;
+    pub fn rf_sharded_corpus_size(c: *const rf_sharded_corpus) -> u64;
+    pub fn rf_sharded_batch_create_u8(metric: c_int, query: *const u8, len: u32, devices: *const c_int, ndev: c_int, out: *mut *mut rf_sharded_batch) -> c_int;
+    pub fn rf_sharded_batch_destroy(b: *mut rf_sharded_batch) -> c_int;
+    pub fn rf_sharded_score_u32(b: *const rf_sharded_batch, c: *const rf_sharded_corpus, kind: c_int, args: *const rf_args, out: *mut u32) -> c_int;
+    pub fn rf_sharded_score_f64(b: *const rf_sharded_batch, c: *const rf_sharded_corpus, kind: c_int, args: *const rf_args, out: *mut f64) -> c_int;
+    pub fn rf_sharded_score_u32_allgather_device(b: *const rf_sharded_batch, c: *const rf_sharded_corpus, kind: c_int, args: *const rf_args, out_device: *const *mut u32) -> c_int;
+    pub fn rf_sharded_extract_u32(b: *const rf_sharded_batch, c: *const rf_sharded_corpus, kind: c_int, args: *const rf_args, k: u32, idx: *mut u64, score: *mut u32, n_out: *mut u32) -> c_int;
+    pub fn rf_sharded_cdist_topk_u8(q_chars: *const u8, q_offsets: *const u64, nq: u32, c: *const rf_sharded_corpus, args: *const rf_args, k: u32, idx: *mut u64, dist: *mut u32) -> c_int;
+    pub fn rf_sharded_stream_u32(b: *const rf_sharded_batch, chars: *const u8, offsets: *const u64, n: u64, kind: c_int, args: *const rf_args, out: *mut u32) -> c_int;
+    // one process per GPU: communicator + scoring with the final all-gather of the score vectors
+    pub fn rf_comm_unique_id(out128: *mut c_void) -> c_int;
+    pub fn rf_comm_create_rank(id128: *const c_void, nranks: c_int, rank: c_int, device: c_int, out: *mut *mut rf_comm) -> c_int;
+    pub fn rf_comm_destroy(comm: *mut rf_comm) -> c_int;
+    pub fn rf_batch_score_u32_allgather_device(b: *const rf_batch, c: *const rf_corpus, comm: *mut rf_comm, kind: c_int, args: *const rf_args,
+                                               out_device: *mut u32, out_capacity: u64, counts_out: *mut u64, stream: *mut c_void) -> c_int;
     // packing + corpus files
     pub fn rf_pack_u8(strings: *const *const u8, lengths: *const u64, n: u64, offsets_out: *mut u64, chars_out: *mut u8, nthreads: c_int) -> c_int;
     pub fn rf_corpus_file_write(path: *const c_char, chars: *const u8, offsets: *const u64, n: u64) -> c_int;
@@ -136,6 +176,70 @@ impl Corpus {
     pub fn len(&self) -> usize { unsafe { rf_corpus_size(self.h) as usize } }
 }
 impl Drop for Corpus { fn drop(&mut self) { unsafe { rf_corpus_destroy(self.h); } } }
+
+/// The candidates sharded over several GPUs of one box, driven by THIS process (no MPI, no PyTorch): the counterpart of
+/// `Corpus` for `rf_corpus_create_sharded_u8`.  `BatchComparator` is `Clone + Send + Sync` in the reference
+/// (src/distance/levenshtein.rs:1635-1639); so are these handles.
+pub struct ShardedCorpus { h: *mut rf_sharded_corpus, devices: Vec<c_int> }
+unsafe impl Send for ShardedCorpus {}
+unsafe impl Sync for ShardedCorpus {}
+impl ShardedCorpus {
+    pub fn new<I, S>(candidates: I, devices: &[i32]) -> Self where I: IntoIterator<Item = S>, S: AsRef<[u8]> {
+        let mut chars = Vec::new();
+        let mut offsets = vec![0u64];
+        for s in candidates { chars.extend_from_slice(s.as_ref()); offsets.push(chars.len() as u64); }
+        let devs: Vec<c_int> = devices.iter().map(|&d| d as c_int).collect();
+        let mut h = std::ptr::null_mut();
+        check(unsafe { rf_corpus_create_sharded_u8(chars.as_ptr(), offsets.as_ptr(), (offsets.len() - 1) as u64, devs.as_ptr(), devs.len() as c_int, &mut h) });
+        ShardedCorpus { h, devices: devs }
+    }
+    pub fn len(&self) -> usize { unsafe { rf_sharded_corpus_size(self.h) as usize } }
+    /// `levenshtein::BatchComparator::new(query).distance(c)` for every candidate of the sharded corpus, in candidate order.
+    pub fn levenshtein_distance<Q: AsRef<[u8]>>(&self, query: Q) -> Vec<usize> {
+        let q = query.as_ref();
+        let mut b = std::ptr::null_mut();
+        check(unsafe { rf_sharded_batch_create_u8(RF_LEVENSHTEIN, q.as_ptr(), q.len() as u32, self.devices.as_ptr(), self.devices.len() as c_int, &mut b) });
+        let mut out = vec![0u32; self.len()];
+        let st = unsafe { rf_sharded_score_u32(b, self.h, RF_DISTANCE, std::ptr::null(), out.as_mut_ptr()) };
+        unsafe { rf_sharded_batch_destroy(b) };
+        check(st);
+        out.into_iter().map(|v| v as usize).collect()
+    }
+    /// Many-vs-many over all shards: per query the `k` best (global index, distance); one NCCL all-gather of the per-shard lists.
+    pub fn cdist_topk<I, S>(&self, queries: I, k: u32) -> Vec<Vec<(u64, u32)>> where I: IntoIterator<Item = S>, S: AsRef<[u8]> {
+        let mut chars = Vec::new();
+        let mut offsets = vec![0u64];
+        for q in queries { chars.extend_from_slice(q.as_ref()); offsets.push(chars.len() as u64); }
+        let nq = offsets.len() - 1;
+        let mut idx = vec![u64::MAX; nq * k as usize];
+        let mut dist = vec![u32::MAX; nq * k as usize];
+        check(unsafe { rf_sharded_cdist_topk_u8(chars.as_ptr(), offsets.as_ptr(), nq as u32, self.h, std::ptr::null(), k, idx.as_mut_ptr(), dist.as_mut_ptr()) });
+        (0..nq).map(|q| (0..k as usize).map(|i| (idx[q * k as usize + i], dist[q * k as usize + i]))
+                                       .take_while(|&(i, _)| i != u64::MAX).collect()).collect()
+    }
+}
+impl Drop for ShardedCorpus { fn drop(&mut self) { unsafe { rf_sharded_corpus_destroy(self.h); } } }
+
+/// Element types other than `u8` / `char` go to the library as they are (`rf_*_create_elems` widens BY VALUE).
+pub trait Elem: Copy { const TYPE: c_int; }
+impl Elem for u8 { const TYPE: c_int = RF_ELEM_U8; }
+impl Elem for u16 { const TYPE: c_int = RF_ELEM_U16; }
+impl Elem for u32 { const TYPE: c_int = RF_ELEM_U32; }
+impl Elem for u64 { const TYPE: c_int = RF_ELEM_U64; }
+impl Elem for i8 { const TYPE: c_int = RF_ELEM_I8; }
+impl Elem for i16 { const TYPE: c_int = RF_ELEM_I16; }
+impl Elem for i32 { const TYPE: c_int = RF_ELEM_I32; }
+impl Elem for i64 { const TYPE: c_int = RF_ELEM_I64; }
+impl Corpus {
+    pub fn from_elems<T: Elem>(candidates: &[&[T]], device: i32) -> Self {
+        let mut elems: Vec<T> = Vec::new();
+        let mut offsets = vec![0u64];
+        for s in candidates { elems.extend_from_slice(s); offsets.push(elems.len() as u64); }
+        let mut h = std::ptr::null_mut();
+        check(unsafe { rf_corpus_create_elems(elems.as_ptr() as *const c_void, T::TYPE, offsets.as_ptr(), (offsets.len() - 1) as u64, device, &mut h) });
+        Corpus { h }
+    }
+}
 
 /// Many-vs-many (new on this side): for every query the `k` best candidates of `corpus` by (Levenshtein distance, index);
 /// rows with fewer than `k` hits are shorter.  Queries of at most 64 bytes.

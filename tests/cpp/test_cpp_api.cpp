@@ -79,6 +79,14 @@ int main() {
     auto tc = process::cdist_topk(std::vector<std::string>{"aabd"}, corpus, 3, Args<uint32_t>{}.score_cutoff(1));
     EXPECT(tc.at(0, 0).has_value() && !tc.at(0, 1).has_value());
   }
+  {  // one process, the corpus split over a device list (the same device three times on a one-GPU box): identical results
+    const std::vector<int> devs{0, 0, 0};
+    sharded::Corpus sc(cands, devs);
+    sharded::BatchComparator<RF_LEVENSHTEIN> ssk("South Korea", devs);
+    EXPECT(sc.size() == cands.size() && ssk.distance(sc) == d);
+    auto stk = sharded::cdist_topk(std::vector<std::string>{"South Korea", "aabd"}, sc, 2);
+    EXPECT(stk.index[0] == 1 && stk.distance[0] == 0 && stk.index[1] == 0 && stk.distance[1] == 2 && stk.index[2] == 3 && stk.distance[2] == 1);
+  }
   std::printf(fails ? "cpp api: %d failure(s)\n" : "cpp api: all ok\n", fails);
   return fails ? 1 : 0;
 }

@@ -78,5 +78,46 @@ for qq in (q, synth.synth_query(2, 64), synth.synth_query(2, 70)):
         b._score("distance", corpus, a)
         b.close()
 corpus_l.close()
+# ---- round 2: register-column kernels (4 / 8 / 12 / 16 limbs), stripe kernel, Jaro long, len8 / elems32 streaming, sharded
+for qlen in (100, 256, 300, 500):
+    qq = synth.synth_query(7, qlen)
+    for m in ("levenshtein", "indel", "osa"):
+        b = bc(m, qq)
+        b._score("distance", corpus3, None)
+        b.close()
+qlong = np.random.default_rng(5).integers(97, 101, 17000).astype(np.uint8)
+lens = np.array([0, 5, 300, 16999, 17001, 40000])
+cl = np.random.default_rng(6).integers(97, 101, int(lens.sum())).astype(np.uint8)
+ol = np.zeros(len(lens) + 1, np.uint64); ol[1:] = np.cumsum(lens)
+corpus_x = rf.Corpus(cl, ol)
+for m in ("levenshtein", "indel", "osa"):
+    b = bc(m, qlong)
+    b._score("distance", corpus_x, None)
+    b.close()
+for m in ("jaro", "jaro_winkler"):
+    b = bc(m, qlong[:3000])
+    b._score("similarity", corpus_x, None)
+    b.close()
+corpus_x.close()
+b = bc("levenshtein", q)
+lens8 = np.diff(offsets.astype(np.int64)).astype(np.uint8)
+b.stream_len8("distance", chars, lens8)
+b.stream_len8("distance", chars, lens8, u8_results=True)
+b.close()
+b = bc("levenshtein", q.astype(np.uint32) + 1000)
+b.stream_elems32("distance", chars.astype(np.uint32) + 1000, offsets)
+b.close()
+from rapidfuzz_b200 import sharding
+devs = [0, 0]
+sc = sharding.ShardedCorpus(chars, offsets, devs)
+sb = sharding.ShardedBatchComparator("levenshtein", q, devs)
+sb.score("distance", sc)
+sb.extract("distance", sc, k=5)
+import torch
+bufs = [torch.empty(len(sc), dtype=torch.int32, device="cuda") for _ in devs]
+sb.score_allgather("distance", sc, [x.data_ptr() for x in bufs])
+sharding.sharded_cdist_topk(q, np.array([0, 32], np.uint64), sc, k=5)
+sb.stream("distance", chars, offsets)
+sb.close(); sc.close()
 corpus.close(); corpus3.close()
 print("sanitize smoke done")

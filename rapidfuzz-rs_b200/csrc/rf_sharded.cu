@@ -254,27 +254,36 @@ rf_status scan_allgather_copies(rf_sharded_corpus* c, const rf_sharded_batch* b,
       const cudaError_t e = cudaEventRecord(ev(i, k), c->streams[i]);
       if (e != cudaSuccess) s = rfi::cuda_fail(e, "cudaEventRecord");
     }
-    for (int i = 0; i < nd && s == RF_OK; ++i) {
-      DevGuard dg(c->devices[i]);
-      for (int d = 1; d < nd && s == RF_OK; ++d) {
-        const int r = (i + d) % nd;  // staggered: at any moment every source serves a different destination
-        uint64_t a, z;
-        piece_range(c->lo[r + 1] - c->lo[r], K, k, &a, &z);
-        if (z == a) continue;
-        const uint64_t off = (c->lo[r] + a) * esz;
-        cudaError_t e = cudaStreamWaitEvent(c->comm_streams[i], ev(r, k), 0);
-        if (e == cudaSuccess)
-          e = cudaMemcpyPeerAsync((char*)out_device[i] + off, c->devices[i], (const char*)out_device[r] + off, c->devices[r],
-                                  (z - a) * esz, c->comm_streams[i]);
-        if (e != cudaSuccess) s = rfi::cuda_fail(e, "peer copy");
+    // PUSH: the source's copy engine writes its piece into every peer's buffer (NVLink writes are posted; remote reads
+    // pay a round trip per request -- pulling measured 2.2x slower at 8 GPUs: 6.06 vs 2.81 ms, profiles/r2_sharded_abi_one_process_n8*.json).  Staggered targets: at any moment every
+    // destination receives from a different source.
+    for (int r = 0; r < nd && s == RF_OK; ++r) {
+      DevGuard dg(c->devices[r]);
+      uint64_t a, z;
+      piece_range(c->lo[r + 1] - c->lo[r], K, k, &a, &z);
+      if (z == a) continue;
+      const uint64_t off = (c->lo[r] + a) * esz;
+      cudaError_t e = cudaStreamWaitEvent(c->comm_streams[r], ev(r, k), 0);
+      for (int d = 1; d < nd && e == cudaSuccess; ++d) {
+        const int i = (r + d) % nd;
+        e = cudaMemcpyPeerAsync((char*)out_device[i] + off, c->devices[i], (const char*)out_device[r] + off, c->devices[r],
+                                (z - a) * esz, c->comm_streams[r]);
       }
+      if (e != cudaSuccess) s = rfi::cuda_fail(e, "peer copy");
     }
+  }
+  // every device's compute stream continues once ALL sources have delivered
+  for (int r = 0; r < nd; ++r) {
+    DevGuard dg(c->devices[r]);
+    const cudaError_t e = cudaEventRecord(ev(r, kMaxChunks), c->comm_streams[r]);
+    if (e != cudaSuccess && s == RF_OK) s = rfi::cuda_fail(e, "cudaEventRecord");
   }
   for (int i = 0; i < nd; ++i) {
     DevGuard dg(c->devices[i]);
-    cudaError_t e = cudaEventRecord(ev(i, kMaxChunks), c->comm_streams[i]);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(c->streams[i], ev(i, kMaxChunks), 0);
-    if (e != cudaSuccess && s == RF_OK) s = rfi::cuda_fail(e, "scan/gather ordering");
+    for (int r = 0; r < nd; ++r) {
+      const cudaError_t e = cudaStreamWaitEvent(c->streams[i], ev(r, kMaxChunks), 0);
+      if (e != cudaSuccess && s == RF_OK) s = rfi::cuda_fail(e, "scan/gather ordering");
+    }
   }
   return s;
 }

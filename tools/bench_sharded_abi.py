@@ -42,6 +42,7 @@ def main():
     ap.add_argument("--per-gpu", type=int, default=50_000_000)
     ap.add_argument("--c5-queries", type=int, default=10_000)
     ap.add_argument("--c5-candidates", type=int, default=10_000_000)
+    ap.add_argument("--only-gather", action="store_true")
     a = ap.parse_args()
     L = _ffi.lib()
     devs = list(range(a.gpus))
@@ -86,6 +87,10 @@ def main():
     _ffi.check(L.rf_set_option(b"sharded_collective", 0))
     _ffi.check(L.rf_set_option(b"allgather_chunks", 0))
     del bufs
+
+    if a.only_gather:
+        print(json.dumps(out))
+        return
 
     def stream():
         sb.stream("distance", chars, offsets, out=host)

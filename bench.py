@@ -622,10 +622,25 @@ def main():
                                                None, out_host.ctypes.data))
         L.rf_batch_destroy(b2)
 
-    def e2e_step():   # one length byte per candidate in, one score byte per candidate out (query len 32, candidates <= 64)
+    def e2e_step_len8():   # one length byte per candidate in, one score byte per candidate out (query len 32, candidates <= 64)
         b2 = create_batch()
         _ffi.check(L.rf_batch_stream_u8_len8(b2, chars.ctypes.data, lens8.ctypes.data, n, _ffi.KINDS["distance"],
                                              None, out8.ctypes.data))
+        L.rf_batch_destroy(b2)
+
+    # the 62-symbol corpus packed to 6 bits per character ONCE on the host (rf_pack6_u8, like packing the strings into CSR in
+    # the first place: not part of a step); a step sends the packed stream and unpacks each chunk on the device
+    import rapidfuzz_b200 as rf
+    t_pack = time.perf_counter()
+    packed6, dict64 = rf.pack6(chars, nthreads=gen_threads, pinned=True)
+    t_pack = time.perf_counter() - t_pack
+    out8p_t = torch.empty(n, dtype=torch.uint8).pin_memory()
+    out8p = out8p_t.numpy()
+
+    def e2e_step():
+        b2 = create_batch()
+        _ffi.check(L.rf_batch_stream_u8_len8_packed6(b2, packed6.ctypes.data, dict64.ctypes.data, lens8.ctypes.data, n,
+                                                     _ffi.KINDS["distance"], None, out8p.ctypes.data))
         L.rf_batch_destroy(b2)
 
     def wall(fn):
@@ -637,10 +652,12 @@ def main():
         barrier()
         return (time.perf_counter() - t0) / e2e_steps
     e2e_csr_s = wall(e2e_step_csr)
+    e2e_len8_s = wall(e2e_step_len8)
     e2e_s = wall(e2e_step)
     tables = 2 * 256 * 4 + 2 * 256 * 8 + 256 * 8
     h2d_csr, d2h_csr = int(total + 4 * (n + 1) + tables), int(4 * n)
-    h2d, d2h = int(total + n + tables), int(n)
+    h2d_len8, d2h_len8 = int(total + n + tables), int(n)
+    h2d, d2h = int((total + 3) // 4 * 3 + n + tables), int(n)
     if ok is not None:
         from oracle import oracle as orc
         m = min(n, 200_000)
@@ -648,6 +665,7 @@ def main():
         ok = ok and bool(np.array_equal(out_host[:m], exp))
         ok = ok and bool(np.array_equal(out_host[n - m_tail:], tail_dev.cpu().numpy().view(np.uint32)))
         ok = ok and bool(np.array_equal(out8, out_host.astype(np.uint8)) and int(out_host.max()) <= 254)   # byte results == u32 results, all n
+        ok = ok and bool(np.array_equal(out8p, out8))                                                        # packed input == plain input, all n
     # secondary: upload + build a RESIDENT corpus (CSR + interleaved layout), score once, download, destroy
     out_host[:] = 0
     barrier()
@@ -667,9 +685,9 @@ def main():
 
     # ---- aggregate over ranks (device time: max over ranks; pairs: sum over ranks)
     if dist is not None:
-        t = torch.tensor([ms, e2e_s, resident_s, e2e_csr_s], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms, e2e_s, resident_s, e2e_csr_s, e2e_len8_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s, resident_s, e2e_csr_s = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+        ms, e2e_s, resident_s, e2e_csr_s, e2e_len8_s = float(t[0]), float(t[1]), float(t[2]), float(t[3]), float(t[4])
         cnt = torch.tensor([n, total], dtype=torch.int64, device="cuda")
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         n_all = int(cnt[0])
@@ -694,9 +712,13 @@ def main():
             "e2e": {"value": n_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                     "h2d_gbs": h2d / e2e_s / 1e9,
-                    "what": "rf_batch_create_u8 + rf_batch_stream_u8_len8 (pinned host chars + one length byte per candidate -> "
-                            "chunked H2D / prefix sum / scan / narrow / D2H pipeline -> pinned host byte scores) + rf_batch_destroy, "
-                            "per step; PCIe-bound",
+                    "what": "rf_batch_create_u8 + rf_batch_stream_u8_len8_packed6 (pinned host buffers: the candidates' characters "
+                            "6-bit packed once by rf_pack6_u8 + one length byte per candidate -> chunked H2D / unpack / prefix sum / "
+                            "scan / narrow / D2H pipeline -> pinned host byte scores) + rf_batch_destroy, per step; PCIe-bound",
+                    "one_time_host_pack6_s": round(t_pack, 2),
+                    "len8": {"value": n_all / e2e_len8_s, "ms_per_step": e2e_len8_s * 1e3, "h2d_bytes_per_step": h2d_len8,
+                             "d2h_bytes_per_step": d2h_len8, "h2d_gbs": h2d_len8 / e2e_len8_s / 1e9,
+                             "what": "the same through rf_batch_stream_u8_len8: plain bytes + one length byte in, one score byte out"},
                     "csr_u32": {"value": n_all / e2e_csr_s, "ms_per_step": e2e_csr_s * 1e3, "h2d_bytes_per_step": h2d_csr,
                                 "d2h_bytes_per_step": d2h_csr, "h2d_gbs": h2d_csr / e2e_csr_s / 1e9,
                                 "what": "the same through rf_batch_stream_u32_off32: u32 CSR starts in, u32 scores out (round 1's e2e)"},

@@ -221,6 +221,18 @@ rf_status rf_batch_stream_u32_len8(const rf_batch* b, const uint8_t* chars, cons
 rf_status rf_batch_stream_u8_len8(const rf_batch* b, const uint8_t* chars, const uint8_t* lens, uint64_t n, rf_kind kind,
                                   const rf_args* args, uint8_t* out_host);
 
+/* ... and fewer still when the corpus has at most 64 distinct symbols (ASCII alphanumerics: 62): rf_pack6_u8 packs the
+ * concatenated candidates ONCE on the host, 4 characters into 3 bytes (packed_out: rf_pack6_size(total) bytes; dict_out:
+ * 64 bytes, code -> symbol; more than 64 symbols -> RF_ERR_UNSUPPORTED); the _packed6 streaming entry points send the
+ * packed stream (27 instead of 36 bytes per config-2 pair) and unpack each chunk on the device before the scan.  Same
+ * results, same error behaviour as the _len8 entry points. */
+uint64_t rf_pack6_size(uint64_t total_chars);
+rf_status rf_pack6_u8(const uint8_t* chars, uint64_t total_chars, uint8_t* packed_out, uint8_t* dict_out, int nthreads);
+rf_status rf_batch_stream_u32_len8_packed6(const rf_batch* b, const uint8_t* packed, const uint8_t* dict64, const uint8_t* lens,
+                                           uint64_t n, rf_kind kind, const rf_args* args, uint32_t* out_host);
+rf_status rf_batch_stream_u8_len8_packed6(const rf_batch* b, const uint8_t* packed, const uint8_t* dict64, const uint8_t* lens,
+                                          uint64_t n, rf_kind kind, const rf_args* args, uint8_t* out_host);
+
 /* ---- many-vs-many (new on this side; the reference has no cdist -- SURVEY fact 3): for each of nq queries
  * the k best candidates by (distance ascending, index ascending); fewer than k hits are padded with
  * (UINT32_MAX, UINT32_MAX).  Levenshtein distance (unit weights), queries of length <= 64, k <= 64; with

@@ -1158,6 +1158,7 @@ struct StreamSlot {
   cudaStream_t st = nullptr;
   uint8_t* d_chars = nullptr;
   uint8_t* d_renamed = nullptr;  // u32-query comparators: the chunk renamed to the query's byte alphabet (lazily allocated)
+  uint8_t* d_packed = nullptr;   // *_packed6 entry points: the chunk's 6-bit packed characters as they crossed the link
   uint8_t* d_lens = nullptr;     // *_len8 entry points: the chunk's u8 lengths, the scan's temporary storage, the narrowed results
   void* d_scan_tmp = nullptr;
   size_t scan_tmp_bytes = 0;
@@ -1185,6 +1186,7 @@ void stream_ctx_release(StreamCtx* x) {
   for (auto& s : x->slot) {
     if (s.d_chars) cudaFree(s.d_chars);
     if (s.d_renamed) cudaFree(s.d_renamed);
+    if (s.d_packed) cudaFree(s.d_packed);
     if (s.d_lens) cudaFree(s.d_lens);
     if (s.d_scan_tmp) cudaFree(s.d_scan_tmp);
     if (s.d_out8) cudaFree(s.d_out8);
@@ -1312,11 +1314,36 @@ __global__ void __launch_bounds__(256) narrow_results_u8(const uint32_t* __restr
   }
 }
 
+// 6-bit packed characters (rf_pack6_u8: 4 characters in 3 bytes) -> bytes through the 64-entry dictionary; 16 characters per
+// thread: three aligned 32-bit loads, one 16-byte store
+struct Dict64 { uint8_t b[64]; };
+__global__ void __launch_bounds__(256) unpack6_kernel(const uint32_t* __restrict__ in, uint64_t nchars16, const Dict64 dict,
+                                                      uint4* __restrict__ out) {
+  __shared__ uint8_t sd[64];
+  if (threadIdx.x < 64) sd[threadIdx.x] = dict.b[threadIdx.x];
+  __syncthreads();
+  for (uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x; t < nchars16; t += (uint64_t)gridDim.x * 256) {
+    const uint32_t w0 = in[t * 3], w1 = in[t * 3 + 1], w2 = in[t * 3 + 2];
+    // 96 bits = 16 codes of 6 bits, little endian
+    const uint64_t lo = (uint64_t)w0 | ((uint64_t)w1 << 32);  // codes 0..9 (60 bits) + 4 bits of code 10
+    const uint64_t hi = ((uint64_t)w1 >> 28) | ((uint64_t)w2 << 4);  // from bit 60: codes 10..15
+    uint32_t o[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const uint32_t code = (k < 10) ? (uint32_t)(lo >> (6 * k)) & 63u : (uint32_t)(hi >> (6 * (k - 10))) & 63u;
+      o[k >> 2] |= (uint32_t)sd[code] << (8 * (k & 3));
+    }
+    out[t] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // rf_batch_stream_*_len8: the candidates' lengths cross PCIe as ONE byte each instead of a 4- or 8-byte CSR start (the
 // starts of a chunk are rebuilt on the device by a prefix sum), and the results can come back as one byte each: 36.9 + 1
 // instead of 39.9 + 4 bytes per config-2 pair on the host side of the link.
+// packed6: `chars` is the 6-bit packed stream of rf_pack6_u8 (character i at bits [6i, 6i+6)), `dict` its 64 symbols.
 rf_status stream_len8_impl(const rf_batch* b, const uint8_t* chars, const uint8_t* lens, uint64_t n, rf_kind kind,
-                           const rf_args* args, void* out_host, bool out_u8) {
+                           const rf_args* args, void* out_host, bool out_u8, const uint8_t* dict = nullptr) {
+  const bool packed6 = dict != nullptr;
   if (!b) return fail(RF_ERR_INVALID_ARG, "NULL handle");
   if ((int)kind < 0 || (int)kind > 3) return fail(RF_ERR_INVALID_ARG, "unknown kind");
   if (rf_result_is_float(b->metric, kind)) return fail(RF_ERR_INVALID_ARG, "this (metric, kind) yields f64 results; the _len8 entry points return integer scores");
@@ -1331,6 +1358,14 @@ rf_status stream_len8_impl(const rf_batch* b, const uint8_t* chars, const uint8_
   const uint64_t cap_n = (uint64_t)(g_stream_kcand.load() > 0 ? g_stream_kcand.load() : 1) << 10;
   cudaError_t e = stream_ctx_prepare(x, cap_bytes, cap_n);
   if (e != cudaSuccess) return cuda_fail(e, "streaming buffers");
+  if (packed6)
+    for (auto& sl : x->slot) {
+      if (sl.d_packed) continue;
+      if ((e = cudaMalloc(&sl.d_packed, cap_bytes / 4 * 3 + 256)) != cudaSuccess) return cuda_fail(e, "streaming buffers");
+    }
+  Dict64 dk;
+  memset(&dk, 0, sizeof(dk));
+  if (packed6) memcpy(dk.b, dict, 64);
   for (auto& sl : x->slot) {
     if (sl.d_lens) continue;
     sl.scan_tmp_bytes = lens_to_offsets_tmp_bytes(cap_n);
@@ -1347,7 +1382,7 @@ rf_status stream_len8_impl(const rf_batch* b, const uint8_t* chars, const uint8_
   uint64_t i0 = 0, pos = 0;  // pos = byte position of candidate i0
   int k = 0;
   while (i0 < n && s == RF_OK) {
-    const uint64_t B0 = pos & ~15ull;
+    const uint64_t B0 = packed6 ? (pos & ~63ull) : (pos & ~15ull);  // packed: 64 characters = 48 bytes keep every piece 16-byte aligned
     uint64_t i1 = i0, bytes = pos - B0;
     while (i1 < n && i1 - i0 < cap_n) {
       const uint64_t j1 = (n - i1 < kBlock) ? n : i1 + kBlock;
@@ -1364,7 +1399,18 @@ rf_status stream_len8_impl(const rf_batch* b, const uint8_t* chars, const uint8_
     k = (k + 1) % kSlots;
     if (B1 > B0) {
       if (!chars) { s = fail(RF_ERR_INVALID_ARG, "chars is NULL"); break; }
-      e = cudaMemcpyAsync(sl.d_chars, chars + B0, B1 - B0, cudaMemcpyHostToDevice, sl.st);
+      if (packed6) {
+        const uint64_t n16 = (B1 - B0 + 15) / 16;  // 16-character groups = 12 packed bytes each
+        e = cudaMemcpyAsync(sl.d_packed, chars + B0 / 4 * 3, n16 * 12, cudaMemcpyHostToDevice, sl.st);
+        if (e == cudaSuccess) {
+          const uint64_t blocks = (n16 + 255) / 256;
+          unpack6_kernel<<<(uint32_t)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, sl.st>>>((const uint32_t*)sl.d_packed, n16, dk, (uint4*)sl.d_chars);
+          rfk::count_launches(1);
+          e = cudaGetLastError();
+        }
+      } else {
+        e = cudaMemcpyAsync(sl.d_chars, chars + B0, B1 - B0, cudaMemcpyHostToDevice, sl.st);
+      }
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(sl.d_lens, lens + i0, cn, cudaMemcpyHostToDevice, sl.st);
     if (e == cudaSuccess) e = lens_to_offsets(sl.d_lens, cn, (uint32_t)(pos - B0), (uint32_t*)sl.d_offs, sl.d_scan_tmp, sl.scan_tmp_bytes, sl.st);
@@ -1517,6 +1563,16 @@ rf_status rf_batch_stream_u32_len8(const rf_batch* b, const uint8_t* chars, cons
 rf_status rf_batch_stream_u8_len8(const rf_batch* b, const uint8_t* chars, const uint8_t* lens, uint64_t n, rf_kind kind,
                                   const rf_args* args, uint8_t* out_host) {
   return stream_len8_impl(b, chars, lens, n, kind, args, out_host, true);
+}
+rf_status rf_batch_stream_u32_len8_packed6(const rf_batch* b, const uint8_t* packed, const uint8_t* dict64, const uint8_t* lens,
+                                           uint64_t n, rf_kind kind, const rf_args* args, uint32_t* out_host) {
+  if (!dict64) return fail(RF_ERR_INVALID_ARG, "dict64 is NULL");
+  return stream_len8_impl(b, packed, lens, n, kind, args, out_host, false, dict64);
+}
+rf_status rf_batch_stream_u8_len8_packed6(const rf_batch* b, const uint8_t* packed, const uint8_t* dict64, const uint8_t* lens,
+                                          uint64_t n, rf_kind kind, const rf_args* args, uint8_t* out_host) {
+  if (!dict64) return fail(RF_ERR_INVALID_ARG, "dict64 is NULL");
+  return stream_len8_impl(b, packed, lens, n, kind, args, out_host, true, dict64);
 }
 }  // extern "C"
 

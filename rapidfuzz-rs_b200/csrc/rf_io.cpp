@@ -79,6 +79,52 @@ rf_status rf_pack_u8(const uint8_t* const* strings, const uint64_t* lengths, uin
   return RF_OK;
 }
 
+// 6-bit packing of a byte corpus with at most 64 distinct symbols (ASCII alphanumerics: 62): 4 characters -> 3 bytes, codes
+// in ascending byte order.  The packed stream crosses PCIe 25 % smaller (rf_batch_stream_*_packed6 unpacks it on the device).
+uint64_t rf_pack6_size(uint64_t total_chars) { return (total_chars + 3) / 4 * 3 + 64; }
+
+rf_status rf_pack6_u8(const uint8_t* chars, uint64_t total, uint8_t* packed_out, uint8_t* dict_out, int nthreads) {
+  if (!dict_out || !packed_out) return io_fail(RF_ERR_INVALID_ARG, "NULL output");
+  if (total && !chars) return io_fail(RF_ERR_INVALID_ARG, "chars is NULL");
+#ifdef _OPENMP
+  const int threads = nthreads > 0 ? nthreads : omp_get_max_threads();
+#else
+  const int threads = 1;
+#endif
+  (void)threads;
+  uint64_t seen[4] = {0, 0, 0, 0};
+#pragma omp parallel num_threads(threads)
+  {
+    uint64_t mine[4] = {0, 0, 0, 0};
+#pragma omp for schedule(static) nowait
+    for (int64_t i = 0; i < (int64_t)total; ++i) mine[chars[i] >> 6] |= 1ull << (chars[i] & 63);
+#pragma omp critical
+    for (int k = 0; k < 4; ++k) seen[k] |= mine[k];
+  }
+  uint8_t code_of[256];
+  memset(code_of, 0, sizeof(code_of));
+  memset(dict_out, 0, 64);
+  uint32_t d = 0;
+  for (int v = 0; v < 256; ++v) {
+    if (!((seen[v >> 6] >> (v & 63)) & 1)) continue;
+    if (d == 64) return io_fail(RF_ERR_UNSUPPORTED, "more than 64 distinct symbols: the corpus cannot be packed to 6 bits");
+    code_of[v] = (uint8_t)d;
+    dict_out[d++] = (uint8_t)v;
+  }
+  const uint64_t quads = (total + 3) / 4;
+#pragma omp parallel for schedule(static) num_threads(threads)
+  for (int64_t qd = 0; qd < (int64_t)quads; ++qd) {
+    uint32_t c[4];
+    for (int j = 0; j < 4; ++j) c[j] = ((uint64_t)qd * 4 + j < total) ? code_of[chars[(uint64_t)qd * 4 + j]] : 0u;
+    const uint32_t w = c[0] | (c[1] << 6) | (c[2] << 12) | (c[3] << 18);
+    packed_out[qd * 3 + 0] = (uint8_t)w;
+    packed_out[qd * 3 + 1] = (uint8_t)(w >> 8);
+    packed_out[qd * 3 + 2] = (uint8_t)(w >> 16);
+  }
+  memset(packed_out + quads * 3, 0, 64);
+  return RF_OK;
+}
+
 rf_status rf_corpus_file_write(const char* path, const uint8_t* chars, const uint64_t* offsets, uint64_t n) {
   if (!path || !offsets) return io_fail(RF_ERR_INVALID_ARG, "NULL argument");
   if (offsets[0] != 0) return io_fail(RF_ERR_INVALID_ARG, "offsets[0] must be 0");

@@ -76,6 +76,10 @@ SYMBOLS = {
     "rf_batch_stream_f64_elems32": (_int, [_vp, _vp, _vp, _u64, _int, _PA, _vp]),
     "rf_batch_stream_u32_len8": (_int, [_vp, _vp, _vp, _u64, _int, _PA, _vp]),
     "rf_batch_stream_u8_len8": (_int, [_vp, _vp, _vp, _u64, _int, _PA, _vp]),
+    "rf_pack6_size": (_u64, [_u64]),
+    "rf_pack6_u8": (_int, [_vp, _u64, _vp, _vp, _int]),
+    "rf_batch_stream_u32_len8_packed6": (_int, [_vp, _vp, _vp, _vp, _u64, _int, _PA, _vp]),
+    "rf_batch_stream_u8_len8_packed6": (_int, [_vp, _vp, _vp, _vp, _u64, _int, _PA, _vp]),
     "rf_cdist_topk_u8": (_int, [_vp, _vp, _u32, _vp, _PA, _u32, _vp, _vp]),
     "rf_cdist_topk_u8_device": (_int, [_vp, _vp, _u32, _vp, _PA, _u32, _vp, _vp, _vp]),
     "rf_cdist_topk_u32": (_int, [_vp, _vp, _u32, _vp, _PA, _u32, _vp, _vp]),

@@ -253,6 +253,22 @@ class BatchComparatorBase:
                                              C.byref(ca), out.ctypes.data))
         return out
 
+    def stream_len8_packed6(self, kind, packed, dict64, lens, args=None, out=None, u8_results=False):
+        """rf_batch_stream_{u32,u8}_len8_packed6: like stream_len8 with the characters 6-bit packed by corpus.pack6."""
+        args = args if args is not None else Args()
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        dict64 = np.ascontiguousarray(dict64, dtype=np.uint8)
+        lens = np.ascontiguousarray(lens, dtype=np.uint8)
+        n = len(lens)
+        ca = args._c(False)
+        dt = np.uint8 if u8_results else np.uint32
+        if out is None:
+            out = np.empty(n, dtype=dt)
+        assert out.dtype == dt and len(out) >= n and out.flags.c_contiguous and len(dict64) == 64
+        fn = _ffi.lib().rf_batch_stream_u8_len8_packed6 if u8_results else _ffi.lib().rf_batch_stream_u32_len8_packed6
+        _ffi.check(fn(self._h, packed.ctypes.data, dict64.ctypes.data, lens.ctypes.data, n, _ffi.KINDS[kind], C.byref(ca), out.ctypes.data))
+        return out
+
     def stream_len8(self, kind, chars, lens, args=None, out=None, u8_results=False):
         """rf_batch_stream_{u32,u8}_len8: host-resident candidates described by one LENGTH byte each (<= 255 elements),
         integer-valued kinds; with u8_results the scores come back as bytes (0xFF == None, scores must be <= 254)."""

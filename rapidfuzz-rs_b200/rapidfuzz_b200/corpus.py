@@ -138,6 +138,23 @@ def pack_strings(strings, nthreads=0):
     return chars, offsets
 
 
+def pack6(chars, nthreads=0, pinned=False):
+    """rf_pack6_u8: concatenated byte candidates with at most 64 distinct symbols -> (packed u8, dict u8[64]); 4 characters in
+    3 bytes, for the *_packed6 streaming entry points."""
+    chars = np.ascontiguousarray(chars, dtype=np.uint8)
+    l = _ffi.lib()
+    size = int(l.rf_pack6_size(len(chars)))
+    if pinned:
+        import torch
+        packed_t = torch.empty(size, dtype=torch.uint8).pin_memory()
+        packed = packed_t.numpy()
+    else:
+        packed = np.empty(size, dtype=np.uint8)
+    d = np.zeros(64, dtype=np.uint8)
+    _ffi.check(l.rf_pack6_u8(chars.ctypes.data, len(chars), packed.ctypes.data, d.ctypes.data, nthreads))
+    return packed, d
+
+
 def write_corpus_file(path, chars, offsets):
     """rf_corpus_file_write: CSR corpus -> a file that maps back without parsing (see include/rfgpu.h)."""
     chars = np.ascontiguousarray(chars, dtype=np.uint8)

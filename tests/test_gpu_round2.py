@@ -641,3 +641,35 @@ def test_comm_allgather_overlapped_equals_oracle(chunks):
         assert np.array_equal(out[r]["levenshtein"].view(np.uint32), exp["levenshtein"]), r
         assert np.array_equal(out[r]["jaro_winkler"], exp["jaro_winkler"]), r
         assert np.array_equal(out[r]["hamming"].view(np.uint32), exp["hamming"]), r
+
+
+@pytest.mark.parametrize("chunk_mb,chunk_kcand", [(64, 2048), (1, 2048), (1, 4)])
+def test_streaming_6bit_packed_characters(chunk_mb, chunk_kcand):
+    """rf_pack6_u8 + rf_batch_stream_*_len8_packed6: the candidates cross PCIe 6-bit packed (62-symbol alphabet) and are
+    unpacked per chunk on the device; identical to the oracle for every chunking, byte results included."""
+    L = _ffi.lib()
+    _ffi.check(L.rf_set_option(b"stream_chunk_mb", chunk_mb))
+    _ffi.check(L.rf_set_option(b"stream_chunk_kcand", chunk_kcand))
+    try:
+        q = synth.synth_query(2, 32)
+        chars, offsets = synth.synth_corpus(2, q, 300_007, 0, 64, 16)
+        lens = np.diff(offsets.astype(np.int64)).astype(np.uint8)
+        packed, d64 = rf.pack6(chars)
+        for m, kind, kw in (("levenshtein", "distance", {}), ("levenshtein", "distance", {"cutoff": 9}), ("indel", "distance", {}),
+                            ("osa", "distance", {})):
+            b = _bc(m, q)
+            a = Args().score_cutoff(kw["cutoff"]) if kw else Args()
+            exp = orc.batch(m, kind, q, chars, offsets, nthreads=0, **kw)
+            assert_same(b.stream_len8_packed6(kind, packed, d64, lens, a), exp, ("packed6", m, kw, chunk_mb))
+            got8 = b.stream_len8_packed6(kind, packed, d64, lens, a, u8_results=True)
+            assert np.array_equal(got8, np.where(exp == 0xFFFFFFFF, 255, exp).astype(np.uint8)), ("packed6 u8", m, kw)
+            b.close()
+        # a query symbol outside the corpus' dictionary simply never matches
+        q2 = q.copy()
+        q2[::3] = ord("#")
+        b = _bc("levenshtein", q2)
+        assert_same(b.stream_len8_packed6("distance", packed, d64, lens), orc.batch("levenshtein", "distance", q2, chars, offsets, nthreads=0), "packed6 foreign symbol")
+        b.close()
+    finally:
+        _ffi.check(L.rf_set_option(b"stream_chunk_mb", 64))
+        _ffi.check(L.rf_set_option(b"stream_chunk_kcand", 2048))

@@ -66,3 +66,22 @@ def test_corpus_file_rejects_garbage(tmp_path):
     with pytest.raises(rf.RfError) as ei:
         rf.CorpusFile(str(tmp_path / "corrupt.rfc"))
     assert ei.value.status == _ffi.RF_ERR_INVALID_ARG
+
+
+def test_pack6_round_trip_on_the_host():
+    """rf_pack6_u8: 4 characters -> 3 bytes, dictionary in ascending symbol order; more than 64 symbols are refused."""
+    rng = np.random.default_rng(4)
+    alpha = np.frombuffer(b"abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789", dtype=np.uint8)
+    for total in (0, 1, 3, 4, 5, 63, 64, 65, 100_003):
+        chars = alpha[rng.integers(0, len(alpha), total)]
+        packed, d = rf.pack6(chars, nthreads=3)
+        assert len(packed) == (total + 3) // 4 * 3 + 64
+        used = np.unique(chars)
+        assert np.array_equal(d[: len(used)], used) and not d[len(used):].any()
+        bits = np.unpackbits(packed[: (total + 3) // 4 * 3], bitorder="little")
+        codes = bits[: total * 6].reshape(total, 6).dot(1 << np.arange(6)).astype(np.uint8) if total else np.zeros(0, np.uint8)
+        assert np.array_equal(d[codes], chars)
+    with pytest.raises(rf.RfError) as ei:
+        rf.pack6(np.arange(65, dtype=np.uint8))
+    assert ei.value.status == _ffi.RF_ERR_UNSUPPORTED
+    rf.pack6(np.arange(64, dtype=np.uint8) + 100)    # exactly 64 symbols fit

@@ -1,11 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for v in base evl; do
-  if [ $v = evl ]; then export RF_LIB_PATH=$PWD/rapidfuzz-rs_b200/lib/librfgpu_evl.so; else unset RF_LIB_PATH; fi
-  python bench.py --steps 50 --warmup 5 --configs "" --no-cpu-baseline --e2e-steps 1 2>/dev/null | grep '^{' | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$v lev ms', d['ms_per_step'], 'ok', d['run']['results_match_oracle_sample'])"
-  python tools/bench_configs.py fam 2>/dev/null | python -c "
-import sys,json
-for l in sys.stdin:
-    d=json.loads(l); print('$v', d['config'], round(d['ms_per_step'],4), d['matches_oracle_sample'])"
-  RF_CFG_SCALE=0.5 ncu --metrics dram__bytes_write.sum,dram__bytes_read.sum,gpu__time_duration.sum --clock-control none -k regex:scan_lb_kernel -s 3 -c 1 --csv python tools/bench_configs.py indel 2>/dev/null | grep -E "dram__bytes|gpu__time" | cut -d, -f13- | tr '\n' ' '; echo " <- $v ncu indel 0.5 scale"
-done
+python -m pytest tests/test_gpu_round2.py -x -q -k "packed or len8 or typed or u32_streaming" > gpurun_out/pytest_r2k.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/pytest_r2k.log
+timeout 600 python bench.py --steps 20 --warmup 5 --configs "" > gpurun_out/bench_r2k.json 2> gpurun_out/bench_r2k.err; echo "bench rc=$?"
+python - <<'P'
+import json
+d=json.loads([l for l in open('gpurun_out/bench_r2k.json') if l.startswith('{')][-1])
+e=d['e2e']; print('value',d['value'],'e2e packed6',e['value'],e['ms_per_step'],e['h2d_gbs'],'pack s',e['one_time_host_pack6_s'],'len8',e['len8']['value'],'csr',e['csr_u32']['value'],d['run'])
+P
+tail -3 gpurun_out/bench_r2k.err

@@ -2081,14 +2081,20 @@ cudaError_t launch_scan_mw(const ScanLaunch& L) {
 // unrolling puts 32 steps = 54 KB of code into the loop, which thrashes the 32 KB L1.5 instruction cache (ncu:
 // "no_instruction" was the top stall, issue 35 %).  Here one row (or one 4-character word, WORD_LOOP) per iteration,
 // still two rows in flight + the L2 prefetch; the ragged tail is a rolled loop with a run-time byte selector.
-template <bool WORD_LOOP, class Rd, class St>
-__device__ __forceinline__ void walk_rows8_compact(Rd rd, uint32_t len2, St& st) {
+// CUT: after every row the lane tests whether its bottom-row value can still come back under the cutoff (each remaining
+// column lowers it by at most one) and leaves the loop for good otherwise; returns false for such a lane.
+template <bool WORD_LOOP, bool CUT = false, class Rd, class St>
+__device__ __forceinline__ bool walk_rows8_compact(Rd rd, uint32_t len2, St& st, uint32_t cut = 0) {
   static_assert(Rd::kRow8, "interleaved rows only");
   uint2 A = rd.q0, B = rd.q1;
   const uint2* p = rd.p;
   const uint32_t nfull = len2 >> 3;
 #pragma unroll 1
   for (uint32_t i = 0; i < nfull; ++i) {
+    if constexpr (CUT) {
+      const uint32_t j = i * 8u;
+      if (st.bottom(j) > cut + (len2 - j)) return false;
+    }
     if constexpr (Rd::kStream) prefetch_l2(p + 32 * kPfDist);
     const uint2 C = ld_row8<Rd::kStream>(p);
     p += 32;
@@ -2112,6 +2118,7 @@ __device__ __forceinline__ void walk_rows8_compact(Rd rd, uint32_t len2, St& st)
     if (k == 4) w = A.y;
     st.step_sel(w, 0x80u << (8u * (k & 3u)));
   }
+  return true;
 }
 
 // ------------------------------------------------------------------------------------------------ lbn
@@ -2292,6 +2299,8 @@ struct LevNStep {
     for (int i = 0; i < L; ++i) r += (uint32_t)__popc(VP[i]) - (uint32_t)__popc(VN[i]);
     return r;
   }
+  // D[len1][j] after j columns: the top-aligned form makes the bottom-row value available at any column
+  __device__ __forceinline__ uint32_t bottom(uint32_t j) const { return result(j); }
 };
 
 // LCS length (lcs_seq.rs:199-261, :267-341) on the same limbs, bottom-aligned table: S = (S + U) | (S & ~U), U = S & X.
@@ -2324,7 +2333,10 @@ struct LcsNStep {
   }
 };
 
-template <int FAM, int Q, int NT>
+// CUT (Levenshtein distance with a score_cutoff above 63, unit weights): lanes drop out as soon as their candidate cannot
+// come back under the cutoff (the job of the reference's Ukkonen band, levenshtein.rs:897-985); only ever turns a result
+// into None.
+template <int FAM, int Q, int NT, bool CUT = false>
 __global__ void __launch_bounds__(NT) scan_lbn_kernel(const __grid_constant__ LbParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int L = 4 * Q;
@@ -2369,6 +2381,7 @@ __global__ void __launch_bounds__(NT) scan_lbn_kernel(const __grid_constant__ Lb
         second_n = ld_row8<true>(grp + 32);
       }
       uint32_t raw;
+      bool dead = false;  // CUT only: this lane's candidate is beyond the cutoff for certain
       if constexpr (FAM == F_LCS) {
         LcsNStep<Q> st;
         st.init(p.len1, base, p.two);
@@ -2377,23 +2390,29 @@ __global__ void __launch_bounds__(NT) scan_lbn_kernel(const __grid_constant__ Lb
       } else {
         LevNStep<Q, FAM == F_OSA> st;
         st.init(p.len1, base, p.two);
-        walk_rows8_compact<(Q > 2 || FAM == F_OSA)>(src.reader(), len2, st);
+        if constexpr (CUT) {
+          const uint32_t cut = (uint32_t)(p.epi.cutoff_u / p.epi.w_ins > 0x7FFFFFFFull ? 0x7FFFFFFFull : p.epi.cutoff_u / p.epi.w_ins);
+          const uint32_t diff = p.len1 > len2 ? p.len1 - len2 : len2 - p.len1;
+          dead = diff > cut || !walk_rows8_compact<(Q > 2), true>(src.reader(), len2, st, cut);  // levenshtein.rs:1045-1047
+        } else {
+          walk_rows8_compact<(Q > 2 || FAM == F_OSA)>(src.reader(), len2, st);
+        }
         raw = st.result(len2);
       }
       if (idx != 0xFFFFFFFFu) {
         if (p.out_f64) reinterpret_cast<double*>(p.out)[idx] = finish_norm(p.epi, raw, p.len1, len2);
-        else reinterpret_cast<uint32_t*>(p.out)[idx] = finish_int(p.epi, raw, p.len1, len2);
+        else reinterpret_cast<uint32_t*>(p.out)[idx] = dead ? NONE_U32 : finish_int(p.epi, raw, p.len1, len2);
       }
     }
     chunk = __shfl_sync(0xffffffffu, next_chunk, 0);
   }
 }
 
-template <int FAM, int Q>
+template <int FAM, int Q, bool CUT = false>
 static cudaError_t launch_lbn_inst(const ScanLaunch& L, const void* tab) {
   // 64 KB of table per CTA (Q = 2) lets 3 CTAs live on an SM: 320 threads each = 30 warps within the 64 K registers at 68
   constexpr int NT = (Q == 2 && FAM != F_OSA) ? 320 : 256;
-  auto kern = scan_lbn_kernel<FAM, Q, NT>;
+  auto kern = scan_lbn_kernel<FAM, Q, NT, CUT>;
   const size_t smem = (size_t)Q * 32768;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -2427,6 +2446,19 @@ static cudaError_t launch_lbn_inst(const ScanLaunch& L, const void* tab) {
 
 template <int FAM>
 static cudaError_t launch_lbn_fam(const ScanLaunch& L, const void* tab) {
+  if constexpr (FAM == F_LEV) {
+    const bool lev_cut = L.epi.metric == M_LEVENSHTEIN && L.epi.kind == K_DISTANCE && L.epi.has_cutoff && L.epi.wclass == WC_UNIFORM &&
+                         !L.out_is_f64;
+    if (lev_cut) {
+      switch (L.query.limbs / 4) {
+        case 1: return launch_lbn_inst<FAM, 1, true>(L, tab);
+        case 2: return launch_lbn_inst<FAM, 2, true>(L, tab);
+        case 3: return launch_lbn_inst<FAM, 3, true>(L, tab);
+        case 4: return launch_lbn_inst<FAM, 4, true>(L, tab);
+        default: return cudaErrorInvalidValue;
+      }
+    }
+  }
   switch (L.query.limbs / 4) {
     case 1: return launch_lbn_inst<FAM, 1>(L, tab);
     case 2: return launch_lbn_inst<FAM, 2>(L, tab);

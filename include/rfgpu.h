@@ -27,7 +27,7 @@ typedef enum rf_status {
   RF_OK = 0,
   RF_ERR_INVALID_ARG = 1,
   RF_ERR_UNSUPPORTED = 2, /* e.g. query longer than RF_MAX_QUERY_LEN; generic (non-uniform, non-indel) Levenshtein weights
-                             with a query longer than 2048; u32 query with more than 255 distinct symbols */
+                             with a query longer than 2048; u32 query AND u32 corpus with more than 255 distinct symbols each */
   RF_ERR_CUDA = 3,
   RF_ERR_OOM = 4,
   RF_ERR_NCCL = 5 /* a collective of the sharded (multi-GPU) entry points failed */
@@ -131,11 +131,14 @@ int rf_corpus_device(const rf_corpus* c);
  * (levenshtein.rs:1645-1657, pattern_match_vector.rs:203-281). */
 rf_status rf_batch_create_u8(rf_metric metric, const uint8_t* query, uint32_t query_len, int device,
                              rf_batch** out);
-/* u32-element query.  Its distinct symbols (at most 255, else RF_ERR_UNSUPPORTED) are renamed to bytes and every
- * scoring call renames the candidates on the device first (symbols absent from the query -> a byte that matches
- * nothing).  All metrics of this library depend only on which query/candidate positions hold equal symbols, so
- * the scores are identical to the reference's hashmap-based lookup (pattern_match_vector.rs:20-65, :226-280).
- * Works against u8 and u32 corpora; costs one extra pass over the candidates per call. */
+/* u32-element query.  All metrics of this library depend only on which query / candidate positions hold equal symbols, so
+ * renaming symbols is exact (scores identical to the reference's hashmap-based lookup, pattern_match_vector.rs:20-65,
+ * :226-280).  Against byte candidates (u8 corpora, the byte streaming entry points) and against u32 corpora that were
+ * renamed to bytes at creation, the QUERY is mapped into the candidates' symbol domain (a symbol they cannot contain
+ * matches nothing): no extra pass, any number of distinct query symbols.  Against a u32 corpus with more than 255
+ * distinct symbols the candidates are renamed to the query's byte alphabet on the device per call (one extra pass); that
+ * route, and the metrics that compare symbols directly (Hamming / Prefix / Postfix / Damerau-Levenshtein / generic
+ * weights), need a query of at most 255 distinct symbols (else RF_ERR_UNSUPPORTED at scoring time). */
 rf_status rf_batch_create_u32(rf_metric metric, const uint32_t* query, uint32_t query_len, int device, rf_batch** out);
 /* query of any element type (see rf_corpus_create_elems); the comparator scores u8 and u32 / typed corpora alike */
 rf_status rf_batch_create_elems(rf_metric metric, const void* query, rf_elem_type type, uint32_t query_len, int device,

@@ -437,7 +437,10 @@ static cudaError_t upload_sync(void* dst, const void* src, size_t bytes, int dev
   return e;
 }
 
-static rf_status batch_create_bytes(rf_metric metric, const uint8_t* query, uint32_t query_len, int device, rf_batch** out) {
+// nomatch (optional, [query_len]): positions flagged 1 hold a symbol no candidate element can equal (a u32 query symbol outside
+// the corpus' byte / dictionary domain): they set no bit in any match table, which is exact for every table-driven metric.
+static rf_status batch_create_bytes(rf_metric metric, const uint8_t* query, uint32_t query_len, int device, rf_batch** out,
+                                    const uint8_t* nomatch = nullptr) {
   if (!out) return fail(RF_ERR_INVALID_ARG, "out is NULL");
   *out = nullptr;
   if ((int)metric < 0 || (int)metric > (int)RF_DAMERAU_LEVENSHTEIN) return fail(RF_ERR_INVALID_ARG, "unknown metric");
@@ -476,8 +479,11 @@ static rf_status batch_create_bytes(rf_metric metric, const uint8_t* query, uint
   uint64_t* t64b = t64t + 256;
   uint64_t* pmw = t64b + 256;
   uint32_t* pmb = (uint32_t*)(pmw + (size_t)256 * words);
-  for (uint32_t i = 0; i < query_len; ++i) pmw[(size_t)query[i] * words + i / 64] |= 1ull << (i % 64);
-  for (uint32_t i = 0; i < query_len; ++i) pmb[(size_t)query[i] * bstride + 2 + i / 32] |= 1u << (i % 32);
+  for (uint32_t i = 0; i < query_len; ++i) {
+    if (nomatch && nomatch[i]) continue;
+    pmw[(size_t)query[i] * words + i / 64] |= 1ull << (i % 64);
+    pmb[(size_t)query[i] * bstride + 2 + i / 32] |= 1u << (i % 32);
+  }
   if (query_len >= 1 && query_len <= 64) {
     for (int ch = 0; ch < 256; ++ch) {
       const uint64_t m = pmw[(size_t)ch * words];
@@ -545,21 +551,33 @@ rf_status rf_batch_create_u32(rf_metric metric, const uint32_t* query, uint32_t 
   std::vector<uint32_t> keys(kAlphaSlots, 0);
   std::vector<uint8_t> codes(kAlphaSlots, 0), renamed(query_len);
   uint32_t distinct = 0;
+  bool overflow = false;
   for (uint32_t i = 0; i < query_len; ++i) {
     uint32_t slot = alpha_hash(query[i]);
     while (codes[slot] && keys[slot] != query[i]) slot = (slot + 1) & (kAlphaSlots - 1);
     if (!codes[slot]) {
-      if (distinct == 255) return fail(RF_ERR_UNSUPPORTED, "u32 query with more than 255 distinct symbols");
+      if (distinct == 255) { overflow = true; break; }
       keys[slot] = query[i];
       codes[slot] = (uint8_t)++distinct;
     }
     renamed[i] = codes[slot];
   }
   rf_batch* b = nullptr;
-  rf_status s = batch_create_bytes(metric, renamed.data(), query_len, device, &b);
+  rf_status s;
+  if (overflow) {
+    // more than 255 distinct symbols: the query cannot be renamed to bytes on its own.  It still scores byte corpora and
+    // u32 corpora that were renamed to bytes at creation, where it is mapped into the CORPUS' symbol domain (byte_sub /
+    // compact_sub: symbols the corpus cannot contain match nothing); its own tables stay empty.
+    std::vector<uint8_t> none(query_len, 1);
+    std::fill(renamed.begin(), renamed.end(), 0);
+    s = batch_create_bytes(metric, renamed.data(), query_len, device, &b, none.data());
+  } else {
+    s = batch_create_bytes(metric, renamed.data(), query_len, device, &b);
+  }
   if (s != RF_OK) return s;
   DeviceGuard g(device);
   b->wide = true;
+  b->alpha_overflow = overflow;
   b->s1w.assign(query, query + query_len);
   cudaError_t e = cudaMalloc(&b->d_alpha_keys, kAlphaSlots * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMalloc(&b->d_alpha_codes, kAlphaSlots);
@@ -951,6 +969,35 @@ static const rf_batch* compact_sub(const rf_batch* b, const rf_corpus* c) {
   return sub;
 }
 
+// the byte comparator of a u32 query against BYTE candidates (cached under serial 0): a symbol below 256 is its own byte,
+// anything else can equal no candidate element and sets no table bit.  Exact for the table-driven metrics; no pass over
+// the candidates, and the interleaved-layout kernels apply.
+static const rf_batch* byte_sub(const rf_batch* b) {
+  std::lock_guard<std::mutex> lk(b->sub_mu);
+  auto it = b->subs.find(0);
+  if (it != b->subs.end()) return it->second;
+  std::vector<uint8_t> bytes(b->s1w.size()), none(b->s1w.size());
+  for (size_t i = 0; i < b->s1w.size(); ++i) {
+    bytes[i] = (uint8_t)b->s1w[i];
+    none[i] = b->s1w[i] > 255 ? 1 : 0;
+  }
+  rf_batch* sub = nullptr;
+  if (batch_create_bytes(b->metric, bytes.data(), (uint32_t)bytes.size(), b->device, &sub, none.data()) != RF_OK) return nullptr;
+  sub->opt = b->opt;
+  b->subs.emplace(0, sub);
+  return sub;
+}
+static bool table_driven(rf_metric m, const rf_args* a) {
+  switch (m) {
+    case RF_LEVENSHTEIN:
+      if (!a) return true;
+      return a->insertion_cost == a->deletion_cost &&
+             (a->insertion_cost == a->substitution_cost || a->substitution_cost >= a->insertion_cost + a->deletion_cost);
+    case RF_INDEL: case RF_LCS_SEQ: case RF_OSA: case RF_JARO: case RF_JARO_WINKLER: case RF_RATIO: return true;
+    default: return false;  // hamming / prefix / postfix / Damerau-Levenshtein / generic weights compare symbols directly
+  }
+}
+
 extern "C" {
 
 static rf_status score_device(const rf_batch* b, const rf_corpus* c, rf_kind kind, const rf_args* args, void* out_dev,
@@ -968,7 +1015,17 @@ static rf_status score_device(const rf_batch* b, const rf_corpus* c, rf_kind kin
     return score_view(sub, CorpusView{c->d_chars, c->d_off32, c->d_off64, c->n, c->total, c->max_len}, &c->lb, c->device, kind, args,
                       out_dev, want_f64, st, d_err);
   }
+  if (b->wide && !c->d_elems32 && table_driven(b->metric, args)) {  // u32 query, byte corpus: map the QUERY into the byte domain
+    if (b->device != c->device) return fail(RF_ERR_INVALID_ARG, "batch and corpus live on different devices");
+    const rf_batch* sub = byte_sub(b);
+    if (!sub) return RF_ERR_CUDA;
+    return score_view(sub, CorpusView{c->d_chars, c->d_off32, c->d_off64, c->n, c->total, c->max_len}, &c->lb, c->device, kind, args,
+                      out_dev, want_f64, st, d_err);
+  }
   if (b->wide) {
+    if (b->alpha_overflow)
+      return fail(RF_ERR_UNSUPPORTED, c->d_elems32 ? "u32 query AND u32 corpus with more than 255 distinct symbols each"
+                                                   : "this metric compares symbols directly: u32 queries with more than 255 distinct symbols are not supported for it");
     if (b->device != c->device) return fail(RF_ERR_INVALID_ARG, "batch and corpus live on different devices");
     if (c->n == 0) return RF_OK;
     DeviceGuard g(c->device);
@@ -1234,6 +1291,16 @@ rf_status stream_impl(const rf_batch* b, const uint8_t* chars, const OffT* offse
   if (offsets[0] != 0 && !sub_range) return fail(RF_ERR_INVALID_ARG, "offsets[0] must be 0");
   if (offsets[n] && !chars) return fail(RF_ERR_INVALID_ARG, "chars is NULL");
   if (rf_device_count() <= b->device) return fail(RF_ERR_CUDA, "no such CUDA device");
+  // u32-query comparator on byte candidates: the table-driven metrics score with the query mapped into the byte domain
+  // (no renaming pass over the chunk); the others rename the chunk through the query's own alphabet
+  const rf_batch* sb = b;
+  if (b->wide && table_driven(b->metric, args)) {
+    sb = byte_sub(b);
+    if (!sb) return RF_ERR_CUDA;
+  } else if (b->wide && b->alpha_overflow) {
+    return fail(RF_ERR_UNSUPPORTED, "this metric compares symbols directly: u32 queries with more than 255 distinct symbols are not supported for it");
+  }
+
   DeviceGuard g(b->device);
   if (!g.ok) return fail(RF_ERR_CUDA, "cudaSetDevice failed");
   StreamCtx* x = stream_ctx(b->device);
@@ -1267,9 +1334,9 @@ rf_status stream_impl(const rf_batch* b, const uint8_t* chars, const OffT* offse
     if (e == cudaSuccess) e = cudaMemcpyAsync(sl.d_offs, offsets + i0, (cn + 1) * osz, cudaMemcpyHostToDevice, sl.st);
     if (e != cudaSuccess) { s = cuda_fail(e, "chunk upload"); break; }
     const uint8_t* d_src = sl.d_chars;
-    if (b->wide && B1 > B0) {
-      // comparator made by rf_batch_create_u32: its tables are over renamed bytes 1..D, so the candidates' bytes go
-      // through the same renaming first (exactly what score_device does for a resident corpus)
+    if (b->wide && B1 > B0 && sb == b) {
+      // comparator made by rf_batch_create_u32 and a metric that compares symbols directly: its tables are over renamed
+      // bytes 1..D, so the candidates' bytes go through the same renaming first
       if (!sl.d_renamed) {
         if ((e = cudaMalloc(&sl.d_renamed, cap_bytes + 256)) == cudaSuccess) e = cudaMemsetAsync(sl.d_renamed, 0, cap_bytes + 256, sl.st);
         if (e != cudaSuccess) { s = cuda_fail(e, "streaming buffers"); break; }
@@ -1284,7 +1351,7 @@ rf_status stream_impl(const rf_batch* b, const uint8_t* chars, const OffT* offse
     // the kernels index chars with the caller's absolute offsets: hand them the slot shifted back by B0
     CorpusView cv{d_src - B0, osz == 4 ? (const uint32_t*)sl.d_offs : nullptr,
                   osz == 8 ? (const uint64_t*)sl.d_offs : nullptr, cn, B1 - (uint64_t)offsets[i0]};
-    s = score_view(b, cv, nullptr, b->device, kind, args, sl.d_out, want_f64, sl.st);
+    s = score_view(sb, cv, nullptr, b->device, kind, args, sl.d_out, want_f64, sl.st);
     if (s != RF_OK) break;
     e = cudaMemcpyAsync((uint8_t*)out_host + i0 * rsz, sl.d_out, cn * rsz, cudaMemcpyDeviceToHost, sl.st);
     if (e != cudaSuccess) { s = cuda_fail(e, "chunk download"); break; }
@@ -1367,6 +1434,16 @@ rf_status stream_len8_impl(const rf_batch* b, const uint8_t* chars, const uint8_
   if (n == 0) return RF_OK;
   if (!lens || !out_host) return fail(RF_ERR_INVALID_ARG, "NULL argument");
   if (rf_device_count() <= b->device) return fail(RF_ERR_CUDA, "no such CUDA device");
+  // u32-query comparator on byte candidates: the table-driven metrics score with the query mapped into the byte domain
+  // (no renaming pass over the chunk); the others rename the chunk through the query's own alphabet
+  const rf_batch* sb = b;
+  if (b->wide && table_driven(b->metric, args)) {
+    sb = byte_sub(b);
+    if (!sb) return RF_ERR_CUDA;
+  } else if (b->wide && b->alpha_overflow) {
+    return fail(RF_ERR_UNSUPPORTED, "this metric compares symbols directly: u32 queries with more than 255 distinct symbols are not supported for it");
+  }
+
   DeviceGuard g(b->device);
   if (!g.ok) return fail(RF_ERR_CUDA, "cudaSetDevice failed");
   StreamCtx* x = stream_ctx(b->device);
@@ -1433,7 +1510,7 @@ rf_status stream_len8_impl(const rf_batch* b, const uint8_t* chars, const uint8_
     if (e != cudaSuccess) { s = cuda_fail(e, "chunk upload"); break; }
     rfk::count_launches(1);
     const uint8_t* d_src = sl.d_chars;
-    if (b->wide && B1 > B0) {
+    if (b->wide && B1 > B0 && sb == b) {
       if (!sl.d_renamed) {
         if ((e = cudaMalloc(&sl.d_renamed, cap_bytes + 256)) == cudaSuccess) e = cudaMemsetAsync(sl.d_renamed, 0, cap_bytes + 256, sl.st);
         if (e != cudaSuccess) { s = cuda_fail(e, "streaming buffers"); break; }
@@ -1446,7 +1523,7 @@ rf_status stream_len8_impl(const rf_batch* b, const uint8_t* chars, const uint8_
       d_src = sl.d_renamed;
     }
     CorpusView cv{d_src, (const uint32_t*)sl.d_offs, nullptr, cn, bytes - (pos - B0), 255};
-    s = score_view(b, cv, nullptr, b->device, kind, args, sl.d_out, false, sl.st);
+    s = score_view(sb, cv, nullptr, b->device, kind, args, sl.d_out, false, sl.st);
     if (s != RF_OK) break;
     if (out_u8) {
       const uint64_t blocks = ((cn + 3) / 4 + 255) / 256;
@@ -1481,6 +1558,7 @@ rf_status stream_elems32_impl(const rf_batch* b, const uint32_t* elems, const ui
                               const rf_args* args, void* out_host, bool want_f64) {
   if (!b) return fail(RF_ERR_INVALID_ARG, "NULL handle");
   if (!b->wide) return fail(RF_ERR_INVALID_ARG, "u32 candidates need a comparator created with rf_batch_create_u32");
+  if (b->alpha_overflow) return fail(RF_ERR_UNSUPPORTED, "u32 candidates against a u32 query with more than 255 distinct symbols");
   if ((int)kind < 0 || (int)kind > 3) return fail(RF_ERR_INVALID_ARG, "unknown kind");
   if ((rf_result_is_float(b->metric, kind) != 0) != want_f64)
     return fail(RF_ERR_INVALID_ARG, want_f64 ? "this (metric, kind) yields u32 results; use the _u32 entry point"

@@ -45,6 +45,7 @@ struct rf_batch {
   // renamed on the device per scoring call (symbols the query does not contain become 0, which matches nothing).
   // Every metric here depends only on which (query, candidate) positions are equal, so the result is exact.
   bool wide = false;
+  bool alpha_overflow = false;  // wide query with more than 255 distinct symbols: no byte alphabet of its own (see rf_batch_create_u32)
   std::vector<uint32_t> s1w;         // the u32 query as given
   mutable std::mutex sub_mu;         // byte comparators of this query against compact u32 corpora, by dictionary
   mutable std::unordered_map<uint64_t, rf_batch*> subs;

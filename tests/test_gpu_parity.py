@@ -446,9 +446,20 @@ def test_u32_host_mirror_and_limits():
     assert rf.distance.levenshtein.BatchComparator("kitten").distance("sittinĝ") == 3   # byte query, wide candidate
     c = rf.Corpus.from_unicode(["Петрунко", "Иванко", "", "abc"])
     assert rf.distance.levenshtein.BatchComparator("Иванко").distance(c).tolist() == [5, 0, 6, 6]
-    with pytest.raises(rf.RfError) as ei:    # more distinct symbols than the byte renaming can hold
-        rf.distance.levenshtein.BatchComparator(np.arange(1000, 1300, dtype=np.uint32))
-    assert ei.value.status == _ffi.RF_ERR_UNSUPPORTED
+    # more distinct symbols than a byte alphabet holds: fine against byte / byte-renamed corpora (the query is mapped into
+    # THEIR symbol domain), refused only against a u32 corpus that itself has more than 255 distinct symbols
+    big = rf.distance.levenshtein.BatchComparator(np.arange(1000, 1300, dtype=np.uint32))
+    assert big.distance(c).tolist() == [300, 300, 300, 300]
+    _ffi.check(_ffi.lib().rf_set_option(b"compact_u32_corpus", 0))
+    try:
+        c_raw = rf.Corpus.from_unicode(["Петрунко", "abc"])
+        with pytest.raises(rf.RfError) as ei:
+            big.distance(c_raw)
+        assert ei.value.status == _ffi.RF_ERR_UNSUPPORTED
+        c_raw.close()
+    finally:
+        _ffi.check(_ffi.lib().rf_set_option(b"compact_u32_corpus", 1))
+    big.close()
     with pytest.raises(rf.RfError):          # u32 corpus with a byte comparator handle
         b = rf.distance.levenshtein.BatchComparator(b"abc")
         out = np.zeros(4, np.uint32)

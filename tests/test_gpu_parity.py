@@ -449,7 +449,10 @@ def test_u32_host_mirror_and_limits():
     # more distinct symbols than a byte alphabet holds: fine against byte / byte-renamed corpora (the query is mapped into
     # THEIR symbol domain), refused only against a u32 corpus that itself has more than 255 distinct symbols
     big = rf.distance.levenshtein.BatchComparator(np.arange(1000, 1300, dtype=np.uint32))
-    assert big.distance(c).tolist() == [300, 300, 300, 300]
+    strs = ["Петрунко", "Иванко", "", "abc"]     # 1000..1299 covers most of the Cyrillic block: some letters do match
+    cps = np.array([ord(ch) for s_ in strs for ch in s_], dtype=np.uint32)
+    offs = np.cumsum([0] + [len(s_) for s_ in strs]).astype(np.uint64)
+    assert np.array_equal(big.distance(c), orc.batch("levenshtein", "distance", np.arange(1000, 1300, dtype=np.uint32), cps, offs, nthreads=0))
     _ffi.check(_ffi.lib().rf_set_option(b"compact_u32_corpus", 0))
     try:
         c_raw = rf.Corpus.from_unicode(["Петрунко", "abc"])

@@ -695,7 +695,7 @@ def test_u32_queries_with_more_than_255_distinct_symbols(qlen, distinct):
     for _ in range(200):
         if rng.random() < 0.5:
             c = q.copy()
-            hit = rng.random(qlen) < 0.1
+            hit = (rng.random(qlen) < 0.1) | ~np.isin(c, alpha_c)      # the corpus itself stays within its 196 symbols
             c[hit] = alpha_c[rng.integers(0, len(alpha_c), int(hit.sum()))]
             cands.append(c[: int(rng.integers(qlen // 2, qlen + 1))])
         else:

@@ -27,7 +27,7 @@ typedef enum rf_status {
   RF_OK = 0,
   RF_ERR_INVALID_ARG = 1,
   RF_ERR_UNSUPPORTED = 2, /* e.g. query longer than RF_MAX_QUERY_LEN; generic (non-uniform, non-indel) Levenshtein weights
-                             with a query longer than 2048; u32 query AND u32 corpus with more than 255 distinct symbols each */
+                             with a query longer than 2048; 64-bit element values that do not fit the 32-bit symbol domain */
   RF_ERR_CUDA = 3,
   RF_ERR_OOM = 4,
   RF_ERR_NCCL = 5 /* a collective of the sharded (multi-GPU) entry points failed */
@@ -136,9 +136,11 @@ rf_status rf_batch_create_u8(rf_metric metric, const uint8_t* query, uint32_t qu
  * :226-280).  Against byte candidates (u8 corpora, the byte streaming entry points) and against u32 corpora that were
  * renamed to bytes at creation, the QUERY is mapped into the candidates' symbol domain (a symbol they cannot contain
  * matches nothing): no extra pass, any number of distinct query symbols.  Against a u32 corpus with more than 255
- * distinct symbols the candidates are renamed to the query's byte alphabet on the device per call (one extra pass); that
- * route, and the metrics that compare symbols directly (Hamming / Prefix / Postfix / Damerau-Levenshtein / generic
- * weights), need a query of at most 255 distinct symbols (else RF_ERR_UNSUPPORTED at scoring time). */
+ * distinct symbols the candidates are renamed to the query's own alphabet on the device per call (one extra pass): to
+ * bytes when the query has at most 255 distinct symbols, to 16-bit codes otherwise (at most 65 535 distinct symbols; the
+ * multi-word kernels over uint16_t elements with one match-table row per code).  The metrics that compare symbols
+ * directly (Hamming / Prefix / Postfix / Damerau-Levenshtein / generic weights) need a query of at most 255 distinct
+ * symbols (else RF_ERR_UNSUPPORTED at scoring time). */
 rf_status rf_batch_create_u32(rf_metric metric, const uint32_t* query, uint32_t query_len, int device, rf_batch** out);
 /* query of any element type (see rf_corpus_create_elems); the comparator scores u8 and u32 / typed corpora alike */
 rf_status rf_batch_create_elems(rf_metric metric, const void* query, rf_elem_type type, uint32_t query_len, int device,

@@ -676,6 +676,9 @@ rf_status rf_batch_destroy(rf_batch* b) {
   if (b->d_blob) cudaFree(b->d_blob);
   if (b->d_alpha_keys) cudaFree(b->d_alpha_keys);
   if (b->d_alpha_codes) cudaFree(b->d_alpha_codes);
+  if (b->d_w16_keys) cudaFree(b->d_w16_keys);
+  if (b->d_w16_codes) cudaFree(b->d_w16_codes);
+  if (b->d_w16_pm) cudaFree(b->d_w16_pm);
   for (auto& kv : b->subs) rf_batch_destroy(kv.second);
   delete b;
   return RF_OK;
@@ -969,6 +972,59 @@ static const rf_batch* compact_sub(const rf_batch* b, const rf_corpus* c) {
   return sub;
 }
 
+// ---- 16-bit codes: a u32 query with more than 255 distinct symbols against a u32 corpus with more than 255 distinct symbols.
+// The query's D distinct symbols become the codes 1..D (D <= 65535), the candidates are renamed per call (symbols the query
+// does not contain -> 0, whose match row is empty) and scored by the multi-word kernels instantiated for uint16_t elements
+// with one match-table row per code -- the role of the reference's per-block hashmap (pattern_match_vector.rs:20-65).
+__global__ void __launch_bounds__(256) remap16_kernel(const uint32_t* __restrict__ in, uint64_t total, const uint32_t* __restrict__ keys,
+                                                      const uint16_t* __restrict__ codes, uint32_t slot_mask, uint32_t shift,
+                                                      uint16_t* __restrict__ out) {
+  for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (uint64_t)gridDim.x * 256) {
+    const uint32_t x = in[i];
+    uint32_t slot = (x * 2654435761u) >> shift;
+    uint32_t code;
+    while ((code = __ldg(codes + slot)) != 0 && __ldg(keys + slot) != x) slot = (slot + 1) & slot_mask;
+    out[i] = (uint16_t)code;
+  }
+}
+
+static rf_status ensure_w16(const rf_batch* b) {
+  std::lock_guard<std::mutex> lk(b->sub_mu);
+  if (b->w16_ready) return RF_OK;
+  const uint32_t len1 = (uint32_t)b->s1w.size(), words = (len1 + 63) / 64;
+  uint32_t slots = 1024, bits = 10;
+  while (slots < 4 * (uint64_t)len1 && slots < (1u << 20)) { slots <<= 1; ++bits; }
+  std::vector<uint32_t> keys(slots, 0);
+  std::vector<uint16_t> codes(slots, 0), code_of(len1);
+  uint32_t distinct = 0;
+  for (uint32_t i = 0; i < len1; ++i) {
+    const uint32_t x = b->s1w[i];
+    uint32_t slot = (x * 2654435761u) >> (32 - bits);
+    while (codes[slot] && keys[slot] != x) slot = (slot + 1) & (slots - 1);
+    if (!codes[slot]) {
+      if (distinct == 65535) return fail(RF_ERR_UNSUPPORTED, "u32 query with more than 65535 distinct symbols against a u32 corpus with more than 255");
+      keys[slot] = x;
+      codes[slot] = (uint16_t)++distinct;
+    }
+    code_of[i] = codes[slot];
+  }
+  const uint64_t pm_bytes = (uint64_t)(distinct + 1) * words * 8;
+  if (pm_bytes > (4ull << 30)) return fail(RF_ERR_UNSUPPORTED, "match table of this query (distinct symbols x length / 8 bytes) exceeds 4 GiB");
+  std::vector<uint64_t> pm((size_t)(distinct + 1) * words, 0);
+  for (uint32_t i = 0; i < len1; ++i) pm[(size_t)code_of[i] * words + i / 64] |= 1ull << (i % 64);
+  DeviceGuard g(b->device);
+  cudaError_t e = cudaMalloc(&b->d_w16_keys, (size_t)slots * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&b->d_w16_codes, (size_t)slots * 2);
+  if (e == cudaSuccess) e = cudaMalloc(&b->d_w16_pm, pm_bytes);
+  if (e == cudaSuccess) e = upload_sync(b->d_w16_keys, keys.data(), (size_t)slots * 4, b->device);
+  if (e == cudaSuccess) e = upload_sync(b->d_w16_codes, codes.data(), (size_t)slots * 2, b->device);
+  if (e == cudaSuccess) e = upload_sync(b->d_w16_pm, pm.data(), pm_bytes, b->device);
+  if (e != cudaSuccess) return cuda_fail(e, "16-bit alphabet tables");
+  b->w16_slots = slots;
+  b->w16_ready = true;
+  return RF_OK;
+}
+
 // the byte comparator of a u32 query against BYTE candidates (cached under serial 0): a symbol below 256 is its own byte,
 // anything else can equal no candidate element and sets no table bit.  Exact for the table-driven metrics; no pass over
 // the candidates, and the interleaved-layout kernels apply.
@@ -1022,10 +1078,57 @@ static rf_status score_device(const rf_batch* b, const rf_corpus* c, rf_kind kin
     return score_view(sub, CorpusView{c->d_chars, c->d_off32, c->d_off64, c->n, c->total, c->max_len}, &c->lb, c->device, kind, args,
                       out_dev, want_f64, st, d_err);
   }
+  if (b->wide && b->alpha_overflow && c->d_elems32 && table_driven(b->metric, args)) {
+    // both sides have large alphabets: candidates renamed to the query's 16-bit codes, multi-word kernels over uint16_t
+    if (b->device != c->device) return fail(RF_ERR_INVALID_ARG, "batch and corpus live on different devices");
+    if ((int)kind < 0 || (int)kind > 3) return fail(RF_ERR_INVALID_ARG, "unknown kind");
+    if ((rf_result_is_float(b->metric, kind) != 0) != want_f64)
+      return fail(RF_ERR_INVALID_ARG, want_f64 ? "this (metric, kind) yields u32 results; use the _u32 entry point"
+                                               : "this (metric, kind) yields f64 results; use the _f64 entry point");
+    if (c->n == 0) return RF_OK;
+    if (!out_dev) return fail(RF_ERR_INVALID_ARG, "out is NULL");
+    rf_status s = ensure_w16(b);
+    if (s != RF_OK) return s;
+    DeviceGuard g(c->device);
+    if (!g.ok) return fail(RF_ERR_CUDA, "cudaSetDevice failed");
+    uint16_t* d_codes = nullptr;
+    cudaError_t e = dev_alloc(&d_codes, (c->total + 64) * 2, st);
+    if (e != cudaSuccess) return cuda_fail(e, "renamed candidates");
+    e = cudaMemsetAsync(d_codes + c->total, 0, 128, st);
+    if (e == cudaSuccess && c->total) {
+      const uint64_t blocks = (c->total + 255) / 256;
+      uint32_t bits = 0;
+      while ((1u << bits) < b->w16_slots) ++bits;
+      remap16_kernel<<<(uint32_t)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(c->d_elems32, c->total, b->d_w16_keys, b->d_w16_codes,
+                                                                                        b->w16_slots - 1, 32 - bits, d_codes);
+      rfk::count_launches(1);
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) {
+      ScanLaunch L{};
+      s = make_epi(b, kind, args, &L.epi);
+      L.corpus = CorpusView{reinterpret_cast<const uint8_t*>(d_codes), c->d_off32, c->d_off64, c->n, c->total, c->max_len};
+      L.query = b->view;
+      L.query.pm_words = b->d_w16_pm;
+      L.out = out_dev;
+      L.out_is_f64 = want_f64 ? 1 : 0;
+      L.stream = st;
+      L.sm_count = sm_count_of(c->device);
+      L.elem16 = 1;
+      if (s == RF_OK) {
+        const Family fam = family_of(L.epi.metric, L.epi.wclass);
+        e = fam == F_JARO ? launch_jaro_mw(L) : (L.query.words > 256 ? launch_scan_long(L) : launch_scan_mw(L));
+        if (e != cudaSuccess) s = cuda_fail(e, "kernel launch");
+      }
+    } else {
+      s = cuda_fail(e, "alphabet renaming");
+    }
+    dev_free(d_codes, st);
+    return s;
+  }
   if (b->wide) {
     if (b->alpha_overflow)
-      return fail(RF_ERR_UNSUPPORTED, c->d_elems32 ? "u32 query AND u32 corpus with more than 255 distinct symbols each"
-                                                   : "this metric compares symbols directly: u32 queries with more than 255 distinct symbols are not supported for it");
+      return fail(RF_ERR_UNSUPPORTED, "this metric compares symbols directly: u32 queries with more than 255 distinct symbols are not supported for it");
     if (b->device != c->device) return fail(RF_ERR_INVALID_ARG, "batch and corpus live on different devices");
     if (c->n == 0) return RF_OK;
     DeviceGuard g(c->device);

@@ -474,7 +474,7 @@ RF_HD bool jaro_common_char_filter(uint32_t p_len, uint32_t t_len, uint32_t cc, 
 //   Query length 1..MAXQ (MAXQ multiple of 64); the candidate may have any length: instead of the
 //   reference's t_flag bit-vector (which grows with the candidate) the matched text characters are kept
 //   in order (at most len1 of them), which yields the identical transposition count.
-template <int MAXQ, class PMW, class Bytes>
+template <int MAXQ, class MT = uint8_t, class PMW, class Bytes>
 RF_HD double jaro_similarity_generic(const PMW& pmw, const Bytes& bytes, uint32_t len1, uint32_t len2, double cutoff) {
   const uint32_t len1_orig = len1, len2_orig = len2;
   if (cutoff > 1.0) return 0.0;
@@ -492,7 +492,7 @@ RF_HD double jaro_similarity_generic(const PMW& pmw, const Bytes& bytes, uint32_
   if (len1 == 0 || len2 == 0) return jaro_calculate_similarity(len1_orig, len2_orig, 0, 0);  // NaN like the reference (0/0); unreachable: both >= 1 here
   constexpr int PW = MAXQ / 64;
   uint64_t P[PW];
-  uint8_t matched[MAXQ];
+  MT matched[MAXQ];  // MT = uint16_t for candidates renamed to 16-bit codes
 RF_UNROLL
   for (int i = 0; i < PW; ++i) P[i] = 0;
   const uint32_t words = (len1_orig + 63) / 64;
@@ -511,7 +511,7 @@ RF_UNROLL
       if (w == w1) m &= ~0ULL >> (63 - (hi % 64));
       if (m) {
         P[w] |= m & (0 - m);
-        matched[cc++] = (uint8_t)ch;
+        matched[cc++] = (MT)ch;
         break;
       }
     }

@@ -49,6 +49,12 @@ struct rf_batch {
   std::vector<uint32_t> s1w;         // the u32 query as given
   mutable std::mutex sub_mu;         // byte comparators of this query against compact u32 corpora, by dictionary
   mutable std::unordered_map<uint64_t, rf_batch*> subs;
+  // alpha_overflow queries against u32 corpora with more than 255 distinct symbols: 16-bit codes (built on first use)
+  mutable bool w16_ready = false;
+  mutable uint32_t w16_slots = 0;             // power of two
+  mutable uint32_t* d_w16_keys = nullptr;     // [w16_slots] symbol ...
+  mutable uint16_t* d_w16_codes = nullptr;    // ... -> code 1..D, 0 = empty slot / symbol not in the query
+  mutable uint64_t* d_w16_pm = nullptr;       // [(D + 1)][words] match vectors per code (row 0 = all zero)
   uint32_t* d_alpha_keys = nullptr;  // [kAlphaSlots] open-addressing table: symbol ...
   uint8_t* d_alpha_codes = nullptr;  // ... -> byte code, 0 = empty slot
 };

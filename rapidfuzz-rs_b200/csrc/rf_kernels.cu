@@ -1840,8 +1840,11 @@ struct MwParams {
   Epi epi;
 };
 
-template <int FAM, int WPL>
+// T = uint16_t: candidates renamed to 16-bit codes (u32 queries with more than 255 distinct symbols against u32 corpora with
+// more than 255 distinct symbols: p.pm then has one row per code, p.chars is an array of T)
+template <int FAM, int WPL, class T = uint8_t>
 __global__ void __launch_bounds__(256) scan_mw_kernel(const __grid_constant__ MwParams p) {
+  constexpr uint32_t CH_BITS = sizeof(T) * 8, CH_MASK = (1u << CH_BITS) - 1u;
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t G = p.G;
   const uint32_t gl = lane & (G - 1u);       // lane within the candidate's group
@@ -1901,7 +1904,7 @@ __global__ void __launch_bounds__(256) scan_mw_kernel(const __grid_constant__ Mw
       const uint32_t len2 = have ? len2_src : 0u;
       for (uint32_t i = 0; i < gpw; ++i) todo &= todo - 1;  // retire the gpw candidates of this pass
 
-      const uint8_t* __restrict__ txt = p.chars + o0;
+      const T* __restrict__ txt = reinterpret_cast<const T*>(p.chars) + o0;
       const uint32_t my_steps = have ? len2 + act - 1u : 0u;
       const uint32_t steps = __reduce_max_sync(0xffffffffu, my_steps);
 
@@ -1924,7 +1927,7 @@ __global__ void __launch_bounds__(256) scan_mw_kernel(const __grid_constant__ Mw
       }
       uint32_t cout = 0;
       for (uint32_t t = 0; t < steps; ++t) {
-        const uint32_t pk_in = __shfl_up_sync(0xffffffffu, ch_cur | (cout << 8), 1, G);
+        const uint32_t pk_in = __shfl_up_sync(0xffffffffu, ch_cur | (cout << CH_BITS), 1, G);
         uint32_t ch_nxt, cin;
         if (gl == 0) {
           ch_nxt = c1;
@@ -1932,8 +1935,8 @@ __global__ void __launch_bounds__(256) scan_mw_kernel(const __grid_constant__ Mw
           c2 = (t + 3 < len2) ? (uint32_t)txt[t + 3] : 0u;
           cin = (FAM == F_LCS) ? 0u : 1u;  // Levenshtein/OSA: +1 horizontal delta enters row 0; LCS: no carry
         } else {
-          ch_nxt = pk_in & 0xffu;
-          cin = pk_in >> 8;
+          ch_nxt = pk_in & CH_MASK;
+          cin = pk_in >> CH_BITS;
         }
         // this lane's match words for the NEXT step (text char flows one step ahead of the carries)
 #pragma unroll
@@ -2058,11 +2061,20 @@ static cudaError_t launch_mw_fam(const ScanLaunch& L) {
   const uint64_t max_blocks = (uint64_t)L.sm_count * 8;  // 8 x 256 threads = 2048 threads / SM
   if (blocks > max_blocks) blocks = max_blocks;
   if (blocks < 1) blocks = 1;
-  switch (wpl) {
-    case 1: scan_mw_kernel<FAM, 1><<<(uint32_t)blocks, 256, 0, L.stream>>>(p); break;
-    case 2: scan_mw_kernel<FAM, 2><<<(uint32_t)blocks, 256, 0, L.stream>>>(p); break;
-    case 4: scan_mw_kernel<FAM, 4><<<(uint32_t)blocks, 256, 0, L.stream>>>(p); break;
-    default: scan_mw_kernel<FAM, 8><<<(uint32_t)blocks, 256, 0, L.stream>>>(p); break;
+  if (L.elem16) {
+    switch (wpl) {
+      case 1: scan_mw_kernel<FAM, 1, uint16_t><<<(uint32_t)blocks, 256, 0, L.stream>>>(p); break;
+      case 2: scan_mw_kernel<FAM, 2, uint16_t><<<(uint32_t)blocks, 256, 0, L.stream>>>(p); break;
+      case 4: scan_mw_kernel<FAM, 4, uint16_t><<<(uint32_t)blocks, 256, 0, L.stream>>>(p); break;
+      default: scan_mw_kernel<FAM, 8, uint16_t><<<(uint32_t)blocks, 256, 0, L.stream>>>(p); break;
+    }
+  } else {
+    switch (wpl) {
+      case 1: scan_mw_kernel<FAM, 1><<<(uint32_t)blocks, 256, 0, L.stream>>>(p); break;
+      case 2: scan_mw_kernel<FAM, 2><<<(uint32_t)blocks, 256, 0, L.stream>>>(p); break;
+      case 4: scan_mw_kernel<FAM, 4><<<(uint32_t)blocks, 256, 0, L.stream>>>(p); break;
+      default: scan_mw_kernel<FAM, 8><<<(uint32_t)blocks, 256, 0, L.stream>>>(p); break;
+    }
   }
   g_launches.fetch_add(1);
   return cudaGetLastError();
@@ -2500,8 +2512,9 @@ struct LongParams {
   Epi epi;
 };
 
-template <int FAM>
+template <int FAM, class T = uint8_t>
 __global__ void __launch_bounds__(128) scan_long_kernel(const __grid_constant__ LongParams p) {
+  constexpr uint32_t CH_BITS = sizeof(T) * 8, CH_MASK = (1u << CH_BITS) - 1u;
   constexpr int WPL = 8;
   constexpr uint32_t SW = 32 * WPL;  // blocks per stripe
   const uint32_t lane = threadIdx.x & 31u;
@@ -2537,7 +2550,7 @@ __global__ void __launch_bounds__(128) scan_long_kernel(const __grid_constant__ 
       }
       continue;
     }
-    const uint8_t* __restrict__ txt = p.chars + o0;
+    const T* __restrict__ txt = reinterpret_cast<const T*>(p.chars) + o0;
     int32_t score = 0;
     uint32_t lcs_cnt = 0;
     for (uint32_t s = 0; s < nstripes; ++s) {
@@ -2571,7 +2584,7 @@ __global__ void __launch_bounds__(128) scan_long_kernel(const __grid_constant__ 
       }
       uint32_t cout = 0;
       for (uint32_t t = 0; t < steps; ++t) {
-        const uint32_t pk_in = __shfl_up_sync(0xffffffffu, ch_cur | (cout << 8), 1);
+        const uint32_t pk_in = __shfl_up_sync(0xffffffffu, ch_cur | (cout << CH_BITS), 1);
         uint32_t ch_nxt, cin;
         if (lane == 0) {
           ch_nxt = c1;
@@ -2582,8 +2595,8 @@ __global__ void __launch_bounds__(128) scan_long_kernel(const __grid_constant__ 
           in1 = in2;
           in2 = (s > 0 && t + 3 < len2) ? (uint32_t)__ldcg(carry + t + 3) : top0;
         } else {
-          ch_nxt = pk_in & 0xffu;
-          cin = pk_in >> 8;
+          ch_nxt = pk_in & CH_MASK;
+          cin = pk_in >> CH_BITS;
         }
 #pragma unroll
         for (int k = 0; k < WPL; ++k) Xn[k] = (w0 + k < words) ? __ldg(pm + (uint64_t)ch_nxt * words + w0 + k) : 0ull;
@@ -2690,7 +2703,8 @@ static cudaError_t launch_long_fam(const ScanLaunch& L) {
   const uint32_t blocks = (uint32_t)((warps + 3) / 4);
   cudaError_t e = dev_alloc(&p.scratch, (uint64_t)blocks * 4 * p.stride, L.stream);
   if (e != cudaSuccess) return e;
-  scan_long_kernel<FAM><<<blocks, 128, 0, L.stream>>>(p);
+  if (L.elem16) scan_long_kernel<FAM, uint16_t><<<blocks, 128, 0, L.stream>>>(p);
+  else scan_long_kernel<FAM><<<blocks, 128, 0, L.stream>>>(p);
   g_launches.fetch_add(1);
   e = cudaGetLastError();
   dev_free(p.scratch, L.stream);
@@ -3340,7 +3354,7 @@ cudaError_t launch_dl(const ScanLaunch& L) {
 }
 
 // ------------------------------------------------------------------------------------------------ jaro mw
-template <int MAXQ>
+template <int MAXQ, class T = uint8_t>
 __global__ void __launch_bounds__(128) jaro_mw_kernel(const __grid_constant__ MwParams p) {
   const bool off64 = p.off64 != nullptr;
   const uint64_t* __restrict__ pm = p.pm;
@@ -3349,11 +3363,11 @@ __global__ void __launch_bounds__(128) jaro_mw_kernel(const __grid_constant__ Mw
     const uint64_t o0 = off64 ? p.off64[c] : (uint64_t)p.off32[c];
     const uint64_t o1 = off64 ? p.off64[c + 1] : (uint64_t)p.off32[c + 1];
     const uint32_t len2 = (uint32_t)(o1 - o0);
-    const uint8_t* __restrict__ txt = p.chars + o0;
+    const T* __restrict__ txt = reinterpret_cast<const T*>(p.chars) + o0;
     auto pmw = [&](uint32_t w, uint32_t ch) -> uint64_t { return __ldg(pm + (uint64_t)ch * words + w); };
     auto bytes = [&](uint32_t j) -> uint32_t { return txt[j]; };
     const uint32_t len1 = p.len1;
-    auto jaro = [&](double cut) { return jaro_similarity_generic<MAXQ>(pmw, bytes, len1, len2, cut); };
+    auto jaro = [&](double cut) { return jaro_similarity_generic<MAXQ, T>(pmw, bytes, len1, len2, cut); };
     double r;
     if (p.epi.metric == M_JARO) {
       r = finish_float(p.epi, jaro);
@@ -3387,6 +3401,7 @@ struct JaroLongParams {
   Epi epi;
 };
 
+template <class T>
 __global__ void __launch_bounds__(128) jaro_long_kernel(const __grid_constant__ JaroLongParams p) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint64_t warp_global = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -3395,12 +3410,12 @@ __global__ void __launch_bounds__(128) jaro_long_kernel(const __grid_constant__ 
   const uint64_t* __restrict__ pm = p.pm;
   const uint32_t words = p.words;
   unsigned long long* P = reinterpret_cast<unsigned long long*>(p.scratch + warp_global * p.stride);
-  uint8_t* matched = reinterpret_cast<uint8_t*>(P + words);
+  T* matched = reinterpret_cast<T*>(P + words);
   for (uint64_t c = warp_global; c < p.n; c += total_warps) {
     const uint64_t o0 = off64 ? p.off64[c] : (uint64_t)p.off32[c];
     const uint64_t o1 = off64 ? p.off64[c + 1] : (uint64_t)p.off32[c + 1];
     const uint32_t len2_orig = (uint32_t)(o1 - o0), len1_orig = p.len1;
-    const uint8_t* __restrict__ txt = p.chars + o0;
+    const T* __restrict__ txt = reinterpret_cast<const T*>(p.chars) + o0;
     auto jaro = [&](double cutoff) -> double {  // warp-uniform: every lane returns the same value
       if (cutoff > 1.0) return 0.0;
       if (len1_orig == 0 && len2_orig == 0) return 1.0;
@@ -3434,7 +3449,7 @@ __global__ void __launch_bounds__(128) jaro_long_kernel(const __grid_constant__ 
             if (ball) {
               if (lane == (uint32_t)__ffs(ball) - 1u) {
                 __stcg(P + w, __ldcg(P + w) | (m & (0ull - m)));
-                matched[cc] = (uint8_t)ch;
+                matched[cc] = (T)ch;
               }
               ++cc;
               __syncwarp();
@@ -3495,14 +3510,15 @@ static cudaError_t launch_jaro_long(const ScanLaunch& L) {
   p.words = L.query.words;
   p.out = L.out;
   p.epi = L.epi;
-  p.stride = ((uint64_t)p.words * 8 + p.len1 + 63) / 64 * 64;
+  p.stride = ((uint64_t)p.words * 8 + (uint64_t)p.len1 * (L.elem16 ? 2 : 1) + 63) / 64 * 64;
   uint64_t warps = (uint64_t)L.sm_count * 16;
   if (warps > p.n) warps = p.n;
   if (warps < 1) warps = 1;
   const uint32_t blocks = (uint32_t)((warps + 3) / 4);
   cudaError_t e = dev_alloc(&p.scratch, (uint64_t)blocks * 4 * p.stride, L.stream);
   if (e != cudaSuccess) return e;
-  jaro_long_kernel<<<blocks, 128, 0, L.stream>>>(p);
+  if (L.elem16) jaro_long_kernel<uint16_t><<<blocks, 128, 0, L.stream>>>(p);
+  else jaro_long_kernel<uint8_t><<<blocks, 128, 0, L.stream>>>(p);
   g_launches.fetch_add(1);
   e = cudaGetLastError();
   dev_free(p.scratch, L.stream);
@@ -3525,7 +3541,8 @@ cudaError_t launch_jaro_mw(const ScanLaunch& L) {
   uint64_t blocks = (p.n + 127) / 128;
   const uint64_t max_blocks = (uint64_t)L.sm_count * 8;
   if (blocks > max_blocks) blocks = max_blocks;
-  if (p.len1 <= 256) jaro_mw_kernel<256><<<(uint32_t)blocks, 128, 0, L.stream>>>(p);
+  if (L.elem16) jaro_mw_kernel<2048, uint16_t><<<(uint32_t)blocks, 128, 0, L.stream>>>(p);
+  else if (p.len1 <= 256) jaro_mw_kernel<256><<<(uint32_t)blocks, 128, 0, L.stream>>>(p);
   else if (p.len1 <= 2048) jaro_mw_kernel<2048><<<(uint32_t)blocks, 128, 0, L.stream>>>(p);
   else return cudaErrorInvalidValue;
   g_launches.fetch_add(1);

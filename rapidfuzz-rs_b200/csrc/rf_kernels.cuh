@@ -77,6 +77,7 @@ struct ScanLaunch {
   int out_is_f64;
   cudaStream_t stream;
   int sm_count;
+  int elem16;         // corpus.chars is an array of uint16_t codes and query.pm_words has one row per code (multi-word kernels only)
   int jaro32;         // Jaro / Jaro-Winkler, query <= 32: 1 = row-wise 32-bit kernel, 0 = generic per-lane routine
 };
 

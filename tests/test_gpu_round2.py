@@ -711,6 +711,25 @@ def test_u32_queries_with_more_than_255_distinct_symbols(qlen, distinct):
     for m, kind, kw in metrics:
         assert_same(gpu_batch(m, kind, q, corpus8, **kw), orc.batch(m, kind, q, chars.astype(np.uint32), offsets, nthreads=0, **kw), ("wide q / u8 corpus", m, kw))
         assert_same(gpu_batch(m, kind, q, corpus32, **kw), orc.batch(m, kind, q, elems, off32, nthreads=0, **kw), ("wide q / compact u32 corpus", m, kw))
+    # (c) u32 candidates with a LARGE alphabet of their own (near-copies of the query keep its symbols): 16-bit codes
+    cands = []
+    for _ in range(120):
+        if rng.random() < 0.6:
+            c = q.copy()
+            hit = rng.random(qlen) < 0.05
+            c[hit] = base[rng.integers(0, len(base), int(hit.sum()))] + (rng.random(int(hit.sum())) < 0.3) * 50000
+            lo_ = int(rng.integers(0, qlen // 4 + 1))
+            cands.append(c[lo_: int(rng.integers(qlen // 2, qlen + 1))])
+        else:
+            cands.append((base[rng.integers(0, len(base), int(rng.choice([0, 1, 70, qlen])))] + 7).astype(np.uint32))
+    elems_c = np.concatenate(cands).astype(np.uint32)
+    off_c = np.zeros(len(cands) + 1, np.uint64)
+    off_c[1:] = np.cumsum([len(c) for c in cands])
+    corpus_big = rf.Corpus.from_u32(elems_c, off_c)
+    assert len(np.unique(elems_c)) > 255
+    for m, kind, kw in metrics:
+        assert_same(gpu_batch(m, kind, q, corpus_big, **kw), orc.batch(m, kind, q, elems_c, off_c, nthreads=0, **kw), ("wide q / big-alphabet u32 corpus", m, kw))
+    corpus_big.close()
     b = _bc("levenshtein", q)
     assert_same(b.stream("distance", chars, offsets), orc.batch("levenshtein", "distance", q, chars.astype(np.uint32), offsets, nthreads=0), "wide q stream")
     with pytest.raises(rf.RfError) as ei:      # symbol-comparing metrics still need a byte alphabet of the query's own

@@ -396,6 +396,12 @@ rf_status rf_corpus_create_u32(const uint32_t* elems, const uint64_t* offsets, u
     rf_status vs = check_offsets(off64 ? (const void*)c->d_off64 : (const void*)c->d_off32, off64, n, total, st, &c->max_len);
     if (vs != RF_OK) { rf_corpus_destroy(c); return vs; }
   }
+  {  // an unsigned element >= 2^31 shares its bit pattern with a negative signed one (see rf_corpus_create_elems)
+    int hug = 0;
+#pragma omp parallel for schedule(static) reduction(| : hug)
+    for (int64_t i = 0; i < (int64_t)total; ++i) hug |= (int)(elems[i] >> 31);
+    c->has_huge = hug != 0;
+  }
   if (g_compact32.load() && total) {
     rf_status s = compact_u32_corpus(c, st);
     if (s != RF_OK) { rf_corpus_destroy(c); return s; }
@@ -579,6 +585,8 @@ rf_status rf_batch_create_u32(rf_metric metric, const uint32_t* query, uint32_t 
   b->wide = true;
   b->alpha_overflow = overflow;
   b->s1w.assign(query, query + query_len);
+  for (uint32_t i = 0; i < query_len; ++i)
+    if (query[i] >> 31) b->has_huge = true;
   cudaError_t e = cudaMalloc(&b->d_alpha_keys, kAlphaSlots * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMalloc(&b->d_alpha_codes, kAlphaSlots);
   if (e == cudaSuccess) e = upload_sync(b->d_alpha_keys, keys.data(), kAlphaSlots * sizeof(uint32_t), device);
@@ -642,7 +650,7 @@ rf_status rf_corpus_create_elems(const void* elems, rf_elem_type type, const uin
   rf_status s = widen_to_u32(elems, type, offsets[n], &w, &neg, &huge);
   if (s != RF_OK) return s;
   s = rf_corpus_create_u32(w.data(), offsets, n, device, out);
-  if (s == RF_OK) { (*out)->has_negative = neg; (*out)->has_huge = huge; }
+  if (s == RF_OK) { (*out)->has_negative = neg; (*out)->has_huge = huge; }  // (the u32 path saw the negatives' patterns as "huge")
   return s;
 }
 
@@ -1922,14 +1930,12 @@ static rf_status cdist_u32_impl(const uint32_t* q_elems, const uint64_t* q_offse
     if (c->compact32) {
       uint32_t slot = alpha_hash(x);
       while (c->dict_codes[slot] && c->dict_keys[slot] != x) slot = (slot + 1) & (kAlphaSlots - 1);
-      renamed[i] = c->dict_codes[slot];
+      renamed[i] = c->dict_codes[slot];  // 0 (never a candidate code) when the corpus does not contain x
     } else {
-      renamed[i] = x < 256 ? (uint8_t)x : 0;  // a plain byte corpus: wider symbols match nothing ...
+      // a plain byte corpus may hold every byte value, so a wider symbol has no byte that "matches nothing": refuse
+      if (x > 255) return fail(RF_ERR_UNSUPPORTED, "rf_cdist_topk_u32 on a u8 corpus: query symbols beyond 255");
+      renamed[i] = (uint8_t)x;
     }
-  }
-  if (!c->compact32) {  // ... but 0 IS a byte there: give non-byte symbols a byte the corpus cannot equal is impossible in
-    for (uint64_t i = 0; i < q_offsets[nq]; ++i)  // general, so refuse them instead of guessing
-      if (q_elems[i] > 255) return fail(RF_ERR_UNSUPPORTED, "rf_cdist_topk_u32 on a u8 corpus: query symbols beyond 255");
   }
   return cdist_impl(renamed.data(), q_offsets, nq, c, args, k, idx_out, dist_out, on_device, st, true);
 }

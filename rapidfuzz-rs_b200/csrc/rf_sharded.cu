@@ -85,11 +85,17 @@ rf_status for_each_shard(size_t count, Fn fn) {
   }
   std::vector<std::thread> th;
   th.reserve(count);
-  for (size_t i = 0; i < count; ++i)
-    th.emplace_back([&, i] {
+  for (size_t i = 0; i < count; ++i) {
+    try {
+      th.emplace_back([&, i] {
+        st[i] = fn(i);
+        if (st[i] != RF_OK) msg[i] = rfi::last_error();
+      });
+    } catch (...) {  // no thread to be had (nothing may propagate across the C boundary): this shard runs on the caller's
       st[i] = fn(i);
       if (st[i] != RF_OK) msg[i] = rfi::last_error();
-    });
+    }
+  }
   for (auto& t : th) t.join();
   for (size_t i = 0; i < count; ++i)
     if (st[i] != RF_OK) return rfi::fail(st[i], "shard " + std::to_string(i) + ": " + msg[i]);

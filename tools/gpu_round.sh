@@ -1,4 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest_r2l.log 2>&1; echo "pytest rc=$?"; tail -12 gpurun_out/pytest_r2l.log
-python tools/bench_configs.py mw 2>gpurun_out/r2_mw_new4.err | head -3 > gpurun_out/r2_mw_new4.jsonl; cut -c1-330 gpurun_out/r2_mw_new4.jsonl
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_r2.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke_r2.log
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/sanitize_smoke.py > gpurun_out/r2_sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -4 gpurun_out/r2_sanitizer_memcheck.log
+timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python tools/sanitize_smoke.py > gpurun_out/r2_sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -4 gpurun_out/r2_sanitizer_racecheck.log
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r2_launches_bench.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1 --c5-queries 200 > gpurun_out/bench_under_ncu_r2.log 2>&1; echo "ncu rc=$?"; wc -l gpurun_out/r2_launches_bench.csv

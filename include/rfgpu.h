@@ -324,6 +324,15 @@ rf_status rf_sharded_stream_u32(const rf_sharded_batch* b, const uint8_t* chars,
                                 const rf_args* args, uint32_t* out_host);
 rf_status rf_sharded_stream_f64(const rf_sharded_batch* b, const uint8_t* chars, const uint64_t* offsets, uint64_t n, rf_kind kind,
                                 const rf_args* args, double* out_host);
+/* == rf_batch_stream_*_len8[_packed6] over the batch's devices, with NO static split: the per-device pipelines take their
+ * chunks from one shared planner as their slots free up, so a device behind a faster PCIe link takes more chunks and the
+ * call runs at the aggregate host-to-device rate of the box instead of waiting for the slowest link. */
+rf_status rf_sharded_stream_u32_len8(const rf_sharded_batch* b, const uint8_t* chars, const uint8_t* lens, uint64_t n, rf_kind kind,
+                                     const rf_args* args, uint32_t* out_host);
+rf_status rf_sharded_stream_u8_len8(const rf_sharded_batch* b, const uint8_t* chars, const uint8_t* lens, uint64_t n, rf_kind kind,
+                                    const rf_args* args, uint8_t* out_host);
+rf_status rf_sharded_stream_u8_len8_packed6(const rf_sharded_batch* b, const uint8_t* packed, const uint8_t* dict64, const uint8_t* lens,
+                                            uint64_t n, rf_kind kind, const rf_args* args, uint8_t* out_host);
 
 /* ---- one process per GPU (MPI / torchrun style hosts): a communicator over the ranks + scoring with the final
  * all-gather of the score vectors (the path's only exchange step, north star: "NCCL all-gather only for the final score

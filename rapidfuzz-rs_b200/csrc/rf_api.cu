@@ -1327,6 +1327,8 @@ namespace {
 constexpr int kSlots = 3;
 struct StreamSlot {
   cudaStream_t st = nullptr;
+  cudaEvent_t done = nullptr;    // recorded behind the slot's last chunk (back-pressure of the _len8 entry points)
+  bool busy = false;
   uint8_t* d_chars = nullptr;
   uint8_t* d_renamed = nullptr;  // u32-query comparators: the chunk renamed to the query's byte alphabet (lazily allocated)
   uint8_t* d_packed = nullptr;   // *_packed6 entry points: the chunk's 6-bit packed characters as they crossed the link
@@ -1363,6 +1365,7 @@ void stream_ctx_release(StreamCtx* x) {
     if (s.d_out8) cudaFree(s.d_out8);
     if (s.d_offs) cudaFree(s.d_offs);
     if (s.d_out) cudaFree(s.d_out);
+    if (s.done) cudaEventDestroy(s.done);
     if (s.st) cudaStreamDestroy(s.st);
     s = StreamSlot{};
   }
@@ -1375,6 +1378,7 @@ cudaError_t stream_ctx_prepare(StreamCtx* x, uint64_t cap_bytes, uint64_t cap_n)
   cudaError_t e = cudaSuccess;
   for (auto& s : x->slot) {
     if ((e = cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking)) != cudaSuccess) break;
+    if ((e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming | cudaEventBlockingSync)) != cudaSuccess) break;
     // chars: 16 bytes of alignment lead-in + 64 bytes of over-read slack; offsets: 16 entries of slack
     if ((e = cudaMalloc(&s.d_chars, cap_bytes + 256)) != cudaSuccess) break;
     if ((e = cudaMemset(s.d_chars, 0, cap_bytes + 256)) != cudaSuccess) break;
@@ -1532,12 +1536,48 @@ __global__ void __launch_bounds__(256) unpack6_kernel(const uint32_t* __restrict
   }
 }
 
+// Hands out the chunks of a _len8 streaming call.  One device: a private planner.  rf_sharded_stream_*_len8*: ONE planner
+// shared by the per-device workers, each of which takes its next chunk only when one of its three pipeline slots is free,
+// so a device behind a faster PCIe link simply takes more chunks (the 8-GPU box gives GPUs 0-3 23 GB/s and GPUs 4-7 35 GB/s
+// when all copy at once: equal static shares wait for the slowest link).
+struct Len8Planner {
+  std::mutex mu;
+  const uint8_t* lens = nullptr;
+  uint64_t n = 0, cap_n = 0, cap_bytes = 0;
+  bool packed6 = false;
+  uint64_t i0 = 0, pos = 0;  // next candidate, its character position
+  struct Chunk { uint64_t i0, i1, pos, B0, bytes; };
+  // false: nothing left (or *too_small: one block of 4096 candidates does not fit a chunk)
+  bool next(Chunk* c, bool* too_small) {
+    constexpr uint64_t kBlock = 4096;  // chunk boundaries fall on multiples of kBlock candidates: lengths are summed block-wise
+    std::lock_guard<std::mutex> lk(mu);
+    *too_small = false;
+    if (i0 >= n) return false;
+    const uint64_t B0 = packed6 ? (pos & ~63ull) : (pos & ~15ull);  // packed: 64 characters = 48 bytes keep every piece 16-byte aligned
+    uint64_t i1 = i0, bytes = pos - B0;
+    while (i1 < n && i1 - i0 < cap_n) {
+      const uint64_t j1 = (n - i1 < kBlock) ? n : i1 + kBlock;
+      if (j1 - i0 > cap_n) break;
+      const uint64_t sum = sum_bytes(lens + i1, j1 - i1);
+      if (bytes + sum > cap_bytes) break;
+      bytes += sum;
+      i1 = j1;
+    }
+    if (i1 == i0) { *too_small = true; return false; }
+    *c = Chunk{i0, i1, pos, B0, bytes};
+    pos = B0 + bytes;
+    i0 = i1;
+    return true;
+  }
+};
+
 // rf_batch_stream_*_len8: the candidates' lengths cross PCIe as ONE byte each instead of a 4- or 8-byte CSR start (the
 // starts of a chunk are rebuilt on the device by a prefix sum), and the results can come back as one byte each: 36.9 + 1
 // instead of 39.9 + 4 bytes per config-2 pair on the host side of the link.
 // packed6: `chars` is the 6-bit packed stream of rf_pack6_u8 (character i at bits [6i, 6i+6)), `dict` its 64 symbols.
 rf_status stream_len8_impl(const rf_batch* b, const uint8_t* chars, const uint8_t* lens, uint64_t n, rf_kind kind,
-                           const rf_args* args, void* out_host, bool out_u8, const uint8_t* dict = nullptr) {
+                           const rf_args* args, void* out_host, bool out_u8, const uint8_t* dict = nullptr,
+                           Len8Planner* shared = nullptr) {
   const bool packed6 = dict != nullptr;
   if (!b) return fail(RF_ERR_INVALID_ARG, "NULL handle");
   if ((int)kind < 0 || (int)kind > 3) return fail(RF_ERR_INVALID_ARG, "unknown kind");
@@ -1582,25 +1622,33 @@ rf_status stream_len8_impl(const rf_batch* b, const uint8_t* chars, const uint8_
   uint32_t* d_over = nullptr;
   if ((e = cudaMalloc(&d_over, 16)) != cudaSuccess) return cuda_fail(e, "streaming buffers");
   if ((e = cudaMemset(d_over, 0, 16)) != cudaSuccess) { cudaFree(d_over); return cuda_fail(e, "streaming buffers"); }
-  constexpr uint64_t kBlock = 4096;  // chunk boundaries fall on multiples of kBlock candidates: the host only sums lengths block-wise
+  Len8Planner local;
+  Len8Planner* plan = shared ? shared : &local;
+  if (!shared) {
+    local.lens = lens;
+    local.n = n;
+    local.cap_n = cap_n;
+    local.cap_bytes = cap_bytes;
+    local.packed6 = packed6;
+  }
   rf_status s = RF_OK;
-  uint64_t i0 = 0, pos = 0;  // pos = byte position of candidate i0
   int k = 0;
-  while (i0 < n && s == RF_OK) {
-    const uint64_t B0 = packed6 ? (pos & ~63ull) : (pos & ~15ull);  // packed: 64 characters = 48 bytes keep every piece 16-byte aligned
-    uint64_t i1 = i0, bytes = pos - B0;
-    while (i1 < n && i1 - i0 < cap_n) {
-      const uint64_t j1 = (n - i1 < kBlock) ? n : i1 + kBlock;
-      if (j1 - i0 > cap_n) break;
-      const uint64_t sum = sum_bytes(lens + i1, j1 - i1);
-      if (bytes + sum > cap_bytes) break;
-      bytes += sum;
-      i1 = j1;
-    }
-    if (i1 == i0) { s = fail(RF_ERR_UNSUPPORTED, "stream_chunk_mb / stream_chunk_kcand too small for one block of 4096 candidates"); break; }
-    const uint64_t cn = i1 - i0, B1 = B0 + bytes;
+  for (auto& sl : x->slot) sl.busy = false;
+  for (;;) {
     StreamSlot& sl = x->slot[k];
     k = (k + 1) % kSlots;
+    if (sl.busy) {  // back-pressure: the slot's previous chunk must have left the device before the next one is taken
+      if ((e = cudaEventSynchronize(sl.done)) != cudaSuccess) { s = cuda_fail(e, "streaming scan"); break; }
+      sl.busy = false;
+    }
+    Len8Planner::Chunk ch;
+    bool too_small = false;
+    if (!plan->next(&ch, &too_small)) {
+      if (too_small) s = fail(RF_ERR_UNSUPPORTED, "stream_chunk_mb / stream_chunk_kcand too small for one block of 4096 candidates");
+      break;
+    }
+    const uint64_t i0 = ch.i0, i1 = ch.i1, pos = ch.pos, B0 = ch.B0, bytes = ch.bytes;
+    const uint64_t cn = i1 - i0, B1 = B0 + bytes;
     if (B1 > B0) {
       if (!chars) { s = fail(RF_ERR_INVALID_ARG, "chars is NULL"); break; }
       if (packed6) {
@@ -1645,12 +1693,13 @@ rf_status stream_len8_impl(const rf_batch* b, const uint8_t* chars, const uint8_
     } else {
       e = cudaMemcpyAsync((uint8_t*)out_host + i0 * 4, sl.d_out, cn * 4, cudaMemcpyDeviceToHost, sl.st);
     }
+    if (e == cudaSuccess) e = cudaEventRecord(sl.done, sl.st);
     if (e != cudaSuccess) { s = cuda_fail(e, "chunk download"); break; }
-    pos = B1;
-    i0 = i1;
+    sl.busy = true;
   }
   for (auto& sl : x->slot) {
     e = cudaStreamSynchronize(sl.st);
+    sl.busy = false;
     if (e != cudaSuccess && s == RF_OK) s = cuda_fail(e, "streaming scan");
   }
   uint32_t over = 0;
@@ -2000,6 +2049,22 @@ rf_status score_device_range(const rf_batch* b, const rf_corpus* c, rf_kind kind
   if (b->wide || c->d_elems32 || c->compact32) return ::fail(RF_ERR_UNSUPPORTED, "candidate sub-ranges need a byte comparator and a byte corpus");
   return ::score_view(b, CorpusView{c->d_chars, c->d_off32, c->d_off64, c->n, c->total, c->max_len}, &c->lb, c->device, kind, args,
                       out_dev, want_f64, st, nullptr, r0, r1);
+}
+// rf_sharded_stream_*_len8*: the per-device workers of one call share `plan` (created by stream_len8_plan_create)
+void* stream_len8_plan_create(const uint8_t* lens, uint64_t n, bool packed6) {
+  Len8Planner* p = new (std::nothrow) Len8Planner();
+  if (!p) return nullptr;
+  p->lens = lens;
+  p->n = n;
+  p->cap_bytes = (uint64_t)(g_stream_mb.load() > 0 ? g_stream_mb.load() : 1) << 20;
+  p->cap_n = (uint64_t)(g_stream_kcand.load() > 0 ? g_stream_kcand.load() : 1) << 10;
+  p->packed6 = packed6;
+  return p;
+}
+void stream_len8_plan_destroy(void* plan) { delete static_cast<Len8Planner*>(plan); }
+rf_status stream_len8_shared(const rf_batch* b, const uint8_t* chars, const uint8_t* dict64, const uint8_t* lens, uint64_t n,
+                             rf_kind kind, const rf_args* args, void* out_host, bool out_u8, void* plan) {
+  return stream_len8_impl(b, chars, lens, n, kind, args, out_host, out_u8, dict64, static_cast<Len8Planner*>(plan));
 }
 rf_status corpus_create_sub(const uint8_t* chars, const uint64_t* offsets, uint64_t lo, uint64_t hi, int device, rf_corpus** out) {
   return ::corpus_create_host(chars, offsets + lo, true, hi - lo, device, out, offsets[lo]);

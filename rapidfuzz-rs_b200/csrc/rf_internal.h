@@ -84,6 +84,11 @@ rf_status stream_u64(const rf_batch* b, const uint8_t* chars, const uint64_t* of
                      void* out_host, bool want_f64);
 rf_status stream_u32(const rf_batch* b, const uint8_t* chars, const uint32_t* offsets, uint64_t n, rf_kind kind, const rf_args* args,
                      void* out_host, bool want_f64);
+// _len8 streaming with the chunks handed out by ONE planner shared between the per-device workers of a sharded call
+void* stream_len8_plan_create(const uint8_t* lens, uint64_t n, bool packed6);
+void stream_len8_plan_destroy(void* plan);
+rf_status stream_len8_shared(const rf_batch* b, const uint8_t* chars, const uint8_t* dict64, const uint8_t* lens, uint64_t n,
+                             rf_kind kind, const rf_args* args, void* out_host, bool out_u8, void* plan);
 int sm_count_of(int device);
 // corpus of the candidates [lo, hi) of a larger host CSR (chars = the larger array's start, offsets = its full index)
 rf_status corpus_create_sub(const uint8_t* chars, const uint64_t* offsets, uint64_t lo, uint64_t hi, int device, rf_corpus** out);

@@ -233,8 +233,8 @@ void piece_range(uint64_t n, int K, int k, uint64_t* a, uint64_t* z) {
   *z = std::min<uint64_t>(n, (uint64_t)(k + 1) * per);
 }
 
-// The same with the copy engines instead of NCCL kernels (one process, peer access): device i PULLS piece k of every other
-// shard over NVLink on its communication stream as soon as that shard's compute stream has produced it.  DMA transfers
+// The same with the copy engines instead of NCCL kernels (one process, peer access): as soon as a shard's compute stream
+// has produced piece k, that device's communication stream PUSHES it into every peer's buffer over NVLink.  DMA transfers
 // need no SM, so they overlap the persistent scan kernel of piece k+1 completely -- NCCL's broadcast kernels cannot: the
 // scan occupies every CTA slot, and the transfer of piece k only starts when piece k+1 retires (measured: no gain).
 rf_status scan_allgather_copies(rf_sharded_corpus* c, const rf_sharded_batch* b, rf_kind kind, const rf_args* args,
@@ -819,6 +819,42 @@ static rf_status sharded_stream(const rf_sharded_batch* b, const uint8_t* chars,
     if (lo[i + 1] == lo[i]) return RF_OK;
     return rfi::stream_u64(b->per[i], chars, offsets + lo[i], lo[i + 1] - lo[i], kind, args, (uint8_t*)out_host + lo[i] * esz, want_f64);
   });
+}
+// ... and with one length byte per candidate on the wire (optionally 6-bit packed characters, byte results): no static
+// split at all -- the devices' workers take chunks from ONE shared planner as their pipeline slots free up, so every
+// PCIe link runs at whatever rate the host gives it and the call ends when the AGGREGATE is through.
+static rf_status sharded_stream_len8(const rf_sharded_batch* b, const uint8_t* chars, const uint8_t* dict64, const uint8_t* lens,
+                                     uint64_t n, rf_kind kind, const rf_args* args, void* out_host, bool out_u8) {
+  if (!b) return rfi::fail(RF_ERR_INVALID_ARG, "NULL handle");
+  if (n == 0) return RF_OK;
+  if (!lens || !out_host) return rfi::fail(RF_ERR_INVALID_ARG, "NULL argument");
+  void* plan = rfi::stream_len8_plan_create(lens, n, dict64 != nullptr);
+  if (!plan) return rfi::fail(RF_ERR_OOM, "host allocation failed");
+  // a device listed twice shares one pipeline (the per-device streaming context is exclusive): one worker per distinct device
+  std::vector<size_t> workers;
+  for (size_t i = 0; i < b->devices.size(); ++i) {
+    bool seen = false;
+    for (size_t j : workers) seen = seen || b->devices[j] == b->devices[i];
+    if (!seen) workers.push_back(i);
+  }
+  const rf_status s = for_each_shard(workers.size(), [&](size_t w) {
+    return rfi::stream_len8_shared(b->per[workers[w]], chars, dict64, lens, n, kind, args, out_host, out_u8, plan);
+  });
+  rfi::stream_len8_plan_destroy(plan);
+  return s;
+}
+rf_status rf_sharded_stream_u32_len8(const rf_sharded_batch* b, const uint8_t* chars, const uint8_t* lens, uint64_t n, rf_kind kind,
+                                     const rf_args* args, uint32_t* out_host) {
+  return sharded_stream_len8(b, chars, nullptr, lens, n, kind, args, out_host, false);
+}
+rf_status rf_sharded_stream_u8_len8(const rf_sharded_batch* b, const uint8_t* chars, const uint8_t* lens, uint64_t n, rf_kind kind,
+                                    const rf_args* args, uint8_t* out_host) {
+  return sharded_stream_len8(b, chars, nullptr, lens, n, kind, args, out_host, true);
+}
+rf_status rf_sharded_stream_u8_len8_packed6(const rf_sharded_batch* b, const uint8_t* packed, const uint8_t* dict64, const uint8_t* lens,
+                                            uint64_t n, rf_kind kind, const rf_args* args, uint8_t* out_host) {
+  if (!dict64) return rfi::fail(RF_ERR_INVALID_ARG, "dict64 is NULL");
+  return sharded_stream_len8(b, packed, dict64, lens, n, kind, args, out_host, true);
 }
 rf_status rf_sharded_stream_u32(const rf_sharded_batch* b, const uint8_t* chars, const uint64_t* offsets, uint64_t n, rf_kind kind,
                                 const rf_args* args, uint32_t* out_host) {

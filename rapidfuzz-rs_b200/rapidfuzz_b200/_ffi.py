@@ -104,6 +104,9 @@ SYMBOLS = {
     "rf_sharded_cdist_topk_u8": (_int, [_vp, _vp, _u32, _vp, _PA, _u32, _vp, _vp]),
     "rf_sharded_stream_u32": (_int, [_vp, _vp, _vp, _u64, _int, _PA, _vp]),
     "rf_sharded_stream_f64": (_int, [_vp, _vp, _vp, _u64, _int, _PA, _vp]),
+    "rf_sharded_stream_u32_len8": (_int, [_vp, _vp, _vp, _u64, _int, _PA, _vp]),
+    "rf_sharded_stream_u8_len8": (_int, [_vp, _vp, _vp, _u64, _int, _PA, _vp]),
+    "rf_sharded_stream_u8_len8_packed6": (_int, [_vp, _vp, _vp, _vp, _u64, _int, _PA, _vp]),
     "rf_comm_unique_id": (_int, [_vp]),
     "rf_comm_create_rank": (_int, [_vp, _int, _int, _int, C.POINTER(_vp)]),
     "rf_comm_destroy": (_int, [_vp]),

@@ -267,6 +267,31 @@ class ShardedBatchComparator:
         _ffi.check(fn(self._h, chars.ctypes.data, offsets.ctypes.data, n, _ffi.KINDS[kind], C.byref(ca), out.ctypes.data))
         return out
 
+    def stream_len8(self, kind, chars, lens, args=None, out=None, u8_results=False, dict64=None):
+        """rf_sharded_stream_{u32,u8}_len8[_packed6]: one length byte per candidate on the wire, chunks handed to the devices
+        dynamically (no static split).  dict64 given: `chars` is the 6-bit packed stream of corpus.pack6 (u8 results only)."""
+        import ctypes as C
+        from . import _ffi
+        from ._scorer import Args
+        chars = np.ascontiguousarray(chars, dtype=np.uint8)
+        lens = np.ascontiguousarray(lens, dtype=np.uint8)
+        n = len(lens)
+        ca = (args if args is not None else Args())._c(False)
+        dt = np.uint8 if u8_results else np.uint32
+        if out is None:
+            out = np.empty(n, dtype=dt)
+        assert out.dtype == dt and len(out) >= n and out.flags.c_contiguous
+        L = _ffi.lib()
+        if dict64 is not None:
+            assert u8_results, "the packed form returns byte scores"
+            d = np.ascontiguousarray(dict64, dtype=np.uint8)
+            _ffi.check(L.rf_sharded_stream_u8_len8_packed6(self._h, chars.ctypes.data, d.ctypes.data, lens.ctypes.data, n,
+                                                           _ffi.KINDS[kind], C.byref(ca), out.ctypes.data))
+        else:
+            fn = L.rf_sharded_stream_u8_len8 if u8_results else L.rf_sharded_stream_u32_len8
+            _ffi.check(fn(self._h, chars.ctypes.data, lens.ctypes.data, n, _ffi.KINDS[kind], C.byref(ca), out.ctypes.data))
+        return out
+
     def close(self):
         from . import _ffi
         if getattr(self, "_h", None):

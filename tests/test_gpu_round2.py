@@ -178,6 +178,26 @@ def test_sharded_stream_and_edge_shapes(devices):
     sb = sharding.ShardedBatchComparator("levenshtein", q, devices)
     exp = orc.batch("levenshtein", "distance", q, chars, offsets, nthreads=0)
     assert_same(sb.stream("distance", chars, offsets), exp, "sharded stream")
+    # ... and the dynamically balanced forms: one length byte per candidate, optional byte results / 6-bit packed characters
+    L = _ffi.lib()
+    for mb, kc in ((64, 2048), (1, 4)):
+        _ffi.check(L.rf_set_option(b"stream_chunk_mb", mb))
+        _ffi.check(L.rf_set_option(b"stream_chunk_kcand", kc))
+        try:
+            ok_len = np.diff(offsets.astype(np.int64)) <= 255
+            assert ok_len.all()
+            lens8 = np.diff(offsets.astype(np.int64)).astype(np.uint8)
+            assert_same(sb.stream_len8("distance", chars, lens8), exp, ("sharded len8", mb))
+            sub = exp <= 254
+            got8 = sb.stream_len8("distance", chars[: int(offsets[20000])], lens8[:20000], u8_results=True) if sub[:20000].all() else None
+            if got8 is not None:
+                assert np.array_equal(got8, exp[:20000].astype(np.uint8))
+            packed, d64 = rf.pack6(chars)
+            if sub.all():
+                assert np.array_equal(sb.stream_len8("distance", packed, lens8, u8_results=True, dict64=d64), exp.astype(np.uint8)), ("sharded packed6", mb)
+        finally:
+            _ffi.check(L.rf_set_option(b"stream_chunk_mb", 64))
+            _ffi.check(L.rf_set_option(b"stream_chunk_kcand", 2048))
     # fewer candidates than shards, empty corpus, all-empty candidates
     for n in (0, 1, 2):
         sc = sharding.ShardedCorpus(chars[: int(offsets[n])], offsets[: n + 1], devices)

@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--c5-queries", type=int, default=10_000)
     ap.add_argument("--c5-candidates", type=int, default=10_000_000)
     ap.add_argument("--only-gather", action="store_true")
+    ap.add_argument("--skip-c5", action="store_true")
     a = ap.parse_args()
     L = _ffi.lib()
     devs = list(range(a.gpus))
@@ -97,8 +98,23 @@ def main():
     ms = best_of(stream, reps=2)
     out["stream_from_pinned_host"] = {"ms": ms, "pairs_per_s": n / (ms * 1e-3), "h2d_GBps_total": (float(offsets[n]) + 8.0 * n) / ms / 1e6,
                                       "equals_resident_scores": bool(np.array_equal(host, ref))}
+    # the dynamically balanced forms (shared chunk planner): plain bytes + length bytes, byte results; 6-bit packed characters
+    lens8 = torch.empty(n, dtype=torch.uint8).pin_memory().numpy()
+    np.copyto(lens8, np.diff(offsets.view(np.int64)), casting="unsafe")
+    out8 = torch.empty(n, dtype=torch.uint8).pin_memory().numpy()
+    ms = best_of(lambda: sb.stream_len8("distance", chars, lens8, out=out8, u8_results=True), reps=2)
+    out["stream_len8_dynamic"] = {"ms": ms, "pairs_per_s": n / (ms * 1e-3), "h2d_GBps_total": (float(offsets[n]) + n) / ms / 1e6,
+                                  "equals_resident_scores": bool(np.array_equal(out8, ref.astype(np.uint8)))}
+    packed, d64 = rf.pack6(chars, pinned=True)
+    out8[:] = 0
+    ms = best_of(lambda: sb.stream_len8("distance", packed, lens8, out=out8, u8_results=True, dict64=d64), reps=2)
+    out["stream_len8_packed6_dynamic"] = {"ms": ms, "pairs_per_s": n / (ms * 1e-3), "h2d_GBps_total": (float(offsets[n]) * 0.75 + n) / ms / 1e6,
+                                          "equals_resident_scores": bool(np.array_equal(out8, ref.astype(np.uint8)))}
     sb.close()
     sc.close()
+    if a.skip_c5:
+        print(json.dumps(out))
+        return
     # config 5: many-vs-many over the sharded corpus
     nq, n5, k = a.c5_queries, a.c5_candidates, 10
     qs = np.stack([synth.synth_query(5 + i, 32) for i in range(nq)])

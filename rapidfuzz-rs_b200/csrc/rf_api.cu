@@ -1324,7 +1324,7 @@ rf_status rf_batch_filter_f64(const rf_batch* b, const rf_corpus* c, rf_kind kin
 // D2H on one of kSlots streams, so the PCIe copies of one chunk overlap the scan and the result download of
 // the others.  Steady state is bound by the H2D link (about len+4 bytes per candidate).
 namespace {
-constexpr int kSlots = 3;
+constexpr int kSlots = 4;
 struct StreamSlot {
   cudaStream_t st = nullptr;
   cudaEvent_t done = nullptr;    // recorded behind the slot's last chunk (back-pressure of the _len8 entry points)
@@ -1545,6 +1545,8 @@ struct Len8Planner {
   const uint8_t* lens = nullptr;
   uint64_t n = 0, cap_n = 0, cap_bytes = 0;
   bool packed6 = false;
+  std::vector<uint32_t> block_sums;  // shared planner: the length sum of every 4096-candidate block, computed up front by all
+                                     // host threads (a serial 4 GB/s summing loop under the lock capped 8 GPUs at 4.2e9 pairs/s)
   uint64_t i0 = 0, pos = 0;  // next candidate, its character position
   struct Chunk { uint64_t i0, i1, pos, B0, bytes; };
   // false: nothing left (or *too_small: one block of 4096 candidates does not fit a chunk)
@@ -1558,7 +1560,7 @@ struct Len8Planner {
     while (i1 < n && i1 - i0 < cap_n) {
       const uint64_t j1 = (n - i1 < kBlock) ? n : i1 + kBlock;
       if (j1 - i0 > cap_n) break;
-      const uint64_t sum = sum_bytes(lens + i1, j1 - i1);
+      const uint64_t sum = block_sums.empty() ? sum_bytes(lens + i1, j1 - i1) : block_sums[i1 / kBlock];
       if (bytes + sum > cap_bytes) break;
       bytes += sum;
       i1 = j1;
@@ -2059,6 +2061,13 @@ void* stream_len8_plan_create(const uint8_t* lens, uint64_t n, bool packed6) {
   p->cap_bytes = (uint64_t)(g_stream_mb.load() > 0 ? g_stream_mb.load() : 1) << 20;
   p->cap_n = (uint64_t)(g_stream_kcand.load() > 0 ? g_stream_kcand.load() : 1) << 10;
   p->packed6 = packed6;
+  const uint64_t nblocks = (n + 4095) / 4096;
+  p->block_sums.resize(nblocks);
+#pragma omp parallel for schedule(static)
+  for (int64_t bl = 0; bl < (int64_t)nblocks; ++bl) {
+    const uint64_t a = (uint64_t)bl * 4096, z = a + 4096 < n ? a + 4096 : n;
+    p->block_sums[bl] = (uint32_t)sum_bytes(lens + a, z - a);
+  }
   return p;
 }
 void stream_len8_plan_destroy(void* plan) { delete static_cast<Len8Planner*>(plan); }

@@ -184,17 +184,14 @@ def test_sharded_stream_and_edge_shapes(devices):
         _ffi.check(L.rf_set_option(b"stream_chunk_mb", mb))
         _ffi.check(L.rf_set_option(b"stream_chunk_kcand", kc))
         try:
-            ok_len = np.diff(offsets.astype(np.int64)) <= 255
-            assert ok_len.all()
-            lens8 = np.diff(offsets.astype(np.int64)).astype(np.uint8)
-            assert_same(sb.stream_len8("distance", chars, lens8), exp, ("sharded len8", mb))
-            sub = exp <= 254
-            got8 = sb.stream_len8("distance", chars[: int(offsets[20000])], lens8[:20000], u8_results=True) if sub[:20000].all() else None
-            if got8 is not None:
-                assert np.array_equal(got8, exp[:20000].astype(np.uint8))
-            packed, d64 = rf.pack6(chars)
-            if sub.all():
-                assert np.array_equal(sb.stream_len8("distance", packed, lens8, u8_results=True, dict64=d64), exp.astype(np.uint8)), ("sharded packed6", mb)
+            c8, o8 = make_corpus(np.random.default_rng(6), 30_000, [0, 1, 3, 8, 20, 33, 64, 70, 255], alphabet=5, query=q)
+            e8 = orc.batch("levenshtein", "distance", q, c8, o8, nthreads=0)
+            lens8 = np.diff(o8.astype(np.int64)).astype(np.uint8)
+            assert_same(sb.stream_len8("distance", c8, lens8), e8, ("sharded len8", mb))
+            assert int(e8.max()) <= 254
+            assert np.array_equal(sb.stream_len8("distance", c8, lens8, u8_results=True), e8.astype(np.uint8)), ("sharded len8 u8", mb)
+            packed, d64 = rf.pack6(c8)
+            assert np.array_equal(sb.stream_len8("distance", packed, lens8, u8_results=True, dict64=d64), e8.astype(np.uint8)), ("sharded packed6", mb)
         finally:
             _ffi.check(L.rf_set_option(b"stream_chunk_mb", 64))
             _ffi.check(L.rf_set_option(b"stream_chunk_kcand", 2048))

@@ -44,6 +44,7 @@ def main():
     ap.add_argument("--c5-candidates", type=int, default=10_000_000)
     ap.add_argument("--only-gather", action="store_true")
     ap.add_argument("--skip-c5", action="store_true")
+    ap.add_argument("--skip-gather", action="store_true")
     a = ap.parse_args()
     L = _ffi.lib()
     devs = list(range(a.gpus))
@@ -72,7 +73,7 @@ def main():
     ptrs = (C.c_void_p * a.gpus)(*[b.data_ptr() for b in bufs])
     out["score_allgather_device"] = {}
     for mode, mname in ((1, "copy_engines"), (2, "nccl")):
-        if a.gpus == 1 and mode == 2:
+        if (a.gpus == 1 and mode == 2) or a.skip_gather:
             continue
         for chunks in (1, 4, 8):
             _ffi.check(L.rf_set_option(b"sharded_collective", mode))

@@ -1,18 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/bench_r2s_n8.json 2> gpurun_out/bench_r2s_n8.err; echo "bench n8 rc=$?"
+python -m pytest tests/test_gpu_round2.py -x -q -k "sharded_stream" > gpurun_out/pytest_r2v.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_r2v.log
+timeout 900 python tools/bench_sharded_abi.py --gpus 8 --per-gpu 50000000 --skip-c5 --skip-gather > gpurun_out/sharded_abi_n8_dyn3.json 2> gpurun_out/sharded_abi_n8_dyn3.err; echo "abi rc=$?"
 python - <<'P'
 import json
-d=json.loads([l for l in open('gpurun_out/bench_r2s_n8.json') if l.startswith('{')][-1])
-e=d['e2e']; print('value',d['value'],'e2e',e['value'],e['ms_per_step'],e['h2d_gbs'],'len8',e['len8']['value'],'csr',e['csr_u32']['value'],d['run'], 'pack', e['one_time_host_pack6_s'])
-for k,v in d['configs'].items(): print(k, {a:b for a,b in v.items() if a in ('ms_per_step','pairs_per_s','error','skipped','scan_ms_max_over_ranks','gather_merge_ms')})
-print(d['configs']['c2_gather'].get('rf_batch_score_u32_allgather_device'))
+d=json.loads([l for l in open('gpurun_out/sharded_abi_n8_dyn3.json') if l.startswith('{')][-1])
+for k in ('stream_from_pinned_host','stream_len8_dynamic','stream_len8_packed6_dynamic'): print(k, d.get(k))
 P
-tail -3 gpurun_out/bench_r2s_n8.err
-timeout 600 python bench.py --gpus 4 --steps 20 --warmup 5 > gpurun_out/bench_r2s_n4.json 2> gpurun_out/bench_r2s_n4.err; echo "bench n4 rc=$?"
-python - <<'P'
-import json
-d=json.loads([l for l in open('gpurun_out/bench_r2s_n4.json') if l.startswith('{')][-1])
-e=d['e2e']; print('N4 value',d['value'],'e2e',e['value'],'len8',e['len8']['value'],'csr',e['csr_u32']['value'])
-for k,v in d['configs'].items(): print(k, {a:b for a,b in v.items() if a in ('ms_per_step','pairs_per_s','error','skipped')})
-P
+tail -3 gpurun_out/sharded_abi_n8_dyn3.err

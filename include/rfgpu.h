@@ -250,6 +250,14 @@ rf_status rf_cdist_topk_u8_device(const uint8_t* q_chars, const uint64_t* q_offs
                                   const rf_corpus* c, const rf_args* args, uint32_t k, uint32_t* idx_device,
                                   uint32_t* dist_device, void* stream);
 
+/* the same for the other bit-parallel distances: metric = RF_LEVENSHTEIN | RF_OSA | RF_INDEL | RF_LCS_SEQ (the k smallest
+ * DISTANCES of that metric, ties by index; every one of them is bounded below by the length difference, so the length
+ * skip of the scan stays exact) */
+rf_status rf_cdist_topk_metric_u8(rf_metric metric, const uint8_t* q_chars, const uint64_t* q_offsets, uint32_t nq, const rf_corpus* c,
+                                  const rf_args* args, uint32_t k, uint32_t* idx_host, uint32_t* dist_host);
+rf_status rf_cdist_topk_metric_u8_device(rf_metric metric, const uint8_t* q_chars, const uint64_t* q_offsets, uint32_t nq,
+                                         const rf_corpus* c, const rf_args* args, uint32_t k, uint32_t* idx_device,
+                                         uint32_t* dist_device, void* stream);
 /* u32-element queries against a corpus made by rf_corpus_create_u32 that was renamed to bytes at creation (at most 255
  * distinct symbols; a larger alphabet -> RF_ERR_UNSUPPORTED), or against a u8 corpus when every query symbol is a byte */
 rf_status rf_cdist_topk_u32(const uint32_t* q_elems, const uint64_t* q_offsets, uint32_t nq, const rf_corpus* c,

@@ -1837,8 +1837,11 @@ extern "C" {
 // ------------------------------------------------------------------------------------------------ cdist
 static rf_status cdist_impl(const uint8_t* q_chars, const uint64_t* q_offsets, uint32_t nq, const rf_corpus* c,
                             const rf_args* args, uint32_t k, uint32_t* idx_out, uint32_t* dist_out, bool out_on_device,
-                            cudaStream_t user_stream, bool queries_in_corpus_codes = false) {
+                            cudaStream_t user_stream, bool queries_in_corpus_codes = false, rf_metric metric = RF_LEVENSHTEIN) {
   if (!c) return fail(RF_ERR_INVALID_ARG, "NULL corpus");
+  if (metric != RF_LEVENSHTEIN && metric != RF_OSA && metric != RF_INDEL && metric != RF_LCS_SEQ)
+    return fail(RF_ERR_UNSUPPORTED, "many-vs-many top-k supports the Levenshtein, OSA, Indel and LCSseq distances");
+  const bool bottom = metric == RF_INDEL || metric == RF_LCS_SEQ;  // LCS family: bottom-aligned match tables
   if (c->d_elems32 || (c->compact32 && !queries_in_corpus_codes))
     return fail(RF_ERR_UNSUPPORTED, "rf_cdist_topk_u8 needs a u8 corpus (this one was made by rf_corpus_create_u32; use rf_cdist_topk_u32)");
   if (nq == 0) return RF_OK;
@@ -1849,7 +1852,7 @@ static rf_status cdist_impl(const uint8_t* q_chars, const uint64_t* q_offsets, u
   rf_args def;
   rf_args_default(&def);
   const rf_args* a = args ? args : &def;
-  if (a->insertion_cost != 1 || a->deletion_cost != 1 || a->substitution_cost != 1)
+  if (metric == RF_LEVENSHTEIN && (a->insertion_cost != 1 || a->deletion_cost != 1 || a->substitution_cost != 1))
     return fail(RF_ERR_UNSUPPORTED, "cdist top-k supports unit Levenshtein weights only");
   uint32_t max_len = 0;
   for (uint32_t q = 0; q < nq; ++q) {
@@ -1896,10 +1899,10 @@ static rf_status cdist_impl(const uint8_t* q_chars, const uint64_t* q_offsets, u
       qlen[q] = l;
       if (wide) {
         uint64_t* t = (uint64_t*)tabs.data() + (size_t)q * 256;
-        for (uint32_t i = 0; i < l; ++i) t[s1[i]] |= 1ull << (i + 64 - l);
+        for (uint32_t i = 0; i < l; ++i) t[s1[i]] |= 1ull << (bottom ? i : i + 64 - l);
       } else {
         uint32_t* t = (uint32_t*)tabs.data() + (size_t)q * 256;
-        for (uint32_t i = 0; i < l; ++i) t[s1[i]] |= 1u << (i + 32 - l);
+        for (uint32_t i = 0; i < l; ++i) t[s1[i]] |= 1u << (bottom ? i : i + 32 - l);
       }
     }
     const int sms = sm_count_of(c->device);
@@ -1933,6 +1936,7 @@ static rf_status cdist_impl(const uint8_t* q_chars, const uint64_t* q_offsets, u
       L.nslices = nslices;
       L.grid = cdist_grid(sms);
       L.skip = g_cdist_skip.load();
+      L.metric = (int)metric;
       L.stream = st;
       if ((e = launch_cdist_topk(L)) != cudaSuccess) break;
       if (!out_on_device) {
@@ -1961,6 +1965,17 @@ rf_status rf_cdist_topk_u8_device(const uint8_t* q_chars, const uint64_t* q_offs
 rf_status rf_cdist_topk_u8(const uint8_t* q_chars, const uint64_t* q_offsets, uint32_t nq, const rf_corpus* c,
                            const rf_args* args, uint32_t k, uint32_t* idx_host, uint32_t* dist_host) {
   return cdist_impl(q_chars, q_offsets, nq, c, args, k, idx_host, dist_host, false, nullptr);
+}
+
+// the same many-vs-many top-k for the other bit-parallel distances: RF_LEVENSHTEIN, RF_OSA, RF_INDEL, RF_LCS_SEQ
+rf_status rf_cdist_topk_metric_u8(rf_metric metric, const uint8_t* q_chars, const uint64_t* q_offsets, uint32_t nq, const rf_corpus* c,
+                                  const rf_args* args, uint32_t k, uint32_t* idx_host, uint32_t* dist_host) {
+  return cdist_impl(q_chars, q_offsets, nq, c, args, k, idx_host, dist_host, false, nullptr, false, metric);
+}
+rf_status rf_cdist_topk_metric_u8_device(rf_metric metric, const uint8_t* q_chars, const uint64_t* q_offsets, uint32_t nq,
+                                         const rf_corpus* c, const rf_args* args, uint32_t k, uint32_t* idx_device,
+                                         uint32_t* dist_device, void* stream) {
+  return cdist_impl(q_chars, q_offsets, nq, c, args, k, idx_device, dist_device, true, (cudaStream_t)stream, false, metric);
 }
 
 // u32-element queries against a u32 corpus that was renamed to bytes at creation (at most 255 distinct symbols, see

@@ -1531,6 +1531,7 @@ struct CdistParams {
   uint32_t* out_dist;
   uint32_t two;
   int skip;                     // group skipping by length on (run-time switch for measurements)
+  int metric;                   // M_LEVENSHTEIN / M_OSA / M_INDEL / M_LCS_SEQ
 };
 
 // CTA-wide extraction of the k smallest keys of keys[0..m) (destroys them), ascending, into best[0..k)
@@ -1618,7 +1619,9 @@ struct WarpTopK {
   }
 };
 
-template <class W, int KR>
+// FAM: F_LEV (Levenshtein), F_OSA, F_LCS (Indel: len1 + len2 - 2 lcs; LCSseq distance: max(len1, len2) - lcs; p.metric tells
+// which).  All four are bounded below by |len1 - len2|, so the length skip stays exact.
+template <class W, int KR, int FAM = F_LEV>
 __global__ void __launch_bounds__(CD_NT) cdist_scan_kernel(const __grid_constant__ CdistParams p) {
   constexpr int NW = CD_NT / 32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1717,9 +1720,21 @@ __global__ void __launch_bounds__(CD_NT) cdist_scan_kernel(const __grid_constant
       const bool live = idx != 0xFFFFFFFFu && ldiff <= bd;
       if (p.skip && !__any_sync(0xffffffffu, live)) continue;
       uint32_t d;
-      if (len1 == 0) d = len2;
-      else if constexpr (sizeof(W) == 4) d = lev_w1_u32_fast(smem_u32(pm_lane), src.reader(), len2, len1, p.two);
-      else d = lev_w1_u64_fast(smem_u32(reinterpret_cast<const uint32_t*>(smem_raw) + lane), src.reader(), len2, len1, p.two);
+      const uint32_t saddr = sizeof(W) == 4 ? smem_u32(pm_lane) : smem_u32(reinterpret_cast<const uint32_t*>(smem_raw) + lane);
+      if constexpr (FAM == F_LCS) {
+        uint32_t lcs = 0;
+        if (len1 != 0) {
+          if constexpr (sizeof(W) == 4) lcs = lcs_w1_u32_fast(saddr, src.reader(), len2, p.two);
+          else lcs = lcs_w1_u64_fast(saddr, src.reader(), len2, p.two);
+        }
+        d = p.metric == M_INDEL ? len1 + len2 - 2u * lcs : (len1 > len2 ? len1 : len2) - lcs;
+      } else if (len1 == 0) {
+        d = len2;
+      } else if constexpr (sizeof(W) == 4) {
+        d = myers_w1_u32_fast<FAM == F_OSA>(saddr, src.reader(), len2, len1, p.two);
+      } else {
+        d = myers_w1_u64_fast<FAM == F_OSA>(saddr, src.reader(), len2, len1, p.two);
+      }
       const bool ok = idx != 0xFFFFFFFFu && d <= static_bound;
       top.offer(ok ? (((unsigned long long)d << 32) | idx) : CD_NOKEY, bound, k, lane, &s_kth);
     }
@@ -1798,6 +1813,7 @@ cudaError_t launch_cdist_topk(const CdistLaunch& L) {
   p.out_dist = L.out_dist;
   p.two = 2;
   p.skip = L.skip;
+  p.metric = L.metric;
   const size_t wsz = L.wide ? 8 : 4;
   const size_t smem = wsz * 8192 + sizeof(unsigned long long) * ((CD_NT / 32) * CD_KMAX + CD_KMAX + CD_NT / 32);
   cudaError_t e = cudaMemsetAsync(L.counter, 0, sizeof(unsigned long long), L.stream);
@@ -1811,8 +1827,17 @@ cudaError_t launch_cdist_topk(const CdistLaunch& L) {
     return cudaGetLastError();
   };
   const int kr = L.k <= 32 ? 1 : (L.k <= 64 ? 2 : 4);
-  if (L.wide) e = kr == 1 ? launch(cdist_scan_kernel<uint64_t, 1>) : kr == 2 ? launch(cdist_scan_kernel<uint64_t, 2>) : launch(cdist_scan_kernel<uint64_t, 4>);
-  else e = kr == 1 ? launch(cdist_scan_kernel<uint32_t, 1>) : kr == 2 ? launch(cdist_scan_kernel<uint32_t, 2>) : launch(cdist_scan_kernel<uint32_t, 4>);
+  auto pick = [&](auto fam_tag) -> cudaError_t {
+    constexpr int FAM = decltype(fam_tag)::value;
+    if (L.wide) return kr == 1 ? launch(cdist_scan_kernel<uint64_t, 1, FAM>) : kr == 2 ? launch(cdist_scan_kernel<uint64_t, 2, FAM>) : launch(cdist_scan_kernel<uint64_t, 4, FAM>);
+    return kr == 1 ? launch(cdist_scan_kernel<uint32_t, 1, FAM>) : kr == 2 ? launch(cdist_scan_kernel<uint32_t, 2, FAM>) : launch(cdist_scan_kernel<uint32_t, 4, FAM>);
+  };
+  switch (L.metric) {
+    case M_LEVENSHTEIN: e = pick(std::integral_constant<int, F_LEV>{}); break;
+    case M_OSA: e = pick(std::integral_constant<int, F_OSA>{}); break;
+    case M_INDEL: case M_LCS_SEQ: e = pick(std::integral_constant<int, F_LCS>{}); break;
+    default: return cudaErrorInvalidValue;
+  }
   if (e != cudaSuccess) return e;
   g_launches.fetch_add(1);
   if (L.nslices == 1) return cudaSuccess;

@@ -122,6 +122,7 @@ struct CdistLaunch {
   uint32_t nslices;         // corpus slices (cdist_slices); work units = nslices * nq
   uint32_t grid;            // persistent CTAs (cdist_grid)
   int skip;                 // 1: skip groups that cannot reach the current k-th distance by length alone
+  int metric;               // M_LEVENSHTEIN (default 0) / M_OSA / M_INDEL / M_LCS_SEQ; tables bottom-aligned for the last two
   cudaStream_t stream;
 };
 cudaError_t launch_cdist_topk(const CdistLaunch& L);

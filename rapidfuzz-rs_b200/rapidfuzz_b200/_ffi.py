@@ -82,6 +82,8 @@ SYMBOLS = {
     "rf_batch_stream_u8_len8_packed6": (_int, [_vp, _vp, _vp, _vp, _u64, _int, _PA, _vp]),
     "rf_cdist_topk_u8": (_int, [_vp, _vp, _u32, _vp, _PA, _u32, _vp, _vp]),
     "rf_cdist_topk_u8_device": (_int, [_vp, _vp, _u32, _vp, _PA, _u32, _vp, _vp, _vp]),
+    "rf_cdist_topk_metric_u8": (_int, [_int, _vp, _vp, _u32, _vp, _PA, _u32, _vp, _vp]),
+    "rf_cdist_topk_metric_u8_device": (_int, [_int, _vp, _vp, _u32, _vp, _PA, _u32, _vp, _vp, _vp]),
     "rf_cdist_topk_u32": (_int, [_vp, _vp, _u32, _vp, _PA, _u32, _vp, _vp]),
     "rf_cdist_topk_u32_device": (_int, [_vp, _vp, _u32, _vp, _PA, _u32, _vp, _vp, _vp]),
     "rf_topk_merge_device": (_int, [_vp, _vp, _u64, _vp, _u32, _u32, _u32, _vp, _vp, _int, _vp]),

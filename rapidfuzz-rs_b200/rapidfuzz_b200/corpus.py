@@ -212,8 +212,9 @@ def cdist_topk_u32(q_elems, q_offsets, corpus, k=10, score_cutoff=None):
     return idx, dist
 
 
-def cdist_topk(queries, corpus, k=10, score_cutoff=None):
-    """Many-vs-many Levenshtein: for every query the k best candidates of `corpus` by (distance, index).
+def cdist_topk(queries, corpus, k=10, score_cutoff=None, metric="levenshtein"):
+    """Many-vs-many: for every query the k best candidates of `corpus` by (distance, index); metric = levenshtein (default),
+    osa, indel or lcs_seq (rf_cdist_topk_metric_u8).
     New on this side (the reference has no cdist).  queries: list of bytes/str, or (chars u8, offsets u64).
     Returns (idx [nq,k] uint32, dist [nq,k] uint32); rows with fewer than k hits are padded with 0xFFFFFFFF."""
     import ctypes as C
@@ -234,6 +235,10 @@ def cdist_topk(queries, corpus, k=10, score_cutoff=None):
         a.cutoff_u = int(score_cutoff)
     idx = np.empty((nq, k), dtype=np.uint32)
     dist = np.empty((nq, k), dtype=np.uint32)
-    _ffi.check(_ffi.lib().rf_cdist_topk_u8(q_chars.ctypes.data, q_off.ctypes.data, nq, corpus._h, C.byref(a), k,
-                                          idx.ctypes.data, dist.ctypes.data))
+    if metric == "levenshtein":
+        _ffi.check(_ffi.lib().rf_cdist_topk_u8(q_chars.ctypes.data, q_off.ctypes.data, nq, corpus._h, C.byref(a), k,
+                                              idx.ctypes.data, dist.ctypes.data))
+    else:
+        _ffi.check(_ffi.lib().rf_cdist_topk_metric_u8(_ffi.METRICS[metric], q_chars.ctypes.data, q_off.ctypes.data, nq, corpus._h,
+                                                     C.byref(a), k, idx.ctypes.data, dist.ctypes.data))
     return idx, dist

@@ -25,6 +25,20 @@ static std::atomic<uint64_t> g_launches{0};
 uint64_t kernel_launch_count() { return g_launches.load(); }
 void count_launches(uint64_t n) { g_launches.fetch_add(n); }
 
+// Grid of a statically partitioned (grid-stride) kernel: exactly the CTAs that are resident at once.  A fixed "8 CTAs of
+// 256 threads per SM" over-subscribes every kernel that needs more than 32 registers (40 registers -> 6 resident CTAs):
+// the CTAs of the second wave start when the first wave retires and run their equal share of the work at a third of the
+// occupancy, i.e. the kernel takes ~1.5x as long as the same work spread over one wave.
+template <class K>
+static uint64_t resident_ctas(K kern, int threads, size_t smem, int sm_count, int fallback_per_sm) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1) {
+    (void)cudaGetLastError();
+    per_sm = fallback_per_sm;
+  }
+  return (uint64_t)sm_count * (uint64_t)per_sm;
+}
+
 // ------------------------------------------------------------------------------------------------ PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -1207,6 +1221,304 @@ static cudaError_t launch_jaro32(const ScanLaunch& L) {
   return cudaGetLastError();
 }
 
+template <int LUT>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+  return d;
+}
+// x * 2 as {low word, bit that falls out}: IMAD.WIDE.U32 (`two` is opaque to ptxas, so it stays on the FMA pipe)
+__device__ __forceinline__ void mul2_wide(uint32_t x, uint32_t two, uint32_t& lo, uint32_t& hi) {
+  asm("{\n\t.reg .b64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo), "=r"(hi) : "r"(x), "r"(two));
+}
+
+// ------------------------------------------------------------------------------------------------ jaro64
+// The same row-wise scheme for queries of 33..64 elements (they used to take the per-lane generic routine: 8.5 ms per
+// 10^8 candidates against 3.43 ms for queries up to 32): pattern flags, window mask and transposition marks are 64-bit,
+// held as 32-bit halves with the carries on IADD3.X / IMAD.WIDE like the 64-bit Levenshtein recurrence; the match table is
+// split into a low-word and a high-word copy 32 KB apart (one IDP.4A address, two LDS).  Candidates (truncated) beyond 64
+// characters go to jaro64_long_kernel as before.
+struct Jaro64Dev {
+  uint32_t Pl, Ph, wl, wh, Ml, Mh;
+  uint64_t T;
+  template <int K>
+  __device__ __forceinline__ void look(uint32_t w, uint32_t pm_lane_saddr, uint32_t& Xl, uint32_t& Xh) const {
+    const uint32_t addr = __dp4a(w, 0x80u << (8 * K), pm_lane_saddr);
+    asm("ld.shared.u32 %0, [%1];" : "=r"(Xl) : "r"(addr));
+    asm("ld.shared.u32 %0, [%1+32768];" : "=r"(Xh) : "r"(addr));
+  }
+  template <int LO, bool LENP, int K>
+  __device__ __forceinline__ void flag_step(uint32_t w, uint32_t j, uint32_t len2, uint32_t rb, uint32_t pm_lane_saddr,
+                                            uint32_t two, uint32_t& t8) {
+    uint32_t Xl, Xh;
+    look<(K & 3)>(w, pm_lane_saddr, Xl, Xh);
+    uint32_t ml = lop3<0x40>(Xl, wl, Pl), mh = lop3<0x40>(Xh, wh, Ph);  // X & win & ~P
+    if (LENP) { ml = (j < len2) ? ml : 0u; mh = (j < len2) ? mh : 0u; }
+    // lowest set bit of the 64-bit m: the low word's if it has one, else the high word's.  hmask = all ones iff ml == 0
+    // (0xFFFFFFFF + carry of ml + 0xFFFFFFFF)
+    uint32_t hmask;
+    asm("{\n\t.reg .u32 d;\n\tadd.cc.u32 d, %1, 0xFFFFFFFF;\n\taddc.u32 %0, 0xFFFFFFFF, 0;\n\t}" : "=r"(hmask) : "r"(ml));
+    Pl |= ml & (0u - ml);
+    Ph |= mh & (0u - mh) & hmask;
+    const uint32_t any = ml | mh;
+    asm("{\n\t.reg .u32 d;\n\tadd.cc.u32 d, %1, 0xFFFFFFFF;\n\tmadc.lo.u32 %0, %0, %2, 0;\n\t}" : "+r"(t8) : "r"(any), "r"(two));
+    // window: win' = 2 * win + (j < bound) on 64 bits
+    uint32_t lo2, c;
+    mul2_wide(wl, two, lo2, c);
+    wh = wh * two + c;
+    if (LO == 0) wl = lo2 + (two >> 1);
+    if (LO == 1) wl = lo2;
+    if (LO == 2) {  // carry of rb + (2^32 - 1 - K) is set iff K < rb
+      uint32_t inc;
+      asm("{\n\t.reg .u32 d;\n\tadd.cc.u32 d, %1, %2;\n\taddc.u32 %0, 0, 0;\n\t}" : "=r"(inc) : "r"(rb), "n"(0xFFFFFFFFu - (uint32_t)K));
+      wl = lo2 + inc;
+    }
+  }
+  template <int LO, bool LENP>
+  __device__ __forceinline__ void flag_row(uint2 v, uint32_t r, uint32_t len2, uint32_t bound, uint32_t pm_lane_saddr, uint32_t two) {
+    uint32_t t8 = 0;
+    const uint32_t j0 = r * 8u;
+    const uint32_t rb = bound > j0 ? bound - j0 : 0u;
+    flag_step<LO, LENP, 0>(v.x, j0 + 0, len2, rb, pm_lane_saddr, two, t8);
+    flag_step<LO, LENP, 1>(v.x, j0 + 1, len2, rb, pm_lane_saddr, two, t8);
+    flag_step<LO, LENP, 2>(v.x, j0 + 2, len2, rb, pm_lane_saddr, two, t8);
+    flag_step<LO, LENP, 3>(v.x, j0 + 3, len2, rb, pm_lane_saddr, two, t8);
+    flag_step<LO, LENP, 4>(v.y, j0 + 4, len2, rb, pm_lane_saddr, two, t8);
+    flag_step<LO, LENP, 5>(v.y, j0 + 5, len2, rb, pm_lane_saddr, two, t8);
+    flag_step<LO, LENP, 6>(v.y, j0 + 6, len2, rb, pm_lane_saddr, two, t8);
+    flag_step<LO, LENP, 7>(v.y, j0 + 7, len2, rb, pm_lane_saddr, two, t8);
+    T = (T << 8) | t8;
+  }
+  __device__ __forceinline__ void align_T(uint32_t nrows) { T = nrows ? T << (8u * (8u - nrows)) : 0ull; }
+  // x = P - flagged on 64 bits: the add.cc shifts the (inverted) text flag into the carry, the two addc's compute
+  // P + (2^64 - 1) + !flagged; P & ~x is the lowest remaining pattern flag (or 0), P &= x retires it
+  template <int K>
+  __device__ __forceinline__ void trans_step(uint32_t w, uint32_t& tt, uint32_t pm_lane_saddr) {
+    uint32_t Xl, Xh, xl, xh;
+    look<K>(w, pm_lane_saddr, Xl, Xh);
+    asm("{\n\tadd.cc.u32 %2, %2, %2;\n\taddc.cc.u32 %0, %3, 0xFFFFFFFF;\n\taddc.u32 %1, %4, 0xFFFFFFFF;\n\t}"
+        : "=r"(xl), "=r"(xh), "+r"(tt) : "r"(Pl), "r"(Ph));
+    Ml |= lop3<0x02>(xl, Xl, Pl);  // ~x & ~X & P
+    Mh |= lop3<0x02>(xh, Xh, Ph);
+    Pl &= xl;
+    Ph &= xh;
+  }
+  __device__ __forceinline__ void trans_row(uint2 v, uint32_t pm_lane_saddr) {
+    uint32_t tt = ~(uint32_t)(T >> 32) & 0xFF000000u;
+    T <<= 8;
+    trans_step<0>(v.x, tt, pm_lane_saddr);
+    trans_step<1>(v.x, tt, pm_lane_saddr);
+    trans_step<2>(v.x, tt, pm_lane_saddr);
+    trans_step<3>(v.x, tt, pm_lane_saddr);
+    trans_step<0>(v.y, tt, pm_lane_saddr);
+    trans_step<1>(v.y, tt, pm_lane_saddr);
+    trans_step<2>(v.y, tt, pm_lane_saddr);
+    trans_step<3>(v.y, tt, pm_lane_saddr);
+  }
+};
+
+__device__ __noinline__ double jaro64_long_fallback(const uint32_t* __restrict__ pm32_lane, const uint2* __restrict__ col,
+                                                    uint32_t len1, uint32_t len2, const Epi& epi) {
+  const LaneSrcT<false> src{col, __ldg(col), __ldg(col + 32)};
+  auto tab64 = [&](uint32_t ch) -> uint64_t { return (uint64_t)pm32_lane[ch * 32u] | ((uint64_t)pm32_lane[8192u + ch * 32u] << 32); };
+  auto bytes = [&](uint32_t j) -> uint32_t { return src.byte(j); };
+  auto jaro = [&](double c) { return jaro_similarity_w1(tab64, bytes, len1, len2, c); };
+  if (epi.metric == M_JARO) return finish_float(epi, jaro);
+  uint32_t prefix = 0;
+  while (prefix < 4 && prefix < len1 && prefix < len2 && ((tab64(bytes(prefix)) >> prefix) & 1u)) ++prefix;
+  const double pw = epi.prefix_weight;
+  auto jw = [&](double c) { return jaro_winkler_from(jaro, prefix, pw, c); };
+  return finish_float(epi, jw);
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) scan_jaro64_kernel(const __grid_constant__ LbParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint32_t* pm32 = reinterpret_cast<uint32_t*>(smem_raw);
+  {
+    const uint64_t* __restrict__ t = reinterpret_cast<const uint64_t*>(p.tab);
+    for (uint32_t i = threadIdx.x; i < 256u * 32u; i += NT) {
+      const uint64_t v = t[i >> 5];
+      pm32[i] = (uint32_t)v;
+      pm32[i + 8192u] = (uint32_t)(v >> 32);
+    }
+  }
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t* __restrict__ pm_lane = pm32 + lane;
+  const bool zero_ok = pm32[0] == 0u && pm32[8192] == 0u;  // PM[0]: no query element is the zero byte
+  const uint64_t total_warps = (uint64_t)gridDim.x * (NT / 32);
+  const uint64_t ngroups = p.lb.ngroups;
+  const uint64_t nchunks = (ngroups + p.chunk - 1) / p.chunk;
+  const uint2* __restrict__ gdata = reinterpret_cast<const uint2*>(p.lb.gdata);
+  auto tab_lo = [&](uint32_t ch) -> uint32_t { return pm_lane[ch * 32u]; };
+  uint64_t chunk = (uint64_t)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
+  while (chunk < nchunks) {
+    unsigned long long next_chunk = 0;
+    if (lane == 0) next_chunk = total_warps + atomicAdd(p.counter, 1ull);
+    const uint64_t g0 = chunk * p.chunk;
+    const uint64_t g1 = (g0 + p.chunk < ngroups) ? g0 + p.chunk : ngroups;
+    uint64_t r = __ldg(p.lb.goff + g0);
+    uint32_t len_n = __ldg(p.lb.lens + g0 * 32 + lane);
+    uint32_t idx_n = __ldg(p.lb.perm + g0 * 32 + lane);
+    uint2 first_n = __ldg(gdata + r * 32 + lane);
+    for (uint64_t g = g0; g < g1; ++g) {
+      const uint32_t len2 = len_n, idx = idx_n;
+      const uint2 first = first_n;
+      const uint2* col = gdata + r * 32 + lane;
+      r += (__reduce_max_sync(0xffffffffu, len2) + 7u) >> 3;
+      if (g + 1 < g1) {
+        len_n = __ldg(p.lb.lens + (g + 1) * 32 + lane);
+        idx_n = __ldg(p.lb.perm + (g + 1) * 32 + lane);
+        const uint2* ncol = gdata + r * 32 + lane;
+        first_n = __ldg(ncol);
+#pragma unroll
+        for (int k = 1; k < 8; ++k) prefetch_l2(ncol + k * 32);
+      }
+      uint32_t l1e = p.len1, l2e = len2, bound = 0;
+      jaro_bounds(l1e, l2e, bound);
+      const uint32_t l2max = __reduce_max_sync(0xffffffffu, l2e);
+      double res;
+      if (l2max <= 64) {
+        const uint32_t pm_lane_saddr = smem_u32(pm_lane);
+        const uint32_t nrows = (l2max + 7u) >> 3;
+        const uint32_t l2min = __reduce_min_sync(0xffffffffu, l2e);
+        const uint32_t bcl = bound < 64u ? bound : 64u;
+        const uint32_t bmin = __reduce_min_sync(0xffffffffu, bcl), bmax = __reduce_max_sync(0xffffffffu, bcl);
+        Jaro64Dev J;
+        J.Pl = J.Ph = J.Ml = J.Mh = 0;
+        J.T = 0;
+        {  // bits 0 .. bound of the window (a wrapped radius -- 1 x 1 / empty / padding lanes -- opens everything)
+          const uint64_t w0 = (bound + 1 < 64) ? ((1ull << (bound + 1)) - 1ull) : ~0ull;
+          J.wl = (uint32_t)w0;
+          J.wh = (uint32_t)(w0 >> 32);
+        }
+        const uint32_t rF = zero_ok ? nrows : (l2min >> 3);
+        const uint32_t rA = (bmin < l2min ? bmin : l2min) >> 3;
+        uint32_t rB = (bmax + 7u) >> 3;
+        rB = rB < rF ? rB : rF;
+        rB = rB > rA ? rB : rA;
+        uint2 v = first;
+        uint32_t rr = 0;
+#define RF_JROW64(LO, LENP)                                                 \
+  {                                                                         \
+    const uint2 cur = v;                                                    \
+    if (rr + 1 < nrows) v = __ldg(col + (rr + 1) * 32u);                    \
+    J.flag_row<LO, LENP>(cur, rr, l2e, bound, pm_lane_saddr, p.two);        \
+  }
+        for (; rr < rA; ++rr) RF_JROW64(0, false)
+        for (; rr < rB; ++rr) RF_JROW64(2, false)
+        for (; rr < rF; ++rr) RF_JROW64(1, false)
+        for (; rr < nrows; ++rr) RF_JROW64(2, true)
+#undef RF_JROW64
+        J.align_T(nrows);
+        Jaro32Result jr;
+        jr.cc = (uint32_t)__popc(J.Pl) + (uint32_t)__popc(J.Ph);
+        v = first;
+        for (rr = 0; rr < nrows; ++rr) {
+          const uint2 cur = v;
+          if (rr + 1 < nrows) v = __ldg(col + (rr + 1) * 32u);
+          J.trans_row(cur, pm_lane_saddr);
+        }
+        jr.transpositions = (uint32_t)__popc(J.Ml) + (uint32_t)__popc(J.Mh);
+        const uint32_t w0 = len2 ? first.x : 0u;
+        const bool fm = len2 && (tab_lo(w0 & 0xffu) & 1u);
+        const uint32_t len1 = p.len1;
+        const double* quot = p.quot;
+        auto jaro = [&](double c) { return jaro32_finish(len1, len2, jr, fm, c, quot); };
+        if (p.epi.metric == M_JARO) {
+          res = finish_float(p.epi, jaro);
+        } else {
+          uint32_t prefix = 0;
+          const uint32_t lim = len1 < len2 ? (len1 < 4 ? len1 : 4) : (len2 < 4 ? len2 : 4);
+          while (prefix < lim && ((tab_lo((w0 >> (8 * prefix)) & 0xffu) >> prefix) & 1u)) ++prefix;
+          const double pw = p.epi.prefix_weight;
+          auto jw = [&](double c) { return jaro_winkler_from(jaro, prefix, pw, c); };
+          res = finish_float(p.epi, jw);
+        }
+      } else {
+        if (lane == 0) *p.flag = 1ull;
+        continue;
+      }
+      if (idx != 0xFFFFFFFFu) reinterpret_cast<double*>(p.out)[idx] = res;
+    }
+    chunk = __shfl_sync(0xffffffffu, next_chunk, 0);
+  }
+}
+
+__global__ void __launch_bounds__(256) jaro64_long_kernel(const __grid_constant__ LbParams p) {
+  if (*reinterpret_cast<const volatile unsigned long long*>(p.flag) == 0ull) return;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint32_t* pm32 = reinterpret_cast<uint32_t*>(smem_raw);
+  {
+    const uint64_t* __restrict__ t = reinterpret_cast<const uint64_t*>(p.tab);
+    for (uint32_t i = threadIdx.x; i < 256u * 32u; i += 256) {
+      const uint64_t v = t[i >> 5];
+      pm32[i] = (uint32_t)v;
+      pm32[i + 8192u] = (uint32_t)(v >> 32);
+    }
+  }
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint2* __restrict__ gdata = reinterpret_cast<const uint2*>(p.lb.gdata);
+  const uint64_t nwarps = (uint64_t)gridDim.x * 8, w0 = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  for (uint64_t g = w0; g < p.lb.ngroups; g += nwarps) {
+    const uint32_t len2 = __ldg(p.lb.lens + g * 32 + lane);
+    const uint32_t idx = __ldg(p.lb.perm + g * 32 + lane);
+    uint32_t l1e = p.len1, l2e = len2, bound = 0;
+    jaro_bounds(l1e, l2e, bound);
+    if (__reduce_max_sync(0xffffffffu, l2e) <= 64) continue;  // scored by the fast kernel
+    const uint2* col = gdata + __ldg(p.lb.goff + g) * 32 + lane;
+    const double res = jaro64_long_fallback(pm32 + lane, col, p.len1, len2, p.epi);
+    if (idx != 0xFFFFFFFFu) reinterpret_cast<double*>(p.out)[idx] = res;
+  }
+}
+
+static cudaError_t launch_jaro64(const ScanLaunch& L) {
+  constexpr int NT = 256;
+  auto kern = scan_jaro64_kernel<NT>;
+  const size_t smem = sizeof(uint64_t) * 256 * 32;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
+  int ctas_per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, NT, smem);
+  if (e != cudaSuccess) return e;
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  LbParams p{};
+  p.lb = L.lb;
+  p.tab = L.query.tab64_bot;
+  p.quot = L.query.quot;
+  p.len1 = L.query.len1;
+  p.out = L.out;
+  p.out_f64 = 1;
+  p.two = 2;
+  p.chunk = 16;
+  p.counter = L.lb_counter;
+  p.flag = L.lb_flag;
+  p.epi = L.epi;
+  e = cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), L.stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(p.flag, 0, sizeof(unsigned long long), L.stream);
+  if (e != cudaSuccess) return e;
+  uint64_t grid = (uint64_t)L.sm_count * ctas_per_sm;
+  const uint64_t nchunks = (L.lb.ngroups + p.chunk - 1) / p.chunk;
+  const uint64_t need = (nchunks + NT / 32 - 1) / (NT / 32);
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  kern<<<(uint32_t)grid, NT, smem, L.stream>>>(p);
+  g_launches.fetch_add(1);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(jaro64_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  uint64_t lgrid = (uint64_t)L.sm_count * 2;
+  const uint64_t lneed = (L.lb.ngroups + 7) / 8;
+  if (lgrid > lneed) lgrid = lneed;
+  jaro64_long_kernel<<<(uint32_t)lgrid, 256, smem, L.stream>>>(p);
+  g_launches.fetch_add(1);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_scan_lb(const ScanLaunch& L) {
   const Family fam = family_of(L.epi.metric, L.epi.wclass);
   const bool w32 = L.query.len1 <= 32;
@@ -1230,6 +1542,7 @@ cudaError_t launch_scan_lb(const ScanLaunch& L) {
                  : launch_lb_inst<F_LCS, uint64_t, 512>(L, L.query.tab64_bot);
     default:
       if (L.query.len1 >= 1 && L.query.len1 <= 32 && L.jaro32) return launch_jaro32(L);
+      if (L.query.len1 > 32 && L.query.len1 <= 64 && L.jaro32) return launch_jaro64(L);
       return launch_lb_inst<F_JARO, uint64_t, 512>(L, L.query.tab64_bot);
   }
 }
@@ -2083,24 +2396,26 @@ static cudaError_t launch_mw_fam(const ScanLaunch& L) {
   const uint32_t warps_per_block = 8;
   const uint64_t warps_needed = (p.n + 31) / 32;
   uint64_t blocks = (warps_needed + warps_per_block - 1) / warps_per_block;
-  const uint64_t max_blocks = (uint64_t)L.sm_count * 8;  // 8 x 256 threads = 2048 threads / SM
-  if (blocks > max_blocks) blocks = max_blocks;
-  if (blocks < 1) blocks = 1;
+  void (*kern)(MwParams);
   if (L.elem16) {
     switch (wpl) {
-      case 1: scan_mw_kernel<FAM, 1, uint16_t><<<(uint32_t)blocks, 256, 0, L.stream>>>(p); break;
-      case 2: scan_mw_kernel<FAM, 2, uint16_t><<<(uint32_t)blocks, 256, 0, L.stream>>>(p); break;
-      case 4: scan_mw_kernel<FAM, 4, uint16_t><<<(uint32_t)blocks, 256, 0, L.stream>>>(p); break;
-      default: scan_mw_kernel<FAM, 8, uint16_t><<<(uint32_t)blocks, 256, 0, L.stream>>>(p); break;
+      case 1: kern = scan_mw_kernel<FAM, 1, uint16_t>; break;
+      case 2: kern = scan_mw_kernel<FAM, 2, uint16_t>; break;
+      case 4: kern = scan_mw_kernel<FAM, 4, uint16_t>; break;
+      default: kern = scan_mw_kernel<FAM, 8, uint16_t>; break;
     }
   } else {
     switch (wpl) {
-      case 1: scan_mw_kernel<FAM, 1><<<(uint32_t)blocks, 256, 0, L.stream>>>(p); break;
-      case 2: scan_mw_kernel<FAM, 2><<<(uint32_t)blocks, 256, 0, L.stream>>>(p); break;
-      case 4: scan_mw_kernel<FAM, 4><<<(uint32_t)blocks, 256, 0, L.stream>>>(p); break;
-      default: scan_mw_kernel<FAM, 8><<<(uint32_t)blocks, 256, 0, L.stream>>>(p); break;
+      case 1: kern = scan_mw_kernel<FAM, 1>; break;
+      case 2: kern = scan_mw_kernel<FAM, 2>; break;
+      case 4: kern = scan_mw_kernel<FAM, 4>; break;
+      default: kern = scan_mw_kernel<FAM, 8>; break;
     }
   }
+  const uint64_t max_blocks = resident_ctas(kern, 256, 0, L.sm_count, 2);  // one wave (48 ... 128 registers per thread)
+  if (blocks > max_blocks) blocks = max_blocks;
+  if (blocks < 1) blocks = 1;
+  kern<<<(uint32_t)blocks, 256, 0, L.stream>>>(p);
   g_launches.fetch_add(1);
   return cudaGetLastError();
 }
@@ -2257,17 +2572,6 @@ __device__ __forceinline__ void pmn_load(uint32_t addr, uint32_t (&X)[4 * Q]) {
   if constexpr (Q > 2) lds128_off<65536>(addr, X[8], X[9], X[10], X[11]);
   if constexpr (Q > 3) lds128_off<98304>(addr, X[12], X[13], X[14], X[15]);
 }
-template <int LUT>
-__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
-  uint32_t d;
-  asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT));
-  return d;
-}
-// x * 2 as {low word, bit that falls out}: IMAD.WIDE.U32 (`two` is opaque to ptxas, so it stays on the FMA pipe)
-__device__ __forceinline__ void mul2_wide(uint32_t x, uint32_t two, uint32_t& lo, uint32_t& hi) {
-  asm("{\n\t.reg .b64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo), "=r"(hi) : "r"(x), "r"(two));
-}
-
 template <int Q, bool OSA>
 struct LevNStep {
   static constexpr int L = 4 * Q;
@@ -2946,7 +3250,8 @@ cudaError_t launch_scan_band(const ScanLaunch& L, uint32_t cut) {
   }
   // columns of the first pass: random candidates leave the band after about k columns
   const uint32_t cols_a = (cut + cut / 4 + 8 + 15) / 16 * 16;
-  const uint32_t grid_max = (uint32_t)L.sm_count * 8;
+  const uint32_t grid_max = (uint32_t)resident_ctas(run_a, 256, smem, L.sm_count, 4);  // one wave (see resident_ctas)
+  const uint32_t grid_cl = (uint32_t)resident_ctas(band_classify_kernel, 256, 0, L.sm_count, 8);
   for (uint64_t i0 = 0; i0 < n && e == cudaSuccess; i0 += kBatch) {
     p.i0 = i0;
     p.i1 = (i0 + kBatch < n) ? i0 + kBatch : n;
@@ -2956,7 +3261,7 @@ cudaError_t launch_scan_band(const ScanLaunch& L, uint32_t cut) {
     const uint64_t cl_ctas = (nb + 256 * BAND_CL_ITEMS - 1) / (256 * BAND_CL_ITEMS);
     const uint32_t grid = (uint32_t)((nb + 255) / 256 < grid_max ? (nb + 255) / 256 : grid_max);
     p.list_out = listA; p.cnt_out = cnts;
-    band_classify_kernel<<<(uint32_t)(cl_ctas < grid_max ? cl_ctas : grid_max), 256, 0, L.stream>>>(p);
+    band_classify_kernel<<<(uint32_t)(cl_ctas < grid_cl ? cl_ctas : grid_cl), 256, 0, L.stream>>>(p);
     p.list_in = listA; p.cnt_in = cnts; p.list_out = listB; p.cnt_out = cnts + 1; p.maxcols = cols_a;
     run_a<<<grid, 256, smem, L.stream>>>(p);
     p.list_in = listB; p.cnt_in = cnts + 1; p.list_out = nullptr; p.cnt_out = nullptr; p.maxcols = 0xFFFFFFFFu;
@@ -3038,10 +3343,22 @@ __global__ void __launch_bounds__(256) hamming_lb_kernel(const __grid_constant__
   const uint2* __restrict__ gdata = reinterpret_cast<const uint2*>(p.lb.gdata);
   const uint64_t nwarps = (uint64_t)gridDim.x * 8, w0 = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   auto diff2 = [](uint2 a, uint2 b) -> uint32_t { return differing_bytes(a.x, b.x) + differing_bytes(a.y, b.y); };
+  // the next group's metadata is requested before the current group's rows: one DRAM latency per group instead of two
+  uint32_t len_n = 0, idx_n = 0xFFFFFFFFu;
+  uint64_t off_n = 0;
+  if (w0 < p.lb.ngroups) {
+    len_n = __ldg(p.lb.lens + w0 * 32 + lane);
+    idx_n = __ldg(p.lb.perm + w0 * 32 + lane);
+    off_n = __ldg(p.lb.goff + w0);
+  }
   for (uint64_t g = w0; g < p.lb.ngroups; g += nwarps) {
-    const uint32_t len2 = __ldg(p.lb.lens + g * 32 + lane);
-    const uint32_t idx = __ldg(p.lb.perm + g * 32 + lane);
-    const uint2* col = gdata + __ldg(p.lb.goff + g) * 32 + lane;
+    const uint32_t len2 = len_n, idx = idx_n;
+    const uint2* col = gdata + off_n * 32 + lane;
+    if (g + nwarps < p.lb.ngroups) {
+      len_n = __ldg(p.lb.lens + (g + nwarps) * 32 + lane);
+      idx_n = __ldg(p.lb.perm + (g + nwarps) * 32 + lane);
+      off_n = __ldg(p.lb.goff + g + nwarps);
+    }
     if (idx == 0xFFFFFFFFu) continue;
     const uint32_t mn = len1 < len2 ? len1 : len2, mx = len1 < len2 ? len2 : len1;
     bool none = false;
@@ -3083,7 +3400,7 @@ cudaError_t launch_simple(const ScanLaunch& L, uint32_t* err_flag) {
     q.lb = L.lb;
     const size_t smem = ((size_t)(q.len1 + 3) / 4 + 4) * 4 + 8;
     uint64_t blocks = (L.lb.ngroups + 7) / 8;
-    const uint64_t max_blocks = (uint64_t)L.sm_count * 8;
+    const uint64_t max_blocks = resident_ctas(hamming_lb_kernel, 256, smem, L.sm_count, 4);
     if (blocks > max_blocks) blocks = max_blocks;
     if (blocks < 1) blocks = 1;
     hamming_lb_kernel<<<(uint32_t)blocks, 256, smem, L.stream>>>(q);
@@ -3103,7 +3420,7 @@ cudaError_t launch_simple(const ScanLaunch& L, uint32_t* err_flag) {
   p.epi = L.epi;
   const size_t smem = ((size_t)(p.len1 + 3) / 4 + 4) * 4;
   uint64_t blocks = (p.n + 255) / 256;
-  const uint64_t max_blocks = (uint64_t)L.sm_count * 8;
+  const uint64_t max_blocks = resident_ctas(simple_kernel, 256, smem, L.sm_count, 4);
   if (blocks > max_blocks) blocks = max_blocks;
   if (blocks < 1) blocks = 1;
   simple_kernel<<<(uint32_t)blocks, 256, smem, L.stream>>>(p);

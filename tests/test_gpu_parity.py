@@ -307,18 +307,18 @@ def test_u32_elements_vs_oracle(qlen):
     c8.close()
 
 
-@pytest.mark.parametrize("qlen", [1, 2, 5, 31, 32])
+@pytest.mark.parametrize("qlen", [1, 2, 5, 31, 32, 33, 40, 63, 64])
 def test_jaro_rowwise_kernel_degenerate_lanes(qlen):
     """The row-wise Jaro kernel splits a group's rows into warp-uniform segments from the lanes' window radii.  Padding
     lanes (length 0) and 1 x 1 pairs have a WRAPPED radius (jaro.rs: len/2 - 1): they must not drag the real lanes of
     their group into the wrong segment.  Small alphabet, lengths that put 1 / 65 / 100 long candidates and the padding
     of the last group into shared groups, candidates longer than the truncated length (jaro.rs:553-565)."""
     rng = np.random.default_rng(70 + qlen)
-    q = rng.integers(1, 5, qlen).astype(np.uint8)
-    for n in (3001, 33, 1):
+    for n, lo in ((3001, 1), (33, 1), (1, 1), (3001, 0)):         # lo = 0: zero bytes in query and candidates (the layout's padding byte)
+        q = rng.integers(lo, 5, qlen).astype(np.uint8)
         lens = rng.choice([0, 1, 3, 8, 31, 32, 33, 50, 64, 65, 100], n)
         lens[-1] = 100                                            # the longest candidates share a group with the padding
-        chars = rng.integers(1, 5, int(lens.sum())).astype(np.uint8)
+        chars = rng.integers(lo, 5, int(lens.sum())).astype(np.uint8)
         off = np.zeros(n + 1, np.uint64)
         off[1:] = np.cumsum(lens)
         corpus = rf.Corpus(chars, off)

@@ -393,8 +393,10 @@ rf_status rf_corpus_create_from_file(const char* path, int device, rf_corpus** o
  *            interleaved copy and the streaming entry points use;
  *        2 = interleaved layout, rows streamed into per-warp shared-memory rings by TMA bulk copies (Jaro /
  *            Jaro-Winkler, which need random access to the candidate, stay on 0);
- *   "jaro32" (default 1): Jaro / Jaro-Winkler queries of at most 32 elements use the row-wise 32-bit kernel
- *        (interleaved layout only); 0 = the generic per-lane routine;
+ *   "jaro32" (default 1): Jaro / Jaro-Winkler queries of at most 64 elements use the row-wise kernels (32-bit flags up to
+ *        32 elements, 64-bit flags on 32-bit halves up to 64; interleaved layout only) with the f64 score algebra looked up
+ *        in a per-launch table; 2 = the same kernels with the score algebra computed per pair, 3 = table, 48-register build (5 CTAs per SM)
+ *        (both kept for A/B runs and cross-checks); 0 = the generic per-lane routine;
  *   "multi_word_path" (default 0): queries of 65..512 elements on a resident corpus: 0 = one thread per candidate, the
  *        whole bit-vector column in registers (interleaved layout), 1 = the sub-warp shuffle kernel (what longer
  *        queries, corpora without the interleaved copy and the streaming entry points use);

@@ -133,7 +133,7 @@ rf_status rf_set_option(const char* name, int value) {
   if (!name) return fail(RF_ERR_INVALID_ARG, "name is NULL");
   if (!strcmp(name, "build_interleaved_layout")) { g_build_lb.store(value ? 1 : 0); return RF_OK; }
   if (!strcmp(name, "single_word_path")) { g_w1_path.store(value); return RF_OK; }
-  if (!strcmp(name, "jaro32")) { g_jaro32.store(value ? 1 : 0); return RF_OK; }
+  if (!strcmp(name, "jaro32")) { g_jaro32.store(value >= 0 && value <= 3 ? value : 1); return RF_OK; }
   if (!strcmp(name, "multi_word_path")) { g_mw_path.store(value ? 1 : 0); return RF_OK; }
   if (!strcmp(name, "banded_levenshtein")) { g_band.store(value ? 1 : 0); return RF_OK; }
   if (!strcmp(name, "stream_chunk_mb")) { if (value < 1) return fail(RF_ERR_INVALID_ARG, "stream_chunk_mb < 1"); g_stream_mb.store(value); return RF_OK; }
@@ -672,7 +672,7 @@ rf_status rf_batch_set_option(rf_batch* b, const char* name, int value) {
   if (!strcmp(name, "single_word_path")) b->opt.w1_path = value;
   else if (!strcmp(name, "multi_word_path")) b->opt.mw_path = value ? 1 : 0;
   else if (!strcmp(name, "banded_levenshtein")) b->opt.band = value ? 1 : 0;
-  else if (!strcmp(name, "jaro32")) b->opt.jaro32 = value ? 1 : 0;
+  else if (!strcmp(name, "jaro32")) b->opt.jaro32 = value >= 0 && value <= 3 ? value : 1;
   else return fail(RF_ERR_INVALID_ARG, std::string("not a per-comparator option: ") + name);
   for (auto& kv : b->subs) rf_batch_set_option(kv.second, name, value);
   return RF_OK;

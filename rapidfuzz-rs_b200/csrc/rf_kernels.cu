@@ -820,6 +820,8 @@ struct LbParams {
   uint32_t chunk;               // consecutive groups handed to a warp at a time
   unsigned long long* counter;  // dynamic chunk scheduler (zeroed before the launch)
   unsigned long long* flag;     // scan_jaro32_kernel: set when a group was left to jaro32_long_kernel (zeroed before the launch)
+  const double* jtab;           // row-wise Jaro kernels: the whole f64 epilogue as a table (jaro_epi_table_kernel), or NULL
+  uint32_t j_l2dim, j_ccdim, j_trdim, j_pfdim;
   Epi epi;
 };
 
@@ -1037,8 +1039,88 @@ __device__ __noinline__ double jaro32_long_fallback(const uint32_t* __restrict__
   return finish_float(epi, jw);
 }
 
-template <int NT>
-__global__ void __launch_bounds__(NT) scan_jaro32_kernel(const __grid_constant__ LbParams p) {
+// The f64 epilogue of the row-wise Jaro kernels as a TABLE.  With the query, the kind, the cutoff and the prefix weight
+// fixed for a launch, the result of a pair is a pure function of four small integers: the candidate's length, the number
+// of common characters, the halved transposition count and (Jaro-Winkler) the common prefix.  The score algebra -- two
+// filters, the similarity formula, the Winkler bonus, the Metricf64 chain of the four kinds, the final cutoff test:
+// 150-250 executed instructions per group of 32 candidates, a quarter of them double precision, and 1700 instructions
+// of code for the four kinds -- is evaluated once per launch for every reachable combination by THE SAME device
+// functions (so the results stay bit-identical) and the scan kernel's epilogue becomes three IMADs and one load.
+//   index = ((len2 * ccdim + cc) * trdim + transpositions / 2) * pfdim + prefix
+// 1 x 1 pairs: jaro32_finish answers from `first_match`; the scan kernel stores that flag in cc for them.
+struct JaroTabParams {
+  double* tab;
+  const double* quot;
+  uint32_t len1, l2dim, ccdim, trdim, pfdim;
+  Epi epi;
+};
+__global__ void __launch_bounds__(256) jaro_epi_table_kernel(const __grid_constant__ JaroTabParams p) {
+  const uint32_t total = p.l2dim * p.ccdim * p.trdim * p.pfdim;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    uint32_t r = i;
+    const uint32_t prefix = r % p.pfdim; r /= p.pfdim;
+    const uint32_t th = r % p.trdim; r /= p.trdim;
+    const uint32_t cc = r % p.ccdim;
+    const uint32_t len2 = r / p.ccdim;
+    double res = 0.0;
+    // combinations no pair can produce (more common characters than characters, ...) are never looked up
+    if (cc <= len2 && cc <= p.len1 && 2u * th <= cc && prefix <= len2 && prefix <= p.len1) {
+      Jaro32Result jr;
+      jr.cc = cc;
+      jr.transpositions = 2u * th;
+      const bool fm = cc != 0u;
+      const uint32_t len1 = p.len1;
+      const double* quot = p.quot;
+      auto jaro = [&](double c) { return jaro32_finish(len1, len2, jr, fm, c, quot); };
+      if (p.epi.metric == M_JARO) {
+        res = finish_float(p.epi, jaro);
+      } else {
+        const double pw = p.epi.prefix_weight;
+        auto jw = [&](double c) { return jaro_winkler_from(jaro, prefix, pw, c); };
+        res = finish_float(p.epi, jw);
+      }
+    }
+    p.tab[i] = res;
+  }
+}
+// fills p.jtab / p.j_*dim; the caller frees *tab_out (stream-ordered) after its scan kernel is enqueued
+static cudaError_t jaro_epi_table(const ScanLaunch& L, LbParams& p, double** tab_out) {
+  const uint32_t len1 = L.query.len1;  // 1..64
+  // longest ORIGINAL candidate the row-wise kernels score: truncated length len1 + len2/2 - 1 <= 64 (jaro.rs:553-565)
+  const uint32_t l2max = (131u > 2u * len1 && 131u - 2u * len1 > 64u) ? 131u - 2u * len1 : 64u;
+  JaroTabParams t{};
+  t.len1 = len1;
+  t.l2dim = l2max + 1u;
+  t.ccdim = len1 + 1u;
+  t.trdim = len1 / 2u + 1u;
+  t.pfdim = L.epi.metric == M_JARO ? 1u : 5u;
+  t.quot = L.query.quot;
+  t.epi = L.epi;
+  const uint64_t total = (uint64_t)t.l2dim * t.ccdim * t.trdim * t.pfdim;  // <= 66 * 65 * 33 * 5 = 707 850 entries (5.7 MB)
+  cudaError_t e = dev_alloc(&t.tab, total * sizeof(double), L.stream);
+  if (e != cudaSuccess) return e;
+  uint64_t blocks = (total + 255) / 256;
+  if (blocks > (uint64_t)L.sm_count * 8) blocks = (uint64_t)L.sm_count * 8;
+  jaro_epi_table_kernel<<<(uint32_t)blocks, 256, 0, L.stream>>>(t);
+  g_launches.fetch_add(1);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { dev_free(t.tab, L.stream); return e; }
+  p.jtab = t.tab;
+  p.j_l2dim = t.l2dim;
+  p.j_ccdim = t.ccdim;
+  p.j_trdim = t.trdim;
+  p.j_pfdim = t.pfdim;
+  *tab_out = t.tab;
+  return cudaSuccess;
+}
+// the table lookup of a scored pair (len2 = the candidate's ORIGINAL length; the clamp never acts, see jaro_epi_table)
+__device__ __forceinline__ double jaro_tab_lookup(const LbParams& p, uint32_t len2, uint32_t cc, uint32_t tr, uint32_t prefix) {
+  const uint32_t l2c = len2 < p.j_l2dim ? len2 : p.j_l2dim - 1u;
+  return __ldg(p.jtab + (((l2c * p.j_ccdim + cc) * p.j_trdim + (tr >> 1)) * p.j_pfdim + prefix));
+}
+
+template <int NT, bool TABEPI, int MINB = 4>
+__global__ void __launch_bounds__(NT, MINB) scan_jaro32_kernel(const __grid_constant__ LbParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint32_t* pm = reinterpret_cast<uint32_t*>(smem_raw);
   {
@@ -1124,19 +1206,31 @@ __global__ void __launch_bounds__(NT) scan_jaro32_kernel(const __grid_constant__
         }
         jr.transpositions = (uint32_t)__popc(J.M);
         const uint32_t w0 = len2 ? first.x : 0u;
-        const bool fm = len2 && (tab(w0 & 0xffu) & 1u);
         const uint32_t len1 = p.len1;
-        const double* quot = p.quot;
-        auto jaro = [&](double c) { return jaro32_finish(len1, len2, jr, fm, c, quot); };
-        if (p.epi.metric == M_JARO) {
-          res = finish_float(p.epi, jaro);
-        } else {
+        if constexpr (TABEPI) {
           uint32_t prefix = 0;  // common prefix, at most 4 (jaro_winkler.rs:118-123)
-          const uint32_t lim = len1 < len2 ? (len1 < 4 ? len1 : 4) : (len2 < 4 ? len2 : 4);
-          while (prefix < lim && ((tab((w0 >> (8 * prefix)) & 0xffu) >> prefix) & 1u)) ++prefix;
-          const double pw = p.epi.prefix_weight;
-          auto jw = [&](double c) { return jaro_winkler_from(jaro, prefix, pw, c); };
-          res = finish_float(p.epi, jw);
+          if (p.j_pfdim > 1u) {
+            const uint32_t lim = len1 < len2 ? (len1 < 4 ? len1 : 4) : (len2 < 4 ? len2 : 4);
+            while (prefix < lim && ((tab((w0 >> (8 * prefix)) & 0xffu) >> prefix) & 1u)) ++prefix;
+          }
+          // 1 x 1: the wrapped radius leaves the window empty and the reference answers from the first characters
+          // (jaro.rs:546-548); the table holds that answer under cc = 1 / cc = 0
+          if (len1 == 1u && len2 == 1u) jr.cc = tab(w0 & 0xffu) & 1u;
+          res = jaro_tab_lookup(p, len2, jr.cc, jr.transpositions, prefix);
+        } else {
+          const bool fm = len2 && (tab(w0 & 0xffu) & 1u);
+          const double* quot = p.quot;
+          auto jaro = [&](double c) { return jaro32_finish(len1, len2, jr, fm, c, quot); };
+          if (p.epi.metric == M_JARO) {
+            res = finish_float(p.epi, jaro);
+          } else {
+            uint32_t prefix = 0;
+            const uint32_t lim = len1 < len2 ? (len1 < 4 ? len1 : 4) : (len2 < 4 ? len2 : 4);
+            while (prefix < lim && ((tab((w0 >> (8 * prefix)) & 0xffu) >> prefix) & 1u)) ++prefix;
+            const double pw = p.epi.prefix_weight;
+            auto jw = [&](double c) { return jaro_winkler_from(jaro, prefix, pw, c); };
+            res = finish_float(p.epi, jw);
+          }
         }
       } else {
         // (truncated) candidates longer than 64 characters: left to jaro32_long_kernel, which runs right after this
@@ -1179,7 +1273,10 @@ __global__ void __launch_bounds__(256) jaro32_long_kernel(const __grid_constant_
 
 static cudaError_t launch_jaro32(const ScanLaunch& L) {
   constexpr int NT = 256;
-  auto kern = scan_jaro32_kernel<NT>;
+  const bool tabepi = L.jaro32 != 2;  // 2 = the in-kernel f64 epilogue (kept for A/B runs and as a cross-check in the tests)
+  // without the f64 epilogue the kernel also fits 48 registers = 5 CTAs per SM instead of 4 (jaro32 = 3): measured 3.17 ms per
+  // 10^8 candidates against 3.14 ms for the 64-register build, so 4 CTAs stay the default
+  auto kern = !tabepi ? scan_jaro32_kernel<NT, false> : (L.jaro32 == 3 ? scan_jaro32_kernel<NT, true, 5> : scan_jaro32_kernel<NT, true, 4>);
   const size_t smem = sizeof(uint32_t) * 256 * 32;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -1207,9 +1304,13 @@ static cudaError_t launch_jaro32(const ScanLaunch& L) {
   const uint64_t need = (nchunks + NT / 32 - 1) / (NT / 32);
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
+  double* jtab = nullptr;
+  if (tabepi && (e = jaro_epi_table(L, p, &jtab)) != cudaSuccess) return e;
   kern<<<(uint32_t)grid, NT, smem, L.stream>>>(p);
   g_launches.fetch_add(1);
-  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  e = cudaGetLastError();
+  dev_free(jtab, L.stream);
+  if (e != cudaSuccess) return e;
   // groups with candidates beyond 64 characters (none in BASELINE config 4): a no-op launch unless the flag was raised
   e = cudaFuncSetAttribute(jaro32_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -1331,7 +1432,7 @@ __device__ __noinline__ double jaro64_long_fallback(const uint32_t* __restrict__
   return finish_float(epi, jw);
 }
 
-template <int NT>
+template <int NT, bool TABEPI>
 __global__ void __launch_bounds__(NT) scan_jaro64_kernel(const __grid_constant__ LbParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint32_t* pm32 = reinterpret_cast<uint32_t*>(smem_raw);
@@ -1422,19 +1523,28 @@ __global__ void __launch_bounds__(NT) scan_jaro64_kernel(const __grid_constant__
         }
         jr.transpositions = (uint32_t)__popc(J.Ml) + (uint32_t)__popc(J.Mh);
         const uint32_t w0 = len2 ? first.x : 0u;
-        const bool fm = len2 && (tab_lo(w0 & 0xffu) & 1u);
         const uint32_t len1 = p.len1;
-        const double* quot = p.quot;
-        auto jaro = [&](double c) { return jaro32_finish(len1, len2, jr, fm, c, quot); };
-        if (p.epi.metric == M_JARO) {
-          res = finish_float(p.epi, jaro);
-        } else {
+        if constexpr (TABEPI) {
           uint32_t prefix = 0;
-          const uint32_t lim = len1 < len2 ? (len1 < 4 ? len1 : 4) : (len2 < 4 ? len2 : 4);
-          while (prefix < lim && ((tab_lo((w0 >> (8 * prefix)) & 0xffu) >> prefix) & 1u)) ++prefix;
-          const double pw = p.epi.prefix_weight;
-          auto jw = [&](double c) { return jaro_winkler_from(jaro, prefix, pw, c); };
-          res = finish_float(p.epi, jw);
+          if (p.j_pfdim > 1u) {
+            const uint32_t lim = len1 < len2 ? (len1 < 4 ? len1 : 4) : (len2 < 4 ? len2 : 4);
+            while (prefix < lim && ((tab_lo((w0 >> (8 * prefix)) & 0xffu) >> prefix) & 1u)) ++prefix;
+          }
+          res = jaro_tab_lookup(p, len2, jr.cc, jr.transpositions, prefix);
+        } else {
+          const bool fm = len2 && (tab_lo(w0 & 0xffu) & 1u);
+          const double* quot = p.quot;
+          auto jaro = [&](double c) { return jaro32_finish(len1, len2, jr, fm, c, quot); };
+          if (p.epi.metric == M_JARO) {
+            res = finish_float(p.epi, jaro);
+          } else {
+            uint32_t prefix = 0;
+            const uint32_t lim = len1 < len2 ? (len1 < 4 ? len1 : 4) : (len2 < 4 ? len2 : 4);
+            while (prefix < lim && ((tab_lo((w0 >> (8 * prefix)) & 0xffu) >> prefix) & 1u)) ++prefix;
+            const double pw = p.epi.prefix_weight;
+            auto jw = [&](double c) { return jaro_winkler_from(jaro, prefix, pw, c); };
+            res = finish_float(p.epi, jw);
+          }
         }
       } else {
         if (lane == 0) *p.flag = 1ull;
@@ -1476,7 +1586,8 @@ __global__ void __launch_bounds__(256) jaro64_long_kernel(const __grid_constant_
 
 static cudaError_t launch_jaro64(const ScanLaunch& L) {
   constexpr int NT = 256;
-  auto kern = scan_jaro64_kernel<NT>;
+  const bool tabepi = L.jaro32 != 2;
+  auto kern = tabepi ? scan_jaro64_kernel<NT, true> : scan_jaro64_kernel<NT, false>;
   const size_t smem = sizeof(uint64_t) * 256 * 32;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -1506,9 +1617,13 @@ static cudaError_t launch_jaro64(const ScanLaunch& L) {
   const uint64_t need = (nchunks + NT / 32 - 1) / (NT / 32);
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
+  double* jtab = nullptr;
+  if (tabepi && (e = jaro_epi_table(L, p, &jtab)) != cudaSuccess) return e;
   kern<<<(uint32_t)grid, NT, smem, L.stream>>>(p);
   g_launches.fetch_add(1);
-  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  e = cudaGetLastError();
+  dev_free(jtab, L.stream);
+  if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(jaro64_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   uint64_t lgrid = (uint64_t)L.sm_count * 2;

@@ -439,6 +439,56 @@ def test_eight_threads_share_handles():
     corpus.close()
 
 
+def gpu_batch_with(b, kind, corpus, cutoff=None, prefix_weight=0.1):
+    """gpu_util.gpu_batch on an existing comparator (whose options were set by the test)."""
+    a = Args()
+    if cutoff is not None:
+        a = a.score_cutoff(cutoff)
+    r = b._score(kind, corpus, a.prefix_weight(prefix_weight))
+    if isinstance(r, np.ma.MaskedArray):
+        return r.filled(np.nan if r.dtype == np.float64 else _ffi.NONE_U32)
+    return r
+
+
+@pytest.mark.parametrize("qlen", [1, 2, 7, 32, 33, 47, 64])
+def test_jaro_table_epilogue_equals_per_pair_epilogue_equals_oracle(qlen):
+    """The row-wise Jaro kernels look the whole f64 score algebra up in a per-launch table indexed by (candidate length,
+    common characters, transpositions / 2, prefix) -- built by the same device functions that option jaro32=2 runs per
+    pair.  All four kinds, with and without cutoffs (incl. > 0.7, which back-translates through the prefix:
+    jaro_winkler.rs:125-133), two prefix weights, 1 x 1 pairs, empty candidates, candidates up to the longest the
+    row-wise kernels take and beyond (jaro.rs:553-565): table == per pair == generic routine == oracle, bit for bit."""
+    L = _ffi.lib()
+    rng = np.random.default_rng(900 + qlen)
+    q = rng.integers(97, 101, qlen).astype(np.uint8)
+    n = 6000
+    lens = rng.choice([0, 1, 2, 3, 7, 8, 9, 31, 32, 33, 40, 63, 64, 65, 66, 67, 100, 128, 129, 130, 200], n)
+    chars = rng.integers(97, 101, int(lens.sum())).astype(np.uint8)
+    off = np.zeros(n + 1, np.uint64)
+    off[1:] = np.cumsum(lens)
+    for i in range(0, n, 7):                       # near matches: shared prefixes, many common characters
+        a, b = int(off[i]), int(off[i + 1])
+        m = min(b - a, qlen)
+        chars[a:a + m] = q[:m]
+    corpus = rf.Corpus(chars, off)
+    for metric in ("jaro", "jaro_winkler"):
+        variants = []
+        for opt in (1, 2, 3, 0):
+            b = _bc(metric, q)
+            _ffi.check(L.rf_batch_set_option(b._h, b"jaro32", opt))
+            variants.append(b)
+        for kind in ("similarity", "distance", "normalized_similarity", "normalized_distance"):
+            for kw in ({}, {"cutoff": 0.0}, {"cutoff": 0.5}, {"cutoff": 0.71}, {"cutoff": 0.9}, {"cutoff": 1.0}, {"cutoff": 1.2},
+                       {"prefix_weight": 0.25, "cutoff": 0.8}):
+                if "prefix_weight" in kw and metric == "jaro":
+                    continue
+                exp = orc.batch(metric, kind, q, chars, off, nthreads=0, **kw)
+                for opt, b in zip((1, 2, 3, 0), variants):
+                    assert_same(gpu_batch_with(b, kind, corpus, **kw), exp, (metric, kind, kw, "jaro32=%d" % opt, qlen))
+        for b in variants:
+            b.close()
+    corpus.close()
+
+
 def test_options_are_per_comparator():
     """The kernel-choice knobs are copied into a comparator at creation (rf_batch_set_option changes one comparator):
     two comparators with different settings give the same results side by side, and flipping the process-wide default

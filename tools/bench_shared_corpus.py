@@ -4,7 +4,7 @@ the corpus is generated, uploaded and laid out once, every case is timed with CU
 spot-checked against the CPU oracle on a sample.  One JSON line per case.
 
   python tools/bench_shared_corpus.py [case,case,...]     RF_CFG_SCALE=0.1 for a 10^7-candidate corpus
-cases: lev32 lev64 indel32 osa32 ham pre post jw32 jw48 jaro64 jw48off (the 48-element Jaro-Winkler query with the row-wise
+cases: lev32 lev64 indel32 osa32 ham pre post jw32 jw48 jaro64 jw32pair jw32r48 jw48pair jw48off (the 48-element Jaro-Winkler query with the row-wise
 kernel switched off = the per-lane routine it replaces)"""
 import json
 import os
@@ -41,6 +41,9 @@ CASES = {
     "jw48": ("jaro_winkler", "similarity", 48, True, None, {}),
     "jaro64": ("jaro", "similarity", 64, True, None, {}),
     "jw48off": ("jaro_winkler", "similarity", 48, True, None, {"jaro32": 0}),
+    "jw32pair": ("jaro_winkler", "normalized_similarity", 32, True, None, {"jaro32": 2}),   # score algebra per pair instead of the table
+    "jw32r48": ("jaro_winkler", "normalized_similarity", 32, True, None, {"jaro32": 3}),    # table, 48-register build (5 CTAs / SM)
+    "jw48pair": ("jaro_winkler", "similarity", 48, True, None, {"jaro32": 2}),
 }
 
 

@@ -146,7 +146,7 @@ rf_status rf_batch_create_u32(rf_metric metric, const uint32_t* query, uint32_t 
 rf_status rf_batch_create_elems(rf_metric metric, const void* query, rf_elem_type type, uint32_t query_len, int device,
                                 rf_batch** out);
 rf_status rf_batch_destroy(rf_batch* b);
-/* Kernel-choice knobs of ONE comparator ("single_word_path", "multi_word_path", "banded_levenshtein", "jaro32"; see
+/* Kernel-choice knobs of ONE comparator ("single_word_path", "multi_word_path", "banded_levenshtein", "jaro32", "epilogue_table"; see
  * rf_set_option for their meaning).  A comparator copies the process-wide defaults when it is created; scoring calls
  * read the comparator's copy only, so threads that want different kernels do not race on global state.  Call it
  * before the comparator is shared between threads. */
@@ -382,7 +382,7 @@ const void* rf_corpus_file_offsets(const rf_corpus_file* f);
 const uint8_t* rf_corpus_file_chars(const rf_corpus_file* f);
 rf_status rf_corpus_create_from_file(const char* path, int device, rf_corpus** out);
 
-/* tuning knobs (process-wide DEFAULTS: "single_word_path", "multi_word_path", "banded_levenshtein" and "jaro32" are
+/* tuning knobs (process-wide DEFAULTS: "single_word_path", "multi_word_path", "banded_levenshtein", "jaro32" and "epilogue_table" are
  * copied into every comparator at creation -- rf_batch_set_option changes one comparator; "build_interleaved_layout" and
  * "compact_u32_corpus" act at corpus creation; the stream / cdist / sharded knobs are read once at the start of a call):
  *   "build_interleaved_layout" (default 1): corpora created afterwards also keep the length-bucketed,
@@ -397,6 +397,10 @@ rf_status rf_corpus_create_from_file(const char* path, int device, rf_corpus** o
  *        32 elements, 64-bit flags on 32-bit halves up to 64; interleaved layout only) with the f64 score algebra looked up
  *        in a per-launch table; 2 = the same kernels with the score algebra computed per pair, 3 = table, 48-register build (5 CTAs per SM)
  *        (both kept for A/B runs and cross-checks); 0 = the generic per-lane routine;
+ *   "epilogue_table" (default 1): integer metrics with queries of at most 64 elements on a resident corpus whose candidates
+ *        are at most 255 elements long: the score algebra (distance <-> similarity, normalisation, cutoff conversions, the
+ *        final score() filter) is evaluated once per launch for every (candidate length, raw result) and looked up per
+ *        pair; 0 = evaluated per pair (same results);
  *   "multi_word_path" (default 0): queries of 65..512 elements on a resident corpus: 0 = one thread per candidate, the
  *        whole bit-vector column in registers (interleaved layout), 1 = the sub-warp shuffle kernel (what longer
  *        queries, corpora without the interleaved copy and the streaming entry points use);

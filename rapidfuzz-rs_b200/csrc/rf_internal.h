@@ -29,7 +29,7 @@ struct rf_corpus {
 // kernel-choice knobs, copied from the process-wide defaults (rf_set_option) when the comparator is created and changed
 // per comparator with rf_batch_set_option
 struct rf_batch_opts {
-  int w1_path = 0, mw_path = 0, band = 1, jaro32 = 1;
+  int w1_path = 0, mw_path = 0, band = 1, jaro32 = 1, epi_table = 1;
 };
 
 struct rf_batch {

@@ -4,7 +4,7 @@ the corpus is generated, uploaded and laid out once, every case is timed with CU
 spot-checked against the CPU oracle on a sample.  One JSON line per case.
 
   python tools/bench_shared_corpus.py [case,case,...]     RF_CFG_SCALE=0.1 for a 10^7-candidate corpus
-cases: lev32 lev64 indel32 osa32 ham pre post jw32 jw48 jaro64 jw32pair jw32r48 jw48pair jw48off (the 48-element Jaro-Winkler query with the row-wise
+cases: lev32 lev64 indel32 osa32 ham pre post jw32 jw48 jaro64 jw32pair jw32r48 jw48pair jw48off levns32 levns32pair ratio32 ratio32pair indel32pair lcs32 (the 48-element Jaro-Winkler query with the row-wise
 kernel switched off = the per-lane routine it replaces)"""
 import json
 import os
@@ -41,6 +41,12 @@ CASES = {
     "jw48": ("jaro_winkler", "similarity", 48, True, None, {}),
     "jaro64": ("jaro", "similarity", 64, True, None, {}),
     "jw48off": ("jaro_winkler", "similarity", 48, True, None, {"jaro32": 0}),
+    "levns32": ("levenshtein", "normalized_similarity", 32, True, None, {}),
+    "levns32pair": ("levenshtein", "normalized_similarity", 32, True, None, {"epilogue_table": 0}),
+    "ratio32": ("ratio", "similarity", 32, True, None, {}),
+    "ratio32pair": ("ratio", "similarity", 32, True, None, {"epilogue_table": 0}),
+    "indel32pair": ("indel", "distance", 32, False, None, {"epilogue_table": 0}),
+    "lcs32": ("lcs_seq", "similarity", 32, False, None, {}),
     "jw32pair": ("jaro_winkler", "normalized_similarity", 32, True, None, {"jaro32": 2}),   # score algebra per pair instead of the table
     "jw32r48": ("jaro_winkler", "normalized_similarity", 32, True, None, {"jaro32": 3}),    # table, 48-register build (5 CTAs / SM)
     "jw48pair": ("jaro_winkler", "similarity", 48, True, None, {"jaro32": 2}),
@@ -62,6 +68,9 @@ def timed(fn, steps, warmup=3):
 
 def main():
     which = sys.argv[1].split(",") if len(sys.argv) > 1 else list(CASES)
+    for kv in os.environ.get("RF_OPTS", "").split(","):   # process-wide knobs set BEFORE the corpus is created, e.g. layout_sort_block=2048
+        if kv:
+            _ffi.check(L.rf_set_option(kv.split("=")[0].encode(), int(kv.split("=")[1])))
     n = int(1e8 * scale)
     q0 = synth.synth_query(2, 32)
     chars, offsets = synth.synth_corpus(2, q0, n, 8, 64, 16)
@@ -88,7 +97,7 @@ def main():
         else:
             exact = bool(np.array_equal(got.view(np.uint32), exp))
         alg = total + (12.0 if f64 else 8.0) * n
-        print(json.dumps({"case": name, "metric": metric, "kind": kind, "query_len": qlen, "n": n, "options": opts, "ms_per_step": ms,
+        print(json.dumps({"case": name, "metric": metric, "kind": kind, "query_len": qlen, "n": n, "options": opts, "process_options": os.environ.get("RF_OPTS", ""), "ms_per_step": ms,
                           "pairs_per_s": n / (ms * 1e-3), "algorithmic_GBps": alg / (ms * 1e-3) / 1e9,
                           "hbm_frac_of_measured_peak": alg / (ms * 1e-3) / 1e9 / PEAK, "bit_exact_vs_oracle_sample": exact}), flush=True)
         b.close()

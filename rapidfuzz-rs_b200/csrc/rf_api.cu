@@ -29,7 +29,6 @@ static std::atomic<int> g_build_lb{1};   // build the length-bucketed interleave
 static std::atomic<int> g_w1_path{0};    // 0: interleaved-layout kernel when available, 1: CSR/TMA-tile kernel
 static std::atomic<int> g_mw_path{0};    // queries of 65..512 on a resident corpus: 0 register kernel (scan_lbn), 1 shuffle kernel (scan_mw)
 static std::atomic<int> g_band{1};       // multi-word Levenshtein with cutoff <= 63: banded kernel (0: block kernel)
-static std::atomic<int> g_lb_sort_block{65536};  // candidates per sort block of the interleaved layout of corpora created afterwards
 static std::atomic<int> g_epi_table{1};  // integer metrics, interleaved layout: score algebra as a per-launch table (0: per pair)
 static std::atomic<int> g_jaro32{1};     // Jaro / Jaro-Winkler, query <= 32: row-wise 32-bit kernel (0: generic per-lane routine)
 // The four knobs above are DEFAULTS: a comparator takes a snapshot of them when it is created (rf_batch::opt) and its
@@ -134,11 +133,6 @@ uint64_t rf_kernel_launch_count(void) { return kernel_launch_count(); }
 rf_status rf_set_option(const char* name, int value) {
   if (!name) return fail(RF_ERR_INVALID_ARG, "name is NULL");
   if (!strcmp(name, "build_interleaved_layout")) { g_build_lb.store(value ? 1 : 0); return RF_OK; }
-  if (!strcmp(name, "layout_sort_block")) {
-    if (value < 1024 || value > 65536 || (value & (value - 1)) != 0) return fail(RF_ERR_INVALID_ARG, "layout_sort_block: a power of two in 1024..65536");
-    g_lb_sort_block.store(value);
-    return RF_OK;
-  }
   if (!strcmp(name, "single_word_path")) { g_w1_path.store(value); return RF_OK; }
   if (!strcmp(name, "epilogue_table")) { g_epi_table.store(value ? 1 : 0); return RF_OK; }
   if (!strcmp(name, "jaro32")) { g_jaro32.store(value >= 0 && value <= 3 ? value : 1); return RF_OK; }
@@ -242,7 +236,7 @@ static rf_status corpus_finish(rf_corpus* c, cudaStream_t st) {
   RF_CUDA(cudaGetLastError());
   if (g_build_lb.load()) {
     CorpusView v{c->d_chars, c->d_off32, c->d_off64, c->n, c->total};
-    RF_CUDA(lb_build(v, st, &c->lb, (uint32_t)g_lb_sort_block.load()));
+    RF_CUDA(lb_build(v, st, &c->lb));
   }
   return RF_OK;
 }
@@ -782,14 +776,13 @@ static rf_status score_view(const rf_batch* b, const CorpusView& cv_in, const Lb
     }
   }
   if (use_lb) {
-    L.lb = LbView{lb->perm, lb->lens, lb->goff, lb->gdata, lb->ngroups, lb->sort_block, 0, cv_in.n};
+    L.lb = LbView{lb->perm, lb->lens, lb->goff, lb->gdata, lb->ngroups};
     if (ranged) {  // whole 65536-candidate blocks = whole groups; results are scattered through perm (absolute indices)
       const uint64_t g0 = r0 / 32, g1 = (r1 + 31) / 32;
       L.lb.perm += g0 * 32;
       L.lb.lens += g0 * 32;
       L.lb.goff += g0;
       L.lb.ngroups = g1 - g0;
-      L.lb.cand_base = r0;
     }
     L.lb_counter = counter_slot(device);
     L.lb_flag = counter_slot(device);
@@ -802,7 +795,6 @@ static rf_status score_view(const rf_batch* b, const CorpusView& cv_in, const Lb
   L.sm_count = sm_count_of(device);
   L.jaro32 = opt.jaro32;
   L.epi_table = opt.epi_table;
-  L.no_coop = opt.w1_path == 3 ? 1 : 0;
   const Family fam = family_of(L.epi.metric, L.epi.wclass);
   cudaError_t e;
   if (fam == F_SIMPLE) e = launch_simple(L, d_err);
@@ -1932,7 +1924,7 @@ static rf_status cdist_impl(const uint8_t* q_chars, const uint64_t* q_offsets, u
       if ((e = cudaMemcpyAsync(d_tabs, tabs.data(), tabs.size(), cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
       if ((e = cudaMemcpyAsync(d_qlen, qlen.data(), nq * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
       CdistLaunch L{};
-      L.lb = LbView{c->lb.perm, c->lb.lens, c->lb.goff, c->lb.gdata, c->lb.ngroups, c->lb.sort_block, 0, c->n};
+      L.lb = LbView{c->lb.perm, c->lb.lens, c->lb.goff, c->lb.gdata, c->lb.ngroups};
       L.total_rows = c->lb.total_rows;
       L.q_tabs = d_tabs;
       L.wide = wide ? 1 : 0;

@@ -923,120 +923,6 @@ __global__ void __launch_bounds__(NT) scan_lb_kernel(const __grid_constant__ LbP
   }
 }
 
-// ------------------------------------------------------------------------------------------------ lbc
-// Block-cooperative form of scan_lb_kernel for layouts sorted in SMALL blocks (LbView::sort_block <= LB_COOP_MAX).
-// Why: scan_lb_kernel stores every result straight to out[original index] -- 32 scattered 4-byte stores per warp
-// instruction, i.e. one L2 write transaction per RESULT.  Measured on B200 that path costs ~0.44 ms per 10^8 results
-// whatever the metric (Hamming 0.85 ms, Indel 1.40 ms and fuzz::ratio 1.84 ms per 10^8 pairs are all "reads at HBM speed
-// + 0.44 ms per 0.4 GB of results"), and DRAM sees 2.2x the result bytes.  Here a CTA owns one sort block at a time: its
-// warps take the block's groups round-robin (warp w: groups w, w + NW, ... -- every warp sees every length, so they finish
-// together), park the results in shared memory at [original index - block start], and after one barrier the CTA writes
-// the block's result row as full 128-byte lines.  Blocks are handed out by a global counter, one atomic per block.
-// f64 results are parked as indices into the epilogue table (int_epi_table) and expanded while they are written.
-template <int FAM, class W, int NT, bool RAWDIST>
-__global__ void __launch_bounds__(NT) scan_lbc_kernel(const __grid_constant__ LbParams p) {
-  static_assert(FAM == F_LEV || FAM == F_OSA || FAM == F_LCS, "integer metrics only");
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ unsigned long long s_next;
-  constexpr bool SPLIT64 = sizeof(W) == 8;
-  constexpr int NW = NT / 32;
-  W* pm = reinterpret_cast<W*>(smem_raw);
-  uint32_t* stage = reinterpret_cast<uint32_t*>(smem_raw + sizeof(W) * 256 * 32);
-  {
-    const W* __restrict__ t = reinterpret_cast<const W*>(p.tab);
-    if constexpr (SPLIT64) {
-      uint32_t* pm32 = reinterpret_cast<uint32_t*>(smem_raw);
-      for (uint32_t i = threadIdx.x; i < 256u * 32u; i += NT) {
-        const uint64_t v = t[i >> 5];
-        pm32[i] = (uint32_t)v;
-        pm32[i + 256u * 32u] = (uint32_t)(v >> 32);
-      }
-    } else {
-      for (uint32_t i = threadIdx.x; i < 256u * 32u; i += NT) pm[i] = t[i >> 5];
-    }
-  }
-  __syncthreads();
-  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const W* __restrict__ pm_lane = SPLIT64 ? reinterpret_cast<const W*>(reinterpret_cast<const uint32_t*>(smem_raw) + lane) : pm + lane;
-  const uint32_t S = p.lb.sort_block, GPB = S >> 5;
-  const uint64_t ngroups = p.lb.ngroups;
-  const uint64_t nblocks = (ngroups + GPB - 1) / GPB;
-  const uint2* __restrict__ gdata = reinterpret_cast<const uint2*>(p.lb.gdata);
-  const bool tab_f64 = p.out_f64 != 0;  // (the launcher only takes this kernel for f64 results when the table exists)
-  uint64_t blk = blockIdx.x;
-  while (blk < nblocks) {
-    const uint64_t g_base = blk * GPB;
-    const uint32_t ng = (uint32_t)((g_base + GPB <= ngroups) ? GPB : ngroups - g_base);
-    const uint32_t c0 = (uint32_t)(p.lb.cand_base + blk * S);  // original index of the block's first candidate (< 2^32: perm is u32)
-    // the next block is claimed NOW: the atomic's round trip (~1 us) hides behind this block's groups instead of sitting
-    // in front of the barrier (first version: 2.15 ms instead of 1.99 ms per 10^8 pairs)
-    unsigned long long claimed = 0;
-    if (threadIdx.x == 0) claimed = (unsigned long long)gridDim.x + atomicAdd(p.counter, 1ull);
-    // first rows of this warp's groups: lane l fetches the offset of the warp's l-th group (at most GPB / NW <= 32 of them)
-    uint64_t my_off = 0;
-    if (warp + NW * lane < ng) my_off = __ldg(p.lb.goff + g_base + warp + NW * lane);
-    uint32_t gi = warp, k = 0;
-    uint32_t len_n = 0;
-    uint2 first_n = make_uint2(0u, 0u), second_n = first_n;
-    const uint2* col_n = gdata;
-    if (gi < ng) {
-      col_n = gdata + __shfl_sync(0xffffffffu, my_off, 0) * 32 + lane;
-      len_n = __ldg(p.lb.lens + (g_base + gi) * 32 + lane);
-      first_n = ld_row8<true>(col_n);
-      second_n = ld_row8<true>(col_n + 32);
-    }
-    for (; gi < ng; gi += NW, ++k) {
-      const uint32_t len2 = len_n;
-      const uint32_t idx = __ldg(p.lb.perm + (g_base + gi) * 32 + lane);
-      const LaneSrcT<true> src{col_n, first_n, second_n};
-      if (gi + NW < ng) {  // the warp's next group: length and first rows requested now, they arrive while this one is scored
-        col_n = gdata + __shfl_sync(0xffffffffu, my_off, k + 1) * 32 + lane;
-        len_n = __ldg(p.lb.lens + (g_base + gi + NW) * 32 + lane);
-        first_n = ld_row8<true>(col_n);
-        second_n = ld_row8<true>(col_n + 32);
-      }
-      uint32_t v;
-      const uint32_t raw = raw_one<FAM, W, LaneSrcT<true>, SPLIT64>(pm_lane, src, len2, p.len1, p.two);
-      if constexpr (RAWDIST) {
-        v = raw;
-      } else if (p.jtab != nullptr) {
-        const uint32_t l2c = len2 < p.j_l2dim ? len2 : p.j_l2dim - 1u;
-        const uint32_t rc = raw < p.j_ccdim ? raw : p.j_ccdim - 1u;
-        const uint32_t ti = l2c * p.j_ccdim + rc;
-        v = tab_f64 ? ti : __ldg(reinterpret_cast<const uint32_t*>(p.jtab) + ti);
-      } else {
-        v = finish_int(p.epi, raw, p.len1, len2);
-      }
-      if (idx != 0xFFFFFFFFu) stage[idx - c0] = v;
-    }
-    if (threadIdx.x == 0) s_next = claimed;
-    __syncthreads();
-    // the block's result row, coalesced
-    const uint64_t cbeg = p.lb.cand_base + blk * S;
-    const uint32_t cnt = (uint32_t)(cbeg + S <= p.lb.n_total ? S : (cbeg < p.lb.n_total ? p.lb.n_total - cbeg : 0));
-    if (tab_f64) {
-      double* __restrict__ o = reinterpret_cast<double*>(p.out) + cbeg;
-      for (uint32_t i = threadIdx.x; i < cnt; i += NT) o[i] = __ldg(p.jtab + stage[i]);
-    } else {
-      uint32_t* __restrict__ o = reinterpret_cast<uint32_t*>(p.out) + cbeg;
-      if (cnt == S) {  // full block: 16 bytes per thread (cbeg is a multiple of S, the row is 16-byte aligned with the buffer)
-        if ((reinterpret_cast<uintptr_t>(o) & 15u) == 0) {
-          const uint4* s4 = reinterpret_cast<const uint4*>(stage);
-          uint4* o4 = reinterpret_cast<uint4*>(o);
-          for (uint32_t i = threadIdx.x; i < S / 4; i += NT) o4[i] = s4[i];
-        } else {
-          for (uint32_t i = threadIdx.x; i < cnt; i += NT) o[i] = stage[i];
-        }
-      } else {
-        for (uint32_t i = threadIdx.x; i < cnt; i += NT) o[i] = stage[i];
-      }
-    }
-    const unsigned long long nxt = s_next;
-    __syncthreads();  // the staging row and s_next are reused by the next block
-    blk = nxt;
-  }
-}
-
 // The score algebra of the integer metrics (MetricUsize: distance <-> similarity, normalisation, cutoff conversions and the
 // final score() filter, details/distance.rs:154-275) as a per-launch TABLE over (candidate length, raw kernel result):
 // with the query, kind and cutoff fixed, nothing else enters.  Built by finish_int / finish_norm themselves, so the results
@@ -1085,58 +971,8 @@ static cudaError_t int_epi_table(const ScanLaunch& L, LbParams& p, void** tab_ou
   return cudaSuccess;
 }
 
-template <int FAM, class W, int NT, bool RAWDIST>
-static cudaError_t launch_lbc_inst(const ScanLaunch& L, const void* tab) {
-  auto kern = scan_lbc_kernel<FAM, W, NT, RAWDIST>;
-  const size_t smem = sizeof(W) * 256 * 32 + (size_t)L.lb.sort_block * sizeof(uint32_t);
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  if (e != cudaSuccess) return e;
-  int ctas_per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, NT, smem);
-  if (e != cudaSuccess) return e;
-  if (ctas_per_sm < 1) ctas_per_sm = 1;
-  LbParams p{};
-  p.lb = L.lb;
-  p.tab = tab;
-  p.len1 = L.query.len1;
-  p.out = L.out;
-  p.out_f64 = L.out_is_f64;
-  p.two = 2;
-  p.counter = L.lb_counter;
-  p.epi = L.epi;
-  e = cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), L.stream);
-  if (e != cudaSuccess) return e;
-  const uint64_t gpb = L.lb.sort_block / 32;
-  const uint64_t nblocks = (L.lb.ngroups + gpb - 1) / gpb;
-  uint64_t grid = (uint64_t)L.sm_count * ctas_per_sm;
-  if (grid > nblocks) grid = nblocks;
-  if (grid < 1) grid = 1;
-  void* etab = nullptr;
-  if constexpr (!RAWDIST) {
-    if ((e = int_epi_table(L, p, &etab)) != cudaSuccess) return e;
-    if (L.out_is_f64 && !etab) return cudaErrorInvalidValue;  // (launch_lb_inst checks lbc_applies first)
-  }
-  kern<<<(uint32_t)grid, NT, smem, L.stream>>>(p);
-  g_launches.fetch_add(1);
-  e = cudaGetLastError();
-  dev_free(etab, L.stream);
-  return e;
-}
-// the cooperative kernel parks 4 bytes per candidate: f64 results need the epilogue table to exist (int_epi_table's conditions)
-static bool lbc_applies(const ScanLaunch& L, bool rawdist) {
-  if (L.no_coop || L.lb.sort_block > LB_COOP_MAX || L.lb.sort_block < 1024) return false;
-  if (L.lb.cand_base + L.lb.ngroups * 32 > 0xFFFFFFFFull) return false;
-  if (rawdist || !L.out_is_f64) return true;
-  return L.corpus.max_len != 0 && L.corpus.max_len <= kIntTabMaxLen && L.lb.ngroups >= kIntTabMinGroups && L.epi_table;
-}
-
 template <int FAM, class W, int NT, bool RAWDIST = false>
 static cudaError_t launch_lb_inst(const ScanLaunch& L, const void* tab) {
-  if constexpr (FAM == F_LEV || FAM == F_OSA || FAM == F_LCS) {
-    if (lbc_applies(L, RAWDIST)) return launch_lbc_inst<FAM, W, (sizeof(W) == 4 ? 256 : NT), RAWDIST>(L, tab);
-  }
   auto kern = scan_lb_kernel<FAM, W, NT, RAWDIST>;
   const size_t smem = sizeof(W) * 256 * 32;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

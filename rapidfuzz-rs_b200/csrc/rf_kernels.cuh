@@ -46,12 +46,8 @@ struct LbView {
   const uint64_t* goff;   // [ngroups+1]  first row of each group
   const uint32_t* gdata;  // [total_rows*64 (+ slack)] viewed as uint2 rows
   uint64_t ngroups;
-  uint32_t sort_block;    // candidates per sort block (power of two, 1024 ... LB_BLOCK): block b holds candidates [b, b+1) * sort_block
-  uint64_t cand_base;     // candidate index of this view's first group's block (0 unless the view is a sub-range)
-  uint64_t n_total;       // candidates of the whole corpus (bounds the cooperative kernel's result rows)
 };
-constexpr uint32_t LB_BLOCK = 65536;      // sub-range granularity; every sort block size divides it
-constexpr uint32_t LB_COOP_MAX = 4096;    // largest sort block the block-cooperative kernel stages in shared memory
+constexpr uint32_t LB_BLOCK = 65536;
 
 struct LbAlloc {  // owning pointers of an LbView
   uint32_t* perm = nullptr;
@@ -59,11 +55,10 @@ struct LbAlloc {  // owning pointers of an LbView
   uint64_t* goff = nullptr;
   uint32_t* gdata = nullptr;
   uint64_t ngroups = 0;
-  uint32_t sort_block = LB_BLOCK;
   uint64_t total_rows = 0;
 };
 // Builds the layout from the CSR corpus on `stream` (synchronises once to size the data array).
-cudaError_t lb_build(const CorpusView& c, cudaStream_t stream, LbAlloc* out, uint32_t sort_block = LB_BLOCK);
+cudaError_t lb_build(const CorpusView& c, cudaStream_t stream, LbAlloc* out);
 void lb_free(LbAlloc* a, cudaStream_t stream);
 
 // u8 candidate lengths of a streaming chunk -> its u32 CSR starts (cn + 1 entries, first = init); rf_layout.cu
@@ -84,7 +79,6 @@ struct ScanLaunch {
   int sm_count;
   int elem16;         // corpus.chars is an array of uint16_t codes and query.pm_words has one row per code (multi-word kernels only)
   int jaro32;         // Jaro / Jaro-Winkler, query <= 64: 1 = row-wise kernels + table epilogue, 2 = per-pair epilogue, 3 = 48-register build, 0 = generic per-lane routine
-  int no_coop = 0;    // 1 = never the block-cooperative kernel (scan_lbc_kernel), whatever the layout's sort block
   int epi_table = 1;  // integer metrics on the interleaved layout: 1 = score algebra as a per-launch table (candidates <= 255 elements), 0 = per pair
 };
 

@@ -22,12 +22,12 @@ __device__ __forceinline__ uint64_t off_ld(const uint32_t* o32, const uint64_t* 
 // one CTA per block of LB_BLOCK candidates: counting sort by length -> perm / lens in sorted order
 __global__ void __launch_bounds__(1024) lb_sort_kernel(const uint32_t* __restrict__ o32, const uint64_t* __restrict__ o64,
                                                        uint64_t n, uint64_t n_pad, uint32_t* __restrict__ perm,
-                                                       uint32_t* __restrict__ lens, uint32_t sort_block) {
+                                                       uint32_t* __restrict__ lens) {
   __shared__ uint32_t hist[LB_KEYS];
   __shared__ uint32_t wsum[32];
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  const uint64_t b0 = (uint64_t)blockIdx.x * sort_block;
-  const uint64_t b1 = (b0 + sort_block < n) ? b0 + sort_block : n;
+  const uint64_t b0 = (uint64_t)blockIdx.x * LB_BLOCK;
+  const uint64_t b1 = (b0 + LB_BLOCK < n) ? b0 + LB_BLOCK : n;
   for (uint32_t i = tid; i < LB_KEYS; i += 1024) hist[i] = 0;
   __syncthreads();
   for (uint64_t i = b0 + tid; i < b1; i += 1024) {
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(1024) lb_sort_kernel(const uint32_t* __restric
     lens[b0 + pos] = (uint32_t)len;
   }
   // padding lanes of the very last group
-  const uint64_t e1 = (b0 + sort_block < n_pad) ? b0 + sort_block : n_pad;
+  const uint64_t e1 = (b0 + LB_BLOCK < n_pad) ? b0 + LB_BLOCK : n_pad;
   for (uint64_t j = b1 + tid; j < e1; j += 1024) {
     perm[j] = 0xFFFFFFFFu;
     lens[j] = 0;
@@ -195,16 +195,14 @@ void lb_free(LbAlloc* a, cudaStream_t st) {
   *a = LbAlloc{};
 }
 
-cudaError_t lb_build(const CorpusView& c, cudaStream_t st, LbAlloc* out, uint32_t sort_block) {
+cudaError_t lb_build(const CorpusView& c, cudaStream_t st, LbAlloc* out) {
   *out = LbAlloc{};
   if (c.n == 0) return cudaSuccess;
-  if (sort_block < 1024 || sort_block > LB_BLOCK || (sort_block & (sort_block - 1)) != 0) return cudaErrorInvalidValue;
   const uint64_t n_pad = (c.n + 31) / 32 * 32;
   const uint64_t ngroups = n_pad / 32;
-  const uint32_t nblocks = (uint32_t)((c.n + sort_block - 1) / sort_block);
+  const uint32_t nblocks = (uint32_t)((c.n + LB_BLOCK - 1) / LB_BLOCK);
   LbAlloc a;
   a.ngroups = ngroups;
-  a.sort_block = sort_block;
   uint32_t* grows = nullptr;
   void* tmp = nullptr;
   size_t tmp_bytes = 0;
@@ -218,7 +216,7 @@ cudaError_t lb_build(const CorpusView& c, cudaStream_t st, LbAlloc* out, uint32_
   LB_TRY(dev_alloc(&a.lens, n_pad * sizeof(uint32_t), st));
   LB_TRY(dev_alloc(&a.goff, (ngroups + 1) * sizeof(uint64_t), st));
   LB_TRY(dev_alloc(&grows, (ngroups + 1) * sizeof(uint32_t), st));
-  lb_sort_kernel<<<nblocks, 1024, 0, st>>>(c.off32, c.off64, c.n, n_pad, a.perm, a.lens, sort_block);
+  lb_sort_kernel<<<nblocks, 1024, 0, st>>>(c.off32, c.off64, c.n, n_pad, a.perm, a.lens);
   LB_TRY(cudaGetLastError());
   {
     uint64_t blocks = (ngroups + 1 + 7) / 8;

@@ -540,55 +540,6 @@ def test_integer_epilogue_table_equals_per_pair_epilogue_equals_oracle(qlen):
     corpus.close()
 
 
-@pytest.mark.parametrize("sort_block", [1024, 2048, 4096])
-def test_block_cooperative_kernel_on_small_sort_blocks(sort_block):
-    """Corpora whose interleaved layout is sorted in blocks of at most 4096 candidates are scored by the block-cooperative
-    kernel (results parked in shared memory, written as whole rows): every integer metric x kind with 32- and 64-bit words,
-    with and without the epilogue table (corpus above / below 65 536 candidates), partial last blocks, empty candidates,
-    candidates longer than 255 (no table: f64 kinds fall back to the scattering kernel), == the scattering kernel
-    (single_word_path = 3) == oracle; the other kernels over the same layout (Jaro, Hamming, multi-word, many-vs-many) too."""
-    L = _ffi.lib()
-    _ffi.check(L.rf_set_option(b"layout_sort_block", sort_block))
-    try:
-        rng = np.random.default_rng(sort_block)
-        for n, lens_set in ((70_001, [0, 1, 5, 8, 9, 20, 31, 32, 33, 40, 63, 64, 65, 100, 255]), (5_000, [0, 3, 8, 33, 64, 300]),
-                            (sort_block, [8, 16, 40]), (1, [12])):
-            for qlen in (32, 50):
-                q = (rng.integers(0, 5, qlen) + 97).astype(np.uint8)
-                chars, off = make_corpus(rng, n, lens_set, alphabet=5, query=q, near_frac=0.3)
-                corpus = rf.Corpus(chars, off)
-                cases = [(m, k, {}) for m in ("levenshtein", "osa", "indel", "lcs_seq") for k in ("distance", "similarity", "normalized_distance", "normalized_similarity")]
-                cases += [("levenshtein", "distance", {"cutoff": 7}), ("indel", "similarity", {"cutoff": 20}), ("ratio", "similarity", {"cutoff": 0.5}),
-                          ("osa", "normalized_similarity", {"cutoff": 0.4}), ("levenshtein", "distance", {"weights": (1, 1, 2)}),
-                          ("jaro_winkler", "similarity", {}), ("hamming", "distance", {"pad": True})]
-                for metric, kind, kw in cases:
-                    exp = orc.batch(metric, kind, q, chars, off, nthreads=0, **kw)
-                    for path in (0, 3):
-                        b = _bc(metric, q)
-                        _ffi.check(L.rf_batch_set_option(b._h, b"single_word_path", path))
-                        a = Args()
-                        if "cutoff" in kw:
-                            a = a.score_cutoff(kw["cutoff"])
-                        if "weights" in kw:
-                            a = a.weights(*kw["weights"])
-                        if "pad" in kw:
-                            a = a.pad(True)
-                        r = b._score(kind, corpus, a)
-                        if isinstance(r, np.ma.MaskedArray):
-                            r = r.filled(np.nan if r.dtype == np.float64 else _ffi.NONE_U32)
-                        assert_same(r, exp, (metric, kind, kw, "path %d" % path, n, qlen, sort_block))
-                        b.close()
-                corpus.close()
-        # multi-word (register-column kernel) and many-vs-many over the same layout
-        q3 = synth.synth_query(3, 200)
-        c3, o3 = synth.synth_corpus(3, q3, 20_000, 64, 256, 48)
-        corpus3 = rf.Corpus(c3, o3)
-        assert_same(gpu_batch("levenshtein", "distance", q3, corpus3), orc.batch("levenshtein", "distance", q3, c3, o3, nthreads=0), "lbn on small sort blocks")
-        corpus3.close()
-    finally:
-        _ffi.check(L.rf_set_option(b"layout_sort_block", 65536))
-
-
 def test_options_are_per_comparator():
     """The kernel-choice knobs are copied into a comparator at creation (rf_batch_set_option changes one comparator):
     two comparators with different settings give the same results side by side, and flipping the process-wide default

@@ -119,5 +119,6 @@ sb.score_allgather("distance", sc, [x.data_ptr() for x in bufs])
 sharding.sharded_cdist_topk(q, np.array([0, 32], np.uint64), sc, k=5)
 sb.stream("distance", chars, offsets)
 sb.close(); sc.close()
+exec(open(os.path.join(ROOT, "tools", "sanitize_smoke_late_r2.py")).read())   # the kernels added at the end of round 2
 corpus.close(); corpus3.close()
 print("sanitize smoke done")

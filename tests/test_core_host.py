@@ -237,3 +237,20 @@ def test_damerau_zhao_vs_oracle(core):
     for a, b in _pairs(rng, 3000, [0] + QL, CL, 3):
         got = core.core_dl(a.ctypes.data, len(a), b.ctypes.data, len(b))
         assert got == orc.pair("damerau_levenshtein", "distance", a, b), (bytes(a), bytes(b), got)
+
+
+def test_jaro_epilogue_table_dimensions_cover_every_reachable_pair():
+    """The row-wise Jaro kernels look their f64 result up at [original candidate length][common characters]
+    [transpositions / 2][prefix] (rf_kernels.cu jaro_epi_table).  They score a pair only when the TRUNCATED candidate
+    length (jaro.rs:553-565) is at most 64, so the table's first dimension must cover every ORIGINAL length that can reach
+    them: max(64, 131 - 2 * len1).  Exhaustive check of that bound against a restatement of jaro_bounds."""
+    def truncated_len2(len1, len2):
+        if len2 > len1:
+            bound = len2 // 2 - 1
+            return min(len2, len1 + bound)
+        return len2
+    for len1 in range(1, 65):
+        l2max = 131 - 2 * len1 if 131 - 2 * len1 > 64 else 64
+        reach = [len2 for len2 in range(0, 400) if truncated_len2(len1, len2) <= 64]
+        assert max(reach) == l2max, (len1, max(reach), l2max)
+        assert reach == list(range(0, l2max + 1)), len1      # contiguous: nothing beyond the bound comes back under 64

@@ -123,6 +123,16 @@ rf_status rf_corpus_create_elems(const void* elems, rf_elem_type type, const uin
                                  rf_corpus** out);
 /* Waits for the device to drain first (asynchronous *_device calls may still be reading the corpus). */
 rf_status rf_corpus_destroy(rf_corpus* c);
+/* A corpus holds its candidates twice: as the CSR copy it was given and as the length-bucketed interleaved layout the
+ * single-word kernels read, about 2.2x the candidates' bytes in all.  rf_corpus_release_csr frees the
+ * CSR copy (45 % of the footprint) for hosts that only need what the layout serves: Levenshtein / OSA / Indel / LCSseq /
+ * ratio with queries of at most 512 elements, Jaro / Jaro-Winkler up to 64, Hamming, Damerau-Levenshtein and generic weights
+ * up to 64 (candidates up to 32 000 elements), extract / filter on those, and rf_cdist_topk_*.  Everything else (longer
+ * queries, Prefix / Postfix, u32 queries that need a renaming pass, the small-cutoff band kernel -- such calls take the
+ * register-column kernel instead, same results) returns RF_ERR_UNSUPPORTED afterwards.  Not reversible; waits for the device
+ * to drain; must not run concurrently with calls on the same corpus. */
+rf_status rf_corpus_release_csr(rf_corpus* c);
+int rf_corpus_has_csr(const rf_corpus* c); /* 0 after rf_corpus_release_csr */
 uint64_t rf_corpus_size(const rf_corpus* c);        /* number of candidates */
 uint64_t rf_corpus_total_chars(const rf_corpus* c); /* sum of candidate lengths */
 int rf_corpus_device(const rf_corpus* c);
@@ -165,6 +175,14 @@ rf_status rf_batch_score_u32_device(const rf_batch* b, const rf_corpus* c, rf_ki
                                     uint32_t* out_device, void* stream);
 rf_status rf_batch_score_f64_device(const rf_batch* b, const rf_corpus* c, rf_kind kind, const rf_args* args,
                                     double* out_device, void* stream);
+/* Integer-valued results as BYTES (None = 0xFF): a quarter of the result bytes to download, for corpora and queries whose
+ * scores stay below 255 (the result download of rf_batch_score_u32 on BASELINE config 2 takes 3.5x as long as the scan).
+ * A score above 254 does not fit: such entries read 0xFF and the host-output call returns RF_ERR_INVALID_ARG after filling
+ * the output (the *_device call, which does not synchronise, only writes 0xFF).  Float-valued (metric, kind) pairs ->
+ * RF_ERR_INVALID_ARG. */
+rf_status rf_batch_score_u8(const rf_batch* b, const rf_corpus* c, rf_kind kind, const rf_args* args, uint8_t* out_host);
+rf_status rf_batch_score_u8_device(const rf_batch* b, const rf_corpus* c, rf_kind kind, const rf_args* args,
+                                   uint8_t* out_device, void* stream);
 /* 1 if (metric, kind) yields f64, 0 if u32 */
 int rf_result_is_float(rf_metric metric, rf_kind kind);
 

@@ -99,6 +99,9 @@ class Corpus {
   Corpus& operator=(const Corpus&) = delete;
   ~Corpus() { rf_corpus_destroy(h_); }
   uint64_t size() const { return rf_corpus_size(h_); }
+  // frees the CSR copy (45 % of the footprint): afterwards only what the interleaved layout serves works (see rfgpu.h)
+  void release_csr() { check(rf_corpus_release_csr(h_)); }
+  bool has_csr() const { return rf_corpus_has_csr(h_) != 0; }
   const rf_corpus* handle() const { return h_; }
 
  private:
@@ -219,6 +222,14 @@ struct MetricModule {
     template <class C> auto similarity_with_args(const Corpus& c, const Args<IntT, C>& a) const { return wrap<IntT, C>(score<IntT>(c, RF_SIMILARITY, a)); }
     template <class C> auto normalized_distance_with_args(const Corpus& c, const Args<double, C>& a) const { return wrap<double, C>(score<double>(c, RF_NORMALIZED_DISTANCE, a)); }
     template <class C> auto normalized_similarity_with_args(const Corpus& c, const Args<double, C>& a) const { return wrap<double, C>(score<double>(c, RF_NORMALIZED_SIMILARITY, a)); }
+    // integer scores as bytes (None = 0xFF): a quarter of the result download; throws when a score exceeds 254
+    template <class C>
+    std::vector<uint8_t> score_u8(const Corpus& c, rf_kind kind, const Args<IntT, C>& a) const {
+      std::vector<uint8_t> out(c.size());
+      const rf_args ca = detail::to_c(a);
+      check(rf_batch_score_u8(h_, c.handle(), kind, &ca, out.data()));
+      return out;
+    }
     // new on this side: the k best candidates by (score best-first, index), selected on the GPU; every candidate
     // within the score_cutoff in index order; one-shot scoring of host-resident candidates (chunked PCIe pipeline).
     // T = IntT for RF_DISTANCE / RF_SIMILARITY of the edit-distance metrics, double otherwise.

@@ -427,6 +427,26 @@ rf_status rf_corpus_destroy(rf_corpus* c) {
   delete c;
   return RF_OK;
 }
+// Frees the CSR copy (characters + starts) of a byte corpus that also holds the interleaved layout: 3.6 + 0.4 of the 8.8 GB
+// BASELINE config 2 occupies.  Everything the interleaved layout serves keeps working (see rfgpu.h); the rest is refused.
+rf_status rf_corpus_release_csr(rf_corpus* c) {
+  if (!c) return fail(RF_ERR_INVALID_ARG, "NULL handle");
+  if (c->d_elems32) return fail(RF_ERR_UNSUPPORTED, "a u32 corpus with more than 255 distinct symbols has no interleaved layout to fall back on");
+  if (c->n && !c->lb.gdata) return fail(RF_ERR_UNSUPPORTED, "the corpus was created without the interleaved layout (build_interleaved_layout = 0)");
+  DeviceGuard g(c->device);
+  if (!g.ok) return fail(RF_ERR_CUDA, "cudaSetDevice failed");
+  cudaDeviceSynchronize();  // asynchronous *_device scans may still read the copy (as in rf_corpus_destroy)
+  cudaStream_t st = util_stream(c->device);
+  dev_free(c->d_chars, st);
+  dev_free(c->d_off32, st);
+  dev_free(c->d_off64, st);
+  c->d_chars = nullptr;
+  c->d_off32 = nullptr;
+  c->d_off64 = nullptr;
+  c->csr_released = true;
+  return RF_OK;
+}
+int rf_corpus_has_csr(const rf_corpus* c) { return c && !c->csr_released ? 1 : 0; }
 uint64_t rf_corpus_size(const rf_corpus* c) { return c ? c->n : 0; }
 uint64_t rf_corpus_total_chars(const rf_corpus* c) { return c ? c->total : 0; }
 int rf_corpus_device(const rf_corpus* c) { return c ? c->device : -1; }
@@ -763,8 +783,17 @@ static rf_status score_view(const rf_batch* b, const CorpusView& cv_in, const Lb
   L.corpus = cv;
   const Family fam0 = family_of(L.epi.metric, L.epi.wclass);
   const rf_batch_opts opt = b->opt;  // per-comparator snapshot of the kernel-choice knobs
-  const bool use_lb = lb && lb->gdata && opt.w1_path != 1 && (fam0 != F_SIMPLE || L.epi.metric == M_HAMMING) &&
+  // rf_corpus_release_csr: only what the interleaved layout serves is left (single_word_path = 1, the CSR kernel, is ignored)
+  const bool have_csr = cv.off32 != nullptr || cv.off64 != nullptr;
+  const bool use_lb = lb && lb->gdata && (opt.w1_path != 1 || !have_csr) && (fam0 != F_SIMPLE || L.epi.metric == M_HAMMING) &&
                       ((fam0 != F_DL && fam0 != F_WF) || b->len1 <= 64);  // the two DP kernels: shared-memory rows up to 64
+  if (!have_csr) {
+    const char* why = nullptr;
+    if (!use_lb) why = "this metric / query length is served by the CSR copy, which rf_corpus_release_csr freed";
+    else if ((fam0 == F_DL || fam0 == F_WF) && cv.max_len > 32000) why = "candidates beyond 32 000 elements take the CSR kernel, and rf_corpus_release_csr freed that copy";
+    else if (b->len1 > 64 && (fam0 == F_JARO || !b->view.limbs)) why = "queries beyond 512 elements (Jaro: beyond 64) are served by the CSR copy, which rf_corpus_release_csr freed";
+    if (why) return fail(RF_ERR_UNSUPPORTED, why);
+  }
   if (ranged) {
     const bool dp = fam0 == F_DL || fam0 == F_WF || fam0 == F_SIMPLE;
     if (use_lb && dp) return fail(RF_ERR_UNSUPPORTED, "candidate sub-ranges are not available for this metric on the interleaved layout");
@@ -810,9 +839,9 @@ static rf_status score_view(const rf_batch* b, const CorpusView& cv_in, const Lb
     e = !use_lb ? launch_scan_w1(L) : path == 2 ? launch_scan_lbr(L) : launch_scan_lb(L);
   }
   else if (fam == F_JARO) e = launch_jaro_mw(L);
-  else if (use_lb && L.query.limbs && opt.mw_path == 0 &&
+  else if (use_lb && L.query.limbs && (!have_csr || (opt.mw_path == 0 &&
            !(opt.band && L.epi.metric == M_LEVENSHTEIN && L.epi.wclass == WC_UNIFORM && L.epi.kind == K_DISTANCE &&
-             L.epi.has_cutoff && L.epi.cutoff_u / L.epi.w_ins <= 63))
+             L.epi.has_cutoff && L.epi.cutoff_u / L.epi.w_ins <= 63))))
     e = launch_scan_lbn(L);  // 65..512 elements on a resident corpus: thread per candidate, column in registers
   else if (opt.band && L.epi.metric == M_LEVENSHTEIN && L.epi.wclass == WC_UNIFORM && L.epi.kind == K_DISTANCE &&
            L.epi.has_cutoff && L.epi.cutoff_u / L.epi.w_ins <= 63)
@@ -1141,6 +1170,7 @@ static rf_status score_device(const rf_batch* b, const rf_corpus* c, rf_kind kin
   if (b->wide) {
     if (b->alpha_overflow)
       return fail(RF_ERR_UNSUPPORTED, "this metric compares symbols directly: u32 queries with more than 255 distinct symbols are not supported for it");
+    if (c->csr_released) return fail(RF_ERR_UNSUPPORTED, "renaming the candidates for this u32 query needs the CSR copy, which rf_corpus_release_csr freed");
     if (b->device != c->device) return fail(RF_ERR_INVALID_ARG, "batch and corpus live on different devices");
     if (c->n == 0) return RF_OK;
     DeviceGuard g(c->device);
@@ -1838,6 +1868,54 @@ rf_status rf_batch_stream_u8_len8_packed6(const rf_batch* b, const uint8_t* pack
                                           uint64_t n, rf_kind kind, const rf_args* args, uint8_t* out_host) {
   if (!dict64) return fail(RF_ERR_INVALID_ARG, "dict64 is NULL");
   return stream_len8_impl(b, packed, lens, n, kind, args, out_host, true, dict64);
+}
+
+// Resident corpus, integer results as BYTES (None = 0xFF): the scan writes its u32 scores into scratch, narrow_results_u8 packs
+// them, and a quarter of the bytes cross PCIe (config 2: the 0.4 GB result download of rf_batch_score_u32 takes 3.5x as long as
+// the scan itself).  A score above 254 -> RF_ERR_INVALID_ARG after the output is filled (such entries read 0xFF).
+static rf_status score_u8_impl(const rf_batch* b, const rf_corpus* c, rf_kind kind, const rf_args* args, uint8_t* out, bool out_on_device,
+                               cudaStream_t user_st) {
+  if (!b || !c) return fail(RF_ERR_INVALID_ARG, "NULL handle");
+  if ((int)kind < 0 || (int)kind > 3) return fail(RF_ERR_INVALID_ARG, "unknown kind");
+  if (rf_result_is_float(b->metric, kind)) return fail(RF_ERR_INVALID_ARG, "this (metric, kind) yields f64 results; byte results exist for integer scores only");
+  if (c->n == 0) return score_device(b, c, kind, args, nullptr, false, nullptr);
+  if (!out) return fail(RF_ERR_INVALID_ARG, "out is NULL");
+  DeviceGuard g(c->device);
+  if (!g.ok) return fail(RF_ERR_CUDA, "cudaSetDevice failed");
+  cudaStream_t st = user_st;
+  cudaError_t e = cudaSuccess;
+  if (!out_on_device && (e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
+  const size_t n4 = (size_t)c->n * 4, n1 = ((size_t)c->n + 3) / 4 * 4;
+  uint8_t* d_buf = nullptr;  // [u32 scores][16 B: hamming error flag, overflow flag][byte scores (host-output calls)]
+  e = dev_alloc(&d_buf, n4 + 16 + (out_on_device ? 0 : n1), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_buf + n4, 0, 16, st);
+  rf_status s = e == cudaSuccess ? RF_OK : cuda_fail(e, "result buffer");
+  uint32_t flags[2] = {0, 0};
+  if (s == RF_OK) s = score_device(b, c, kind, args, d_buf, false, st, (uint32_t*)(d_buf + n4));
+  if (s == RF_OK) {
+    uint8_t* d_out8 = out_on_device ? out : d_buf + n4 + 16;
+    const uint64_t blocks = (((uint64_t)c->n + 3) / 4 + 255) / 256;
+    narrow_results_u8<<<(uint32_t)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, st>>>((const uint32_t*)d_buf, c->n, d_out8, (uint32_t*)(d_buf + n4 + 4));
+    rfk::count_launches(1);
+    e = cudaGetLastError();
+    if (e == cudaSuccess && !out_on_device) e = cudaMemcpyAsync(out, d_out8, c->n, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && !out_on_device) {
+      e = cudaMemcpyAsync(flags, d_buf + n4, 8, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    if (e != cudaSuccess) s = cuda_fail(e, "byte results");
+    else if (flags[0]) s = fail(RF_ERR_INVALID_ARG, "Differing length arguments provided");
+    else if (flags[1]) s = fail(RF_ERR_INVALID_ARG, "a score above 254 does not fit the u8 result; use rf_batch_score_u32");
+  }
+  dev_free(d_buf, st);
+  if (!out_on_device) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+  return s;
+}
+rf_status rf_batch_score_u8(const rf_batch* b, const rf_corpus* c, rf_kind kind, const rf_args* args, uint8_t* out) {
+  return score_u8_impl(b, c, kind, args, out, false, nullptr);
+}
+rf_status rf_batch_score_u8_device(const rf_batch* b, const rf_corpus* c, rf_kind kind, const rf_args* args, uint8_t* out, void* stream) {
+  return score_u8_impl(b, c, kind, args, out, true, (cudaStream_t)stream);
 }
 }  // extern "C"
 

@@ -12,6 +12,7 @@ struct rf_corpus {
   int device = 0;
   uint64_t n = 0, total = 0, max_len = 0;  // max_len: longest candidate (elements)
   bool has_negative = false, has_huge = false;  // rf_corpus_create_elems: a negative signed value / an unsigned value >= 2^31 was seen
+  bool csr_released = false;      // rf_corpus_release_csr: d_chars / d_off* are gone, only the interleaved layout is left
   uint8_t* d_chars = nullptr;     // u8 elements ...
   uint32_t* d_elems32 = nullptr;  // ... or u32 elements (rf_corpus_create_u32); exactly one of the two is set
   uint32_t* d_off32 = nullptr;

@@ -45,6 +45,8 @@ SYMBOLS = {
     "rf_corpus_create_u32": (_int, [_vp, _vp, _u64, _int, C.POINTER(_vp)]),
     "rf_corpus_create_elems": (_int, [_vp, _int, _vp, _u64, _int, C.POINTER(_vp)]),
     "rf_corpus_destroy": (_int, [_vp]),
+    "rf_corpus_release_csr": (_int, [_vp]),
+    "rf_corpus_has_csr": (_int, [_vp]),
     "rf_corpus_size": (_u64, [_vp]),
     "rf_corpus_total_chars": (_u64, [_vp]),
     "rf_corpus_device": (_int, [_vp]),
@@ -54,6 +56,8 @@ SYMBOLS = {
     "rf_batch_destroy": (_int, [_vp]),
     "rf_batch_set_option": (_int, [_vp, C.c_char_p, _int]),
     "rf_batch_score_u32": (_int, [_vp, _vp, _int, _PA, _vp]),
+    "rf_batch_score_u8": (_int, [_vp, _vp, _int, _PA, _vp]),
+    "rf_batch_score_u8_device": (_int, [_vp, _vp, _int, _PA, _vp, _vp]),
     "rf_batch_score_f64": (_int, [_vp, _vp, _int, _PA, _vp]),
     "rf_batch_score_u32_device": (_int, [_vp, _vp, _int, _PA, _vp, _vp]),
     "rf_batch_score_f64_device": (_int, [_vp, _vp, _int, _PA, _vp, _vp]),

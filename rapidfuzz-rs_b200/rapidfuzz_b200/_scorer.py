@@ -285,6 +285,14 @@ class BatchComparatorBase:
         _ffi.check(fn(self._h, chars.ctypes.data, lens.ctypes.data, n, _ffi.KINDS[kind], C.byref(ca), out.ctypes.data))
         return out
 
+    def score_u8(self, kind, corpus, args=None):
+        """rf_batch_score_u8: integer scores of a resident corpus as bytes (0xFF = None); raises when a score exceeds 254."""
+        args = args if args is not None else Args()
+        ca = args._c(False)
+        out = np.empty(len(corpus), dtype=np.uint8)
+        _ffi.check(_ffi.lib().rf_batch_score_u8(self._h, corpus._h, _ffi.KINDS[kind], C.byref(ca), out.ctypes.data))
+        return out
+
     def score_into(self, kind, corpus, out_ptr, args=None, stream=0):
         """Device-pointer variant (rf_batch_score_*_device): results stay on the GPU at `out_ptr`
         (u32[n] or f64[n]); enqueued on `stream` (a cudaStream_t as int), no synchronisation."""

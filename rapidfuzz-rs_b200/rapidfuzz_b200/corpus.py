@@ -112,6 +112,14 @@ class Corpus:
     def total_chars(self):
         return int(_ffi.lib().rf_corpus_total_chars(self._h))
 
+    def release_csr(self):
+        """rf_corpus_release_csr: frees the CSR copy (45 % of the footprint); only what the interleaved layout serves works afterwards."""
+        _ffi.check(_ffi.lib().rf_corpus_release_csr(self._h))
+
+    @property
+    def has_csr(self):
+        return bool(_ffi.lib().rf_corpus_has_csr(self._h))
+
     def close(self):
         if getattr(self, "_h", None):
             _ffi.lib().rf_corpus_destroy(self._h)

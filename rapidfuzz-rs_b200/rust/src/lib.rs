@@ -67,10 +67,13 @@ extern "C" {
     pub fn rf_corpus_create_u32(elems: *const u32, offsets: *const u64, n: u64, device: c_int, out: *mut *mut rf_corpus) -> c_int;
     pub fn rf_batch_create_u32(metric: c_int, query: *const u32, len: u32, device: c_int, out: *mut *mut rf_batch) -> c_int;
     pub fn rf_corpus_destroy(c: *mut rf_corpus) -> c_int;
+    pub fn rf_corpus_release_csr(c: *mut rf_corpus) -> c_int;
+    pub fn rf_corpus_has_csr(c: *const rf_corpus) -> c_int;
     pub fn rf_corpus_size(c: *const rf_corpus) -> u64;
     pub fn rf_batch_create_u8(metric: c_int, query: *const u8, len: u32, device: c_int, out: *mut *mut rf_batch) -> c_int;
     pub fn rf_batch_destroy(b: *mut rf_batch) -> c_int;
     pub fn rf_batch_score_u32(b: *const rf_batch, c: *const rf_corpus, kind: c_int, args: *const rf_args, out: *mut u32) -> c_int;
+    pub fn rf_batch_score_u8(b: *const rf_batch, c: *const rf_corpus, kind: c_int, args: *const rf_args, out: *mut u8) -> c_int;
     pub fn rf_batch_score_f64(b: *const rf_batch, c: *const rf_corpus, kind: c_int, args: *const rf_args, out: *mut f64) -> c_int;
     pub fn rf_cdist_topk_u8(q_chars: *const u8, q_offsets: *const u64, nq: u32, c: *const rf_corpus, args: *const rf_args,
                             k: u32, idx: *mut u32, dist: *mut u32) -> c_int;
@@ -174,6 +177,9 @@ impl Corpus {
         Corpus { h }
     }
     pub fn len(&self) -> usize { unsafe { rf_corpus_size(self.h) as usize } }
+    /// frees the CSR copy (45 % of the footprint); afterwards only what the interleaved layout serves works (see rfgpu.h)
+    pub fn release_csr(&mut self) { check(unsafe { rf_corpus_release_csr(self.h) }); }
+    pub fn has_csr(&self) -> bool { unsafe { rf_corpus_has_csr(self.h) != 0 } }
 }
 impl Drop for Corpus { fn drop(&mut self) { unsafe { rf_corpus_destroy(self.h); } } }
 
@@ -326,6 +332,12 @@ macro_rules! metric_module {
                 fn run_u32(&self, c: &Corpus, kind: c_int, a: &rf_args) -> Vec<u32> {
                     let mut out = vec![0u32; c.len()];
                     check(unsafe { rf_batch_score_u32(self.h, c.h, kind, a, out.as_mut_ptr()) });
+                    out
+                }
+                /// integer scores as bytes (`None` = 0xFF): a quarter of the result download of `run_u32`
+                pub fn run_u8(&self, c: &Corpus, kind: c_int, a: &rf_args) -> Vec<u8> {
+                    let mut out = vec![0u8; c.len()];
+                    check(unsafe { rf_batch_score_u8(self.h, c.h, kind, a, out.as_mut_ptr()) });
                     out
                 }
                 fn run_f64(&self, c: &Corpus, kind: c_int, a: &rf_args) -> Vec<f64> {

@@ -540,6 +540,115 @@ def test_integer_epilogue_table_equals_per_pair_epilogue_equals_oracle(qlen):
     corpus.close()
 
 
+def test_byte_results_on_a_resident_corpus():
+    """rf_batch_score_u8 / _device: the u32 scores narrowed on the device (None -> 0xFF), == rf_batch_score_u32 == oracle;
+    a score above 254 is refused loudly after the output is filled; float-valued kinds are refused."""
+    import torch
+    L = _ffi.lib()
+    q = synth.synth_query(5, 32)
+    chars, offsets = synth.synth_corpus(5, q, 40_003, 0, 64, 16)
+    corpus = rf.Corpus(chars, offsets)
+    for metric, kind, cut in (("levenshtein", "distance", None), ("levenshtein", "distance", 9), ("indel", "similarity", 30),
+                              ("osa", "distance", None), ("lcs_seq", "similarity", None), ("hamming", "distance", None)):
+        b = _bc(metric, q)
+        a = Args() if cut is None else Args().score_cutoff(cut)
+        if metric == "hamming":
+            a = a.pad(True)
+        kw = {} if cut is None else {"cutoff": cut}
+        if metric == "hamming":
+            kw["pad"] = True
+        exp = orc.batch(metric, kind, q, chars, offsets, nthreads=0, **kw)
+        exp8 = np.where(exp == 0xFFFFFFFF, 255, exp).astype(np.uint8)
+        assert exp[exp != 0xFFFFFFFF].max() <= 254
+        got = b.score_u8(kind, corpus, a)
+        assert np.array_equal(got, exp8), (metric, kind, cut)
+        out = torch.empty(len(corpus), dtype=torch.uint8, device="cuda")
+        ca = a._c(False)
+        _ffi.check(L.rf_batch_score_u8_device(b._h, corpus._h, _ffi.KINDS[kind], C.byref(ca), out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), exp8), (metric, kind, cut, "device")
+        b.close()
+    b = _bc("levenshtein", q)
+    with pytest.raises(rf.RfError):
+        b.score_u8("normalized_distance", corpus)
+    b.close()
+    corpus.close()
+    # one candidate of 300 elements: its distance does not fit a byte
+    lens = np.array([5, 300, 7])
+    ch = np.full(int(lens.sum()), 120, np.uint8)
+    off = np.zeros(4, np.uint64); off[1:] = np.cumsum(lens)
+    c2 = rf.Corpus(ch, off)
+    b = _bc("levenshtein", q)
+    with pytest.raises(rf.RfError, match="254"):
+        b.score_u8("distance", c2)
+    b.close(); c2.close()
+
+
+def test_corpus_without_its_csr_copy():
+    """rf_corpus_release_csr frees the CSR copy; everything the interleaved layout serves gives the same results as before
+    (incl. a small cutoff on a 200-element query, which then takes the register-column kernel instead of the band kernel),
+    the rest is refused loudly -- never a wrong answer or a fault."""
+    rng = np.random.default_rng(77)
+    q = (rng.integers(0, 5, 32) + 97).astype(np.uint8)
+    chars, off = make_corpus(rng, 9000, [0, 1, 8, 20, 33, 64, 70, 200, 260], alphabet=5, query=q)
+    corpus = rf.Corpus(chars, off)
+    assert corpus.has_csr
+    corpus.release_csr()
+    assert not corpus.has_csr
+    q200 = (rng.integers(0, 5, 200) + 97).astype(np.uint8)
+    q64 = (rng.integers(0, 5, 64) + 97).astype(np.uint8)
+    for metric, kind, qq, kw in (("levenshtein", "distance", q, {}), ("levenshtein", "normalized_similarity", q64, {"cutoff": 0.3}),
+                                 ("osa", "distance", q64, {}), ("indel", "similarity", q, {}), ("ratio", "similarity", q, {}),
+                                 ("jaro_winkler", "similarity", q, {}), ("jaro", "distance", q64, {"cutoff": 0.6}),
+                                 ("hamming", "distance", q, {"pad": True}), ("damerau_levenshtein", "distance", q, {}),
+                                 ("levenshtein", "distance", q, {"weights": (1, 2, 3)}),
+                                 ("levenshtein", "distance", q200, {}), ("levenshtein", "distance", q200, {"cutoff": 20}),
+                                 ("indel", "distance", q200, {"cutoff": 150})):
+        b = _bc(metric, qq)
+        a = Args()
+        if "cutoff" in kw:
+            a = a.score_cutoff(kw["cutoff"])
+        if "weights" in kw:
+            a = a.weights(*kw["weights"])
+        if "pad" in kw:
+            a = a.pad(True)
+        r = b._score(kind, corpus, a)
+        if isinstance(r, np.ma.MaskedArray):
+            r = r.filled(np.nan if r.dtype == np.float64 else _ffi.NONE_U32)
+        assert_same(r, orc.batch(metric, kind, qq, chars, off, nthreads=0, **kw), (metric, kind, len(qq), kw))
+        b.close()
+    b = _bc("levenshtein", q)
+    ti, ts = b.extract("distance", corpus, k=7)
+    exp = orc.batch("levenshtein", "distance", q, chars, off, nthreads=0)
+    order = np.lexsort((np.arange(len(exp)), exp))[:7]
+    assert np.array_equal(ti, order.astype(np.uint32)) and np.array_equal(ts, exp[order])
+    _ffi.check(_ffi.lib().rf_batch_set_option(b._h, b"single_word_path", 1))   # the CSR kernel is gone: the knob is ignored
+    assert np.array_equal(b.distance(corpus), exp)
+    b.close()
+    idx, dist = rf.cdist_topk([q, q64[:40]], corpus, k=5)
+    assert np.array_equal(idx[0], order[:5].astype(idx.dtype))
+    qlong = (rng.integers(0, 5, 600) + 97).astype(np.uint8)
+    for metric, qq in (("levenshtein", qlong), ("jaro", q200), ("prefix", q), ("postfix", q)):
+        b = _bc(metric, qq)
+        with pytest.raises(rf.RfError, match="release_csr"):
+            b._score("similarity" if metric in ("prefix", "postfix", "jaro") else "distance", corpus, None)
+        b.close()
+    # u32 query on the byte corpus: the table-driven metrics map the QUERY into the byte domain (no pass over the candidates)
+    # and keep working; the metrics that compare symbols directly would have to rename the candidates -> refused
+    qw = q.astype(np.uint32)
+    qw[::3] += 1000
+    full = rf.Corpus(chars, off)
+    b = _bc("levenshtein", qw)
+    assert np.array_equal(b._score("distance", corpus, None), b._score("distance", full, None))
+    b.close()
+    b = _bc("hamming", qw)
+    with pytest.raises(rf.RfError, match="release_csr"):
+        b._score("distance", corpus, Args().pad(True))
+    b.close()
+    full.close()
+    corpus.close()
+
+
 def test_options_are_per_comparator():
     """The kernel-choice knobs are copied into a comparator at creation (rf_batch_set_option changes one comparator):
     two comparators with different settings give the same results side by side, and flipping the process-wide default

@@ -1542,7 +1542,14 @@ __global__ void __launch_bounds__(256) narrow_results_u8(const uint32_t* __restr
       else if (v > 254u) { over = true; v = 0xFFu; }
       packed |= v << (8 * j);
     }
-    reinterpret_cast<uint32_t*>(out)[qd] = packed;
+    // whole, 4-byte aligned quads as one word; the last partial quad (and a misaligned caller buffer: rf_batch_score_u8_device)
+    // byte by byte, so nothing is written past out[n - 1]
+    if (qd * 4 + 4 <= n && (reinterpret_cast<uintptr_t>(out) & 3u) == 0) {
+      reinterpret_cast<uint32_t*>(out)[qd] = packed;
+    } else {
+      for (int j = 0; j < 4; ++j)
+        if (qd * 4 + j < n) out[qd * 4 + j] = (uint8_t)(packed >> (8 * j));
+    }
     if (over) atomicOr(overflow, 1u);
   }
 }

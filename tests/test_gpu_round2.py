@@ -562,11 +562,15 @@ def test_byte_results_on_a_resident_corpus():
         assert exp[exp != 0xFFFFFFFF].max() <= 254
         got = b.score_u8(kind, corpus, a)
         assert np.array_equal(got, exp8), (metric, kind, cut)
-        out = torch.empty(len(corpus), dtype=torch.uint8, device="cuda")
-        ca = a._c(False)
-        _ffi.check(L.rf_batch_score_u8_device(b._h, corpus._h, _ffi.KINDS[kind], C.byref(ca), out.data_ptr(), torch.cuda.current_stream().cuda_stream))
-        torch.cuda.synchronize()
-        assert np.array_equal(out.cpu().numpy(), exp8), (metric, kind, cut, "device")
+        for shift in (0, 1):       # a byte-aligned caller buffer too; the bytes around the result stay untouched
+            buf = torch.full((len(corpus) + 16,), 0xAB, dtype=torch.uint8, device="cuda")
+            out = buf[4 + shift: 4 + shift + len(corpus)]
+            ca = a._c(False)
+            _ffi.check(L.rf_batch_score_u8_device(b._h, corpus._h, _ffi.KINDS[kind], C.byref(ca), out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+            torch.cuda.synchronize()
+            h = buf.cpu().numpy()
+            assert np.array_equal(h[4 + shift: 4 + shift + len(corpus)], exp8), (metric, kind, cut, "device", shift)
+            assert np.all(h[: 4 + shift] == 0xAB) and np.all(h[4 + shift + len(corpus):] == 0xAB), "wrote outside the result"
         b.close()
     b = _bc("levenshtein", q)
     with pytest.raises(rf.RfError):

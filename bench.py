@@ -725,8 +725,9 @@ def main():
                     "resident_corpus_build_and_score_ms": resident_s * 1e3},
             "gpu_launches": launches,
             "roofline": roofline(alg_bytes, ms_per_step, "scan_lb_kernel<F_LEV,u32,256,RAWDIST>", traffic,
-                                 "ALU-pipe bound by design (7 LOP3 per candidate char on a 16-lane/clk pipe); traffic = ncu DRAM "
-                                 "bytes of one launch; see DESIGN.md section 5"),
+                                 "ALU-pipe bound by design (7 LOP3 per candidate char on a 16-lane/clk pipe): the inner step alone "
+                                 "runs at 18.4 SM clocks per warp-character (1.78 ms per 1e8 candidates, profiles/r2_step32_ubench.txt), "
+                                 "the kernel at 89 % of that; traffic = ncu DRAM bytes of one launch; see DESIGN.md section 5"),
             "configs": sub,
         }
         if not args.no_cpu_baseline:

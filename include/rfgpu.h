@@ -27,7 +27,7 @@ typedef enum rf_status {
   RF_OK = 0,
   RF_ERR_INVALID_ARG = 1,
   RF_ERR_UNSUPPORTED = 2, /* e.g. query longer than RF_MAX_QUERY_LEN; generic (non-uniform, non-indel) Levenshtein weights
-                             with a query longer than 2048; 64-bit element values that do not fit the 32-bit symbol domain */
+                             with a query longer than 200 000; 64-bit element values that do not fit the 32-bit symbol domain */
   RF_ERR_CUDA = 3,
   RF_ERR_OOM = 4,
   RF_ERR_NCCL = 5 /* a collective of the sharded (multi-GPU) entry points failed */
@@ -46,7 +46,7 @@ typedef enum rf_metric {
   RF_HAMMING = 7, /* hamming.rs:136-199; see rf_args.pad */
   RF_PREFIX = 8,  /* prefix.rs:47-71: similarity = common prefix length */
   RF_POSTFIX = 9, /* postfix.rs:47-71: similarity = common suffix length */
-  RF_DAMERAU_LEVENSHTEIN = 10 /* damerau_levenshtein.rs:111-214 (unrestricted; query <= 2048 elements) */
+  RF_DAMERAU_LEVENSHTEIN = 10 /* damerau_levenshtein.rs:111-214 (unrestricted; query <= 200 000 elements) */
 } rf_metric;
 
 /* which BatchComparator method: distance / similarity / normalized_distance / normalized_similarity */

@@ -828,10 +828,10 @@ static rf_status score_view(const rf_batch* b, const CorpusView& cv_in, const Lb
   cudaError_t e;
   if (fam == F_SIMPLE) e = launch_simple(L, d_err);
   else if (fam == F_WF) {
-    if (b->len1 > 2048) return fail(RF_ERR_UNSUPPORTED, "generic Levenshtein weights: queries longer than 2048 elements");
+    if (b->len1 > kDpMaxQuery) return fail(RF_ERR_UNSUPPORTED, "generic Levenshtein weights: queries longer than 200 000 elements");
     e = launch_wf(L);
   } else if (fam == F_DL) {
-    if (b->len1 > 2048) return fail(RF_ERR_UNSUPPORTED, "Damerau-Levenshtein: queries longer than 2048 elements");
+    if (b->len1 > kDpMaxQuery) return fail(RF_ERR_UNSUPPORTED, "Damerau-Levenshtein: queries longer than 200 000 elements");
     e = launch_dl(L);
   }
   else if (b->len1 <= 64) {

@@ -3680,8 +3680,19 @@ __global__ void __launch_bounds__(WF_NT) wf_lb_kernel(const __grid_constant__ Wf
   }
 }
 
+// Queries beyond 64 elements (thread per candidate, DP rows in global scratch): the grid shrinks with the query so that the
+// rows of all threads stay within kDpScratchBytes, the query bytes sit in (opt-in) shared memory up to kDpMaxQuery elements.
+constexpr uint64_t kDpScratchBytes = 1ull << 31;
+static uint64_t dp_blocks(uint64_t n, uint64_t bytes_per_thread, uint64_t max_blocks) {
+  uint64_t blocks = (n + 127) / 128;
+  if (blocks > max_blocks) blocks = max_blocks;
+  const uint64_t fit = kDpScratchBytes / (bytes_per_thread * 128);
+  if (blocks > fit) blocks = fit;
+  return blocks < 1 ? 1 : blocks;
+}
+
 cudaError_t launch_wf(const ScanLaunch& L) {
-  if (L.query.len1 > 2048) return cudaErrorNotSupported;
+  if (L.query.len1 > kDpMaxQuery) return cudaErrorNotSupported;
   if (L.lb.gdata != nullptr && L.query.len1 <= 64) {
     WfParams q{};
     q.qbytes = L.query.qbytes;
@@ -3715,12 +3726,12 @@ cudaError_t launch_wf(const ScanLaunch& L) {
   p.out = L.out;
   p.out_f64 = L.out_is_f64;
   p.epi = L.epi;
-  uint64_t blocks = (p.n + 127) / 128;
-  const uint64_t max_blocks = (uint64_t)L.sm_count * 4;
-  if (blocks > max_blocks) blocks = max_blocks;
-  if (blocks < 1) blocks = 1;
+  const uint64_t blocks = dp_blocks(p.n, (uint64_t)(p.len1 + 1) * sizeof(uint64_t), (uint64_t)L.sm_count * 4);
   p.T = (uint32_t)blocks * 128u;
-  cudaError_t e = dev_alloc(&p.scratch, (size_t)(p.len1 + 1) * p.T * sizeof(uint64_t), L.stream);
+  cudaError_t e = cudaSuccess;
+  if (p.len1 + 16 > 48 * 1024) e = cudaFuncSetAttribute(wf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(p.len1 + 16));
+  if (e != cudaSuccess) return e;
+  e = dev_alloc(&p.scratch, (size_t)(p.len1 + 1) * p.T * sizeof(uint64_t), L.stream);
   if (e != cudaSuccess) return e;
   wf_kernel<<<(uint32_t)blocks, 128, p.len1 + 16, L.stream>>>(p);
   g_launches.fetch_add(1);
@@ -3824,7 +3835,7 @@ __global__ void __launch_bounds__(DL_NT) dl_lb_kernel(const __grid_constant__ Dl
 }
 
 cudaError_t launch_dl(const ScanLaunch& L) {
-  if (L.query.len1 > 2048) return cudaErrorNotSupported;
+  if (L.query.len1 > kDpMaxQuery) return cudaErrorNotSupported;
   const bool use_lb = L.lb.gdata != nullptr && L.query.len1 <= 64 && L.lb_flag != nullptr;
   if (use_lb) {
     DlParams q{};
@@ -3864,13 +3875,14 @@ cudaError_t launch_dl(const ScanLaunch& L) {
   p.out = L.out;
   p.out_f64 = L.out_is_f64;
   p.epi = L.epi;
-  uint64_t blocks = (p.n + 127) / 128;
-  const uint64_t max_blocks = (uint64_t)L.sm_count * (p.only_long ? 1 : 4);  // the rare leftovers: a small grid (scratch!)
-  if (blocks > max_blocks) blocks = max_blocks;
-  if (blocks < 1) blocks = 1;
-  p.T = (uint32_t)blocks * 128u;
   const size_t entries = (size_t)3 * (p.len1 + 2) + 256;
-  cudaError_t e = dev_alloc(&p.scratch, entries * p.T * sizeof(int32_t), L.stream);
+  // (only_long: the rare leftovers of dl_lb_kernel -- a small grid)
+  const uint64_t blocks = dp_blocks(p.n, entries * sizeof(int32_t), (uint64_t)L.sm_count * (p.only_long ? 1 : 4));
+  p.T = (uint32_t)blocks * 128u;
+  cudaError_t e = cudaSuccess;
+  if (p.len1 + 16 > 48 * 1024) e = cudaFuncSetAttribute(dl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(p.len1 + 16));
+  if (e != cudaSuccess) return e;
+  e = dev_alloc(&p.scratch, entries * p.T * sizeof(int32_t), L.stream);
   if (e != cudaSuccess) return e;
   dl_init_kernel<<<(uint32_t)blocks, 256, 0, L.stream>>>(p.scratch + (size_t)3 * (p.len1 + 2) * p.T, (uint64_t)256 * p.T);
   dl_kernel<<<(uint32_t)blocks, 128, p.len1 + 16, L.stream>>>(p);

@@ -48,6 +48,9 @@ struct LbView {
   uint64_t ngroups;
 };
 constexpr uint32_t LB_BLOCK = 65536;
+// longest query of the O(len1 * len2) DP kernels (generic Levenshtein weights, Damerau-Levenshtein): their copy of the
+// query lives in shared memory
+constexpr uint32_t kDpMaxQuery = 200000;
 
 struct LbAlloc {  // owning pointers of an LbView
   uint32_t* perm = nullptr;

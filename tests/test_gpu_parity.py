@@ -547,8 +547,8 @@ def test_hamming_prefix_postfix_known_answers():
 def test_unsupported_is_loud():
     c = rf.Corpus.from_strings([b"abc"])
     assert rf.distance.levenshtein.BatchComparator(b"abcd").distance_with_args(c, rf.Args().weights(1, 2, 3)).tolist() == [2]
-    with pytest.raises(rf.RfError) as ei:   # generic weights (Wagner-Fischer) are limited to queries of 2048 elements
-        rf.distance.levenshtein.BatchComparator(np.full(2049, 97, np.uint8)).distance_with_args(c, rf.Args().weights(1, 2, 3))
+    with pytest.raises(rf.RfError) as ei:   # generic weights (Wagner-Fischer) are limited to queries of 200 000 elements
+        rf.distance.levenshtein.BatchComparator(np.full(200_001, 97, np.uint8)).distance_with_args(c, rf.Args().weights(1, 2, 3))
     assert ei.value.status == _ffi.RF_ERR_UNSUPPORTED
     with pytest.raises(rf.RfError):
         rf.distance.levenshtein.BatchComparator(np.zeros(_ffi.RF_MAX_QUERY_LEN + 1, np.uint8))

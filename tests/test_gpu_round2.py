@@ -653,6 +653,36 @@ def test_corpus_without_its_csr_copy():
     corpus.close()
 
 
+@pytest.mark.parametrize("qlen", [65, 2048, 2049, 5000, 70_000])
+def test_dp_metrics_with_long_queries(qlen):
+    """Generic Levenshtein weights (weighted_wagner_fischer, levenshtein.rs:212-259) and Damerau-Levenshtein
+    (damerau_levenshtein.rs:111-214) have no query-length limit in the reference.  Thread-per-candidate kernels with the DP
+    rows in global scratch: the grid shrinks with the query so the rows stay within 2 GB; queries beyond 48 K elements need
+    the opt-in shared-memory size for their copy of the query.  (Round 1 refused everything beyond 2048.)"""
+    rng = np.random.default_rng(qlen)
+    q = (rng.integers(0, 4, qlen) + 97).astype(np.uint8)
+    n = 20 if qlen > 10_000 else 300
+    lens = rng.choice([0, 1, 17, 64] if qlen > 10_000 else [0, 1, 17, 64, 200], n)   # (one thread walks len1 x len2 cells)
+    chars = (rng.integers(0, 4, int(lens.sum())) + 97).astype(np.uint8)
+    off = np.zeros(n + 1, np.uint64)
+    off[1:] = np.cumsum(lens)
+    corpus = rf.Corpus(chars, off)
+    for metric, kw in (("levenshtein", {"weights": (1, 2, 3)}), ("levenshtein", {"weights": (3, 1, 2), "cutoff": qlen}),
+                       ("damerau_levenshtein", {}), ("damerau_levenshtein", {"cutoff": qlen - 10})):
+        b = _bc(metric, q)
+        a = Args()
+        if "weights" in kw:
+            a = a.weights(*kw["weights"])
+        if "cutoff" in kw:
+            a = a.score_cutoff(kw["cutoff"])
+        r = b._score("distance", corpus, a)
+        if isinstance(r, np.ma.MaskedArray):
+            r = r.filled(_ffi.NONE_U32)
+        assert_same(r, orc.batch(metric, "distance", q, chars, off, nthreads=0, **kw), (metric, kw, qlen))
+        b.close()
+    corpus.close()
+
+
 def test_options_are_per_comparator():
     """The kernel-choice knobs are copied into a comparator at creation (rf_batch_set_option changes one comparator):
     two comparators with different settings give the same results side by side, and flipping the process-wide default

@@ -73,3 +73,17 @@ def test_synth_is_deterministic_and_shaped():
     assert set(np.unique(c1).tolist()) <= alnum
     c3, _ = synth.synth_corpus(3, q, 20000, 8, 64, 16)
     assert not np.array_equal(c1[:1000], c3[:1000])
+
+
+def test_late_round2_entry_points_validate_arguments_without_a_device():
+    """rf_batch_score_u8[_device], rf_corpus_release_csr, rf_corpus_has_csr: NULL handles are refused with
+    RF_ERR_INVALID_ARG before anything touches a device (so this runs on the CPU-only build box too)."""
+    L = _ffi.lib()
+    out = np.zeros(4, np.uint8)
+    assert L.rf_batch_score_u8(None, None, 0, None, out.ctypes.data) == _ffi.RF_ERR_INVALID_ARG
+    assert L.rf_batch_score_u8_device(None, None, 0, None, out.ctypes.data, None) == _ffi.RF_ERR_INVALID_ARG
+    assert L.rf_corpus_release_csr(None) == _ffi.RF_ERR_INVALID_ARG
+    assert L.rf_corpus_has_csr(None) == 0
+    assert L.rf_set_option(b"epilogue_table", 0) == _ffi.RF_OK and L.rf_set_option(b"epilogue_table", 1) == _ffi.RF_OK
+    assert L.rf_set_option(b"jaro32", 2) == _ffi.RF_OK and L.rf_set_option(b"jaro32", 1) == _ffi.RF_OK
+    assert L.rf_set_option(b"no_such_option", 1) == _ffi.RF_ERR_INVALID_ARG

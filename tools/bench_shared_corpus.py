@@ -68,7 +68,7 @@ def timed(fn, steps, warmup=3):
 
 def main():
     which = sys.argv[1].split(",") if len(sys.argv) > 1 else list(CASES)
-    for kv in os.environ.get("RF_OPTS", "").split(","):   # process-wide knobs set BEFORE the corpus is created, e.g. layout_sort_block=2048
+    for kv in os.environ.get("RF_OPTS", "").split(","):   # process-wide knobs set BEFORE the corpus is created, e.g. build_interleaved_layout=0
         if kv:
             _ffi.check(L.rf_set_option(kv.split("=")[0].encode(), int(kv.split("=")[1])))
     n = int(1e8 * scale)
